@@ -1,0 +1,373 @@
+// avd_env.cu -- batched vehicle-platoon environment for sm_100a.
+//
+// One thread owns one platoon and walks its followers in index order, exactly like Platoon.step's
+// loop (/root/reference/src/environment.py:224-232), so the follower-order semantics (Model B
+// exogenous input = predecessor's action of this step, Model A = predecessor's post-update
+// acceleration, reset chaining of a_lead) need no inter-thread communication.  All arrays are
+// struct-of-arrays with the platoon index fastest, so every load/store of a warp is one fully
+// coalesced 128-byte line; a thread issues 6..9 independent loads per follower before its first
+// dependent use (memory-level parallelism for an HBM-bound kernel: ~60 flop vs >=48 B per vehicle-step).
+//
+// Fused into the step when the corresponding pointers are given: OU exploration noise + action clip
+// (src/noise.py:14-23, agent/ddpgagent.py:18-29), the leader's exogenous draw (workers/trainer.py:
+// 292-295), ReplayBuffer.add for every agent (src/replaybuffer.py:37-47), episodic reward accumulation
+// (workers/trainer.py:321), per-step reward/done statistics (block reduction + one atomic per CTA) and
+// per-platoon auto-reset (src/environment.py:284-301, 520-559).
+#include "avd_common.cuh"
+#include "avd_rng.cuh"
+
+namespace avd {
+
+// ------------------------------------------------------------------------------------------------
+// reset of one platoon (thread-local): Platoon.reset + Vehicle.reset
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void reset_one_platoon(const avd_env_params& prm, const avd_env_io& io, int64_t p,
+                                                  uint32_t ep_tick, float* __restrict__ x_dst) {
+    const int M = prm.M;
+    const int64_t P = io.P;
+    const uint64_t gp = (uint64_t)(io.platoon_id_base + p);
+    const bool uni = prm.rand_uniform != 0;
+    const uint4 wp = rng_words(io.seed, gp, ep_tick, AVD_RNG_RESET_PLATOON);
+    float fa, fu;
+    if (uni) {
+        fa = uniform_sym(wp.x, prm.reset_leader_a);
+        fu = uniform_sym(wp.y, prm.reset_u);
+    } else {
+        float z0, z1;
+        normal_pair(wp.x, wp.y, z0, z1);
+        fa = __fmul_rn(z0, prm.reset_leader_a);
+        fu = __fmul_rn(z1, prm.reset_u);
+    }
+    if (io.front_accel) io.front_accel[p] = fa;
+    if (io.front_u) io.front_u[p] = fu;
+    float a_lead = fa;
+    for (int m = 0; m < M; ++m) {
+        float e0, e1, a;
+        if (prm.reset_mode == 0) {
+            const uint4 wv = rng_words(io.seed, gp * (uint64_t)M + (uint64_t)m, ep_tick, AVD_RNG_RESET_VEHICLE);
+            if (uni) {
+                e0 = uniform_sym(wv.x, prm.reset_ep);
+                e1 = uniform_sym(wv.y, prm.reset_ev);
+                a = uniform_sym(wv.z, prm.reset_a);
+            } else {
+                float z0, z1, z2, z3;
+                normal_pair(wv.x, wv.y, z0, z1);
+                normal_pair(wv.z, wv.w, z2, z3);
+                e0 = __fmul_rn(z0, prm.reset_ep);
+                e1 = __fmul_rn(z1, prm.reset_ev);
+                a = __fmul_rn(z2, prm.reset_a);
+            }
+        } else {  // fixed maxima / evaluator states (environment.py:534-544, 551-555)
+            e0 = prm.reset_ep;
+            e1 = prm.reset_ev;
+            a = prm.reset_a;
+        }
+        const int64_t v = (int64_t)m * P + p;
+        x_dst[(0 * (int64_t)M) * P + v] = e0;
+        x_dst[(1 * (int64_t)M) * P + v] = e1;
+        x_dst[(2 * (int64_t)M) * P + v] = a;
+        x_dst[(3 * (int64_t)M) * P + v] = a_lead;  // leader accel (m=0) or predecessor's fresh x[2]
+        io.prev_a[v] = a;                          // prev_x = x (environment.py:557)
+        if (io.cum_accel) io.cum_accel[v] = 0.0f;
+        a_lead = a;
+    }
+    if (io.step_in_episode) io.step_in_episode[p] = 0;
+}
+
+__global__ void __launch_bounds__(256) env_reset_kernel(const __grid_constant__ avd_env_params prm,
+                                                        const __grid_constant__ avd_env_io io,
+                                                        const uint8_t* __restrict__ mask) {
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < io.P; p += (int64_t)gridDim.x * blockDim.x) {
+        if (mask && !mask[p]) continue;
+        const uint32_t ep = io.episode ? (uint32_t)io.episode[p] : 0u;
+        reset_one_platoon(prm, io, p, ep, io.x_out);
+        if (io.episode) io.episode[p] = (int32_t)(ep + 1u);
+        if (io.ep_reward)
+            for (int m = 0; m < prm.M; ++m) io.ep_reward[(int64_t)m * io.P + p] = 0.0f;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// step
+// ------------------------------------------------------------------------------------------------
+#ifndef AVD_ENV_MIN_CTAS
+#define AVD_ENV_MIN_CTAS 3   // 80 registers/thread, no spills: 768 threads/SM x ~7 loads in flight per follower
+#endif
+
+template <int MT>
+__global__ void __launch_bounds__(256, AVD_ENV_MIN_CTAS) env_step_kernel(const __grid_constant__ avd_env_params prm,
+                                                       const __grid_constant__ avd_env_io io) {
+    const int M = MT ? MT : prm.M;
+    const int64_t P = io.P;
+    const int64_t plane = (int64_t)M * P;  // one state component of all vehicles
+    const uint64_t tick64 = io.clock ? io.clock->step_tick : 0ull;
+    const uint32_t tick = (uint32_t)tick64;
+    const uint64_t ring_count = io.clock ? io.clock->ring_count : 0ull;
+    const int64_t slot = io.ring ? (int64_t)(ring_count % (uint64_t)io.ring_capacity) : 0;
+    const bool uni = prm.rand_uniform != 0;
+    const float inv_max_ep = 1.0f / prm.max_ep, inv_max_ev = 1.0f / prm.max_ev;
+    const float inv_ahigh = 1.0f / fabsf(prm.action_high), inv_2maxa = 1.0f / (2.0f * prm.action_high);
+    const float inv_T = 1.0f / prm.T;
+    const float ou_c = __fmul_rn(prm.ou_sigma, __fsqrt_rn(prm.ou_dt));
+
+    float stat_r[MT ? MT : AVD_MAX_FOLLOWERS];
+#pragma unroll
+    for (int m = 0; m < (MT ? MT : AVD_MAX_FOLLOWERS); ++m) stat_r[m] = 0.0f;
+    float stat_done = 0.0f;
+
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t gp = (uint64_t)(io.platoon_id_base + p);
+        // exogenous input of follower 0 (environment.py:258-259 / 264-265, trainer.py:292-295)
+        float w;
+        if (io.leader_exog) {
+            w = io.leader_exog[p];
+        } else if (io.gen_exog) {
+            const uint4 wx = rng_words(io.seed, gp, tick, AVD_RNG_LEADER_EXOG);
+            w = draw_first(wx.x, wx.y, prm.reset_u, uni);
+        } else {
+            w = prm.model_a ? io.front_accel[p] : io.front_u[p];
+        }
+        bool any_term = false;
+        float rew_sum = 0.0f;
+#pragma unroll
+        for (int m = 0; m < M; ++m) {
+            const int64_t v = (int64_t)m * P + p;
+            const float x0 = io.x_in[v], x1 = io.x_in[plane + v], x2 = io.x_in[2 * plane + v], x3 = io.x_in[3 * plane + v];
+            const float pa = io.prev_a[v];
+            float u = io.action_mu[v];
+            if (io.ou_state) {  // noise.py:14-23 with explicit single roundings (bit-exact vs host restatement)
+                const float n0 = io.ou_state[v];
+                const uint4 wo = rng_words(io.seed, gp * (uint64_t)M + (uint64_t)m, tick, AVD_RNG_OU);
+                float z0, z1;
+                normal_pair(wo.x, wo.y, z0, z1);
+                const float drift = __fmul_rn(__fmul_rn(prm.ou_theta, __fadd_rn(prm.ou_mean, -n0)), prm.ou_dt);
+                const float n1 = __fadd_rn(__fadd_rn(n0, drift), __fmul_rn(ou_c, z0));
+                io.ou_state[v] = n1;
+                u = __fadd_rn(u, n1);
+            }
+            if (io.clip_actions) u = fminf(fmaxf(u, prm.action_low), prm.action_high);  // ddpgagent.py:27
+            if (io.action_out) io.action_out[v] = u;
+
+            // reward terms on the PRE-update state (environment.py:473-477, 505-510)
+            const float da = x2 - pa;
+            const float r_shaped = (prm.rew_ep * (fabsf(x0) * inv_max_ep) + prm.rew_ev * (fabsf(x1) * inv_max_ev) +
+                                    prm.rew_u * (fabsf(u) * inv_ahigh) + prm.rew_jerk * (fabsf(da) * inv_2maxa)) * prm.re_scalar;
+            const bool term = prm.can_terminate && (fabsf(x0) > prm.max_ep || fabsf(x1) > prm.max_ev);
+            const float r = -(term ? prm.terminal_reward * prm.re_scalar : r_shaped);  // Vehicle.step returns -reward
+            any_term |= term;
+            if (io.jerk) io.jerk[v] = da * inv_T;
+            if (io.cum_accel) {  // environment.py:500-503
+                const float cum = io.cum_accel[v] + x2;
+                io.cum_accel[v] = cum;
+                const float vel = cum * prm.T;
+                if (io.velocity) io.velocity[v] = vel;
+                if (io.headway) io.headway[v] = x0 + (8.0f + prm.h * vel);
+            }
+            // x <- A x + B u + C w  (environment.py:513)
+            const float* A = prm.A[m];
+            const float* B = prm.B[m];
+            const float* C = prm.C[m];
+            const float y0 = fmaf(A[0], x0, fmaf(A[1], x1, fmaf(A[2], x2, fmaf(A[3], x3, fmaf(B[0], u, C[0] * w)))));
+            const float y1 = fmaf(A[4], x0, fmaf(A[5], x1, fmaf(A[6], x2, fmaf(A[7], x3, fmaf(B[1], u, C[1] * w)))));
+            const float y2 = fmaf(A[8], x0, fmaf(A[9], x1, fmaf(A[10], x2, fmaf(A[11], x3, fmaf(B[2], u, C[2] * w)))));
+            const float y3 = fmaf(A[12], x0, fmaf(A[13], x1, fmaf(A[14], x2, fmaf(A[15], x3, fmaf(B[3], u, C[3] * w)))));
+            io.x_out[v] = y0;
+            io.x_out[plane + v] = y1;
+            io.x_out[2 * plane + v] = y2;
+            io.x_out[3 * plane + v] = y3;
+            io.prev_a[v] = x2;
+            if (!prm.centralized) io.reward[v] = r;
+            rew_sum += r;
+            if (io.ep_reward) io.ep_reward[v] += r;
+            stat_r[m] += r;
+            if (io.ring) {  // ReplayBuffer.add: (s, a, r, s') -- 40 B record, five 8-byte stores
+                float2* rec = reinterpret_cast<float2*>(io.ring + ((slot * M + m) * P + p) * AVD_RING_RECORD_FLOATS);
+                rec[0] = make_float2(x0, x1);
+                rec[1] = make_float2(x2, x3);
+                rec[2] = make_float2(u, r);
+                rec[3] = make_float2(y0, y1);
+                rec[4] = make_float2(y2, y3);
+            }
+            // next follower's exogenous input (environment.py:261 / 267)
+            w = prm.model_a ? y2 : u;
+        }
+        if (prm.centralized) io.reward[p] = rew_sum * (1.0f / (float)M);  // environment.py:281
+        bool timeout = false;
+        if (io.step_in_episode) {
+            const int s = io.step_in_episode[p] + 1;
+            timeout = prm.steps_per_episode > 0 && s >= prm.steps_per_episode;
+            io.step_in_episode[p] = s;
+        }
+        io.done[p] = (uint8_t)((any_term ? 1 : 0) | (timeout ? 2 : 0));
+        stat_done += any_term ? 1.0f : 0.0f;
+        if (io.auto_reset && (any_term || timeout)) {
+            const uint32_t ep = io.episode ? (uint32_t)io.episode[p] : 0u;
+            reset_one_platoon(prm, io, p, ep, io.x_out);
+            if (io.episode) io.episode[p] = (int32_t)(ep + 1u);
+        }
+    }
+
+    if (io.stats) {  // warp shuffle -> shared -> one atomic per CTA and statistic
+        __shared__ float red[8][AVD_MAX_FOLLOWERS + 1];
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+        for (int m = 0; m < (MT ? MT : AVD_MAX_FOLLOWERS); ++m) {
+            const float s = warp_sum(stat_r[m]);
+            if (lane == 0) red[wid][m] = s;
+        }
+        const float sd = warp_sum(stat_done);
+        if (lane == 0) red[wid][AVD_MAX_FOLLOWERS] = sd;
+        __syncthreads();
+        if (threadIdx.x <= M) {
+            const int col = (threadIdx.x == M) ? AVD_MAX_FOLLOWERS : threadIdx.x;
+            float s = 0.0f;
+            for (int wv = 0; wv < (int)(blockDim.x >> 5); ++wv) s += red[wv][col];
+            atomicAdd(io.stats + threadIdx.x, s);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) ou_sample_kernel(float theta, float mean, float dt, float sigma, float* __restrict__ state,
+                                                        float* __restrict__ out, int64_t n, uint64_t id_base, uint64_t seed,
+                                                        uint32_t tick) {
+    const float ou_c = __fmul_rn(sigma, __fsqrt_rn(dt));
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float n0 = state[i];
+        const uint4 wo = rng_words(seed, id_base + (uint64_t)i, tick, AVD_RNG_OU);
+        float z0, z1;
+        normal_pair(wo.x, wo.y, z0, z1);
+        const float drift = __fmul_rn(__fmul_rn(theta, __fadd_rn(mean, -n0)), dt);
+        const float n1 = __fadd_rn(__fadd_rn(n0, drift), __fmul_rn(ou_c, z0));
+        state[i] = n1;
+        if (out) out[i] = n1;
+    }
+}
+
+__global__ void clock_advance_kernel(avd_clock* c, uint32_t ds, uint32_t dr, uint32_t du) {
+    c->step_tick += ds;
+    c->ring_count += dr;
+    c->update_tick += du;
+}
+
+static int check_env_args(const avd_env_params* prm, const avd_env_io* io) {
+    AVD_REQUIRE(prm && io, "null params");
+    AVD_REQUIRE(prm->M >= 1 && prm->M <= AVD_MAX_FOLLOWERS, "M=%d outside 1..%d", prm->M, AVD_MAX_FOLLOWERS);
+    AVD_REQUIRE(io->P >= 0, "negative platoon count");
+    AVD_REQUIRE(io->prev_a, "prev_a buffer is required");
+    return AVD_OK;
+}
+
+}  // namespace avd
+
+using namespace avd;
+
+extern "C" int avd_clock_advance(avd_clock* clock_dev, uint32_t d_step, uint32_t d_ring, uint32_t d_update, void* stream) {
+    AVD_REQUIRE(clock_dev, "null clock");
+    clock_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(clock_dev, d_step, d_ring, d_update);
+    AVD_LAUNCH_OK();
+    return AVD_OK;
+}
+
+extern "C" int avd_ou_sample(const avd_env_params* prm, float* state, float* out, int64_t n, uint64_t id_base, uint64_t seed,
+                             uint32_t tick, void* stream) {
+    AVD_REQUIRE(prm && state && n >= 0, "bad args");
+    if (n == 0) return AVD_OK;
+    ou_sample_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(prm->ou_theta, prm->ou_mean, prm->ou_dt, prm->ou_sigma, state, out,
+                                                                     n, id_base, seed, tick);
+    AVD_LAUNCH_OK();
+    return AVD_OK;
+}
+
+extern "C" int avd_env_reset(const avd_env_params* prm, const avd_env_io* io, const uint8_t* mask, void* stream) {
+    if (int rc = check_env_args(prm, io)) return rc;
+    AVD_REQUIRE(io->x_out, "x_out is required");
+    if (io->P == 0) return AVD_OK;
+    env_reset_kernel<<<grid_for(io->P), 256, 0, (cudaStream_t)stream>>>(*prm, *io, mask);
+    AVD_LAUNCH_OK();
+    return AVD_OK;
+}
+
+extern "C" int avd_env_step(const avd_env_params* prm, const avd_env_io* io, void* stream) {
+    if (int rc = check_env_args(prm, io)) return rc;
+    AVD_REQUIRE(io->x_in && io->x_out && io->action_mu && io->reward && io->done, "x_in/x_out/action_mu/reward/done are required");
+    AVD_REQUIRE(io->x_in != io->x_out, "x_in and x_out must not alias (ping-pong state buffers)");
+    AVD_REQUIRE(!io->ring || io->ring_capacity > 0, "ring given with capacity %lld", (long long)io->ring_capacity);
+    AVD_REQUIRE(!io->auto_reset || (io->episode && io->step_in_episode), "auto_reset needs episode and step_in_episode");
+    AVD_REQUIRE(io->leader_exog || io->gen_exog || (prm->model_a ? io->front_accel != nullptr : io->front_u != nullptr),
+                "no source for the leader's exogenous input");
+    if (io->P == 0) return AVD_OK;
+    const int grid = grid_for(io->P);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (prm->M) {
+        case 1: env_step_kernel<1><<<grid, 256, 0, st>>>(*prm, *io); break;
+        case 2: env_step_kernel<2><<<grid, 256, 0, st>>>(*prm, *io); break;
+        case 3: env_step_kernel<3><<<grid, 256, 0, st>>>(*prm, *io); break;
+        case 4: env_step_kernel<4><<<grid, 256, 0, st>>>(*prm, *io); break;
+        case 5: env_step_kernel<5><<<grid, 256, 0, st>>>(*prm, *io); break;
+        case 6: env_step_kernel<6><<<grid, 256, 0, st>>>(*prm, *io); break;
+        case 8: env_step_kernel<8><<<grid, 256, 0, st>>>(*prm, *io); break;
+        default: env_step_kernel<0><<<grid, 256, 0, st>>>(*prm, *io); break;
+    }
+    AVD_LAUNCH_OK();
+    return AVD_OK;
+}
+
+extern "C" int avd_env_step_host(const avd_env_params* prm, const avd_env_io* io, const float* actions_host,
+                                 const float* leader_exog_host, float* obs_host, float* reward_host,
+                                 uint8_t* done_host, void* stream) {
+    if (int rc = check_env_args(prm, io)) return rc;
+    AVD_REQUIRE(actions_host && obs_host && reward_host && done_host, "null host buffer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t n = (size_t)prm->M * (size_t)io->P;
+    AVD_CUDA_OK(cudaMemcpyAsync((void*)io->action_mu, actions_host, n * sizeof(float), cudaMemcpyHostToDevice, st));
+    if (leader_exog_host) {
+        AVD_REQUIRE(io->leader_exog, "leader_exog_host given but io->leader_exog staging is NULL");
+        AVD_CUDA_OK(cudaMemcpyAsync((void*)io->leader_exog, leader_exog_host, (size_t)io->P * sizeof(float), cudaMemcpyHostToDevice, st));
+    }
+    if (int rc = avd_env_step(prm, io, stream)) return rc;
+    AVD_CUDA_OK(cudaMemcpyAsync(obs_host, io->x_out, 4 * n * sizeof(float), cudaMemcpyDeviceToHost, st));
+    AVD_CUDA_OK(cudaMemcpyAsync(reward_host, io->reward, (prm->centralized ? (size_t)io->P : n) * sizeof(float), cudaMemcpyDeviceToHost, st));
+    AVD_CUDA_OK(cudaMemcpyAsync(done_host, io->done, (size_t)io->P, cudaMemcpyDeviceToHost, st));
+    AVD_CUDA_OK(cudaStreamSynchronize(st));
+    return AVD_OK;
+}
+
+extern "C" int avd_env_build_matrices(avd_env_params* prm, int method, double T, double h, double tau,
+                                      double pl_leader_tau) {
+    AVD_REQUIRE(prm, "null params");
+    AVD_REQUIRE(prm->M >= 1 && prm->M <= AVD_MAX_FOLLOWERS, "M=%d outside 1..%d", prm->M, AVD_MAX_FOLLOWERS);
+    AVD_REQUIRE(method == 0 || method == 1, "method must be 0 (euler) or 1 (exact)");
+    AVD_REQUIRE(T > 0 && tau > 0 && pl_leader_tau > 0, "sample_rate, dyn_coeff and pl_leader_tau must be positive");
+    prm->T = (float)T;
+    prm->h = (float)h;
+    for (int m = 0; m < prm->M; ++m) {
+        const double tl = (m == 0) ? pl_leader_tau : tau;
+        double A[16] = {0}, B[4] = {0}, C[4] = {0};
+        A[0] = 1.0; A[1] = T; A[5] = 1.0;
+        if (method == 0) {  // environment.py:393-408
+            A[2] = -h * T;
+            A[6] = -T; A[7] = T;
+            A[10] = 1.0 - T / tau;
+            A[15] = 1.0 - T / tl;
+            B[2] = T / tau;
+            C[3] = T / tl;
+        } else {            // environment.py:410-445
+            const double e = exp(-T / tau), el = exp(-T / tl);
+            A[2] = -h * tau + h * tau * e - tau * T + tau * tau - tau * tau * e;
+            A[3] = tl * T - tl * tl + tl * tl * el;
+            A[6] = -tau + tau * e;
+            A[7] = tl - tl * el;
+            A[10] = e;
+            A[15] = el;
+            B[0] = -h * T + h * tau * e - h * tau - T * T / 2 + tau * T + tau * tau * e - tau * tau;
+            B[1] = -T - tau * e + tau;
+            B[2] = 1.0 - e;
+            C[0] = T * T / 2 - tl * T - tl * tl * el + tl * tl;
+            C[1] = T + tl * el - tl;
+            C[3] = 1.0 - el;
+        }
+        for (int i = 0; i < 16; ++i) prm->A[m][i] = (float)A[i];
+        for (int i = 0; i < 4; ++i) { prm->B[m][i] = (float)B[i]; prm->C[m][i] = (float)C[i]; }
+    }
+    return AVD_OK;
+}

@@ -1,0 +1,197 @@
+/* avddpg_b200.h -- C ABI of the B200-native avddpg hot path (libavddpg_b200.so).
+ *
+ * The reference (cboin1996/avddpg) is pure Python and has no FFI of its own; its boundary is the
+ * Python call surface workers/trainer.py uses.  Every entry point below names the
+ * reference interface it replaces (file:line under /root/reference).  INTEGRATION.md shows the
+ * ctypes binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain C: pointers, sizes, PODs.  No torch / C++ types cross this boundary.
+ *   - every `*_dev` / unqualified buffer pointer is DEVICE memory of the current CUDA device;
+ *     entry points whose name ends in `_host` take HOST pointers and do the copies themselves.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  All calls are
+ *     asynchronous with respect to the host unless the name ends in `_host` or `_sync`.
+ *   - return value: 0 on success, negative avd_status on error; avd_last_error() gives the text.
+ *     (The reference raises Python exceptions -- ValueError etc.; the Python mirror in
+ *     avddpg_b200/ converts these codes back into the same exception types.)
+ *   - layouts: platoon state is struct-of-arrays, platoon index fastest:
+ *         x[f][m][p]  -> ((f*M + m)*P + p)      f in 0..3  (ep, ev, a, a_lead)
+ *         per-vehicle scalars (action, reward, prev_a, ...)  [m][p] -> (m*P + p)
+ *     replay ring records are array-of-structs, 10 floats each (s[4], a, r, s'[4]):
+ *         ring[slot][m][p][10] -> (((slot*M + m)*P + p)*10)
+ */
+#ifndef AVDDPG_B200_H
+#define AVDDPG_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AVD_MAX_FOLLOWERS 16
+#define AVD_RING_RECORD_FLOATS 10
+#define AVD_ABI_VERSION 1
+
+typedef enum avd_status {
+    AVD_OK = 0,
+    AVD_ERR_INVALID_ARG = -1,   /* -> ValueError   */
+    AVD_ERR_CUDA = -2,          /* -> RuntimeError */
+    AVD_ERR_UNSUPPORTED = -3,   /* -> NotImplementedError */
+    AVD_ERR_NO_DEVICE = -4      /* -> RuntimeError: no CUDA device / wrong architecture */
+} avd_status;
+
+/* purposes of the Philox4x32-10 counter-based streams (counter word 3) */
+enum {
+    AVD_RNG_RESET_VEHICLE = 0,
+    AVD_RNG_RESET_PLATOON = 1,
+    AVD_RNG_OU = 2,
+    AVD_RNG_LEADER_EXOG = 3,
+    AVD_RNG_REPLAY = 4,
+    AVD_RNG_INIT = 5
+};
+
+/* ---- environment parameters: the Config scalars the hot path reads (src/config.py:41-104),
+ *      plus per-follower system matrices (Vehicle.set_system_matrices, src/environment.py:390-451). */
+typedef struct avd_env_params {
+    int32_t M;               /* followers per platoon, 1..AVD_MAX_FOLLOWERS (config.pl_size)        */
+    int32_t num_states;      /* 4 = Model B, 3 = Model A (environment.py:47-52)                     */
+    int32_t model_a;         /* 1: exogenous input = predecessor's post-update accel (env.py:263-267) */
+    int32_t can_terminate;   /* config.can_terminate (environment.py:505)                           */
+    int32_t centralized;     /* 1: platoon reward = mean over followers (environment.py:234-236)   */
+    int32_t rand_uniform;    /* 1: reset draws U(-v,v) instead of N(0,v) (util.py:66-70)            */
+    int32_t reset_mode;      /* 0 random (rand_states), 1 fixed maxima, 2 evaluator states (env.py:534-555) */
+    int32_t steps_per_episode; /* config.steps_per_episode; 0 = never time out (auto-reset only)    */
+    float T, h;              /* sample_rate, timegap                                                 */
+    float max_ep, max_ev;    /* terminal thresholds                                                  */
+    float action_high, action_low;
+    float rew_ep, rew_ev, rew_u, rew_jerk; /* reward coefficients a,b,c,d                           */
+    float re_scalar, terminal_reward;
+    float reset_ep, reset_ev, reset_a;     /* bounds / std-devs / fixed values selected by reset_mode */
+    float reset_leader_a, reset_u;         /* pl_leader_reset_a, reset_max_u                          */
+    float ou_theta, ou_dt, ou_sigma, ou_mean; /* OUActionNoise (src/noise.py:3-29)                   */
+    float A[AVD_MAX_FOLLOWERS][16];        /* row-major 4x4 per follower                             */
+    float B[AVD_MAX_FOLLOWERS][4];
+    float C[AVD_MAX_FOLLOWERS][4];
+} avd_env_params;
+
+/* ---- device-resident counters, so a captured CUDA graph can be replayed without new arguments */
+typedef struct avd_clock {
+    uint64_t step_tick;      /* env steps taken (keys OU / leader-exog streams)                      */
+    uint64_t ring_count;     /* transitions added per ring == ReplayBuffer.buffer_counter            */
+    uint64_t update_tick;    /* learn() calls (keys the replay sampling stream)                      */
+    uint64_t reserved;
+} avd_clock;
+
+/* ---- buffers of one shard of platoons (all device pointers; nullable ones are marked) */
+typedef struct avd_env_io {
+    int64_t P;                 /* platoons in this shard                                             */
+    int64_t platoon_id_base;   /* global id of local platoon 0: RNG streams do not depend on sharding */
+    uint64_t seed;             /* config.random_seed                                                 */
+    const float* x_in;         /* [4][M][P] state before the step                                    */
+    float* x_out;              /* [4][M][P] state after the step (ping-pong: never aliases x_in)     */
+    float* prev_a;             /* [M][P]   prev_x[2]  (in/out)                                       */
+    float* cum_accel;          /* [M][P]   nullable: kinematic observables off                       */
+    const float* action_mu;    /* [M][P]   actor output or injected action                           */
+    float* ou_state;           /* [M][P]   nullable: no exploration noise (evaluator path)           */
+    float* action_out;         /* [M][P]   nullable: clipped action actually applied                 */
+    const float* leader_exog;  /* [P]      nullable: see gen_exog                                    */
+    float* front_u;            /* [P]      platoon.front_u (used when leader_exog==NULL && !gen_exog) */
+    float* front_accel;        /* [P]      platoon.front_accel (Model A fallback)                    */
+    float* reward;             /* [M][P]   (centralized: [P]) NEGATED reward as Vehicle.step returns */
+    uint8_t* done;             /* [P]      bit0: any follower terminal (platoon_done, environment.py:238);
+                                           bit1: episode time limit reached (steps_per_episode)      */
+    float* jerk;               /* [M][P]   nullable                                                  */
+    float* velocity;           /* [M][P]   nullable (needs cum_accel)                                */
+    float* headway;            /* [M][P]   nullable (needs cum_accel)                                */
+    float* ring;               /* nullable: replay ring [capacity][M][P][10]                         */
+    int64_t ring_capacity;
+    int32_t* episode;          /* [P] nullable: per-platoon episode counter (needed for auto_reset)  */
+    int32_t* step_in_episode;  /* [P] nullable                                                       */
+    float* ep_reward;          /* [M][P] nullable: episodic reward accumulators (trainer.py:321)     */
+    float* stats;              /* nullable: += [0..M-1] sum over platoons of reward, [M] #terminal platoons */
+    const avd_clock* clock;    /* device clock (step_tick, ring_count)                               */
+    int32_t gen_exog;          /* 1: draw leader exog ~ reset_u * N(0,1) on device (trainer.py:292-295) */
+    int32_t auto_reset;        /* 1: platoons that are done / timed out are reset inside the kernel  */
+    int32_t clip_actions;      /* 1: clip the (noisy) action to [action_low, action_high] (ddpgagent.py:27);
+                                  0: apply action_mu as given, like Platoon.step does                 */
+    int32_t reserved0;
+} avd_env_io;
+
+/* ---- library ------------------------------------------------------------------------------- */
+int avd_abi_version(void);
+const char* avd_last_error(void);
+/* sizeof of the ABI structs as compiled (0 avd_env_params, 1 avd_env_io, 2 avd_clock): bindings
+ * assert their own layout against these at load time. */
+int64_t avd_sizeof(int which);
+/* SM count, compute capability major*10+minor of the current device; AVD_ERR_NO_DEVICE if none */
+int avd_device_info(int* sm_count, int* cc, int64_t* total_mem);
+
+/* ---- clock --------------------------------------------------------------------------------- */
+/* clock[0] += (d_step, d_ring, d_update): one tiny kernel so it can live inside a CUDA graph.    */
+int avd_clock_advance(avd_clock* clock_dev, uint32_t d_step, uint32_t d_ring, uint32_t d_update, void* stream);
+
+/* ---- environment --------------------------------------------------------------------------- */
+/* Vehicle.set_system_matrices (environment.py:390-451): fills prm->A/B/C (and prm->T, prm->h) for
+ * prm->M followers, computed in double and rounded once to binary32.  method: 0 euler, 1 exact.
+ * tau_lead of follower 0 is pl_leader_tau, of the others dyn_coeff (environment.py:57,61).        */
+int avd_env_build_matrices(avd_env_params* prm, int method, double sample_rate, double timegap,
+                           double dyn_coeff, double pl_leader_tau);
+
+/* Platoon.reset + Vehicle.reset (environment.py:284-301, 520-559) for every platoon with
+ * mask[p]!=0 (mask==NULL: all).  Writes x_out AND x_in's accel plane is untouched; prev_a, cum_accel,
+ * front_u, front_accel, step_in_episode are reinitialised, episode[p] is incremented afterwards.
+ * Random draws: Philox stream (AVD_RNG_RESET_*, id, tick = episode[p]).                           */
+int avd_env_reset(const avd_env_params* prm, const avd_env_io* io, const uint8_t* mask, void* stream);
+
+/* Platoon.step (environment.py:209-241) for P platoons, fused with, when the pointers are given:
+ * OUActionNoise.__call__ + policy clip (noise.py:14-23, ddpgagent.py:18-29), the leader-exog draw
+ * (trainer.py:292-295), ReplayBuffer.add for every (p,m) (replaybuffer.py:37-47), episodic reward
+ * accumulation (trainer.py:321) and per-platoon auto-reset.                                        */
+int avd_env_step(const avd_env_params* prm, const avd_env_io* io, void* stream);
+
+/* OUActionNoise.__call__ (src/noise.py:14-23) for n independent processes: state[i] is advanced in place
+ * with the Philox stream (AVD_RNG_OU, id_base+i, tick) and the new sample is also written to out[i]
+ * (out may be NULL).  This is the stand-alone form; avd_env_step fuses the same arithmetic.           */
+int avd_ou_sample(const avd_env_params* prm, float* state, float* out, int64_t n, uint64_t id_base,
+                  uint64_t seed, uint32_t tick, void* stream);
+
+/* Same step through HOST buffers (the call a drop-in Platoon.step makes): copies actions[M][P]
+ * (+ leader_exog[P] if non-NULL) to the device, runs avd_env_step on `io` (whose action_mu /
+ * leader_exog must point at device staging of the right size), copies obs (x_out, 4*M*P floats),
+ * reward and done back, and synchronises the stream.                                              */
+int avd_env_step_host(const avd_env_params* prm, const avd_env_io* io, const float* actions_host,
+                      const float* leader_exog_host, float* obs_host, float* reward_host,
+                      uint8_t* done_host, void* stream);
+
+/* ---- replay buffer ------------------------------------------------------------------------- */
+/* ReplayBuffer.add (replaybuffer.py:37-47) for all M*P rings at once from explicit tuples
+ * (the fused path writes the ring from avd_env_step instead).  s, s2: [4][M][P]; a, r: [M][P].   */
+int avd_replay_add(float* ring, int64_t capacity, int64_t M, int64_t P, const avd_clock* clock,
+                   const float* s, const float* a, const float* r, const float* s2, void* stream);
+
+/* ReplayBuffer.sample index draw (replaybuffer.py:52-54): idx[ring][j] uniform in
+ * [0, min(ring_count, capacity)), Philox stream (AVD_RNG_REPLAY, ring_id_base+ring, update_tick).
+ * idx_out: int64 [n_rings][batch].                                                                */
+int avd_replay_sample_indices(int64_t* idx_out, int64_t n_rings, int64_t ring_id_base, int32_t batch,
+                              int64_t capacity, uint64_t seed, const avd_clock* clock, void* stream);
+
+/* ReplayBuffer.sample gathers (replaybuffer.py:57-61): rows are ordered [ring][j]; ring r is
+ * (m = r / P ... see layout) -- ring id = m*P + p.  Outputs row-major: s[n][4], a[n], r[n], s2[n][4]. */
+int avd_replay_gather(const float* ring, int64_t capacity, int64_t M, int64_t P, const int64_t* idx,
+                      int32_t batch, float* s, float* a, float* r, float* s2, void* stream);
+
+/* Fill the whole ring with synthetic transitions (benchmark warm start: steady-state sampling
+ * range without running `capacity` env steps).                                                    */
+int avd_replay_fill_synthetic(float* ring, int64_t capacity, int64_t M, int64_t P, uint64_t seed, void* stream);
+
+/* ---- raw RNG access (parity tests: bit-exact against oracle/philox_np.py) ------------------- */
+int avd_rng_words(uint32_t* out4 /*[n][4]*/, int64_t n, uint64_t id_base, uint32_t tick, uint32_t purpose,
+                  uint64_t seed, void* stream);
+int avd_rng_normals(float* out4 /*[n][4]*/, int64_t n, uint64_t id_base, uint32_t tick, uint32_t purpose,
+                    uint64_t seed, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AVDDPG_B200_H */
