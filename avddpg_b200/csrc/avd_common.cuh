@@ -46,6 +46,21 @@ inline int grid_for(int64_t work_items, int threads = 256, int ctas_per_sm = 8) 
     return (int)(need < cap ? need : cap);
 }
 
+// Grid for a grid-stride kernel: exactly the number of CTAs that are co-resident (SMs x occupancy), so
+// there is a single wave and no tail, capped by the work available.
+template <class Kernel>
+inline int resident_grid(Kernel kernel, int64_t work_items, int threads = 256, size_t smem = 0) {
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem) != cudaSuccess || occ < 1) {
+        cudaGetLastError();
+        occ = 1;
+    }
+    int64_t need = (work_items + threads - 1) / threads;
+    int64_t cap = (int64_t)sm_count() * occ;
+    if (need < 1) need = 1;
+    return (int)(need < cap ? need : cap);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -90,25 +90,124 @@ __global__ void __launch_bounds__(256) env_reset_kernel(const __grid_constant__ 
 // ------------------------------------------------------------------------------------------------
 // step
 // ------------------------------------------------------------------------------------------------
-#ifndef AVD_ENV_MIN_CTAS
-#define AVD_ENV_MIN_CTAS 3   // 80 registers/thread, no spills: 768 threads/SM x ~7 loads in flight per follower
-#endif
+// Everything one follower needs from HBM; loaded for ALL followers of a platoon before the first dependent
+// use so that a thread has 6..8 x M independent requests in flight (the kernel is HBM-latency/bandwidth bound).
+struct FollowerIn {
+    float x0, x1, x2, x3, pa, mu, ou, cum;
+};
 
+struct StepCtx {
+    const float* __restrict__ x_in;
+    float* __restrict__ x_out;
+    float* __restrict__ prev_a;
+    const float* __restrict__ action_mu;
+    float* __restrict__ ou_state;
+    float* __restrict__ action_out;
+    float* __restrict__ reward;
+    float* __restrict__ cum_accel;
+    float* __restrict__ ep_reward;
+    float* __restrict__ ring;
+    float* __restrict__ jerk;
+    float* __restrict__ velocity;
+    float* __restrict__ headway;
+    int64_t P, plane, slot;
+    uint32_t tick;
+    float inv_max_ep, inv_max_ev, inv_ahigh, inv_2maxa, inv_T, ou_c;
+};
+
+__device__ __forceinline__ FollowerIn load_follower(const StepCtx& c, int64_t v) {
+    FollowerIn f;
+    f.x0 = c.x_in[v];
+    f.x1 = c.x_in[c.plane + v];
+    f.x2 = c.x_in[2 * c.plane + v];
+    f.x3 = c.x_in[3 * c.plane + v];
+    f.pa = c.prev_a[v];
+    f.mu = c.action_mu[v];
+    f.ou = c.ou_state ? c.ou_state[v] : 0.0f;
+    f.cum = c.cum_accel ? c.cum_accel[v] : 0.0f;
+    return f;
+}
+
+// One Vehicle.step (environment.py:460-518) + fused OU/clip/replay write.  `w` is this follower's exogenous
+// input on entry and the next follower's on exit.  Returns the (negated) reward; sets `term`.
+__device__ __forceinline__ float step_follower(const avd_env_params& prm, const avd_env_io& io, const StepCtx& c,
+                                               const FollowerIn& f, int m, int M, int64_t p, uint64_t gp, float& w, bool& term) {
+    const int64_t v = (int64_t)m * c.P + p;
+    float u = f.mu;
+    if (c.ou_state) {  // noise.py:14-23 with explicit single roundings (bit-exact vs the host restatement)
+        const uint4 wo = rng_words(io.seed, gp * (uint64_t)M + (uint64_t)m, c.tick, AVD_RNG_OU);
+        float z0, z1;
+        normal_pair(wo.x, wo.y, z0, z1);
+        const float drift = __fmul_rn(__fmul_rn(prm.ou_theta, __fadd_rn(prm.ou_mean, -f.ou)), prm.ou_dt);
+        const float n1 = __fadd_rn(__fadd_rn(f.ou, drift), __fmul_rn(c.ou_c, z0));
+        c.ou_state[v] = n1;
+        u = __fadd_rn(u, n1);
+    }
+    if (io.clip_actions) u = fminf(fmaxf(u, prm.action_low), prm.action_high);  // ddpgagent.py:27
+    if (c.action_out) c.action_out[v] = u;
+
+    // reward terms on the PRE-update state (environment.py:473-477, 505-510)
+    const float da = f.x2 - f.pa;
+    const float r_shaped = (prm.rew_ep * (fabsf(f.x0) * c.inv_max_ep) + prm.rew_ev * (fabsf(f.x1) * c.inv_max_ev) +
+                            prm.rew_u * (fabsf(u) * c.inv_ahigh) + prm.rew_jerk * (fabsf(da) * c.inv_2maxa)) * prm.re_scalar;
+    term = prm.can_terminate && (fabsf(f.x0) > prm.max_ep || fabsf(f.x1) > prm.max_ev);
+    const float r = -(term ? prm.terminal_reward * prm.re_scalar : r_shaped);  // Vehicle.step returns -reward
+    if (c.jerk) c.jerk[v] = da * c.inv_T;
+    if (c.cum_accel) {  // environment.py:500-503
+        const float cum = f.cum + f.x2;
+        c.cum_accel[v] = cum;
+        const float vel = cum * prm.T;
+        if (c.velocity) c.velocity[v] = vel;
+        if (c.headway) c.headway[v] = f.x0 + (8.0f + prm.h * vel);
+    }
+    // x <- A x + B u + C w  (environment.py:513)
+    const float* A = prm.A[m];
+    const float* B = prm.B[m];
+    const float* C = prm.C[m];
+    const float y0 = fmaf(A[0], f.x0, fmaf(A[1], f.x1, fmaf(A[2], f.x2, fmaf(A[3], f.x3, fmaf(B[0], u, C[0] * w)))));
+    const float y1 = fmaf(A[4], f.x0, fmaf(A[5], f.x1, fmaf(A[6], f.x2, fmaf(A[7], f.x3, fmaf(B[1], u, C[1] * w)))));
+    const float y2 = fmaf(A[8], f.x0, fmaf(A[9], f.x1, fmaf(A[10], f.x2, fmaf(A[11], f.x3, fmaf(B[2], u, C[2] * w)))));
+    const float y3 = fmaf(A[12], f.x0, fmaf(A[13], f.x1, fmaf(A[14], f.x2, fmaf(A[15], f.x3, fmaf(B[3], u, C[3] * w)))));
+    c.x_out[v] = y0;
+    c.x_out[c.plane + v] = y1;
+    c.x_out[2 * c.plane + v] = y2;
+    c.x_out[3 * c.plane + v] = y3;
+    c.prev_a[v] = f.x2;
+    if (!prm.centralized) c.reward[v] = r;
+    if (c.ep_reward) c.ep_reward[v] += r;
+    if (c.ring) {  // ReplayBuffer.add: (s, a, r, s') -- one 40 B record, five 8-byte stores
+        float2* rec = reinterpret_cast<float2*>(c.ring + ((c.slot * M + m) * c.P + p) * AVD_RING_RECORD_FLOATS);
+        rec[0] = make_float2(f.x0, f.x1);
+        rec[1] = make_float2(f.x2, f.x3);
+        rec[2] = make_float2(u, r);
+        rec[3] = make_float2(y0, y1);
+        rec[4] = make_float2(y2, y3);
+    }
+    w = prm.model_a ? y2 : u;  // next follower's exogenous input (environment.py:261 / 267)
+    return r;
+}
+
+// Registers: the preloaded inputs cost 8 x M; 1..4 followers fit 80 registers (3 CTAs/SM), 5..8 need 128 (2 CTAs/SM).
 template <int MT>
-__global__ void __launch_bounds__(256, AVD_ENV_MIN_CTAS) env_step_kernel(const __grid_constant__ avd_env_params prm,
-                                                       const __grid_constant__ avd_env_io io) {
+__global__ void __launch_bounds__(256, (MT >= 1 && MT <= 4) ? 3 : 2) env_step_kernel(const __grid_constant__ avd_env_params prm,
+                                                                                      const __grid_constant__ avd_env_io io) {
     const int M = MT ? MT : prm.M;
-    const int64_t P = io.P;
-    const int64_t plane = (int64_t)M * P;  // one state component of all vehicles
+    StepCtx c;
+    c.x_in = io.x_in; c.x_out = io.x_out; c.prev_a = io.prev_a; c.action_mu = io.action_mu; c.ou_state = io.ou_state;
+    c.action_out = io.action_out; c.reward = io.reward; c.cum_accel = io.cum_accel; c.ep_reward = io.ep_reward;
+    c.ring = io.ring; c.jerk = io.jerk; c.velocity = io.velocity; c.headway = io.headway;
+    c.P = io.P;
+    c.plane = (int64_t)M * io.P;  // one state component of all vehicles
     const uint64_t tick64 = io.clock ? io.clock->step_tick : 0ull;
-    const uint32_t tick = (uint32_t)tick64;
+    c.tick = (uint32_t)tick64;
     const uint64_t ring_count = io.clock ? io.clock->ring_count : 0ull;
-    const int64_t slot = io.ring ? (int64_t)(ring_count % (uint64_t)io.ring_capacity) : 0;
+    c.slot = io.ring ? (int64_t)(ring_count % (uint64_t)io.ring_capacity) : 0;
     const bool uni = prm.rand_uniform != 0;
-    const float inv_max_ep = 1.0f / prm.max_ep, inv_max_ev = 1.0f / prm.max_ev;
-    const float inv_ahigh = 1.0f / fabsf(prm.action_high), inv_2maxa = 1.0f / (2.0f * prm.action_high);
-    const float inv_T = 1.0f / prm.T;
-    const float ou_c = __fmul_rn(prm.ou_sigma, __fsqrt_rn(prm.ou_dt));
+    c.inv_max_ep = 1.0f / prm.max_ep; c.inv_max_ev = 1.0f / prm.max_ev;
+    c.inv_ahigh = 1.0f / fabsf(prm.action_high); c.inv_2maxa = 1.0f / (2.0f * prm.action_high);
+    c.inv_T = 1.0f / prm.T;
+    c.ou_c = __fmul_rn(prm.ou_sigma, __fsqrt_rn(prm.ou_dt));
+    const int64_t P = io.P;
 
     float stat_r[MT ? MT : AVD_MAX_FOLLOWERS];
 #pragma unroll
@@ -117,79 +216,41 @@ __global__ void __launch_bounds__(256, AVD_ENV_MIN_CTAS) env_step_kernel(const _
 
     for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (int64_t)gridDim.x * blockDim.x) {
         const uint64_t gp = (uint64_t)(io.platoon_id_base + p);
+        FollowerIn fin[MT ? MT : 1];
+        if (MT) {
+#pragma unroll
+            for (int m = 0; m < MT; ++m) fin[m] = load_follower(c, (int64_t)m * P + p);
+        }
         // exogenous input of follower 0 (environment.py:258-259 / 264-265, trainer.py:292-295)
         float w;
         if (io.leader_exog) {
             w = io.leader_exog[p];
         } else if (io.gen_exog) {
-            const uint4 wx = rng_words(io.seed, gp, tick, AVD_RNG_LEADER_EXOG);
+            const uint4 wx = rng_words(io.seed, gp, c.tick, AVD_RNG_LEADER_EXOG);
             w = draw_first(wx.x, wx.y, prm.reset_u, uni);
         } else {
             w = prm.model_a ? io.front_accel[p] : io.front_u[p];
         }
         bool any_term = false;
         float rew_sum = 0.0f;
+        if (MT) {
 #pragma unroll
-        for (int m = 0; m < M; ++m) {
-            const int64_t v = (int64_t)m * P + p;
-            const float x0 = io.x_in[v], x1 = io.x_in[plane + v], x2 = io.x_in[2 * plane + v], x3 = io.x_in[3 * plane + v];
-            const float pa = io.prev_a[v];
-            float u = io.action_mu[v];
-            if (io.ou_state) {  // noise.py:14-23 with explicit single roundings (bit-exact vs host restatement)
-                const float n0 = io.ou_state[v];
-                const uint4 wo = rng_words(io.seed, gp * (uint64_t)M + (uint64_t)m, tick, AVD_RNG_OU);
-                float z0, z1;
-                normal_pair(wo.x, wo.y, z0, z1);
-                const float drift = __fmul_rn(__fmul_rn(prm.ou_theta, __fadd_rn(prm.ou_mean, -n0)), prm.ou_dt);
-                const float n1 = __fadd_rn(__fadd_rn(n0, drift), __fmul_rn(ou_c, z0));
-                io.ou_state[v] = n1;
-                u = __fadd_rn(u, n1);
+            for (int m = 0; m < MT; ++m) {
+                bool term;
+                const float r = step_follower(prm, io, c, fin[m], m, MT, p, gp, w, term);
+                any_term |= term;
+                rew_sum += r;
+                stat_r[m] += r;
             }
-            if (io.clip_actions) u = fminf(fmaxf(u, prm.action_low), prm.action_high);  // ddpgagent.py:27
-            if (io.action_out) io.action_out[v] = u;
-
-            // reward terms on the PRE-update state (environment.py:473-477, 505-510)
-            const float da = x2 - pa;
-            const float r_shaped = (prm.rew_ep * (fabsf(x0) * inv_max_ep) + prm.rew_ev * (fabsf(x1) * inv_max_ev) +
-                                    prm.rew_u * (fabsf(u) * inv_ahigh) + prm.rew_jerk * (fabsf(da) * inv_2maxa)) * prm.re_scalar;
-            const bool term = prm.can_terminate && (fabsf(x0) > prm.max_ep || fabsf(x1) > prm.max_ev);
-            const float r = -(term ? prm.terminal_reward * prm.re_scalar : r_shaped);  // Vehicle.step returns -reward
-            any_term |= term;
-            if (io.jerk) io.jerk[v] = da * inv_T;
-            if (io.cum_accel) {  // environment.py:500-503
-                const float cum = io.cum_accel[v] + x2;
-                io.cum_accel[v] = cum;
-                const float vel = cum * prm.T;
-                if (io.velocity) io.velocity[v] = vel;
-                if (io.headway) io.headway[v] = x0 + (8.0f + prm.h * vel);
+        } else {
+            for (int m = 0; m < M; ++m) {
+                bool term;
+                const FollowerIn f = load_follower(c, (int64_t)m * P + p);
+                const float r = step_follower(prm, io, c, f, m, M, p, gp, w, term);
+                any_term |= term;
+                rew_sum += r;
+                stat_r[m] += r;
             }
-            // x <- A x + B u + C w  (environment.py:513)
-            const float* A = prm.A[m];
-            const float* B = prm.B[m];
-            const float* C = prm.C[m];
-            const float y0 = fmaf(A[0], x0, fmaf(A[1], x1, fmaf(A[2], x2, fmaf(A[3], x3, fmaf(B[0], u, C[0] * w)))));
-            const float y1 = fmaf(A[4], x0, fmaf(A[5], x1, fmaf(A[6], x2, fmaf(A[7], x3, fmaf(B[1], u, C[1] * w)))));
-            const float y2 = fmaf(A[8], x0, fmaf(A[9], x1, fmaf(A[10], x2, fmaf(A[11], x3, fmaf(B[2], u, C[2] * w)))));
-            const float y3 = fmaf(A[12], x0, fmaf(A[13], x1, fmaf(A[14], x2, fmaf(A[15], x3, fmaf(B[3], u, C[3] * w)))));
-            io.x_out[v] = y0;
-            io.x_out[plane + v] = y1;
-            io.x_out[2 * plane + v] = y2;
-            io.x_out[3 * plane + v] = y3;
-            io.prev_a[v] = x2;
-            if (!prm.centralized) io.reward[v] = r;
-            rew_sum += r;
-            if (io.ep_reward) io.ep_reward[v] += r;
-            stat_r[m] += r;
-            if (io.ring) {  // ReplayBuffer.add: (s, a, r, s') -- 40 B record, five 8-byte stores
-                float2* rec = reinterpret_cast<float2*>(io.ring + ((slot * M + m) * P + p) * AVD_RING_RECORD_FLOATS);
-                rec[0] = make_float2(x0, x1);
-                rec[1] = make_float2(x2, x3);
-                rec[2] = make_float2(u, r);
-                rec[3] = make_float2(y0, y1);
-                rec[4] = make_float2(y2, y3);
-            }
-            // next follower's exogenous input (environment.py:261 / 267)
-            w = prm.model_a ? y2 : u;
         }
         if (prm.centralized) io.reward[p] = rew_sum * (1.0f / (float)M);  // environment.py:281
         bool timeout = false;
@@ -296,18 +357,19 @@ extern "C" int avd_env_step(const avd_env_params* prm, const avd_env_io* io, voi
     AVD_REQUIRE(io->leader_exog || io->gen_exog || (prm->model_a ? io->front_accel != nullptr : io->front_u != nullptr),
                 "no source for the leader's exogenous input");
     if (io->P == 0) return AVD_OK;
-    const int grid = grid_for(io->P);
     cudaStream_t st = (cudaStream_t)stream;
+#define AVD_LAUNCH_STEP(MT) env_step_kernel<MT><<<resident_grid(env_step_kernel<MT>, io->P), 256, 0, st>>>(*prm, *io)
     switch (prm->M) {
-        case 1: env_step_kernel<1><<<grid, 256, 0, st>>>(*prm, *io); break;
-        case 2: env_step_kernel<2><<<grid, 256, 0, st>>>(*prm, *io); break;
-        case 3: env_step_kernel<3><<<grid, 256, 0, st>>>(*prm, *io); break;
-        case 4: env_step_kernel<4><<<grid, 256, 0, st>>>(*prm, *io); break;
-        case 5: env_step_kernel<5><<<grid, 256, 0, st>>>(*prm, *io); break;
-        case 6: env_step_kernel<6><<<grid, 256, 0, st>>>(*prm, *io); break;
-        case 8: env_step_kernel<8><<<grid, 256, 0, st>>>(*prm, *io); break;
-        default: env_step_kernel<0><<<grid, 256, 0, st>>>(*prm, *io); break;
+        case 1: AVD_LAUNCH_STEP(1); break;
+        case 2: AVD_LAUNCH_STEP(2); break;
+        case 3: AVD_LAUNCH_STEP(3); break;
+        case 4: AVD_LAUNCH_STEP(4); break;
+        case 5: AVD_LAUNCH_STEP(5); break;
+        case 6: AVD_LAUNCH_STEP(6); break;
+        case 8: AVD_LAUNCH_STEP(8); break;
+        default: AVD_LAUNCH_STEP(0); break;
     }
+#undef AVD_LAUNCH_STEP
     AVD_LAUNCH_OK();
     return AVD_OK;
 }

@@ -59,7 +59,8 @@ class BatchedPlatoons:
     def __init__(self, num_platoons: int, length: int, config, *, device=None, platoon_id_base: int = 0,
                  seed: Optional[int] = None, rand_states: bool = True, evaluator_states_enabled: bool = False,
                  track_kinematics: bool = True, ring=None, clock: Optional[DeviceClock] = None,
-                 steps_per_episode: Optional[int] = None, auto_reset: bool = False, collect_stats: bool = False):
+                 steps_per_episode: Optional[int] = None, auto_reset: bool = False, collect_stats: bool = False,
+                 track_episodes: bool = True, store_actions: bool = True):
         self.lib = _lib.load()
         _lib.require_device()
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
@@ -81,15 +82,17 @@ class BatchedPlatoons:
         self.headway = torch.zeros(M, P, **f32) if track_kinematics else None
         self.ou_state = torch.zeros(M, P, **f32)
         self.action_mu = torch.zeros(M, P, **f32)
-        self.action_out = torch.zeros(M, P, **f32)
+        self.action_out = torch.zeros(M, P, **f32) if store_actions else None
         self.leader_exog = torch.zeros(P, **f32)
         self.front_u = torch.zeros(P, **f32)
         self.front_accel = torch.zeros(P, **f32)
         self._reward = torch.zeros((P,) if self.centralized else (M, P), **f32)
         self._done = torch.zeros(P, dtype=torch.uint8, device=dev)
-        self.episode = torch.zeros(P, dtype=torch.int32, device=dev)
-        self.step_in_episode = torch.zeros(P, dtype=torch.int32, device=dev)
-        self.ep_reward = torch.zeros(M, P, **f32)
+        if auto_reset and not track_episodes:
+            raise ValueError("auto_reset needs track_episodes=True")
+        self.episode = torch.zeros(P, dtype=torch.int32, device=dev) if track_episodes else None
+        self.step_in_episode = torch.zeros(P, dtype=torch.int32, device=dev) if track_episodes else None
+        self.ep_reward = torch.zeros(M, P, **f32) if track_episodes else None
         self.stats = torch.zeros(M + 1, **f32) if collect_stats else None
         self.clock = clock if clock is not None else DeviceClock(dev)
         self.ring = ring
@@ -148,13 +151,18 @@ class BatchedPlatoons:
     def set_state(self, x, front_accel=None, front_u=None):
         """Inject states: x[P, M, 3|4] = (ep, ev, a[, a_lead]).  With 3 columns a_lead is chained as
         Platoon.reset does (environment.py:291-294).  prev_x := x, kinematic sums := 0."""
-        x = torch.as_tensor(x, dtype=torch.float32, device=self.device)
+        def dev(v, shape):
+            if not torch.is_tensor(v):
+                v = np.asarray(v, dtype=np.float32)
+            return torch.as_tensor(v, dtype=torch.float32, device=self.device).reshape(shape)
+
+        x = dev(x, (self.P, self.M, -1)) if not torch.is_tensor(x) else x.to(self.device, torch.float32)
         if x.shape[:2] != (self.P, self.M):
             raise ValueError(f"expected [P={self.P}, M={self.M}, 3|4], got {tuple(x.shape)}")
         if front_accel is not None:
-            self.front_accel.copy_(torch.as_tensor(front_accel, dtype=torch.float32, device=self.device).reshape(self.P))
+            self.front_accel.copy_(dev(front_accel, self.P))
         if front_u is not None:
-            self.front_u.copy_(torch.as_tensor(front_u, dtype=torch.float32, device=self.device).reshape(self.P))
+            self.front_u.copy_(dev(front_u, self.P))
         full = torch.zeros(self.P, self.M, 4, dtype=torch.float32, device=self.device)
         full[..., : x.shape[-1]] = x
         if x.shape[-1] == 3:
@@ -164,7 +172,8 @@ class BatchedPlatoons:
         self.prev_a.copy_(self._x[self._cur][2])
         if self.cum_accel is not None:
             self.cum_accel.zero_()
-        self.step_in_episode.zero_()
+        if self.step_in_episode is not None:
+            self.step_in_episode.zero_()
         return self.obs
 
     def reset(self, mask=None):
@@ -187,7 +196,7 @@ class BatchedPlatoons:
         io.x_out = self._x[self._cur ^ 1].data_ptr()
         io.action_mu = self.action_mu.data_ptr()
         io.ou_state = self.ou_state.data_ptr() if explore else None
-        io.action_out = self.action_out.data_ptr()
+        io.action_out = None if self.action_out is None else self.action_out.data_ptr()
         io.clip_actions = int(explore if clip is None else clip)
         io.leader_exog = self.leader_exog.data_ptr() if leader_exog else None
         io.gen_exog = int(gen_exog)
@@ -208,10 +217,14 @@ class BatchedPlatoons:
         """Platoon.step for the whole batch.  actions: [P, M] (tensor or array); leader_exog: [P], scalar
         or None (None -> platoon.front_u / front_accel, or a fresh N(0, reset_max_u) draw when
         gen_exog=True, as workers/trainer.py:292-295 does).  Returns (obs[P,M,ns], reward[P,M], done[P])."""
+        if not torch.is_tensor(actions):
+            actions = np.asarray(actions, dtype=np.float32)
         a = torch.as_tensor(actions, dtype=torch.float32, device=self.device).reshape(self.P, self.M)
         self.action_mu.copy_(a.t())
         if leader_exog is not None:
-            self.leader_exog.copy_(torch.as_tensor(leader_exog, dtype=torch.float32, device=self.device).expand(self.P))
+            if not torch.is_tensor(leader_exog):
+                leader_exog = np.asarray(leader_exog, dtype=np.float32)
+            self.leader_exog.copy_(torch.as_tensor(leader_exog, dtype=torch.float32, device=self.device).reshape(-1).expand(self.P))
         self.step_native(explore=explore, clip=clip, leader_exog=leader_exog is not None, gen_exog=gen_exog)
         return self.obs, self.reward, self.done
 

@@ -147,7 +147,7 @@ def time_env_roofline(P_big, M, steps=20, warmup=5):
     from avddpg_b200.config import Config
     from avddpg_b200.environment import BatchedPlatoons
     conf = Config(pl_size=M, can_terminate=False)
-    env = BatchedPlatoons(P_big, M, conf, track_kinematics=False)
+    env = BatchedPlatoons(P_big, M, conf, track_kinematics=False, track_episodes=False, store_actions=False)
     env.reset()
     env.action_mu.normal_(0, 0.5)
     env.leader_exog.normal_(0, 0.1)

@@ -143,10 +143,17 @@ def test_large_batch_vs_oracle(mods, P, M, method):
     for k in range(12):
         a = np.clip(rs.normal(0, 1.2, (P, M)), -2.5, 2.5).astype(np.float32)
         w = rs.normal(0, 0.1, P).astype(np.float32)
+        pre = ora.st.x.copy()
         o, r, d = env.step(a, w)
         oo, ro, do = ora.step(a, w)
-        assert np.array_equal(d.cpu().numpy(), do), k
-        assert _normwise(o.cpu().numpy(), oo) <= REL and _normwise(r.cpu().numpy(), ro) <= REL
+        # a vehicle sitting within fp32 rounding of the terminal threshold may legitimately fall on either
+        # side of it in fp32 vs float64: leave those (a handful in 5e5 vehicles) out of the comparison
+        tie = (np.abs(np.abs(pre[..., 0]) - conf.max_ep) < 1e-4) | (np.abs(np.abs(pre[..., 1]) - conf.max_ev) < 1e-4)
+        assert tie.mean() < 1e-3
+        ok_pl = ~tie.any(axis=1)
+        assert np.array_equal(d.cpu().numpy()[ok_pl], do[ok_pl]), k
+        assert _normwise(o.cpu().numpy(), oo) <= REL
+        assert _normwise(np.where(tie, 0, r.cpu().numpy()), np.where(tie, 0, ro)) <= REL
     assert do.any() or P < 100
 
 
