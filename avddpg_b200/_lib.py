@@ -58,6 +58,26 @@ class EnvIO(C.Structure):
     ]
 
 
+class NetDims(C.Structure):
+    _fields_ = [("ns", C.c_int32), ("l1", C.c_int32), ("la", C.c_int32), ("l2", C.c_int32)]
+
+
+class LearnIO(C.Structure):
+    _fields_ = [
+        ("dims", NetDims), ("A", C.c_int32), ("apply_updates", C.c_int32), ("rows_per_agent", C.c_int64),
+        ("gamma", C.c_float), ("action_high", C.c_float), ("tau", C.c_float), ("actor_lr", C.c_float), ("critic_lr", C.c_float),
+        ("adam_beta1", C.c_float), ("adam_beta2", C.c_float), ("adam_eps", C.c_float),
+        ("s", C.c_void_p), ("a", C.c_void_p), ("r", C.c_void_p), ("s2", C.c_void_p),
+        ("actor", C.c_void_p), ("critic", C.c_void_p), ("t_actor", C.c_void_p), ("t_critic", C.c_void_p),
+        ("actor_grad", C.c_void_p), ("critic_grad", C.c_void_p),
+        ("actor_m", C.c_void_p), ("actor_v", C.c_void_p), ("critic_m", C.c_void_p), ("critic_v", C.c_void_p),
+        ("actor_t", C.c_void_p), ("critic_t", C.c_void_p),
+        ("apply_mask", C.c_void_p), ("loss", C.c_void_p),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
+        ("precision", C.c_int32), ("reserved0", C.c_int32),
+    ]
+
+
 class AvdError(RuntimeError):
     pass
 
@@ -87,6 +107,20 @@ SIGNATURES = {
     "avd_replay_gather": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "avd_replay_fill_synthetic": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_uint64, C.c_void_p]),
+    "avd_ddpg_param_counts": (C.c_int, [C.POINTER(NetDims), C.POINTER(C.c_int64)]),
+    "avd_ddpg_workspace_bytes": (C.c_int64, [C.POINTER(NetDims), C.c_int32, C.c_int64]),
+    "avd_ddpg_learn": (C.c_int, [C.POINTER(LearnIO), C.c_void_p]),
+    "avd_actor_forward": (C.c_int, [C.POINTER(NetDims), C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
+                                    C.c_float, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
+    "avd_critic_forward": (C.c_int, [C.POINTER(NetDims), C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
+    "avd_adam_apply": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_int32, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p]),
+    "avd_polyak_update": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_void_p]),
+    "avd_fed_reduce": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int64, C.c_int64,
+                                 C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "avd_fed_broadcast": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int64, C.c_int64,
+                                    C.c_void_p, C.c_int64, C.c_void_p]),
     "avd_rng_words": (C.c_int, [C.c_void_p, C.c_int64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64, C.c_void_p]),
     "avd_rng_normals": (C.c_int, [C.c_void_p, C.c_int64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64, C.c_void_p]),
 }
@@ -110,7 +144,7 @@ def load():
         fn.restype, fn.argtypes = res, args
     if lib.avd_abi_version() != ABI_VERSION:
         raise AvdError(f"ABI mismatch: library {lib.avd_abi_version()} vs binding {ABI_VERSION}")
-    for which, st in enumerate((EnvParams, EnvIO, Clock)):
+    for which, st in enumerate((EnvParams, EnvIO, Clock, NetDims, LearnIO)):
         if lib.avd_sizeof(which) != C.sizeof(st):
             raise AvdError(f"struct layout mismatch for {st.__name__}: C {lib.avd_sizeof(which)} vs ctypes {C.sizeof(st)}")
     _lib = lib

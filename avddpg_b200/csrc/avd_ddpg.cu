@@ -1,0 +1,764 @@
+// avd_ddpg.cu -- DDPG learn step for a population of agents (workers/trainer.py:472-508 + 345-356).
+//
+// Data flow (all launches batched over the A agents; rows of agent a are [a*R, (a+1)*R)):
+//   target actor(s')  -> a'      | layer1 -> GEMM(l1 x l2)      -> head(tanh)
+//   target critic(s',a') -> y    | layer1 -> GEMM((l1+la) x l2) -> head(+TD target r + gamma q')
+//   critic(s,a) -> q, dLc/dz2    | layer1 -> GEMM -> head-backward (MSE grad, head/BN/bias grads, dz2)
+//                                | wgrad GEMM (cat^T dz2), dgrad GEMM (dz2 W2^T), layer1-backward
+//   actor(s) -> pi ; critic(s,pi)| layer1 -> GEMM -> head ; layer1 -> GEMM -> head-backward(action only)
+//                                | dgrad (action columns) -> d pi ; actor head-backward, wgrad, dgrad, layer1-backward
+//   Adam x2 (TF-Keras form), Polyak x2
+// The three big contractions (forward, wgrad, dgrad on the l1 x l2 and (l1+la) x l2 layers, 97% of the FLOPs)
+// go through `gemm_batched`, which dispatches on io->precision: 0 = fp32 SIMT tiles (parity mode, this
+// file), 1 = bf16 tcgen05/TMEM tensor-core kernels (avd_umma.cu).  Everything else (K=ns and K=1 layers,
+// heads with N=1, BatchNorm affine, reductions for bias/BN gradients, TD target, losses) is fused into the
+// layer1 / head kernels below.
+//
+// BatchNormalization is always the inference affine (models are never called with training=True):
+//   y = g*(x-mu)/sqrt(var+1e-3)+be, with trainable g/be and frozen mu/var.
+#include <algorithm>
+
+#include "avd_common.cuh"
+#include "avd_ddpg_layout.cuh"
+
+namespace avd {
+
+// ------------------------------------------------------------------------------------------------
+// layer 1: H[n][f] = bn(relu(x[n] . W[:,f] + b[f]))   (state columns, then -- critic -- action columns)
+// ------------------------------------------------------------------------------------------------
+constexpr int kL1Rows = 32;
+
+template <bool CRITIC>
+__global__ void __launch_bounds__(128) l1_forward_kernel(avd_net_dims d, const float* __restrict__ params, int64_t pstride,
+                                                         const float* __restrict__ s, int64_t s_rs, int64_t s_cs,
+                                                         const float* __restrict__ act, int64_t R, float* __restrict__ H) {
+    const int agent = blockIdx.y;
+    const float* P = params + (int64_t)agent * pstride;
+    const int F = CRITIC ? d.l1 + d.la : d.l1;
+    const int64_t row0 = (int64_t)blockIdx.x * kL1Rows;
+    const int nrows = (int)min((int64_t)kL1Rows, R - row0);
+    const int64_t base = (int64_t)agent * R + row0;
+    __shared__ float xs[kL1Rows][9];  // up to 8 state words + action
+    for (int i = threadIdx.x; i < nrows * (d.ns + (CRITIC ? 1 : 0)); i += blockDim.x) {
+        const int r = i / (d.ns + (CRITIC ? 1 : 0)), k = i % (d.ns + (CRITIC ? 1 : 0));
+        xs[r][k] = (k < d.ns) ? s[(base + r) * s_rs + k * s_cs] : act[base + r];
+    }
+    __syncthreads();
+    int64_t oW, ob, og, obe, omu, ovar;
+    for (int f = threadIdx.x; f < F; f += blockDim.x) {
+        const bool is_act = CRITIC && f >= d.l1;
+        const int c = is_act ? f - d.l1 : f;
+        if (CRITIC) {
+            const CriticOff o = critic_off(d);
+            oW = is_act ? o.Wa : o.Ws; ob = is_act ? o.ba : o.bs; og = is_act ? o.ga : o.gs; obe = is_act ? o.bea : o.bes;
+            omu = is_act ? o.mua : o.mus; ovar = is_act ? o.vara : o.vars;
+        } else {
+            const ActorOff o = actor_off(d);
+            oW = o.W1; ob = o.b1; og = o.g1; obe = o.be1; omu = o.mu1; ovar = o.var1;
+        }
+        const int width = is_act ? d.la : d.l1;
+        const int nin = is_act ? 1 : d.ns;
+        float w[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) w[k] = (k < nin) ? P[oW + (int64_t)k * width + c] : 0.0f;
+        const float b = P[ob + c];
+        const float inv = 1.0f / sqrtf(P[ovar + c] + kBnEps);
+        const float sc = P[og + c] * inv, sh = P[obe + c] - P[omu + c] * sc;
+        for (int r = 0; r < nrows; ++r) {
+            float z = b;
+            if (is_act) {
+                z = fmaf(xs[r][d.ns], w[0], z);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    if (k < nin) z = fmaf(xs[r][k], w[k], z);
+            }
+            H[(base + r) * F + f] = fmaf(fmaxf(z, 0.0f), sc, sh);
+        }
+    }
+}
+
+// layer-1 backward: from dH[n][f] accumulate dW, db, dg, dbe (atomics, one set per CTA and column)
+template <bool CRITIC>
+__global__ void __launch_bounds__(128) l1_backward_kernel(avd_net_dims d, const float* __restrict__ params, int64_t pstride,
+                                                          const float* __restrict__ s, const float* __restrict__ act, int64_t R,
+                                                          const float* __restrict__ dH, float* __restrict__ grads, int64_t gstride) {
+    constexpr int ROWS = 64;
+    const int agent = blockIdx.y;
+    const float* P = params + (int64_t)agent * pstride;
+    float* G = grads + (int64_t)agent * gstride;
+    const int F = CRITIC ? d.l1 + d.la : d.l1;
+    const int64_t row0 = (int64_t)blockIdx.x * ROWS;
+    const int nrows = (int)min((int64_t)ROWS, R - row0);
+    const int64_t base = (int64_t)agent * R + row0;
+    __shared__ float xs[ROWS][9];
+    const int nx = d.ns + (CRITIC ? 1 : 0);
+    for (int i = threadIdx.x; i < nrows * nx; i += blockDim.x) {
+        const int r = i / nx, k = i % nx;
+        xs[r][k] = (k < d.ns) ? s[(base + r) * d.ns + k] : act[base + r];
+    }
+    __syncthreads();
+    int64_t oW, ob, og, obe, omu, ovar;
+    for (int f = threadIdx.x; f < F; f += blockDim.x) {
+        const bool is_act = CRITIC && f >= d.l1;
+        const int c = is_act ? f - d.l1 : f;
+        if (CRITIC) {
+            const CriticOff o = critic_off(d);
+            oW = is_act ? o.Wa : o.Ws; ob = is_act ? o.ba : o.bs; og = is_act ? o.ga : o.gs; obe = is_act ? o.bea : o.bes;
+            omu = is_act ? o.mua : o.mus; ovar = is_act ? o.vara : o.vars;
+        } else {
+            const ActorOff o = actor_off(d);
+            oW = o.W1; ob = o.b1; og = o.g1; obe = o.be1; omu = o.mu1; ovar = o.var1;
+        }
+        const int width = is_act ? d.la : d.l1;
+        const int nin = is_act ? 1 : d.ns;
+        float w[8], dw[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { w[k] = (k < nin) ? P[oW + (int64_t)k * width + c] : 0.0f; dw[k] = 0.0f; }
+        const float b = P[ob + c], mu = P[omu + c];
+        const float inv = 1.0f / sqrtf(P[ovar + c] + kBnEps);
+        const float ginv = P[og + c] * inv;
+        float db = 0.0f, dg = 0.0f, dbe = 0.0f;
+        for (int r = 0; r < nrows; ++r) {
+            const float dh = dH[(base + r) * F + f];
+            float z = b;
+            if (is_act) {
+                z = fmaf(xs[r][d.ns], w[0], z);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    if (k < nin) z = fmaf(xs[r][k], w[k], z);
+            }
+            const float rl = fmaxf(z, 0.0f);
+            dg = fmaf(dh, (rl - mu) * inv, dg);
+            dbe += dh;
+            const float dz = z > 0.0f ? dh * ginv : 0.0f;
+            db += dz;
+            if (is_act) {
+                dw[0] = fmaf(xs[r][d.ns], dz, dw[0]);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    if (k < nin) dw[k] = fmaf(xs[r][k], dz, dw[k]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (k < nin) atomicAdd(G + oW + (int64_t)k * width + c, dw[k]);
+        atomicAdd(G + ob + c, db);
+        atomicAdd(G + og + c, dg);
+        atomicAdd(G + obe + c, dbe);
+    }
+}
+
+// d(action)[n] = sum_f dza[n][f] * Wa[f], dza = dHa * ga*inva * (za > 0): the critic -> actor link (trainer.py:503-506)
+__global__ void __launch_bounds__(256) action_grad_kernel(avd_net_dims d, const float* __restrict__ params, int64_t pstride,
+                                                          const float* __restrict__ act, int64_t R, const float* __restrict__ dHa,
+                                                          float* __restrict__ dact) {
+    const CriticOff o = critic_off(d);
+    const int agent = blockIdx.y;
+    const float* P = params + (int64_t)agent * pstride;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int64_t r = (int64_t)blockIdx.x * nw + wid; r < R; r += (int64_t)gridDim.x * nw) {
+        const int64_t n = (int64_t)agent * R + r;
+        const float a = act[n];
+        float acc = 0.0f;
+        for (int f = lane; f < d.la; f += 32) {
+            const float wa = P[o.Wa + f];
+            const float z = fmaf(a, wa, P[o.ba + f]);
+            const float ginv = P[o.ga + f] / sqrtf(P[o.vara + f] + kBnEps);
+            const float dz = z > 0.0f ? dHa[n * d.la + f] * ginv : 0.0f;
+            acc = fmaf(dz, wa, acc);
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) dact[n] = acc;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// heads: everything after the l2-wide GEMM.  One warp per row, lane owns columns lane, lane+32, ...
+// ------------------------------------------------------------------------------------------------
+enum HeadMode { HEAD_ACTOR_FWD = 0, HEAD_CRITIC_TARGET = 1, HEAD_CRITIC_Q = 2, HEAD_CRITIC_BWD = 3, HEAD_CRITIC_BWD_ACTION = 4, HEAD_ACTOR_BWD = 5 };
+
+struct HeadArgs {
+    const float* params;   // [A][pstride]
+    int64_t pstride;
+    int64_t o_b2, o_g2, o_be2, o_mu2, o_var2, o_W3, o_b3;
+    const float* Z;        // [A*R][L2] raw GEMM output (bias not yet added)
+    int64_t R;
+    float high, gamma;
+    const float* rew;      // TARGET
+    const float* y;        // CRITIC_BWD
+    const float* dpi;      // ACTOR_BWD
+    float* out;            // ACTOR_FWD: action, TARGET: y, Q/BWD: q (nullable for BWD)
+    float* DZ;             // BWD modes
+    float* grads;          // [A][gstride] (BWD, ACTOR_BWD)
+    int64_t gstride;
+    float* loss;           // [A][2] nullable
+};
+
+template <int MODE, int CPL>   // CPL = columns per lane (l2 = 32*CPL)
+__global__ void __launch_bounds__(256) head_kernel(HeadArgs h) {
+    constexpr int L2 = 32 * CPL;
+    constexpr int ROWS = 64;
+    constexpr bool BWD = MODE == HEAD_CRITIC_BWD || MODE == HEAD_ACTOR_BWD;
+    const int agent = blockIdx.y;
+    const float* P = h.params + (int64_t)agent * h.pstride;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int64_t row0 = (int64_t)blockIdx.x * ROWS;
+    const int nrows = (int)min((int64_t)ROWS, h.R - row0);
+    float b2[CPL], sc[CPL], sh[CPL], inv[CPL], mu[CPL], w3[CPL], ginv[CPL];
+    float aW3[CPL], aG[CPL], aBe[CPL], aB2[CPL];
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) {
+        const int c = lane + 32 * j;
+        b2[j] = P[h.o_b2 + c];
+        inv[j] = 1.0f / sqrtf(P[h.o_var2 + c] + kBnEps);
+        mu[j] = P[h.o_mu2 + c];
+        ginv[j] = P[h.o_g2 + c] * inv[j];
+        sc[j] = ginv[j];
+        sh[j] = P[h.o_be2 + c] - mu[j] * sc[j];
+        w3[j] = P[h.o_W3 + c];
+        aW3[j] = aG[j] = aBe[j] = aB2[j] = 0.0f;
+    }
+    const float b3 = P[h.o_b3];
+    const float invR = 1.0f / (float)h.R;
+    float aB3 = 0.0f, aLoss = 0.0f;
+    for (int r = wid; r < nrows; r += 8) {
+        const int64_t n = (int64_t)agent * h.R + row0 + r;
+        float z[CPL], hh[CPL];
+        float part = 0.0f;
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) {
+            z[j] = h.Z[n * L2 + lane + 32 * j] + b2[j];
+            hh[j] = fmaf(fmaxf(z[j], 0.0f), sc[j], sh[j]);
+            part = fmaf(hh[j], w3[j], part);
+        }
+        const float pre = warp_sum(part) + b3;
+        if (MODE == HEAD_ACTOR_FWD) {
+            if (lane == 0) h.out[n] = h.high * tanhf(pre);
+        } else if (MODE == HEAD_CRITIC_TARGET) {
+            if (lane == 0) h.out[n] = h.rew[n] + h.gamma * pre;   // trainer.py:494 (no terminal mask)
+        } else if (MODE == HEAD_CRITIC_Q) {
+            if (lane == 0) h.out[n] = pre;
+        } else {
+            float dq;
+            if (MODE == HEAD_CRITIC_BWD) {
+                const float diff = pre - h.y[n];
+                dq = 2.0f * diff * invR;                           // d mean((y-q)^2) / dq
+                aLoss = fmaf(diff, diff * invR, aLoss);
+                if (h.out && lane == 0) h.out[n] = pre;
+            } else if (MODE == HEAD_CRITIC_BWD_ACTION) {
+                dq = -invR;                                        // d(-mean(q)) / dq
+                aLoss -= pre * invR;
+            } else {  // HEAD_ACTOR_BWD
+                const float t = tanhf(pre);
+                dq = h.dpi[n] * h.high * (1.0f - t * t);
+            }
+            if (BWD) aB3 += dq;
+#pragma unroll
+            for (int j = 0; j < CPL; ++j) {
+                const float dh = dq * w3[j];
+                const float dz = z[j] > 0.0f ? dh * ginv[j] : 0.0f;
+                h.DZ[n * L2 + lane + 32 * j] = dz;
+                if (BWD) {
+                    aW3[j] = fmaf(hh[j], dq, aW3[j]);
+                    aG[j] = fmaf(dh, (fmaxf(z[j], 0.0f) - mu[j]) * inv[j], aG[j]);
+                    aBe[j] += dh;
+                    aB2[j] += dz;
+                }
+            }
+        }
+    }
+    if (MODE == HEAD_CRITIC_BWD || MODE == HEAD_CRITIC_BWD_ACTION || MODE == HEAD_ACTOR_BWD) {
+        __shared__ float red[8][L2];
+        __shared__ float red1[8][2];
+        float* G = BWD ? h.grads + (int64_t)agent * h.gstride : nullptr;
+        if (BWD) {
+            const int64_t offs[4] = {h.o_W3, h.o_g2, h.o_be2, h.o_b2};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+#pragma unroll
+                for (int j = 0; j < CPL; ++j) red[wid][lane + 32 * j] = (q == 0 ? aW3[j] : q == 1 ? aG[j] : q == 2 ? aBe[j] : aB2[j]);
+                __syncthreads();
+                if (threadIdx.x < L2) {
+                    float s = 0.0f;
+#pragma unroll
+                    for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+                    atomicAdd(G + offs[q] + threadIdx.x, s);
+                }
+                __syncthreads();
+            }
+        }
+        if (lane == 0) { red1[wid][0] = aB3; red1[wid][1] = aLoss; }   // lane 0 holds the row-level sums (all lanes equal)
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float sb = 0.0f, sl = 0.0f;
+            for (int w = 0; w < 8; ++w) { sb += red1[w][0]; sl += red1[w][1]; }
+            if (BWD) atomicAdd(G + h.o_b3, sb);
+            if (h.loss && MODE != HEAD_ACTOR_BWD) atomicAdd(h.loss + 2 * agent + (MODE == HEAD_CRITIC_BWD ? 0 : 1), sl);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fp32 SIMT GEMM, strided + batched: C[b] (MxN) (+)= A[b] (MxK) B[b] (KxN).  64x64x16 tiles, 4x4 per thread.
+// ------------------------------------------------------------------------------------------------
+struct GemmArgs {
+    const float* A; int64_t a_m, a_k, a_batch;   // element (m,k) at A[b*a_batch + m*a_m + k*a_k]
+    const float* B; int64_t b_k, b_n, b_batch;
+    float* C; int64_t c_m, c_n, c_batch;
+    int M, N, K, splitk;
+};
+
+template <bool A_KCONTIG, bool B_NCONTIG>
+__global__ void __launch_bounds__(256) sgemm_kernel(GemmArgs g) {
+    constexpr int BM = 64, BN = 64, BK = 16;
+    __shared__ float As[BK][BM + 4];
+    __shared__ float Bs[BK][BN + 4];
+    const int batch = blockIdx.z / g.splitk, split = blockIdx.z % g.splitk;
+    const float* A = g.A + (int64_t)batch * g.a_batch;
+    const float* B = g.B + (int64_t)batch * g.b_batch;
+    float* C = g.C + (int64_t)batch * g.c_batch;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int kchunk = (((g.K + g.splitk - 1) / g.splitk) + BK - 1) / BK * BK;
+    const int kbeg = split * kchunk, kend = min(g.K, kbeg + kchunk);
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    float acc[4][4] = {};
+    for (int k0 = kbeg; k0 < kend; k0 += BK) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int e = threadIdx.x + i * 256;
+            int m, k;
+            if (A_KCONTIG) { k = e & 15; m = e >> 4; } else { m = e & 63; k = e >> 6; }
+            const int gm = m0 + m, gk = k0 + k;
+            As[k][m] = (gm < g.M && gk < kend) ? A[(int64_t)gm * g.a_m + (int64_t)gk * g.a_k] : 0.0f;
+            int n, kb;
+            if (B_NCONTIG) { n = e & 63; kb = e >> 6; } else { kb = e & 15; n = e >> 4; }
+            const int gn = n0 + n, gkb = k0 + kb;
+            Bs[kb][n] = (gn < g.N && gkb < kend) ? B[(int64_t)gkb * g.b_k + (int64_t)gn * g.b_n] : 0.0f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+            float a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { a[i] = As[k][ty * 4 + i]; b[i] = Bs[k][tx * 4 + i]; }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int gm = m0 + ty * 4 + i;
+        if (gm >= g.M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int gn = n0 + tx * 4 + j;
+            if (gn >= g.N) continue;
+            float* dst = C + (int64_t)gm * g.c_m + (int64_t)gn * g.c_n;
+            if (g.splitk > 1) atomicAdd(dst, acc[i][j]); else *dst = acc[i][j];
+        }
+    }
+}
+
+static int launch_sgemm(const GemmArgs& g, int nbatch, cudaStream_t st) {
+    dim3 grid((g.N + 63) / 64, (g.M + 63) / 64, nbatch * g.splitk);
+    const bool ak = g.a_k == 1, bn = g.b_n == 1;
+    if (ak && bn) sgemm_kernel<true, true><<<grid, 256, 0, st>>>(g);
+    else if (ak && !bn) sgemm_kernel<true, false><<<grid, 256, 0, st>>>(g);
+    else if (!ak && bn) sgemm_kernel<false, true><<<grid, 256, 0, st>>>(g);
+    else sgemm_kernel<false, false><<<grid, 256, 0, st>>>(g);
+    AVD_LAUNCH_OK();
+    return AVD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// optimiser, targets, federated reductions
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ params, int64_t pstride, const float* __restrict__ grads,
+                                                   int64_t gstride, float* __restrict__ m, float* __restrict__ v,
+                                                   const int32_t* __restrict__ step, const uint8_t* __restrict__ mask, int64_t n,
+                                                   float lr, float b1, float b2, float eps) {
+    const int agent = blockIdx.y;
+    if (mask && !mask[agent]) return;
+    const float t = (float)(step[agent] + 1);
+    const float lr_t = lr * sqrtf(1.0f - powf(b2, t)) / (1.0f - powf(b1, t));
+    float* P = params + (int64_t)agent * pstride;
+    const float* G = grads + (int64_t)agent * gstride;
+    float* Mm = m + (int64_t)agent * n;
+    float* Vv = v + (int64_t)agent * n;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float g = G[i];
+        const float mi = Mm[i] + (g - Mm[i]) * (1.0f - b1);
+        const float vi = Vv[i] + (g * g - Vv[i]) * (1.0f - b2);
+        Mm[i] = mi;
+        Vv[i] = vi;
+        P[i] -= lr_t * mi / (sqrtf(vi) + eps);
+    }
+}
+
+__global__ void step_increment_kernel(int32_t* step, const uint8_t* mask, int A) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a < A && (!mask || mask[a])) step[a] += 1;
+}
+
+__global__ void __launch_bounds__(256) polyak_kernel(float* __restrict__ target, const float* __restrict__ online,
+                                                     const uint8_t* __restrict__ mask, int64_t n, float tau) {
+    const int agent = blockIdx.y;
+    if (mask && !mask[agent]) return;
+    float* T = target + (int64_t)agent * n;
+    const float* O = online + (int64_t)agent * n;
+    const float omt = 1.0f - tau;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        T[i] = O[i] * tau + T[i] * omt;   // ddpgagent.py:46,53: variable * tau + target * (1 - tau)
+}
+
+__global__ void __launch_bounds__(256) fed_reduce_kernel(float* __restrict__ out, int64_t out_pitch, const float* __restrict__ in,
+                                                         int64_t pitch, int n_members, int64_t stride_s, int64_t stride_x,
+                                                         const float* __restrict__ weights, const float* __restrict__ scale, int64_t n) {
+    const int s = blockIdx.y;
+    const float sc = scale ? scale[s] : 1.0f / (float)n_members;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float acc = 0.0f;
+        for (int x = 0; x < n_members; ++x) {
+            const float w = weights ? weights[(int64_t)s * n_members + x] : 1.0f;
+            acc = fmaf(w, in[((int64_t)s * stride_s + (int64_t)x * stride_x) * pitch + i], acc);
+        }
+        out[(int64_t)s * out_pitch + i] = sc * acc;
+    }
+}
+
+__global__ void __launch_bounds__(256) fed_broadcast_kernel(float* __restrict__ out, int64_t out_pitch, const float* __restrict__ in,
+                                                            int64_t in_pitch, int n_members, int64_t stride_s, int64_t stride_x,
+                                                            const uint8_t* __restrict__ mask, int64_t n) {
+    const int s = blockIdx.y, x = blockIdx.z;
+    const int64_t member = (int64_t)s * stride_s + (int64_t)x * stride_x;
+    if (mask && !mask[member]) return;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[member * out_pitch + i] = in[(int64_t)s * in_pitch + i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// host orchestration
+// ------------------------------------------------------------------------------------------------
+struct Workspace {
+    float *H, *H1a, *Z, *Za, *DZ, *DH, *a2, *y, *q, *dpi;
+    static int64_t floats(const avd_net_dims& d, int64_t N) {
+        return N * (2 * (int64_t)(d.l1 + d.la) + d.l1 + 3 * (int64_t)d.l2 + 4);
+    }
+    void carve(float* base, const avd_net_dims& d, int64_t N) {
+        float* p = base;
+        H = p; p += N * (d.l1 + d.la);
+        DH = p; p += N * (d.l1 + d.la);
+        H1a = p; p += N * d.l1;
+        Z = p; p += N * d.l2;
+        Za = p; p += N * d.l2;
+        DZ = p; p += N * d.l2;
+        a2 = p; p += N;
+        y = p; p += N;
+        q = p; p += N;
+        dpi = p; p += N;
+    }
+};
+
+static int check_dims(const avd_net_dims* d) {
+    AVD_REQUIRE(d, "null dims");
+    AVD_REQUIRE(d->ns >= 1 && d->ns <= 8, "ns=%d outside 1..8", d->ns);
+    AVD_REQUIRE(d->l1 >= 1 && d->la >= 1, "bad layer sizes");
+    if (d->l2 != 32 && d->l2 != 64 && d->l2 != 96 && d->l2 != 128) {
+        set_error("layer2 size %d not supported (32, 64, 96 or 128)", d->l2);
+        return AVD_ERR_UNSUPPORTED;
+    }
+    return AVD_OK;
+}
+
+template <int MODE>
+static int launch_head(const HeadArgs& h, int l2, int A, cudaStream_t st) {
+    dim3 grid((unsigned)((h.R + 63) / 64), A);
+    switch (l2 / 32) {
+        case 1: head_kernel<MODE, 1><<<grid, 256, 0, st>>>(h); break;
+        case 2: head_kernel<MODE, 2><<<grid, 256, 0, st>>>(h); break;
+        case 3: head_kernel<MODE, 3><<<grid, 256, 0, st>>>(h); break;
+        default: head_kernel<MODE, 4><<<grid, 256, 0, st>>>(h); break;
+    }
+    AVD_LAUNCH_OK();
+    return AVD_OK;
+}
+
+static HeadArgs actor_head(const avd_net_dims& d, const float* params, const float* Z, int64_t R, float high) {
+    const ActorOff o = actor_off(d);
+    HeadArgs h = {};
+    h.params = params; h.pstride = o.total;
+    h.o_b2 = o.b2; h.o_g2 = o.g2; h.o_be2 = o.be2; h.o_mu2 = o.mu2; h.o_var2 = o.var2; h.o_W3 = o.W3; h.o_b3 = o.b3;
+    h.Z = Z; h.R = R; h.high = high;
+    return h;
+}
+
+static HeadArgs critic_head(const avd_net_dims& d, const float* params, const float* Z, int64_t R) {
+    const CriticOff o = critic_off(d);
+    HeadArgs h = {};
+    h.params = params; h.pstride = o.total;
+    h.o_b2 = o.b2; h.o_g2 = o.g2; h.o_be2 = o.be2; h.o_mu2 = o.mu2; h.o_var2 = o.var2; h.o_W3 = o.W3; h.o_b3 = o.b3;
+    h.Z = Z; h.R = R;
+    return h;
+}
+
+// C[a] (R x l2) = H[a] (R x F) . W2[a] (F x l2)
+static int gemm_forward(const float* H, int F, const float* params, int64_t pstride, int64_t oW2, float* Z, int l2, int A, int64_t R,
+                        cudaStream_t st) {
+    GemmArgs g = {};
+    g.A = H; g.a_m = F; g.a_k = 1; g.a_batch = R * F;
+    g.B = params + oW2; g.b_k = l2; g.b_n = 1; g.b_batch = pstride;
+    g.C = Z; g.c_m = l2; g.c_n = 1; g.c_batch = R * l2;
+    g.M = (int)R; g.N = l2; g.K = F; g.splitk = 1;
+    return launch_sgemm(g, A, st);
+}
+
+// dW2[a] (F x l2) += H[a]^T (F x R) . DZ[a] (R x l2)   (split-K over rows, atomics into pre-zeroed grads)
+static int gemm_wgrad(const float* H, int F, const float* DZ, float* grads, int64_t gstride, int64_t oW2, int l2, int A, int64_t R,
+                      cudaStream_t st) {
+    GemmArgs g = {};
+    g.A = H; g.a_m = 1; g.a_k = F; g.a_batch = R * F;
+    g.B = DZ; g.b_k = l2; g.b_n = 1; g.b_batch = R * l2;
+    g.C = grads + oW2; g.c_m = l2; g.c_n = 1; g.c_batch = gstride;
+    g.M = F; g.N = l2; g.K = (int)R;
+    const int tiles = ((F + 63) / 64) * ((l2 + 63) / 64) * A;
+    int split = (int)std::min<int64_t>((R + 255) / 256, std::max(1, 2 * sm_count() / std::max(1, tiles)));
+    g.splitk = std::max(1, split);
+    return launch_sgemm(g, A, st);
+}
+
+// DH[a] (R x Fsub) = DZ[a] (R x l2) . W2[a][f0:f0+Fsub, :]^T
+static int gemm_dgrad(const float* DZ, const float* params, int64_t pstride, int64_t oW2, int f0, int Fsub, float* DH, int l2, int A,
+                      int64_t R, cudaStream_t st) {
+    GemmArgs g = {};
+    g.A = DZ; g.a_m = l2; g.a_k = 1; g.a_batch = R * l2;
+    g.B = params + oW2 + (int64_t)f0 * l2; g.b_k = 1; g.b_n = l2; g.b_batch = pstride;
+    g.C = DH; g.c_m = Fsub; g.c_n = 1; g.c_batch = R * Fsub;
+    g.M = (int)R; g.N = Fsub; g.K = l2; g.splitk = 1;
+    return launch_sgemm(g, A, st);
+}
+
+}  // namespace avd
+
+using namespace avd;
+
+extern "C" int avd_ddpg_param_counts(const avd_net_dims* dims, int64_t* out4) {
+    if (int rc = check_dims(dims)) return rc;
+    AVD_REQUIRE(out4, "null out");
+    const ActorOff a = actor_off(*dims);
+    const CriticOff c = critic_off(*dims);
+    out4[0] = a.n_train; out4[1] = a.total; out4[2] = c.n_train; out4[3] = c.total;
+    return AVD_OK;
+}
+
+extern "C" int64_t avd_ddpg_workspace_bytes(const avd_net_dims* dims, int32_t A, int64_t rows_per_agent) {
+    if (!dims || A < 0 || rows_per_agent < 0) return -1;
+    return Workspace::floats(*dims, (int64_t)A * rows_per_agent) * (int64_t)sizeof(float) + 256;
+}
+
+#define AVD_TRY(expr)             \
+    do {                          \
+        int _rc = (expr);         \
+        if (_rc) return _rc;      \
+    } while (0)
+
+extern "C" int avd_actor_forward(const avd_net_dims* dims, int32_t A, int64_t R, const float* actor_params, const float* s,
+                                 int64_t s_rs, int64_t s_cs, float action_high, float* out, void* workspace,
+                                 int64_t workspace_bytes, int32_t precision, void* stream) {
+    AVD_TRY(check_dims(dims));
+    AVD_REQUIRE(actor_params && s && out && workspace, "null buffer");
+    AVD_REQUIRE(A >= 0 && R >= 0, "bad sizes");
+    AVD_REQUIRE(precision == 0, "precision %d not available in this build", precision);
+    const avd_net_dims d = *dims;
+    const int64_t N = (int64_t)A * R;
+    AVD_REQUIRE(workspace_bytes >= N * (d.l1 + d.l2) * (int64_t)sizeof(float), "workspace too small");
+    if (N == 0) return AVD_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const ActorOff o = actor_off(d);
+    float* H = (float*)workspace;
+    float* Z = H + N * d.l1;
+    l1_forward_kernel<false><<<dim3((unsigned)((R + kL1Rows - 1) / kL1Rows), A), 128, 0, st>>>(d, actor_params, o.total, s, s_rs, s_cs, nullptr, R, H);
+    AVD_LAUNCH_OK();
+    AVD_TRY(gemm_forward(H, d.l1, actor_params, o.total, o.W2, Z, d.l2, A, R, st));
+    HeadArgs h = actor_head(d, actor_params, Z, R, action_high);
+    h.out = out;
+    return launch_head<HEAD_ACTOR_FWD>(h, d.l2, A, st);
+}
+
+extern "C" int avd_critic_forward(const avd_net_dims* dims, int32_t A, int64_t R, const float* critic_params, const float* s,
+                                  const float* a, float* q, void* workspace, int64_t workspace_bytes, int32_t precision,
+                                  void* stream) {
+    AVD_TRY(check_dims(dims));
+    AVD_REQUIRE(critic_params && s && a && q && workspace, "null buffer");
+    AVD_REQUIRE(A >= 0 && R >= 0, "bad sizes");
+    AVD_REQUIRE(precision == 0, "precision %d not available in this build", precision);
+    const avd_net_dims d = *dims;
+    const int64_t N = (int64_t)A * R;
+    const int F = d.l1 + d.la;
+    AVD_REQUIRE(workspace_bytes >= N * (F + d.l2) * (int64_t)sizeof(float), "workspace too small");
+    if (N == 0) return AVD_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const CriticOff o = critic_off(d);
+    float* H = (float*)workspace;
+    float* Z = H + N * F;
+    l1_forward_kernel<true><<<dim3((unsigned)((R + kL1Rows - 1) / kL1Rows), A), 128, 0, st>>>(d, critic_params, o.total, s, d.ns, 1, a, R, H);
+    AVD_LAUNCH_OK();
+    AVD_TRY(gemm_forward(H, F, critic_params, o.total, o.W2, Z, d.l2, A, R, st));
+    HeadArgs h = critic_head(d, critic_params, Z, R);
+    h.out = q;
+    return launch_head<HEAD_CRITIC_Q>(h, d.l2, A, st);
+}
+
+extern "C" int avd_adam_apply(float* params, int64_t param_stride, const float* grads, int64_t grad_agent_stride, float* m, float* v,
+                              int32_t* step, const uint8_t* apply_mask, int32_t A, int64_t n, float lr, float beta1, float beta2,
+                              float eps, void* stream) {
+    AVD_REQUIRE(params && grads && m && v && step, "null buffer");
+    AVD_REQUIRE(A >= 0 && n >= 0 && param_stride >= n, "bad sizes");
+    if (A == 0 || n == 0) return AVD_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int gx = (int)std::min<int64_t>((n + 255) / 256, 64);
+    adam_kernel<<<dim3(gx, A), 256, 0, st>>>(params, param_stride, grads, grad_agent_stride, m, v, step, apply_mask, n, lr, beta1, beta2, eps);
+    AVD_LAUNCH_OK();
+    step_increment_kernel<<<(A + 127) / 128, 128, 0, st>>>(step, apply_mask, A);
+    AVD_LAUNCH_OK();
+    return AVD_OK;
+}
+
+extern "C" int avd_polyak_update(float* target, const float* online, const uint8_t* apply_mask, int32_t A, int64_t n, float tau,
+                                 void* stream) {
+    AVD_REQUIRE(target && online, "null buffer");
+    AVD_REQUIRE(A >= 0 && n >= 0, "bad sizes");
+    if (A == 0 || n == 0) return AVD_OK;
+    const int gx = (int)std::min<int64_t>((n + 255) / 256, 64);
+    polyak_kernel<<<dim3(gx, A), 256, 0, (cudaStream_t)stream>>>(target, online, apply_mask, n, tau);
+    AVD_LAUNCH_OK();
+    return AVD_OK;
+}
+
+extern "C" int avd_fed_reduce(float* out, int64_t out_pitch, const float* in, int64_t pitch, int32_t n_systems, int32_t n_members,
+                              int64_t member_stride_s, int64_t member_stride_x, const float* weights, const float* scale, int64_t n,
+                              void* stream) {
+    AVD_REQUIRE(out && in, "null buffer");
+    AVD_REQUIRE(n_systems >= 0 && n_members >= 1 && n >= 0, "bad sizes");
+    if (n_systems == 0 || n == 0) return AVD_OK;
+    const int gx = (int)std::min<int64_t>((n + 255) / 256, 128);
+    fed_reduce_kernel<<<dim3(gx, n_systems), 256, 0, (cudaStream_t)stream>>>(out, out_pitch, in, pitch, n_members, member_stride_s,
+                                                                              member_stride_x, weights, scale, n);
+    AVD_LAUNCH_OK();
+    return AVD_OK;
+}
+
+extern "C" int avd_fed_broadcast(float* out, int64_t out_pitch, const float* in, int64_t in_pitch, int32_t n_systems, int32_t n_members,
+                                 int64_t member_stride_s, int64_t member_stride_x, const uint8_t* apply_mask, int64_t n, void* stream) {
+    AVD_REQUIRE(out && in, "null buffer");
+    AVD_REQUIRE(n_systems >= 0 && n_members >= 1 && n >= 0, "bad sizes");
+    if (n_systems == 0 || n == 0) return AVD_OK;
+    const int gx = (int)std::min<int64_t>((n + 255) / 256, 64);
+    fed_broadcast_kernel<<<dim3(gx, n_systems, n_members), 256, 0, (cudaStream_t)stream>>>(out, out_pitch, in, in_pitch, n_members,
+                                                                                            member_stride_s, member_stride_x, apply_mask, n);
+    AVD_LAUNCH_OK();
+    return AVD_OK;
+}
+
+extern "C" int avd_ddpg_learn(const avd_learn_io* io, void* stream) {
+    AVD_REQUIRE(io, "null io");
+    AVD_TRY(check_dims(&io->dims));
+    AVD_REQUIRE(io->s && io->a && io->r && io->s2, "null batch");
+    AVD_REQUIRE(io->actor && io->critic && io->t_actor && io->t_critic && io->actor_grad && io->critic_grad, "null parameters");
+    AVD_REQUIRE(io->A >= 0 && io->rows_per_agent >= 1, "bad sizes");
+    AVD_REQUIRE(io->precision == 0, "precision %d not available in this build", io->precision);
+    AVD_REQUIRE(!io->apply_updates || (io->actor_m && io->actor_v && io->critic_m && io->critic_v && io->actor_t && io->critic_t),
+                "apply_updates needs Adam state");
+    const avd_net_dims d = io->dims;
+    const int A = io->A;
+    const int64_t R = io->rows_per_agent, N = (int64_t)A * R;
+    AVD_REQUIRE(io->workspace && io->workspace_bytes >= avd_ddpg_workspace_bytes(&d, A, R), "workspace too small");
+    if (A == 0) return AVD_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const ActorOff ao = actor_off(d);
+    const CriticOff co = critic_off(d);
+    const int F = d.l1 + d.la;
+    Workspace w;
+    uintptr_t base = ((uintptr_t)io->workspace + 255) & ~(uintptr_t)255;
+    w.carve((float*)base, d, N);
+    const dim3 gl1((unsigned)((R + kL1Rows - 1) / kL1Rows), A), gl1b((unsigned)((R + 63) / 64), A);
+
+    AVD_CUDA_OK(cudaMemsetAsync(io->actor_grad, 0, (size_t)A * ao.n_train * sizeof(float), st));
+    AVD_CUDA_OK(cudaMemsetAsync(io->critic_grad, 0, (size_t)A * co.n_train * sizeof(float), st));
+    if (io->loss) AVD_CUDA_OK(cudaMemsetAsync(io->loss, 0, (size_t)A * 2 * sizeof(float), st));
+
+    // ---- TD target: y = r + gamma * target_critic(s', target_actor(s'))            trainer.py:493-494
+    l1_forward_kernel<false><<<gl1, 128, 0, st>>>(d, io->t_actor, ao.total, io->s2, d.ns, 1, nullptr, R, w.H1a);
+    AVD_LAUNCH_OK();
+    AVD_TRY(gemm_forward(w.H1a, d.l1, io->t_actor, ao.total, ao.W2, w.Z, d.l2, A, R, st));
+    {
+        HeadArgs h = actor_head(d, io->t_actor, w.Z, R, io->action_high);
+        h.out = w.a2;
+        AVD_TRY(launch_head<HEAD_ACTOR_FWD>(h, d.l2, A, st));
+    }
+    l1_forward_kernel<true><<<gl1, 128, 0, st>>>(d, io->t_critic, co.total, io->s2, d.ns, 1, w.a2, R, w.H);
+    AVD_LAUNCH_OK();
+    AVD_TRY(gemm_forward(w.H, F, io->t_critic, co.total, co.W2, w.Z, d.l2, A, R, st));
+    {
+        HeadArgs h = critic_head(d, io->t_critic, w.Z, R);
+        h.rew = io->r; h.gamma = io->gamma; h.out = w.y;
+        AVD_TRY(launch_head<HEAD_CRITIC_TARGET>(h, d.l2, A, st));
+    }
+    // ---- critic loss gradient on (s, a)                                             trainer.py:495-498
+    l1_forward_kernel<true><<<gl1, 128, 0, st>>>(d, io->critic, co.total, io->s, d.ns, 1, io->a, R, w.H);
+    AVD_LAUNCH_OK();
+    AVD_TRY(gemm_forward(w.H, F, io->critic, co.total, co.W2, w.Z, d.l2, A, R, st));
+    {
+        HeadArgs h = critic_head(d, io->critic, w.Z, R);
+        h.y = w.y; h.out = w.q; h.DZ = w.DZ; h.grads = io->critic_grad; h.gstride = co.n_train; h.loss = io->loss;
+        AVD_TRY(launch_head<HEAD_CRITIC_BWD>(h, d.l2, A, st));
+    }
+    AVD_TRY(gemm_wgrad(w.H, F, w.DZ, io->critic_grad, co.n_train, co.W2, d.l2, A, R, st));
+    AVD_TRY(gemm_dgrad(w.DZ, io->critic, co.total, co.W2, 0, F, w.DH, d.l2, A, R, st));
+    l1_backward_kernel<true><<<gl1b, 128, 0, st>>>(d, io->critic, co.total, io->s, io->a, R, w.DH, io->critic_grad, co.n_train);
+    AVD_LAUNCH_OK();
+    // ---- actor loss gradient: -mean(critic(s, actor(s)))                            trainer.py:501-506
+    l1_forward_kernel<false><<<gl1, 128, 0, st>>>(d, io->actor, ao.total, io->s, d.ns, 1, nullptr, R, w.H1a);
+    AVD_LAUNCH_OK();
+    AVD_TRY(gemm_forward(w.H1a, d.l1, io->actor, ao.total, ao.W2, w.Za, d.l2, A, R, st));
+    {
+        HeadArgs h = actor_head(d, io->actor, w.Za, R, io->action_high);
+        h.out = w.a2;   // pi
+        AVD_TRY(launch_head<HEAD_ACTOR_FWD>(h, d.l2, A, st));
+    }
+    l1_forward_kernel<true><<<gl1, 128, 0, st>>>(d, io->critic, co.total, io->s, d.ns, 1, w.a2, R, w.H);
+    AVD_LAUNCH_OK();
+    AVD_TRY(gemm_forward(w.H, F, io->critic, co.total, co.W2, w.Z, d.l2, A, R, st));
+    {
+        HeadArgs h = critic_head(d, io->critic, w.Z, R);
+        h.DZ = w.DZ; h.loss = io->loss;
+        AVD_TRY(launch_head<HEAD_CRITIC_BWD_ACTION>(h, d.l2, A, st));
+    }
+    AVD_TRY(gemm_dgrad(w.DZ, io->critic, co.total, co.W2, d.l1, d.la, w.DH, d.l2, A, R, st));   // action columns only
+    action_grad_kernel<<<dim3((unsigned)std::min<int64_t>((R + 7) / 8, 1024), A), 256, 0, st>>>(d, io->critic, co.total, w.a2, R, w.DH, w.dpi);
+    AVD_LAUNCH_OK();
+    {
+        HeadArgs h = actor_head(d, io->actor, w.Za, R, io->action_high);
+        h.dpi = w.dpi; h.DZ = w.DZ; h.grads = io->actor_grad; h.gstride = ao.n_train;
+        AVD_TRY(launch_head<HEAD_ACTOR_BWD>(h, d.l2, A, st));
+    }
+    AVD_TRY(gemm_wgrad(w.H1a, d.l1, w.DZ, io->actor_grad, ao.n_train, ao.W2, d.l2, A, R, st));
+    AVD_TRY(gemm_dgrad(w.DZ, io->actor, ao.total, ao.W2, 0, d.l1, w.DH, d.l2, A, R, st));
+    l1_backward_kernel<false><<<gl1b, 128, 0, st>>>(d, io->actor, ao.total, io->s, nullptr, R, w.DH, io->actor_grad, ao.n_train);
+    AVD_LAUNCH_OK();
+    // ---- local update: Adam on both nets, then Polyak of the targets                trainer.py:345-356
+    if (io->apply_updates) {
+        AVD_TRY(avd_adam_apply(io->critic, co.total, io->critic_grad, co.n_train, io->critic_m, io->critic_v, io->critic_t, io->apply_mask,
+                               A, co.n_train, io->critic_lr, io->adam_beta1, io->adam_beta2, io->adam_eps, stream));
+        AVD_TRY(avd_adam_apply(io->actor, ao.total, io->actor_grad, ao.n_train, io->actor_m, io->actor_v, io->actor_t, io->apply_mask, A,
+                               ao.n_train, io->actor_lr, io->adam_beta1, io->adam_beta2, io->adam_eps, stream));
+        AVD_TRY(avd_polyak_update(io->t_critic, io->critic, io->apply_mask, A, co.total, io->tau, stream));
+        AVD_TRY(avd_polyak_update(io->t_actor, io->actor, io->apply_mask, A, ao.total, io->tau, stream));
+    }
+    return AVD_OK;
+}

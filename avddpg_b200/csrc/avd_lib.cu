@@ -39,6 +39,8 @@ extern "C" int64_t avd_sizeof(int which) {
         case 0: return (int64_t)sizeof(avd_env_params);
         case 1: return (int64_t)sizeof(avd_env_io);
         case 2: return (int64_t)sizeof(avd_clock);
+        case 3: return (int64_t)sizeof(avd_net_dims);
+        case 4: return (int64_t)sizeof(avd_learn_io);
         default: return -1;
     }
 }

@@ -1,0 +1,208 @@
+"""The learn / act / update part of the reference's ``workers/trainer.py`` on the GPU.
+
+``DDPGPopulation`` owns the actor, critic, target networks and Adam state of A agents as flat HBM vectors
+and runs, for all of them at once,
+    act()   : actor(state) for every vehicle (trainer.py:286-289; OU noise + clip are fused into the env step)
+    learn() : Trainer.learn (trainer.py:472-508) + Adam x2 + Polyak (trainer.py:345-356) -- one C-ABI call
+Agent a = m*G + g is follower m of platoon-group g; its ``rows_per_agent`` sampled transitions are rows
+[a*R, (a+1)*R) of the replay gather output, which is exactly the order ReplayRings produces when the
+group's platoons are contiguous (ring id = m*P + p, P = G*E).  With E envs per group every agent's update
+is the mean gradient over its E per-platoon minibatches of 64 -- the reference's interfrl/gradients round
+(trainer.py:400-431) for platoons that share weights, without the E redundant copies of the weights.
+
+``Trainer`` keeps the reference's ``learn(rbuffer, actor, critic, target_actor, target_critic)`` signature for
+single-agent model objects from avddpg_b200.model.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from .model import NetBank, dims_from_config
+
+
+class DDPGPopulation:
+    def __init__(self, num_groups: int, num_followers: int, config, *, num_states: int = 4, rows_per_agent: int = 64,
+                 device=None, seed: Optional[int] = None, precision: int = 0):
+        self.lib = _lib.load()
+        _lib.require_device()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.G, self.M, self.A = int(num_groups), int(num_followers), int(num_groups) * int(num_followers)
+        self.config, self.R, self.precision = config, int(rows_per_agent), int(precision)
+        self.dims = dims_from_config(config, num_states)
+        dev = self.device
+        self.actor = NetBank("actor", self.dims, self.A, dev, with_optimizer=True)
+        self.critic = NetBank("critic", self.dims, self.A, dev, with_optimizer=True)
+        self.t_actor = NetBank("actor", self.dims, self.A, dev)
+        self.t_critic = NetBank("critic", self.dims, self.A, dev)
+        gen = torch.Generator().manual_seed(int(getattr(config, "random_seed", 1) if seed is None else seed))
+        self.actor.init_reference(gen)
+        self.critic.init_reference(gen)
+        self.sync_targets()
+        self.loss = torch.zeros(self.A, 2, dtype=torch.float32, device=dev)
+        self._ws = None
+        self._act_ws = None
+        self.io = _lib.LearnIO()
+        self.launches = 0
+
+    def sync_targets(self):
+        """target.set_weights(online.get_weights())  (trainer.py:130-131)."""
+        self.t_actor.flat.copy_(self.actor.flat)
+        self.t_critic.flat.copy_(self.critic.flat)
+
+    def _workspace(self, rows):
+        need = self.lib.avd_ddpg_workspace_bytes(C.byref(self.dims), self.A, rows)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    # ------------------------------------------------------------------ acting
+    def act(self, native_state: torch.Tensor, out: torch.Tensor, envs_per_group: int):
+        """actor(state) for every vehicle of a BatchedPlatoons batch: native_state [4, M, P] (P = G*E),
+        out [M, P] (e.g. env.action_mu).  Row n = m*P + p belongs to agent n // E."""
+        d = self.dims
+        M, P = native_state.shape[1], native_state.shape[2]
+        if M != self.M or P != self.G * envs_per_group:
+            raise ValueError("state batch does not match the population")
+        rows = envs_per_group
+        need = self.A * rows * (d.l1 + d.l2) * 4 + 256
+        if self._act_ws is None or self._act_ws.numel() < need:
+            self._act_ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        _lib.check(self.lib.avd_actor_forward(C.byref(d), self.A, rows, _lib.ptr(self.actor.flat), _lib.ptr(native_state), 1,
+                                              M * P, float(self.config.action_high), _lib.ptr(out), _lib.ptr(self._act_ws),
+                                              self._act_ws.numel(), self.precision, _lib.current_stream()))
+        self.launches += 3
+        return out
+
+    # ------------------------------------------------------------------ learning
+    def learn(self, s, a, r, s2, *, apply_updates: bool = True, apply_mask: Optional[torch.Tensor] = None,
+              rows_per_agent: Optional[int] = None):
+        """One Trainer.learn for every agent.  s, s2: [A*R, 4]; a, r: [A*R] (float32, CUDA, contiguous).
+        Gradients land in self.actor.grad / self.critic.grad ([A, n_trainable], `trainable_variables` order);
+        with apply_updates the weights, Adam state and targets are updated in place."""
+        R = self.R if rows_per_agent is None else int(rows_per_agent)
+        n = self.A * R
+        for t, width in ((s, 4), (s2, 4)):
+            if t.shape != (n, width) or t.dtype != torch.float32 or not t.is_contiguous():
+                raise ValueError(f"state batches must be contiguous float32 [A*R={n}, 4]")
+        conf, io = self.config, self.io
+        ws = self._workspace(R)
+        io.dims, io.A, io.apply_updates, io.rows_per_agent = self.dims, self.A, int(apply_updates), R
+        io.gamma, io.action_high, io.tau = float(conf.gamma), float(conf.action_high), float(conf.tau)
+        io.actor_lr, io.critic_lr = float(conf.actor_lr), float(conf.critic_lr)
+        io.adam_beta1, io.adam_beta2, io.adam_eps = 0.9, 0.999, 1e-7     # tf.keras.optimizers.Adam defaults
+        io.s, io.a, io.r, io.s2 = s.data_ptr(), a.data_ptr(), r.data_ptr(), s2.data_ptr()
+        io.actor, io.critic = self.actor.flat.data_ptr(), self.critic.flat.data_ptr()
+        io.t_actor, io.t_critic = self.t_actor.flat.data_ptr(), self.t_critic.flat.data_ptr()
+        io.actor_grad, io.critic_grad = self.actor.grad.data_ptr(), self.critic.grad.data_ptr()
+        io.actor_m, io.actor_v = self.actor.m.data_ptr(), self.actor.v.data_ptr()
+        io.critic_m, io.critic_v = self.critic.m.data_ptr(), self.critic.v.data_ptr()
+        io.actor_t, io.critic_t = self.actor.step.data_ptr(), self.critic.step.data_ptr()
+        io.apply_mask = None if apply_mask is None else apply_mask.data_ptr()
+        io.loss = self.loss.data_ptr()
+        io.workspace, io.workspace_bytes = ws.data_ptr(), ws.numel()
+        io.precision = self.precision
+        _lib.check(self.lib.avd_ddpg_learn(C.byref(io), _lib.current_stream()))
+        self.launches += 27 + (8 if apply_updates else 0)
+        return self.critic.grad, self.actor.grad
+
+    def apply_gradients(self, apply_mask: Optional[torch.Tensor] = None):
+        """optimizer.apply_gradients for both nets with whatever is in .grad (trainer.py:348-349 / 420-425)."""
+        conf = self.config
+        for bank, lr in ((self.critic, conf.critic_lr), (self.actor, conf.actor_lr)):
+            _lib.check(self.lib.avd_adam_apply(_lib.ptr(bank.flat), bank.total, _lib.ptr(bank.grad), bank.n_train, _lib.ptr(bank.m),
+                                               _lib.ptr(bank.v), _lib.ptr(bank.step), _lib.ptr(apply_mask), self.A, bank.n_train,
+                                               float(lr), 0.9, 0.999, 1e-7, _lib.current_stream()))
+        self.launches += 4
+
+    def soft_update(self, apply_mask: Optional[torch.Tensor] = None):
+        """ddpgagent.update_target + set_weights for every agent (trainer.py:352-356)."""
+        for tgt, onl in ((self.t_critic, self.critic), (self.t_actor, self.actor)):
+            _lib.check(self.lib.avd_polyak_update(_lib.ptr(tgt.flat), _lib.ptr(onl.flat), _lib.ptr(apply_mask), self.A, onl.total,
+                                                  float(self.config.tau), _lib.current_stream()))
+        self.launches += 2
+
+
+class Trainer:
+    """Reference-shaped wrapper: ``learn`` on single-agent model objects (trainer.py:472-508)."""
+
+    def __init__(self, base_dir=None, timestamp=None, debug_enabled=False, conf=None):
+        self.base_dir, self.timestamp, self.debug_enabled, self.conf = base_dir, timestamp, debug_enabled, conf
+        self._ws = None
+
+    def learn(self, rbuffer, actor_model, critic_model, target_actor, target_critic, indices=None):
+        """-> (critic_grad, actor_grad): lists of tensors ordered like ``trainable_variables``."""
+        lib = _lib.load()
+        conf = self.conf
+        s, a, r, s2 = rbuffer.sample(indices)
+        d = critic_model.bank.dims
+        n = s.shape[0]
+
+        def pad4(x):
+            if x.shape[1] == 4:
+                return x.contiguous()
+            out = torch.zeros(n, 4, dtype=torch.float32, device=x.device)
+            out[:, : x.shape[1]] = x
+            return out
+
+        if d.ns != 4:
+            raise NotImplementedError("per-object learn supports the 4-state Model B layout")
+        s, s2 = pad4(s), pad4(s2)
+        a, r = a.reshape(-1).contiguous(), r.reshape(-1).contiguous()
+        dev = s.device
+        ag = torch.zeros(1, actor_model.bank.n_train, dtype=torch.float32, device=dev)
+        cg = torch.zeros(1, critic_model.bank.n_train, dtype=torch.float32, device=dev)
+        need = lib.avd_ddpg_workspace_bytes(C.byref(d), 1, n)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        io = _lib.LearnIO()
+        io.dims, io.A, io.apply_updates, io.rows_per_agent = d, 1, 0, n
+        io.gamma, io.action_high = float(conf.gamma), float(conf.action_high)
+        io.s, io.a, io.r, io.s2 = s.data_ptr(), a.data_ptr(), r.data_ptr(), s2.data_ptr()
+        io.actor, io.critic = actor_model.bank.flat.data_ptr(), critic_model.bank.flat.data_ptr()
+        io.t_actor, io.t_critic = target_actor.bank.flat.data_ptr(), target_critic.bank.flat.data_ptr()
+        io.actor_grad, io.critic_grad = ag.data_ptr(), cg.data_ptr()
+        io.workspace, io.workspace_bytes = self._ws.data_ptr(), self._ws.numel()
+        _lib.check(lib.avd_ddpg_learn(C.byref(io), _lib.current_stream()))
+        critic_grad = [critic_model.bank.view(nm, 0, cg) for nm in critic_model.bank.trainable_names]
+        actor_grad = [actor_model.bank.view(nm, 0, ag) for nm in actor_model.bank.trainable_names]
+        return critic_grad, actor_grad
+
+
+# ---- FRL scheduling predicates (workers/trainer.py:631-695), pure host logic ---------------------------
+def is_fed_enabled(conf) -> bool:
+    return (conf.fed_method == conf.interfrl or conf.fed_method == conf.intrafrl) and (conf.framework == conf.dcntrl)
+
+
+def is_gradient_updates_enabled(conf) -> bool:
+    return conf.aggregation_method == conf.gradients
+
+
+def is_model_weight_updates_enabled(conf) -> bool:
+    return conf.aggregation_method == conf.weights
+
+
+def is_weighted_fed_enabled(conf, training_episode: int) -> bool:
+    return bool(conf.weighted_average_enabled and training_episode >= conf.weighted_window)
+
+
+def is_valid_update_episode(conf, training_episode: int) -> bool:
+    return bool(conf.fed_enabled and (training_episode % conf.fed_update_count) == 0 and training_episode <= conf.fed_cutoff_episode)
+
+
+def is_valid_update_step(conf, training_step: int) -> bool:
+    return (training_step % conf.fed_update_delay_steps) == 0
+
+
+def is_valid_step_for_federated_training_with_gradients(conf, training_episode, training_step):
+    return (is_fed_enabled(conf) and is_valid_update_episode(conf, training_episode) and is_valid_update_step(conf, training_step)
+            and is_gradient_updates_enabled(conf))
+
+
+def is_valid_step_for_federated_training_with_weights(conf, training_episode, training_step):
+    return (is_fed_enabled(conf) and is_valid_update_episode(conf, training_episode) and is_valid_update_step(conf, training_step)
+            and is_model_weight_updates_enabled(conf))

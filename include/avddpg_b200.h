@@ -185,6 +185,96 @@ int avd_replay_gather(const float* ring, int64_t capacity, int64_t M, int64_t P,
  * range without running `capacity` env steps).                                                    */
 int avd_replay_fill_synthetic(float* ring, int64_t capacity, int64_t M, int64_t P, uint64_t seed, void* stream);
 
+/* ---- DDPG agents ----------------------------------------------------------------------------
+ * A population of `A` agents, each with its own actor / critic / target networks (agent/model.py:4-85),
+ * Adam state (workers/trainer.py:138-139) and `rows_per_agent` sampled transitions per update.
+ * Parameters of one net are one flat fp32 vector per agent, trainable tensors first:
+ *   actor  : W1[ns,l1] b1 g1 be1 | W2[l1,l2] b2 g2 be2 | W3[l2,1] b3 || mu1 var1 mu2 var2
+ *   critic : Ws[ns,l1] bs Wa[1,la] ba gs bes ga bea | W2[l1+la,l2] b2 g2 be2 | W3[l2,1] b3 || mus vars mua vara mu2 var2
+ * (g/be = BatchNormalization gamma/beta, mu/var = its frozen moving statistics; `||` separates the
+ * trainable prefix -- the order of Keras `trainable_variables` -- from the non-trainable tail.  The Python
+ * mirror exposes views in Keras `.weights` order.)  Dense kernels are row-major [in, out] like Keras.      */
+typedef struct avd_net_dims {
+    int32_t ns;   /* state width: 4 (Model B) or 3 (Model A)              */
+    int32_t l1;   /* actor_layer1_size == critic_layer1_size (256)        */
+    int32_t la;   /* critic_act_layer_size (48)                           */
+    int32_t l2;   /* actor_layer2_size == critic_layer2_size (128)        */
+} avd_net_dims;
+
+typedef struct avd_learn_io {
+    avd_net_dims dims;
+    int32_t A;                  /* agents                                                              */
+    int32_t apply_updates;      /* 1: Adam x2 + Polyak after the gradients (trainer.py:345-356); 0: gradients only */
+    int64_t rows_per_agent;     /* transitions per agent and update (reference: batch_size = 64)       */
+    float gamma, action_high, tau, actor_lr, critic_lr;
+    float adam_beta1, adam_beta2, adam_eps;
+    const float* s;             /* [A*rows][4]  sampled states   (replay gather output)                */
+    const float* a;             /* [A*rows]                                                            */
+    const float* r;             /* [A*rows]                                                            */
+    const float* s2;            /* [A*rows][4]                                                         */
+    float* actor;               /* [A][actor_total]                                                    */
+    float* critic;              /* [A][critic_total]                                                   */
+    float* t_actor;
+    float* t_critic;
+    float* actor_grad;          /* [A][actor_trainable]   out                                          */
+    float* critic_grad;         /* [A][critic_trainable]  out                                          */
+    float* actor_m; float* actor_v; float* critic_m; float* critic_v;   /* Adam moments, trainable sizes */
+    int32_t* actor_t; int32_t* critic_t;                                  /* [A] Adam step counters       */
+    const uint8_t* apply_mask;  /* [A] nullable: agents with 0 keep their weights (intrafrl "leader is king") */
+    float* loss;                /* [A][2] nullable: critic_loss, actor_loss                            */
+    void* workspace;            /* avd_ddpg_workspace_bytes() bytes                                    */
+    int64_t workspace_bytes;
+    int32_t precision;          /* 0: fp32 SIMT kernels (parity mode); 1: bf16 tcgen05 tensor-core GEMMs */
+    int32_t reserved0;
+} avd_learn_io;
+
+/* sizes of the flat parameter vectors: out4 = {actor_trainable, actor_total, critic_trainable, critic_total} */
+int avd_ddpg_param_counts(const avd_net_dims* dims, int64_t* out4);
+int64_t avd_ddpg_workspace_bytes(const avd_net_dims* dims, int32_t A, int64_t rows_per_agent);
+
+/* Trainer.learn (workers/trainer.py:472-508) for all agents at once: TD target from the target nets,
+ * critic MSE gradient, actor -mean(Q) gradient (both on the pre-update weights); then, if apply_updates,
+ * tf.keras Adam on both nets (trainer.py:348-349) and ddpgagent.update_target (agent/ddpgagent.py:31-55). */
+int avd_ddpg_learn(const avd_learn_io* io, void* stream);
+
+/* actor(state) for `rows_per_agent` rows per agent (trainer.py:287-289 batched).  s element (row n, k) is read
+ * at s[n*s_row_stride + k*s_col_stride] so the env's native [4][M][P] state can be fed without a transpose
+ * (row stride 1, column stride M*P).  out[n] = action_high * tanh(.)                                    */
+int avd_actor_forward(const avd_net_dims* dims, int32_t A, int64_t rows_per_agent, const float* actor_params,
+                      const float* s, int64_t s_row_stride, int64_t s_col_stride, float action_high, float* out,
+                      void* workspace, int64_t workspace_bytes, int32_t precision, void* stream);
+
+/* critic([state, action]) -> q[n] (row-major s[n][ns], a[n]); used by tests and the evaluator. */
+int avd_critic_forward(const avd_net_dims* dims, int32_t A, int64_t rows_per_agent, const float* critic_params,
+                       const float* s, const float* a, float* q, void* workspace, int64_t workspace_bytes,
+                       int32_t precision, void* stream);
+
+/* tf.keras.optimizers.Adam.apply_gradients for [A][n] trainable prefixes of [A][stride] parameter vectors:
+ * t = ++step[a];  lr_t = lr*sqrt(1-b2^t)/(1-b1^t);  m += (g-m)(1-b1);  v += (g*g-v)(1-b2);
+ * theta -= lr_t*m/(sqrt(v)+eps).  grad_agent_stride = n for per-agent gradients, 0 to apply ONE shared
+ * gradient vector to every agent (FedAvg'd gradients, trainer.py:419-425).                              */
+int avd_adam_apply(float* params, int64_t param_stride, const float* grads, int64_t grad_agent_stride, float* m,
+                   float* v, int32_t* step, const uint8_t* apply_mask, int32_t A, int64_t n, float lr, float beta1,
+                   float beta2, float eps, void* stream);
+
+/* ddpgagent.update_target (agent/ddpgagent.py:44-55): target = tau*online + (1-tau)*target over n floats
+ * per agent (ALL weights incl. BN statistics).                                                          */
+int avd_polyak_update(float* target, const float* online, const uint8_t* apply_mask, int32_t A, int64_t n, float tau,
+                      void* stream);
+
+/* federated.Server.get_avg_params / get_weighted_avg_params (src/server/federated.py:18-122) for flat
+ * vectors: out[s][j] = scale[s] * sum_x weight[s][x] * in[member(s,x)][j].  Members of system s are
+ * in[(s*member_stride_s + x*member_stride_x)] rows of length n (row pitch `pitch`); weights NULL = 1;
+ * scale NULL = 1/X (plain mean).  One launch; used locally before / after the NCCL allreduce.           */
+int avd_fed_reduce(float* out, int64_t out_pitch, const float* in, int64_t pitch, int32_t n_systems, int32_t n_members,
+                   int64_t member_stride_s, int64_t member_stride_x, const float* weights, const float* scale, int64_t n,
+                   void* stream);
+
+/* out[a][j] = in[src(a)][j]: broadcast system averages back onto members (set_weights, trainer.py:448-456). */
+int avd_fed_broadcast(float* out, int64_t out_pitch, const float* in, int64_t in_pitch, int32_t n_systems,
+                      int32_t n_members, int64_t member_stride_s, int64_t member_stride_x, const uint8_t* apply_mask,
+                      int64_t n, void* stream);
+
 /* ---- raw RNG access (parity tests: bit-exact against oracle/philox_np.py) ------------------- */
 int avd_rng_words(uint32_t* out4 /*[n][4]*/, int64_t n, uint64_t id_base, uint32_t tick, uint32_t purpose,
                   uint64_t seed, void* stream);

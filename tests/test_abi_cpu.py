@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layouts_match():
     lib = _lib.load()
-    for which, st in enumerate((_lib.EnvParams, _lib.EnvIO, _lib.Clock)):
+    for which, st in enumerate((_lib.EnvParams, _lib.EnvIO, _lib.Clock, _lib.NetDims, _lib.LearnIO)):
         assert lib.avd_sizeof(which) == C.sizeof(st)
     assert lib.avd_abi_version() == _lib.ABI_VERSION
 

@@ -1,0 +1,288 @@
+"""GPU parity tests of the DDPG learn path (C ABI: avd_ddpg_learn, avd_actor_forward, avd_critic_forward,
+avd_adam_apply, avd_polyak_update, avd_fed_*) against oracle/ddpg_np.py and the reference-generated goldens.
+
+Tolerances (fp32 SIMT kernels, `precision=0`): forward values 1e-5 relative; gradients 2e-4 normwise per
+tensor (the reductions over the batch run in a different order than NumPy's); parameters after Adam/Polyak
+steps 1e-5.  The bf16 tensor-core mode (`precision=1`) is checked in test_gpu_umma.py with its own bar.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ddpg_np as D
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def mods():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from avddpg_b200 import _lib, ddpgagent, model, replaybuffer, trainer
+    from avddpg_b200.config import Config
+    from avddpg_b200.server import federated
+    _lib.require_device()
+    return dict(lib=_lib, model=model, trainer=trainer, Config=Config, fed=federated, agent=ddpgagent, rb=replaybuffer)
+
+
+def _nrm(got, ref):
+    got, ref = np.asarray(got, np.float64), np.asarray(ref, np.float64)
+    return np.max(np.abs(got - ref)) / max(np.max(np.abs(ref)), 1e-12)
+
+
+def make_nets(seed):
+    rng = np.random.default_rng(seed)
+    nets = [D.init_actor(rng), D.init_critic(rng), D.init_actor(rng), D.init_critic(rng)]
+    for p in (nets[0], nets[2]):
+        D.randomize_bn(p, rng, [("g1", "be1", "mu1", "var1"), ("g2", "be2", "mu2", "var2")])
+    for p in (nets[1], nets[3]):
+        D.randomize_bn(p, rng, [("gs", "bes", "mus", "vars"), ("ga", "bea", "mua", "vara"), ("g2", "be2", "mu2", "var2")])
+    for p in nets:
+        for k in p:
+            if k.startswith("b") and not k.startswith("be"):
+                p[k] = rng.normal(0, 0.05, p[k].shape).astype(np.float32)
+    nets[0]["W3"] *= 50; nets[1]["W3"] *= 300; nets[2]["W3"] *= 50; nets[3]["W3"] *= 300
+    return nets
+
+
+def make_batch(seed, B):
+    rng = np.random.default_rng(seed)
+    s = rng.normal(0, 2, (B, 4)).astype(np.float32); a = rng.uniform(-2.5, 2.5, (B, 1)).astype(np.float32)
+    r = -rng.uniform(0, 0.5, (B, 1)).astype(np.float32); s2 = (s + rng.normal(0, 0.2, (B, 4))).astype(np.float32)
+    return s, a, r, s2
+
+
+def build_population(mods, A, R, seeds, G=None, M=None):
+    conf = mods["Config"]()
+    G = A if G is None else G
+    M = 1 if M is None else M
+    pop = mods["trainer"].DDPGPopulation(G, M, conf, rows_per_agent=R)
+    nets = [make_nets(sd) for sd in seeds]
+    for a, (ac, cr, ta, tc) in enumerate(nets):
+        pop.actor.load_named(a, ac); pop.critic.load_named(a, cr); pop.t_actor.load_named(a, ta); pop.t_critic.load_named(a, tc)
+    batches = [make_batch(100 + sd, R) for sd in seeds]
+    cat = lambda i, w: torch.as_tensor(np.concatenate([b[i].reshape(R, w) for b in batches]), device="cuda").contiguous()
+    s, a, r, s2 = cat(0, 4), cat(1, 1).reshape(-1), cat(2, 1).reshape(-1), cat(3, 4)
+    return conf, pop, nets, batches, (s, a, r, s2)
+
+
+def test_forward_vs_oracle(mods):
+    conf, pop, nets, batches, (s, a, r, s2) = build_population(mods, 3, 70, [1, 2, 3])
+    lib, d = mods["lib"], pop.dims
+    n = 3 * 70
+    out = torch.empty(n, device="cuda"); q = torch.empty(n, device="cuda")
+    ws = torch.empty(n * (d.l1 + d.la + d.l2) * 4 + 256, dtype=torch.uint8, device="cuda")
+    lib.check(lib.load().avd_actor_forward(d, 3, 70, lib.ptr(pop.actor.flat), lib.ptr(s), 4, 1, 2.5, lib.ptr(out), lib.ptr(ws), ws.numel(), 0, lib.current_stream()))
+    lib.check(lib.load().avd_critic_forward(d, 3, 70, lib.ptr(pop.critic.flat), lib.ptr(s), lib.ptr(a), lib.ptr(q), lib.ptr(ws), ws.numel(), 0, lib.current_stream()))
+    for i in range(3):
+        ref_a, _ = D.actor_forward(nets[i][0], batches[i][0])
+        ref_q, _ = D.critic_forward(nets[i][1], batches[i][0], batches[i][1])
+        assert _nrm(out[i * 70:(i + 1) * 70].cpu().numpy(), ref_a.ravel()) < 1e-5
+        assert _nrm(q[i * 70:(i + 1) * 70].cpu().numpy(), ref_q.ravel()) < 1e-5
+
+
+@pytest.mark.parametrize("A,R", [(1, 64), (3, 64), (2, 200), (2, 1000)])
+def test_learn_gradients_vs_oracle(mods, A, R):
+    conf, pop, nets, batches, (s, a, r, s2) = build_population(mods, A, R, list(range(10, 10 + A)))
+    cg, ag = pop.learn(s, a, r, s2, apply_updates=False)
+    torch.cuda.synchronize()
+    for i in range(A):
+        ocg, oag, info = D.learn(nets[i][0], nets[i][1], nets[i][2], nets[i][3], batches[i], gamma=conf.gamma, high=conf.action_high)
+        for name in pop.critic.trainable_names:
+            got = pop.critic.view(name, i, pop.critic.grad).cpu().numpy()
+            assert _nrm(got, ocg[name].reshape(got.shape)) < 2e-4, ("critic", name)
+        for name in pop.actor.trainable_names:
+            got = pop.actor.view(name, i, pop.actor.grad).cpu().numpy()
+            assert _nrm(got, oag[name].reshape(got.shape)) < 2e-4, ("actor", name)
+        loss = pop.loss[i].cpu().numpy()
+        assert abs(loss[0] - info["critic_loss"]) < 1e-4 * max(1, abs(info["critic_loss"]))
+        assert abs(loss[1] - info["actor_loss"]) < 1e-4 * max(1, abs(info["actor_loss"]))
+
+
+def test_learn_apply_updates_sequence(mods):
+    """3 consecutive local updates (Adam x2 + Polyak) stay on the oracle's trajectory."""
+    A, R = 2, 64
+    conf, pop, nets, batches, (s, a, r, s2) = build_population(mods, A, R, [21, 22])
+    state = []
+    for ac, cr, ta, tc in nets:
+        z = lambda p, names: {k: np.zeros_like(p[k]) for k in names}
+        state.append(dict(am=z(ac, D.ACTOR_TRAINABLE), av=z(ac, D.ACTOR_TRAINABLE), cm=z(cr, D.CRITIC_TRAINABLE), cv=z(cr, D.CRITIC_TRAINABLE)))
+    for step in range(1, 4):
+        pop.learn(s, a, r, s2, apply_updates=True)
+        for i, (ac, cr, ta, tc) in enumerate(nets):
+            ocg, oag, _ = D.learn(ac, cr, ta, tc, batches[i], gamma=conf.gamma, high=conf.action_high)
+            D.adam_apply(cr, ocg, state[i]["cm"], state[i]["cv"], step, conf.critic_lr, D.CRITIC_TRAINABLE)
+            D.adam_apply(ac, oag, state[i]["am"], state[i]["av"], step, conf.actor_lr, D.ACTOR_TRAINABLE)
+            nets[i][3] = tc = D.polyak(tc, cr, conf.tau, D.CRITIC_WEIGHTS)
+            nets[i][2] = ta = D.polyak(ta, ac, conf.tau, D.ACTOR_WEIGHTS)
+    torch.cuda.synchronize()
+    assert pop.actor.step.tolist() == [3, 3] and pop.critic.step.tolist() == [3, 3]
+    for i, (ac, cr, ta, tc) in enumerate(nets):
+        for bank, ref in ((pop.actor, ac), (pop.critic, cr), (pop.t_actor, ta), (pop.t_critic, tc)):
+            for name in bank.weight_names:
+                got = bank.view(name, i).cpu().numpy()
+                np.testing.assert_allclose(got, ref[name].reshape(got.shape), rtol=2e-4, atol=2e-6, err_msg=f"{bank.kind}.{name}")
+
+
+def test_adam_and_polyak_kernels(mods, golden):
+    lib = mods["lib"]
+    rng = np.random.default_rng(5)
+    A, n, stride = 3, 1000, 1100
+    p = rng.normal(size=(A, stride)).astype(np.float32); g = rng.normal(size=(A, n)).astype(np.float32)
+    tp, tg = torch.as_tensor(p, device="cuda"), torch.as_tensor(g, device="cuda")
+    m, v = torch.zeros(A, n, device="cuda"), torch.zeros(A, n, device="cuda")
+    step = torch.tensor([0, 4, 9], dtype=torch.int32, device="cuda")
+    mask = torch.tensor([1, 0, 1], dtype=torch.uint8, device="cuda")
+    lib.check(lib.load().avd_adam_apply(lib.ptr(tp), stride, lib.ptr(tg), n, lib.ptr(m), lib.ptr(v), lib.ptr(step), lib.ptr(mask), A, n,
+                                        5e-4, 0.9, 0.999, 1e-7, lib.current_stream()))
+    assert step.tolist() == [1, 4, 10]
+    for a, t in ((0, 1), (2, 10)):
+        P = {"w": p[a, :n].copy()}; M = {"w": np.zeros(n, np.float32)}; V = {"w": np.zeros(n, np.float32)}
+        D.adam_apply(P, {"w": g[a]}, M, V, t, 5e-4, ["w"])
+        np.testing.assert_allclose(tp[a, :n].cpu().numpy(), P["w"], rtol=1e-5, atol=1e-7)
+    assert np.array_equal(tp[1].cpu().numpy(), p[1]) and np.array_equal(tp[:, n:].cpu().numpy(), p[:, n:])
+    # Polyak against the REFERENCE's update_target outputs
+    gp = golden("polyak")
+    tcw = [gp[f"tc{i}"] for i in range(int(gp["n_c"]))]; cw = [gp[f"c{i}"] for i in range(int(gp["n_c"]))]
+    taw = [gp[f"ta{i}"] for i in range(int(gp["n_a"]))]; aw = [gp[f"a{i}"] for i in range(int(gp["n_a"]))]
+    tc_new, ta_new = mods["agent"].update_target(float(gp["tau"]), tcw, cw, taw, aw)
+    for i, t in enumerate(tc_new):
+        np.testing.assert_allclose(t.cpu().numpy(), gp[f"tc_new{i}"], rtol=1e-6, atol=1e-7)
+    for i, t in enumerate(ta_new):
+        np.testing.assert_allclose(t.cpu().numpy(), gp[f"ta_new{i}"], rtol=1e-6, atol=1e-7)
+
+
+def test_policy_dropin(mods):
+    out = mods["agent"].policy(torch.tensor([[3.1]], device="cuda"), None, -2.5, 2.5)
+    assert isinstance(out, list) and float(out[0]) == 2.5
+    out = mods["agent"].policy(torch.tensor([[0.5]], device="cuda"), lambda: np.array([0.25]), -2.5, 2.5)
+    assert abs(float(out[0]) - 0.75) < 1e-7
+
+
+def test_server_dropin_vs_reference_golden(mods, golden):
+    g = golden("fedavg")
+    srv = mods["fed"].Server("t", False)
+    P, M, L = 2, 2, 3
+    w = g["kat_weights"]
+    weighted = [[[np.float32(w[p][m]) * g[f"kat_in_{p}_{m}_{l}"] for l in range(L)] for p in range(P)] for m in range(M)]
+    plain = [[[g[f"kat_in_{p}_{m}_{l}"] for l in range(L)] for p in range(P)] for m in range(M)]
+    wavg = srv.get_weighted_avg_params(weighted, g["kat_sums"]); avg = srv.get_avg_params(plain)
+    for m in range(M):
+        for l in range(L):
+            np.testing.assert_allclose(wavg[m][l].cpu().numpy(), g[f"kat_wavg_{m}_{l}"], rtol=1e-6)
+            np.testing.assert_allclose(avg[m][l].cpu().numpy(), g[f"kat_avg_{m}_{l}"], rtol=1e-6)
+    S, X, L = (int(v) for v in g["rnd_shape"])
+    plain = [[[g[f"rnd_in_{s}_{x}_{l}"] for l in range(L)] for x in range(X)] for s in range(S)]
+    avg = srv.get_avg_params(plain)
+    for s in range(S):
+        for l in range(L):
+            assert avg[s][l].shape == g[f"rnd_avg_{s}_{l}"].shape
+            np.testing.assert_allclose(avg[s][l].cpu().numpy(), g[f"rnd_avg_{s}_{l}"], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("method", ["interfrl", "intrafrl"])
+@pytest.mark.parametrize("weighted", [False, True])
+def test_aggregator_gradients(mods, method, weighted):
+    G, M, R = 3, 2, 64
+    A = G * M
+    conf, pop, nets, batches, (s, a, r, s2) = build_population(mods, A, R, list(range(30, 30 + A)), G=G, M=M)
+    conf.fed_method = method
+    pop.learn(s, a, r, s2, apply_updates=False)
+    ag0, cg0 = pop.actor.grad.cpu().numpy().copy(), pop.critic.grad.cpu().numpy().copy()
+    agg = mods["fed"].FederatedAggregator(pop, conf)
+    rng = np.random.default_rng(1)
+    S, X = (M, G) if method == "interfrl" else (G, M)
+    w = rng.uniform(0.2, 2.0, (S, X)).astype(np.float32) if weighted else None
+    before = pop.actor.flat.clone()
+    agg.aggregate_gradients(weights=w, apply=True)
+    member = (lambda s_, x: s_ * G + x) if method == "interfrl" else (lambda s_, x: x * G + s_)
+    for s_ in range(S):
+        rows = [member(s_, x) for x in range(X)]
+        if weighted:
+            ea = (w[s_][:, None] * ag0[rows]).sum(0) * np.float32(1 / w[s_].sum()); ec = (w[s_][:, None] * cg0[rows]).sum(0) * np.float32(1 / w[s_].sum())
+        else:
+            ea, ec = ag0[rows].mean(0), cg0[rows].mean(0)
+        for row in rows:
+            np.testing.assert_allclose(pop.actor.grad[row].cpu().numpy(), ea, rtol=2e-5, atol=1e-9)
+            np.testing.assert_allclose(pop.critic.grad[row].cpu().numpy(), ec, rtol=2e-5, atol=1e-9)
+    assert pop.actor.step.tolist() == [1] * A and not torch.equal(before, pop.actor.flat)
+
+
+def test_aggregator_weights_mode_and_quirk(mods):
+    G, M, R = 2, 2, 64
+    A = G * M
+    conf, pop, nets, batches, _ = build_population(mods, A, R, list(range(40, 40 + A)), G=G, M=M)
+    conf.fed_method = "interfrl"
+    a0, c0 = pop.actor.flat.cpu().numpy().copy(), pop.critic.flat.cpu().numpy().copy()
+    mods["fed"].FederatedAggregator(pop, conf, reference_weights_quirk=False).aggregate_weights()
+    for m in range(M):
+        rows = [m * G + g for g in range(G)]
+        for row in rows:
+            np.testing.assert_allclose(pop.actor.flat[row].cpu().numpy(), a0[rows].mean(0), rtol=1e-6, atol=1e-7)
+            np.testing.assert_allclose(pop.t_critic.flat[row].cpu().numpy(), c0[rows].mean(0), rtol=1e-6, atol=1e-7)
+    pop.actor.flat.copy_(torch.as_tensor(a0)); pop.critic.flat.copy_(torch.as_tensor(c0))
+    mods["fed"].FederatedAggregator(pop, conf, reference_weights_quirk=True).aggregate_weights()   # trainer.py:442-456: `[0]`
+    sys0 = [g for g in range(G)]
+    for row in range(A):
+        np.testing.assert_allclose(pop.actor.flat[row].cpu().numpy(), a0[sys0].mean(0), rtol=1e-6, atol=1e-7)
+        np.testing.assert_allclose(pop.t_actor.flat[row].cpu().numpy(), a0[sys0].mean(0), rtol=1e-6, atol=1e-7)
+    # intrafrl + directional averaging leaves follower 0 untouched
+    conf.fed_method = "intrafrl"; conf.intra_directional_averaging = True
+    pop.actor.flat.copy_(torch.as_tensor(a0))
+    mods["fed"].FederatedAggregator(pop, conf, reference_weights_quirk=False).aggregate_weights()
+    for g in range(G):
+        assert np.array_equal(pop.actor.flat[g].cpu().numpy(), a0[g])            # m = 0 rows
+        np.testing.assert_allclose(pop.actor.flat[G + g].cpu().numpy(), a0[[g, G + g]].mean(0), rtol=1e-6, atol=1e-7)
+
+
+def test_reference_shaped_learn_with_model_objects(mods, golden):
+    """Trainer.learn(rbuffer, actor, critic, target_actor, target_critic) on drop-in objects, with the
+    reference's own np.random.choice indices injected (identical inputs -> gradients vs oracle)."""
+    conf = mods["Config"]()
+    m = mods["model"]
+    actor = m.get_actor(4, 1, conf.action_high, seed_int=1, layer1_size=256, layer2_size=128)
+    critic = m.get_critic(4, 1, layer1_size=256, layer2_size=128, action_layer_size=48)
+    t_actor = m.get_actor(4, 1, conf.action_high, seed_int=1, layer1_size=256, layer2_size=128)
+    t_critic = m.get_critic(4, 1, layer1_size=256, layer2_size=128, action_layer_size=48)
+    ac, cr, ta, tc = make_nets(77)
+    for obj, ref, names in ((actor, ac, D.ACTOR_WEIGHTS), (t_actor, ta, D.ACTOR_WEIGHTS), (critic, cr, D.CRITIC_WEIGHTS), (t_critic, tc, D.CRITIC_WEIGHTS)):
+        obj.set_weights([ref[k] for k in names])
+        assert len(obj.weights) == len(names) and len(obj.trainable_variables) == len(names) - (4 if "W1" in ref else 6)
+    g = golden("replay")
+    rb = mods["rb"].ReplayBuffer(128, 16, 4, 1, 2)
+    for i in range(128):
+        rb.add((g["S"][i], g["A"][i], g["R"][i], g["S2"][i]))
+    idx = g["idx"][1]   # drawn by the reference at i = 127 (range 128)
+    cg, ag = mods["trainer"].Trainer(conf=conf).learn(rb, actor, critic, t_actor, t_critic, indices=idx)
+    batch = (g["ring_s"][idx][:, :4], g["ring_a"][idx], g["ring_r"][idx], g["ring_s2"][idx])
+    # ring arrays in the golden are the final (wrapped) state of a 300-add run; rebuild the 128-add state
+    batch = (g["S"][:128][idx], g["A"][:128][idx], g["R"][:128][idx].reshape(-1, 1), g["S2"][:128][idx])
+    ocg, oag, _ = D.learn(ac, cr, ta, tc, batch, gamma=conf.gamma, high=conf.action_high)
+    assert len(cg) == 14 and len(ag) == 10
+    for t, name in zip(cg, D.CRITIC_TRAINABLE):
+        assert _nrm(t.cpu().numpy(), ocg[name].reshape(t.shape)) < 2e-4, name
+    for t, name in zip(ag, D.ACTOR_TRAINABLE):
+        assert _nrm(t.cpu().numpy(), oag[name].reshape(t.shape)) < 2e-4, name
+    a_out = actor(torch.as_tensor(batch[0], dtype=torch.float32))
+    assert a_out.shape == (16, 1) and _nrm(a_out.cpu().numpy(), D.actor_forward(ac, batch[0])[0]) < 1e-5
+    q_out = critic([batch[0], batch[1]])
+    assert _nrm(q_out.cpu().numpy(), D.critic_forward(cr, batch[0], batch[1])[0]) < 1e-5
+
+
+def test_population_act_on_native_state(mods):
+    from avddpg_b200.environment import BatchedPlatoons
+    conf = mods["Config"](pl_size=3)
+    G, M, E = 2, 3, 50
+    pop = mods["trainer"].DDPGPopulation(G, M, conf)
+    nets = [make_nets(60 + a) for a in range(G * M)]
+    for a, (ac, _, _, _) in enumerate(nets):
+        pop.actor.load_named(a, ac)
+    env = BatchedPlatoons(G * E, M, conf)
+    env.reset()
+    pop.act(env.native_state, env.action_mu, envs_per_group=E)
+    st = env.state.cpu().numpy()      # [P, M, 4]
+    mu = env.action_mu.cpu().numpy()   # [M, P]
+    for m in range(M):
+        for g in range(G):
+            ref, _ = D.actor_forward(nets[m * G + g][0], st[g * E:(g + 1) * E, m])
+            assert _nrm(mu[m, g * E:(g + 1) * E], ref.ravel()) < 1e-5
