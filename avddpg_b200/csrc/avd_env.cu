@@ -314,7 +314,7 @@ static int check_env_args(const avd_env_params* prm, const avd_env_io* io) {
     AVD_REQUIRE(prm && io, "null params");
     AVD_REQUIRE(prm->M >= 1 && prm->M <= AVD_MAX_FOLLOWERS, "M=%d outside 1..%d", prm->M, AVD_MAX_FOLLOWERS);
     AVD_REQUIRE(io->P >= 0, "negative platoon count");
-    AVD_REQUIRE(io->prev_a, "prev_a buffer is required");
+    AVD_REQUIRE(io->P == 0 || io->prev_a, "prev_a buffer is required");
     return AVD_OK;
 }
 
@@ -341,8 +341,8 @@ extern "C" int avd_ou_sample(const avd_env_params* prm, float* state, float* out
 
 extern "C" int avd_env_reset(const avd_env_params* prm, const avd_env_io* io, const uint8_t* mask, void* stream) {
     if (int rc = check_env_args(prm, io)) return rc;
-    AVD_REQUIRE(io->x_out, "x_out is required");
     if (io->P == 0) return AVD_OK;
+    AVD_REQUIRE(io->x_out, "x_out is required");
     env_reset_kernel<<<grid_for(io->P), 256, 0, (cudaStream_t)stream>>>(*prm, *io, mask);
     AVD_LAUNCH_OK();
     return AVD_OK;
@@ -350,6 +350,7 @@ extern "C" int avd_env_reset(const avd_env_params* prm, const avd_env_io* io, co
 
 extern "C" int avd_env_step(const avd_env_params* prm, const avd_env_io* io, void* stream) {
     if (int rc = check_env_args(prm, io)) return rc;
+    if (io->P == 0) return AVD_OK;
     AVD_REQUIRE(io->x_in && io->x_out && io->action_mu && io->reward && io->done, "x_in/x_out/action_mu/reward/done are required");
     AVD_REQUIRE(io->x_in != io->x_out, "x_in and x_out must not alias (ping-pong state buffers)");
     AVD_REQUIRE(!io->ring || io->ring_capacity > 0, "ring given with capacity %lld", (long long)io->ring_capacity);
@@ -378,6 +379,7 @@ extern "C" int avd_env_step_host(const avd_env_params* prm, const avd_env_io* io
                                  const float* leader_exog_host, float* obs_host, float* reward_host,
                                  uint8_t* done_host, void* stream) {
     if (int rc = check_env_args(prm, io)) return rc;
+    if (io->P == 0) return AVD_OK;
     AVD_REQUIRE(actions_host && obs_host && reward_host && done_host, "null host buffer");
     cudaStream_t st = (cudaStream_t)stream;
     const size_t n = (size_t)prm->M * (size_t)io->P;

@@ -127,6 +127,92 @@ class DDPGPopulation:
         self.launches += 2
 
 
+class BatchedTrainer:
+    """The hot loop of workers/trainer.py:251-271 for a whole population on one GPU (rank):
+
+        actor(prev_state) -> OU noise + clip -> Platoon.step -> ReplayBuffer.add        (advance_environment, 282-302)
+        if buffer_counter > batch_size: sample -> learn -> [FRL stash] -> Adam, Polyak   (train_all_models, 304-359)
+        [federated round on the steps the predicates select]                             (400-456)
+
+    G platoon-groups x E environments per group x M followers; the M*G agents' weights live in a
+    DDPGPopulation, the M*G*E replay rings in ReplayRings, the platoons in BatchedPlatoons.  Everything stays
+    on the device; the host only launches kernels (optionally a captured CUDA graph of the whole step).
+    Per-platoon episode handling replaces the reference's "any platoon terminal ends the episode for all"
+    (trainer.py:268-269): a platoon that terminates or reaches steps_per_episode is reset inside the env kernel.
+    """
+
+    def __init__(self, conf, num_groups: int, envs_per_group: int = 1, *, ring_capacity=None, rank: int = 0, world: int = 1,
+                 process_group=None, precision: int = 0, seed=None, track_kinematics: bool = False):
+        from .environment import BatchedPlatoons
+        from .replaybuffer import ReplayRings
+        self.conf, self.G, self.E, self.M = conf, int(num_groups), int(envs_per_group), int(conf.pl_size)
+        self.P = self.G * self.E
+        self.rank, self.world = rank, world
+        seed = int(getattr(conf, "random_seed", 1) if seed is None else seed)
+        cap = int(conf.buffer_size if ring_capacity is None else ring_capacity)
+        self.rings = ReplayRings(cap, self.M, self.P, int(conf.batch_size), seed=seed, ring_id_base=rank * self.M * self.P)
+        self.env = BatchedPlatoons(self.P, self.M, conf, platoon_id_base=rank * self.P, seed=seed, ring=self.rings,
+                                   clock=self.rings.clock, auto_reset=True, collect_stats=True, track_kinematics=track_kinematics)
+        self.pop = DDPGPopulation(self.G, self.M, conf, num_states=self.env.num_states, rows_per_agent=self.E * int(conf.batch_size),
+                                  seed=seed, precision=precision)
+        self.fed = None
+        if is_fed_enabled(conf):
+            from .server.federated import FederatedAggregator
+            self.fed = FederatedAggregator(self.pop, conf, process_group=process_group)
+        self.buffer_counter = 0          # == ReplayBuffer.buffer_counter of every ring
+        self.step_in_run = 0
+        self.episode = 0                 # used only by the FRL scheduling predicates
+        self.graph = None
+        self.env.reset()
+
+    @property
+    def gpu_launches(self):
+        return self.env.gpu_launches + self.pop.launches
+
+    def step(self, learn: bool = True):
+        """One environment step for every platoon + one learn() for every agent (when the buffers hold more than
+        batch_size transitions, trainer.py:322)."""
+        env, pop, rings, conf = self.env, self.pop, self.rings, self.conf
+        pop.act(env.native_state, env.action_mu, self.E)
+        env.step_native(explore=True, gen_exog=True, advance_clock=False)
+        rings.clock.advance(step=1, ring=1)
+        self.buffer_counter += 1
+        if learn and self.buffer_counter > conf.batch_size:
+            s, a, r, s2 = rings.sample(advance_clock=True)
+            fed_step = self.fed is not None and is_valid_update_step(conf, self.step_in_run)
+            pop.learn(s, a, r, s2, apply_updates=not fed_step)          # trainer.py:345: local update unless FRL step
+            if self.fed is not None:
+                if is_valid_step_for_federated_training_with_gradients(conf, self.episode, self.step_in_run):
+                    self.fed.aggregate_gradients()
+                if is_valid_step_for_federated_training_with_weights(conf, self.episode, self.step_in_run):
+                    self.fed.aggregate_weights()
+        self.step_in_run += 1
+
+    def capture(self, warmup: int = 3):
+        """Capture one full step (learn included) into a CUDA graph; afterwards `replay()` costs one launch."""
+        assert self.buffer_counter > self.conf.batch_size, "fill the buffers past batch_size before capturing"
+        stream = torch.cuda.Stream()
+        stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(stream):
+            for _ in range(warmup):
+                self.step()
+        torch.cuda.current_stream().wait_stream(stream)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        cur, counters = self.env._cur, (self.buffer_counter, self.step_in_run)
+        with torch.cuda.graph(self.graph):
+            self.step()
+            self.step()      # two steps per graph so the ping-pong state buffers end where they started
+        assert self.env._cur == cur
+        self.buffer_counter, self.step_in_run = counters     # capturing executes nothing on the device
+        return self.graph
+
+    def replay(self):
+        self.graph.replay()
+        self.buffer_counter += 2
+        self.step_in_run += 2
+
+
 class Trainer:
     """Reference-shaped wrapper: ``learn`` on single-agent model objects (trainer.py:472-508)."""
 

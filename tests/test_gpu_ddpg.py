@@ -286,3 +286,42 @@ def test_population_act_on_native_state(mods):
         for g in range(G):
             ref, _ = D.actor_forward(nets[m * G + g][0], st[g * E:(g + 1) * E, m])
             assert _nrm(mu[m, g * E:(g + 1) * E], ref.ravel()) < 1e-5
+
+
+def test_batched_trainer_end_to_end(mods):
+    """act -> env -> replay add -> sample -> learn -> Adam -> Polyak for a small population; weights move, the
+    replay rings fill, statistics stay finite; CUDA-graph replay continues the same trajectory."""
+    conf = mods["Config"](pl_size=2, batch_size=8, buffer_size=64)
+    tr = mods["trainer"].BatchedTrainer(conf, num_groups=2, envs_per_group=3, ring_capacity=64)
+    w0 = tr.pop.actor.flat.clone()
+    for _ in range(8):
+        tr.step()
+    assert torch.equal(w0, tr.pop.actor.flat)            # nothing learned until buffer_counter > batch_size (trainer.py:322)
+    for _ in range(6):
+        tr.step()
+    torch.cuda.synchronize()
+    assert not torch.equal(w0, tr.pop.actor.flat) and torch.isfinite(tr.pop.actor.flat).all() and torch.isfinite(tr.pop.critic.flat).all()
+    assert tr.pop.actor.step.tolist() == [6] * 4
+    clk = tr.rings.clock.read()
+    assert clk["ring_count"] == 14 and clk["step_tick"] == 14 and clk["update_tick"] == 6
+    tr.capture(warmup=1)
+    before = tr.pop.actor.flat.clone()
+    tr.replay(); tr.replay()
+    torch.cuda.synchronize()
+    assert not torch.equal(before, tr.pop.actor.flat) and torch.isfinite(tr.pop.actor.flat).all()
+    assert tr.rings.clock.read()["ring_count"] == 14 + 1 + 4 == tr.buffer_counter   # capture itself executes nothing
+
+
+def test_batched_trainer_interfrl_keeps_replicas_identical(mods):
+    """interfrl + gradients with delay 1 == synchronous data-parallel SGD: all platoons' agents for a follower
+    start identical (trainer.py:121-131) and must stay identical after federated rounds."""
+    conf = mods["Config"](pl_size=2, batch_size=8, buffer_size=64, fed_method="interfrl", weighted_average_enabled=False)
+    tr = mods["trainer"].BatchedTrainer(conf, num_groups=3, envs_per_group=1, ring_capacity=64)
+    for _ in range(14):
+        tr.step()
+    torch.cuda.synchronize()
+    G = 3
+    for m in range(2):
+        rows = tr.pop.actor.flat[m * G:(m + 1) * G]
+        assert torch.equal(rows[0], rows[1]) and torch.equal(rows[0], rows[2])
+    assert tr.fed.rounds == 6 and tr.pop.actor.step.tolist() == [6] * 6

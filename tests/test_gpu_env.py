@@ -149,7 +149,7 @@ def test_large_batch_vs_oracle(mods, P, M, method):
         # a vehicle sitting within fp32 rounding of the terminal threshold may legitimately fall on either
         # side of it in fp32 vs float64: leave those (a handful in 5e5 vehicles) out of the comparison
         tie = (np.abs(np.abs(pre[..., 0]) - conf.max_ep) < 1e-4) | (np.abs(np.abs(pre[..., 1]) - conf.max_ev) < 1e-4)
-        assert tie.mean() < 1e-3
+        assert tie.sum() <= max(3, 1e-3 * tie.size)
         ok_pl = ~tie.any(axis=1)
         assert np.array_equal(d.cpu().numpy()[ok_pl], do[ok_pl]), k
         assert _normwise(o.cpu().numpy(), oo) <= REL
