@@ -169,12 +169,17 @@ class BatchedTrainer:
     def gpu_launches(self):
         return self.env.gpu_launches + self.pop.launches
 
-    def step(self, learn: bool = True):
+    def step(self, learn: bool = True, host_leader_exog: Optional[torch.Tensor] = None):
         """One environment step for every platoon + one learn() for every agent (when the buffers hold more than
-        batch_size transitions, trainer.py:322)."""
+        batch_size transitions, trainer.py:322).  host_leader_exog: pinned host tensor [P] with the leaders'
+        exogenous inputs (the reference draws them on the host, trainer.py:292-295); None = drawn on the device."""
         env, pop, rings, conf = self.env, self.pop, self.rings, self.conf
         pop.act(env.native_state, env.action_mu, self.E)
-        env.step_native(explore=True, gen_exog=True, advance_clock=False)
+        if host_leader_exog is not None:
+            env.leader_exog.copy_(host_leader_exog, non_blocking=True)
+            env.step_native(explore=True, leader_exog=True, advance_clock=False)
+        else:
+            env.step_native(explore=True, gen_exog=True, advance_clock=False)
         rings.clock.advance(step=1, ring=1)
         self.buffer_counter += 1
         if learn and self.buffer_counter > conf.batch_size:

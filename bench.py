@@ -112,37 +112,30 @@ def _barrier(world):
 
 
 # --------------------------------------------------------------------------------------------- native arm
-def build_population(rank, P=P_C2, M=M_C2, ring_cap=RING_CAP, prefill=True):
+LEARN_MACS_PER_SAMPLE = 340_464          # reference-equivalent MACs per sampled transition
+ENV_BYTES_PER_VEHICLE_STEP = 48
+
+
+def build_trainer(rank, world, args, pg=None):
     import torch
     from avddpg_b200.config import Config
-    from avddpg_b200.environment import BatchedPlatoons
-    from avddpg_b200.replaybuffer import ReplayRings
-    conf = Config(pl_size=M, num_platoons=P)
+    from avddpg_b200.trainer import BatchedTrainer
+    conf = Config(pl_size=M_C2, num_platoons=P_C2)
     free, _ = torch.cuda.mem_get_info()
-    need = ring_cap * M * P * 40
-    if need > 0.8 * free:   # never drive the box out of memory: shrink the ring, say so
-        ring_cap = int(0.5 * free / (M * P * 40))
-    rings = ReplayRings(ring_cap, M, P, BATCH, seed=conf.random_seed, ring_id_base=rank * M * P)
-    env = BatchedPlatoons(P, M, conf, platoon_id_base=rank * P, ring=rings, clock=rings.clock, auto_reset=True,
-                          collect_stats=True)
-    env.reset()
-    if prefill:
-        rings.fill_synthetic()      # steady state: sampling range == capacity from the first timed step
-    return conf, env, rings
-
-
-def native_step(env, rings):
-    """act(OU+clip) + Platoon.step + ReplayBuffer.add (one fused launch) -> sample 64/ring (2 launches)."""
-    env.step_native(explore=True, gen_exog=True, advance_clock=False)
-    rings.sample_indices()
-    rings.gather()
-    env.clock.advance(step=1, ring=1, update=1)
-    return 4     # kernels launched
+    ring_cap = RING_CAP
+    if ring_cap * M_C2 * P_C2 * 40 > 0.6 * free:      # never drive the box out of memory: shrink the ring and say so
+        ring_cap = int(0.4 * free / (M_C2 * P_C2 * 40))
+    tr = BatchedTrainer(conf, num_groups=1, envs_per_group=P_C2, ring_capacity=ring_cap, rank=rank, world=world,
+                        process_group=pg, precision=args.precision)
+    tr.rings.fill_synthetic()                # steady state: sampling range == capacity from the first timed step
+    tr.buffer_counter = ring_cap
+    return conf, tr
 
 
 def time_env_roofline(P_big, M, steps=20, warmup=5):
     """Env-step kernel alone on a population whose working set exceeds L2 (126 MB): CUDA events around each
-    launch, average duration -> achieved algorithmic GB/s."""
+    launch on the launching stream, average duration -> achieved algorithmic GB/s (48 B per vehicle-step:
+    x[4], prev_a, u in; x'[4], prev_a', reward out; +5 B per platoon for the leader input and the done flag)."""
     import torch
     from avddpg_b200.config import Config
     from avddpg_b200.environment import BatchedPlatoons
@@ -162,12 +155,22 @@ def time_env_roofline(P_big, M, steps=20, warmup=5):
     torch.cuda.synchronize()
     ms = sorted(a.elapsed_time(b) for a, b in evs)
     avg = sum(ms) / len(ms)
-    bytes_per_vehicle = 48.0
-    per_platoon = 5.0
-    alg = P_big * (M * bytes_per_vehicle + per_platoon)
+    alg = P_big * (M * ENV_BYTES_PER_VEHICLE_STEP + 5.0)
     del env
     torch.cuda.empty_cache()
-    return dict(avg_ms=avg, min_ms=ms[0], alg_bytes=alg, working_set_mb=P_big * M * 4 * (8 + 1 + 1 + 1) / 1e6)
+    return dict(avg_ms=avg, min_ms=ms[0], alg_bytes=alg, working_set_mb=P_big * M * 4 * 11 / 1e6)
+
+
+def _timed(fn, n, world):
+    import torch
+    _barrier(world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    _barrier(world)
+    return _max_over_ranks(e0.elapsed_time(e1), world) / n
 
 
 def run_native(args):
@@ -176,75 +179,105 @@ def run_native(args):
     from avddpg_b200 import _lib
     _lib.require_device()
     hbm_peak, tf_peak, peak_src = _peaks()
-    conf, env, rings = build_population(rank)
+    conf, tr = build_trainer(rank, world, args)
+    env, rings, pop = tr.env, tr.rings, tr.pop
     P, M = env.P, env.M
-    launches = 0
-    for _ in range(max(3, args.warmup)):
-        native_step(env, rings)
-    # ---- device-resident timing (inputs already in HBM)
-    _barrier(world)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    warm = max(3, args.warmup)
+    for _ in range(warm):
+        tr.step()
+    if args.graph:
+        tr.capture(warmup=1)
+    step_fn = (lambda: tr.replay()) if args.graph else (lambda: tr.step())
+    steps_per_call = 2 if args.graph else 1
+    calls = max(1, args.steps // steps_per_call)
+
+    # ---- device-resident timing of the whole training step (inputs already in HBM)
+    l0 = tr.gpu_launches
     with ClockSampler(local) as clk:
-        e0.record()
-        for _ in range(args.steps):
-            launches += native_step(env, rings)
-        e1.record()
-        _barrier(world)
-    ms_total = _max_over_ranks(e0.elapsed_time(e1), world)
-    ms_step = ms_total / args.steps
+        ms_call = _timed(step_fn, calls, world)
+    ms_step = ms_call / steps_per_call
+    launches = (tr.gpu_launches - l0) if not args.graph else calls * steps_per_call * 45
     value = world * P * M / (ms_step * 1e-3)
 
-    # ---- end to end through host buffers: pinned leader inputs in, reward/done statistics out, every step
+    # ---- attribution: env part (act + env step + replay add) and learn part (sample + learn + Adam + Polyak) alone
+    def env_part():
+        pop.act(env.native_state, env.action_mu, tr.E)
+        env.step_native(explore=True, gen_exog=True, advance_clock=False)
+        rings.clock.advance(step=1, ring=1)
+
+    def learn_part():
+        s, a, r, s2 = rings.sample(advance_clock=True)
+        pop.learn(s, a, r, s2, apply_updates=True)
+
+    n_attr = max(5, min(30, args.steps // 4))
+    ms_env = _timed(env_part, n_attr, world)
+    ms_learn = _timed(learn_part, n_attr, world)
+
+    # ---- end to end through host buffers: pinned leader inputs in, reward/done statistics + losses out, every step
     h_exog = torch.zeros(P, dtype=torch.float32).pin_memory()
-    h_stats = torch.zeros(M + 1, dtype=torch.float32).pin_memory()
+    h_out = torch.zeros(M + 1 + 2 * pop.A, dtype=torch.float32).pin_memory()
     gen = torch.Generator().manual_seed(1 + rank)
 
     def e2e_step():
         h_exog.normal_(0, 0.1, generator=gen)
-        env.leader_exog.copy_(h_exog, non_blocking=True)
         env.stats.zero_()
-        env.step_native(explore=True, leader_exog=True, advance_clock=False)
-        rings.sample_indices()
-        rings.gather()
-        env.clock.advance(step=1, ring=1, update=1)
-        h_stats.copy_(env.stats, non_blocking=True)
+        tr.step(host_leader_exog=h_exog)
+        h_out[: M + 1].copy_(env.stats, non_blocking=True)
+        h_out[M + 1:].copy_(pop.loss.reshape(-1), non_blocking=True)
         torch.cuda.current_stream().synchronize()
-        return float(h_stats[0])
+        return float(h_out[0])
 
     for _ in range(3):
         e2e_step()
     _barrier(world)
+    n_e2e = max(5, min(args.steps, 50))
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(n_e2e):
         e2e_step()
     _barrier(world)
-    e2e_ms = _max_over_ranks((time.perf_counter() - t0) * 1e3, world) / args.steps
-    e2e = {"value": world * P * M / (e2e_ms * 1e-3), "unit": METRIC, "h2d_bytes_per_step": P * 4, "d2h_bytes_per_step": (M + 1) * 4,
-           "ms_per_step": e2e_ms}
+    e2e_ms = _max_over_ranks((time.perf_counter() - t0) * 1e3, world) / n_e2e
+    e2e = {"value": world * P * M / (e2e_ms * 1e-3), "unit": METRIC, "h2d_bytes_per_step": P * 4,
+           "d2h_bytes_per_step": int(h_out.numel()) * 4, "ms_per_step": e2e_ms, "steps": n_e2e,
+           "api": "BatchedTrainer.step(host_leader_exog=pinned) + D2H of reward/done statistics and losses"}
 
     out = None
     if rank == 0:
-        # ---- roofline of the env kernel (HBM-bound) on a >L2 population, this GPU only
+        rows = pop.A * pop.R
+        learn_flops = 2.0 * LEARN_MACS_PER_SAMPLE * rows
+        learn_tf = learn_flops / (ms_learn * 1e-3) / 1e12
         rl = time_env_roofline(args.roofline_platoons, M)
         achieved = rl["alg_bytes"] / (rl["avg_ms"] * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": "env_step_kernel<4>", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
-                    "population": f"{args.roofline_platoons} platoons x {M} (state working set {rl['working_set_mb']:.0f} MB > 126 MB L2)",
-                    "alg_bytes_per_vehicle_step": 48, "avg_launch_ms": rl["avg_ms"],
-                    "vehicle_steps_per_s": args.roofline_platoons * M / (rl["avg_ms"] * 1e-3)}
+        roofline_env = {"bound": "hbm", "kernel": "env_step_kernel<4>", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                        "population": f"{args.roofline_platoons} platoons x {M} (state working set {rl['working_set_mb']:.0f} MB > 126 MB L2)",
+                        "alg_bytes_per_vehicle_step": ENV_BYTES_PER_VEHICLE_STEP, "avg_launch_ms": rl["avg_ms"],
+                        "vehicle_steps_per_s": args.roofline_platoons * M / (rl["avg_ms"] * 1e-3)}
+        roofline_learn = {"bound": "tensor", "kernel": "learn step GEMMs (" + ("bf16 tcgen05" if args.precision else "fp32 SIMT parity mode") + ")",
+                          "achieved": learn_tf, "peak": tf_peak / 1e0, "unit": "TFLOP/s", "frac": learn_tf / tf_peak, "traffic": None,
+                          "peak_source": peak_src + " bf16 sustained", "alg_flops_per_step": learn_flops,
+                          "alg_macs_per_sample": LEARN_MACS_PER_SAMPLE, "rows_per_step": rows, "learn_ms": ms_learn}
+        dominant = roofline_learn if ms_learn > ms_env else roofline_env
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             from oracle import cpu_baseline
-            cpu = cpu_baseline.time_env_steps(M=M, target_seconds=args.cpu_seconds)
-        out = {"metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-               "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-               "data": "synthetic", "impl": "native",
-               "config": {"workload": WORKLOAD, "platoons_per_gpu": P, "followers": M, "ring_capacity": rings.capacity,
+            cpu = cpu_baseline.time_env_steps(M=M, target_seconds=args.cpu_seconds, with_learn=True)
+            cpu_env = cpu_baseline.time_env_steps(M=M, target_seconds=max(2.0, args.cpu_seconds / 3), with_learn=False)
+            cpu["env_only_loop"] = {"value": cpu_env["value"], "sample": cpu_env["sample"]}
+        out = {"metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": calls * steps_per_call, "warmup": warm,
+               "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": "bf16" if args.precision else "f32", "data": "synthetic", "impl": "native",
+               "config": {"workload": WORKLOAD, "platoons_per_gpu": P, "followers": M, "agents_per_gpu": pop.A,
+                          "rows_per_agent_update": pop.R, "ring_capacity": rings.capacity, "cuda_graph": bool(args.graph),
                           "l2": "C2 state is 0.8 MB/step (L2-resident by nature); replay gathers hit a pre-filled "
-                                f"{rings.capacity * M * P * 40 / 1e9:.1f} GB ring (>> L2); roofline measured on a >L2 population",
-                          "learn": "not in this step yet (env+OU+replay add+sample)"},
-               "clocks": clk.summary(), "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
-               "platoon_steps_per_s": value / M}
+                                f"{rings.capacity * M * P * 40 / 1e9:.1f} GB ring and the learn workspace is "
+                                f"{pop._ws.numel() / 1e9:.1f} GB (both >> 126 MB L2); env roofline measured on a >L2 population",
+                          "step": "act(actor fwd) + OU/clip + Platoon.step + ReplayBuffer.add + sample(64/ring) + learn + Adam x2 + Polyak"},
+               "clocks": clk.summary(), "e2e": e2e, "gpu_launches": launches,
+               "roofline": dominant, "roofline_env": roofline_env, "roofline_learn": roofline_learn, "cpu_baseline": cpu,
+               "platoon_steps_per_s": value / M,
+               "ddpg_minibatch_updates_per_s": world * P * M / (ms_step * 1e-3),
+               "ddpg_weight_updates_per_s": world * pop.A / (ms_step * 1e-3),
+               "ms_env_part": ms_env, "ms_learn_part": ms_learn}
         print(json.dumps(out))
     if world > 1:
         import torch.distributed as dist
@@ -263,7 +296,7 @@ def run_reference(args):
     from oracle import cpu_baseline
     total = max(1, args.steps)
     budget = max(0.25, min(args.cpu_seconds, 150.0 / (total + args.warmup)))
-    pool = cpu_baseline.EnvLoopPool(M=M_C2)
+    pool = cpu_baseline.EnvLoopPool(M=M_C2, with_learn=True)
     vals, steps, slowest = [], 0, 0.0
     try:
         for i in range(args.warmup + total):
@@ -284,12 +317,14 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--roofline-platoons", type=int, default=4 * 1024 * 1024)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", type=int, default=0, help="0: fp32 SIMT learn kernels (parity mode); 1: bf16 tcgen05 GEMMs")
+    ap.add_argument("--graph", action="store_true", help="replay a captured CUDA graph of the training step")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
