@@ -275,6 +275,18 @@ int avd_fed_broadcast(float* out, int64_t out_pitch, const float* in, int64_t in
                       int32_t n_members, int64_t member_stride_s, int64_t member_stride_x, const uint8_t* apply_mask,
                       int64_t n, void* stream);
 
+/* ---- tensor-core GEMM (tcgen05 + TMEM + TMA), the building block of precision = 1 ------------------
+ * C[b] (fp32, M x N, row pitch ldc) = / += op(A[b]) op(B[b]) with bf16 operands and fp32 accumulation.
+ *   layout 0 (TN: forward, dgrad): A[b] is [M][K] (pitch lda), B[b] is [N][K] (pitch ldb); C = A B^T; splitk>1 accumulates
+ *                                  atomically into C (caller zeroes it).
+ *   layout 1 (NT: wgrad)         : A[b] is [K][M], B[b] is [K][N]; C += A^T B, always accumulated atomically (the
+ *                                  contraction runs over batch rows and is split over `splitk` CTAs).
+ * Pitches and batch strides are in elements and must be multiples of 8; operands 16-byte aligned.
+ * Replaces the Dense(256->128) / Dense(304->128) matmuls and their gradients inside Trainer.learn
+ * (workers/trainer.py:492-506 via agent/model.py:30,74).                                                  */
+int avd_gemm_bf16(int layout, int batch, int M, int N, int K, const void* A, int64_t lda, int64_t a_batch, const void* B,
+                  int64_t ldb, int64_t b_batch, float* C, int64_t ldc, int64_t c_batch, int splitk, void* stream);
+
 /* ---- raw RNG access (parity tests: bit-exact against oracle/philox_np.py) ------------------- */
 int avd_rng_words(uint32_t* out4 /*[n][4]*/, int64_t n, uint64_t id_base, uint32_t tick, uint32_t purpose,
                   uint64_t seed, void* stream);
