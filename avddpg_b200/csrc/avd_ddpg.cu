@@ -18,36 +18,64 @@
 //   y = g*(x-mu)/sqrt(var+1e-3)+be, with trainable g/be and frozen mu/var.
 #include <algorithm>
 
+#include <cuda_bf16.h>
+
 #include "avd_common.cuh"
 #include "avd_ddpg_layout.cuh"
 
 namespace avd {
 
+typedef __nv_bfloat16 bf16;
+
+namespace fused {  // avd_fused.cu
+bool supported(const avd_net_dims& d, bool critic);
+int forward(const avd_net_dims& d, bool critic, int A, int64_t R, const float* params, int64_t pstride, const bf16* W2T, const float* s,
+            int64_t s_rs, int64_t s_cs, const float* act, bf16* H_out, float* Z_out, int head, const float* rew, float gamma, float high,
+            float* out, cudaStream_t st);
+}
+
+namespace umma {   // avd_umma.cu
+int gemm_bf16(int layout, int batch, int M, int N, int K, const void* A, int64_t lda, int64_t a_batch, const void* B, int64_t ldb,
+              int64_t b_batch, float* C, int64_t ldc, int64_t c_batch, int splitk, cudaStream_t st);
+}
+
+__device__ __forceinline__ void store_out(float* p, float v) { *p = v; }
+__device__ __forceinline__ void store_out(bf16* p, float v) { *p = __float2bfloat16_rn(v); }
+
 // ------------------------------------------------------------------------------------------------
 // layer 1: H[n][f] = bn(relu(x[n] . W[:,f] + b[f]))   (state columns, then -- critic -- action columns)
 // ------------------------------------------------------------------------------------------------
-constexpr int kL1Rows = 32;
+constexpr int kL1Rows = 128;
+constexpr int kL1BwdRows = 256;
 
-template <bool CRITIC>
+__device__ __forceinline__ void store_pair(float* p, float v0, float v1) { *reinterpret_cast<float2*>(p) = make_float2(v0, v1); }
+__device__ __forceinline__ void store_pair(bf16* p, float v0, float v1) {
+    *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(v0, v1);
+}
+
+// One thread owns a PAIR of adjacent columns (packed 4/8-byte stores, a warp writes 128/256 contiguous bytes per row);
+// l1 and la must be even so that a pair never straddles the state/action boundary.
+template <bool CRITIC, typename TOut>
 __global__ void __launch_bounds__(128) l1_forward_kernel(avd_net_dims d, const float* __restrict__ params, int64_t pstride,
                                                          const float* __restrict__ s, int64_t s_rs, int64_t s_cs,
-                                                         const float* __restrict__ act, int64_t R, float* __restrict__ H) {
+                                                         const float* __restrict__ act, int64_t R, TOut* __restrict__ H) {
     const int agent = blockIdx.y;
     const float* P = params + (int64_t)agent * pstride;
     const int F = CRITIC ? d.l1 + d.la : d.l1;
     const int64_t row0 = (int64_t)blockIdx.x * kL1Rows;
     const int nrows = (int)min((int64_t)kL1Rows, R - row0);
     const int64_t base = (int64_t)agent * R + row0;
+    const int nx = d.ns + (CRITIC ? 1 : 0);
     __shared__ float xs[kL1Rows][9];  // up to 8 state words + action
-    for (int i = threadIdx.x; i < nrows * (d.ns + (CRITIC ? 1 : 0)); i += blockDim.x) {
-        const int r = i / (d.ns + (CRITIC ? 1 : 0)), k = i % (d.ns + (CRITIC ? 1 : 0));
+    for (int i = threadIdx.x; i < nrows * nx; i += blockDim.x) {
+        const int r = i / nx, k = i % nx;
         xs[r][k] = (k < d.ns) ? s[(base + r) * s_rs + k * s_cs] : act[base + r];
     }
     __syncthreads();
-    int64_t oW, ob, og, obe, omu, ovar;
-    for (int f = threadIdx.x; f < F; f += blockDim.x) {
+    for (int f = 2 * threadIdx.x; f < F; f += 2 * blockDim.x) {
         const bool is_act = CRITIC && f >= d.l1;
         const int c = is_act ? f - d.l1 : f;
+        int64_t oW, ob, og, obe, omu, ovar;
         if (CRITIC) {
             const CriticOff o = critic_off(d);
             oW = is_act ? o.Wa : o.Ws; ob = is_act ? o.ba : o.bs; og = is_act ? o.ga : o.gs; obe = is_act ? o.bea : o.bes;
@@ -58,22 +86,27 @@ __global__ void __launch_bounds__(128) l1_forward_kernel(avd_net_dims d, const f
         }
         const int width = is_act ? d.la : d.l1;
         const int nin = is_act ? 1 : d.ns;
-        float w[8];
+        const int xoff = is_act ? d.ns : 0;
+        float w0[8], w1[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) w[k] = (k < nin) ? P[oW + (int64_t)k * width + c] : 0.0f;
-        const float b = P[ob + c];
-        const float inv = 1.0f / sqrtf(P[ovar + c] + kBnEps);
-        const float sc = P[og + c] * inv, sh = P[obe + c] - P[omu + c] * sc;
+        for (int k = 0; k < 8; ++k) {
+            w0[k] = (k < nin) ? P[oW + (int64_t)k * width + c] : 0.0f;
+            w1[k] = (k < nin) ? P[oW + (int64_t)k * width + c + 1] : 0.0f;
+        }
+        const float b0 = P[ob + c], b1 = P[ob + c + 1];
+        const float inv0 = 1.0f / sqrtf(P[ovar + c] + kBnEps), inv1 = 1.0f / sqrtf(P[ovar + c + 1] + kBnEps);
+        const float sc0 = P[og + c] * inv0, sc1 = P[og + c + 1] * inv1;
+        const float sh0 = P[obe + c] - P[omu + c] * sc0, sh1 = P[obe + c + 1] - P[omu + c + 1] * sc1;
         for (int r = 0; r < nrows; ++r) {
-            float z = b;
-            if (is_act) {
-                z = fmaf(xs[r][d.ns], w[0], z);
-            } else {
+            float z0 = b0, z1 = b1;
 #pragma unroll
-                for (int k = 0; k < 8; ++k)
-                    if (k < nin) z = fmaf(xs[r][k], w[k], z);
-            }
-            H[(base + r) * F + f] = fmaf(fmaxf(z, 0.0f), sc, sh);
+            for (int k = 0; k < 8; ++k)
+                if (k < nin) {
+                    const float x = xs[r][xoff + k];
+                    z0 = fmaf(x, w0[k], z0);
+                    z1 = fmaf(x, w1[k], z1);
+                }
+            store_pair(H + (base + r) * F + f, fmaf(fmaxf(z0, 0.0f), sc0, sh0), fmaf(fmaxf(z1, 0.0f), sc1, sh1));
         }
     }
 }
@@ -83,7 +116,7 @@ template <bool CRITIC>
 __global__ void __launch_bounds__(128) l1_backward_kernel(avd_net_dims d, const float* __restrict__ params, int64_t pstride,
                                                           const float* __restrict__ s, const float* __restrict__ act, int64_t R,
                                                           const float* __restrict__ dH, float* __restrict__ grads, int64_t gstride) {
-    constexpr int ROWS = 64;
+    constexpr int ROWS = kL1BwdRows;   // one set of atomics per column and 512 rows
     const int agent = blockIdx.y;
     const float* P = params + (int64_t)agent * pstride;
     float* G = grads + (int64_t)agent * gstride;
@@ -119,27 +152,34 @@ __global__ void __launch_bounds__(128) l1_backward_kernel(avd_net_dims d, const 
         const float inv = 1.0f / sqrtf(P[ovar + c] + kBnEps);
         const float ginv = P[og + c] * inv;
         float db = 0.0f, dg = 0.0f, dbe = 0.0f;
-        for (int r = 0; r < nrows; ++r) {
-            const float dh = dH[(base + r) * F + f];
-            float z = b;
-            if (is_act) {
-                z = fmaf(xs[r][d.ns], w[0], z);
-            } else {
+        for (int r0 = 0; r0 < nrows; r0 += 8) {
+            float dhv[8];
 #pragma unroll
-                for (int k = 0; k < 8; ++k)
-                    if (k < nin) z = fmaf(xs[r][k], w[k], z);
-            }
-            const float rl = fmaxf(z, 0.0f);
-            dg = fmaf(dh, (rl - mu) * inv, dg);
-            dbe += dh;
-            const float dz = z > 0.0f ? dh * ginv : 0.0f;
-            db += dz;
-            if (is_act) {
-                dw[0] = fmaf(xs[r][d.ns], dz, dw[0]);
-            } else {
+            for (int u = 0; u < 8; ++u) dhv[u] = (r0 + u < nrows) ? dH[(base + r0 + u) * F + f] : 0.0f;   // 8 loads in flight
 #pragma unroll
-                for (int k = 0; k < 8; ++k)
-                    if (k < nin) dw[k] = fmaf(xs[r][k], dz, dw[k]);
+            for (int u = 0; u < 8; ++u) {
+                const int r = min(r0 + u, nrows - 1);
+                const float dh = dhv[u];
+                float z = b;
+                if (is_act) {
+                    z = fmaf(xs[r][d.ns], w[0], z);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        if (k < nin) z = fmaf(xs[r][k], w[k], z);
+                }
+                const float rl = fmaxf(z, 0.0f);
+                dg = fmaf(dh, (rl - mu) * inv, dg);
+                dbe += dh;
+                const float dz = z > 0.0f ? dh * ginv : 0.0f;
+                db += dz;
+                if (is_act) {
+                    dw[0] = fmaf(xs[r][d.ns], dz, dw[0]);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        if (k < nin) dw[k] = fmaf(xs[r][k], dz, dw[k]);
+                }
             }
         }
 #pragma unroll
@@ -152,26 +192,36 @@ __global__ void __launch_bounds__(128) l1_backward_kernel(avd_net_dims d, const 
 }
 
 // d(action)[n] = sum_f dza[n][f] * Wa[f], dza = dHa * ga*inva * (za > 0): the critic -> actor link (trainer.py:503-506)
+// One thread per row; the la (<= 64) per-column parameters are staged in shared memory.
 __global__ void __launch_bounds__(256) action_grad_kernel(avd_net_dims d, const float* __restrict__ params, int64_t pstride,
                                                           const float* __restrict__ act, int64_t R, const float* __restrict__ dHa,
                                                           float* __restrict__ dact) {
     const CriticOff o = critic_off(d);
     const int agent = blockIdx.y;
     const float* P = params + (int64_t)agent * pstride;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    for (int64_t r = (int64_t)blockIdx.x * nw + wid; r < R; r += (int64_t)gridDim.x * nw) {
+    __shared__ float wa[64], ba[64], gi[64];
+    for (int f = threadIdx.x; f < d.la; f += blockDim.x) {
+        wa[f] = P[o.Wa + f];
+        ba[f] = P[o.ba + f];
+        gi[f] = P[o.ga + f] / sqrtf(P[o.vara + f] + kBnEps);
+    }
+    __syncthreads();
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < R; r += (int64_t)gridDim.x * blockDim.x) {
         const int64_t n = (int64_t)agent * R + r;
         const float a = act[n];
+        const float4* row = reinterpret_cast<const float4*>(dHa + n * d.la);
         float acc = 0.0f;
-        for (int f = lane; f < d.la; f += 32) {
-            const float wa = P[o.Wa + f];
-            const float z = fmaf(a, wa, P[o.ba + f]);
-            const float ginv = P[o.ga + f] / sqrtf(P[o.vara + f] + kBnEps);
-            const float dz = z > 0.0f ? dHa[n * d.la + f] * ginv : 0.0f;
-            acc = fmaf(dz, wa, acc);
+        for (int f4 = 0; f4 < d.la / 4; ++f4) {
+            const float4 v = row[f4];
+            const float dv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int f = 4 * f4 + j;
+                const float z = fmaf(a, wa[f], ba[f]);
+                acc = fmaf(z > 0.0f ? dv[j] * gi[f] : 0.0f, wa[f], acc);
+            }
         }
-        acc = warp_sum(acc);
-        if (lane == 0) dact[n] = acc;
+        dact[n] = acc;
     }
 }
 
@@ -191,13 +241,13 @@ struct HeadArgs {
     const float* y;        // CRITIC_BWD
     const float* dpi;      // ACTOR_BWD
     float* out;            // ACTOR_FWD: action, TARGET: y, Q/BWD: q (nullable for BWD)
-    float* DZ;             // BWD modes
+    void* DZ;              // BWD modes: float* (precision 0) or bf16* (precision 1)
     float* grads;          // [A][gstride] (BWD, ACTOR_BWD)
     int64_t gstride;
     float* loss;           // [A][2] nullable
 };
 
-template <int MODE, int CPL>   // CPL = columns per lane (l2 = 32*CPL)
+template <int MODE, int CPL, typename TDZ>   // CPL = columns per lane (l2 = 32*CPL)
 __global__ void __launch_bounds__(256) head_kernel(HeadArgs h) {
     constexpr int L2 = 32 * CPL;
     constexpr int ROWS = 64;
@@ -260,7 +310,7 @@ __global__ void __launch_bounds__(256) head_kernel(HeadArgs h) {
             for (int j = 0; j < CPL; ++j) {
                 const float dh = dq * w3[j];
                 const float dz = z[j] > 0.0f ? dh * ginv[j] : 0.0f;
-                h.DZ[n * L2 + lane + 32 * j] = dz;
+                store_out(reinterpret_cast<TDZ*>(h.DZ) + n * L2 + lane + 32 * j, dz);
                 if (BWD) {
                     aW3[j] = fmaf(hh[j], dq, aW3[j]);
                     aG[j] = fmaf(dh, (fmaxf(z[j], 0.0f) - mu[j]) * inv[j], aG[j]);
@@ -443,47 +493,94 @@ __global__ void __launch_bounds__(256) fed_broadcast_kernel(float* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------------
+// bf16 copies of the layer-2 kernels for the tensor-core path: W2b [F][l2] (dgrad B operand, K-major) and
+// W2T [l2][F] (forward B operand, K-major)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pack_w2_kernel(const float* __restrict__ params, int64_t pstride, int64_t oW2, int F, int l2,
+                                                      bf16* __restrict__ W2b, bf16* __restrict__ W2T) {
+    const int agent = blockIdx.y;
+    const float* W = params + (int64_t)agent * pstride + oW2;
+    const int n = F * l2;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int f = i / l2, c = i - f * l2;
+        const bf16 v = __float2bfloat16_rn(W[i]);
+        if (W2b) W2b[(int64_t)agent * n + i] = v;
+        W2T[(int64_t)agent * n + (int64_t)c * F + f] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // host orchestration
 // ------------------------------------------------------------------------------------------------
 struct Workspace {
     float *H, *H1a, *Z, *Za, *DZ, *DH, *a2, *y, *q, *dpi;
-    static int64_t floats(const avd_net_dims& d, int64_t N) {
-        return N * (2 * (int64_t)(d.l1 + d.la) + d.l1 + 3 * (int64_t)d.l2 + 4);
+    bf16 *cW2b, *cW2T, *tcW2T, *aW2b, *aW2T, *taW2T;   // packed weights (precision 1)
+    static int64_t bytes(const avd_net_dims& d, int64_t A, int64_t N) {
+        const int64_t F = d.l1 + d.la;
+        const int64_t acts = N * (2 * F + d.l1 + 3 * (int64_t)d.l2) * (int64_t)sizeof(float);
+        const int64_t packed = A * (3 * F + 3 * (int64_t)d.l1) * d.l2 * (int64_t)sizeof(bf16);
+        const int64_t vecs = 4 * ((N + 3) / 4 * 4) * (int64_t)sizeof(float);
+        return acts + packed + vecs + 512;
     }
-    void carve(float* base, const avd_net_dims& d, int64_t N) {
-        float* p = base;
-        H = p; p += N * (d.l1 + d.la);
-        DH = p; p += N * (d.l1 + d.la);
+    void carve(void* base_, const avd_net_dims& d, int64_t A, int64_t N) {
+        const int64_t F = d.l1 + d.la;
+        float* p = reinterpret_cast<float*>(((uintptr_t)base_ + 255) & ~(uintptr_t)255);
+        H = p; p += N * F;
+        DH = p; p += N * F;
         H1a = p; p += N * d.l1;
         Z = p; p += N * d.l2;
         Za = p; p += N * d.l2;
         DZ = p; p += N * d.l2;
-        a2 = p; p += N;
-        y = p; p += N;
-        q = p; p += N;
-        dpi = p; p += N;
+        bf16* b = reinterpret_cast<bf16*>(p);
+        cW2b = b; b += A * F * d.l2;
+        cW2T = b; b += A * F * d.l2;
+        tcW2T = b; b += A * F * d.l2;
+        aW2b = b; b += A * (int64_t)d.l1 * d.l2;
+        aW2T = b; b += A * (int64_t)d.l1 * d.l2;
+        taW2T = b; b += A * (int64_t)d.l1 * d.l2;
+        p = reinterpret_cast<float*>(((uintptr_t)b + 15) & ~(uintptr_t)15);
+        const int64_t Np = (N + 3) / 4 * 4;
+        a2 = p; p += Np;
+        y = p; p += Np;
+        q = p; p += Np;
+        dpi = p; p += Np;
     }
 };
 
-static int check_dims(const avd_net_dims* d) {
+static int check_dims(const avd_net_dims* d, int precision = 0) {
     AVD_REQUIRE(d, "null dims");
     AVD_REQUIRE(d->ns >= 1 && d->ns <= 8, "ns=%d outside 1..8", d->ns);
-    AVD_REQUIRE(d->l1 >= 1 && d->la >= 1, "bad layer sizes");
+    AVD_REQUIRE(d->l1 >= 4 && d->la >= 4 && d->l1 % 4 == 0 && d->la % 4 == 0 && d->la <= 64,
+                "layer sizes must be multiples of 4 and la <= 64 (l1=%d, la=%d)", d->l1, d->la);
+    AVD_REQUIRE(precision == 0 || precision == 1, "precision must be 0 (fp32 SIMT) or 1 (bf16 tcgen05)");
     if (d->l2 != 32 && d->l2 != 64 && d->l2 != 96 && d->l2 != 128) {
         set_error("layer2 size %d not supported (32, 64, 96 or 128)", d->l2);
+        return AVD_ERR_UNSUPPORTED;
+    }
+    if (precision == 1 && (d->l1 % 8 || d->la % 8 || d->l2 % 8)) {
+        set_error("precision 1 needs layer sizes that are multiples of 8 (TMA 16-byte pitch)");
         return AVD_ERR_UNSUPPORTED;
     }
     return AVD_OK;
 }
 
 template <int MODE>
-static int launch_head(const HeadArgs& h, int l2, int A, cudaStream_t st) {
+static int launch_head(const HeadArgs& h, int l2, int A, cudaStream_t st, bool dz_bf16 = false) {
     dim3 grid((unsigned)((h.R + 63) / 64), A);
-    switch (l2 / 32) {
-        case 1: head_kernel<MODE, 1><<<grid, 256, 0, st>>>(h); break;
-        case 2: head_kernel<MODE, 2><<<grid, 256, 0, st>>>(h); break;
-        case 3: head_kernel<MODE, 3><<<grid, 256, 0, st>>>(h); break;
-        default: head_kernel<MODE, 4><<<grid, 256, 0, st>>>(h); break;
+    if (dz_bf16) {
+        switch (l2 / 32) {
+            case 1: head_kernel<MODE, 1, bf16><<<grid, 256, 0, st>>>(h); break;
+            case 2: head_kernel<MODE, 2, bf16><<<grid, 256, 0, st>>>(h); break;
+            case 3: head_kernel<MODE, 3, bf16><<<grid, 256, 0, st>>>(h); break;
+            default: head_kernel<MODE, 4, bf16><<<grid, 256, 0, st>>>(h); break;
+        }
+    } else {
+        switch (l2 / 32) {
+            case 1: head_kernel<MODE, 1, float><<<grid, 256, 0, st>>>(h); break;
+            case 2: head_kernel<MODE, 2, float><<<grid, 256, 0, st>>>(h); break;
+            case 3: head_kernel<MODE, 3, float><<<grid, 256, 0, st>>>(h); break;
+            default: head_kernel<MODE, 4, float><<<grid, 256, 0, st>>>(h); break;
+        }
     }
     AVD_LAUNCH_OK();
     return AVD_OK;
@@ -507,41 +604,76 @@ static HeadArgs critic_head(const avd_net_dims& d, const float* params, const fl
     return h;
 }
 
-// C[a] (R x l2) = H[a] (R x F) . W2[a] (F x l2)
-static int gemm_forward(const float* H, int F, const float* params, int64_t pstride, int64_t oW2, float* Z, int l2, int A, int64_t R,
-                        cudaStream_t st) {
-    GemmArgs g = {};
-    g.A = H; g.a_m = F; g.a_k = 1; g.a_batch = R * F;
-    g.B = params + oW2; g.b_k = l2; g.b_n = 1; g.b_batch = pstride;
-    g.C = Z; g.c_m = l2; g.c_n = 1; g.c_batch = R * l2;
-    g.M = (int)R; g.N = l2; g.K = F; g.splitk = 1;
-    return launch_sgemm(g, A, st);
-}
+// Everything a pass needs; `prec` selects fp32 SIMT tiles or bf16 tcgen05 for the three big contractions.
+struct Pass {
+    avd_net_dims d;
+    int A, prec;
+    int64_t R;
+    cudaStream_t st;
 
-// dW2[a] (F x l2) += H[a]^T (F x R) . DZ[a] (R x l2)   (split-K over rows, atomics into pre-zeroed grads)
-static int gemm_wgrad(const float* H, int F, const float* DZ, float* grads, int64_t gstride, int64_t oW2, int l2, int A, int64_t R,
-                      cudaStream_t st) {
-    GemmArgs g = {};
-    g.A = H; g.a_m = 1; g.a_k = F; g.a_batch = R * F;
-    g.B = DZ; g.b_k = l2; g.b_n = 1; g.b_batch = R * l2;
-    g.C = grads + oW2; g.c_m = l2; g.c_n = 1; g.c_batch = gstride;
-    g.M = F; g.N = l2; g.K = (int)R;
-    const int tiles = ((F + 63) / 64) * ((l2 + 63) / 64) * A;
-    int split = (int)std::min<int64_t>((R + 255) / 256, std::max(1, 2 * sm_count() / std::max(1, tiles)));
-    g.splitk = std::max(1, split);
-    return launch_sgemm(g, A, st);
-}
+    dim3 l1_grid() const { return dim3((unsigned)((R + kL1Rows - 1) / kL1Rows), A); }
 
-// DH[a] (R x Fsub) = DZ[a] (R x l2) . W2[a][f0:f0+Fsub, :]^T
-static int gemm_dgrad(const float* DZ, const float* params, int64_t pstride, int64_t oW2, int f0, int Fsub, float* DH, int l2, int A,
-                      int64_t R, cudaStream_t st) {
-    GemmArgs g = {};
-    g.A = DZ; g.a_m = l2; g.a_k = 1; g.a_batch = R * l2;
-    g.B = params + oW2 + (int64_t)f0 * l2; g.b_k = 1; g.b_n = l2; g.b_batch = pstride;
-    g.C = DH; g.c_m = Fsub; g.c_n = 1; g.c_batch = R * Fsub;
-    g.M = (int)R; g.N = Fsub; g.K = l2; g.splitk = 1;
-    return launch_sgemm(g, A, st);
-}
+    // layer 1 (+BN) of the actor (critic=false) or critic (true) into H ([N][F] fp32 or bf16)
+    int layer1(bool critic, const float* params, const float* s, int64_t s_rs, int64_t s_cs, const float* act, void* H) const {
+        const int64_t ps = critic ? critic_off(d).total : actor_off(d).total;
+        if (prec) {
+            if (critic) l1_forward_kernel<true, bf16><<<l1_grid(), 128, 0, st>>>(d, params, ps, s, s_rs, s_cs, act, R, (bf16*)H);
+            else l1_forward_kernel<false, bf16><<<l1_grid(), 128, 0, st>>>(d, params, ps, s, s_rs, s_cs, act, R, (bf16*)H);
+        } else {
+            if (critic) l1_forward_kernel<true, float><<<l1_grid(), 128, 0, st>>>(d, params, ps, s, s_rs, s_cs, act, R, (float*)H);
+            else l1_forward_kernel<false, float><<<l1_grid(), 128, 0, st>>>(d, params, ps, s, s_rs, s_cs, act, R, (float*)H);
+        }
+        AVD_LAUNCH_OK();
+        return AVD_OK;
+    }
+
+    int pack(const float* params, int64_t pstride, int64_t oW2, int F, bf16* W2b, bf16* W2T) const {
+        pack_w2_kernel<<<dim3((unsigned)((F * d.l2 + 255) / 256), A), 256, 0, st>>>(params, pstride, oW2, F, d.l2, W2b, W2T);
+        AVD_LAUNCH_OK();
+        return AVD_OK;
+    }
+
+    // Z[a] (R x l2) = H[a] (R x F) . W2[a] (F x l2)
+    int forward(const void* H, int F, const float* params, int64_t pstride, int64_t oW2, const bf16* W2T, float* Z) const {
+        if (prec)
+            return umma::gemm_bf16(0, A, (int)R, d.l2, F, H, F, R * F, W2T, F, (int64_t)d.l2 * F, Z, d.l2, R * d.l2, 1, st);
+        GemmArgs g = {};
+        g.A = (const float*)H; g.a_m = F; g.a_k = 1; g.a_batch = R * F;
+        g.B = params + oW2; g.b_k = d.l2; g.b_n = 1; g.b_batch = pstride;
+        g.C = Z; g.c_m = d.l2; g.c_n = 1; g.c_batch = R * d.l2;
+        g.M = (int)R; g.N = d.l2; g.K = F; g.splitk = 1;
+        return launch_sgemm(g, A, st);
+    }
+
+    // dW2[a] (F x l2) += H[a]^T . DZ[a]   (contraction over the R rows, split over CTAs, atomics into zeroed grads)
+    int wgrad(const void* H, int F, const void* DZ, float* grads, int64_t gstride, int64_t oW2) const {
+        const int tiles = ((F + (prec ? 127 : 63)) / (prec ? 128 : 64)) * ((d.l2 + (prec ? 127 : 63)) / (prec ? 128 : 64)) * A;
+        const int64_t chunk = prec ? 64 : 256;
+        int split = (int)std::min<int64_t>((R + chunk - 1) / chunk, std::max(1, 4 * sm_count() / std::max(1, tiles)));
+        split = std::max(1, split);
+        if (prec)
+            return umma::gemm_bf16(1, A, F, d.l2, (int)R, H, F, R * F, DZ, d.l2, R * d.l2, grads + oW2, d.l2, gstride, split, st);
+        GemmArgs g = {};
+        g.A = (const float*)H; g.a_m = 1; g.a_k = F; g.a_batch = R * F;
+        g.B = (const float*)DZ; g.b_k = d.l2; g.b_n = 1; g.b_batch = R * d.l2;
+        g.C = grads + oW2; g.c_m = d.l2; g.c_n = 1; g.c_batch = gstride;
+        g.M = F; g.N = d.l2; g.K = (int)R; g.splitk = split;
+        return launch_sgemm(g, A, st);
+    }
+
+    // DH[a] (R x Fsub) = DZ[a] (R x l2) . W2[a][f0:f0+Fsub, :]^T
+    int dgrad(const void* DZ, const float* params, int64_t pstride, int64_t oW2, const bf16* W2b, int F, int f0, int Fsub, float* DH) const {
+        if (prec)
+            return umma::gemm_bf16(0, A, (int)R, Fsub, d.l2, DZ, d.l2, R * d.l2, W2b + (int64_t)f0 * d.l2, d.l2, (int64_t)F * d.l2, DH, Fsub,
+                                   R * Fsub, 1, st);
+        GemmArgs g = {};
+        g.A = (const float*)DZ; g.a_m = d.l2; g.a_k = 1; g.a_batch = R * d.l2;
+        g.B = params + oW2 + (int64_t)f0 * d.l2; g.b_k = 1; g.b_n = d.l2; g.b_batch = pstride;
+        g.C = DH; g.c_m = Fsub; g.c_n = 1; g.c_batch = R * Fsub;
+        g.M = (int)R; g.N = Fsub; g.K = d.l2; g.splitk = 1;
+        return launch_sgemm(g, A, st);
+    }
+};
 
 }  // namespace avd
 
@@ -558,7 +690,7 @@ extern "C" int avd_ddpg_param_counts(const avd_net_dims* dims, int64_t* out4) {
 
 extern "C" int64_t avd_ddpg_workspace_bytes(const avd_net_dims* dims, int32_t A, int64_t rows_per_agent) {
     if (!dims || A < 0 || rows_per_agent < 0) return -1;
-    return Workspace::floats(*dims, (int64_t)A * rows_per_agent) * (int64_t)sizeof(float) + 256;
+    return Workspace::bytes(*dims, A, (int64_t)A * rows_per_agent);
 }
 
 #define AVD_TRY(expr)             \
@@ -570,48 +702,55 @@ extern "C" int64_t avd_ddpg_workspace_bytes(const avd_net_dims* dims, int32_t A,
 extern "C" int avd_actor_forward(const avd_net_dims* dims, int32_t A, int64_t R, const float* actor_params, const float* s,
                                  int64_t s_rs, int64_t s_cs, float action_high, float* out, void* workspace,
                                  int64_t workspace_bytes, int32_t precision, void* stream) {
-    AVD_TRY(check_dims(dims));
+    AVD_TRY(check_dims(dims, precision));
     AVD_REQUIRE(actor_params && s && out && workspace, "null buffer");
     AVD_REQUIRE(A >= 0 && R >= 0, "bad sizes");
-    AVD_REQUIRE(precision == 0, "precision %d not available in this build", precision);
     const avd_net_dims d = *dims;
     const int64_t N = (int64_t)A * R;
-    AVD_REQUIRE(workspace_bytes >= N * (d.l1 + d.l2) * (int64_t)sizeof(float), "workspace too small");
+    const int64_t need = N * (d.l1 + d.l2) * (int64_t)sizeof(float) + (int64_t)A * d.l1 * d.l2 * (int64_t)sizeof(bf16) + 512;
+    AVD_REQUIRE(workspace_bytes >= need, "workspace too small (%lld < %lld)", (long long)workspace_bytes, (long long)need);
     if (N == 0) return AVD_OK;
-    cudaStream_t st = (cudaStream_t)stream;
+    const Pass p{d, A, precision, R, (cudaStream_t)stream};
     const ActorOff o = actor_off(d);
-    float* H = (float*)workspace;
+    float* H = reinterpret_cast<float*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
     float* Z = H + N * d.l1;
-    l1_forward_kernel<false><<<dim3((unsigned)((R + kL1Rows - 1) / kL1Rows), A), 128, 0, st>>>(d, actor_params, o.total, s, s_rs, s_cs, nullptr, R, H);
-    AVD_LAUNCH_OK();
-    AVD_TRY(gemm_forward(H, d.l1, actor_params, o.total, o.W2, Z, d.l2, A, R, st));
+    bf16* W2T = reinterpret_cast<bf16*>(Z + N * d.l2);
+    if (precision) AVD_TRY(p.pack(actor_params, o.total, o.W2, d.l1, nullptr, W2T));
+    if (precision && fused::supported(d, false))
+        return fused::forward(d, false, A, R, actor_params, o.total, W2T, s, s_rs, s_cs, nullptr, nullptr, nullptr, 1, nullptr, 0.f, action_high, out,
+                              p.st);
+    AVD_TRY(p.layer1(false, actor_params, s, s_rs, s_cs, nullptr, H));
+    AVD_TRY(p.forward(H, d.l1, actor_params, o.total, o.W2, W2T, Z));
     HeadArgs h = actor_head(d, actor_params, Z, R, action_high);
     h.out = out;
-    return launch_head<HEAD_ACTOR_FWD>(h, d.l2, A, st);
+    return launch_head<HEAD_ACTOR_FWD>(h, d.l2, A, p.st);
 }
 
 extern "C" int avd_critic_forward(const avd_net_dims* dims, int32_t A, int64_t R, const float* critic_params, const float* s,
                                   const float* a, float* q, void* workspace, int64_t workspace_bytes, int32_t precision,
                                   void* stream) {
-    AVD_TRY(check_dims(dims));
+    AVD_TRY(check_dims(dims, precision));
     AVD_REQUIRE(critic_params && s && a && q && workspace, "null buffer");
     AVD_REQUIRE(A >= 0 && R >= 0, "bad sizes");
-    AVD_REQUIRE(precision == 0, "precision %d not available in this build", precision);
     const avd_net_dims d = *dims;
     const int64_t N = (int64_t)A * R;
     const int F = d.l1 + d.la;
-    AVD_REQUIRE(workspace_bytes >= N * (F + d.l2) * (int64_t)sizeof(float), "workspace too small");
+    const int64_t need = N * (F + d.l2) * (int64_t)sizeof(float) + (int64_t)A * F * d.l2 * (int64_t)sizeof(bf16) + 512;
+    AVD_REQUIRE(workspace_bytes >= need, "workspace too small (%lld < %lld)", (long long)workspace_bytes, (long long)need);
     if (N == 0) return AVD_OK;
-    cudaStream_t st = (cudaStream_t)stream;
+    const Pass p{d, A, precision, R, (cudaStream_t)stream};
     const CriticOff o = critic_off(d);
-    float* H = (float*)workspace;
+    float* H = reinterpret_cast<float*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
     float* Z = H + N * F;
-    l1_forward_kernel<true><<<dim3((unsigned)((R + kL1Rows - 1) / kL1Rows), A), 128, 0, st>>>(d, critic_params, o.total, s, d.ns, 1, a, R, H);
-    AVD_LAUNCH_OK();
-    AVD_TRY(gemm_forward(H, F, critic_params, o.total, o.W2, Z, d.l2, A, R, st));
+    bf16* W2T = reinterpret_cast<bf16*>(Z + N * d.l2);
+    if (precision) AVD_TRY(p.pack(critic_params, o.total, o.W2, F, nullptr, W2T));
+    if (precision && fused::supported(d, true))
+        return fused::forward(d, true, A, R, critic_params, o.total, W2T, s, d.ns, 1, a, nullptr, nullptr, 3, nullptr, 0.f, 0.f, q, p.st);
+    AVD_TRY(p.layer1(true, critic_params, s, d.ns, 1, a, H));
+    AVD_TRY(p.forward(H, F, critic_params, o.total, o.W2, W2T, Z));
     HeadArgs h = critic_head(d, critic_params, Z, R);
     h.out = q;
-    return launch_head<HEAD_CRITIC_Q>(h, d.l2, A, st);
+    return launch_head<HEAD_CRITIC_Q>(h, d.l2, A, p.st);
 }
 
 extern "C" int avd_adam_apply(float* params, int64_t param_stride, const float* grads, int64_t grad_agent_stride, float* m, float* v,
@@ -667,11 +806,10 @@ extern "C" int avd_fed_broadcast(float* out, int64_t out_pitch, const float* in,
 
 extern "C" int avd_ddpg_learn(const avd_learn_io* io, void* stream) {
     AVD_REQUIRE(io, "null io");
-    AVD_TRY(check_dims(&io->dims));
+    AVD_TRY(check_dims(&io->dims, io->precision));
     AVD_REQUIRE(io->s && io->a && io->r && io->s2, "null batch");
     AVD_REQUIRE(io->actor && io->critic && io->t_actor && io->t_critic && io->actor_grad && io->critic_grad, "null parameters");
     AVD_REQUIRE(io->A >= 0 && io->rows_per_agent >= 1, "bad sizes");
-    AVD_REQUIRE(io->precision == 0, "precision %d not available in this build", io->precision);
     AVD_REQUIRE(!io->apply_updates || (io->actor_m && io->actor_v && io->critic_m && io->critic_v && io->actor_t && io->critic_t),
                 "apply_updates needs Adam state");
     const avd_net_dims d = io->dims;
@@ -680,75 +818,95 @@ extern "C" int avd_ddpg_learn(const avd_learn_io* io, void* stream) {
     AVD_REQUIRE(io->workspace && io->workspace_bytes >= avd_ddpg_workspace_bytes(&d, A, R), "workspace too small");
     if (A == 0) return AVD_OK;
     cudaStream_t st = (cudaStream_t)stream;
+    const bool tc = io->precision != 0;
+    const Pass p{d, A, io->precision, R, st};
     const ActorOff ao = actor_off(d);
     const CriticOff co = critic_off(d);
     const int F = d.l1 + d.la;
     Workspace w;
-    uintptr_t base = ((uintptr_t)io->workspace + 255) & ~(uintptr_t)255;
-    w.carve((float*)base, d, N);
-    const dim3 gl1((unsigned)((R + kL1Rows - 1) / kL1Rows), A), gl1b((unsigned)((R + 63) / 64), A);
+    w.carve(io->workspace, d, A, N);
+    const dim3 gl1b((unsigned)((R + kL1BwdRows - 1) / kL1BwdRows), A);
 
     AVD_CUDA_OK(cudaMemsetAsync(io->actor_grad, 0, (size_t)A * ao.n_train * sizeof(float), st));
     AVD_CUDA_OK(cudaMemsetAsync(io->critic_grad, 0, (size_t)A * co.n_train * sizeof(float), st));
     if (io->loss) AVD_CUDA_OK(cudaMemsetAsync(io->loss, 0, (size_t)A * 2 * sizeof(float), st));
-
-    // ---- TD target: y = r + gamma * target_critic(s', target_actor(s'))            trainer.py:493-494
-    l1_forward_kernel<false><<<gl1, 128, 0, st>>>(d, io->t_actor, ao.total, io->s2, d.ns, 1, nullptr, R, w.H1a);
-    AVD_LAUNCH_OK();
-    AVD_TRY(gemm_forward(w.H1a, d.l1, io->t_actor, ao.total, ao.W2, w.Z, d.l2, A, R, st));
-    {
-        HeadArgs h = actor_head(d, io->t_actor, w.Z, R, io->action_high);
-        h.out = w.a2;
-        AVD_TRY(launch_head<HEAD_ACTOR_FWD>(h, d.l2, A, st));
+    if (tc) {   // bf16 copies of the four layer-2 kernels (K-major for forward, and for dgrad on the online nets)
+        AVD_TRY(p.pack(io->t_actor, ao.total, ao.W2, d.l1, nullptr, w.taW2T));
+        AVD_TRY(p.pack(io->t_critic, co.total, co.W2, F, nullptr, w.tcW2T));
+        AVD_TRY(p.pack(io->critic, co.total, co.W2, F, w.cW2b, w.cW2T));
+        AVD_TRY(p.pack(io->actor, ao.total, ao.W2, d.l1, w.aW2b, w.aW2T));
     }
-    l1_forward_kernel<true><<<gl1, 128, 0, st>>>(d, io->t_critic, co.total, io->s2, d.ns, 1, w.a2, R, w.H);
-    AVD_LAUNCH_OK();
-    AVD_TRY(gemm_forward(w.H, F, io->t_critic, co.total, co.W2, w.Z, d.l2, A, R, st));
-    {
-        HeadArgs h = critic_head(d, io->t_critic, w.Z, R);
-        h.rew = io->r; h.gamma = io->gamma; h.out = w.y;
-        AVD_TRY(launch_head<HEAD_CRITIC_TARGET>(h, d.l2, A, st));
+
+    const bool fz = tc && fused::supported(d, false) && fused::supported(d, true);   // fused layer1 -> tcgen05 -> head kernels
+    // ---- TD target: y = r + gamma * target_critic(s', target_actor(s'))            trainer.py:493-494
+    if (fz) {
+        AVD_TRY(fused::forward(d, false, A, R, io->t_actor, ao.total, w.taW2T, io->s2, d.ns, 1, nullptr, nullptr, nullptr, 1, nullptr, 0.f,
+                               io->action_high, w.a2, st));
+        AVD_TRY(fused::forward(d, true, A, R, io->t_critic, co.total, w.tcW2T, io->s2, d.ns, 1, w.a2, nullptr, nullptr, 2, io->r, io->gamma, 0.f,
+                               w.y, st));
+    } else {
+        AVD_TRY(p.layer1(false, io->t_actor, io->s2, d.ns, 1, nullptr, w.H1a));
+        AVD_TRY(p.forward(w.H1a, d.l1, io->t_actor, ao.total, ao.W2, w.taW2T, w.Z));
+        {
+            HeadArgs h = actor_head(d, io->t_actor, w.Z, R, io->action_high);
+            h.out = w.a2;
+            AVD_TRY(launch_head<HEAD_ACTOR_FWD>(h, d.l2, A, st));
+        }
+        AVD_TRY(p.layer1(true, io->t_critic, io->s2, d.ns, 1, w.a2, w.H));
+        AVD_TRY(p.forward(w.H, F, io->t_critic, co.total, co.W2, w.tcW2T, w.Z));
+        {
+            HeadArgs h = critic_head(d, io->t_critic, w.Z, R);
+            h.rew = io->r; h.gamma = io->gamma; h.out = w.y;
+            AVD_TRY(launch_head<HEAD_CRITIC_TARGET>(h, d.l2, A, st));
+        }
     }
     // ---- critic loss gradient on (s, a)                                             trainer.py:495-498
-    l1_forward_kernel<true><<<gl1, 128, 0, st>>>(d, io->critic, co.total, io->s, d.ns, 1, io->a, R, w.H);
-    AVD_LAUNCH_OK();
-    AVD_TRY(gemm_forward(w.H, F, io->critic, co.total, co.W2, w.Z, d.l2, A, R, st));
+    if (fz) {
+        AVD_TRY(fused::forward(d, true, A, R, io->critic, co.total, w.cW2T, io->s, d.ns, 1, io->a, (bf16*)w.H, w.Z, 0, nullptr, 0.f, 0.f, nullptr, st));
+    } else {
+        AVD_TRY(p.layer1(true, io->critic, io->s, d.ns, 1, io->a, w.H));
+        AVD_TRY(p.forward(w.H, F, io->critic, co.total, co.W2, w.cW2T, w.Z));
+    }
     {
         HeadArgs h = critic_head(d, io->critic, w.Z, R);
         h.y = w.y; h.out = w.q; h.DZ = w.DZ; h.grads = io->critic_grad; h.gstride = co.n_train; h.loss = io->loss;
-        AVD_TRY(launch_head<HEAD_CRITIC_BWD>(h, d.l2, A, st));
+        AVD_TRY(launch_head<HEAD_CRITIC_BWD>(h, d.l2, A, st, tc));
     }
-    AVD_TRY(gemm_wgrad(w.H, F, w.DZ, io->critic_grad, co.n_train, co.W2, d.l2, A, R, st));
-    AVD_TRY(gemm_dgrad(w.DZ, io->critic, co.total, co.W2, 0, F, w.DH, d.l2, A, R, st));
+    AVD_TRY(p.wgrad(w.H, F, w.DZ, io->critic_grad, co.n_train, co.W2));
+    AVD_TRY(p.dgrad(w.DZ, io->critic, co.total, co.W2, w.cW2b, F, 0, F, w.DH));
     l1_backward_kernel<true><<<gl1b, 128, 0, st>>>(d, io->critic, co.total, io->s, io->a, R, w.DH, io->critic_grad, co.n_train);
     AVD_LAUNCH_OK();
     // ---- actor loss gradient: -mean(critic(s, actor(s)))                            trainer.py:501-506
-    l1_forward_kernel<false><<<gl1, 128, 0, st>>>(d, io->actor, ao.total, io->s, d.ns, 1, nullptr, R, w.H1a);
-    AVD_LAUNCH_OK();
-    AVD_TRY(gemm_forward(w.H1a, d.l1, io->actor, ao.total, ao.W2, w.Za, d.l2, A, R, st));
-    {
-        HeadArgs h = actor_head(d, io->actor, w.Za, R, io->action_high);
-        h.out = w.a2;   // pi
-        AVD_TRY(launch_head<HEAD_ACTOR_FWD>(h, d.l2, A, st));
+    if (fz) {
+        AVD_TRY(fused::forward(d, false, A, R, io->actor, ao.total, w.aW2T, io->s, d.ns, 1, nullptr, (bf16*)w.H1a, w.Za, 1, nullptr, 0.f,
+                               io->action_high, w.a2, st));   // pi
+        AVD_TRY(fused::forward(d, true, A, R, io->critic, co.total, w.cW2T, io->s, d.ns, 1, w.a2, nullptr, w.Z, 0, nullptr, 0.f, 0.f, nullptr, st));
+    } else {
+        AVD_TRY(p.layer1(false, io->actor, io->s, d.ns, 1, nullptr, w.H1a));
+        AVD_TRY(p.forward(w.H1a, d.l1, io->actor, ao.total, ao.W2, w.aW2T, w.Za));
+        {
+            HeadArgs h = actor_head(d, io->actor, w.Za, R, io->action_high);
+            h.out = w.a2;   // pi
+            AVD_TRY(launch_head<HEAD_ACTOR_FWD>(h, d.l2, A, st));
+        }
+        AVD_TRY(p.layer1(true, io->critic, io->s, d.ns, 1, w.a2, w.H));
+        AVD_TRY(p.forward(w.H, F, io->critic, co.total, co.W2, w.cW2T, w.Z));
     }
-    l1_forward_kernel<true><<<gl1, 128, 0, st>>>(d, io->critic, co.total, io->s, d.ns, 1, w.a2, R, w.H);
-    AVD_LAUNCH_OK();
-    AVD_TRY(gemm_forward(w.H, F, io->critic, co.total, co.W2, w.Z, d.l2, A, R, st));
     {
         HeadArgs h = critic_head(d, io->critic, w.Z, R);
         h.DZ = w.DZ; h.loss = io->loss;
-        AVD_TRY(launch_head<HEAD_CRITIC_BWD_ACTION>(h, d.l2, A, st));
+        AVD_TRY(launch_head<HEAD_CRITIC_BWD_ACTION>(h, d.l2, A, st, tc));
     }
-    AVD_TRY(gemm_dgrad(w.DZ, io->critic, co.total, co.W2, d.l1, d.la, w.DH, d.l2, A, R, st));   // action columns only
-    action_grad_kernel<<<dim3((unsigned)std::min<int64_t>((R + 7) / 8, 1024), A), 256, 0, st>>>(d, io->critic, co.total, w.a2, R, w.DH, w.dpi);
+    AVD_TRY(p.dgrad(w.DZ, io->critic, co.total, co.W2, w.cW2b, F, d.l1, d.la, w.DH));   // action columns only
+    action_grad_kernel<<<dim3((unsigned)std::min<int64_t>((R + 255) / 256, 2048), A), 256, 0, st>>>(d, io->critic, co.total, w.a2, R, w.DH, w.dpi);
     AVD_LAUNCH_OK();
     {
         HeadArgs h = actor_head(d, io->actor, w.Za, R, io->action_high);
         h.dpi = w.dpi; h.DZ = w.DZ; h.grads = io->actor_grad; h.gstride = ao.n_train;
-        AVD_TRY(launch_head<HEAD_ACTOR_BWD>(h, d.l2, A, st));
+        AVD_TRY(launch_head<HEAD_ACTOR_BWD>(h, d.l2, A, st, tc));
     }
-    AVD_TRY(gemm_wgrad(w.H1a, d.l1, w.DZ, io->actor_grad, ao.n_train, ao.W2, d.l2, A, R, st));
-    AVD_TRY(gemm_dgrad(w.DZ, io->actor, ao.total, ao.W2, 0, d.l1, w.DH, d.l2, A, R, st));
+    AVD_TRY(p.wgrad(w.H1a, d.l1, w.DZ, io->actor_grad, ao.n_train, ao.W2));
+    AVD_TRY(p.dgrad(w.DZ, io->actor, ao.total, ao.W2, w.aW2b, d.l1, 0, d.l1, w.DH));
     l1_backward_kernel<false><<<gl1b, 128, 0, st>>>(d, io->actor, ao.total, io->s, nullptr, R, w.DH, io->actor_grad, ao.n_train);
     AVD_LAUNCH_OK();
     // ---- local update: Adam on both nets, then Polyak of the targets                trainer.py:345-356

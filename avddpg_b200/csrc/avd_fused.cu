@@ -1,0 +1,376 @@
+// avd_fused.cu -- fused two-layer forward of the actor / critic on sm_100a:
+//
+//   x[n] (4 state words [+ action])  --CUDA cores-->  h1 = BN(relu(x W1 + b1))  (bf16, written straight into the
+//   128-byte-swizzled K-major A tile in shared memory, never to HBM unless the caller wants it for wgrad)
+//   --tcgen05.mma, W2^T resident in shared memory (TMA), fp32 accumulators in TMEM-->  z2
+//   --epilogue from TMEM (one thread per row)-->  BN(relu(z2 + b2)) . W3 + b3  -> tanh*high | r + gamma*q | q
+//
+// One persistent CTA per SM walks a contiguous range of 128-row tiles.  Roles (13 warps):
+//   warp 0      : TMEM allocation; one elected thread loads W2^T when the agent changes (TMA) and issues all MMAs
+//   warps 1..4  : epilogue, TMEM lane quadrant = warp % 4; double-buffered accumulator (2 x 128 columns)
+//   warps 5..12 : producers; 256 threads fill one 128 x 64 k-block (16 KB) at a time into an 8-slot ring, so the MMA
+//                 of k-block j overlaps the production of k-block j+1 and tiles overlap each other
+// This replaces, per pass, l1_forward + gemm + head (three kernels and two HBM round trips of the activations).
+// Reference semantics: agent/model.py:19-37 (actor), 55-83 (critic); workers/trainer.py:493-495, 502-503, 287.
+#include <cudaTypedefs.h>
+
+#include "avd_common.cuh"
+#include "avd_ddpg_layout.cuh"
+#include "avd_umma.cuh"
+
+namespace avd {
+namespace fused {
+
+using namespace umma;
+typedef __nv_bfloat16 bf16;
+
+constexpr int TILE_M = 128, L2N = 128, KB = 64;
+constexpr int NSLOT = 8;                       // ring of 16 KB k-block slots for A
+constexpr int MAX_KB = 5;                      // up to 320 input features for layer 2
+constexpr int PTAB_COLS = MAX_KB * KB;         // 320
+constexpr int NUM_PRODUCERS = 256, NUM_THREADS = 32 + 128 + NUM_PRODUCERS;
+constexpr int SLOT_BYTES = TILE_M * KB * 2;    // 16 KB
+constexpr int W_BYTES = MAX_KB * L2N * KB * 2; // 80 KB
+constexpr int OFF_W = NSLOT * SLOT_BYTES;                       // 128 KB
+constexpr int OFF_PTAB = OFF_W + W_BYTES;                       // + 80 KB
+constexpr int OFF_ETAB = OFF_PTAB + 8 * PTAB_COLS * 4;          // + 10 KB
+constexpr int OFF_BAR = OFF_ETAB + (4 * L2N + 4) * 4;           // + 2 KB
+constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
+
+enum HeadMode { HEAD_NONE = 0, HEAD_ACTOR = 1, HEAD_TARGET = 2, HEAD_Q = 3 };
+
+struct Args {
+    avd_net_dims d;
+    int critic;                 // 0 actor, 1 critic
+    int A;
+    int64_t R;
+    const float* params;        // [A][pstride]
+    int64_t pstride;
+    const float* s;             // element (n, k) at s[n*s_rs + k*s_cs]
+    int64_t s_rs, s_cs;
+    const float* act;           // [A*R] (critic)
+    bf16* H_out;                // nullable: [A*R][F] bf16 layer-1 activations (operand of the wgrad GEMM)
+    float* Z_out;               // nullable: [A*R][128] raw layer-2 product (input of the head-backward kernels)
+    int head;                   // HeadMode
+    const float* rew;
+    float gamma, high;
+    float* out;                 // [A*R]
+    int tiles_per_agent, total_tiles, tiles_per_cta;
+};
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1) fused_forward_kernel(const __grid_constant__ CUtensorMap tmW, Args g) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    float* ptab = reinterpret_cast<float*>(smem + OFF_PTAB);      // [8][320]: w0..w4, bias, scale, shift
+    float* etab = reinterpret_cast<float*>(smem + OFF_ETAB);      // [4][128]: b2, scale2, shift2, w3 ; then b3
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+    uint64_t* a_empty = a_full + NSLOT;
+    uint64_t* acc_full = a_empty + NSLOT;
+    uint64_t* acc_empty = acc_full + 2;
+    uint64_t* w_full = acc_empty + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const avd_net_dims d = g.d;
+    const int F = g.critic ? d.l1 + d.la : d.l1;
+    const int nkb = (F + KB - 1) / KB;
+    const int tile_begin = blockIdx.x * g.tiles_per_cta;
+    const int tile_end = min(g.total_tiles, tile_begin + g.tiles_per_cta);
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmW);
+        for (int i = 0; i < NSLOT; ++i) { mbar_init(&a_full[i], NUM_PRODUCERS / 32); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+        mbar_init(w_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(tmem_slot, 2 * L2N);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================================== MMA issuer + weight loader =====================================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(TILE_M, L2N, false, false);
+            const uint32_t w_addr = smem_u32(smem + OFF_W);
+            uint32_t kc = 0, wph = 0;
+            int cur_agent = -1;
+            for (int t = tile_begin, tc = 0; t < tile_end; ++t, ++tc) {
+                const int agent = t / g.tiles_per_agent;
+                const int buf = tc & 1;
+                const uint32_t nt = (uint32_t)tc >> 1;
+                if (agent != cur_agent) {
+                    if (tc > 0) {   // every MMA that reads the old weights has completed once the previous tile's accumulator is full
+                        mbar_wait(&acc_full[(tc - 1) & 1], ((uint32_t)(tc - 1) >> 1) & 1);
+                    }
+                    mbar_expect_tx(w_full, (uint32_t)nkb * L2N * KB * 2);
+                    for (int kb = 0; kb < nkb; ++kb) tma_load_3d(smem + OFF_W + kb * (L2N * KB * 2), &tmW, w_full, kb * KB, 0, agent);
+                    mbar_wait(w_full, wph);
+                    wph ^= 1;
+                    cur_agent = agent;
+                }
+                mbar_wait(&acc_empty[buf], (nt & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t tacc = tmem_base + (uint32_t)(buf * L2N);
+                for (int kb = 0; kb < nkb; ++kb, ++kc) {
+                    const uint32_t slot = kc % NSLOT, n = kc / NSLOT;
+                    mbar_wait(&a_full[slot], n & 1);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(smem + slot * SLOT_BYTES);
+                    const int nm = min(4, (F - kb * KB) / 16);
+                    for (int j = 0; j < nm; ++j) {
+                        mma_bf16(tacc, make_smem_desc(a_addr + j * 32, 16, 1024), make_smem_desc(w_addr + kb * (L2N * KB * 2) + j * 32, 16, 1024),
+                                 idesc, (kb | j) != 0);
+                    }
+                    mma_commit(&a_empty[slot]);
+                }
+                mma_commit(&acc_full[buf]);
+            }
+        }
+    } else if (warp <= 4) {
+        // ===================================== epilogue (4 warps) =============================================
+        const int q = warp & 3;
+        const int et = threadIdx.x - 32;     // 0..127
+        int cur_agent = -1;
+        for (int t = tile_begin, tc = 0; t < tile_end; ++t, ++tc) {
+            const int agent = t / g.tiles_per_agent;
+            const int tile_in_agent = t - agent * g.tiles_per_agent;
+            if (agent != cur_agent) {        // per-agent head parameters -> shared (broadcast reads below)
+                asm volatile("bar.sync 2, 128;" ::: "memory");
+                const float* P = g.params + (int64_t)agent * g.pstride;
+                int64_t ob2, og2, obe2, omu2, ovar2, oW3, ob3;
+                if (g.critic) { const CriticOff o = critic_off(d); ob2 = o.b2; og2 = o.g2; obe2 = o.be2; omu2 = o.mu2; ovar2 = o.var2; oW3 = o.W3; ob3 = o.b3; }
+                else { const ActorOff o = actor_off(d); ob2 = o.b2; og2 = o.g2; obe2 = o.be2; omu2 = o.mu2; ovar2 = o.var2; oW3 = o.W3; ob3 = o.b3; }
+                {
+                    const int c = et;
+                    const float inv = 1.0f / sqrtf(P[ovar2 + c] + kBnEps);
+                    const float sc = P[og2 + c] * inv;
+                    etab[c] = P[ob2 + c];
+                    etab[L2N + c] = sc;
+                    etab[2 * L2N + c] = P[obe2 + c] - P[omu2 + c] * sc;
+                    etab[3 * L2N + c] = P[oW3 + c];
+                    if (c == 0) etab[4 * L2N] = P[ob3];
+                }
+                asm volatile("bar.sync 2, 128;" ::: "memory");
+                cur_agent = agent;
+            }
+            const int buf = tc & 1;
+            const uint32_t nt = (uint32_t)tc >> 1;
+            mbar_wait(&acc_full[buf], nt & 1);
+            tc_fence_after();
+            const int64_t row_in_agent = (int64_t)tile_in_agent * TILE_M + q * 32 + lane;
+            const bool valid = row_in_agent < g.R;
+            const int64_t n = (int64_t)agent * g.R + row_in_agent;
+            float acc = 0.0f;
+#pragma unroll 1
+            for (int c = 0; c < L2N / 32; ++c) {
+                float v[32];
+                tmem_ld32(tmem_base + (uint32_t)(buf * L2N) + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+                if (g.Z_out && valid) {
+                    float4* dst = reinterpret_cast<float4*>(g.Z_out + n * L2N + c * 32);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                }
+                if (g.head != HEAD_NONE) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int col = c * 32 + j;
+                        const float z = v[j] + etab[col];
+                        acc = fmaf(fmaf(fmaxf(z, 0.0f), etab[L2N + col], etab[2 * L2N + col]), etab[3 * L2N + col], acc);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[buf]);
+            if (g.head != HEAD_NONE && valid) {
+                const float pre = acc + etab[4 * L2N];
+                float o;
+                if (g.head == HEAD_ACTOR) o = g.high * tanhf(pre);
+                else if (g.head == HEAD_TARGET) o = g.rew[n] + g.gamma * pre;     // trainer.py:494
+                else o = pre;
+                g.out[n] = o;
+            }
+        }
+    } else {
+        // ===================================== producers (8 warps) ============================================
+        const int pt = threadIdx.x - 160;    // 0..255
+        const int chunk = pt & 7;            // 16-byte chunk (8 columns) inside the 64-column k-block
+        const int rg = pt >> 3;              // rows rg*4 .. rg*4+3
+        const int nx = d.ns + (g.critic ? 1 : 0);
+        uint32_t kc = 0;
+        int cur_agent = -1;
+        for (int t = tile_begin; t < tile_end; ++t) {
+            const int agent = t / g.tiles_per_agent;
+            const int tile_in_agent = t - agent * g.tiles_per_agent;
+            if (agent != cur_agent) {        // layer-1 parameter table of this agent -> shared
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                const float* P = g.params + (int64_t)agent * g.pstride;
+                for (int c = pt; c < PTAB_COLS; c += NUM_PRODUCERS) {
+                    float w[5] = {0.f, 0.f, 0.f, 0.f, 0.f}, b = 0.f, sc = 0.f, sh = 0.f;
+                    if (c < F) {
+                        const bool is_act = g.critic && c >= d.l1;
+                        const int cc = is_act ? c - d.l1 : c;
+                        int64_t oW, ob, og, obe, omu, ovar;
+                        if (g.critic) {
+                            const CriticOff o = critic_off(d);
+                            oW = is_act ? o.Wa : o.Ws; ob = is_act ? o.ba : o.bs; og = is_act ? o.ga : o.gs; obe = is_act ? o.bea : o.bes;
+                            omu = is_act ? o.mua : o.mus; ovar = is_act ? o.vara : o.vars;
+                        } else {
+                            const ActorOff o = actor_off(d);
+                            oW = o.W1; ob = o.b1; og = o.g1; obe = o.be1; omu = o.mu1; ovar = o.var1;
+                        }
+                        if (is_act) w[4] = P[oW + cc];
+                        else for (int k = 0; k < d.ns; ++k) w[k] = P[oW + (int64_t)k * d.l1 + cc];
+                        b = P[ob + cc];
+                        const float inv = 1.0f / sqrtf(P[ovar + cc] + kBnEps);
+                        sc = P[og + cc] * inv;
+                        sh = P[obe + cc] - P[omu + cc] * sc;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 5; ++k) ptab[k * PTAB_COLS + c] = w[k];
+                    ptab[5 * PTAB_COLS + c] = b;
+                    ptab[6 * PTAB_COLS + c] = sc;
+                    ptab[7 * PTAB_COLS + c] = sh;
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                cur_agent = agent;
+            }
+            // inputs of my four rows (rows past the end of the agent's batch are clamped; the epilogue masks them)
+            float x[4][5];
+            int64_t nrow[4];
+            bool rvalid[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int64_t r_in = (int64_t)tile_in_agent * TILE_M + rg * 4 + i;
+                rvalid[i] = r_in < g.R;
+                nrow[i] = (int64_t)agent * g.R + (rvalid[i] ? r_in : g.R - 1);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) x[i][k] = (k < d.ns) ? g.s[nrow[i] * g.s_rs + k * g.s_cs] : 0.0f;
+                x[i][4] = g.critic ? g.act[nrow[i]] : 0.0f;
+            }
+            (void)nx;
+            for (int kb = 0; kb < nkb; ++kb, ++kc) {
+                const uint32_t slot = kc % NSLOT, n = kc / NSLOT;
+                mbar_wait(&a_empty[slot], (n & 1) ^ 1);
+                const int col0 = kb * KB + chunk * 8;
+                if (col0 < F) {
+                    float w[5][8], b[8], sc[8], sh[8];
+#pragma unroll
+                    for (int k = 0; k < 5; ++k) {
+                        const float4 lo = *reinterpret_cast<const float4*>(ptab + k * PTAB_COLS + col0);
+                        const float4 hi = *reinterpret_cast<const float4*>(ptab + k * PTAB_COLS + col0 + 4);
+                        w[k][0] = lo.x; w[k][1] = lo.y; w[k][2] = lo.z; w[k][3] = lo.w; w[k][4] = hi.x; w[k][5] = hi.y; w[k][6] = hi.z; w[k][7] = hi.w;
+                    }
+                    {
+                        const float4 lo = *reinterpret_cast<const float4*>(ptab + 5 * PTAB_COLS + col0), hi = *reinterpret_cast<const float4*>(ptab + 5 * PTAB_COLS + col0 + 4);
+                        b[0] = lo.x; b[1] = lo.y; b[2] = lo.z; b[3] = lo.w; b[4] = hi.x; b[5] = hi.y; b[6] = hi.z; b[7] = hi.w;
+                    }
+                    {
+                        const float4 lo = *reinterpret_cast<const float4*>(ptab + 6 * PTAB_COLS + col0), hi = *reinterpret_cast<const float4*>(ptab + 6 * PTAB_COLS + col0 + 4);
+                        sc[0] = lo.x; sc[1] = lo.y; sc[2] = lo.z; sc[3] = lo.w; sc[4] = hi.x; sc[5] = hi.y; sc[6] = hi.z; sc[7] = hi.w;
+                    }
+                    {
+                        const float4 lo = *reinterpret_cast<const float4*>(ptab + 7 * PTAB_COLS + col0), hi = *reinterpret_cast<const float4*>(ptab + 7 * PTAB_COLS + col0 + 4);
+                        sh[0] = lo.x; sh[1] = lo.y; sh[2] = lo.z; sh[3] = lo.w; sh[4] = hi.x; sh[5] = hi.y; sh[6] = hi.z; sh[7] = hi.w;
+                    }
+                    uint8_t* slot_base = smem + slot * SLOT_BYTES;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int row = rg * 4 + i;
+                        float h[8];
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            float z = b[c];
+#pragma unroll
+                            for (int k = 0; k < 5; ++k) z = fmaf(x[i][k], w[k][c], z);
+                            h[c] = fmaf(fmaxf(z, 0.0f), sc[c], sh[c]);
+                        }
+                        const uint4 packed = make_uint4(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]), pack_bf16x2(h[4], h[5]), pack_bf16x2(h[6], h[7]));
+                        *reinterpret_cast<uint4*>(slot_base + row * 128 + ((chunk ^ (row & 7)) << 4)) = packed;   // SWIZZLE_128B
+                        if (g.H_out && rvalid[i]) *reinterpret_cast<uint4*>(g.H_out + nrow[i] * F + col0) = packed;
+                    }
+                }
+                fence_proxy_async();     // generic-proxy smem writes -> visible to the tensor core (async proxy)
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&a_full[slot]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 2 * L2N);
+    }
+}
+
+static PFN_cuTensorMapEncodeTiled encode_fn() {
+    static PFN_cuTensorMapEncodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(p);
+    }
+    return fn;
+}
+
+bool supported(const avd_net_dims& d, bool critic) {
+    const int F = critic ? d.l1 + d.la : d.l1;
+    return d.l2 == L2N && d.ns <= 4 && F % 16 == 0 && F <= MAX_KB * KB && d.l1 % 8 == 0 && d.la % 8 == 0;
+}
+
+// W2T: bf16 [A][128][F] (K-major copy of the layer-2 kernel, see pack_w2_kernel)
+int forward(const avd_net_dims& d, bool critic, int A, int64_t R, const float* params, int64_t pstride, const bf16* W2T, const float* s,
+            int64_t s_rs, int64_t s_cs, const float* act, bf16* H_out, float* Z_out, int head, const float* rew, float gamma, float high,
+            float* out, cudaStream_t st) {
+    if (!supported(d, critic)) {
+        set_error("fused forward kernel does not support these layer sizes");
+        return AVD_ERR_UNSUPPORTED;
+    }
+    PFN_cuTensorMapEncodeTiled enc = encode_fn();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled is not available from the driver");
+        return AVD_ERR_CUDA;
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        AVD_CUDA_OK(cudaFuncSetAttribute(fused_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        attr_set = true;
+    }
+    const int F = critic ? d.l1 + d.la : d.l1;
+    CUtensorMap tm;
+    cuuint64_t dims[3] = {(cuuint64_t)F, (cuuint64_t)L2N, (cuuint64_t)A};
+    cuuint64_t strides[2] = {(cuuint64_t)F * 2, (cuuint64_t)F * L2N * 2};
+    cuuint32_t box[3] = {KB, L2N, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<bf16*>(W2T), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled(W2T) failed with %d", (int)r);
+        return AVD_ERR_CUDA;
+    }
+    Args g;
+    g.d = d; g.critic = critic ? 1 : 0; g.A = A; g.R = R; g.params = params; g.pstride = pstride;
+    g.s = s; g.s_rs = s_rs; g.s_cs = s_cs; g.act = act; g.H_out = H_out; g.Z_out = Z_out; g.head = head; g.rew = rew;
+    g.gamma = gamma; g.high = high; g.out = out;
+    g.tiles_per_agent = (int)((R + TILE_M - 1) / TILE_M);
+    g.total_tiles = g.tiles_per_agent * A;
+    const int ctas = std::min(g.total_tiles, sm_count());
+    g.tiles_per_cta = (g.total_tiles + ctas - 1) / ctas;
+    const int grid = (g.total_tiles + g.tiles_per_cta - 1) / g.tiles_per_cta;
+    fused_forward_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tm, g);
+    AVD_LAUNCH_OK();
+    return AVD_OK;
+}
+
+}  // namespace fused
+}  // namespace avd

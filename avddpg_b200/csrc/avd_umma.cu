@@ -19,11 +19,14 @@
 namespace avd {
 namespace umma {
 
-constexpr int BM = 128, BN = 128, BK = 64, STAGES = 4;
+constexpr int BM = 128, BN = 128, BK = 64;
 constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KB
 constexpr int B_STAGE_BYTES = BN * BK * 2;   // 16 KB
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int smem_bytes(int stages) { return stages * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/; }
+// TN GEMMs of the learn step have K <= 320 (2..5 k-blocks): 2 stages = 65 KB so that three CTAs share an SM and one
+// CTA's prologue/epilogue overlaps another's MMAs; the NT weight-gradient GEMM streams thousands of rows: 4 stages.
+constexpr int STAGES_TN = 2, STAGES_NT = 4;
 constexpr int NUM_THREADS = 192;             // warp 0 TMA, warp 1 MMA (+TMEM alloc), warps 2..5 epilogue
 
 struct GemmParams {
@@ -35,8 +38,8 @@ struct GemmParams {
     int atomic;            // 1: atomicAdd into C (split-K)
 };
 
-template <bool MN_MAJOR>
-__global__ void __launch_bounds__(NUM_THREADS, 1) gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA,
+template <bool MN_MAJOR, int STAGES>
+__global__ void __launch_bounds__(NUM_THREADS, (STAGES <= 2) ? 3 : 1) gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                    const __grid_constant__ CUtensorMap tmB, GemmParams g) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -192,8 +195,8 @@ int gemm_bf16(int layout, int batch, int M, int N, int K, const void* A, int64_t
     AVD_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0, "operands must be 16-byte aligned");
     static bool attr_set = false;
     if (!attr_set) {
-        AVD_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        AVD_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        AVD_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_kernel<false, STAGES_TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(STAGES_TN)));
+        AVD_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_kernel<true, STAGES_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(STAGES_NT)));
         attr_set = true;
     }
     CUtensorMap tmA, tmB;
@@ -207,11 +210,11 @@ int gemm_bf16(int layout, int batch, int M, int N, int K, const void* A, int64_t
     if (layout == 0) {
         if (int rc = make_map(&tmA, A, K, M, batch, lda, a_batch, BK, BM)) return rc;
         if (int rc = make_map(&tmB, B, K, N, batch, ldb, b_batch, BK, BN)) return rc;
-        gemm_bf16_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmA, tmB, g);
+        gemm_bf16_kernel<false, STAGES_TN><<<grid, NUM_THREADS, smem_bytes(STAGES_TN), st>>>(tmA, tmB, g);
     } else {
         if (int rc = make_map(&tmA, A, M, K, batch, lda, a_batch, 64, BK)) return rc;
         if (int rc = make_map(&tmB, B, N, K, batch, ldb, b_batch, 64, BK)) return rc;
-        gemm_bf16_kernel<true><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmA, tmB, g);
+        gemm_bf16_kernel<true, STAGES_NT><<<grid, NUM_THREADS, smem_bytes(STAGES_NT), st>>>(tmA, tmB, g);
     }
     AVD_LAUNCH_OK();
     return AVD_OK;

@@ -194,7 +194,8 @@ class _Model:
                  **{f"{i:02d}_{n}": w for i, (n, w) in enumerate(zip(self.bank.weight_names, self.get_weights()))})
 
     def _workspace(self, rows, width):
-        need = rows * width * 4 + 256
+        d = self.bank.dims
+        need = rows * width * 4 + (d.l1 + d.la) * d.l2 * 2 + 1024
         if self._ws is None or self._ws.numel() < need:
             self._ws = torch.empty(need, dtype=torch.uint8, device=self.bank.flat.device)
         return self._ws

@@ -30,6 +30,11 @@ def _nrm(got, ref):
     return np.max(np.abs(got - ref)) / max(np.max(np.abs(ref)), 1e-12)
 
 
+def _l2(got, ref):
+    got, ref = np.asarray(got, np.float64), np.asarray(ref, np.float64)
+    return np.linalg.norm(got - ref) / max(np.linalg.norm(ref), 1e-30)
+
+
 def make_nets(seed):
     rng = np.random.default_rng(seed)
     nets = [D.init_actor(rng), D.init_critic(rng), D.init_actor(rng), D.init_critic(rng)]
@@ -71,7 +76,7 @@ def test_forward_vs_oracle(mods):
     lib, d = mods["lib"], pop.dims
     n = 3 * 70
     out = torch.empty(n, device="cuda"); q = torch.empty(n, device="cuda")
-    ws = torch.empty(n * (d.l1 + d.la + d.l2) * 4 + 256, dtype=torch.uint8, device="cuda")
+    ws = torch.empty(n * (d.l1 + d.la + d.l2) * 4 + (d.l1 + d.la) * d.l2 * 2 * 3 + 1024, dtype=torch.uint8, device="cuda")
     lib.check(lib.load().avd_actor_forward(d, 3, 70, lib.ptr(pop.actor.flat), lib.ptr(s), 4, 1, 2.5, lib.ptr(out), lib.ptr(ws), ws.numel(), 0, lib.current_stream()))
     lib.check(lib.load().avd_critic_forward(d, 3, 70, lib.ptr(pop.critic.flat), lib.ptr(s), lib.ptr(a), lib.ptr(q), lib.ptr(ws), ws.numel(), 0, lib.current_stream()))
     for i in range(3):
@@ -325,3 +330,56 @@ def test_batched_trainer_interfrl_keeps_replicas_identical(mods):
         rows = tr.pop.actor.flat[m * G:(m + 1) * G]
         assert torch.equal(rows[0], rows[1]) and torch.equal(rows[0], rows[2])
     assert tr.fed.rounds == 6 and tr.pop.actor.step.tolist() == [6] * 6
+
+
+# ------------------------------------------------------------------------------------------ bf16 tensor-core mode
+@pytest.mark.parametrize("A,R", [(1, 64), (3, 64), (2, 1000), (1, 4096)])
+def test_learn_gradients_tensor_core_mode(mods, A, R):
+    """precision=1: the 256x128 / 304x128 contractions run as bf16 tcgen05 GEMMs with fp32 TMEM accumulation.
+    Bar against the fp32 oracle, per gradient tensor: relative L2 error < 3e-2 (critic) / 1e-1 (actor: its gradient is a difference of many bf16-rounded terms) (bf16 has
+    an 8-bit mantissa and the actor gradient passes through five bf16-rounded operands: dz2', W2c, dz2, W2, h1);
+    losses agree to 1e-2."""
+    conf, pop, nets, batches, (s, a, r, s2) = build_population(mods, A, R, list(range(50, 50 + A)))
+    pop.precision = 1
+    pop.learn(s, a, r, s2, apply_updates=False)
+    torch.cuda.synchronize()
+    for i in range(A):
+        ocg, oag, info = D.learn(nets[i][0], nets[i][1], nets[i][2], nets[i][3], batches[i], gamma=conf.gamma, high=conf.action_high)
+        for name in pop.critic.trainable_names:
+            got = pop.critic.view(name, i, pop.critic.grad).cpu().numpy()
+            assert _l2(got, ocg[name].reshape(got.shape)) < 3e-2 and _nrm(got, ocg[name].reshape(got.shape)) < 1e-1, ("critic", name)
+        for name in pop.actor.trainable_names:
+            got = pop.actor.view(name, i, pop.actor.grad).cpu().numpy()
+            assert _l2(got, oag[name].reshape(got.shape)) < 1e-1 and _nrm(got, oag[name].reshape(got.shape)) < 2e-1, ("actor", name)
+        loss = pop.loss[i].cpu().numpy()
+        assert abs(loss[0] - info["critic_loss"]) < 1e-2 * max(1, abs(info["critic_loss"]))
+        assert abs(loss[1] - info["actor_loss"]) < 1e-2 * max(1, abs(info["actor_loss"]))
+
+
+def test_forward_tensor_core_mode(mods):
+    conf, pop, nets, batches, (s, a, r, s2) = build_population(mods, 2, 300, [71, 72])
+    lib, d = mods["lib"], pop.dims
+    n = 2 * 300
+    out = torch.empty(n, device="cuda"); q = torch.empty(n, device="cuda")
+    ws = torch.empty(n * (d.l1 + d.la + d.l2) * 4 + 2 * (d.l1 + d.la) * d.l2 * 2 + 1024, dtype=torch.uint8, device="cuda")
+    lib.check(lib.load().avd_actor_forward(d, 2, 300, lib.ptr(pop.actor.flat), lib.ptr(s), 4, 1, 2.5, lib.ptr(out), lib.ptr(ws), ws.numel(), 1, lib.current_stream()))
+    lib.check(lib.load().avd_critic_forward(d, 2, 300, lib.ptr(pop.critic.flat), lib.ptr(s), lib.ptr(a), lib.ptr(q), lib.ptr(ws), ws.numel(), 1, lib.current_stream()))
+    for i in range(2):
+        ref_a, _ = D.actor_forward(nets[i][0], batches[i][0])
+        ref_q, _ = D.critic_forward(nets[i][1], batches[i][0], batches[i][1])
+        assert _nrm(out[i * 300:(i + 1) * 300].cpu().numpy(), ref_a.ravel()) < 1e-2
+        assert _nrm(q[i * 300:(i + 1) * 300].cpu().numpy(), ref_q.ravel()) < 1e-2
+
+
+def test_batched_trainer_tensor_core_mode(mods):
+    conf = mods["Config"](pl_size=2, batch_size=8, buffer_size=64)
+    tr = mods["trainer"].BatchedTrainer(conf, num_groups=2, envs_per_group=40, ring_capacity=64, precision=1)
+    w0 = tr.pop.critic.flat.clone()
+    for _ in range(14):
+        tr.step()
+    torch.cuda.synchronize()
+    assert not torch.equal(w0, tr.pop.critic.flat) and torch.isfinite(tr.pop.actor.flat).all() and torch.isfinite(tr.pop.critic.flat).all()
+    tr.capture(warmup=1)
+    tr.replay()
+    torch.cuda.synchronize()
+    assert torch.isfinite(tr.pop.actor.flat).all()
