@@ -111,12 +111,15 @@ __global__ void __launch_bounds__(128) l1_forward_kernel(avd_net_dims d, const f
     }
 }
 
-// layer-1 backward: from dH[n][f] accumulate dW, db, dg, dbe (atomics, one set per CTA and column)
+// layer-1 backward: from dH[n][f] accumulate dW, db, dg, dbe (one set of atomics per CTA and column).
+// The kernel is instruction-issue bound (ncu: 73 % issue-active), so the inner loop is kept minimal: inputs of a
+// row come from ONE 16-byte shared-memory broadcast, rows past the end are zero-padded instead of clamped, and the
+// state / action columns run in separately specialised loops.
 template <bool CRITIC>
 __global__ void __launch_bounds__(128) l1_backward_kernel(avd_net_dims d, const float* __restrict__ params, int64_t pstride,
                                                           const float* __restrict__ s, const float* __restrict__ act, int64_t R,
                                                           const float* __restrict__ dH, float* __restrict__ grads, int64_t gstride) {
-    constexpr int ROWS = kL1BwdRows;   // one set of atomics per column and 512 rows
+    constexpr int ROWS = kL1BwdRows;
     const int agent = blockIdx.y;
     const float* P = params + (int64_t)agent * pstride;
     float* G = grads + (int64_t)agent * gstride;
@@ -124,70 +127,95 @@ __global__ void __launch_bounds__(128) l1_backward_kernel(avd_net_dims d, const 
     const int64_t row0 = (int64_t)blockIdx.x * ROWS;
     const int nrows = (int)min((int64_t)ROWS, R - row0);
     const int64_t base = (int64_t)agent * R + row0;
-    __shared__ float xs[ROWS][9];
-    const int nx = d.ns + (CRITIC ? 1 : 0);
-    for (int i = threadIdx.x; i < nrows * nx; i += blockDim.x) {
-        const int r = i / nx, k = i % nx;
-        xs[r][k] = (k < d.ns) ? s[(base + r) * d.ns + k] : act[base + r];
+    __shared__ float4 xs4[ROWS];     // state words 0..3 (ns <= 4 fast path; words 4..7 in xs_hi)
+    __shared__ float4 xs_hi[ROWS];
+    __shared__ float xa[ROWS];
+    for (int r = threadIdx.x; r < ROWS; r += blockDim.x) {
+        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (r < nrows)
+            for (int k = 0; k < d.ns; ++k) v[k] = s[(base + r) * d.ns + k];
+        xs4[r] = make_float4(v[0], v[1], v[2], v[3]);
+        xs_hi[r] = make_float4(v[4], v[5], v[6], v[7]);
+        xa[r] = (CRITIC && r < nrows) ? act[base + r] : 0.0f;
     }
     __syncthreads();
-    int64_t oW, ob, og, obe, omu, ovar;
-    for (int f = threadIdx.x; f < F; f += blockDim.x) {
-        const bool is_act = CRITIC && f >= d.l1;
-        const int c = is_act ? f - d.l1 : f;
-        if (CRITIC) {
-            const CriticOff o = critic_off(d);
-            oW = is_act ? o.Wa : o.Ws; ob = is_act ? o.ba : o.bs; og = is_act ? o.ga : o.gs; obe = is_act ? o.bea : o.bes;
-            omu = is_act ? o.mua : o.mus; ovar = is_act ? o.vara : o.vars;
-        } else {
-            const ActorOff o = actor_off(d);
-            oW = o.W1; ob = o.b1; og = o.g1; obe = o.be1; omu = o.mu1; ovar = o.var1;
-        }
-        const int width = is_act ? d.la : d.l1;
-        const int nin = is_act ? 1 : d.ns;
-        float w[8], dw[8];
+    const int nrows8 = (nrows + 7) & ~7;
+    // ---- state columns
+    {
+        int64_t oW, ob, og, obe, omu, ovar;
+        if (CRITIC) { const CriticOff o = critic_off(d); oW = o.Ws; ob = o.bs; og = o.gs; obe = o.bes; omu = o.mus; ovar = o.vars; }
+        else { const ActorOff o = actor_off(d); oW = o.W1; ob = o.b1; og = o.g1; obe = o.be1; omu = o.mu1; ovar = o.var1; }
+        for (int f = threadIdx.x; f < d.l1; f += blockDim.x) {
+            float w[8], dw[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { w[k] = (k < nin) ? P[oW + (int64_t)k * width + c] : 0.0f; dw[k] = 0.0f; }
-        const float b = P[ob + c], mu = P[omu + c];
-        const float inv = 1.0f / sqrtf(P[ovar + c] + kBnEps);
-        const float ginv = P[og + c] * inv;
-        float db = 0.0f, dg = 0.0f, dbe = 0.0f;
-        for (int r0 = 0; r0 < nrows; r0 += 8) {
-            float dhv[8];
+            for (int k = 0; k < 8; ++k) { w[k] = (k < d.ns) ? P[oW + (int64_t)k * d.l1 + f] : 0.0f; dw[k] = 0.0f; }
+            const float b = P[ob + f], mu = P[omu + f];
+            const float inv = 1.0f / sqrtf(P[ovar + f] + kBnEps);
+            const float ginv = P[og + f] * inv;
+            float db = 0.0f, dg = 0.0f, dbe = 0.0f;
+            const float* dcol = dH + base * F + f;
+            for (int r0 = 0; r0 < nrows8; r0 += 8) {
+                float dhv[8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) dhv[u] = (r0 + u < nrows) ? dH[(base + r0 + u) * F + f] : 0.0f;   // 8 loads in flight
+                for (int u = 0; u < 8; ++u) dhv[u] = (r0 + u < nrows) ? dcol[(int64_t)(r0 + u) * F] : 0.0f;   // 8 loads in flight
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int r = min(r0 + u, nrows - 1);
-                const float dh = dhv[u];
-                float z = b;
-                if (is_act) {
-                    z = fmaf(xs[r][d.ns], w[0], z);
-                } else {
-#pragma unroll
-                    for (int k = 0; k < 8; ++k)
-                        if (k < nin) z = fmaf(xs[r][k], w[k], z);
-                }
-                const float rl = fmaxf(z, 0.0f);
-                dg = fmaf(dh, (rl - mu) * inv, dg);
-                dbe += dh;
-                const float dz = z > 0.0f ? dh * ginv : 0.0f;
-                db += dz;
-                if (is_act) {
-                    dw[0] = fmaf(xs[r][d.ns], dz, dw[0]);
-                } else {
-#pragma unroll
-                    for (int k = 0; k < 8; ++k)
-                        if (k < nin) dw[k] = fmaf(xs[r][k], dz, dw[k]);
+                for (int u = 0; u < 8; ++u) {
+                    const float4 x = xs4[r0 + u];
+                    float z = fmaf(x.x, w[0], fmaf(x.y, w[1], fmaf(x.z, w[2], fmaf(x.w, w[3], b))));
+                    float4 xh4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (d.ns > 4) {
+                        xh4 = xs_hi[r0 + u];
+                        z = fmaf(xh4.x, w[4], fmaf(xh4.y, w[5], fmaf(xh4.z, w[6], fmaf(xh4.w, w[7], z))));
+                    }
+                    const float dh = dhv[u];
+                    dg = fmaf(dh, (fmaxf(z, 0.0f) - mu) * inv, dg);
+                    dbe += dh;
+                    const float dz = z > 0.0f ? dh * ginv : 0.0f;
+                    db += dz;
+                    dw[0] = fmaf(x.x, dz, dw[0]); dw[1] = fmaf(x.y, dz, dw[1]); dw[2] = fmaf(x.z, dz, dw[2]); dw[3] = fmaf(x.w, dz, dw[3]);
+                    if (d.ns > 4) {
+                        dw[4] = fmaf(xh4.x, dz, dw[4]); dw[5] = fmaf(xh4.y, dz, dw[5]); dw[6] = fmaf(xh4.z, dz, dw[6]); dw[7] = fmaf(xh4.w, dz, dw[7]);
+                    }
                 }
             }
-        }
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-            if (k < nin) atomicAdd(G + oW + (int64_t)k * width + c, dw[k]);
-        atomicAdd(G + ob + c, db);
-        atomicAdd(G + og + c, dg);
-        atomicAdd(G + obe + c, dbe);
+            for (int k = 0; k < 8; ++k)
+                if (k < d.ns) atomicAdd(G + oW + (int64_t)k * d.l1 + f, dw[k]);
+            atomicAdd(G + ob + f, db);
+            atomicAdd(G + og + f, dg);
+            atomicAdd(G + obe + f, dbe);
+        }
+    }
+    // ---- action columns (critic only)
+    if (CRITIC) {
+        const CriticOff o = critic_off(d);
+        for (int c = threadIdx.x; c < d.la; c += blockDim.x) {
+            const float w = P[o.Wa + c], b = P[o.ba + c], mu = P[o.mua + c];
+            const float inv = 1.0f / sqrtf(P[o.vara + c] + kBnEps);
+            const float ginv = P[o.ga + c] * inv;
+            float dw = 0.0f, db = 0.0f, dg = 0.0f, dbe = 0.0f;
+            const float* dcol = dH + base * F + d.l1 + c;
+            for (int r0 = 0; r0 < nrows8; r0 += 8) {
+                float dhv[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) dhv[u] = (r0 + u < nrows) ? dcol[(int64_t)(r0 + u) * F] : 0.0f;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const float a = xa[r0 + u];
+                    const float z = fmaf(a, w, b);
+                    const float dh = dhv[u];
+                    dg = fmaf(dh, (fmaxf(z, 0.0f) - mu) * inv, dg);
+                    dbe += dh;
+                    const float dz = z > 0.0f ? dh * ginv : 0.0f;
+                    db += dz;
+                    dw = fmaf(a, dz, dw);
+                }
+            }
+            atomicAdd(G + o.Wa + c, dw);
+            atomicAdd(G + o.ba + c, db);
+            atomicAdd(G + o.ga + c, dg);
+            atomicAdd(G + o.bea + c, dbe);
+        }
     }
 }
 

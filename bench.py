@@ -240,6 +240,22 @@ def run_native(args):
            "d2h_bytes_per_step": int(h_out.numel()) * 4, "ms_per_step": e2e_ms, "steps": n_e2e,
            "api": "BatchedTrainer.step(host_leader_exog=pinned) + D2H of reward/done statistics and losses"}
 
+    # ---- FRL round (interfrl, gradients): local reduce -> ONE all_reduce over NVLink -> scale -> broadcast -> Adam x2 -> Polyak x2
+    from avddpg_b200.config import Config as _Config
+    from avddpg_b200.server.federated import FederatedAggregator
+    pg = None
+    if world > 1:
+        import torch.distributed as dist
+        pg = dist.group.WORLD
+    agg = FederatedAggregator(pop, _Config(pl_size=M, fed_method="interfrl", weighted_average_enabled=False), process_group=pg)
+    for _ in range(5):
+        agg.aggregate_gradients()
+    ms_frl = _timed(lambda: agg.aggregate_gradients(), 50, world)
+    ms_frl_exchange = _timed(lambda: agg.aggregate_gradients(apply=False), 50, world)
+    frl = {"mode": "interfrl / gradients / unweighted", "round_us": ms_frl * 1e3, "reduce_exchange_broadcast_us": ms_frl_exchange * 1e3,
+           "payload_bytes": int(M * (pop.actor.n_train + pop.critic.n_train + 1) * 4), "ranks": world,
+           "includes": "avd_fed_reduce + NCCL all_reduce(sum) [N>1] + scale + avd_fed_broadcast + Adam x2 + Polyak x2"}
+
     out = None
     if rank == 0:
         rows = pop.A * pop.R
@@ -277,7 +293,7 @@ def run_native(args):
                "platoon_steps_per_s": value / M,
                "ddpg_minibatch_updates_per_s": world * P * M / (ms_step * 1e-3),
                "ddpg_weight_updates_per_s": world * pop.A / (ms_step * 1e-3),
-               "ms_env_part": ms_env, "ms_learn_part": ms_learn}
+               "ms_env_part": ms_env, "ms_learn_part": ms_learn, "frl": frl}
         print(json.dumps(out))
     if world > 1:
         import torch.distributed as dist
@@ -323,7 +339,7 @@ def main():
     ap.add_argument("--roofline-platoons", type=int, default=4 * 1024 * 1024)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--precision", type=int, default=0, help="0: fp32 SIMT learn kernels (parity mode); 1: bf16 tcgen05 GEMMs")
+    ap.add_argument("--precision", type=int, default=1, help="0: fp32 SIMT learn kernels (parity mode); 1: bf16 tcgen05 GEMMs")
     ap.add_argument("--graph", action="store_true", help="replay a captured CUDA graph of the training step")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -1,0 +1,78 @@
+"""Multi-GPU tests (run with at least 2 visible GPUs; skipped otherwise): interfrl aggregation over NCCL equals the
+single-process aggregation over the union of the platoons, and sharded platoons reproduce the single-GPU streams."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from avddpg_b200.config import Config
+    from avddpg_b200.environment import BatchedPlatoons
+    from avddpg_b200.server.federated import FederatedAggregator
+    from avddpg_b200.trainer import DDPGPopulation
+    conf = Config(pl_size=2, fed_method="interfrl", weighted_average_enabled=False)
+    G_total, M = 4, 2
+    G = G_total // world
+    pop = DDPGPopulation(G, M, conf)
+    gen = torch.Generator(device="cuda").manual_seed(123)
+    full_a = torch.randn(M, G_total, pop.actor.n_train, device="cuda", generator=gen)      # same on every rank
+    full_c = torch.randn(M, G_total, pop.critic.n_train, device="cuda", generator=gen)
+    lo = rank * G
+    pop.actor.grad.copy_(full_a[:, lo:lo + G].reshape(M * G, -1))
+    pop.critic.grad.copy_(full_c[:, lo:lo + G].reshape(M * G, -1))
+    agg = FederatedAggregator(pop, conf, process_group=dist.group.WORLD)
+    agg.aggregate_gradients(apply=False)
+    ok_a = torch.allclose(pop.actor.grad.reshape(M, G, -1), full_a.mean(1, keepdim=True).expand(M, G, -1), rtol=1e-5, atol=1e-6)
+    ok_c = torch.allclose(pop.critic.grad.reshape(M, G, -1), full_c.mean(1, keepdim=True).expand(M, G, -1), rtol=1e-5, atol=1e-6)
+    # sharded env == slice of the global env (RNG streams keyed by global platoon id)
+    P_total = 64
+    Pl = P_total // world
+    env = BatchedPlatoons(Pl, M, conf, platoon_id_base=rank * Pl, seed=9)
+    env.reset()
+    for _ in range(5):
+        env.action_mu.zero_()
+        env.step_native(explore=True, gen_exog=True)
+    q.put((rank, bool(ok_a), bool(ok_c), env.state.cpu().numpy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_interfrl_nccl_and_sharded_env_world2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=300) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert all(r[1] and r[2] for r in res)
+    from avddpg_b200.config import Config
+    from avddpg_b200.environment import BatchedPlatoons
+    conf = Config(pl_size=2)
+    env = BatchedPlatoons(64, 2, conf, seed=9)
+    env.reset()
+    for _ in range(5):
+        env.action_mu.zero_()
+        env.step_native(explore=True, gen_exog=True)
+    full = env.state.cpu().numpy()
+    assert np.array_equal(np.concatenate([res[0][3], res[1][3]], axis=0), full)
