@@ -8,7 +8,7 @@
 // One persistent CTA per SM walks a contiguous range of 128-row tiles.  Roles (13 warps):
 //   warp 0      : TMEM allocation; one elected thread loads W2^T when the agent changes (TMA) and issues all MMAs
 //   warps 1..4  : epilogue, TMEM lane quadrant = warp % 4; double-buffered accumulator (2 x 128 columns)
-//   warps 5..12 : producers; 256 threads fill one 128 x 64 k-block (16 KB) at a time into an 8-slot ring, so the MMA
+//   warps 5..12 : producers; 256 threads fill one 128 x 64 k-block (16 KB) at a time into a 7-slot ring, so the MMA
 //                 of k-block j overlaps the production of k-block j+1 and tiles overlap each other
 // This replaces, per pass, l1_forward + gemm + head (three kernels and two HBM round trips of the activations).
 // Reference semantics: agent/model.py:19-37 (actor), 55-83 (critic); workers/trainer.py:493-495, 502-503, 287.
@@ -25,7 +25,7 @@ using namespace umma;
 typedef __nv_bfloat16 bf16;
 
 constexpr int TILE_M = 128, L2N = 128, KB = 64;
-constexpr int NSLOT = 8;                       // ring of 16 KB k-block slots for A
+constexpr int NSLOT = 7;                       // ring of 16 KB k-block slots for A
 constexpr int MAX_KB = 5;                      // up to 320 input features for layer 2
 constexpr int PTAB_COLS = MAX_KB * KB;         // 320
 constexpr int NUM_PRODUCERS = 256, NUM_THREADS = 32 + 128 + NUM_PRODUCERS;
@@ -34,8 +34,10 @@ constexpr int W_BYTES = MAX_KB * L2N * KB * 2; // 80 KB
 constexpr int OFF_W = NSLOT * SLOT_BYTES;                       // 128 KB
 constexpr int OFF_PTAB = OFF_W + W_BYTES;                       // + 80 KB
 constexpr int OFF_ETAB = OFF_PTAB + 8 * PTAB_COLS * 4;          // + 10 KB
-constexpr int OFF_BAR = OFF_ETAB + (4 * L2N + 4) * 4;           // + 2 KB
+constexpr int OFF_SCRATCH = OFF_ETAB + (4 * L2N + 4) * 4;       // + 2 KB
+constexpr int OFF_BAR = OFF_SCRATCH + 4 * 32 * 33 * 4;          // + 16.5 KB (Z-store transpose scratch, one per epilogue warp)
 constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
+static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB shared memory of an sm_100 CTA");
 
 enum HeadMode { HEAD_NONE = 0, HEAD_ACTOR = 1, HEAD_TARGET = 2, HEAD_Q = 3 };
 
@@ -173,10 +175,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused_forward_kernel(const __g
             for (int c = 0; c < L2N / 32; ++c) {
                 float v[32];
                 tmem_ld32(tmem_base + (uint32_t)(buf * L2N) + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
-                if (g.Z_out && valid) {
-                    float4* dst = reinterpret_cast<float4*>(g.Z_out + n * L2N + c * 32);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                if (g.Z_out) {   // coalesced through the per-warp transpose scratch
+                    const int64_t blk_row = (int64_t)tile_in_agent * TILE_M + q * 32;
+                    const int rows_here = (int)min((int64_t)32, g.R - blk_row);
+                    if (rows_here > 0)
+                        store_block_32x32(reinterpret_cast<float*>(smem + OFF_SCRATCH) + (warp - 1) * (32 * 33), v,
+                                          g.Z_out + ((int64_t)agent * g.R + blk_row) * L2N + c * 32, L2N, rows_here, 32, lane);
                 }
                 if (g.head != HEAD_NONE) {
 #pragma unroll

@@ -23,7 +23,8 @@ constexpr int BM = 128, BN = 128, BK = 64;
 constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KB
 constexpr int B_STAGE_BYTES = BN * BK * 2;   // 16 KB
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-constexpr int smem_bytes(int stages) { return stages * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/; }
+constexpr int SCRATCH_BYTES = 4 * 32 * 33 * 4;   // per-epilogue-warp transpose scratch
+constexpr int smem_bytes(int stages) { return stages * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + SCRATCH_BYTES; }
 // TN GEMMs of the learn step have K <= 320 (2..5 k-blocks): 2 stages = 65 KB so that three CTAs share an SM and one
 // CTA's prologue/epilogue overlaps another's MMAs; the NT weight-gradient GEMM streams thousands of rows: 4 stages.
 constexpr int STAGES_TN = 2, STAGES_NT = 4;
@@ -48,6 +49,7 @@ __global__ void __launch_bounds__(NUM_THREADS, (STAGES <= 2) ? 3 : 1) gemm_bf16_
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* accum_bar = empty_bar + STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+    float* scratch_all = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
@@ -123,24 +125,22 @@ __global__ void __launch_bounds__(NUM_THREADS, (STAGES <= 2) ? 3 : 1) gemm_bf16_
         tc_fence_after();
         const int row = m0 + q * 32 + lane;
         float* crow = g.C + (int64_t)batch * g.c_batch + (int64_t)row * g.ldc;
+        float* scratch = scratch_all + (warp - 2) * (32 * 33);
+        float* cblock = g.C + (int64_t)batch * g.c_batch + (int64_t)(m0 + q * 32) * g.ldc;
+        const int rows_here = min(32, g.M - (m0 + q * 32));
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
             float v[32];
             tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
-            if (row < g.M) {
-                const int col0 = n0 + c * 32;
-                if (g.atomic) {
+            const int col0 = n0 + c * 32;
+            if (g.atomic) {
+                if (row < g.M) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
                         if (col0 + j < g.N) atomicAdd(crow + col0 + j, v[j]);
-                } else if (col0 + 32 <= g.N && ((reinterpret_cast<uintptr_t>(crow + col0) & 15) == 0)) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(crow + col0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (col0 + j < g.N) crow[col0 + j] = v[j];
                 }
+            } else if (col0 < g.N && rows_here > 0) {
+                store_block_32x32(scratch, v, cblock + col0, g.ldc, rows_here, min(32, g.N - col0), lane);
             }
         }
         tc_fence_before();

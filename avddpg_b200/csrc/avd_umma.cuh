@@ -99,6 +99,38 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// ---- coalesced store of a 32 x 32 fp32 block held one-row-per-lane -----------------------------------
+// After tcgen05.ld.32x32b every lane owns 32 consecutive columns of ITS row, so a direct store makes each
+// instruction touch 32 different 128-byte lines (32 L1 wavefronts).  Staging the block through a padded
+// per-warp shared-memory scratch ([32][33] floats) and reading it back with lane = column-quad turns every
+// store instruction into four fully used 128-byte lines.  `row_ptr0` points at (row 0 of the block, column 0
+// of the block); rows are `ld` floats apart; rows >= nrows and columns >= ncols are masked.
+__device__ __forceinline__ void store_block_32x32(float* scratch, const float* v, float* row_ptr0, int64_t ld, int nrows, int ncols, int lane) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) scratch[lane * 33 + j] = v[j];
+    __syncwarp();
+    const int cq = (lane & 7) * 4;       // first of my four columns
+    const int rsub = lane >> 3;          // 0..3
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(row_ptr0) & 15) == 0) && ((ld & 3) == 0) && (ncols == 32);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int r = i * 4 + rsub;
+        const float a = scratch[r * 33 + cq], b = scratch[r * 33 + cq + 1], c = scratch[r * 33 + cq + 2], d = scratch[r * 33 + cq + 3];
+        if (r < nrows) {
+            float* dst = row_ptr0 + (int64_t)r * ld + cq;
+            if (vec_ok) {
+                *reinterpret_cast<float4*>(dst) = make_float4(a, b, c, d);
+            } else {
+                if (cq < ncols) dst[0] = a;
+                if (cq + 1 < ncols) dst[1] = b;
+                if (cq + 2 < ncols) dst[2] = c;
+                if (cq + 3 < ncols) dst[3] = d;
+            }
+        }
+    }
+    __syncwarp();
+}
+
 // ---- descriptors ---------------------------------------------------------------------------------
 // shared-memory matrix descriptor, SWIZZLE_128B, version 1 (Blackwell):
 //   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 | [32,46) stride byte offset >> 4 | [46,48) = 1 | [61,64) = 2
