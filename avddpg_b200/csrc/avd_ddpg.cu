@@ -510,6 +510,12 @@ __global__ void __launch_bounds__(256) fed_reduce_kernel(float* __restrict__ out
     }
 }
 
+__global__ void __launch_bounds__(256) fed_finalize_kernel(float* __restrict__ buf, int64_t pitch, int64_t n) {
+    float* row = buf + (int64_t)blockIdx.y * pitch;
+    const float inv = 1.0f / row[n];
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) row[i] *= inv;
+}
+
 __global__ void __launch_bounds__(256) fed_broadcast_kernel(float* __restrict__ out, int64_t out_pitch, const float* __restrict__ in,
                                                             int64_t in_pitch, int n_members, int64_t stride_s, int64_t stride_x,
                                                             const uint8_t* __restrict__ mask, int64_t n) {
@@ -816,6 +822,15 @@ extern "C" int avd_fed_reduce(float* out, int64_t out_pitch, const float* in, in
     const int gx = (int)std::min<int64_t>((n + 255) / 256, 128);
     fed_reduce_kernel<<<dim3(gx, n_systems), 256, 0, (cudaStream_t)stream>>>(out, out_pitch, in, pitch, n_members, member_stride_s,
                                                                               member_stride_x, weights, scale, n);
+    AVD_LAUNCH_OK();
+    return AVD_OK;
+}
+
+extern "C" int avd_fed_finalize(float* buf, int64_t pitch, int32_t n_systems, int64_t n, void* stream) {
+    AVD_REQUIRE(buf && n_systems >= 0 && n >= 0 && pitch > n, "bad args");
+    if (n_systems == 0 || n == 0) return AVD_OK;
+    const int gx = (int)std::min<int64_t>((n + 255) / 256, 128);
+    fed_finalize_kernel<<<dim3(gx, n_systems), 256, 0, (cudaStream_t)stream>>>(buf, pitch, n);
     AVD_LAUNCH_OK();
     return AVD_OK;
 }

@@ -32,12 +32,16 @@ class ReplayRings:
         self.seed, self.ring_id_base = int(seed), int(ring_id_base)
         self.data = torch.empty(self.capacity, self.M, self.P, _lib.RING_RECORD_FLOATS, dtype=torch.float32, device=self.device)
         self.clock = clock if clock is not None else DeviceClock(self.device)
-        n = self.n_rings * self.batch_size
-        self.idx = torch.zeros(self.n_rings, self.batch_size, dtype=torch.int64, device=self.device)
-        self.s = torch.zeros(n, 4, dtype=torch.float32, device=self.device)
-        self.a = torch.zeros(n, dtype=torch.float32, device=self.device)
-        self.r = torch.zeros(n, dtype=torch.float32, device=self.device)
-        self.s2 = torch.zeros(n, 4, dtype=torch.float32, device=self.device)
+        self.idx = self.s = self.a = self.r = self.s2 = None      # sample buffers: allocated on first use
+
+    def _alloc_sample_buffers(self):
+        if self.idx is None:
+            n = self.n_rings * self.batch_size
+            self.idx = torch.zeros(self.n_rings, self.batch_size, dtype=torch.int64, device=self.device)
+            self.s = torch.zeros(n, 4, dtype=torch.float32, device=self.device)
+            self.a = torch.zeros(n, dtype=torch.float32, device=self.device)
+            self.r = torch.zeros(n, dtype=torch.float32, device=self.device)
+            self.s2 = torch.zeros(n, 4, dtype=torch.float32, device=self.device)
 
     def add(self, s, a, r, s2, advance_clock=True):
         """Stand-alone ReplayBuffer.add for all rings: s, s2 [4][M][P]; a, r [M][P] (native layout)."""
@@ -52,11 +56,13 @@ class ReplayRings:
         self.clock.set(ring_count=self.capacity)
 
     def sample_indices(self):
+        self._alloc_sample_buffers()
         _lib.check(self.lib.avd_replay_sample_indices(_lib.ptr(self.idx), self.n_rings, self.ring_id_base, self.batch_size,
                                                       self.capacity, self.seed, self.clock.ptr, _lib.current_stream()))
         return self.idx
 
     def gather(self, idx=None):
+        self._alloc_sample_buffers()
         idx = self.idx if idx is None else idx
         _lib.check(self.lib.avd_replay_gather(_lib.ptr(self.data), self.capacity, self.M, self.P, _lib.ptr(idx),
                                               self.batch_size, _lib.ptr(self.s), _lib.ptr(self.a), _lib.ptr(self.r),

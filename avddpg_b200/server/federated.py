@@ -74,7 +74,10 @@ def exchange_and_scale(buf: torch.Tensor, process_group=None) -> torch.Tensor:
     if process_group is not None:
         import torch.distributed as dist
         dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=process_group)
-    buf[:, :-1] *= (1.0 / buf[:, -1]).unsqueeze(1)
+    if buf.is_cuda:
+        _lib.check(_lib.load().avd_fed_finalize(_lib.ptr(buf), buf.shape[1], buf.shape[0], buf.shape[1] - 1, _lib.current_stream()))
+    else:   # host tensors: only the gloo unit test of the exchange logic
+        buf[:, :-1] *= (1.0 / buf[:, -1]).unsqueeze(1)
     return buf
 
 
@@ -110,6 +113,8 @@ class FederatedAggregator:
         dev = population.device
         self._bufs = {}
         self.device = dev
+        self._ones = torch.ones(self.n_systems, dtype=torch.float32, device=dev)
+        self._count = torch.full((self.n_systems,), float(self.n_members), dtype=torch.float32, device=dev)
         self.apply_mask = None
         if (not self.inter) and getattr(conf, "intra_directional_averaging", False):
             mask = torch.ones(G * M, dtype=torch.uint8, device=dev)
@@ -129,7 +134,7 @@ class FederatedAggregator:
         buf = self._buffer(na, nc)
         pitch = buf.shape[1]
         st = _lib.current_stream()
-        ones = torch.ones(S, dtype=torch.float32, device=self.device)
+        ones = self._ones
         w = None
         if weights is not None:
             w = torch.as_tensor(weights, dtype=torch.float32, device=self.device).reshape(S, X).contiguous()
@@ -137,7 +142,7 @@ class FederatedAggregator:
             out = buf[:, off:]
             _lib.check(self.lib.avd_fed_reduce(_lib.ptr(out), pitch, _lib.ptr(src), src_pitch, S, X, self.stride_s, self.stride_x,
                                                _lib.ptr(w), _lib.ptr(ones), n, st))
-        buf[:, na + nc] = w.sum(dim=1) if w is not None else float(X)
+        buf[:, na + nc].copy_(w.sum(dim=1) if w is not None else self._count)
         exchange_and_scale(buf, self.pg if (self.inter and self.world > 1) else None)
         self.rounds += 1
         return buf

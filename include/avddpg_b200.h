@@ -270,6 +270,10 @@ int avd_fed_reduce(float* out, int64_t out_pitch, const float* in, int64_t pitch
                    int64_t member_stride_s, int64_t member_stride_x, const float* weights, const float* scale, int64_t n,
                    void* stream);
 
+/* buf[s][0..n) *= 1 / buf[s][n]: turns the exchanged (weighted) sums into means (federated.py:62 / :110); the
+ * divisor (member count or sum of weights) travels in column n of the same buffer through the all_reduce.     */
+int avd_fed_finalize(float* buf, int64_t pitch, int32_t n_systems, int64_t n, void* stream);
+
 /* out[a][j] = in[src(a)][j]: broadcast system averages back onto members (set_weights, trainer.py:448-456). */
 int avd_fed_broadcast(float* out, int64_t out_pitch, const float* in, int64_t in_pitch, int32_t n_systems,
                       int32_t n_members, int64_t member_stride_s, int64_t member_stride_x, const uint8_t* apply_mask,
