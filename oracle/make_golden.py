@@ -280,3 +280,8 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+# The evaluator fixture (tests/golden/evaluator.npz) is produced by tools/make_evaluator_golden.py: the reference's
+# Platoon(evaluator_states_enabled=True) + its own pre-drawn leader inputs + ddpgagent.policy, driven by the oracle's
+# actor forward (the reference's Keras actors need TensorFlow).

@@ -387,3 +387,27 @@ def test_batched_trainer_tensor_core_mode(mods):
     tr.replay()
     torch.cuda.synchronize()
     assert torch.isfinite(tr.pop.actor.flat).all()
+
+
+def test_evaluator_rollout_vs_reference_golden(mods, golden):
+    """N2: noise-free evaluation rollout (workers/evaluator.py:40-96,145) on the reference's own seed-6 leader inputs
+    and fixed evaluator initial state; actors injected.  precision=0 so the 100-step closed loop stays on the
+    reference trajectory; pl_rew is the value the reference reports (3 decimals)."""
+    from avddpg_b200 import evaluator
+    g = golden("evaluator")
+    conf = mods["Config"](pl_size=3)
+    pop = mods["trainer"].DDPGPopulation(1, 3, conf)
+    for m in range(3):
+        pop.actor.load_named(m, {k[len(f"actor{m}_"):]: v for k, v in g.items() if k.startswith(f"actor{m}_")})
+    T = int(g["T"])
+    pl_rew, tr = evaluator.run(conf, pop, num_platoons=2, leader_inputs=np.repeat(g["inputs"][:, None], 2, axis=1),
+                               manual_timestep_override=T, precision=0, return_traces=True)
+    st = tr["states"].cpu().numpy()
+    assert np.array_equal(st[:, 0], st[:, 1])                 # both platoons saw the same inputs
+    assert _nrm(st[:, 0], g["states"]) < 2e-5 and _nrm(tr["inputs"][:, 0].cpu().numpy(), g["actions"]) < 2e-5
+    assert _nrm(tr["jerks"][:, 0].cpu().numpy(), g["jerks"]) < 5e-4
+    np.testing.assert_allclose(tr["rewards"][0].cpu().numpy(), g["ep_reward"], rtol=2e-5)
+    assert abs(pl_rew - float(g["pl_rew"])) <= 1e-3
+    # device-drawn leader inputs: runs, finite, same initial state
+    pl2 = evaluator.run(conf, pop, num_platoons=64, manual_timestep_override=20, precision=1)
+    assert np.isfinite(pl2)
