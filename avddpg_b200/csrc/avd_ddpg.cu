@@ -31,7 +31,7 @@ namespace fused {  // avd_fused.cu
 bool supported(const avd_net_dims& d, bool critic);
 int forward(const avd_net_dims& d, bool critic, int A, int64_t R, const float* params, int64_t pstride, const bf16* W2T, const float* s,
             int64_t s_rs, int64_t s_cs, const float* act, bf16* H_out, float* Z_out, int head, const float* rew, float gamma, float high,
-            float* out, cudaStream_t st);
+            float* out, cudaStream_t st, bf16* DZ_out = nullptr, float* loss = nullptr);
 }
 
 namespace umma {   // avd_umma.cu
@@ -923,7 +923,9 @@ extern "C" int avd_ddpg_learn(const avd_learn_io* io, void* stream) {
     if (fz) {
         AVD_TRY(fused::forward(d, false, A, R, io->actor, ao.total, w.aW2T, io->s, d.ns, 1, nullptr, (bf16*)w.H1a, w.Za, 1, nullptr, 0.f,
                                io->action_high, w.a2, st));   // pi
-        AVD_TRY(fused::forward(d, true, A, R, io->critic, co.total, w.cW2T, io->s, d.ns, 1, w.a2, nullptr, w.Z, 0, nullptr, 0.f, 0.f, nullptr, st));
+        // critic(s, pi) with the action-only head-backward fused into the TMEM epilogue: emits dz2 (bf16) directly
+        AVD_TRY(fused::forward(d, true, A, R, io->critic, co.total, w.cW2T, io->s, d.ns, 1, w.a2, nullptr, nullptr, 4, nullptr, 0.f, 0.f, nullptr, st,
+                               (bf16*)w.DZ, io->loss));
     } else {
         AVD_TRY(p.layer1(false, io->actor, io->s, d.ns, 1, nullptr, w.H1a));
         AVD_TRY(p.forward(w.H1a, d.l1, io->actor, ao.total, ao.W2, w.aW2T, w.Za));
@@ -934,8 +936,6 @@ extern "C" int avd_ddpg_learn(const avd_learn_io* io, void* stream) {
         }
         AVD_TRY(p.layer1(true, io->critic, io->s, d.ns, 1, w.a2, w.H));
         AVD_TRY(p.forward(w.H, F, io->critic, co.total, co.W2, w.cW2T, w.Z));
-    }
-    {
         HeadArgs h = critic_head(d, io->critic, w.Z, R);
         h.DZ = w.DZ; h.loss = io->loss;
         AVD_TRY(launch_head<HEAD_CRITIC_BWD_ACTION>(h, d.l2, A, st, tc));

@@ -39,7 +39,7 @@ constexpr int OFF_BAR = OFF_SCRATCH + 4 * 32 * 33 * 4;          // + 16.5 KB (Z-
 constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB shared memory of an sm_100 CTA");
 
-enum HeadMode { HEAD_NONE = 0, HEAD_ACTOR = 1, HEAD_TARGET = 2, HEAD_Q = 3 };
+enum HeadMode { HEAD_NONE = 0, HEAD_ACTOR = 1, HEAD_TARGET = 2, HEAD_Q = 3, HEAD_BWD_ACTION = 4 };
 
 struct Args {
     avd_net_dims d;
@@ -57,6 +57,8 @@ struct Args {
     const float* rew;
     float gamma, high;
     float* out;                 // [A*R]
+    bf16* DZ_out;               // HEAD_BWD_ACTION: [A*R][128] bf16  d(-mean q)/dz2   (trainer.py:503-506)
+    float* loss;                // HEAD_BWD_ACTION: loss[2*agent+1] += -mean(q)  (nullable)
     int tiles_per_agent, total_tiles, tiles_per_cta;
 };
 
@@ -182,7 +184,23 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused_forward_kernel(const __g
                         store_block_32x32(reinterpret_cast<float*>(smem + OFF_SCRATCH) + (warp - 1) * (32 * 33), v,
                                           g.Z_out + ((int64_t)agent * g.R + blk_row) * L2N + c * 32, L2N, rows_here, 32, lane);
                 }
-                if (g.head != HEAD_NONE) {
+                if (g.head == HEAD_BWD_ACTION) {
+                    // actor loss -mean(q): dq = -1/R for every row, so dz2 = (z2 > 0) ? -W3*g2*inv2/R : 0 needs no row reduction
+                    const float neg_inv_R = -1.0f / (float)g.R;
+                    float dz[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int col = c * 32 + j;
+                        const float z = v[j] + etab[col];
+                        acc = fmaf(fmaf(fmaxf(z, 0.0f), etab[L2N + col], etab[2 * L2N + col]), etab[3 * L2N + col], acc);
+                        dz[j] = z > 0.0f ? neg_inv_R * etab[3 * L2N + col] * etab[L2N + col] : 0.0f;
+                    }
+                    const int64_t blk_row = (int64_t)tile_in_agent * TILE_M + q * 32;
+                    const int rows_here = (int)min((int64_t)32, g.R - blk_row);
+                    if (rows_here > 0)
+                        store_block_32x32_bf16(reinterpret_cast<float*>(smem + OFF_SCRATCH) + (warp - 1) * (32 * 33), dz,
+                                               g.DZ_out + ((int64_t)agent * g.R + blk_row) * L2N + c * 32, L2N, rows_here, lane);
+                } else if (g.head != HEAD_NONE) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         const int col = c * 32 + j;
@@ -194,7 +212,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused_forward_kernel(const __g
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[buf]);
-            if (g.head != HEAD_NONE && valid) {
+            if (g.head == HEAD_BWD_ACTION) {
+                if (g.loss) {
+                    const float part = warp_sum(valid ? -(acc + etab[4 * L2N]) / (float)g.R : 0.0f);
+                    if (lane == 0) atomicAdd(g.loss + 2 * agent + 1, part);
+                }
+            } else if (g.head != HEAD_NONE && valid) {
                 const float pre = acc + etab[4 * L2N];
                 float o;
                 if (g.head == HEAD_ACTOR) o = g.high * tanhf(pre);
@@ -286,15 +309,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused_forward_kernel(const __g
                         sh[0] = lo.x; sh[1] = lo.y; sh[2] = lo.z; sh[3] = lo.w; sh[4] = hi.x; sh[5] = hi.y; sh[6] = hi.z; sh[7] = hi.w;
                     }
                     uint8_t* slot_base = smem + slot * SLOT_BYTES;
+                    const bool act_chunk = g.critic && col0 >= d.l1;
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const int row = rg * 4 + i;
                         float h[8];
 #pragma unroll
                         for (int c = 0; c < 8; ++c) {
-                            float z = b[c];
-#pragma unroll
-                            for (int k = 0; k < 5; ++k) z = fmaf(x[i][k], w[k][c], z);
+                            float z;
+                            if (act_chunk) {      // action branch of the critic: one input (model.py:69-70)
+                                z = fmaf(x[i][4], w[4][c], b[c]);
+                            } else {              // state columns: ns <= 4 inputs (unused weights are zero)
+                                z = fmaf(x[i][0], w[0][c], fmaf(x[i][1], w[1][c], fmaf(x[i][2], w[2][c], fmaf(x[i][3], w[3][c], b[c]))));
+                            }
                             h[c] = fmaf(fmaxf(z, 0.0f), sc[c], sh[c]);
                         }
                         const uint4 packed = make_uint4(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]), pack_bf16x2(h[4], h[5]), pack_bf16x2(h[6], h[7]));
@@ -335,7 +362,7 @@ bool supported(const avd_net_dims& d, bool critic) {
 // W2T: bf16 [A][128][F] (K-major copy of the layer-2 kernel, see pack_w2_kernel)
 int forward(const avd_net_dims& d, bool critic, int A, int64_t R, const float* params, int64_t pstride, const bf16* W2T, const float* s,
             int64_t s_rs, int64_t s_cs, const float* act, bf16* H_out, float* Z_out, int head, const float* rew, float gamma, float high,
-            float* out, cudaStream_t st) {
+            float* out, cudaStream_t st, bf16* DZ_out, float* loss) {
     if (!supported(d, critic)) {
         set_error("fused forward kernel does not support these layer sizes");
         return AVD_ERR_UNSUPPORTED;
@@ -365,7 +392,7 @@ int forward(const avd_net_dims& d, bool critic, int A, int64_t R, const float* p
     Args g;
     g.d = d; g.critic = critic ? 1 : 0; g.A = A; g.R = R; g.params = params; g.pstride = pstride;
     g.s = s; g.s_rs = s_rs; g.s_cs = s_cs; g.act = act; g.H_out = H_out; g.Z_out = Z_out; g.head = head; g.rew = rew;
-    g.gamma = gamma; g.high = high; g.out = out;
+    g.gamma = gamma; g.high = high; g.out = out; g.DZ_out = DZ_out; g.loss = loss;
     g.tiles_per_agent = (int)((R + TILE_M - 1) / TILE_M);
     g.total_tiles = g.tiles_per_agent * A;
     const int ctas = std::min(g.total_tiles, sm_count());

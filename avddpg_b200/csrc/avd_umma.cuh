@@ -131,6 +131,27 @@ __device__ __forceinline__ void store_block_32x32(float* scratch, const float* v
     __syncwarp();
 }
 
+// Same staging, bf16 output (e.g. dz2 tiles consumed by the dgrad / wgrad GEMMs): 8-byte stores, 4 rows x 64 B per instruction.
+__device__ __forceinline__ void store_block_32x32_bf16(float* scratch, const float* v, __nv_bfloat16* row_ptr0, int64_t ld, int nrows, int lane) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) scratch[lane * 33 + j] = v[j];
+    __syncwarp();
+    const int cq = (lane & 7) * 4, rsub = lane >> 3;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int r = i * 4 + rsub;
+        const __nv_bfloat162 lo = __floats2bfloat162_rn(scratch[r * 33 + cq], scratch[r * 33 + cq + 1]);
+        const __nv_bfloat162 hi = __floats2bfloat162_rn(scratch[r * 33 + cq + 2], scratch[r * 33 + cq + 3]);
+        if (r < nrows) {
+            uint2 pk;
+            pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+            pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+            *reinterpret_cast<uint2*>(row_ptr0 + (int64_t)r * ld + cq) = pk;
+        }
+    }
+    __syncwarp();
+}
+
 // ---- descriptors ---------------------------------------------------------------------------------
 // shared-memory matrix descriptor, SWIZZLE_128B, version 1 (Blackwell):
 //   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 | [32,46) stride byte offset >> 4 | [46,48) = 1 | [61,64) = 2
