@@ -22,6 +22,7 @@
 
 #include "avd_common.cuh"
 #include "avd_ddpg_layout.cuh"
+#include "avd_umma.cuh"
 
 namespace avd {
 
@@ -29,14 +30,14 @@ typedef __nv_bfloat16 bf16;
 
 namespace fused {  // avd_fused.cu
 bool supported(const avd_net_dims& d, bool critic);
-int forward(const avd_net_dims& d, bool critic, int A, int64_t R, const float* params, int64_t pstride, const bf16* W2T, const float* s,
-            int64_t s_rs, int64_t s_cs, const float* act, bf16* H_out, float* Z_out, int head, const float* rew, float gamma, float high,
-            float* out, cudaStream_t st, bf16* DZ_out = nullptr, float* loss = nullptr);
+int forward(const avd_net_dims& d, bool critic, int A, int64_t R, const float* params, int64_t pstride, const bf16* W2T, const float* b2f,
+            const float* s, int64_t s_rs, int64_t s_cs, const float* act, bf16* H_out, uint32_t* mask_out, float* Z_out, int head,
+            const float* rew, float gamma, float high, float* out, cudaStream_t st, bf16* DZ_out = nullptr, float* loss = nullptr);
 }
 
 namespace umma {   // avd_umma.cu
 int gemm_bf16(int layout, int batch, int M, int N, int K, const void* A, int64_t lda, int64_t a_batch, const void* B, int64_t ldb,
-              int64_t b_batch, float* C, int64_t ldc, int64_t c_batch, int splitk, cudaStream_t st);
+              int64_t b_batch, float* C, int64_t ldc, int64_t c_batch, int splitk, cudaStream_t st, const ReluMaskEpilogue* rm = nullptr);
 }
 
 __device__ __forceinline__ void store_out(float* p, float v) { *p = v; }
@@ -223,7 +224,7 @@ __global__ void __launch_bounds__(128) l1_backward_kernel(avd_net_dims d, const 
 // One thread per row; the la (<= 64) per-column parameters are staged in shared memory.
 __global__ void __launch_bounds__(256) action_grad_kernel(avd_net_dims d, const float* __restrict__ params, int64_t pstride,
                                                           const float* __restrict__ act, int64_t R, const float* __restrict__ dHa,
-                                                          float* __restrict__ dact) {
+                                                          float* __restrict__ dact, int folded) {
     const CriticOff o = critic_off(d);
     const int agent = blockIdx.y;
     const float* P = params + (int64_t)agent * pstride;
@@ -231,7 +232,7 @@ __global__ void __launch_bounds__(256) action_grad_kernel(avd_net_dims d, const 
     for (int f = threadIdx.x; f < d.la; f += blockDim.x) {
         wa[f] = P[o.Wa + f];
         ba[f] = P[o.ba + f];
-        gi[f] = P[o.ga + f] / sqrtf(P[o.vara + f] + kBnEps);
+        gi[f] = folded ? 1.0f : P[o.ga + f] / sqrtf(P[o.vara + f] + kBnEps);   // folded: dHa already carries ga*inva (W2' = diag(sc1) W2)
     }
     __syncthreads();
     for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < R; r += (int64_t)gridDim.x * blockDim.x) {
@@ -262,6 +263,7 @@ struct HeadArgs {
     const float* params;   // [A][pstride]
     int64_t pstride;
     int64_t o_b2, o_g2, o_be2, o_mu2, o_var2, o_W3, o_b3;
+    const float* b2f;      // nullable [A][L2]: folded layer-2 bias that replaces params[o_b2] (BN-folded tensor-core path)
     const float* Z;        // [A*R][L2] raw GEMM output (bias not yet added)
     int64_t R;
     float high, gamma;
@@ -290,7 +292,7 @@ __global__ void __launch_bounds__(256) head_kernel(HeadArgs h) {
 #pragma unroll
     for (int j = 0; j < CPL; ++j) {
         const int c = lane + 32 * j;
-        b2[j] = P[h.o_b2 + c];
+        b2[j] = h.b2f ? h.b2f[(int64_t)agent * L2 + c] : P[h.o_b2 + c];
         inv[j] = 1.0f / sqrtf(P[h.o_var2 + c] + kBnEps);
         mu[j] = P[h.o_mu2 + c];
         ginv[j] = P[h.o_g2 + c] * inv[j];
@@ -543,18 +545,146 @@ __global__ void __launch_bounds__(256) pack_w2_kernel(const float* __restrict__ 
     }
 }
 
+// BN-folded packing for the fused tensor-core path.  With h1 = r1*sc1 + sh1 (r1 = relu(z1), inference BatchNorm):
+//   z2 = h1 W2 + b2 = r1 W2' + b2',   W2'[f][j] = sc1[f] W2[f][j],   b2'[j] = b2[j] + sum_f sh1[f] W2[f][j]
+// W2T [l2][F] is the forward B operand (K-major), W2b [F][l2] the dgrad B operand (nullable), b2f [l2] fp32.
+// One CTA per agent and 32-column slab of l2; thread (fy, j) walks features fy, fy+8, ...
+struct FoldOff {
+    int64_t W2, b2;
+    int64_t g[2], be[2], mu[2], var[2];   // BN of the state columns [0] and of the action columns [1]
+    int l1;                               // features < l1 use set 0
+};
+
+__global__ void __launch_bounds__(256) pack_fold_kernel(const float* __restrict__ params, int64_t pstride, FoldOff o, int F, int l2,
+                                                        bf16* __restrict__ W2b, bf16* __restrict__ W2T, float* __restrict__ b2f) {
+    // grid: (l2/32 column slabs, feature slabs of 8, agents); thread (fy, j) owns feature blockIdx.y*8 + fy, column j.
+    // b2f must be zero on entry: every CTA adds its partial sum, the first feature slab also adds b2.
+    const int agent = blockIdx.z;
+    const float* P = params + (int64_t)agent * pstride;
+    const int j = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int fy = threadIdx.x >> 5;
+    const int f = blockIdx.y * 8 + fy;
+    __shared__ float red[8][32];
+    float acc = 0.0f;
+    if (j < l2 && f < F) {
+        const bool st = f < o.l1;
+        const int c = st ? f : f - o.l1;
+        const float sc = P[(st ? o.g[0] : o.g[1]) + c] / sqrtf(P[(st ? o.var[0] : o.var[1]) + c] + kBnEps);
+        const float sh = P[(st ? o.be[0] : o.be[1]) + c] - P[(st ? o.mu[0] : o.mu[1]) + c] * sc;
+        const float w = P[o.W2 + (int64_t)f * l2 + j];
+        const bf16 v = __float2bfloat16_rn(sc * w);
+        if (W2b) W2b[((int64_t)agent * F + f) * l2 + j] = v;
+        W2T[((int64_t)agent * l2 + j) * F + f] = v;
+        acc = sh * w;
+    }
+    red[fy][threadIdx.x & 31] = acc;
+    __syncthreads();
+    if (fy == 0 && j < l2) {
+        float t = blockIdx.y == 0 ? P[o.b2 + j] : 0.0f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x];
+        atomicAdd(b2f + (int64_t)agent * l2 + j, t);
+    }
+}
+
+// xext[n] = [ s_hi(4) a_hi 1 0 0 | s_lo(4) a_lo 0 0 0 ] (bf16): B operand of the layer-1 weight-gradient GEMM
+//   G1[f][c] = sum_n dz1[n][f] xext[n][c]   =>  dW1[k][f] = G1[f][k] + G1[f][8+k],  dWa[f] = G1[l1+f][4] + G1[l1+f][12],  db[f] = G1[f][5]
+__global__ void __launch_bounds__(256) xext_kernel(const float* __restrict__ s, const float* __restrict__ a, int ns, int64_t N,
+                                                   bf16* __restrict__ xext) {
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    float v[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int k = 0; k < ns && k < 4; ++k) v[k] = s[n * ns + k];
+    v[4] = a[n];
+    bf16 hi[8], lo[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { hi[k] = __float2bfloat16_rn(0.0f); lo[k] = hi[k]; }
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        hi[k] = __float2bfloat16_rn(v[k]);
+        lo[k] = __float2bfloat16_rn(v[k] - __bfloat162float(hi[k]));
+    }
+    hi[5] = __float2bfloat16_rn(1.0f);
+    uint4 h4, l4;
+    h4.x = (uint32_t)__bfloat16_as_ushort(hi[0]) | ((uint32_t)__bfloat16_as_ushort(hi[1]) << 16);
+    h4.y = (uint32_t)__bfloat16_as_ushort(hi[2]) | ((uint32_t)__bfloat16_as_ushort(hi[3]) << 16);
+    h4.z = (uint32_t)__bfloat16_as_ushort(hi[4]) | ((uint32_t)__bfloat16_as_ushort(hi[5]) << 16);
+    h4.w = 0;
+    l4.x = (uint32_t)__bfloat16_as_ushort(lo[0]) | ((uint32_t)__bfloat16_as_ushort(lo[1]) << 16);
+    l4.y = (uint32_t)__bfloat16_as_ushort(lo[2]) | ((uint32_t)__bfloat16_as_ushort(lo[3]) << 16);
+    l4.z = (uint32_t)__bfloat16_as_ushort(lo[4]);
+    l4.w = 0;
+    uint4* dst = reinterpret_cast<uint4*>(xext + n * 16);
+    dst[0] = h4;
+    dst[1] = l4;
+}
+
+// Unfold the gradients of the BN-folded formulation into the Keras trainable tensors (one warp per layer-1 feature f).
+// In:  G[oW2 + f*l2 + j] = G2[f][j] = sum_n r1[n][f] dz2[n][j]   (wgrad GEMM),  G[ob2 + j] = db2[j]  (head-backward kernel),
+//      G1[f][16] (layer-1 weight-gradient GEMM, see xext_kernel).
+// Out: dW2[f][j] = sc1[f] G2[f][j] + sh1[f] db2[j];   dsh1[f] = sum_j W2[f][j] db2[j];   dsc1[f] = sum_j W2[f][j] G2[f][j];
+//      dbeta1 = dsh1;   dgamma1 = inv1 (dsc1 - mu1 dsh1);   dW1 / db1 from G1.          (trainer.py:498, 506; model.py:19-33, 62-77)
+struct UnfoldOff {
+    FoldOff f;
+    int64_t W1[2], b1[2];     // layer-1 kernel / bias of the state columns [0] ([ns][l1]) and of the action columns [1] ([la])
+};
+
+__global__ void __launch_bounds__(256) unfold_kernel(const float* __restrict__ params, int64_t pstride, float* __restrict__ grads, int64_t gstride,
+                                                     const float* __restrict__ G1, UnfoldOff o, int F, int Fp, int l2, int ns) {
+    const int agent = blockIdx.y;
+    const int f = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (f >= F) return;
+    const float* P = params + (int64_t)agent * pstride;
+    float* G = grads + (int64_t)agent * gstride;
+    const bool st = f < o.f.l1;
+    const int c = st ? f : f - o.f.l1;
+    const int64_t og = st ? o.f.g[0] : o.f.g[1], obe = st ? o.f.be[0] : o.f.be[1], ob1 = st ? o.b1[0] : o.b1[1];
+    const float inv = 1.0f / sqrtf(P[(st ? o.f.var[0] : o.f.var[1]) + c] + kBnEps);
+    const float sc = P[og + c] * inv;
+    const float mu = P[(st ? o.f.mu[0] : o.f.mu[1]) + c];
+    const float sh = P[obe + c] - mu * sc;
+    float dsc = 0.0f, dsh = 0.0f;
+    for (int j = lane; j < l2; j += 32) {
+        const int64_t i = o.f.W2 + (int64_t)f * l2 + j;
+        const float g2 = G[i], w = P[i], db2 = G[o.f.b2 + j];
+        dsc = fmaf(w, g2, dsc);
+        dsh = fmaf(w, db2, dsh);
+        G[i] = fmaf(sc, g2, sh * db2);
+    }
+    dsc = warp_sum(dsc);
+    dsh = warp_sum(dsh);
+    if (lane == 0) {
+        G[obe + c] = dsh;
+        G[og + c] = inv * (dsc - mu * dsh);
+        const float* g1 = G1 + ((int64_t)agent * Fp + f) * 16;
+        G[ob1 + c] = g1[5];
+        if (st) {
+            for (int x = 0; x < ns && x < 4; ++x) G[o.W1[0] + (int64_t)x * o.f.l1 + c] = g1[x] + g1[8 + x];
+        } else {
+            G[o.W1[1] + c] = g1[4] + g1[12];
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // host orchestration
 // ------------------------------------------------------------------------------------------------
 struct Workspace {
     float *H, *H1a, *Z, *Za, *DZ, *DH, *a2, *y, *q, *dpi;
     bf16 *cW2b, *cW2T, *tcW2T, *aW2b, *aW2T, *taW2T;   // packed weights (precision 1)
+    // BN-folded tensor-core path: sign masks of z1, [x_hi | 1 | x_lo] operand, layer-1 weight-gradient accumulator, folded biases
+    uint32_t* mask;
+    bf16* xext;
+    float *G1, *c_b2f, *tc_b2f, *a_b2f, *ta_b2f;
+    static constexpr int kMaskWords = 10, kFp = 320;
     static int64_t bytes(const avd_net_dims& d, int64_t A, int64_t N) {
         const int64_t F = d.l1 + d.la;
         const int64_t acts = N * (2 * F + d.l1 + 3 * (int64_t)d.l2) * (int64_t)sizeof(float);
         const int64_t packed = A * (3 * F + 3 * (int64_t)d.l1) * d.l2 * (int64_t)sizeof(bf16);
         const int64_t vecs = 4 * ((N + 3) / 4 * 4) * (int64_t)sizeof(float);
-        return acts + packed + vecs + 512;
+        const int64_t fold = N * (kMaskWords * 4 + 16 * 2) + A * (kFp * 16 + 4 * (int64_t)d.l2) * (int64_t)sizeof(float);
+        return acts + packed + vecs + fold + 1024;
     }
     void carve(void* base_, const avd_net_dims& d, int64_t A, int64_t N) {
         const int64_t F = d.l1 + d.la;
@@ -578,6 +708,13 @@ struct Workspace {
         y = p; p += Np;
         q = p; p += Np;
         dpi = p; p += Np;
+        G1 = p; p += A * kFp * 16;
+        c_b2f = p; p += A * d.l2;
+        tc_b2f = p; p += A * d.l2;
+        a_b2f = p; p += A * d.l2;
+        ta_b2f = p; p += A * d.l2;
+        mask = reinterpret_cast<uint32_t*>(p); p += N * kMaskWords;
+        xext = reinterpret_cast<bf16*>(((uintptr_t)p + 15) & ~(uintptr_t)15);
     }
 };
 
@@ -667,6 +804,59 @@ struct Pass {
         return AVD_OK;
     }
 
+    // BN-folded packing (fused tensor-core path)
+    int pack_fold(bool critic, const float* params, bf16* W2b, bf16* W2T, float* b2f) const {
+        const FoldOff o = fold_off(critic);
+        const int F = critic ? d.l1 + d.la : d.l1;
+        const int64_t ps = critic ? critic_off(d).total : actor_off(d).total;
+        AVD_CUDA_OK(cudaMemsetAsync(b2f, 0, (size_t)A * d.l2 * sizeof(float), st));
+        pack_fold_kernel<<<dim3((unsigned)((d.l2 + 31) / 32), (unsigned)((F + 7) / 8), A), 256, 0, st>>>(params, ps, o, F, d.l2, W2b, W2T, b2f);
+        AVD_LAUNCH_OK();
+        return AVD_OK;
+    }
+
+    FoldOff fold_off(bool critic) const {
+        FoldOff o;
+        if (critic) {
+            const CriticOff c = critic_off(d);
+            o.W2 = c.W2; o.b2 = c.b2; o.l1 = d.l1;
+            o.g[0] = c.gs; o.be[0] = c.bes; o.mu[0] = c.mus; o.var[0] = c.vars;
+            o.g[1] = c.ga; o.be[1] = c.bea; o.mu[1] = c.mua; o.var[1] = c.vara;
+        } else {
+            const ActorOff a = actor_off(d);
+            o.W2 = a.W2; o.b2 = a.b2; o.l1 = d.l1;
+            for (int k = 0; k < 2; ++k) { o.g[k] = a.g1; o.be[k] = a.be1; o.mu[k] = a.mu1; o.var[k] = a.var1; }
+        }
+        return o;
+    }
+
+    // dz1[a] (R x Fp, bf16, zero pad) = relu'(z1) . (DZ[a] (R x l2) . W2'[a]^T): dgrad GEMM with the sign-mask epilogue
+    int dgrad_masked(const void* DZ, const bf16* W2b, int F, const uint32_t* mask, int mask_words, bf16* dz1, int Fp) const {
+        umma::ReluMaskEpilogue rm{mask, mask_words, dz1, Fp};
+        return umma::gemm_bf16(0, A, (int)R, F, d.l2, DZ, d.l2, R * d.l2, W2b, d.l2, (int64_t)F * d.l2, nullptr, 0, 0, 1, st, &rm);
+    }
+
+    // G1[a] (Fp x 16) += dz1[a]^T (F x R) . xext[a] (R x 16); then unfold everything into the Keras gradient tensors
+    int l1_wgrad_unfold(bool critic, const float* params, const bf16* dz1, int F, int Fp, const bf16* xext, float* G1, float* grads) const {
+        AVD_CUDA_OK(cudaMemsetAsync(G1, 0, (size_t)A * Fp * 16 * sizeof(float), st));
+        const int tiles = ((F + 127) / 128) * A;
+        int split = (int)std::min<int64_t>((R + 63) / 64, std::max(1, 4 * sm_count() / std::max(1, tiles)));
+        if (int rc = umma::gemm_bf16(1, A, F, 16, (int)R, dz1, Fp, R * Fp, xext, 16, R * 16, G1, 16, (int64_t)Fp * 16, std::max(1, split), st)) return rc;
+        UnfoldOff u;
+        u.f = fold_off(critic);
+        int64_t ps, gs;
+        if (critic) {
+            const CriticOff c = critic_off(d);
+            u.W1[0] = c.Ws; u.b1[0] = c.bs; u.W1[1] = c.Wa; u.b1[1] = c.ba; ps = c.total; gs = c.n_train;
+        } else {
+            const ActorOff a = actor_off(d);
+            u.W1[0] = u.W1[1] = a.W1; u.b1[0] = u.b1[1] = a.b1; ps = a.total; gs = a.n_train;
+        }
+        unfold_kernel<<<dim3((unsigned)((F + 7) / 8), A), 256, 0, st>>>(params, ps, grads, gs, G1, u, F, Fp, d.l2, d.ns);
+        AVD_LAUNCH_OK();
+        return AVD_OK;
+    }
+
     // Z[a] (R x l2) = H[a] (R x F) . W2[a] (F x l2)
     int forward(const void* H, int F, const float* params, int64_t pstride, int64_t oW2, const bf16* W2T, float* Z) const {
         if (prec)
@@ -749,10 +939,12 @@ extern "C" int avd_actor_forward(const avd_net_dims* dims, int32_t A, int64_t R,
     float* H = reinterpret_cast<float*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
     float* Z = H + N * d.l1;
     bf16* W2T = reinterpret_cast<bf16*>(Z + N * d.l2);
+    if (precision && fused::supported(d, false)) {   // fused kernel: H / Z are never materialised, their space holds the folded bias
+        AVD_TRY(p.pack_fold(false, actor_params, nullptr, W2T, H));
+        return fused::forward(d, false, A, R, actor_params, o.total, W2T, H, s, s_rs, s_cs, nullptr, nullptr, nullptr, nullptr, 1, nullptr, 0.f,
+                              action_high, out, p.st);
+    }
     if (precision) AVD_TRY(p.pack(actor_params, o.total, o.W2, d.l1, nullptr, W2T));
-    if (precision && fused::supported(d, false))
-        return fused::forward(d, false, A, R, actor_params, o.total, W2T, s, s_rs, s_cs, nullptr, nullptr, nullptr, 1, nullptr, 0.f, action_high, out,
-                              p.st);
     AVD_TRY(p.layer1(false, actor_params, s, s_rs, s_cs, nullptr, H));
     AVD_TRY(p.forward(H, d.l1, actor_params, o.total, o.W2, W2T, Z));
     HeadArgs h = actor_head(d, actor_params, Z, R, action_high);
@@ -777,9 +969,11 @@ extern "C" int avd_critic_forward(const avd_net_dims* dims, int32_t A, int64_t R
     float* H = reinterpret_cast<float*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
     float* Z = H + N * F;
     bf16* W2T = reinterpret_cast<bf16*>(Z + N * d.l2);
+    if (precision && fused::supported(d, true)) {
+        AVD_TRY(p.pack_fold(true, critic_params, nullptr, W2T, H));
+        return fused::forward(d, true, A, R, critic_params, o.total, W2T, H, s, d.ns, 1, a, nullptr, nullptr, nullptr, 3, nullptr, 0.f, 0.f, q, p.st);
+    }
     if (precision) AVD_TRY(p.pack(critic_params, o.total, o.W2, F, nullptr, W2T));
-    if (precision && fused::supported(d, true))
-        return fused::forward(d, true, A, R, critic_params, o.total, W2T, s, d.ns, 1, a, nullptr, nullptr, 3, nullptr, 0.f, 0.f, q, p.st);
     AVD_TRY(p.layer1(true, critic_params, s, d.ns, 1, a, H));
     AVD_TRY(p.forward(H, F, critic_params, o.total, o.W2, W2T, Z));
     HeadArgs h = critic_head(d, critic_params, Z, R);
@@ -847,6 +1041,81 @@ extern "C" int avd_fed_broadcast(float* out, int64_t out_pitch, const float* in,
     return AVD_OK;
 }
 
+// Adam on both nets, then Polyak of the targets                                       trainer.py:345-356
+static int apply_local_updates(const avd_learn_io* io, void* stream) {
+    if (!io->apply_updates) return AVD_OK;
+    const ActorOff ao = actor_off(io->dims);
+    const CriticOff co = critic_off(io->dims);
+    const int A = io->A;
+    AVD_TRY(avd_adam_apply(io->critic, co.total, io->critic_grad, co.n_train, io->critic_m, io->critic_v, io->critic_t, io->apply_mask,
+                           A, co.n_train, io->critic_lr, io->adam_beta1, io->adam_beta2, io->adam_eps, stream));
+    AVD_TRY(avd_adam_apply(io->actor, ao.total, io->actor_grad, ao.n_train, io->actor_m, io->actor_v, io->actor_t, io->apply_mask, A,
+                           ao.n_train, io->actor_lr, io->adam_beta1, io->adam_beta2, io->adam_eps, stream));
+    AVD_TRY(avd_polyak_update(io->t_critic, io->critic, io->apply_mask, A, co.total, io->tau, stream));
+    AVD_TRY(avd_polyak_update(io->t_actor, io->actor, io->apply_mask, A, ao.total, io->tau, stream));
+    return AVD_OK;
+}
+
+// The learn step on the fused tensor-core kernels (precision 1, 256/48/128 layers).  BatchNorm of layer 1 is folded into
+// layer 2 (pack_fold_kernel), so the stored activation is r1 = relu(z1) and the layer-1 backward needs only its sign mask:
+//   forward (+mask, r1, z2) -> head-backward -> wgrad G2 = r1^T dz2 -> dgrad with ReLU-mask epilogue (dz1, bf16)
+//   -> G1 = dz1^T [x_hi | 1 | x_lo] -> unfold_kernel (dW2, dgamma1, dbeta1, dW1, db1)
+static int learn_fused(const avd_learn_io* io, const Pass& p, const Workspace& w, cudaStream_t st) {
+    const avd_net_dims d = io->dims;
+    const int A = io->A;
+    const int64_t R = io->rows_per_agent, N = (int64_t)A * R;
+    const ActorOff ao = actor_off(d);
+    const CriticOff co = critic_off(d);
+    const int F = d.l1 + d.la;
+    constexpr int Fp = Workspace::kFp, MW = Workspace::kMaskWords;
+    bf16* Hc = reinterpret_cast<bf16*>(w.H);        // r1 of the critic   [N][F]
+    bf16* Ha = reinterpret_cast<bf16*>(w.H1a);      // r1 of the actor    [N][l1]
+    bf16* dz1 = reinterpret_cast<bf16*>(w.DH);      // [N][Fp] (critic) / [N][l1] (actor); shares DH with the action-column dgrad
+    AVD_TRY(p.pack_fold(false, io->t_actor, nullptr, w.taW2T, w.ta_b2f));
+    AVD_TRY(p.pack_fold(true, io->t_critic, nullptr, w.tcW2T, w.tc_b2f));
+    AVD_TRY(p.pack_fold(true, io->critic, w.cW2b, w.cW2T, w.c_b2f));
+    AVD_TRY(p.pack_fold(false, io->actor, w.aW2b, w.aW2T, w.a_b2f));
+    xext_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(io->s, io->a, d.ns, N, w.xext);
+    AVD_LAUNCH_OK();
+    // ---- TD target: y = r + gamma * target_critic(s', target_actor(s'))            trainer.py:493-494
+    AVD_TRY(fused::forward(d, false, A, R, io->t_actor, ao.total, w.taW2T, w.ta_b2f, io->s2, d.ns, 1, nullptr, nullptr, nullptr, nullptr, 1, nullptr,
+                           0.f, io->action_high, w.a2, st));
+    AVD_TRY(fused::forward(d, true, A, R, io->t_critic, co.total, w.tcW2T, w.tc_b2f, io->s2, d.ns, 1, w.a2, nullptr, nullptr, nullptr, 2, io->r,
+                           io->gamma, 0.f, w.y, st));
+    // ---- critic loss gradient on (s, a)                                             trainer.py:495-498
+    AVD_TRY(fused::forward(d, true, A, R, io->critic, co.total, w.cW2T, w.c_b2f, io->s, d.ns, 1, io->a, Hc, w.mask, w.Z, 0, nullptr, 0.f, 0.f, nullptr,
+                           st));
+    {
+        HeadArgs h = critic_head(d, io->critic, w.Z, R);
+        h.b2f = w.c_b2f;
+        h.y = w.y; h.out = w.q; h.DZ = w.DZ; h.grads = io->critic_grad; h.gstride = co.n_train; h.loss = io->loss;
+        AVD_TRY(launch_head<HEAD_CRITIC_BWD>(h, d.l2, A, st, true));
+    }
+    AVD_TRY(p.wgrad(Hc, F, w.DZ, io->critic_grad, co.n_train, co.W2));
+    AVD_TRY(p.dgrad_masked(w.DZ, w.cW2b, F, w.mask, MW, dz1, Fp));
+    AVD_TRY(p.l1_wgrad_unfold(true, io->critic, dz1, F, Fp, w.xext, w.G1, io->critic_grad));
+    // ---- actor loss gradient: -mean(critic(s, actor(s)))                            trainer.py:501-506
+    AVD_TRY(fused::forward(d, false, A, R, io->actor, ao.total, w.aW2T, w.a_b2f, io->s, d.ns, 1, nullptr, Ha, w.mask, w.Za, 1, nullptr, 0.f,
+                           io->action_high, w.a2, st));   // pi
+    // critic(s, pi) with the action-only head-backward fused into the TMEM epilogue: emits dz2 (bf16) directly
+    AVD_TRY(fused::forward(d, true, A, R, io->critic, co.total, w.cW2T, w.c_b2f, io->s, d.ns, 1, w.a2, nullptr, nullptr, nullptr, 4, nullptr, 0.f, 0.f,
+                           nullptr, st, (bf16*)w.DZ, io->loss));
+    AVD_TRY(umma::gemm_bf16(0, A, (int)R, d.la, d.l2, w.DZ, d.l2, R * d.l2, w.cW2b + (int64_t)d.l1 * d.l2, d.l2, (int64_t)F * d.l2, w.DH, d.la,
+                            R * d.la, 1, st));   // action columns of dR only
+    action_grad_kernel<<<dim3((unsigned)std::min<int64_t>((R + 255) / 256, 2048), A), 256, 0, st>>>(d, io->critic, co.total, w.a2, R, w.DH, w.dpi, 1);
+    AVD_LAUNCH_OK();
+    {
+        HeadArgs h = actor_head(d, io->actor, w.Za, R, io->action_high);
+        h.b2f = w.a_b2f;
+        h.dpi = w.dpi; h.DZ = w.DZ; h.grads = io->actor_grad; h.gstride = ao.n_train;
+        AVD_TRY(launch_head<HEAD_ACTOR_BWD>(h, d.l2, A, st, true));
+    }
+    AVD_TRY(p.wgrad(Ha, d.l1, w.DZ, io->actor_grad, ao.n_train, ao.W2));
+    AVD_TRY(p.dgrad_masked(w.DZ, w.aW2b, d.l1, w.mask, 8, dz1, d.l1));
+    AVD_TRY(p.l1_wgrad_unfold(false, io->actor, dz1, d.l1, d.l1, w.xext, w.G1, io->actor_grad));
+    return apply_local_updates(io, (void*)st);
+}
+
 extern "C" int avd_ddpg_learn(const avd_learn_io* io, void* stream) {
     AVD_REQUIRE(io, "null io");
     AVD_TRY(check_dims(&io->dims, io->precision));
@@ -873,43 +1142,32 @@ extern "C" int avd_ddpg_learn(const avd_learn_io* io, void* stream) {
     AVD_CUDA_OK(cudaMemsetAsync(io->actor_grad, 0, (size_t)A * ao.n_train * sizeof(float), st));
     AVD_CUDA_OK(cudaMemsetAsync(io->critic_grad, 0, (size_t)A * co.n_train * sizeof(float), st));
     if (io->loss) AVD_CUDA_OK(cudaMemsetAsync(io->loss, 0, (size_t)A * 2 * sizeof(float), st));
+    const bool fz = tc && fused::supported(d, false) && fused::supported(d, true);   // fused layer1 -> tcgen05 -> head kernels
+    if (fz) return learn_fused(io, p, w, st);
     if (tc) {   // bf16 copies of the four layer-2 kernels (K-major for forward, and for dgrad on the online nets)
         AVD_TRY(p.pack(io->t_actor, ao.total, ao.W2, d.l1, nullptr, w.taW2T));
         AVD_TRY(p.pack(io->t_critic, co.total, co.W2, F, nullptr, w.tcW2T));
         AVD_TRY(p.pack(io->critic, co.total, co.W2, F, w.cW2b, w.cW2T));
         AVD_TRY(p.pack(io->actor, ao.total, ao.W2, d.l1, w.aW2b, w.aW2T));
     }
-
-    const bool fz = tc && fused::supported(d, false) && fused::supported(d, true);   // fused layer1 -> tcgen05 -> head kernels
     // ---- TD target: y = r + gamma * target_critic(s', target_actor(s'))            trainer.py:493-494
-    if (fz) {
-        AVD_TRY(fused::forward(d, false, A, R, io->t_actor, ao.total, w.taW2T, io->s2, d.ns, 1, nullptr, nullptr, nullptr, 1, nullptr, 0.f,
-                               io->action_high, w.a2, st));
-        AVD_TRY(fused::forward(d, true, A, R, io->t_critic, co.total, w.tcW2T, io->s2, d.ns, 1, w.a2, nullptr, nullptr, 2, io->r, io->gamma, 0.f,
-                               w.y, st));
-    } else {
-        AVD_TRY(p.layer1(false, io->t_actor, io->s2, d.ns, 1, nullptr, w.H1a));
-        AVD_TRY(p.forward(w.H1a, d.l1, io->t_actor, ao.total, ao.W2, w.taW2T, w.Z));
-        {
-            HeadArgs h = actor_head(d, io->t_actor, w.Z, R, io->action_high);
-            h.out = w.a2;
-            AVD_TRY(launch_head<HEAD_ACTOR_FWD>(h, d.l2, A, st));
-        }
-        AVD_TRY(p.layer1(true, io->t_critic, io->s2, d.ns, 1, w.a2, w.H));
-        AVD_TRY(p.forward(w.H, F, io->t_critic, co.total, co.W2, w.tcW2T, w.Z));
-        {
-            HeadArgs h = critic_head(d, io->t_critic, w.Z, R);
-            h.rew = io->r; h.gamma = io->gamma; h.out = w.y;
-            AVD_TRY(launch_head<HEAD_CRITIC_TARGET>(h, d.l2, A, st));
-        }
+    AVD_TRY(p.layer1(false, io->t_actor, io->s2, d.ns, 1, nullptr, w.H1a));
+    AVD_TRY(p.forward(w.H1a, d.l1, io->t_actor, ao.total, ao.W2, w.taW2T, w.Z));
+    {
+        HeadArgs h = actor_head(d, io->t_actor, w.Z, R, io->action_high);
+        h.out = w.a2;
+        AVD_TRY(launch_head<HEAD_ACTOR_FWD>(h, d.l2, A, st));
+    }
+    AVD_TRY(p.layer1(true, io->t_critic, io->s2, d.ns, 1, w.a2, w.H));
+    AVD_TRY(p.forward(w.H, F, io->t_critic, co.total, co.W2, w.tcW2T, w.Z));
+    {
+        HeadArgs h = critic_head(d, io->t_critic, w.Z, R);
+        h.rew = io->r; h.gamma = io->gamma; h.out = w.y;
+        AVD_TRY(launch_head<HEAD_CRITIC_TARGET>(h, d.l2, A, st));
     }
     // ---- critic loss gradient on (s, a)                                             trainer.py:495-498
-    if (fz) {
-        AVD_TRY(fused::forward(d, true, A, R, io->critic, co.total, w.cW2T, io->s, d.ns, 1, io->a, (bf16*)w.H, w.Z, 0, nullptr, 0.f, 0.f, nullptr, st));
-    } else {
-        AVD_TRY(p.layer1(true, io->critic, io->s, d.ns, 1, io->a, w.H));
-        AVD_TRY(p.forward(w.H, F, io->critic, co.total, co.W2, w.cW2T, w.Z));
-    }
+    AVD_TRY(p.layer1(true, io->critic, io->s, d.ns, 1, io->a, w.H));
+    AVD_TRY(p.forward(w.H, F, io->critic, co.total, co.W2, w.cW2T, w.Z));
     {
         HeadArgs h = critic_head(d, io->critic, w.Z, R);
         h.y = w.y; h.out = w.q; h.DZ = w.DZ; h.grads = io->critic_grad; h.gstride = co.n_train; h.loss = io->loss;
@@ -920,28 +1178,22 @@ extern "C" int avd_ddpg_learn(const avd_learn_io* io, void* stream) {
     l1_backward_kernel<true><<<gl1b, 128, 0, st>>>(d, io->critic, co.total, io->s, io->a, R, w.DH, io->critic_grad, co.n_train);
     AVD_LAUNCH_OK();
     // ---- actor loss gradient: -mean(critic(s, actor(s)))                            trainer.py:501-506
-    if (fz) {
-        AVD_TRY(fused::forward(d, false, A, R, io->actor, ao.total, w.aW2T, io->s, d.ns, 1, nullptr, (bf16*)w.H1a, w.Za, 1, nullptr, 0.f,
-                               io->action_high, w.a2, st));   // pi
-        // critic(s, pi) with the action-only head-backward fused into the TMEM epilogue: emits dz2 (bf16) directly
-        AVD_TRY(fused::forward(d, true, A, R, io->critic, co.total, w.cW2T, io->s, d.ns, 1, w.a2, nullptr, nullptr, 4, nullptr, 0.f, 0.f, nullptr, st,
-                               (bf16*)w.DZ, io->loss));
-    } else {
-        AVD_TRY(p.layer1(false, io->actor, io->s, d.ns, 1, nullptr, w.H1a));
-        AVD_TRY(p.forward(w.H1a, d.l1, io->actor, ao.total, ao.W2, w.aW2T, w.Za));
-        {
-            HeadArgs h = actor_head(d, io->actor, w.Za, R, io->action_high);
-            h.out = w.a2;   // pi
-            AVD_TRY(launch_head<HEAD_ACTOR_FWD>(h, d.l2, A, st));
-        }
-        AVD_TRY(p.layer1(true, io->critic, io->s, d.ns, 1, w.a2, w.H));
-        AVD_TRY(p.forward(w.H, F, io->critic, co.total, co.W2, w.cW2T, w.Z));
+    AVD_TRY(p.layer1(false, io->actor, io->s, d.ns, 1, nullptr, w.H1a));
+    AVD_TRY(p.forward(w.H1a, d.l1, io->actor, ao.total, ao.W2, w.aW2T, w.Za));
+    {
+        HeadArgs h = actor_head(d, io->actor, w.Za, R, io->action_high);
+        h.out = w.a2;   // pi
+        AVD_TRY(launch_head<HEAD_ACTOR_FWD>(h, d.l2, A, st));
+    }
+    AVD_TRY(p.layer1(true, io->critic, io->s, d.ns, 1, w.a2, w.H));
+    AVD_TRY(p.forward(w.H, F, io->critic, co.total, co.W2, w.cW2T, w.Z));
+    {
         HeadArgs h = critic_head(d, io->critic, w.Z, R);
         h.DZ = w.DZ; h.loss = io->loss;
         AVD_TRY(launch_head<HEAD_CRITIC_BWD_ACTION>(h, d.l2, A, st, tc));
     }
     AVD_TRY(p.dgrad(w.DZ, io->critic, co.total, co.W2, w.cW2b, F, d.l1, d.la, w.DH));   // action columns only
-    action_grad_kernel<<<dim3((unsigned)std::min<int64_t>((R + 255) / 256, 2048), A), 256, 0, st>>>(d, io->critic, co.total, w.a2, R, w.DH, w.dpi);
+    action_grad_kernel<<<dim3((unsigned)std::min<int64_t>((R + 255) / 256, 2048), A), 256, 0, st>>>(d, io->critic, co.total, w.a2, R, w.DH, w.dpi, 0);
     AVD_LAUNCH_OK();
     {
         HeadArgs h = actor_head(d, io->actor, w.Za, R, io->action_high);
@@ -952,14 +1204,6 @@ extern "C" int avd_ddpg_learn(const avd_learn_io* io, void* stream) {
     AVD_TRY(p.dgrad(w.DZ, io->actor, ao.total, ao.W2, w.aW2b, d.l1, 0, d.l1, w.DH));
     l1_backward_kernel<false><<<gl1b, 128, 0, st>>>(d, io->actor, ao.total, io->s, nullptr, R, w.DH, io->actor_grad, ao.n_train);
     AVD_LAUNCH_OK();
-    // ---- local update: Adam on both nets, then Polyak of the targets                trainer.py:345-356
-    if (io->apply_updates) {
-        AVD_TRY(avd_adam_apply(io->critic, co.total, io->critic_grad, co.n_train, io->critic_m, io->critic_v, io->critic_t, io->apply_mask,
-                               A, co.n_train, io->critic_lr, io->adam_beta1, io->adam_beta2, io->adam_eps, stream));
-        AVD_TRY(avd_adam_apply(io->actor, ao.total, io->actor_grad, ao.n_train, io->actor_m, io->actor_v, io->actor_t, io->apply_mask, A,
-                               ao.n_train, io->actor_lr, io->adam_beta1, io->adam_beta2, io->adam_eps, stream));
-        AVD_TRY(avd_polyak_update(io->t_critic, io->critic, io->apply_mask, A, co.total, io->tau, stream));
-        AVD_TRY(avd_polyak_update(io->t_actor, io->actor, io->apply_mask, A, ao.total, io->tau, stream));
-    }
-    return AVD_OK;
+    return apply_local_updates(io, stream);
 }
+

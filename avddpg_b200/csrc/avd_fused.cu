@@ -1,16 +1,13 @@
 // avd_fused.cu -- fused two-layer forward of the actor / critic on sm_100a:
 //
-//   x[n] (4 state words [+ action])  --CUDA cores-->  h1 = BN(relu(x W1 + b1))  (bf16, written straight into the
-//   128-byte-swizzled K-major A tile in shared memory, never to HBM unless the caller wants it for wgrad)
-//   --tcgen05.mma, W2^T resident in shared memory (TMA), fp32 accumulators in TMEM-->  z2
-//   --epilogue from TMEM (one thread per row)-->  BN(relu(z2 + b2)) . W3 + b3  -> tanh*high | r + gamma*q | q
+//   x[n] (4 state words [+ action])  --tcgen05.mma (hi/lo split bf16, K = 16)-->  z1 in TMEM
+//   --converter warps-->  r1 = relu(z1) as bf16, written straight into the 128-byte-swizzled K-major A tile in shared
+//   memory (never to HBM unless the caller wants it for wgrad) plus one sign bit per element for the ReLU backward
+//   --tcgen05.mma, W2'^T resident in shared memory (TMA), fp32 accumulators in TMEM-->  z2
+//   --epilogue from TMEM (one thread per row)-->  BN(relu(z2 + b2')) . W3 + b3  -> tanh*high | r + gamma*q | q
 //
-// One persistent CTA per SM walks a contiguous range of 128-row tiles.  Roles (13 warps):
-//   warp 0      : TMEM allocation; one elected thread loads W2^T when the agent changes (TMA) and issues all MMAs
-//   warps 1..4  : epilogue, TMEM lane quadrant = warp % 4; double-buffered accumulator (2 x 128 columns)
-//   warps 5..12 : producers; 256 threads fill one 128 x 64 k-block (16 KB) at a time into a 7-slot ring, so the MMA
-//                 of k-block j overlaps the production of k-block j+1 and tiles overlap each other
-// This replaces, per pass, l1_forward + gemm + head (three kernels and two HBM round trips of the activations).
+// The layer-1 BatchNormalization (inference affine h1 = r1*sc1 + sh1) is FOLDED into layer 2 by the pack
+// kernel:  W2' = diag(sc1) W2,  b2' = b2 + sh1 W2,  so the converters only clamp and the stored activation is r1.
 // Reference semantics: agent/model.py:19-37 (actor), 55-83 (critic); workers/trainer.py:493-495, 502-503, 287.
 #include <cudaTypedefs.h>
 #include <stdlib.h>
@@ -28,19 +25,10 @@ using namespace umma;
 typedef __nv_bfloat16 bf16;
 
 constexpr int TILE_M = 128, L2N = 128, KB = 64;
-constexpr int NSLOT = 7;                       // ring of 16 KB k-block slots for A
 constexpr int MAX_KB = 5;                      // up to 320 input features for layer 2
 constexpr int PTAB_COLS = MAX_KB * KB;         // 320
-constexpr int NUM_PRODUCERS = 256, NUM_THREADS = 32 + 128 + NUM_PRODUCERS;
 constexpr int SLOT_BYTES = TILE_M * KB * 2;    // 16 KB
 constexpr int W_BYTES = MAX_KB * L2N * KB * 2; // 80 KB
-constexpr int OFF_W = NSLOT * SLOT_BYTES;                       // 128 KB
-constexpr int OFF_PTAB = OFF_W + W_BYTES;                       // + 80 KB
-constexpr int OFF_ETAB = OFF_PTAB + 8 * PTAB_COLS * 4;          // + 10 KB
-constexpr int OFF_SCRATCH = OFF_ETAB + (4 * L2N + 4) * 4;       // + 2 KB
-constexpr int OFF_BAR = OFF_SCRATCH + 4 * 32 * 33 * 4;          // + 16.5 KB (Z-store transpose scratch, one per epilogue warp)
-constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
-static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB shared memory of an sm_100 CTA");
 
 enum HeadMode { HEAD_NONE = 0, HEAD_ACTOR = 1, HEAD_TARGET = 2, HEAD_Q = 3, HEAD_BWD_ACTION = 4 };
 
@@ -51,10 +39,13 @@ struct Args {
     int64_t R;
     const float* params;        // [A][pstride]
     int64_t pstride;
+    const float* b2f;           // [A][128] folded layer-2 bias  b2 + sh1 W2  (pack_fold_kernel)
     const float* s;             // element (n, k) at s[n*s_rs + k*s_cs]
     int64_t s_rs, s_cs;
     const float* act;           // [A*R] (critic)
-    bf16* H_out;                // nullable: [A*R][F] bf16 layer-1 activations (operand of the wgrad GEMM)
+    bf16* H_out;                // nullable: [A*R][F] bf16 r1 = relu(z1) (operand of the wgrad GEMM)
+    uint32_t* mask_out;         // nullable: [A*R][mask_words] sign bits of z1 (column j of word w at bit 31-j, 1 = negative)
+    int mask_words;
     float* Z_out;               // nullable: [A*R][128] raw layer-2 product (input of the head-backward kernels)
     int head;                   // HeadMode
     const float* rew;
@@ -72,7 +63,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
 
 // ---------------------------------------------------------------------------------------------------------
 // Epilogue role (4 warps, TMEM lane quadrant = warp % 4): bias + ReLU + BN + W3 head on the fp32 accumulator of the
-// layer-2 MMA, one output row per thread; optional coalesced z2 / dz2 stores.  Shared by both kernel generations.
+// layer-2 MMA, one output row per thread; optional coalesced z2 / dz2 stores.
 // ---------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void epilogue_role(const Args& g, uint8_t* smem, float* etab, float* scratch_base, uint64_t* acc_full,
                                               uint64_t* acc_empty, uint32_t tmem_base, int warp, int lane, int tile_begin, int tile_end) {
@@ -86,14 +77,14 @@ __device__ __forceinline__ void epilogue_role(const Args& g, uint8_t* smem, floa
             if (agent != cur_agent) {        // per-agent head parameters -> shared (broadcast reads below)
                 asm volatile("bar.sync 2, 128;" ::: "memory");
                 const float* P = g.params + (int64_t)agent * g.pstride;
-                int64_t ob2, og2, obe2, omu2, ovar2, oW3, ob3;
-                if (g.critic) { const CriticOff o = critic_off(d); ob2 = o.b2; og2 = o.g2; obe2 = o.be2; omu2 = o.mu2; ovar2 = o.var2; oW3 = o.W3; ob3 = o.b3; }
-                else { const ActorOff o = actor_off(d); ob2 = o.b2; og2 = o.g2; obe2 = o.be2; omu2 = o.mu2; ovar2 = o.var2; oW3 = o.W3; ob3 = o.b3; }
+                int64_t og2, obe2, omu2, ovar2, oW3, ob3;
+                if (g.critic) { const CriticOff o = critic_off(d); og2 = o.g2; obe2 = o.be2; omu2 = o.mu2; ovar2 = o.var2; oW3 = o.W3; ob3 = o.b3; }
+                else { const ActorOff o = actor_off(d); og2 = o.g2; obe2 = o.be2; omu2 = o.mu2; ovar2 = o.var2; oW3 = o.W3; ob3 = o.b3; }
                 {
                     const int c = et;
                     const float inv = 1.0f / sqrtf(P[ovar2 + c] + kBnEps);
                     const float sc = P[og2 + c] * inv;
-                    etab[c] = P[ob2 + c];
+                    etab[c] = g.b2f[(int64_t)agent * L2N + c];
                     etab[L2N + c] = sc;
                     etab[2 * L2N + c] = P[obe2 + c] - P[omu2 + c] * sc;
                     etab[3 * L2N + c] = P[oW3 + c];
@@ -165,207 +156,17 @@ __device__ __forceinline__ void epilogue_role(const Args& g, uint8_t* smem, floa
         }
 }
 
-__global__ void __launch_bounds__(NUM_THREADS, 1) fused_forward_kernel(const __grid_constant__ CUtensorMap tmW, Args g) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    float* ptab = reinterpret_cast<float*>(smem + OFF_PTAB);      // [8][320]: w0..w4, bias, scale, shift
-    float* etab = reinterpret_cast<float*>(smem + OFF_ETAB);      // [4][128]: b2, scale2, shift2, w3 ; then b3
-    uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
-    uint64_t* a_empty = a_full + NSLOT;
-    uint64_t* acc_full = a_empty + NSLOT;
-    uint64_t* acc_empty = acc_full + 2;
-    uint64_t* w_full = acc_empty + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const avd_net_dims d = g.d;
-    const int F = g.critic ? d.l1 + d.la : d.l1;
-    const int nkb = (F + KB - 1) / KB;
-    const int tile_begin = blockIdx.x * g.tiles_per_cta;
-    const int tile_end = min(g.total_tiles, tile_begin + g.tiles_per_cta);
-
-    if (threadIdx.x == 0) {
-        tma_prefetch_desc(&tmW);
-        for (int i = 0; i < NSLOT; ++i) { mbar_init(&a_full[i], NUM_PRODUCERS / 32); mbar_init(&a_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
-        mbar_init(w_full, 1);
-        fence_barrier_init();
-    }
-    if (warp == 0) tmem_alloc(tmem_slot, 2 * L2N);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == 0) {
-        // ===================================== MMA issuer + weight loader =====================================
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16(TILE_M, L2N, false, false);
-            const uint32_t w_addr = smem_u32(smem + OFF_W);
-            uint32_t kc = 0, wph = 0;
-            int cur_agent = -1;
-            for (int t = tile_begin, tc = 0; t < tile_end; ++t, ++tc) {
-                const int agent = t / g.tiles_per_agent;
-                const int buf = tc & 1;
-                const uint32_t nt = (uint32_t)tc >> 1;
-                if (agent != cur_agent) {
-                    if (tc > 0) {   // every MMA that reads the old weights has completed once the previous tile's accumulator is full
-                        mbar_wait(&acc_full[(tc - 1) & 1], ((uint32_t)(tc - 1) >> 1) & 1);
-                    }
-                    mbar_expect_tx(w_full, (uint32_t)nkb * L2N * KB * 2);
-                    for (int kb = 0; kb < nkb; ++kb) tma_load_3d(smem + OFF_W + kb * (L2N * KB * 2), &tmW, w_full, kb * KB, 0, agent);
-                    mbar_wait(w_full, wph);
-                    wph ^= 1;
-                    cur_agent = agent;
-                }
-                mbar_wait(&acc_empty[buf], (nt & 1) ^ 1);
-                tc_fence_after();
-                const uint32_t tacc = tmem_base + (uint32_t)(buf * L2N);
-                for (int kb = 0; kb < nkb; ++kb, ++kc) {
-                    const uint32_t slot = kc % NSLOT, n = kc / NSLOT;
-                    mbar_wait(&a_full[slot], n & 1);
-                    tc_fence_after();
-                    const uint32_t a_addr = smem_u32(smem + slot * SLOT_BYTES);
-                    const int nm = min(4, (F - kb * KB) / 16);
-                    for (int j = 0; j < nm; ++j) {
-                        mma_bf16(tacc, make_smem_desc(a_addr + j * 32, 16, 1024), make_smem_desc(w_addr + kb * (L2N * KB * 2) + j * 32, 16, 1024),
-                                 idesc, (kb | j) != 0);
-                    }
-                    mma_commit(&a_empty[slot]);
-                }
-                mma_commit(&acc_full[buf]);
-            }
-        }
-    } else if (warp <= 4) {
-        epilogue_role(g, smem, etab, reinterpret_cast<float*>(smem + OFF_SCRATCH), acc_full, acc_empty, tmem_base, warp, lane, tile_begin, tile_end);
-    } else {
-        // ===================================== producers (8 warps) ============================================
-        const int pt = threadIdx.x - 160;    // 0..255
-        const int chunk = pt & 7;            // 16-byte chunk (8 columns) inside the 64-column k-block
-        const int rg = pt >> 3;              // rows rg*4 .. rg*4+3
-        const int nx = d.ns + (g.critic ? 1 : 0);
-        uint32_t kc = 0;
-        int cur_agent = -1;
-        for (int t = tile_begin; t < tile_end; ++t) {
-            const int agent = t / g.tiles_per_agent;
-            const int tile_in_agent = t - agent * g.tiles_per_agent;
-            if (agent != cur_agent) {        // layer-1 parameter table of this agent -> shared
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-                const float* P = g.params + (int64_t)agent * g.pstride;
-                for (int c = pt; c < PTAB_COLS; c += NUM_PRODUCERS) {
-                    float w[5] = {0.f, 0.f, 0.f, 0.f, 0.f}, b = 0.f, sc = 0.f, sh = 0.f;
-                    if (c < F) {
-                        const bool is_act = g.critic && c >= d.l1;
-                        const int cc = is_act ? c - d.l1 : c;
-                        int64_t oW, ob, og, obe, omu, ovar;
-                        if (g.critic) {
-                            const CriticOff o = critic_off(d);
-                            oW = is_act ? o.Wa : o.Ws; ob = is_act ? o.ba : o.bs; og = is_act ? o.ga : o.gs; obe = is_act ? o.bea : o.bes;
-                            omu = is_act ? o.mua : o.mus; ovar = is_act ? o.vara : o.vars;
-                        } else {
-                            const ActorOff o = actor_off(d);
-                            oW = o.W1; ob = o.b1; og = o.g1; obe = o.be1; omu = o.mu1; ovar = o.var1;
-                        }
-                        if (is_act) w[4] = P[oW + cc];
-                        else for (int k = 0; k < d.ns; ++k) w[k] = P[oW + (int64_t)k * d.l1 + cc];
-                        b = P[ob + cc];
-                        const float inv = 1.0f / sqrtf(P[ovar + cc] + kBnEps);
-                        sc = P[og + cc] * inv;
-                        sh = P[obe + cc] - P[omu + cc] * sc;
-                    }
-#pragma unroll
-                    for (int k = 0; k < 5; ++k) ptab[k * PTAB_COLS + c] = w[k];
-                    ptab[5 * PTAB_COLS + c] = b;
-                    ptab[6 * PTAB_COLS + c] = sc;
-                    ptab[7 * PTAB_COLS + c] = sh;
-                }
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-                cur_agent = agent;
-            }
-            // inputs of my four rows (rows past the end of the agent's batch are clamped; the epilogue masks them)
-            float x[4][5];
-            int64_t nrow[4];
-            bool rvalid[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int64_t r_in = (int64_t)tile_in_agent * TILE_M + rg * 4 + i;
-                rvalid[i] = r_in < g.R;
-                nrow[i] = (int64_t)agent * g.R + (rvalid[i] ? r_in : g.R - 1);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) x[i][k] = (k < d.ns) ? g.s[nrow[i] * g.s_rs + k * g.s_cs] : 0.0f;
-                x[i][4] = g.critic ? g.act[nrow[i]] : 0.0f;
-            }
-            (void)nx;
-            for (int kb = 0; kb < nkb; ++kb, ++kc) {
-                const uint32_t slot = kc % NSLOT, n = kc / NSLOT;
-                mbar_wait(&a_empty[slot], (n & 1) ^ 1);
-                const int col0 = kb * KB + chunk * 8;
-                if (col0 < F) {
-                    float w[5][8], b[8], sc[8], sh[8];
-#pragma unroll
-                    for (int k = 0; k < 5; ++k) {
-                        const float4 lo = *reinterpret_cast<const float4*>(ptab + k * PTAB_COLS + col0);
-                        const float4 hi = *reinterpret_cast<const float4*>(ptab + k * PTAB_COLS + col0 + 4);
-                        w[k][0] = lo.x; w[k][1] = lo.y; w[k][2] = lo.z; w[k][3] = lo.w; w[k][4] = hi.x; w[k][5] = hi.y; w[k][6] = hi.z; w[k][7] = hi.w;
-                    }
-                    {
-                        const float4 lo = *reinterpret_cast<const float4*>(ptab + 5 * PTAB_COLS + col0), hi = *reinterpret_cast<const float4*>(ptab + 5 * PTAB_COLS + col0 + 4);
-                        b[0] = lo.x; b[1] = lo.y; b[2] = lo.z; b[3] = lo.w; b[4] = hi.x; b[5] = hi.y; b[6] = hi.z; b[7] = hi.w;
-                    }
-                    {
-                        const float4 lo = *reinterpret_cast<const float4*>(ptab + 6 * PTAB_COLS + col0), hi = *reinterpret_cast<const float4*>(ptab + 6 * PTAB_COLS + col0 + 4);
-                        sc[0] = lo.x; sc[1] = lo.y; sc[2] = lo.z; sc[3] = lo.w; sc[4] = hi.x; sc[5] = hi.y; sc[6] = hi.z; sc[7] = hi.w;
-                    }
-                    {
-                        const float4 lo = *reinterpret_cast<const float4*>(ptab + 7 * PTAB_COLS + col0), hi = *reinterpret_cast<const float4*>(ptab + 7 * PTAB_COLS + col0 + 4);
-                        sh[0] = lo.x; sh[1] = lo.y; sh[2] = lo.z; sh[3] = lo.w; sh[4] = hi.x; sh[5] = hi.y; sh[6] = hi.z; sh[7] = hi.w;
-                    }
-                    uint8_t* slot_base = smem + slot * SLOT_BYTES;
-                    const bool act_chunk = g.critic && col0 >= d.l1;
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int row = rg * 4 + i;
-                        float h[8];
-#pragma unroll
-                        for (int c = 0; c < 8; ++c) {
-                            float z;
-                            if (act_chunk) {      // action branch of the critic: one input (model.py:69-70)
-                                z = fmaf(x[i][4], w[4][c], b[c]);
-                            } else {              // state columns: ns <= 4 inputs (unused weights are zero)
-                                z = fmaf(x[i][0], w[0][c], fmaf(x[i][1], w[1][c], fmaf(x[i][2], w[2][c], fmaf(x[i][3], w[3][c], b[c]))));
-                            }
-                            h[c] = fmaf(fmaxf(z, 0.0f), sc[c], sh[c]);
-                        }
-                        const uint4 packed = make_uint4(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]), pack_bf16x2(h[4], h[5]), pack_bf16x2(h[6], h[7]));
-                        *reinterpret_cast<uint4*>(slot_base + row * 128 + ((chunk ^ (row & 7)) << 4)) = packed;   // SWIZZLE_128B
-                        if (g.H_out && rvalid[i]) *reinterpret_cast<uint4*>(g.H_out + nrow[i] * F + col0) = packed;
-                    }
-                }
-                fence_proxy_async();     // generic-proxy smem writes -> visible to the tensor core (async proxy)
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&a_full[slot]);
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 0) {
-        tc_fence_after();
-        tmem_dealloc(tmem_base, 2 * L2N);
-    }
-}
-
 // =========================================================================================================
-// Generation 2: layer 1 ALSO runs on the tensor cores.
+// Layer 1 ALSO runs on the tensor cores.
 //
-// The first generation spends ~9 CUDA-core instructions per layer-1 element and is issue-bound.  Here the
+// Computing layer 1 on the CUDA cores costs ~9 instructions per element and is issue-bound.  Here the
 // state part of layer 1 (ns <= 4 inputs + bias -> 256 features) is ONE tcgen05.mma per 128 output columns with K = 16:
 //     A1 row = [ v_hi(5) | v_lo(5) | v_hi(5) | 0 ],  v = (s0, s1, s2, s3, 1)            (bf16 hi/lo split of the fp32 inputs)
 //     B1 row = [ W_hi(4), b_hi | W_hi(4), b_hi | W_lo(4), b_lo | 0 ]                    (same split of W1 and b1)
 // so z1 = v_hi W_hi + v_lo W_hi + v_hi W_lo carries ~16 mantissa bits (the dropped v_lo W_lo term is 2^-16 relative) --
-// tighter than a tf32 MMA -- and lands in TMEM.  The former producer warps become CONVERTERS: tcgen05.ld (one row per
-// thread) -> ReLU -> BN affine -> bf16 -> 128B-swizzled A tile of layer 2 (~3 instructions per element).  The 48
-// action-branch columns of the critic (one input each) stay on the CUDA cores.
+// tighter than a tf32 MMA -- and lands in TMEM.  CONVERTER warps do tcgen05.ld (one row per thread) -> sign bit ->
+// ReLU -> bf16 -> 128B-swizzled A tile of layer 2 (~2.5 instructions per element; the BN affine is folded into W2').
+// The 48 action-branch columns of the critic (one input each) stay on the CUDA cores.
 //
 // TMEM (512 columns): [0,128) [128,256) layer-2 accumulators (double buffered), [256,384) [384,512) layer-1 outputs of
 // the two 128-column halves of a tile.  Warps: 0 MMA issuer (+W2^T TMA), 1..4 epilogue, 5..12 converters (two per lane
@@ -380,8 +181,8 @@ constexpr int OFF2_B1 = OFF2_W + W_BYTES;                // + 80 KB W2^T
 constexpr int B1_BYTES = 2 * 256 * 16;                   //   8 KB  W1ext, no-swizzle K-major: [chunk][row][16 B]
 constexpr int OFF2_X = OFF2_B1 + B1_BYTES;
 constexpr int X_BYTES = 2 * TILE_M * 16;                 //   4 KB per buffer: [chunk][row][16 B]
-constexpr int OFF2_CTAB = OFF2_X + 2 * X_BYTES;          // converter tables: sc[320], sh[320], wa[64], ba[64]
-constexpr int OFF2_ETAB = OFF2_CTAB + (2 * PTAB_COLS + 128) * 4;
+constexpr int OFF2_CTAB = OFF2_X + 2 * X_BYTES;          // converter tables (action branch): wa[64], ba[64]
+constexpr int OFF2_ETAB = OFF2_CTAB + 128 * 4;
 constexpr int OFF2_SCRATCH = OFF2_ETAB + 2080;
 constexpr int OFF2_BAR = OFF2_SCRATCH + 4 * 32 * 33 * 4;
 constexpr int SMEM2_BYTES = OFF2_BAR + 512 + 1024;
@@ -407,7 +208,7 @@ __device__ __forceinline__ uint32_t pack2(bf16 a, bf16 b) {
 __global__ void __launch_bounds__(NUM_THREADS2, 1) fused_forward_v2_kernel(const __grid_constant__ CUtensorMap tmW, Args g) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    float* ctab = reinterpret_cast<float*>(smem + OFF2_CTAB);     // sc[320] | sh[320] | wa[64] | ba[64]
+    float* ctab = reinterpret_cast<float*>(smem + OFF2_CTAB);     // wa[64] | ba[64]
     float* etab = reinterpret_cast<float*>(smem + OFF2_ETAB);
     uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + OFF2_BAR);
     uint64_t* a_empty = a_full + NSLOT2;
@@ -517,9 +318,7 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) fused_forward_v2_kernel(const
         const int sub = cw >> 2;             // which 64-column half of a 128-column layer-1 half
         const int ct = threadIdx.x - 160;    // 0..255
         const int row = q * 32 + lane;       // row of the tile owned by this thread
-        float* sc_tab = ctab;
-        float* sh_tab = ctab + PTAB_COLS;
-        float* wa_tab = ctab + 2 * PTAB_COLS;
+        float* wa_tab = ctab;
         float* ba_tab = wa_tab + 64;
         uint32_t kc_base = 0;
         int cur_agent = -1;
@@ -529,10 +328,10 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) fused_forward_v2_kernel(const
             if (agent != cur_agent) {
                 asm volatile("bar.sync 1, 256;" ::: "memory");
                 const float* P = g.params + (int64_t)agent * g.pstride;
-                int64_t oW, ob, og, obe, omu, ovar;
-                if (g.critic) { const CriticOff o = critic_off(d); oW = o.Ws; ob = o.bs; og = o.gs; obe = o.bes; omu = o.mus; ovar = o.vars; }
-                else { const ActorOff o = actor_off(d); oW = o.W1; ob = o.b1; og = o.g1; obe = o.be1; omu = o.mu1; ovar = o.var1; }
-                {   // thread ct owns layer-1 output column ct (l1 == 256): W1ext row + BN affine
+                int64_t oW, ob;
+                if (g.critic) { const CriticOff o = critic_off(d); oW = o.Ws; ob = o.bs; }
+                else { const ActorOff o = actor_off(d); oW = o.W1; ob = o.b1; }
+                {   // thread ct owns layer-1 output column ct (l1 == 256): W1ext row
                     const int n = ct;
                     bf16 whi[4], wlo[4], bhi, blo;
 #pragma unroll
@@ -544,21 +343,12 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) fused_forward_v2_kernel(const
                     const uint4 c1 = make_uint4(pack2(whi[3], bhi), pack2(wlo[0], wlo[1]), pack2(wlo[2], wlo[3]), pack2(blo, zero));
                     *reinterpret_cast<uint4*>(smem + OFF2_B1 + n * 16) = c0;
                     *reinterpret_cast<uint4*>(smem + OFF2_B1 + 256 * 16 + n * 16) = c1;
-                    const float inv = 1.0f / sqrtf(P[ovar + n] + kBnEps);
-                    const float sc = P[og + n] * inv;
-                    sc_tab[n] = sc;
-                    sh_tab[n] = P[obe + n] - P[omu + n] * sc;
                 }
                 if (g.critic && ct < 64) {   // action branch (la <= 64 columns)
                     const CriticOff o = critic_off(d);
-                    float wa = 0.f, ba = 0.f, sc = 0.f, sh = 0.f;
-                    if (ct < d.la) {
-                        wa = P[o.Wa + ct]; ba = P[o.ba + ct];
-                        const float inv = 1.0f / sqrtf(P[o.vara + ct] + kBnEps);
-                        sc = P[o.ga + ct] * inv;
-                        sh = P[o.bea + ct] - P[o.mua + ct] * sc;
-                    }
-                    wa_tab[ct] = wa; ba_tab[ct] = ba; sc_tab[256 + ct] = sc; sh_tab[256 + ct] = sh;
+                    float wa = 0.f, ba = 0.f;
+                    if (ct < d.la) { wa = P[o.Wa + ct]; ba = P[o.ba + ct]; }
+                    wa_tab[ct] = wa; ba_tab[ct] = ba;
                 }
                 fence_proxy_async();
                 asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -573,8 +363,13 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) fused_forward_v2_kernel(const
             const int rows_here = (int)max((int64_t)0, min((int64_t)32, g.R - blk_row));
 
             // write one finished 64-column k-block of my row into ring slot `slot` (+ coalesced copy to H_out)
-            auto emit = [&](const float* hv, int ncols, int kb, uint32_t slot) {
+            auto emit = [&](const float* hv, int ncols, int kb, uint32_t slot, uint32_t neg0, uint32_t neg1) {
                 uint8_t* slot_base = smem + slot * SLOT_BYTES;
+                if (g.mask_out && rvalid) {
+                    uint32_t* mrow = g.mask_out + nrow * g.mask_words + 2 * kb;
+                    mrow[0] = neg0;
+                    mrow[1] = neg1;
+                }
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     if (j * 8 < ncols) {
@@ -615,31 +410,33 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) fused_forward_v2_kernel(const
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&z1_empty[h]);          // TMEM half may be overwritten by the next tile's layer-1 MMA
-                const int col0 = kb * KB;
+                uint32_t neg0 = 0, neg1 = 0;     // sign bits of z1: one funnel shift per element
 #pragma unroll
-                for (int j = 0; j < 64; j += 4) {
-                    const float4 s4 = *reinterpret_cast<const float4*>(sc_tab + col0 + j);
-                    const float4 h4 = *reinterpret_cast<const float4*>(sh_tab + col0 + j);
-                    z[j] = fmaf(fmaxf(z[j], 0.0f), s4.x, h4.x);
-                    z[j + 1] = fmaf(fmaxf(z[j + 1], 0.0f), s4.y, h4.y);
-                    z[j + 2] = fmaf(fmaxf(z[j + 2], 0.0f), s4.z, h4.z);
-                    z[j + 3] = fmaf(fmaxf(z[j + 3], 0.0f), s4.w, h4.w);
+                for (int j = 0; j < 32; ++j) {
+                    neg0 = __funnelshift_l(__float_as_uint(z[j]), neg0, 1);
+                    neg1 = __funnelshift_l(__float_as_uint(z[32 + j]), neg1, 1);
+                    z[j] = fmaxf(z[j], 0.0f);
+                    z[32 + j] = fmaxf(z[32 + j], 0.0f);
                 }
                 mbar_wait(&a_empty[slot], (n & 1) ^ 1);
-                emit(z, 64, kb, slot);
+                emit(z, 64, kb, slot, neg0, neg1);
             }
             if (g.critic && sub == 1) {     // action-branch k-block (48 columns, one input): CUDA cores
                 const int kb = 4;
                 const uint32_t kcx = kc_base + (uint32_t)kb;
                 const uint32_t slot = kcx % NSLOT2, n = kcx / NSLOT2;
                 float hv[64];
+                uint32_t neg0 = 0, neg1 = 0;
 #pragma unroll
-                for (int j = 0; j < 64; ++j) {
-                    const float zz = fmaf(a_val, wa_tab[j], ba_tab[j]);
-                    hv[j] = fmaf(fmaxf(zz, 0.0f), sc_tab[256 + j], sh_tab[256 + j]);
+                for (int j = 0; j < 32; ++j) {
+                    const float z0 = fmaf(a_val, wa_tab[j], ba_tab[j]), z1 = fmaf(a_val, wa_tab[32 + j], ba_tab[32 + j]);
+                    neg0 = __funnelshift_l(__float_as_uint(z0), neg0, 1);
+                    neg1 = __funnelshift_l(__float_as_uint(z1), neg1, 1);
+                    hv[j] = fmaxf(z0, 0.0f);
+                    hv[32 + j] = fmaxf(z1, 0.0f);
                 }
                 mbar_wait(&a_empty[slot], (n & 1) ^ 1);
-                emit(hv, d.la, kb, slot);
+                emit(hv, d.la, kb, slot, neg0, neg1);
             }
             kc_base += (uint32_t)nkb;
         }
@@ -695,13 +492,13 @@ static PFN_cuTensorMapEncodeTiled encode_fn() {
 
 bool supported(const avd_net_dims& d, bool critic) {
     const int F = critic ? d.l1 + d.la : d.l1;
-    return d.l2 == L2N && d.ns <= 4 && F % 16 == 0 && F <= MAX_KB * KB && d.l1 % 8 == 0 && d.la % 8 == 0;
+    return d.l2 == L2N && d.ns <= 4 && d.l1 == 256 && F % 16 == 0 && F <= MAX_KB * KB && d.la % 8 == 0 && d.la <= 64;
 }
 
-// W2T: bf16 [A][128][F] (K-major copy of the layer-2 kernel, see pack_w2_kernel)
-int forward(const avd_net_dims& d, bool critic, int A, int64_t R, const float* params, int64_t pstride, const bf16* W2T, const float* s,
-            int64_t s_rs, int64_t s_cs, const float* act, bf16* H_out, float* Z_out, int head, const float* rew, float gamma, float high,
-            float* out, cudaStream_t st, bf16* DZ_out, float* loss) {
+// W2T: bf16 [A][128][F] (K-major copy of the BN-folded layer-2 kernel) and b2f [A][128]: see pack_fold_kernel
+int forward(const avd_net_dims& d, bool critic, int A, int64_t R, const float* params, int64_t pstride, const bf16* W2T, const float* b2f,
+            const float* s, int64_t s_rs, int64_t s_cs, const float* act, bf16* H_out, uint32_t* mask_out, float* Z_out, int head,
+            const float* rew, float gamma, float high, float* out, cudaStream_t st, bf16* DZ_out, float* loss) {
     if (!supported(d, critic)) {
         set_error("fused forward kernel does not support these layer sizes");
         return AVD_ERR_UNSUPPORTED;
@@ -712,12 +509,8 @@ int forward(const avd_net_dims& d, bool critic, int A, int64_t R, const float* p
         return AVD_ERR_CUDA;
     }
     static bool attr_set = false;
-    static int use_v2 = 1;
     if (!attr_set) {
-        AVD_CUDA_OK(cudaFuncSetAttribute(fused_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         AVD_CUDA_OK(cudaFuncSetAttribute(v2::fused_forward_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::SMEM2_BYTES));
-        const char* e = getenv("AVD_FUSED_GEN");      // "1" forces the first-generation kernel (A/B comparisons)
-        if (e && e[0] == '1') use_v2 = 0;
         attr_set = true;
     }
     const int F = critic ? d.l1 + d.la : d.l1;
@@ -733,18 +526,16 @@ int forward(const avd_net_dims& d, bool critic, int A, int64_t R, const float* p
         return AVD_ERR_CUDA;
     }
     Args g;
-    g.d = d; g.critic = critic ? 1 : 0; g.A = A; g.R = R; g.params = params; g.pstride = pstride;
-    g.s = s; g.s_rs = s_rs; g.s_cs = s_cs; g.act = act; g.H_out = H_out; g.Z_out = Z_out; g.head = head; g.rew = rew;
+    g.d = d; g.critic = critic ? 1 : 0; g.A = A; g.R = R; g.params = params; g.pstride = pstride; g.b2f = b2f;
+    g.s = s; g.s_rs = s_rs; g.s_cs = s_cs; g.act = act; g.H_out = H_out; g.mask_out = mask_out; g.mask_words = 2 * ((F + KB - 1) / KB);
+    g.Z_out = Z_out; g.head = head; g.rew = rew;
     g.gamma = gamma; g.high = high; g.out = out; g.DZ_out = DZ_out; g.loss = loss;
     g.tiles_per_agent = (int)((R + TILE_M - 1) / TILE_M);
     g.total_tiles = g.tiles_per_agent * A;
     const int ctas = std::min(g.total_tiles, sm_count());
     g.tiles_per_cta = (g.total_tiles + ctas - 1) / ctas;
     const int grid = (g.total_tiles + g.tiles_per_cta - 1) / g.tiles_per_cta;
-    if (use_v2 && d.l1 == 256)
-        v2::fused_forward_v2_kernel<<<grid, v2::NUM_THREADS2, v2::SMEM2_BYTES, st>>>(tm, g);
-    else
-        fused_forward_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tm, g);
+    v2::fused_forward_v2_kernel<<<grid, v2::NUM_THREADS2, v2::SMEM2_BYTES, st>>>(tm, g);
     AVD_LAUNCH_OK();
     return AVD_OK;
 }

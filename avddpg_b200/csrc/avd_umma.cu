@@ -13,6 +13,8 @@
 // and, unchanged, as the MN-major A of the weight-gradient GEMM.
 #include <cudaTypedefs.h>
 
+#include <utility>
+
 #include "avd_common.cuh"
 #include "avd_umma.cuh"
 
@@ -24,35 +26,40 @@ constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KB
 constexpr int B_STAGE_BYTES = BN * BK * 2;   // 16 KB
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int SCRATCH_BYTES = 4 * 32 * 33 * 4;   // per-epilogue-warp transpose scratch
-constexpr int smem_bytes(int stages) { return stages * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + SCRATCH_BYTES; }
+constexpr int smem_bytes(int stages, int bn = BN) { return stages * (A_STAGE_BYTES + bn * BK * 2) + 1024 /*align slack*/ + 256 /*barriers*/ + SCRATCH_BYTES; }
 // TN GEMMs of the learn step have K <= 320 (2..5 k-blocks): 2 stages = 65 KB so that three CTAs share an SM and one
 // CTA's prologue/epilogue overlaps another's MMAs; the NT weight-gradient GEMM streams thousands of rows: 4 stages.
 constexpr int STAGES_TN = 2, STAGES_NT = 4;
 constexpr int NUM_THREADS = 192;             // warp 0 TMA, warp 1 MMA (+TMEM alloc), warps 2..5 epilogue
 
 struct GemmParams {
+    ReluMaskEpilogue rm;
     int M, N;              // valid output rows / columns (per batch)
     int k_blocks;          // number of 64-deep K blocks per split
     int splitk;
     float* C;
     int64_t ldc, c_batch;
     int atomic;            // 1: atomicAdd into C (split-K)
+    int n_fastest;         // 1: blockIdx.x walks the N tiles, so the CTAs that share an A tile run together and re-read it from L2
 };
 
-template <bool MN_MAJOR, int STAGES>
+template <bool MN_MAJOR, int STAGES, int BN_>
 __global__ void __launch_bounds__(NUM_THREADS, (STAGES <= 2) ? 3 : 1) gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                    const __grid_constant__ CUtensorMap tmB, GemmParams g) {
+    constexpr int B_STAGE = BN_ * BK * 2;
+    constexpr int STAGE = A_STAGE_BYTES + B_STAGE;
+    static_assert(BN_ == 128 || (BN_ == 64 && MN_MAJOR), "64-wide output tiles exist for the MN-major layout only");
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);   // SWIZZLE_128B tiles need 1024-byte alignment
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* accum_bar = empty_bar + STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
-    float* scratch_all = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);
+    float* scratch_all = reinterpret_cast<float*>(smem + STAGES * STAGE + 256);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    const int m0 = (g.n_fastest ? blockIdx.y : blockIdx.x) * BM, n0 = (g.n_fastest ? blockIdx.x : blockIdx.y) * BN_;
     const int batch = blockIdx.z / g.splitk, split = blockIdx.z % g.splitk;
     const int kb0 = split * g.k_blocks;
 
@@ -78,9 +85,9 @@ __global__ void __launch_bounds__(NUM_THREADS, (STAGES <= 2) ? 3 : 1) gemm_bf16_
                 const int s = kb % STAGES;
                 const uint32_t ph = (kb / STAGES) & 1;
                 mbar_wait(&empty_bar[s], ph ^ 1);
-                uint8_t* sa = smem + s * STAGE_BYTES;
+                uint8_t* sa = smem + s * STAGE;
                 uint8_t* sb = sa + A_STAGE_BYTES;
-                mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+                mbar_expect_tx(&full_bar[s], STAGE);
                 const int k = (kb0 + kb) * BK;
                 if (!MN_MAJOR) {   // box {64 k, 128 rows}
                     tma_load_3d(sa, &tmA, &full_bar[s], k, m0, batch);
@@ -89,19 +96,19 @@ __global__ void __launch_bounds__(NUM_THREADS, (STAGES <= 2) ? 3 : 1) gemm_bf16_
                     tma_load_3d(sa, &tmA, &full_bar[s], m0, k, batch);
                     tma_load_3d(sa + A_STAGE_BYTES / 2, &tmA, &full_bar[s], m0 + 64, k, batch);
                     tma_load_3d(sb, &tmB, &full_bar[s], n0, k, batch);
-                    tma_load_3d(sb + B_STAGE_BYTES / 2, &tmB, &full_bar[s], n0 + 64, k, batch);
+                    if (BN_ == 128) tma_load_3d(sb + B_STAGE / 2, &tmB, &full_bar[s], n0 + 64, k, batch);
                 }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {  // ===== MMA issuer =====
-            constexpr uint32_t idesc = make_idesc_bf16(BM, BN, MN_MAJOR, MN_MAJOR);
+            constexpr uint32_t idesc = make_idesc_bf16(BM, BN_, MN_MAJOR, MN_MAJOR);
             for (int kb = 0; kb < g.k_blocks; ++kb) {
                 const int s = kb % STAGES;
                 const uint32_t ph = (kb / STAGES) & 1;
                 mbar_wait(&full_bar[s], ph);
                 tc_fence_after();
-                const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+                const uint32_t sa = smem_u32(smem + s * STAGE);
                 const uint32_t sb = sa + A_STAGE_BYTES;
 #pragma unroll
                 for (int j = 0; j < BK / 16; ++j) {
@@ -111,7 +118,7 @@ __global__ void __launch_bounds__(NUM_THREADS, (STAGES <= 2) ? 3 : 1) gemm_bf16_
                         bd = make_smem_desc(sb + j * 32, 16, 1024);
                     } else {           // advance 16 K rows = two 8-row groups of 1024 B; MN chunks 8 KB apart
                         ad = make_smem_desc(sa + j * 2048, A_STAGE_BYTES / 2, 1024);
-                        bd = make_smem_desc(sb + j * 2048, B_STAGE_BYTES / 2, 1024);
+                        bd = make_smem_desc(sb + j * 2048, BN_ == 128 ? B_STAGE / 2 : 16, 1024);
                     }
                     mma_bf16(tmem_base, ad, bd, idesc, (kb | j) != 0);
                 }
@@ -129,17 +136,27 @@ __global__ void __launch_bounds__(NUM_THREADS, (STAGES <= 2) ? 3 : 1) gemm_bf16_
         float* cblock = g.C + (int64_t)batch * g.c_batch + (int64_t)(m0 + q * 32) * g.ldc;
         const int rows_here = min(32, g.M - (m0 + q * 32));
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = 0; c < BN_ / 32; ++c) {
+            const int col0 = n0 + c * 32;
+            if (g.rm.mask ? (col0 >= g.rm.ldo) : (col0 >= g.N)) break;
             float v[32];
             tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
-            const int col0 = n0 + c * 32;
-            if (g.atomic) {
+            if (g.rm.mask) {
+                if (rows_here > 0) {
+                    const int64_t grow = (int64_t)batch * g.M + min(row, g.M - 1);
+                    const uint32_t neg = g.rm.mask[grow * g.rm.words + (col0 >> 5)];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if ((neg & (0x80000000u >> j)) || col0 + j >= g.N) v[j] = 0.0f;
+                    store_block_32x32_bf16(scratch, v, g.rm.out + ((int64_t)batch * g.M + m0 + q * 32) * g.rm.ldo + col0, g.rm.ldo, rows_here, lane);
+                }
+            } else if (g.atomic) {
                 if (row < g.M) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
                         if (col0 + j < g.N) atomicAdd(crow + col0 + j, v[j]);
                 }
-            } else if (col0 < g.N && rows_here > 0) {
+            } else if (rows_here > 0) {
                 store_block_32x32(scratch, v, cblock + col0, g.ldc, rows_here, min(32, g.N - col0), lane);
             }
         }
@@ -151,6 +168,7 @@ __global__ void __launch_bounds__(NUM_THREADS, (STAGES <= 2) ? 3 : 1) gemm_bf16_
         tmem_dealloc(tmem_base, BN);
     }
 }
+
 
 static PFN_cuTensorMapEncodeTiled encode_fn() {
     static PFN_cuTensorMapEncodeTiled fn = nullptr;
@@ -187,34 +205,44 @@ static int make_map(CUtensorMap* map, const void* base, uint64_t inner, uint64_t
 }
 
 int gemm_bf16(int layout, int batch, int M, int N, int K, const void* A, int64_t lda, int64_t a_batch, const void* B, int64_t ldb,
-              int64_t b_batch, float* C, int64_t ldc, int64_t c_batch, int splitk, cudaStream_t st) {
+              int64_t b_batch, float* C, int64_t ldc, int64_t c_batch, int splitk, cudaStream_t st, const ReluMaskEpilogue* rm) {
     AVD_REQUIRE(layout == 0 || layout == 1, "layout must be 0 (TN) or 1 (NT)");
     AVD_REQUIRE(batch >= 1 && M >= 1 && N >= 1 && K >= 1 && splitk >= 1, "bad GEMM sizes");
-    AVD_REQUIRE(A && B && C, "null operand");
+    AVD_REQUIRE(A && B && (C || rm), "null operand");
+    AVD_REQUIRE(!rm || (layout == 0 && splitk == 1 && rm->mask && rm->out && rm->ldo % 32 == 0 && rm->ldo >= N),
+                "the ReLU-mask epilogue needs the TN layout without split-K and an output pitch that is a multiple of 32");
     AVD_REQUIRE(lda % 8 == 0 && ldb % 8 == 0 && a_batch % 8 == 0 && b_batch % 8 == 0, "bf16 leading dimensions must be multiples of 8 elements (16 B)");
     AVD_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0, "operands must be 16-byte aligned");
     static bool attr_set = false;
     if (!attr_set) {
-        AVD_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_kernel<false, STAGES_TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(STAGES_TN)));
-        AVD_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_kernel<true, STAGES_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(STAGES_NT)));
+        AVD_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_kernel<false, STAGES_TN, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(STAGES_TN)));
+        AVD_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_kernel<true, STAGES_NT, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(STAGES_NT)));
+        AVD_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_kernel<true, STAGES_NT, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(STAGES_NT, 64)));
         attr_set = true;
     }
     CUtensorMap tmA, tmB;
     const int kblocks_total = (K + BK - 1) / BK;
     if (splitk > kblocks_total) splitk = kblocks_total;
     GemmParams g;
+    if (rm) g.rm = *rm; else g.rm = ReluMaskEpilogue{nullptr, 0, nullptr, 0};
     g.M = M; g.N = N; g.splitk = splitk;
     g.k_blocks = (kblocks_total + splitk - 1) / splitk;
     g.C = C; g.ldc = ldc; g.c_batch = c_batch; g.atomic = (splitk > 1 || layout == 1) ? 1 : 0;
-    dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN, batch * splitk);
+    const bool narrow = layout == 1 && N <= 64;     // e.g. the layer-1 weight gradient  dz1^T [x_hi | 1 | x_lo]  (N = 16)
+    const int bn = narrow ? 64 : BN;
+    const int ncols = rm ? (int)rm->ldo : N;        // the mask epilogue also writes the zero pad up to the output pitch
+    dim3 grid((M + BM - 1) / BM, (ncols + bn - 1) / bn, batch * splitk);
+    g.n_fastest = (layout == 0 && grid.y > 1 && grid.x <= 65535) ? 1 : 0;
+    if (g.n_fastest) std::swap(grid.x, grid.y);
     if (layout == 0) {
         if (int rc = make_map(&tmA, A, K, M, batch, lda, a_batch, BK, BM)) return rc;
         if (int rc = make_map(&tmB, B, K, N, batch, ldb, b_batch, BK, BN)) return rc;
-        gemm_bf16_kernel<false, STAGES_TN><<<grid, NUM_THREADS, smem_bytes(STAGES_TN), st>>>(tmA, tmB, g);
+        gemm_bf16_kernel<false, STAGES_TN, 128><<<grid, NUM_THREADS, smem_bytes(STAGES_TN), st>>>(tmA, tmB, g);
     } else {
         if (int rc = make_map(&tmA, A, M, K, batch, lda, a_batch, 64, BK)) return rc;
         if (int rc = make_map(&tmB, B, N, K, batch, ldb, b_batch, 64, BK)) return rc;
-        gemm_bf16_kernel<true, STAGES_NT><<<grid, NUM_THREADS, smem_bytes(STAGES_NT), st>>>(tmA, tmB, g);
+        if (narrow) gemm_bf16_kernel<true, STAGES_NT, 64><<<grid, NUM_THREADS, smem_bytes(STAGES_NT, 64), st>>>(tmA, tmB, g);
+        else gemm_bf16_kernel<true, STAGES_NT, 128><<<grid, NUM_THREADS, smem_bytes(STAGES_NT), st>>>(tmA, tmB, g);
     }
     AVD_LAUNCH_OK();
     return AVD_OK;
@@ -225,5 +253,5 @@ int gemm_bf16(int layout, int batch, int M, int N, int K, const void* A, int64_t
 
 extern "C" int avd_gemm_bf16(int layout, int batch, int M, int N, int K, const void* A, int64_t lda, int64_t a_batch, const void* B,
                              int64_t ldb, int64_t b_batch, float* C, int64_t ldc, int64_t c_batch, int splitk, void* stream) {
-    return avd::umma::gemm_bf16(layout, batch, M, N, K, A, lda, a_batch, B, ldb, b_batch, C, ldc, c_batch, splitk, (cudaStream_t)stream);
+    return avd::umma::gemm_bf16(layout, batch, M, N, K, A, lda, a_batch, B, ldb, b_batch, C, ldc, c_batch, splitk, (cudaStream_t)stream, nullptr);
 }

@@ -9,6 +9,17 @@
 namespace avd {
 namespace umma {
 
+// Optional epilogue of the dgrad GEMM (TN layout): instead of storing dR = dZ W2'^T in fp32, zero the entries whose
+// layer-1 pre-activation was not positive (ReLU backward, agent/model.py:19,27,62,69 through trainer.py:498,506) and
+// store bf16.  The sign bits come from the forward kernel (avd_fused.cu): word w of a row covers columns 32w..32w+31,
+// column j of the word sits at bit 31-j, 1 = "z1 had its sign bit set".  Pad columns N..ldo-1 are written as zeros.
+struct ReluMaskEpilogue {
+    const uint32_t* mask;  // [batch*M][words]   (nullptr: epilogue disabled)
+    int words;
+    __nv_bfloat16* out;    // [batch*M][ldo]
+    int64_t ldo;
+};
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // ---- mbarrier ----------------------------------------------------------------------------------
