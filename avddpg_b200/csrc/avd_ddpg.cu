@@ -16,6 +16,8 @@
 //
 // BatchNormalization is always the inference affine (models are never called with training=True):
 //   y = g*(x-mu)/sqrt(var+1e-3)+be, with trainable g/be and frozen mu/var.
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include <cuda_bf16.h>
@@ -33,6 +35,14 @@ bool supported(const avd_net_dims& d, bool critic);
 int forward(const avd_net_dims& d, bool critic, int A, int64_t R, const float* params, int64_t pstride, const bf16* W2T, const float* b2f,
             const float* s, int64_t s_rs, int64_t s_cs, const float* act, bf16* H_out, uint32_t* mask_out, float* Z_out, int head,
             const float* rew, float gamma, float high, float* out, cudaStream_t st, bf16* DZ_out = nullptr, float* loss = nullptr);
+}
+
+namespace fused3 {  // avd_fused3.cu
+enum Mode { MODE_ACTOR_OUT = 0, MODE_TARGET = 1, MODE_Q = 2, MODE_CRITIC_BWD = 3, MODE_ACTOR_BWD = 4, MODE_CRITIC_ACTION = 5 };
+bool supported(const avd_net_dims& d);
+int run(int mode, const avd_net_dims& d, int A, int64_t R, const float* params, int64_t pstride, const bf16* W2T, const float* b2f, const float* s,
+        int64_t s_rs, int64_t s_cs, const float* act, const float* rew, float gamma, float high, const float* y, const float* dpi, float* out,
+        bf16* R1_out, int64_t r1_pitch, uint32_t* mask_out, bf16* DZ_out, float* U, float* sdq, float* loss, cudaStream_t st);
 }
 
 namespace umma {   // avd_umma.cu
@@ -589,10 +599,15 @@ __global__ void __launch_bounds__(256) pack_fold_kernel(const float* __restrict_
 
 // xext[n] = [ s_hi(4) a_hi 1 0 0 | s_lo(4) a_lo 0 0 0 ] (bf16): B operand of the layer-1 weight-gradient GEMM
 //   G1[f][c] = sum_n dz1[n][f] xext[n][c]   =>  dW1[k][f] = G1[f][k] + G1[f][8+k],  dWa[f] = G1[l1+f][4] + G1[l1+f][12],  db[f] = G1[f][5]
+// Optionally also writes the constant-one column behind the r1 activations of the critic / actor ([N][pitch], column
+// `col`): the weight-gradient GEMM  [r1 | 1]^T dz2  then yields db2 as row F of its output, which is where b2 follows W2.
 __global__ void __launch_bounds__(256) xext_kernel(const float* __restrict__ s, const float* __restrict__ a, int ns, int64_t N,
-                                                   bf16* __restrict__ xext) {
+                                                   bf16* __restrict__ xext, bf16* __restrict__ ones_c, int64_t pitch_c, int col_c,
+                                                   bf16* __restrict__ ones_a, int64_t pitch_a, int col_a) {
     const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N) return;
+    if (ones_c) ones_c[n * pitch_c + col_c] = __float2bfloat16_rn(1.0f);
+    if (ones_a) ones_a[n * pitch_a + col_a] = __float2bfloat16_rn(1.0f);
     float v[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
     for (int k = 0; k < ns && k < 4; ++k) v[k] = s[n * ns + k];
     v[4] = a[n];
@@ -667,6 +682,27 @@ __global__ void __launch_bounds__(256) unfold_kernel(const float* __restrict__ p
     }
 }
 
+// Head / BN2 gradients from the sums the fused backward pass accumulates (avd_fused3.cu):
+//   U[j] = sum_n dq_n relu(z2)[n][j],  sd = sum_n dq_n,   h2 = relu(z2) sc2 + sh2,   q = h2 . w3 + b3
+//   dW3 = sc2 U + sh2 sd;   dgamma2 = w3 inv2 (U - mu2 sd);   dbeta2 = w3 sd;   db3 = sd     (db2 comes out of the wgrad GEMM)
+struct HeadOff { int64_t g2, be2, mu2, var2, W3, b3; };
+
+__global__ void __launch_bounds__(128) head_unfold_kernel(const float* __restrict__ params, int64_t pstride, float* __restrict__ grads, int64_t gstride,
+                                                          const float* __restrict__ U, const float* __restrict__ sdq, HeadOff o, int l2) {
+    const int agent = blockIdx.x, j = threadIdx.x;
+    if (j >= l2) return;
+    const float* P = params + (int64_t)agent * pstride;
+    float* G = grads + (int64_t)agent * gstride;
+    const float inv = 1.0f / sqrtf(P[o.var2 + j] + kBnEps);
+    const float sc = P[o.g2 + j] * inv, mu = P[o.mu2 + j];
+    const float sh = P[o.be2 + j] - mu * sc;
+    const float w3 = P[o.W3 + j], u = U[(int64_t)agent * l2 + j], sd = sdq[agent];
+    G[o.W3 + j] = fmaf(sc, u, sh * sd);
+    G[o.g2 + j] = w3 * inv * (u - mu * sd);
+    G[o.be2 + j] = w3 * sd;
+    if (j == 0) G[o.b3] = sd;
+}
+
 // ------------------------------------------------------------------------------------------------
 // host orchestration
 // ------------------------------------------------------------------------------------------------
@@ -677,13 +713,14 @@ struct Workspace {
     uint32_t* mask;
     bf16* xext;
     float *G1, *c_b2f, *tc_b2f, *a_b2f, *ta_b2f;
+    float *U, *sdq;            // [2][A][l2], [2][A]: head-gradient sums of the critic [0] and actor [1] backward passes
     static constexpr int kMaskWords = 10, kFp = 320;
     static int64_t bytes(const avd_net_dims& d, int64_t A, int64_t N) {
         const int64_t F = d.l1 + d.la;
         const int64_t acts = N * (2 * F + d.l1 + 3 * (int64_t)d.l2) * (int64_t)sizeof(float);
         const int64_t packed = A * (3 * F + 3 * (int64_t)d.l1) * d.l2 * (int64_t)sizeof(bf16);
         const int64_t vecs = 4 * ((N + 3) / 4 * 4) * (int64_t)sizeof(float);
-        const int64_t fold = N * (kMaskWords * 4 + 16 * 2) + A * (kFp * 16 + 4 * (int64_t)d.l2) * (int64_t)sizeof(float);
+        const int64_t fold = N * (kMaskWords * 4 + 16 * 2) + A * (kFp * 16 + 6 * (int64_t)d.l2 + 8) * (int64_t)sizeof(float);
         return acts + packed + vecs + fold + 1024;
     }
     void carve(void* base_, const avd_net_dims& d, int64_t A, int64_t N) {
@@ -713,6 +750,8 @@ struct Workspace {
         tc_b2f = p; p += A * d.l2;
         a_b2f = p; p += A * d.l2;
         ta_b2f = p; p += A * d.l2;
+        U = p; p += 2 * A * d.l2;
+        sdq = p; p += (2 * A + 3) / 4 * 4;
         mask = reinterpret_cast<uint32_t*>(p); p += N * kMaskWords;
         xext = reinterpret_cast<bf16*>(((uintptr_t)p + 15) & ~(uintptr_t)15);
     }
@@ -941,6 +980,9 @@ extern "C" int avd_actor_forward(const avd_net_dims* dims, int32_t A, int64_t R,
     bf16* W2T = reinterpret_cast<bf16*>(Z + N * d.l2);
     if (precision && fused::supported(d, false)) {   // fused kernel: H / Z are never materialised, their space holds the folded bias
         AVD_TRY(p.pack_fold(false, actor_params, nullptr, W2T, H));
+        if (fused3::supported(d))
+            return fused3::run(fused3::MODE_ACTOR_OUT, d, A, R, actor_params, o.total, W2T, H, s, s_rs, s_cs, nullptr, nullptr, 0.f, action_high, nullptr,
+                               nullptr, out, nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr, p.st);
         return fused::forward(d, false, A, R, actor_params, o.total, W2T, H, s, s_rs, s_cs, nullptr, nullptr, nullptr, nullptr, 1, nullptr, 0.f,
                               action_high, out, p.st);
     }
@@ -971,6 +1013,9 @@ extern "C" int avd_critic_forward(const avd_net_dims* dims, int32_t A, int64_t R
     bf16* W2T = reinterpret_cast<bf16*>(Z + N * d.l2);
     if (precision && fused::supported(d, true)) {
         AVD_TRY(p.pack_fold(true, critic_params, nullptr, W2T, H));
+        if (fused3::supported(d))
+            return fused3::run(fused3::MODE_Q, d, A, R, critic_params, o.total, W2T, H, s, d.ns, 1, a, nullptr, 0.f, 0.f, nullptr, nullptr, q, nullptr, 0,
+                               nullptr, nullptr, nullptr, nullptr, nullptr, p.st);
         return fused::forward(d, true, A, R, critic_params, o.total, W2T, H, s, d.ns, 1, a, nullptr, nullptr, nullptr, 3, nullptr, 0.f, 0.f, q, p.st);
     }
     if (precision) AVD_TRY(p.pack(critic_params, o.total, o.W2, F, nullptr, W2T));
@@ -1075,7 +1120,7 @@ static int learn_fused(const avd_learn_io* io, const Pass& p, const Workspace& w
     AVD_TRY(p.pack_fold(true, io->t_critic, nullptr, w.tcW2T, w.tc_b2f));
     AVD_TRY(p.pack_fold(true, io->critic, w.cW2b, w.cW2T, w.c_b2f));
     AVD_TRY(p.pack_fold(false, io->actor, w.aW2b, w.aW2T, w.a_b2f));
-    xext_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(io->s, io->a, d.ns, N, w.xext);
+    xext_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(io->s, io->a, d.ns, N, w.xext, nullptr, 0, 0, nullptr, 0, 0);
     AVD_LAUNCH_OK();
     // ---- TD target: y = r + gamma * target_critic(s', target_actor(s'))            trainer.py:493-494
     AVD_TRY(fused::forward(d, false, A, R, io->t_actor, ao.total, w.taW2T, w.ta_b2f, io->s2, d.ns, 1, nullptr, nullptr, nullptr, nullptr, 1, nullptr,
@@ -1116,6 +1161,70 @@ static int learn_fused(const avd_learn_io* io, const Pass& p, const Workspace& w
     return apply_local_updates(io, (void*)st);
 }
 
+// The learn step on the third-generation fused pass kernels (avd_fused3.cu): six persistent launches cover every forward
+// pass, both head backwards and the critic -> actor link; r1 / dz2 / masks go to HBM once for the three GEMM kinds that
+// remain (wgrad [r1 | 1]^T dz2, dgrad with the ReLU-mask epilogue, layer-1 wgrad dz1^T [x_hi | 1 | x_lo]).
+static int learn_fused3(const avd_learn_io* io, const Pass& p, const Workspace& w, cudaStream_t st) {
+    const avd_net_dims d = io->dims;
+    const int A = io->A;
+    const int64_t R = io->rows_per_agent, N = (int64_t)A * R;
+    const ActorOff ao = actor_off(d);
+    const CriticOff co = critic_off(d);
+    const int F = d.l1 + d.la;
+    constexpr int Fp = Workspace::kFp, MW = Workspace::kMaskWords;
+    bf16* Hc = reinterpret_cast<bf16*>(w.H);        // [N][Fp]: r1 of the critic, column F = 1
+    bf16* Ha = reinterpret_cast<bf16*>(w.H1a);      // [N][Fp]: r1 of the actor, column l1 = 1
+    bf16* DZ = reinterpret_cast<bf16*>(w.DZ);
+    bf16* dz1 = reinterpret_cast<bf16*>(w.DH);      // [N][Fp] (critic) / [N][l1] (actor)
+    float* Uc = w.U;
+    float* Ua = w.U + (int64_t)A * d.l2;
+    AVD_TRY(p.pack_fold(false, io->t_actor, nullptr, w.taW2T, w.ta_b2f));
+    AVD_TRY(p.pack_fold(true, io->t_critic, nullptr, w.tcW2T, w.tc_b2f));
+    AVD_TRY(p.pack_fold(true, io->critic, w.cW2b, w.cW2T, w.c_b2f));
+    AVD_TRY(p.pack_fold(false, io->actor, w.aW2b, w.aW2T, w.a_b2f));
+    xext_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(io->s, io->a, d.ns, N, w.xext, Hc, Fp, F, Ha, Fp, d.l1);
+    AVD_LAUNCH_OK();
+    AVD_CUDA_OK(cudaMemsetAsync(w.U, 0, (size_t)(2 * A * d.l2 + 2 * A) * sizeof(float), st));   // U and sdq are adjacent
+    auto wgrad_ones = [&](const bf16* H, int Fn, float* grads, int64_t gstride, int64_t oW2) {   // rows 0..Fn-1: G2, row Fn: db2
+        const int tiles = ((Fn + 1 + 127) / 128) * A;
+        const int split = (int)std::max<int64_t>(1, std::min<int64_t>((R + 63) / 64, std::max(1, 4 * sm_count() / std::max(1, tiles))));
+        return umma::gemm_bf16(1, A, Fn + 1, d.l2, (int)R, H, Fp, R * Fp, DZ, d.l2, R * d.l2, grads + oW2, d.l2, gstride, split, st);
+    };
+    auto head_unfold = [&](bool critic, const float* params, float* grads, const float* U, const float* sdq) {
+        HeadOff o;
+        int64_t ps, gs;
+        if (critic) { o = HeadOff{co.g2, co.be2, co.mu2, co.var2, co.W3, co.b3}; ps = co.total; gs = co.n_train; }
+        else { o = HeadOff{ao.g2, ao.be2, ao.mu2, ao.var2, ao.W3, ao.b3}; ps = ao.total; gs = ao.n_train; }
+        head_unfold_kernel<<<A, 128, 0, st>>>(params, ps, grads, gs, U, sdq, o, d.l2);
+    };
+    // ---- TD target: y = r + gamma * target_critic(s', target_actor(s'))            trainer.py:493-494
+    AVD_TRY(fused3::run(fused3::MODE_ACTOR_OUT, d, A, R, io->t_actor, ao.total, w.taW2T, w.ta_b2f, io->s2, d.ns, 1, nullptr, nullptr, 0.f,
+                        io->action_high, nullptr, nullptr, w.a2, nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr, st));
+    AVD_TRY(fused3::run(fused3::MODE_TARGET, d, A, R, io->t_critic, co.total, w.tcW2T, w.tc_b2f, io->s2, d.ns, 1, w.a2, io->r, io->gamma, 0.f,
+                        nullptr, nullptr, w.y, nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr, st));
+    // ---- critic loss gradient on (s, a)                                             trainer.py:495-498
+    AVD_TRY(fused3::run(fused3::MODE_CRITIC_BWD, d, A, R, io->critic, co.total, w.cW2T, w.c_b2f, io->s, d.ns, 1, io->a, nullptr, 0.f, 0.f, w.y,
+                        nullptr, w.q, Hc, Fp, w.mask, DZ, Uc, w.sdq, io->loss, st));
+    AVD_TRY(wgrad_ones(Hc, F, io->critic_grad, co.n_train, co.W2));
+    head_unfold(true, io->critic, io->critic_grad, Uc, w.sdq);
+    AVD_LAUNCH_OK();
+    AVD_TRY(p.dgrad_masked(DZ, w.cW2b, F, w.mask, MW, dz1, Fp));
+    AVD_TRY(p.l1_wgrad_unfold(true, io->critic, dz1, F, Fp, w.xext, w.G1, io->critic_grad));
+    // ---- actor loss gradient: -mean(critic(s, actor(s)))                            trainer.py:501-506
+    AVD_TRY(fused3::run(fused3::MODE_ACTOR_OUT, d, A, R, io->actor, ao.total, w.aW2T, w.a_b2f, io->s, d.ns, 1, nullptr, nullptr, 0.f, io->action_high,
+                        nullptr, nullptr, w.a2, nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr, st));   // pi
+    AVD_TRY(fused3::run(fused3::MODE_CRITIC_ACTION, d, A, R, io->critic, co.total, w.cW2T, w.c_b2f, io->s, d.ns, 1, w.a2, nullptr, 0.f, 0.f, nullptr,
+                        nullptr, w.dpi, nullptr, 0, nullptr, nullptr, nullptr, nullptr, io->loss, st));          // d(-mean q)/d pi
+    AVD_TRY(fused3::run(fused3::MODE_ACTOR_BWD, d, A, R, io->actor, ao.total, w.aW2T, w.a_b2f, io->s, d.ns, 1, nullptr, nullptr, 0.f, io->action_high,
+                        nullptr, w.dpi, nullptr, Ha, Fp, w.mask, DZ, Ua, w.sdq + A, nullptr, st));
+    AVD_TRY(wgrad_ones(Ha, d.l1, io->actor_grad, ao.n_train, ao.W2));
+    head_unfold(false, io->actor, io->actor_grad, Ua, w.sdq + A);
+    AVD_LAUNCH_OK();
+    AVD_TRY(p.dgrad_masked(DZ, w.aW2b, d.l1, w.mask, 8, dz1, d.l1));
+    AVD_TRY(p.l1_wgrad_unfold(false, io->actor, dz1, d.l1, d.l1, w.xext, w.G1, io->actor_grad));
+    return apply_local_updates(io, (void*)st);
+}
+
 extern "C" int avd_ddpg_learn(const avd_learn_io* io, void* stream) {
     AVD_REQUIRE(io, "null io");
     AVD_TRY(check_dims(&io->dims, io->precision));
@@ -1143,7 +1252,11 @@ extern "C" int avd_ddpg_learn(const avd_learn_io* io, void* stream) {
     AVD_CUDA_OK(cudaMemsetAsync(io->critic_grad, 0, (size_t)A * co.n_train * sizeof(float), st));
     if (io->loss) AVD_CUDA_OK(cudaMemsetAsync(io->loss, 0, (size_t)A * 2 * sizeof(float), st));
     const bool fz = tc && fused::supported(d, false) && fused::supported(d, true);   // fused layer1 -> tcgen05 -> head kernels
-    if (fz) return learn_fused(io, p, w, st);
+    if (fz) {
+        static int gen = -1;
+        if (gen < 0) { const char* e = getenv("AVD_LEARN_GEN"); gen = (e && e[0] == '2') ? 2 : 3; }   // "2": previous generation (A/B comparisons)
+        return (gen == 3 && fused3::supported(d)) ? learn_fused3(io, p, w, st) : learn_fused(io, p, w, st);
+    }
     if (tc) {   // bf16 copies of the four layer-2 kernels (K-major for forward, and for dgrad on the online nets)
         AVD_TRY(p.pack(io->t_actor, ao.total, ao.W2, d.l1, nullptr, w.taW2T));
         AVD_TRY(p.pack(io->t_critic, co.total, co.W2, F, nullptr, w.tcW2T));

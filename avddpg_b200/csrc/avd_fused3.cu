@@ -1,0 +1,629 @@
+// avd_fused3.cu -- one persistent kernel per network pass of the DDPG learn step (sm_100a): layer 1, layer 2, head and --
+// for the passes that are differentiated -- the head backward, all on one 128-row tile at a time without HBM round trips.
+//
+//   x (4 state words [+ action])  --tcgen05.mma, hi/lo-split bf16, K = 16-->  z1 (TMEM)
+//   --consumer warps-->  r1 = relu(z1) as bf16 into the 128B-swizzled K-major A tile (+ sign bits for the ReLU backward)
+//   --tcgen05.mma against the BN-folded W2'^T (resident in shared memory)-->  z2 (TMEM, double buffered)
+//   --pass 1-->  q = relu(z2 + b2') . w3' + b3'       (row sum split over four warps, combined through shared memory)
+//   --pass 2 (backward modes)-->  dq from the loss, dz2 = dq w3' [z2 + b2' > 0] as bf16 into a shared-memory tile,
+//        per-thread partial sums of  U[j] = sum_n dq_n relu(z2)[n][j]  (head / BN2 weight gradients),  sum dq,  loss
+//   --TMA stores-->  r1 and dz2 tiles to HBM for the weight-gradient GEMMs (avd_umma.cu) and the dgrad GEMM
+//   MODE_CRITIC_ACTION additionally runs the action columns of the dgrad as a third MMA (dz2 . W2'[action rows]^T) and
+//   reduces it to d(-mean q)/d(action) per row -- the critic -> actor link (trainer.py:503-506) never leaves the SM.
+//
+// BatchNorm folding (inference affine):  W2' = diag(sc1) W2,  b2' = b2 + sh1 W2  (pack_fold_kernel);
+// w3' = sc2 * w3,  b3' = b3 + sh2 . w3  (table set-up below).  One CTA works on ONE agent: weights and
+// tables are loaded once.  17 warps: warp 0 issues TMA / MMA, warps 1..16 are identical consumers (TMEM lane quadrant =
+// warp % 4, column quarter = (warp - 1) / 4) running a software pipeline  pass2(i-1) | convert(i+1) | pass1(i)  so that
+// every MMA has a full stage of other work to hide behind.
+// Reference semantics: agent/model.py:19-37 (actor), 55-83 (critic); workers/trainer.py:489-506.
+#include <cudaTypedefs.h>
+
+#include <algorithm>
+
+#include "avd_common.cuh"
+#include "avd_ddpg_layout.cuh"
+#include "avd_umma.cuh"
+
+namespace avd {
+namespace fused3 {
+
+using namespace umma;
+typedef __nv_bfloat16 bf16;
+
+constexpr int TILE_M = 128, L2N = 128, KB = 64, MAX_KB = 5, L1N = 256;
+constexpr int NCONS = 16;
+constexpr int NUM_THREADS = 32 * (1 + NCONS);
+constexpr int SLOT_BYTES = TILE_M * KB * 2;                  // 16 KB
+constexpr int OFF_RING = 0;                                  // r1 k-blocks of the current tile (slot = k-block)
+constexpr int OFF_W = OFF_RING + MAX_KB * SLOT_BYTES;        // W2'^T k-blocks
+constexpr int OFF_DZ = OFF_W + MAX_KB * SLOT_BYTES;          // dz2 tile: 2 k-blocks
+constexpr int OFF_B1 = OFF_DZ + 2 * SLOT_BYTES;              // W1ext, no-swizzle K-major [2 chunks][256 rows][16 B]
+constexpr int B1_BYTES = 2 * L1N * 16;
+constexpr int OFF_X = OFF_B1 + B1_BYTES;                     // 2 input tiles [2 chunks][128 rows][16 B]
+constexpr int X_BYTES = 2 * TILE_M * 16;
+constexpr int OFF_TAB = OFF_X + 2 * X_BYTES;                 // b2f[128] w3f[128] wa[64] ba[64] scal[8]
+constexpr int TAB_BYTES = 2048;
+constexpr int OFF_PART = OFF_TAB + TAB_BYTES;                // [2 buffers][4 quarters][128 rows] partial row sums
+constexpr int OFF_BAR = OFF_PART + 2 * 4 * TILE_M * 4;
+constexpr int SMEM_BYTES = OFF_BAR + 512 + 1024;
+static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB shared memory of an sm_100 CTA");
+
+enum Mode { MODE_ACTOR_OUT = 0, MODE_TARGET = 1, MODE_Q = 2, MODE_CRITIC_BWD = 3, MODE_ACTOR_BWD = 4, MODE_CRITIC_ACTION = 5 };
+
+struct Args {
+    avd_net_dims d;
+    int A;
+    int64_t R;
+    const float* params;        // [A][pstride]
+    int64_t pstride;
+    const float* b2f;           // [A][128] folded layer-2 bias
+    const float* s;             // element (n, k) at s[n*s_rs + k*s_cs]
+    int64_t s_rs, s_cs;
+    const float* act;           // [A*R] critic passes
+    const float* rew;           // MODE_TARGET
+    float gamma, high;
+    const float* y;             // MODE_CRITIC_BWD: TD targets
+    const float* dpi;           // MODE_ACTOR_BWD: d loss / d action
+    float* out;                 // forward modes: [A*R]; MODE_CRITIC_ACTION: d loss / d action; MODE_CRITIC_BWD: q (nullable)
+    uint32_t* mask_out;         // backward modes: [A*R][mask_words] sign bits of z1 (column j of word w at bit 31-j)
+    int mask_words;
+    float* U;                   // backward modes: [A][128]  += sum_n dq_n relu(z2 + b2')[n][j]
+    float* sdq;                 // backward modes: [A]       += sum_n dq_n
+    float* loss;                // nullable; element 2*agent (+1 for the actor loss)
+    int tiles_per_agent, ctas_per_agent;
+};
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ uint64_t make_desc_noswz(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void split_bf16(float v, bf16& hi, bf16& lo) {
+    hi = __float2bfloat16_rn(v);
+    lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+__device__ __forceinline__ uint32_t pack2(bf16 a, bf16 b) {
+    return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(NUM_THREADS, 1) fused3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmR,
+                                                                const __grid_constant__ CUtensorMap tmDZ, Args g) {
+    constexpr bool CRITIC = MODE != MODE_ACTOR_OUT && MODE != MODE_ACTOR_BWD;
+    constexpr bool BWD = MODE == MODE_CRITIC_BWD || MODE == MODE_ACTOR_BWD;      // full backward: masks, r1 / dz2 to HBM, U
+    constexpr bool ACTION = MODE == MODE_CRITIC_ACTION;                          // backward to the action input only
+    constexpr bool HAS_DZ = BWD || ACTION;
+    constexpr int NKB = CRITIC ? 5 : 4;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    float* b2f_tab = reinterpret_cast<float*>(smem + OFF_TAB);
+    float* w3f_tab = b2f_tab + L2N;
+    float* wa_tab = w3f_tab + L2N;
+    float* ba_tab = wa_tab + 64;
+    float* scal = ba_tab + 64;                                   // [1..4] partial sums of sh2 . w3, [5] = b3
+    float* part = reinterpret_cast<float*>(smem + OFF_PART);
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + OFF_BAR);   // [5]
+    uint64_t* a_empty = a_full + MAX_KB;                              // [5]
+    uint64_t* acc_full = a_empty + MAX_KB;                            // [2]
+    uint64_t* acc_empty = acc_full + 2;                               // [2]
+    uint64_t* part_full = acc_empty + 2;                              // [2]
+    uint64_t* x_full = part_full + 2;                                 // [2]
+    uint64_t* z1_full = x_full + 2;
+    uint64_t* z1_empty = z1_full + 1;
+    uint64_t* dz_full = z1_empty + 1;
+    uint64_t* dz_empty = dz_full + 1;
+    uint64_t* dra_full = dz_empty + 1;
+    uint64_t* dra_empty = dra_full + 1;
+    uint64_t* w_full = dra_empty + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const avd_net_dims d = g.d;
+    const int la = CRITIC ? d.la : 0;
+    const int agent = (int)blockIdx.x / g.ctas_per_agent;
+    const int cta = (int)blockIdx.x - agent * g.ctas_per_agent;
+    const int T = (g.tiles_per_agent - cta + g.ctas_per_agent - 1) / g.ctas_per_agent;   // tiles of this CTA: cta, cta + ctas_per_agent, ...
+    const float* P = g.params + (int64_t)agent * g.pstride;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmW);
+        if (BWD) { tma_prefetch_desc(&tmR); tma_prefetch_desc(&tmDZ); }
+        for (int i = 0; i < MAX_KB; ++i) { mbar_init(&a_full[i], i < 4 ? 4 : 8); mbar_init(&a_empty[i], BWD ? 2 : 1); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], NCONS);
+            mbar_init(&part_full[i], NCONS); mbar_init(&x_full[i], 4);
+        }
+        mbar_init(z1_full, 1); mbar_init(z1_empty, NCONS);
+        mbar_init(dz_full, NCONS); mbar_init(dz_empty, 1);
+        mbar_init(dra_full, 1); mbar_init(dra_empty, 4);
+        mbar_init(w_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(tmem_slot, 512);
+
+    // ---- per-agent tables and the extended layer-1 weight tile (built once: one CTA = one agent)
+    if (warp >= 1) {
+        const int ct = threadIdx.x - 32;     // 0..511
+        int64_t oW, ob, og2, obe2, omu2, ovar2, oW3, ob3;
+        if (CRITIC) { const CriticOff o = critic_off(d); oW = o.Ws; ob = o.bs; og2 = o.g2; obe2 = o.be2; omu2 = o.mu2; ovar2 = o.var2; oW3 = o.W3; ob3 = o.b3; }
+        else { const ActorOff o = actor_off(d); oW = o.W1; ob = o.b1; og2 = o.g2; obe2 = o.be2; omu2 = o.mu2; ovar2 = o.var2; oW3 = o.W3; ob3 = o.b3; }
+        if (ct < L1N) {   // W1ext row of layer-1 output column ct:  [W_hi b_hi | W_hi b_hi | W_lo b_lo | 0]  (K = 16)
+            bf16 whi[4], wlo[4], bhi, blo;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) split_bf16(k < d.ns ? P[oW + (int64_t)k * d.l1 + ct] : 0.0f, whi[k], wlo[k]);
+            split_bf16(P[ob + ct], bhi, blo);
+            const bf16 zero = __float2bfloat16_rn(0.0f);
+            const uint4 c0 = make_uint4(pack2(whi[0], whi[1]), pack2(whi[2], whi[3]), pack2(bhi, whi[0]), pack2(whi[1], whi[2]));
+            const uint4 c1 = make_uint4(pack2(whi[3], bhi), pack2(wlo[0], wlo[1]), pack2(wlo[2], wlo[3]), pack2(blo, zero));
+            *reinterpret_cast<uint4*>(smem + OFF_B1 + ct * 16) = c0;
+            *reinterpret_cast<uint4*>(smem + OFF_B1 + L1N * 16 + ct * 16) = c1;
+        } else if (ct < L1N + L2N) {
+            const int c = ct - L1N;
+            const float sc2 = P[og2 + c] / sqrtf(P[ovar2 + c] + kBnEps);
+            const float sh2 = P[obe2 + c] - P[omu2 + c] * sc2;
+            const float w3 = P[oW3 + c];
+            b2f_tab[c] = g.b2f[(int64_t)agent * L2N + c];
+            w3f_tab[c] = w3 * sc2;
+            const float t = warp_sum(sh2 * w3);                  // four full warps hold the 128 columns
+            if (lane == 0) scal[1 + (c >> 5)] = t;
+            if (c == 0) scal[5] = P[ob3];
+        } else if (ct < L1N + L2N + 64) {
+            const int c = ct - L1N - L2N;
+            float wa = 0.f, ba = 0.f;
+            if (CRITIC && c < d.la) { const CriticOff o = critic_off(d); wa = P[o.Wa + c]; ba = P[o.ba + c]; }
+            wa_tab[c] = wa;
+            ba_tab[c] = ba;
+        }
+        fence_proxy_async();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const float b3f = scal[5] + scal[1] + scal[2] + scal[3] + scal[4];       // b3' = b3 + sh2 . w3
+    if (T <= 0) {   // never happens with the host-side grid; keep the TMEM bookkeeping correct anyway
+        __syncthreads();
+        if (warp == 0) tmem_dealloc(tmem_base, 512);
+        return;
+    }
+
+    auto tile_of = [&](int tc) { return cta + tc * g.ctas_per_agent; };
+
+    if (warp == 0) {
+        // ============================================ TMA / MMA issuer ============================================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(TILE_M, L2N, false, false);
+            constexpr uint32_t idesc_act = make_idesc_bf16(TILE_M, 64, false, true);      // dz2 (K-major) x W2'^T block (MN-major)
+            const uint32_t w_addr = smem_u32(smem + OFF_W);
+            const uint32_t b1_addr = smem_u32(smem + OFF_B1);
+            const uint32_t x_addr = smem_u32(smem + OFF_X);
+            const uint32_t dz_addr = smem_u32(smem + OFF_DZ);
+            const int F = L1N + la;
+            mbar_expect_tx(w_full, (uint32_t)NKB * SLOT_BYTES);
+            for (int kb = 0; kb < NKB; ++kb) tma_load_3d(smem + OFF_W + kb * SLOT_BYTES, &tmW, w_full, kb * KB, 0, agent);
+
+            auto mma1 = [&](int t) {          // layer 1 of local tile t -> TMEM columns [256, 512)
+                mbar_wait(&x_full[t & 1], ((uint32_t)t >> 1) & 1);
+                if (t >= 1) mbar_wait(z1_empty, (uint32_t)(t - 1) & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+                    mma_bf16(tmem_base + 256u + (uint32_t)(h * L2N), make_desc_noswz(x_addr + (t & 1) * X_BYTES, TILE_M * 16, 128),
+                             make_desc_noswz(b1_addr + h * (L2N * 16), L1N * 16, 128), idesc, 0);
+                mma_commit(z1_full);
+            };
+            auto mma2 = [&](int t) {          // layer 2 of local tile t -> TMEM accumulator t & 1
+                mbar_wait(&acc_empty[t & 1], (((uint32_t)t >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t tacc = tmem_base + (uint32_t)((t & 1) * L2N);
+                for (int kb = 0; kb < NKB; ++kb) {
+                    mbar_wait(&a_full[kb], (uint32_t)t & 1);
+                    tc_fence_after();
+                    if (BWD) tma_store_3d(&tmR, smem + OFF_RING + kb * SLOT_BYTES, kb * KB, tile_of(t) * TILE_M, agent);
+                    const uint32_t a_addr = smem_u32(smem + OFF_RING + kb * SLOT_BYTES);
+                    const int nm = min(4, (F - kb * KB) / 16);
+                    for (int j = 0; j < nm; ++j)
+                        mma_bf16(tacc, make_smem_desc(a_addr + j * 32, 16, 1024), make_smem_desc(w_addr + kb * SLOT_BYTES + j * 32, 16, 1024), idesc,
+                                 (kb | j) != 0);
+                    mma_commit(&a_empty[kb]);
+                }
+                mma_commit(&acc_full[t & 1]);
+                if (BWD) {                    // the r1 slots are also free only once the TMA stores have read them
+                    bulk_commit();
+                    bulk_wait_read0();
+                    for (int kb = 0; kb < NKB; ++kb) mbar_arrive(&a_empty[kb]);
+                }
+            };
+            auto dz_out = [&](int t) {        // dz2 tile of local tile t: to HBM (BWD) or through the action-column dgrad MMA (ACTION)
+                mbar_wait(dz_full, (uint32_t)t & 1);
+                tc_fence_after();
+                if (BWD) {
+                    tma_store_3d(&tmDZ, smem + OFF_DZ, 0, tile_of(t) * TILE_M, agent);
+                    tma_store_3d(&tmDZ, smem + OFF_DZ + SLOT_BYTES, KB, tile_of(t) * TILE_M, agent);
+                    bulk_commit();
+                    bulk_wait_read0();
+                    mbar_arrive(dz_empty);
+                } else {
+                    if (t + 2 < T) mbar_wait(z1_empty, (uint32_t)(t + 2) & 1);     // convert(t + 2) has drained the z1 columns
+                    tc_fence_after();
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks)
+                        mma_bf16(tmem_base + 256u, make_smem_desc(dz_addr + (ks >> 2) * SLOT_BYTES + (ks & 3) * 32, 16, 1024),
+                                 make_smem_desc(w_addr + 4 * SLOT_BYTES + ks * 2048, 16, 1024), idesc_act, ks != 0);
+                    mma_commit(dra_full);
+                    mma_commit(dz_empty);
+                }
+            };
+
+            mbar_wait(w_full, 0);
+            mma1(0);
+            mma2(0);
+            if (T > 1) mma1(1);
+            for (int i = 0; i < T; ++i) {
+                if (BWD && i >= 1) dz_out(i - 1);
+                if (i + 1 < T) mma2(i + 1);
+                if (ACTION && i >= 1) dz_out(i - 1);
+                if (i + 2 < T) {
+                    if (ACTION && i >= 1) mbar_wait(dra_empty, (uint32_t)(i - 1) & 1);
+                    mma1(i + 2);
+                }
+            }
+            if (HAS_DZ) dz_out(T - 1);
+        }
+    } else {
+        // ================================================ consumers ================================================
+        const int cw = warp - 1;
+        const int q = warp & 3;              // TMEM lane quadrant of this warp
+        const int c4 = cw >> 2;              // column quarter: z1 columns [64 c4, +64), z2 columns [32 c4, +32)
+        const int row = q * 32 + lane;
+        const uint32_t tlane = (uint32_t)(q * 32) << 16;
+        const float invR = 1.0f / (float)g.R;
+        float u[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) u[j] = 0.0f;
+        float sdq_acc = 0.0f, loss_acc = 0.0f;
+
+        auto rowinfo = [&](int tc, bool& valid) -> int64_t {
+            const int64_t r_in = (int64_t)tile_of(tc) * TILE_M + row;
+            valid = r_in < g.R;
+            return (int64_t)agent * g.R + (valid ? r_in : g.R - 1);
+        };
+        // hi/lo-split input row of local tile t -> X buffer t & 1:  [v_hi(5) v_lo(5) v_hi(5) 0],  v = (s0..s3, 1)
+        auto produce_x = [&](int t) {
+            bool valid;
+            const int64_t n = rowinfo(t, valid);
+            bf16 hi[5], lo[5];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) split_bf16(k < d.ns ? __ldg(g.s + n * g.s_rs + k * g.s_cs) : 0.0f, hi[k], lo[k]);
+            hi[4] = __float2bfloat16_rn(1.0f);
+            lo[4] = __float2bfloat16_rn(0.0f);
+            uint8_t* xbase = smem + OFF_X + (t & 1) * X_BYTES;
+            *reinterpret_cast<uint4*>(xbase + row * 16) = make_uint4(pack2(hi[0], hi[1]), pack2(hi[2], hi[3]), pack2(hi[4], lo[0]), pack2(lo[1], lo[2]));
+            *reinterpret_cast<uint4*>(xbase + TILE_M * 16 + row * 16) =
+                make_uint4(pack2(lo[3], lo[4]), pack2(hi[0], hi[1]), pack2(hi[2], hi[3]), pack2(hi[4], lo[4]));
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&x_full[t & 1]);
+        };
+
+        // ---- stage 1: z1 -> relu -> bf16 A tile (+ sign masks), action-branch columns, next input tile
+        auto convert = [&](int tc) {
+            bool valid;
+            const int64_t nrow = rowinfo(tc, valid);
+            const int ga0 = CRITIC ? 2 * (tc & 1) : -1;          // quarter that converts action columns 0..31; ga0 + 1: columns 32..la-1
+            const int xg = CRITIC ? 2 * (1 - (tc & 1)) : (tc & 3);   // quarter that stages the input tile of local tile tc + 2
+            float a_val = 0.0f;
+            if (CRITIC && (c4 == ga0 || c4 == ga0 + 1)) a_val = __ldg(g.act + nrow);
+            mbar_wait(z1_full, (uint32_t)tc & 1);
+            tc_fence_after();
+            mbar_wait(&a_empty[c4], ((uint32_t)tc & 1) ^ 1);
+            uint8_t* slot = smem + OFF_RING + c4 * SLOT_BYTES + row * 128;
+            uint32_t neg[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                float z[32];
+                tmem_ld32(tmem_base + 256u + (uint32_t)(c4 * 64 + h * 32) + tlane, z);
+                uint32_t m = 0;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    m = __funnelshift_l(__float_as_uint(z[j]), m, 1);
+                    z[j] = fmaxf(z[j], 0.0f);
+                }
+                neg[h] = m;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint4 pk = make_uint4(pack_bf16x2(z[8 * k], z[8 * k + 1]), pack_bf16x2(z[8 * k + 2], z[8 * k + 3]),
+                                                pack_bf16x2(z[8 * k + 4], z[8 * k + 5]), pack_bf16x2(z[8 * k + 6], z[8 * k + 7]));
+                    *reinterpret_cast<uint4*>(slot + (((h * 4 + k) ^ (row & 7)) << 4)) = pk;      // SWIZZLE_128B
+                }
+            }
+            tc_fence_before();
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(z1_empty); mbar_arrive(&a_full[c4]); }
+            if (BWD && valid) *reinterpret_cast<uint2*>(g.mask_out + nrow * g.mask_words + 2 * c4) = make_uint2(neg[0], neg[1]);
+            if (CRITIC && (c4 == ga0 || c4 == ga0 + 1)) {        // action branch: one input per column, CUDA cores
+                const int j0 = (c4 == ga0) ? 0 : 32;
+                mbar_wait(&a_empty[4], ((uint32_t)tc & 1) ^ 1);
+                uint8_t* aslot = smem + OFF_RING + 4 * SLOT_BYTES + row * 128;
+                float z[32];
+                uint32_t m = 0;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float zz = fmaf(a_val, wa_tab[j0 + j], ba_tab[j0 + j]);
+                    m = __funnelshift_l(__float_as_uint(zz), m, 1);
+                    z[j] = fmaxf(zz, 0.0f);
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (j0 + 8 * k < la) {
+                        const uint4 pk = make_uint4(pack_bf16x2(z[8 * k], z[8 * k + 1]), pack_bf16x2(z[8 * k + 2], z[8 * k + 3]),
+                                                    pack_bf16x2(z[8 * k + 4], z[8 * k + 5]), pack_bf16x2(z[8 * k + 6], z[8 * k + 7]));
+                        *reinterpret_cast<uint4*>(aslot + (((j0 / 8 + k) ^ (row & 7)) << 4)) = pk;
+                    }
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&a_full[4]);
+                if (BWD && valid) g.mask_out[nrow * g.mask_words + 8 + (j0 >> 5)] = m;
+            }
+            if (c4 == xg && tc + 2 < T) produce_x(tc + 2);       // X buffer tc & 1 is free: z1_full(tc) implies the layer-1 MMA has read it
+        };
+
+        // ---- stage 2: partial row sums of the head over this warp's 32 z2 columns
+        auto pass1 = [&](int tc) {
+            const int buf = tc & 1;
+            mbar_wait(&acc_full[buf], ((uint32_t)tc >> 1) & 1);
+            tc_fence_after();
+            float v[32];
+            tmem_ld32(tmem_base + (uint32_t)(buf * L2N + c4 * 32) + tlane, v);
+            float acc = 0.0f;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                const float4 b4 = *reinterpret_cast<const float4*>(b2f_tab + c4 * 32 + j);
+                const float4 w4 = *reinterpret_cast<const float4*>(w3f_tab + c4 * 32 + j);
+                acc = fmaf(fmaxf(v[j] + b4.x, 0.0f), w4.x, acc);
+                acc = fmaf(fmaxf(v[j + 1] + b4.y, 0.0f), w4.y, acc);
+                acc = fmaf(fmaxf(v[j + 2] + b4.z, 0.0f), w4.z, acc);
+                acc = fmaf(fmaxf(v[j + 3] + b4.w, 0.0f), w4.w, acc);
+            }
+            part[(buf * 4 + c4) * TILE_M + row] = acc;
+            if (!HAS_DZ) tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if (!HAS_DZ) mbar_arrive(&acc_empty[buf]);       // forward modes are done with the accumulator
+                mbar_arrive(&part_full[buf]);
+            }
+        };
+
+        // ---- stage 3: combine the row sums; outputs; backward modes: dq, dz2 tile, U / loss accumulation
+        auto pass2 = [&](int tc) {
+            const int buf = tc & 1;
+            if (!HAS_DZ && c4 != 0) return;
+            bool valid;
+            const int64_t nrow = rowinfo(tc, valid);
+            float yv = 0.0f;
+            if (MODE == MODE_TARGET) yv = __ldg(g.rew + nrow);
+            if (MODE == MODE_CRITIC_BWD) yv = __ldg(g.y + nrow);
+            if (MODE == MODE_ACTOR_BWD) yv = __ldg(g.dpi + nrow);
+            mbar_wait(&part_full[buf], ((uint32_t)tc >> 1) & 1);
+            const float* pb = part + buf * 4 * TILE_M + row;
+            const float qv = pb[0] + pb[TILE_M] + pb[2 * TILE_M] + pb[3 * TILE_M] + b3f;
+            if (!HAS_DZ) {
+                float o;
+                if (MODE == MODE_ACTOR_OUT) o = g.high * tanhf(qv);
+                else if (MODE == MODE_TARGET) o = yv + g.gamma * qv;                 // trainer.py:494 (no terminal mask)
+                else o = qv;
+                if (valid) g.out[nrow] = o;
+                return;
+            }
+            float dq;
+            if (MODE == MODE_CRITIC_BWD) {
+                const float diff = qv - yv;
+                dq = valid ? 2.0f * diff * invR : 0.0f;                              // d mean((y-q)^2) / dq      trainer.py:496
+                if (c4 == 0) {
+                    if (valid) loss_acc = fmaf(diff, diff * invR, loss_acc);
+                    if (valid && g.out) g.out[nrow] = qv;
+                }
+            } else if (MODE == MODE_ACTOR_BWD) {
+                const float t = tanhf(qv);
+                dq = valid ? yv * g.high * (1.0f - t * t) : 0.0f;                    // through high * tanh(.)    model.py:36-37
+            } else {
+                dq = valid ? -invR : 0.0f;                                           // d(-mean q) / dq          trainer.py:504
+                if (c4 == 0 && valid) loss_acc -= qv * invR;
+            }
+            if (c4 == 0) sdq_acc += dq;
+            float v[32];
+            tmem_ld32(tmem_base + (uint32_t)(buf * L2N + c4 * 32) + tlane, v);
+            tc_fence_before();
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                const float4 b4 = *reinterpret_cast<const float4*>(b2f_tab + c4 * 32 + j);
+                const float4 w4 = *reinterpret_cast<const float4*>(w3f_tab + c4 * 32 + j);
+                const float bb[4] = {b4.x, b4.y, b4.z, b4.w}, ww[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float t = v[j + k] + bb[k];
+                    const float e = t > 0.0f ? dq : 0.0f;
+                    if (BWD) u[j + k] = fmaf(e, t, u[j + k]);
+                    v[j + k] = e * ww[k];
+                }
+            }
+            mbar_wait(dz_empty, ((uint32_t)tc & 1) ^ 1);
+            uint8_t* dzrow = smem + OFF_DZ + (c4 >> 1) * SLOT_BYTES + row * 128;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint4 pk = make_uint4(pack_bf16x2(v[8 * k], v[8 * k + 1]), pack_bf16x2(v[8 * k + 2], v[8 * k + 3]),
+                                            pack_bf16x2(v[8 * k + 4], v[8 * k + 5]), pack_bf16x2(v[8 * k + 6], v[8 * k + 7]));
+                *reinterpret_cast<uint4*>(dzrow + ((((c4 & 1) * 4 + k) ^ (row & 7)) << 4)) = pk;
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(&acc_empty[buf]); mbar_arrive(dz_full); }
+        };
+
+        // ---- stage 4 (MODE_CRITIC_ACTION): d loss / d action = sum_f [za_f > 0] dRa_f wa_f      (trainer.py:503-506)
+        auto action_grad = [&](int tc) {
+            if (c4 != (tc & 3)) return;
+            bool valid;
+            const int64_t nrow = rowinfo(tc, valid);
+            const float a_val = __ldg(g.act + nrow);
+            mbar_wait(dra_full, (uint32_t)tc & 1);
+            tc_fence_after();
+            float acc = 0.0f;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                if (h * 32 < la) {
+                    float v[32];
+                    tmem_ld32(tmem_base + 256u + (uint32_t)(h * 32) + tlane, v);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float w = wa_tab[h * 32 + j];                          // zero beyond la
+                        const float zz = fmaf(a_val, w, ba_tab[h * 32 + j]);
+                        acc = fmaf(zz > 0.0f ? v[j] : 0.0f, w, acc);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(dra_empty);
+            if (valid) g.out[nrow] = acc;
+        };
+
+        // ---- software pipeline
+        if (cw < 4) produce_x(0);
+        else if (cw < 8 && T > 1) produce_x(1);
+        convert(0);
+        for (int i = 0; i < T; ++i) {
+            if (i >= 1) pass2(i - 1);
+            if (i + 1 < T) convert(i + 1);
+            pass1(i);
+            if (ACTION && i >= 1) action_grad(i - 1);
+        }
+        pass2(T - 1);
+        if (ACTION) action_grad(T - 1);
+
+        // ---- flush the per-thread partial sums of this CTA
+        if (BWD) {
+            float keep = 0.0f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const float sj = warp_sum(u[j]);
+                if (lane == j) keep = sj;
+            }
+            atomicAdd(g.U + (int64_t)agent * L2N + c4 * 32 + lane, keep);
+        }
+        if (HAS_DZ && c4 == 0) {
+            const float sl = warp_sum(loss_acc), sd = warp_sum(sdq_acc);
+            if (lane == 0) {
+                if (g.loss && MODE != MODE_ACTOR_BWD) atomicAdd(g.loss + 2 * agent + (MODE == MODE_CRITIC_BWD ? 0 : 1), sl);
+                if (BWD) atomicAdd(g.sdq + agent, sd);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+static PFN_cuTensorMapEncodeTiled encode_fn() {
+    static PFN_cuTensorMapEncodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(p);
+    }
+    return fn;
+}
+
+// 3-D bf16 map {inner, rows, batch}, box {64, 128, 1}, 128-byte swizzle
+static int make_map(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t rows, uint64_t batch, uint64_t pitch, uint64_t batch_stride) {
+    PFN_cuTensorMapEncodeTiled enc = encode_fn();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled is not available from the driver");
+        return AVD_ERR_CUDA;
+    }
+    cuuint64_t dims[3] = {inner, rows, batch};
+    cuuint64_t strides[2] = {pitch * 2, batch_stride * 2};
+    cuuint32_t box[3] = {KB, TILE_M, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with %d (inner=%llu rows=%llu batch=%llu pitch=%llu)", (int)r, (unsigned long long)inner,
+                  (unsigned long long)rows, (unsigned long long)batch, (unsigned long long)pitch);
+        return AVD_ERR_CUDA;
+    }
+    return AVD_OK;
+}
+
+bool supported(const avd_net_dims& d) {
+    return d.l2 == L2N && d.ns >= 1 && d.ns <= 4 && d.l1 == L1N && d.la % 16 == 0 && d.la >= 16 && d.la <= 64;
+}
+
+template <int MODE>
+static int launch(const CUtensorMap& tmW, const CUtensorMap& tmR, const CUtensorMap& tmDZ, const Args& g, dim3 grid, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        AVD_CUDA_OK(cudaFuncSetAttribute(fused3_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        attr_set = true;
+    }
+    fused3_kernel<MODE><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmW, tmR, tmDZ, g);
+    AVD_LAUNCH_OK();
+    return AVD_OK;
+}
+
+// One pass.  W2T: bf16 [A][128][F] folded layer-2 kernel (K-major), b2f: [A][128]  (pack_fold_kernel).
+// R1_out: bf16 [A*R][r1_pitch] (backward modes; columns >= F are left untouched), DZ_out: bf16 [A*R][128] (backward modes).
+int run(int mode, const avd_net_dims& d, int A, int64_t R, const float* params, int64_t pstride, const bf16* W2T, const float* b2f, const float* s,
+        int64_t s_rs, int64_t s_cs, const float* act, const float* rew, float gamma, float high, const float* y, const float* dpi, float* out,
+        bf16* R1_out, int64_t r1_pitch, uint32_t* mask_out, bf16* DZ_out, float* U, float* sdq, float* loss, cudaStream_t st) {
+    if (!supported(d)) {
+        set_error("fused pass kernel does not support these layer sizes");
+        return AVD_ERR_UNSUPPORTED;
+    }
+    const bool critic = mode != MODE_ACTOR_OUT && mode != MODE_ACTOR_BWD;
+    const bool bwd = mode == MODE_CRITIC_BWD || mode == MODE_ACTOR_BWD;
+    const int F = critic ? d.l1 + d.la : d.l1;
+    AVD_REQUIRE(params && W2T && b2f && s, "null buffer");
+    AVD_REQUIRE(!critic || act, "critic passes need actions");
+    AVD_REQUIRE(!bwd || (R1_out && mask_out && DZ_out && U && sdq && r1_pitch >= F && r1_pitch % 8 == 0), "backward passes need r1 / mask / dz2 / U / sdq outputs");
+    AVD_REQUIRE(bwd || out, "null output");
+    CUtensorMap tmW, tmR, tmDZ;
+    if (int rc = make_map(&tmW, W2T, (uint64_t)F, L2N, (uint64_t)A, (uint64_t)F, (uint64_t)F * L2N)) return rc;
+    tmR = tmW;
+    tmDZ = tmW;
+    if (bwd) {
+        if (int rc = make_map(&tmR, R1_out, (uint64_t)F, (uint64_t)R, (uint64_t)A, (uint64_t)r1_pitch, (uint64_t)R * r1_pitch)) return rc;
+        if (int rc = make_map(&tmDZ, DZ_out, L2N, (uint64_t)R, (uint64_t)A, L2N, (uint64_t)R * L2N)) return rc;
+    }
+    Args g;
+    g.d = d; g.A = A; g.R = R; g.params = params; g.pstride = pstride; g.b2f = b2f; g.s = s; g.s_rs = s_rs; g.s_cs = s_cs; g.act = act;
+    g.rew = rew; g.gamma = gamma; g.high = high; g.y = y; g.dpi = dpi; g.out = out; g.mask_out = mask_out; g.mask_words = 2 * ((F + KB - 1) / KB);
+    g.U = U; g.sdq = sdq; g.loss = loss;
+    g.tiles_per_agent = (int)((R + TILE_M - 1) / TILE_M);
+    g.ctas_per_agent = std::max(1, std::min(g.tiles_per_agent, sm_count() / std::max(1, A)));
+    const dim3 grid((unsigned)(g.ctas_per_agent * A));
+    switch (mode) {
+        case MODE_ACTOR_OUT: return launch<MODE_ACTOR_OUT>(tmW, tmR, tmDZ, g, grid, st);
+        case MODE_TARGET: return launch<MODE_TARGET>(tmW, tmR, tmDZ, g, grid, st);
+        case MODE_Q: return launch<MODE_Q>(tmW, tmR, tmDZ, g, grid, st);
+        case MODE_CRITIC_BWD: return launch<MODE_CRITIC_BWD>(tmW, tmR, tmDZ, g, grid, st);
+        case MODE_ACTOR_BWD: return launch<MODE_ACTOR_BWD>(tmW, tmR, tmDZ, g, grid, st);
+        case MODE_CRITIC_ACTION: return launch<MODE_CRITIC_ACTION>(tmW, tmR, tmDZ, g, grid, st);
+    }
+    set_error("unknown fused pass mode %d", mode);
+    return AVD_ERR_INVALID_ARG;
+}
+
+}  // namespace fused3
+}  // namespace avd
