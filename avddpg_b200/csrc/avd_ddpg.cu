@@ -45,6 +45,11 @@ int run(int mode, const avd_net_dims& d, int A, int64_t R, const float* params, 
         bf16* R1_out, int64_t r1_pitch, uint32_t* mask_out, bf16* DZ_out, float* U, float* sdq, float* loss, cudaStream_t st);
 }
 
+namespace dgrad3 {  // avd_dgrad3.cu
+int run(int A, int64_t R, int F, const bf16* DZ, const bf16* W2b, const uint32_t* mask, int mask_words, const bf16* xextT, int64_t Rp, float* G1,
+        int Fp, cudaStream_t st);
+}
+
 namespace umma {   // avd_umma.cu
 int gemm_bf16(int layout, int batch, int M, int N, int K, const void* A, int64_t lda, int64_t a_batch, const void* B, int64_t ldb,
               int64_t b_batch, float* C, int64_t ldc, int64_t c_batch, int splitk, cudaStream_t st, const ReluMaskEpilogue* rm = nullptr);
@@ -603,7 +608,8 @@ __global__ void __launch_bounds__(256) pack_fold_kernel(const float* __restrict_
 // `col`): the weight-gradient GEMM  [r1 | 1]^T dz2  then yields db2 as row F of its output, which is where b2 follows W2.
 __global__ void __launch_bounds__(256) xext_kernel(const float* __restrict__ s, const float* __restrict__ a, int ns, int64_t N,
                                                    bf16* __restrict__ xext, bf16* __restrict__ ones_c, int64_t pitch_c, int col_c,
-                                                   bf16* __restrict__ ones_a, int64_t pitch_a, int col_a) {
+                                                   bf16* __restrict__ ones_a, int64_t pitch_a, int col_a, bf16* __restrict__ xextT, int64_t R,
+                                                   int64_t Rp) {
     const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N) return;
     if (ones_c) ones_c[n * pitch_c + col_c] = __float2bfloat16_rn(1.0f);
@@ -629,9 +635,20 @@ __global__ void __launch_bounds__(256) xext_kernel(const float* __restrict__ s, 
     l4.y = (uint32_t)__bfloat16_as_ushort(lo[2]) | ((uint32_t)__bfloat16_as_ushort(lo[3]) << 16);
     l4.z = (uint32_t)__bfloat16_as_ushort(lo[4]);
     l4.w = 0;
-    uint4* dst = reinterpret_cast<uint4*>(xext + n * 16);
-    dst[0] = h4;
-    dst[1] = l4;
+    if (xext) {
+        uint4* dst = reinterpret_cast<uint4*>(xext + n * 16);
+        dst[0] = h4;
+        dst[1] = l4;
+    }
+    if (xextT) {   // transposed copy [A][16][Rp] for the fused dgrad kernel (K-major B operand of dz1^T xext)
+        const int64_t agent = n / R, r = n - agent * R;
+        bf16* col = xextT + agent * 16 * Rp + r;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            col[(int64_t)k * Rp] = hi[k];
+            col[(int64_t)(8 + k) * Rp] = lo[k];
+        }
+    }
 }
 
 // Unfold the gradients of the BN-folded formulation into the Keras trainable tensors (one warp per layer-1 feature f).
@@ -711,7 +728,7 @@ struct Workspace {
     bf16 *cW2b, *cW2T, *tcW2T, *aW2b, *aW2T, *taW2T;   // packed weights (precision 1)
     // BN-folded tensor-core path: sign masks of z1, [x_hi | 1 | x_lo] operand, layer-1 weight-gradient accumulator, folded biases
     uint32_t* mask;
-    bf16* xext;
+    bf16 *xext, *xextT;
     float *G1, *c_b2f, *tc_b2f, *a_b2f, *ta_b2f;
     float *U, *sdq;            // [2][A][l2], [2][A]: head-gradient sums of the critic [0] and actor [1] backward passes
     static constexpr int kMaskWords = 10, kFp = 320;
@@ -720,7 +737,7 @@ struct Workspace {
         const int64_t acts = N * (2 * F + d.l1 + 3 * (int64_t)d.l2) * (int64_t)sizeof(float);
         const int64_t packed = A * (3 * F + 3 * (int64_t)d.l1) * d.l2 * (int64_t)sizeof(bf16);
         const int64_t vecs = 4 * ((N + 3) / 4 * 4) * (int64_t)sizeof(float);
-        const int64_t fold = N * (kMaskWords * 4 + 16 * 2) + A * (kFp * 16 + 6 * (int64_t)d.l2 + 8) * (int64_t)sizeof(float);
+        const int64_t fold = N * (kMaskWords * 4 + 2 * 16 * 2) + A * (kFp * 16 + 6 * (int64_t)d.l2 + 8) * (int64_t)sizeof(float) + A * 16 * 64 * 2;
         return acts + packed + vecs + fold + 1024;
     }
     void carve(void* base_, const avd_net_dims& d, int64_t A, int64_t N) {
@@ -754,6 +771,7 @@ struct Workspace {
         sdq = p; p += (2 * A + 3) / 4 * 4;
         mask = reinterpret_cast<uint32_t*>(p); p += N * kMaskWords;
         xext = reinterpret_cast<bf16*>(((uintptr_t)p + 15) & ~(uintptr_t)15);
+        xextT = xext + N * 16;       // [A][16][Rp], Rp = R rounded up to 64
     }
 };
 
@@ -881,6 +899,18 @@ struct Pass {
         const int tiles = ((F + 127) / 128) * A;
         int split = (int)std::min<int64_t>((R + 63) / 64, std::max(1, 4 * sm_count() / std::max(1, tiles)));
         if (int rc = umma::gemm_bf16(1, A, F, 16, (int)R, dz1, Fp, R * Fp, xext, 16, R * 16, G1, 16, (int64_t)Fp * 16, std::max(1, split), st)) return rc;
+        return unfold(critic, params, F, Fp, G1, grads);
+    }
+
+    // fused dgrad + layer-1 weight gradient (avd_dgrad3.cu), then unfold
+    int dgrad3_unfold(bool critic, const float* params, const bf16* DZ, const bf16* W2b, int F, int Fp, const uint32_t* mask, int mask_words,
+                      const bf16* xextT, float* G1, float* grads) const {
+        AVD_CUDA_OK(cudaMemsetAsync(G1, 0, (size_t)A * Fp * 16 * sizeof(float), st));
+        if (int rc = dgrad3::run(A, R, F, DZ, W2b, mask, mask_words, xextT, (R + 63) / 64 * 64, G1, Fp, st)) return rc;
+        return unfold(critic, params, F, Fp, G1, grads);
+    }
+
+    int unfold(bool critic, const float* params, int F, int Fp, const float* G1, float* grads) const {
         UnfoldOff u;
         u.f = fold_off(critic);
         int64_t ps, gs;
@@ -1120,7 +1150,7 @@ static int learn_fused(const avd_learn_io* io, const Pass& p, const Workspace& w
     AVD_TRY(p.pack_fold(true, io->t_critic, nullptr, w.tcW2T, w.tc_b2f));
     AVD_TRY(p.pack_fold(true, io->critic, w.cW2b, w.cW2T, w.c_b2f));
     AVD_TRY(p.pack_fold(false, io->actor, w.aW2b, w.aW2T, w.a_b2f));
-    xext_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(io->s, io->a, d.ns, N, w.xext, nullptr, 0, 0, nullptr, 0, 0);
+    xext_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(io->s, io->a, d.ns, N, w.xext, nullptr, 0, 0, nullptr, 0, 0, nullptr, R, 0);
     AVD_LAUNCH_OK();
     // ---- TD target: y = r + gamma * target_critic(s', target_actor(s'))            trainer.py:493-494
     AVD_TRY(fused::forward(d, false, A, R, io->t_actor, ao.total, w.taW2T, w.ta_b2f, io->s2, d.ns, 1, nullptr, nullptr, nullptr, nullptr, 1, nullptr,
@@ -1175,14 +1205,14 @@ static int learn_fused3(const avd_learn_io* io, const Pass& p, const Workspace& 
     bf16* Hc = reinterpret_cast<bf16*>(w.H);        // [N][Fp]: r1 of the critic, column F = 1
     bf16* Ha = reinterpret_cast<bf16*>(w.H1a);      // [N][Fp]: r1 of the actor, column l1 = 1
     bf16* DZ = reinterpret_cast<bf16*>(w.DZ);
-    bf16* dz1 = reinterpret_cast<bf16*>(w.DH);      // [N][Fp] (critic) / [N][l1] (actor)
     float* Uc = w.U;
     float* Ua = w.U + (int64_t)A * d.l2;
     AVD_TRY(p.pack_fold(false, io->t_actor, nullptr, w.taW2T, w.ta_b2f));
     AVD_TRY(p.pack_fold(true, io->t_critic, nullptr, w.tcW2T, w.tc_b2f));
     AVD_TRY(p.pack_fold(true, io->critic, w.cW2b, w.cW2T, w.c_b2f));
     AVD_TRY(p.pack_fold(false, io->actor, w.aW2b, w.aW2T, w.a_b2f));
-    xext_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(io->s, io->a, d.ns, N, w.xext, Hc, Fp, F, Ha, Fp, d.l1);
+    const int64_t Rp = (R + 63) / 64 * 64;
+    xext_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(io->s, io->a, d.ns, N, nullptr, Hc, Fp, F, Ha, Fp, d.l1, w.xextT, R, Rp);
     AVD_LAUNCH_OK();
     AVD_CUDA_OK(cudaMemsetAsync(w.U, 0, (size_t)(2 * A * d.l2 + 2 * A) * sizeof(float), st));   // U and sdq are adjacent
     auto wgrad_ones = [&](const bf16* H, int Fn, float* grads, int64_t gstride, int64_t oW2) {   // rows 0..Fn-1: G2, row Fn: db2
@@ -1208,8 +1238,7 @@ static int learn_fused3(const avd_learn_io* io, const Pass& p, const Workspace& 
     AVD_TRY(wgrad_ones(Hc, F, io->critic_grad, co.n_train, co.W2));
     head_unfold(true, io->critic, io->critic_grad, Uc, w.sdq);
     AVD_LAUNCH_OK();
-    AVD_TRY(p.dgrad_masked(DZ, w.cW2b, F, w.mask, MW, dz1, Fp));
-    AVD_TRY(p.l1_wgrad_unfold(true, io->critic, dz1, F, Fp, w.xext, w.G1, io->critic_grad));
+    AVD_TRY(p.dgrad3_unfold(true, io->critic, DZ, w.cW2b, F, Fp, w.mask, MW, w.xextT, w.G1, io->critic_grad));
     // ---- actor loss gradient: -mean(critic(s, actor(s)))                            trainer.py:501-506
     AVD_TRY(fused3::run(fused3::MODE_ACTOR_OUT, d, A, R, io->actor, ao.total, w.aW2T, w.a_b2f, io->s, d.ns, 1, nullptr, nullptr, 0.f, io->action_high,
                         nullptr, nullptr, w.a2, nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr, st));   // pi
@@ -1220,8 +1249,7 @@ static int learn_fused3(const avd_learn_io* io, const Pass& p, const Workspace& 
     AVD_TRY(wgrad_ones(Ha, d.l1, io->actor_grad, ao.n_train, ao.W2));
     head_unfold(false, io->actor, io->actor_grad, Ua, w.sdq + A);
     AVD_LAUNCH_OK();
-    AVD_TRY(p.dgrad_masked(DZ, w.aW2b, d.l1, w.mask, 8, dz1, d.l1));
-    AVD_TRY(p.l1_wgrad_unfold(false, io->actor, dz1, d.l1, d.l1, w.xext, w.G1, io->actor_grad));
+    AVD_TRY(p.dgrad3_unfold(false, io->actor, DZ, w.aW2b, d.l1, Fp, w.mask, 8, w.xextT, w.G1, io->actor_grad));
     return apply_local_updates(io, (void*)st);
 }
 

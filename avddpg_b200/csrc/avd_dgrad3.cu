@@ -1,0 +1,277 @@
+// avd_dgrad3.cu -- layer-1 backward of the DDPG learn step as ONE persistent tensor-core kernel (sm_100a):
+//
+//   dz2 tile [128 rows][128] (bf16, TMA)  --tcgen05.mma against W2' (resident in shared memory, 64-feature chunks)-->
+//   dR chunk [128 rows][64 features] in TMEM  --epilogue warps: ReLU sign mask, bf16-->  dz1 chunk in shared memory
+//   --tcgen05.mma  dz1^T [x_hi | 1 | x_lo]  (MN-major A = the chunk just written, K = the 128 rows)-->  G1 accumulators
+//   that stay in TMEM for the whole kernel and are added to global memory once per CTA.
+//
+// dz1 never reaches HBM: per row the kernel reads 256 B (dz2) + 40 B (masks) + 32 B (x) and writes nothing.
+//   G1[f][c] = sum_n dz1[n][f] xext[n][c]  =>  dW1[k][f] = G1[f][k] + G1[f][8+k],  dWa[f] = G1[l1+f][4] + G1[l1+f][12],
+//   db1[f] = G1[f][5]                                                    (unfold_kernel in avd_ddpg.cu)
+// Math: dR = dz2 W2'^T with W2' = diag(sc1) W2 (BatchNorm folded, pack_fold_kernel), dz1 = dR [z1 > 0]
+// (workers/trainer.py:498, 506 through agent/model.py:19-33, 62-77).
+//
+// Warps: 0 MMA issuer, 1 TMA producer, 2..17 epilogue (TMEM lane quadrant = warp % 4; the four groups of four warps
+// take the 64-column chunks round-robin).  TMEM: 7-slot ring of 64-column dR chunks + 3 x 16 columns of G1.
+#include <cudaTypedefs.h>
+
+#include <algorithm>
+
+#include "avd_common.cuh"
+#include "avd_umma.cuh"
+
+namespace avd {
+namespace dgrad3 {
+
+using namespace umma;
+typedef __nv_bfloat16 bf16;
+
+constexpr int TILE_M = 128, L2N = 128, KB = 64, MAX_NC = 5, NRING = 7;
+constexpr int NUM_THREADS = 32 * 18;
+constexpr int WCHUNK_BYTES = 64 * 128;                       // one 64-feature x 64-k block of W2': 8 KB
+constexpr int OFF_W = 0;                                     // [2 k-blocks][5 chunks][64 rows][128 B] = 80 KB
+constexpr int OFF_A = OFF_W + 2 * MAX_NC * WCHUNK_BYTES;     // 2 buffers x (dz2 tile 32 KB + xext^T tile 4 KB)
+constexpr int A_BYTES = 2 * TILE_M * 128 + 2 * 16 * 128;
+constexpr int OFF_ST = OFF_A + 2 * A_BYTES;                  // 2 pair buffers x 2 chunks x 16 KB
+constexpr int OFF_BAR = OFF_ST + 4 * TILE_M * 128;
+constexpr int SMEM_BYTES = OFF_BAR + 512 + 1024;
+static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB shared memory of an sm_100 CTA");
+static_assert(A_BYTES % 1024 == 0, "swizzled tiles need 1024-byte alignment");
+
+struct Args {
+    int A, F, NC;               // agents, layer-1 features (256 or 256 + la), 64-column chunks
+    int64_t R;
+    const uint32_t* mask;       // [A*R][mask_words]
+    int mask_words;
+    float* G1;                  // [A][Fp][16] +=
+    int Fp;
+    int tiles_per_agent, ctas_per_agent;
+};
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1) dgrad3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmDZ,
+                                                                const __grid_constant__ CUtensorMap tmXT, Args g) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint64_t* d_full = reinterpret_cast<uint64_t*>(smem + OFF_BAR);   // [7]
+    uint64_t* d_empty = d_full + NRING;                               // [7]
+    uint64_t* st_full = d_empty + NRING;                              // [2]
+    uint64_t* st_empty = st_full + 2;                                 // [2]
+    uint64_t* a_full = st_empty + 2;                                  // [2]
+    uint64_t* a_empty = a_full + 2;                                   // [2]
+    uint64_t* w_full = a_empty + 2;
+    uint64_t* g1_done = w_full + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(g1_done + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int agent = (int)blockIdx.x / g.ctas_per_agent;
+    const int cta = (int)blockIdx.x - agent * g.ctas_per_agent;
+    const int T = (g.tiles_per_agent - cta + g.ctas_per_agent - 1) / g.ctas_per_agent;
+    const int NC = g.NC, NP = (NC + 1) >> 1;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmW); tma_prefetch_desc(&tmDZ); tma_prefetch_desc(&tmXT);
+        for (int i = 0; i < NRING; ++i) { mbar_init(&d_full[i], 1); mbar_init(&d_empty[i], 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&st_full[i], 8); mbar_init(&st_empty[i], 1); mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+        mbar_init(w_full, 1);
+        mbar_init(g1_done, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    auto tile_of = [&](int tc) { return cta + tc * g.ctas_per_agent; };
+
+    if (warp == 0) {
+        // ================================================ MMA issuer ================================================
+        if (lane == 0 && T > 0) {
+            constexpr uint32_t idesc_d = make_idesc_bf16(TILE_M, 64, false, false);    // dz2 (K-major) x W2' chunk (K-major)
+            constexpr uint32_t idesc_g = make_idesc_bf16(TILE_M, 16, true, false);     // dz1 (MN-major) x xext^T (K-major)
+            const uint32_t w_addr = smem_u32(smem + OFF_W), a_addr0 = smem_u32(smem + OFF_A), st_addr = smem_u32(smem + OFF_ST);
+            auto mma_tile = [&](int t) {
+                mbar_wait(&a_full[t & 1], ((uint32_t)t >> 1) & 1);
+                tc_fence_after();
+                const uint32_t a_addr = a_addr0 + (t & 1) * A_BYTES;
+                for (int c = 0; c < NC; ++c) {
+                    const uint32_t k = (uint32_t)(t * NC + c), slot = k % NRING;
+                    mbar_wait(&d_empty[slot], ((k / NRING) & 1) ^ 1);
+                    tc_fence_after();
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks)
+                        mma_bf16(tmem_base + slot * 64, make_smem_desc(a_addr + (ks >> 2) * (TILE_M * 128) + (ks & 3) * 32, 16, 1024),
+                                 make_smem_desc(w_addr + ((ks >> 2) * MAX_NC + c) * WCHUNK_BYTES + (ks & 3) * 32, 16, 1024), idesc_d, ks != 0);
+                    mma_commit(&d_full[slot]);
+                }
+            };
+            auto g1_tile = [&](int t) {
+                const uint32_t xt_addr = a_addr0 + (t & 1) * A_BYTES + 2 * TILE_M * 128;
+                for (int p = 0; p < NP; ++p) {
+                    const uint32_t pk = (uint32_t)(t * NP + p), sb = pk & 1;
+                    mbar_wait(&st_full[sb], (pk >> 1) & 1);
+                    tc_fence_after();
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks)
+                        mma_bf16(tmem_base + 448u + (uint32_t)(p * 16), make_smem_desc(st_addr + sb * (2 * TILE_M * 128) + ks * 2048, TILE_M * 128, 1024),
+                                 make_smem_desc(xt_addr + (ks >> 2) * (16 * 128) + (ks & 3) * 32, 16, 1024), idesc_g, (t | ks) != 0);
+                    mma_commit(&st_empty[sb]);
+                }
+                mma_commit(&a_empty[t & 1]);       // dz2 and xext^T tiles of this tile are no longer read
+            };
+            mbar_wait(w_full, 0);
+            mma_tile(0);
+            for (int t = 0; t < T; ++t) {
+                if (t + 1 < T) mma_tile(t + 1);
+                g1_tile(t);
+            }
+            mma_commit(g1_done);
+        }
+    } else if (warp == 1) {
+        // ================================================ TMA producer ================================================
+        if (lane == 0 && T > 0) {
+            mbar_expect_tx(w_full, (uint32_t)(2 * NC * WCHUNK_BYTES));
+            for (int kb = 0; kb < 2; ++kb)
+                for (int c = 0; c < NC; ++c) tma_load_3d(smem + OFF_W + (kb * MAX_NC + c) * WCHUNK_BYTES, &tmW, w_full, kb * KB, c * 64, agent);
+            for (int t = 0; t < T; ++t) {
+                const int b = t & 1;
+                mbar_wait(&a_empty[b], (((uint32_t)t >> 1) & 1) ^ 1);
+                uint8_t* dst = smem + OFF_A + b * A_BYTES;
+                mbar_expect_tx(&a_full[b], A_BYTES);
+                const int r0 = tile_of(t) * TILE_M;
+                tma_load_3d(dst, &tmDZ, &a_full[b], 0, r0, agent);
+                tma_load_3d(dst + TILE_M * 128, &tmDZ, &a_full[b], KB, r0, agent);
+                tma_load_3d(dst + 2 * TILE_M * 128, &tmXT, &a_full[b], r0, 0, agent);
+                tma_load_3d(dst + 2 * TILE_M * 128 + 16 * 128, &tmXT, &a_full[b], r0 + KB, 0, agent);
+            }
+        }
+    } else {
+        // ================================================== epilogue ==================================================
+        const int q = warp & 3, grp = (warp - 2) >> 2;
+        const int row = q * 32 + lane;
+        const uint32_t tlane = (uint32_t)(q * 32) << 16;
+        for (int t = 0; t < T; ++t) {
+            const int64_t r_in = (int64_t)tile_of(t) * TILE_M + row;
+            const int64_t nrow = (int64_t)agent * g.R + (r_in < g.R ? r_in : g.R - 1);
+            for (int c = 0; c < NC; ++c) {
+                const uint32_t k = (uint32_t)(t * NC + c);
+                if ((int)(k & 3) != grp) continue;
+                const uint32_t slot = k % NRING;
+                const uint2 neg = *reinterpret_cast<const uint2*>(g.mask + nrow * g.mask_words + 2 * c);
+                const uint32_t pk = (uint32_t)(t * NP + (c >> 1)), sb = pk & 1;
+                mbar_wait(&d_full[slot], (k / NRING) & 1);
+                tc_fence_after();
+                mbar_wait(&st_empty[sb], ((pk >> 1) & 1) ^ 1);
+                uint8_t* srow = smem + OFF_ST + sb * (2 * TILE_M * 128) + (c & 1) * (TILE_M * 128) + row * 128;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    float v[32];
+                    tmem_ld32(tmem_base + slot * 64 + (uint32_t)(h * 32) + tlane, v);
+                    const uint32_t m = h ? neg.y : neg.x;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (m & (0x80000000u >> j)) v[j] = 0.0f;
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                        const uint4 pkd = make_uint4(pack_bf16x2(v[8 * kk], v[8 * kk + 1]), pack_bf16x2(v[8 * kk + 2], v[8 * kk + 3]),
+                                                     pack_bf16x2(v[8 * kk + 4], v[8 * kk + 5]), pack_bf16x2(v[8 * kk + 6], v[8 * kk + 7]));
+                        *reinterpret_cast<uint4*>(srow + (((h * 4 + kk) ^ (row & 7)) << 4)) = pkd;
+                    }
+                }
+                tc_fence_before();
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(&d_empty[slot]);
+                    mbar_arrive(&st_full[sb]);
+                    if ((NC & 1) && c == NC - 1) mbar_arrive(&st_full[sb]);     // a lone last chunk stands in for its missing partner
+                }
+            }
+        }
+        // ---- G1 accumulators of this CTA -> global (features p*128 + row, 16 columns)
+        if (grp == 0 && T > 0) {
+            mbar_wait(g1_done, 0);
+            tc_fence_after();
+            for (int p = 0; p < NP; ++p) {
+                float v[16];
+                tmem_ld16(tmem_base + 448u + (uint32_t)(p * 16) + tlane, v);
+                const int f = p * 128 + row;
+                if (f < g.F) {
+                    float* dst = g.G1 + ((int64_t)agent * g.Fp + f) * 16;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) atomicAdd(dst + j, v[j]);
+                }
+            }
+            tc_fence_before();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+static PFN_cuTensorMapEncodeTiled encode_fn() {
+    static PFN_cuTensorMapEncodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(p);
+    }
+    return fn;
+}
+
+static int make_map(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t rows, uint64_t batch, uint64_t pitch, uint64_t batch_stride,
+                    uint32_t box_rows) {
+    PFN_cuTensorMapEncodeTiled enc = encode_fn();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled is not available from the driver");
+        return AVD_ERR_CUDA;
+    }
+    cuuint64_t dims[3] = {inner, rows, batch};
+    cuuint64_t strides[2] = {pitch * 2, batch_stride * 2};
+    cuuint32_t box[3] = {KB, box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with %d (inner=%llu rows=%llu batch=%llu pitch=%llu)", (int)r, (unsigned long long)inner,
+                  (unsigned long long)rows, (unsigned long long)batch, (unsigned long long)pitch);
+        return AVD_ERR_CUDA;
+    }
+    return AVD_OK;
+}
+
+// DZ: bf16 [A*R][128];  W2b: bf16 [A][F][128] folded layer-2 kernel;  mask: [A*R][mask_words];  xextT: bf16 [A][16][Rp]
+// (Rp = rows per agent rounded up to a multiple of 64);  G1: fp32 [A][Fp][16], accumulated into (zero it first).
+int run(int A, int64_t R, int F, const bf16* DZ, const bf16* W2b, const uint32_t* mask, int mask_words, const bf16* xextT, int64_t Rp, float* G1,
+        int Fp, cudaStream_t st) {
+    AVD_REQUIRE(A >= 1 && R >= 1 && F >= 64 && F % 16 == 0 && F <= MAX_NC * 64 && Fp >= F, "bad sizes for the fused dgrad kernel");
+    AVD_REQUIRE(DZ && W2b && mask && xextT && G1 && Rp % 64 == 0 && Rp >= R, "null buffer / bad pitch");
+    static bool attr_set = false;
+    if (!attr_set) {
+        AVD_CUDA_OK(cudaFuncSetAttribute(dgrad3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        attr_set = true;
+    }
+    CUtensorMap tmW, tmDZ, tmXT;
+    if (int rc = make_map(&tmW, W2b, L2N, (uint64_t)F, (uint64_t)A, L2N, (uint64_t)F * L2N, 64)) return rc;
+    if (int rc = make_map(&tmDZ, DZ, L2N, (uint64_t)R, (uint64_t)A, L2N, (uint64_t)R * L2N, TILE_M)) return rc;
+    if (int rc = make_map(&tmXT, xextT, (uint64_t)R, 16, (uint64_t)A, (uint64_t)Rp, (uint64_t)16 * Rp, 16)) return rc;
+    Args g;
+    g.A = A; g.F = F; g.NC = (F + 63) / 64; g.R = R; g.mask = mask; g.mask_words = mask_words; g.G1 = G1; g.Fp = Fp;
+    g.tiles_per_agent = (int)((R + TILE_M - 1) / TILE_M);
+    g.ctas_per_agent = std::max(1, std::min(g.tiles_per_agent, sm_count() / std::max(1, A)));
+    dgrad3_kernel<<<(unsigned)(g.ctas_per_agent * A), NUM_THREADS, SMEM_BYTES, st>>>(tmW, tmDZ, tmXT, g);
+    AVD_LAUNCH_OK();
+    return AVD_OK;
+}
+
+}  // namespace dgrad3
+}  // namespace avd
