@@ -1212,7 +1212,7 @@ static int learn_fused3(const avd_learn_io* io, const Pass& p, const Workspace& 
     AVD_TRY(p.pack_fold(true, io->critic, w.cW2b, w.cW2T, w.c_b2f));
     AVD_TRY(p.pack_fold(false, io->actor, w.aW2b, w.aW2T, w.a_b2f));
     const int64_t Rp = (R + 63) / 64 * 64;
-    xext_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(io->s, io->a, d.ns, N, nullptr, Hc, Fp, F, Ha, Fp, d.l1, w.xextT, R, Rp);
+    xext_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(io->s, io->a, d.ns, N, nullptr, nullptr, 0, 0, nullptr, 0, 0, w.xextT, R, Rp);
     AVD_LAUNCH_OK();
     AVD_CUDA_OK(cudaMemsetAsync(w.U, 0, (size_t)(2 * A * d.l2 + 2 * A) * sizeof(float), st));   // U and sdq are adjacent
     auto wgrad_ones = [&](const bf16* H, int Fn, float* grads, int64_t gstride, int64_t oW2) {   // rows 0..Fn-1: G2, row Fn: db2

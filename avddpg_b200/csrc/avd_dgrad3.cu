@@ -94,40 +94,47 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dgrad3_kernel(const __grid_con
             constexpr uint32_t idesc_d = make_idesc_bf16(TILE_M, 64, false, false);    // dz2 (K-major) x W2' chunk (K-major)
             constexpr uint32_t idesc_g = make_idesc_bf16(TILE_M, 16, true, false);     // dz1 (MN-major) x xext^T (K-major)
             const uint32_t w_addr = smem_u32(smem + OFF_W), a_addr0 = smem_u32(smem + OFF_A), st_addr = smem_u32(smem + OFF_ST);
-            auto mma_tile = [&](int t) {
-                mbar_wait(&a_full[t & 1], ((uint32_t)t >> 1) & 1);
-                tc_fence_after();
+            // chunk c of local tile t: dR chunk = dz2 tile . W2'[64 c .. 64 c + 63]^T  -> ring slot (t NC + c) % 7
+            auto mma_chunk = [&](int t, int c) {
+                if (c == 0) {
+                    mbar_wait(&a_full[t & 1], ((uint32_t)t >> 1) & 1);
+                    tc_fence_after();
+                }
                 const uint32_t a_addr = a_addr0 + (t & 1) * A_BYTES;
-                for (int c = 0; c < NC; ++c) {
-                    const uint32_t k = (uint32_t)(t * NC + c), slot = k % NRING;
-                    mbar_wait(&d_empty[slot], ((k / NRING) & 1) ^ 1);
-                    tc_fence_after();
+                const uint32_t k = (uint32_t)(t * NC + c), slot = k % NRING;
+                mbar_wait(&d_empty[slot], ((k / NRING) & 1) ^ 1);
+                tc_fence_after();
 #pragma unroll
-                    for (int ks = 0; ks < 8; ++ks)
-                        mma_bf16(tmem_base + slot * 64, make_smem_desc(a_addr + (ks >> 2) * (TILE_M * 128) + (ks & 3) * 32, 16, 1024),
-                                 make_smem_desc(w_addr + ((ks >> 2) * MAX_NC + c) * WCHUNK_BYTES + (ks & 3) * 32, 16, 1024), idesc_d, ks != 0);
-                    mma_commit(&d_full[slot]);
-                }
+                for (int ks = 0; ks < 8; ++ks)
+                    mma_bf16(tmem_base + slot * 64, make_smem_desc(a_addr + (ks >> 2) * (TILE_M * 128) + (ks & 3) * 32, 16, 1024),
+                             make_smem_desc(w_addr + ((ks >> 2) * MAX_NC + c) * WCHUNK_BYTES + (ks & 3) * 32, 16, 1024), idesc_d, ks != 0);
+                mma_commit(&d_full[slot]);
             };
-            auto g1_tile = [&](int t) {
+            // chunk pair p of local tile t: G1[128 p ..] += dz1 pair^T . xext tile
+            auto g1_pair = [&](int t, int p) {
                 const uint32_t xt_addr = a_addr0 + (t & 1) * A_BYTES + 2 * TILE_M * 128;
-                for (int p = 0; p < NP; ++p) {
-                    const uint32_t pk = (uint32_t)(t * NP + p), sb = pk & 1;
-                    mbar_wait(&st_full[sb], (pk >> 1) & 1);
-                    tc_fence_after();
+                const uint32_t pk = (uint32_t)(t * NP + p), sb = pk & 1;
+                mbar_wait(&st_full[sb], (pk >> 1) & 1);
+                tc_fence_after();
 #pragma unroll
-                    for (int ks = 0; ks < 8; ++ks)
-                        mma_bf16(tmem_base + 448u + (uint32_t)(p * 16), make_smem_desc(st_addr + sb * (2 * TILE_M * 128) + ks * 2048, TILE_M * 128, 1024),
-                                 make_smem_desc(xt_addr + (ks >> 2) * (16 * 128) + (ks & 3) * 32, 16, 1024), idesc_g, (t | ks) != 0);
-                    mma_commit(&st_empty[sb]);
-                }
-                mma_commit(&a_empty[t & 1]);       // dz2 and xext^T tiles of this tile are no longer read
+                for (int ks = 0; ks < 8; ++ks)
+                    mma_bf16(tmem_base + 448u + (uint32_t)(p * 16), make_smem_desc(st_addr + sb * (2 * TILE_M * 128) + ks * 2048, TILE_M * 128, 1024),
+                             make_smem_desc(xt_addr + (ks >> 2) * (16 * 128) + (ks & 3) * 32, 16, 1024), idesc_g, (t | ks) != 0);
+                mma_commit(&st_empty[sb]);
+                if (p == NP - 1) mma_commit(&a_empty[t & 1]);       // dz2 and xext^T tiles of this tile are no longer read
             };
             mbar_wait(w_full, 0);
-            mma_tile(0);
+            for (int c = 0; c < NC; ++c) mma_chunk(0, c);
+            // steady state: the chunk MMAs of tile t + 1 are interleaved with the G1 MMAs of tile t, pair by pair, so that a
+            // staging buffer is handed back as early as possible (every wait only depends on work issued earlier)
             for (int t = 0; t < T; ++t) {
-                if (t + 1 < T) mma_tile(t + 1);
-                g1_tile(t);
+                for (int p = 0; p < NP; ++p) {
+                    if (t + 1 < T) {
+                        mma_chunk(t + 1, 2 * p);
+                        if (2 * p + 1 < NC) mma_chunk(t + 1, 2 * p + 1);
+                    }
+                    g1_pair(t, p);
+                }
             }
             mma_commit(g1_done);
         }

@@ -179,6 +179,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused3_kernel(const __grid_con
             wa_tab[c] = wa;
             ba_tab[c] = ba;
         }
+        if (BWD && !CRITIC && ct < TILE_M) {   // constant tile [1 0 0 ...] behind the 256 actor features (slot 4 is otherwise unused)
+            uint8_t* crow = smem + OFF_RING + 4 * SLOT_BYTES + ct * 128;
+            *reinterpret_cast<uint4*>(crow + ((0 ^ (ct & 7)) << 4)) = make_uint4(0x00003F80u, 0u, 0u, 0u);      // bf16 1.0 = 0x3F80
+            *reinterpret_cast<uint4*>(crow + ((1 ^ (ct & 7)) << 4)) = make_uint4(0u, 0u, 0u, 0u);
+        }
         fence_proxy_async();
     }
     tc_fence_before();
@@ -233,6 +238,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused3_kernel(const __grid_con
                     mma_commit(&a_empty[kb]);
                 }
                 mma_commit(&acc_full[t & 1]);
+                if (BWD && !CRITIC) tma_store_3d(&tmR, smem + OFF_RING + 4 * SLOT_BYTES, L1N, tile_of(t) * TILE_M, agent);   // the constant-one column
                 if (BWD) {                    // the r1 slots are also free only once the TMA stores have read them
                     bulk_commit();
                     bulk_wait_read0();
@@ -361,10 +367,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused3_kernel(const __grid_con
                 }
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    if (j0 + 8 * k < la) {
+                    const int col = j0 + 8 * k;
+                    if (col < la) {
                         const uint4 pk = make_uint4(pack_bf16x2(z[8 * k], z[8 * k + 1]), pack_bf16x2(z[8 * k + 2], z[8 * k + 3]),
                                                     pack_bf16x2(z[8 * k + 4], z[8 * k + 5]), pack_bf16x2(z[8 * k + 6], z[8 * k + 7]));
-                        *reinterpret_cast<uint4*>(aslot + (((j0 / 8 + k) ^ (row & 7)) << 4)) = pk;
+                        *reinterpret_cast<uint4*>(aslot + (((col >> 3) ^ (row & 7)) << 4)) = pk;
+                    } else if (BWD && col < la + 16) {   // [1 0 0 ...]: the constant-one feature that makes the wgrad GEMM produce db2
+                        *reinterpret_cast<uint4*>(aslot + (((col >> 3) ^ (row & 7)) << 4)) = make_uint4(col == la ? 0x00003F80u : 0u, 0u, 0u, 0u);
                     }
                 }
                 fence_proxy_async();
@@ -567,7 +576,7 @@ static int make_map(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t 
 }
 
 bool supported(const avd_net_dims& d) {
-    return d.l2 == L2N && d.ns >= 1 && d.ns <= 4 && d.l1 == L1N && d.la % 16 == 0 && d.la >= 16 && d.la <= 64;
+    return d.l2 == L2N && d.ns >= 1 && d.ns <= 4 && d.l1 == L1N && d.la % 16 == 0 && d.la >= 16 && d.la <= 48;   // la = 64 leaves no pad column for the constant-one feature
 }
 
 template <int MODE>
@@ -583,7 +592,7 @@ static int launch(const CUtensorMap& tmW, const CUtensorMap& tmR, const CUtensor
 }
 
 // One pass.  W2T: bf16 [A][128][F] folded layer-2 kernel (K-major), b2f: [A][128]  (pack_fold_kernel).
-// R1_out: bf16 [A*R][r1_pitch] (backward modes; columns >= F are left untouched), DZ_out: bf16 [A*R][128] (backward modes).
+// R1_out: bf16 [A*R][r1_pitch] (backward modes; columns F..F+15 receive [1 0 ... 0]), DZ_out: bf16 [A*R][128] (backward modes).
 int run(int mode, const avd_net_dims& d, int A, int64_t R, const float* params, int64_t pstride, const bf16* W2T, const float* b2f, const float* s,
         int64_t s_rs, int64_t s_cs, const float* act, const float* rew, float gamma, float high, const float* y, const float* dpi, float* out,
         bf16* R1_out, int64_t r1_pitch, uint32_t* mask_out, bf16* DZ_out, float* U, float* sdq, float* loss, cudaStream_t st) {
@@ -596,14 +605,14 @@ int run(int mode, const avd_net_dims& d, int A, int64_t R, const float* params, 
     const int F = critic ? d.l1 + d.la : d.l1;
     AVD_REQUIRE(params && W2T && b2f && s, "null buffer");
     AVD_REQUIRE(!critic || act, "critic passes need actions");
-    AVD_REQUIRE(!bwd || (R1_out && mask_out && DZ_out && U && sdq && r1_pitch >= F && r1_pitch % 8 == 0), "backward passes need r1 / mask / dz2 / U / sdq outputs");
+    AVD_REQUIRE(!bwd || (R1_out && mask_out && DZ_out && U && sdq && r1_pitch >= F + 16 && r1_pitch % 8 == 0), "backward passes need r1 / mask / dz2 / U / sdq outputs");
     AVD_REQUIRE(bwd || out, "null output");
     CUtensorMap tmW, tmR, tmDZ;
     if (int rc = make_map(&tmW, W2T, (uint64_t)F, L2N, (uint64_t)A, (uint64_t)F, (uint64_t)F * L2N)) return rc;
     tmR = tmW;
     tmDZ = tmW;
     if (bwd) {
-        if (int rc = make_map(&tmR, R1_out, (uint64_t)F, (uint64_t)R, (uint64_t)A, (uint64_t)r1_pitch, (uint64_t)R * r1_pitch)) return rc;
+        if (int rc = make_map(&tmR, R1_out, (uint64_t)F + 16, (uint64_t)R, (uint64_t)A, (uint64_t)r1_pitch, (uint64_t)R * r1_pitch)) return rc;
         if (int rc = make_map(&tmDZ, DZ_out, L2N, (uint64_t)R, (uint64_t)A, L2N, (uint64_t)R * L2N)) return rc;
     }
     Args g;
