@@ -42,12 +42,17 @@ enum Mode { MODE_ACTOR_OUT = 0, MODE_TARGET = 1, MODE_Q = 2, MODE_CRITIC_BWD = 3
 bool supported(const avd_net_dims& d);
 int run(int mode, const avd_net_dims& d, int A, int64_t R, const float* params, int64_t pstride, const bf16* W2T, const float* b2f, const float* s,
         int64_t s_rs, int64_t s_cs, const float* act, const float* rew, float gamma, float high, const float* y, const float* dpi, float* out,
-        bf16* R1_out, int64_t r1_pitch, uint32_t* mask_out, bf16* DZ_out, float* U, float* sdq, float* loss, cudaStream_t st);
+        uint32_t* mask_out, bf16* DZ_out, float* U, float* sdq, float* loss, cudaStream_t st);
+}
+
+namespace wgrad3 {  // avd_wgrad3.cu
+int run(const avd_net_dims& d, bool critic, int A, int64_t R, const float* params, int64_t pstride, const float* s, const float* act, const bf16* DZ,
+        float* grads, int64_t gstride, int64_t oW2, cudaStream_t st);
 }
 
 namespace dgrad3 {  // avd_dgrad3.cu
 int run(int A, int64_t R, int F, const bf16* DZ, const bf16* W2b, const uint32_t* mask, int mask_words, const bf16* xextT, int64_t Rp, float* G1,
-        int Fp, cudaStream_t st);
+        int Fp, float* db2, int64_t db2_stride, cudaStream_t st);
 }
 
 namespace umma {   // avd_umma.cu
@@ -906,7 +911,8 @@ struct Pass {
     int dgrad3_unfold(bool critic, const float* params, const bf16* DZ, const bf16* W2b, int F, int Fp, const uint32_t* mask, int mask_words,
                       const bf16* xextT, float* G1, float* grads) const {
         AVD_CUDA_OK(cudaMemsetAsync(G1, 0, (size_t)A * Fp * 16 * sizeof(float), st));
-        if (int rc = dgrad3::run(A, R, F, DZ, W2b, mask, mask_words, xextT, (R + 63) / 64 * 64, G1, Fp, st)) return rc;
+        const int64_t ob2 = critic ? critic_off(d).b2 : actor_off(d).b2, gs = critic ? critic_off(d).n_train : actor_off(d).n_train;
+        if (int rc = dgrad3::run(A, R, F, DZ, W2b, mask, mask_words, xextT, (R + 63) / 64 * 64, G1, Fp, grads + ob2, gs, st)) return rc;
         return unfold(critic, params, F, Fp, G1, grads);
     }
 
@@ -1012,7 +1018,7 @@ extern "C" int avd_actor_forward(const avd_net_dims* dims, int32_t A, int64_t R,
         AVD_TRY(p.pack_fold(false, actor_params, nullptr, W2T, H));
         if (fused3::supported(d))
             return fused3::run(fused3::MODE_ACTOR_OUT, d, A, R, actor_params, o.total, W2T, H, s, s_rs, s_cs, nullptr, nullptr, 0.f, action_high, nullptr,
-                               nullptr, out, nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr, p.st);
+                               nullptr, out, nullptr, nullptr, nullptr, nullptr, nullptr, p.st);
         return fused::forward(d, false, A, R, actor_params, o.total, W2T, H, s, s_rs, s_cs, nullptr, nullptr, nullptr, nullptr, 1, nullptr, 0.f,
                               action_high, out, p.st);
     }
@@ -1044,8 +1050,8 @@ extern "C" int avd_critic_forward(const avd_net_dims* dims, int32_t A, int64_t R
     if (precision && fused::supported(d, true)) {
         AVD_TRY(p.pack_fold(true, critic_params, nullptr, W2T, H));
         if (fused3::supported(d))
-            return fused3::run(fused3::MODE_Q, d, A, R, critic_params, o.total, W2T, H, s, d.ns, 1, a, nullptr, 0.f, 0.f, nullptr, nullptr, q, nullptr, 0,
-                               nullptr, nullptr, nullptr, nullptr, nullptr, p.st);
+            return fused3::run(fused3::MODE_Q, d, A, R, critic_params, o.total, W2T, H, s, d.ns, 1, a, nullptr, 0.f, 0.f, nullptr, nullptr, q, nullptr,
+                               nullptr, nullptr, nullptr, nullptr, p.st);
         return fused::forward(d, true, A, R, critic_params, o.total, W2T, H, s, d.ns, 1, a, nullptr, nullptr, nullptr, 3, nullptr, 0.f, 0.f, q, p.st);
     }
     if (precision) AVD_TRY(p.pack(critic_params, o.total, o.W2, F, nullptr, W2T));
@@ -1191,9 +1197,10 @@ static int learn_fused(const avd_learn_io* io, const Pass& p, const Workspace& w
     return apply_local_updates(io, (void*)st);
 }
 
-// The learn step on the third-generation fused pass kernels (avd_fused3.cu): six persistent launches cover every forward
-// pass, both head backwards and the critic -> actor link; r1 / dz2 / masks go to HBM once for the three GEMM kinds that
-// remain (wgrad [r1 | 1]^T dz2, dgrad with the ReLU-mask epilogue, layer-1 wgrad dz1^T [x_hi | 1 | x_lo]).
+// The learn step on the third-generation kernels: six persistent pass launches (avd_fused3.cu) cover every forward pass,
+// both head backwards and the critic -> actor link; per differentiated net only dz2 (256 B per row) and the ReLU sign masks
+// (40 B) go to HBM, for the layer-2 weight gradient (avd_wgrad3.cu, recomputes r1 on chip) and the fused dgrad + layer-1
+// weight gradient + layer-2 bias gradient (avd_dgrad3.cu).
 static int learn_fused3(const avd_learn_io* io, const Pass& p, const Workspace& w, cudaStream_t st) {
     const avd_net_dims d = io->dims;
     const int A = io->A;
@@ -1202,8 +1209,6 @@ static int learn_fused3(const avd_learn_io* io, const Pass& p, const Workspace& 
     const CriticOff co = critic_off(d);
     const int F = d.l1 + d.la;
     constexpr int Fp = Workspace::kFp, MW = Workspace::kMaskWords;
-    bf16* Hc = reinterpret_cast<bf16*>(w.H);        // [N][Fp]: r1 of the critic, column F = 1
-    bf16* Ha = reinterpret_cast<bf16*>(w.H1a);      // [N][Fp]: r1 of the actor, column l1 = 1
     bf16* DZ = reinterpret_cast<bf16*>(w.DZ);
     float* Uc = w.U;
     float* Ua = w.U + (int64_t)A * d.l2;
@@ -1215,11 +1220,6 @@ static int learn_fused3(const avd_learn_io* io, const Pass& p, const Workspace& 
     xext_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(io->s, io->a, d.ns, N, nullptr, nullptr, 0, 0, nullptr, 0, 0, w.xextT, R, Rp);
     AVD_LAUNCH_OK();
     AVD_CUDA_OK(cudaMemsetAsync(w.U, 0, (size_t)(2 * A * d.l2 + 2 * A) * sizeof(float), st));   // U and sdq are adjacent
-    auto wgrad_ones = [&](const bf16* H, int Fn, float* grads, int64_t gstride, int64_t oW2) {   // rows 0..Fn-1: G2, row Fn: db2
-        const int tiles = ((Fn + 1 + 127) / 128) * A;
-        const int split = (int)std::max<int64_t>(1, std::min<int64_t>((R + 63) / 64, std::max(1, 4 * sm_count() / std::max(1, tiles))));
-        return umma::gemm_bf16(1, A, Fn + 1, d.l2, (int)R, H, Fp, R * Fp, DZ, d.l2, R * d.l2, grads + oW2, d.l2, gstride, split, st);
-    };
     auto head_unfold = [&](bool critic, const float* params, float* grads, const float* U, const float* sdq) {
         HeadOff o;
         int64_t ps, gs;
@@ -1229,24 +1229,24 @@ static int learn_fused3(const avd_learn_io* io, const Pass& p, const Workspace& 
     };
     // ---- TD target: y = r + gamma * target_critic(s', target_actor(s'))            trainer.py:493-494
     AVD_TRY(fused3::run(fused3::MODE_ACTOR_OUT, d, A, R, io->t_actor, ao.total, w.taW2T, w.ta_b2f, io->s2, d.ns, 1, nullptr, nullptr, 0.f,
-                        io->action_high, nullptr, nullptr, w.a2, nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr, st));
+                        io->action_high, nullptr, nullptr, w.a2, nullptr, nullptr, nullptr, nullptr, nullptr, st));
     AVD_TRY(fused3::run(fused3::MODE_TARGET, d, A, R, io->t_critic, co.total, w.tcW2T, w.tc_b2f, io->s2, d.ns, 1, w.a2, io->r, io->gamma, 0.f,
-                        nullptr, nullptr, w.y, nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr, st));
+                        nullptr, nullptr, w.y, nullptr, nullptr, nullptr, nullptr, nullptr, st));
     // ---- critic loss gradient on (s, a)                                             trainer.py:495-498
     AVD_TRY(fused3::run(fused3::MODE_CRITIC_BWD, d, A, R, io->critic, co.total, w.cW2T, w.c_b2f, io->s, d.ns, 1, io->a, nullptr, 0.f, 0.f, w.y,
-                        nullptr, w.q, Hc, Fp, w.mask, DZ, Uc, w.sdq, io->loss, st));
-    AVD_TRY(wgrad_ones(Hc, F, io->critic_grad, co.n_train, co.W2));
+                        nullptr, w.q, w.mask, DZ, Uc, w.sdq, io->loss, st));
+    AVD_TRY(wgrad3::run(d, true, A, R, io->critic, co.total, io->s, io->a, DZ, io->critic_grad, co.n_train, co.W2, st));
     head_unfold(true, io->critic, io->critic_grad, Uc, w.sdq);
     AVD_LAUNCH_OK();
     AVD_TRY(p.dgrad3_unfold(true, io->critic, DZ, w.cW2b, F, Fp, w.mask, MW, w.xextT, w.G1, io->critic_grad));
     // ---- actor loss gradient: -mean(critic(s, actor(s)))                            trainer.py:501-506
     AVD_TRY(fused3::run(fused3::MODE_ACTOR_OUT, d, A, R, io->actor, ao.total, w.aW2T, w.a_b2f, io->s, d.ns, 1, nullptr, nullptr, 0.f, io->action_high,
-                        nullptr, nullptr, w.a2, nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr, st));   // pi
+                        nullptr, nullptr, w.a2, nullptr, nullptr, nullptr, nullptr, nullptr, st));   // pi
     AVD_TRY(fused3::run(fused3::MODE_CRITIC_ACTION, d, A, R, io->critic, co.total, w.cW2T, w.c_b2f, io->s, d.ns, 1, w.a2, nullptr, 0.f, 0.f, nullptr,
-                        nullptr, w.dpi, nullptr, 0, nullptr, nullptr, nullptr, nullptr, io->loss, st));          // d(-mean q)/d pi
+                        nullptr, w.dpi, nullptr, nullptr, nullptr, nullptr, io->loss, st));          // d(-mean q)/d pi
     AVD_TRY(fused3::run(fused3::MODE_ACTOR_BWD, d, A, R, io->actor, ao.total, w.aW2T, w.a_b2f, io->s, d.ns, 1, nullptr, nullptr, 0.f, io->action_high,
-                        nullptr, w.dpi, nullptr, Ha, Fp, w.mask, DZ, Ua, w.sdq + A, nullptr, st));
-    AVD_TRY(wgrad_ones(Ha, d.l1, io->actor_grad, ao.n_train, ao.W2));
+                        nullptr, w.dpi, nullptr, w.mask, DZ, Ua, w.sdq + A, nullptr, st));
+    AVD_TRY(wgrad3::run(d, false, A, R, io->actor, ao.total, io->s, nullptr, DZ, io->actor_grad, ao.n_train, ao.W2, st));
     head_unfold(false, io->actor, io->actor_grad, Ua, w.sdq + A);
     AVD_LAUNCH_OK();
     AVD_TRY(p.dgrad3_unfold(false, io->actor, DZ, w.aW2b, d.l1, Fp, w.mask, 8, w.xextT, w.G1, io->actor_grad));

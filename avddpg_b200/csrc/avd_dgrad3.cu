@@ -12,7 +12,8 @@
 // (workers/trainer.py:498, 506 through agent/model.py:19-33, 62-77).
 //
 // Warps: 0 MMA issuer, 1 TMA producer, 2..17 epilogue (TMEM lane quadrant = warp % 4; the four groups of four warps
-// take the 64-column chunks round-robin).  TMEM: 7-slot ring of 64-column dR chunks + 3 x 16 columns of G1.
+// take the 64-column chunks round-robin).  TMEM: 7-slot ring of 64-column dR chunks + 3 x 16 columns of G1 + 16 columns of
+// dz2^T xext, whose column 5 (xext's constant one) is the layer-2 bias gradient db2.
 #include <cudaTypedefs.h>
 
 #include <algorithm>
@@ -30,13 +31,15 @@ constexpr int TILE_M = 128, L2N = 128, KB = 64, MAX_NC = 5, NRING = 7;
 constexpr int NUM_THREADS = 32 * 18;
 constexpr int WCHUNK_BYTES = 64 * 128;                       // one 64-feature x 64-k block of W2': 8 KB
 constexpr int OFF_W = 0;                                     // [2 k-blocks][5 chunks][64 rows][128 B] = 80 KB
-constexpr int OFF_A = OFF_W + 2 * MAX_NC * WCHUNK_BYTES;     // 2 buffers x (dz2 tile 32 KB + xext^T tile 4 KB)
-constexpr int A_BYTES = 2 * TILE_M * 128 + 2 * 16 * 128;
-constexpr int OFF_ST = OFF_A + 2 * A_BYTES;                  // 2 pair buffers x 2 chunks x 16 KB
+constexpr int OFF_A = OFF_W + 2 * MAX_NC * WCHUNK_BYTES;     // 2 dz2 tiles of 32 KB (released as soon as the chunk MMAs have read them)
+constexpr int A_BYTES = 2 * TILE_M * 128;
+constexpr int OFF_XT = OFF_A + 2 * A_BYTES;                  // 4 xext^T tiles of 4 KB (read last, by the G1 MMAs): deeper ring
+constexpr int XT_BYTES = 2 * 16 * 128, NXT = 4;
+constexpr int OFF_ST = OFF_XT + NXT * XT_BYTES;              // 2 pair buffers x 2 chunks x 16 KB
 constexpr int OFF_BAR = OFF_ST + 4 * TILE_M * 128;
 constexpr int SMEM_BYTES = OFF_BAR + 512 + 1024;
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB shared memory of an sm_100 CTA");
-static_assert(A_BYTES % 1024 == 0, "swizzled tiles need 1024-byte alignment");
+static_assert(A_BYTES % 1024 == 0 && XT_BYTES % 1024 == 0 && OFF_ST % 1024 == 0, "swizzled tiles need 1024-byte alignment");
 
 struct Args {
     int A, F, NC;               // agents, layer-1 features (256 or 256 + la), 64-column chunks
@@ -45,6 +48,8 @@ struct Args {
     int mask_words;
     float* G1;                  // [A][Fp][16] +=
     int Fp;
+    float* db2;                 // [A][db2_stride] += sum_n dz2[n][j]   (layer-2 bias gradient)
+    int64_t db2_stride;
     int tiles_per_agent, ctas_per_agent;
 };
 
@@ -63,7 +68,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dgrad3_kernel(const __grid_con
     uint64_t* st_empty = st_full + 2;                                 // [2]
     uint64_t* a_full = st_empty + 2;                                  // [2]
     uint64_t* a_empty = a_full + 2;                                   // [2]
-    uint64_t* w_full = a_empty + 2;
+    uint64_t* xt_full = a_empty + 2;                                  // [4]
+    uint64_t* xt_empty = xt_full + NXT;                               // [4]
+    uint64_t* w_full = xt_empty + NXT;
     uint64_t* g1_done = w_full + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(g1_done + 1);
 
@@ -77,6 +84,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dgrad3_kernel(const __grid_con
         tma_prefetch_desc(&tmW); tma_prefetch_desc(&tmDZ); tma_prefetch_desc(&tmXT);
         for (int i = 0; i < NRING; ++i) { mbar_init(&d_full[i], 1); mbar_init(&d_empty[i], 4); }
         for (int i = 0; i < 2; ++i) { mbar_init(&st_full[i], 8); mbar_init(&st_empty[i], 1); mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < NXT; ++i) { mbar_init(&xt_full[i], 1); mbar_init(&xt_empty[i], 1); }
         mbar_init(w_full, 1);
         mbar_init(g1_done, 1);
         fence_barrier_init();
@@ -94,13 +102,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dgrad3_kernel(const __grid_con
             constexpr uint32_t idesc_d = make_idesc_bf16(TILE_M, 64, false, false);    // dz2 (K-major) x W2' chunk (K-major)
             constexpr uint32_t idesc_g = make_idesc_bf16(TILE_M, 16, true, false);     // dz1 (MN-major) x xext^T (K-major)
             const uint32_t w_addr = smem_u32(smem + OFF_W), a_addr0 = smem_u32(smem + OFF_A), st_addr = smem_u32(smem + OFF_ST);
+            const uint32_t xt_addr0 = smem_u32(smem + OFF_XT);
             // chunk c of local tile t: dR chunk = dz2 tile . W2'[64 c .. 64 c + 63]^T  -> ring slot (t NC + c) % 7
             auto mma_chunk = [&](int t, int c) {
+                const uint32_t a_addr = a_addr0 + (t & 1) * A_BYTES;
                 if (c == 0) {
                     mbar_wait(&a_full[t & 1], ((uint32_t)t >> 1) & 1);
+                    mbar_wait(&xt_full[t % NXT], ((uint32_t)t / NXT) & 1);
                     tc_fence_after();
+                    // db2[j] = sum_n dz2[n][j]: the dz2 tile read as an MN-major A operand against the constant-one column (5) of xext
+                    const uint32_t xt_addr = xt_addr0 + (t % NXT) * XT_BYTES;
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks)
+                        mma_bf16(tmem_base + 496u, make_smem_desc(a_addr + ks * 2048, TILE_M * 128, 1024),
+                                 make_smem_desc(xt_addr + (ks >> 2) * (16 * 128) + (ks & 3) * 32, 16, 1024), idesc_g, (t | ks) != 0);
                 }
-                const uint32_t a_addr = a_addr0 + (t & 1) * A_BYTES;
                 const uint32_t k = (uint32_t)(t * NC + c), slot = k % NRING;
                 mbar_wait(&d_empty[slot], ((k / NRING) & 1) ^ 1);
                 tc_fence_after();
@@ -109,11 +125,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dgrad3_kernel(const __grid_con
                     mma_bf16(tmem_base + slot * 64, make_smem_desc(a_addr + (ks >> 2) * (TILE_M * 128) + (ks & 3) * 32, 16, 1024),
                              make_smem_desc(w_addr + ((ks >> 2) * MAX_NC + c) * WCHUNK_BYTES + (ks & 3) * 32, 16, 1024), idesc_d, ks != 0);
                 mma_commit(&d_full[slot]);
+                if (c == NC - 1) mma_commit(&a_empty[t & 1]);       // the dz2 tile can be reloaded two tiles ahead
             };
             // chunk pair p of local tile t: G1[128 p ..] += dz1 pair^T . xext tile
             auto g1_pair = [&](int t, int p) {
-                const uint32_t xt_addr = a_addr0 + (t & 1) * A_BYTES + 2 * TILE_M * 128;
+                const uint32_t xt_addr = xt_addr0 + (t % NXT) * XT_BYTES;
                 const uint32_t pk = (uint32_t)(t * NP + p), sb = pk & 1;
+                if (p == 0) mbar_wait(&xt_full[t % NXT], ((uint32_t)t / NXT) & 1);
                 mbar_wait(&st_full[sb], (pk >> 1) & 1);
                 tc_fence_after();
 #pragma unroll
@@ -121,7 +139,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dgrad3_kernel(const __grid_con
                     mma_bf16(tmem_base + 448u + (uint32_t)(p * 16), make_smem_desc(st_addr + sb * (2 * TILE_M * 128) + ks * 2048, TILE_M * 128, 1024),
                              make_smem_desc(xt_addr + (ks >> 2) * (16 * 128) + (ks & 3) * 32, 16, 1024), idesc_g, (t | ks) != 0);
                 mma_commit(&st_empty[sb]);
-                if (p == NP - 1) mma_commit(&a_empty[t & 1]);       // dz2 and xext^T tiles of this tile are no longer read
+                if (p == NP - 1) mma_commit(&xt_empty[t % NXT]);
             };
             mbar_wait(w_full, 0);
             for (int c = 0; c < NC; ++c) mma_chunk(0, c);
@@ -145,15 +163,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dgrad3_kernel(const __grid_con
             for (int kb = 0; kb < 2; ++kb)
                 for (int c = 0; c < NC; ++c) tma_load_3d(smem + OFF_W + (kb * MAX_NC + c) * WCHUNK_BYTES, &tmW, w_full, kb * KB, c * 64, agent);
             for (int t = 0; t < T; ++t) {
-                const int b = t & 1;
+                const int b = t & 1, xb = t % NXT;
+                const int r0 = tile_of(t) * TILE_M;
+                mbar_wait(&xt_empty[xb], (((uint32_t)t / NXT) & 1) ^ 1);
+                uint8_t* xdst = smem + OFF_XT + xb * XT_BYTES;
+                mbar_expect_tx(&xt_full[xb], XT_BYTES);
+                tma_load_3d(xdst, &tmXT, &xt_full[xb], r0, 0, agent);
+                tma_load_3d(xdst + 16 * 128, &tmXT, &xt_full[xb], r0 + KB, 0, agent);
                 mbar_wait(&a_empty[b], (((uint32_t)t >> 1) & 1) ^ 1);
                 uint8_t* dst = smem + OFF_A + b * A_BYTES;
                 mbar_expect_tx(&a_full[b], A_BYTES);
-                const int r0 = tile_of(t) * TILE_M;
                 tma_load_3d(dst, &tmDZ, &a_full[b], 0, r0, agent);
                 tma_load_3d(dst + TILE_M * 128, &tmDZ, &a_full[b], KB, r0, agent);
-                tma_load_3d(dst + 2 * TILE_M * 128, &tmXT, &a_full[b], r0, 0, agent);
-                tma_load_3d(dst + 2 * TILE_M * 128 + 16 * 128, &tmXT, &a_full[b], r0 + KB, 0, agent);
             }
         }
     } else {
@@ -172,8 +193,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dgrad3_kernel(const __grid_con
                 const uint32_t pk = (uint32_t)(t * NP + (c >> 1)), sb = pk & 1;
                 mbar_wait(&d_full[slot], (k / NRING) & 1);
                 tc_fence_after();
-                mbar_wait(&st_empty[sb], ((pk >> 1) & 1) ^ 1);
-                uint8_t* srow = smem + OFF_ST + sb * (2 * TILE_M * 128) + (c & 1) * (TILE_M * 128) + row * 128;
+                uint32_t pkd[32];            // the masked chunk as bf16 pairs: the TMEM slot is released before the staging buffer is needed
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     float v[32];
@@ -183,17 +203,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dgrad3_kernel(const __grid_con
                     for (int j = 0; j < 32; ++j)
                         if (m & (0x80000000u >> j)) v[j] = 0.0f;
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {
-                        const uint4 pkd = make_uint4(pack_bf16x2(v[8 * kk], v[8 * kk + 1]), pack_bf16x2(v[8 * kk + 2], v[8 * kk + 3]),
-                                                     pack_bf16x2(v[8 * kk + 4], v[8 * kk + 5]), pack_bf16x2(v[8 * kk + 6], v[8 * kk + 7]));
-                        *reinterpret_cast<uint4*>(srow + (((h * 4 + kk) ^ (row & 7)) << 4)) = pkd;
-                    }
+                    for (int j = 0; j < 16; ++j) pkd[h * 16 + j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
                 }
                 tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&d_empty[slot]);
+                mbar_wait(&st_empty[sb], ((pk >> 1) & 1) ^ 1);
+                uint8_t* srow = smem + OFF_ST + sb * (2 * TILE_M * 128) + (c & 1) * (TILE_M * 128) + row * 128;
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk)
+                    *reinterpret_cast<uint4*>(srow + ((kk ^ (row & 7)) << 4)) = make_uint4(pkd[4 * kk], pkd[4 * kk + 1], pkd[4 * kk + 2], pkd[4 * kk + 3]);
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) {
-                    mbar_arrive(&d_empty[slot]);
                     mbar_arrive(&st_full[sb]);
                     if ((NC & 1) && c == NC - 1) mbar_arrive(&st_full[sb]);     // a lone last chunk stands in for its missing partner
                 }
@@ -213,6 +235,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dgrad3_kernel(const __grid_con
                     for (int j = 0; j < 16; ++j) atomicAdd(dst + j, v[j]);
                 }
             }
+            tc_fence_before();
+        }
+        if (grp == 1 && T > 0) {             // layer-2 bias gradient: column 5 of the dz2^T xext accumulator, lane = j
+            mbar_wait(g1_done, 0);
+            tc_fence_after();
+            float v[16];
+            tmem_ld16(tmem_base + 496u + tlane, v);
+            atomicAdd(g.db2 + (int64_t)agent * g.db2_stride + row, v[5]);
             tc_fence_before();
         }
     }
@@ -257,11 +287,12 @@ static int make_map(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t 
 }
 
 // DZ: bf16 [A*R][128];  W2b: bf16 [A][F][128] folded layer-2 kernel;  mask: [A*R][mask_words];  xextT: bf16 [A][16][Rp]
-// (Rp = rows per agent rounded up to a multiple of 64);  G1: fp32 [A][Fp][16], accumulated into (zero it first).
+// (Rp = rows per agent rounded up to a multiple of 64);  G1: fp32 [A][Fp][16] and db2: fp32 [A][db2_stride] (first 128 entries),
+// both accumulated into (zero them first).
 int run(int A, int64_t R, int F, const bf16* DZ, const bf16* W2b, const uint32_t* mask, int mask_words, const bf16* xextT, int64_t Rp, float* G1,
-        int Fp, cudaStream_t st) {
+        int Fp, float* db2, int64_t db2_stride, cudaStream_t st) {
     AVD_REQUIRE(A >= 1 && R >= 1 && F >= 64 && F % 16 == 0 && F <= MAX_NC * 64 && Fp >= F, "bad sizes for the fused dgrad kernel");
-    AVD_REQUIRE(DZ && W2b && mask && xextT && G1 && Rp % 64 == 0 && Rp >= R, "null buffer / bad pitch");
+    AVD_REQUIRE(DZ && W2b && mask && xextT && G1 && db2 && Rp % 64 == 0 && Rp >= R, "null buffer / bad pitch");
     static bool attr_set = false;
     if (!attr_set) {
         AVD_CUDA_OK(cudaFuncSetAttribute(dgrad3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
@@ -272,7 +303,7 @@ int run(int A, int64_t R, int F, const bf16* DZ, const bf16* W2b, const uint32_t
     if (int rc = make_map(&tmDZ, DZ, L2N, (uint64_t)R, (uint64_t)A, L2N, (uint64_t)R * L2N, TILE_M)) return rc;
     if (int rc = make_map(&tmXT, xextT, (uint64_t)R, 16, (uint64_t)A, (uint64_t)Rp, (uint64_t)16 * Rp, 16)) return rc;
     Args g;
-    g.A = A; g.F = F; g.NC = (F + 63) / 64; g.R = R; g.mask = mask; g.mask_words = mask_words; g.G1 = G1; g.Fp = Fp;
+    g.A = A; g.F = F; g.NC = (F + 63) / 64; g.R = R; g.mask = mask; g.mask_words = mask_words; g.G1 = G1; g.Fp = Fp; g.db2 = db2; g.db2_stride = db2_stride;
     g.tiles_per_agent = (int)((R + TILE_M - 1) / TILE_M);
     g.ctas_per_agent = std::max(1, std::min(g.tiles_per_agent, sm_count() / std::max(1, A)));
     dgrad3_kernel<<<(unsigned)(g.ctas_per_agent * A), NUM_THREADS, SMEM_BYTES, st>>>(tmW, tmDZ, tmXT, g);

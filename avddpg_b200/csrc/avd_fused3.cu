@@ -7,14 +7,15 @@
 //   --pass 1-->  q = relu(z2 + b2') . w3' + b3'       (row sum split over four warps, combined through shared memory)
 //   --pass 2 (backward modes)-->  dq from the loss, dz2 = dq w3' [z2 + b2' > 0] as bf16 into a shared-memory tile,
 //        per-thread partial sums of  U[j] = sum_n dq_n relu(z2)[n][j]  (head / BN2 weight gradients),  sum dq,  loss
-//   --TMA stores-->  r1 and dz2 tiles to HBM for the weight-gradient GEMMs (avd_umma.cu) and the dgrad GEMM
+//   --TMA store-->  the dz2 tile to HBM for the weight-gradient kernel (avd_wgrad3.cu, which recomputes r1 from the inputs)
+//        and the dgrad kernel (avd_dgrad3.cu)
 //   MODE_CRITIC_ACTION additionally runs the action columns of the dgrad as a third MMA (dz2 . W2'[action rows]^T) and
 //   reduces it to d(-mean q)/d(action) per row -- the critic -> actor link (trainer.py:503-506) never leaves the SM.
 //
 // BatchNorm folding (inference affine):  W2' = diag(sc1) W2,  b2' = b2 + sh1 W2  (pack_fold_kernel);
 // w3' = sc2 * w3,  b3' = b3 + sh2 . w3  (table set-up below).  One CTA works on ONE agent: weights and
 // tables are loaded once.  17 warps: warp 0 issues TMA / MMA, warps 1..16 are identical consumers (TMEM lane quadrant =
-// warp % 4, column quarter = (warp - 1) / 4) running a software pipeline  pass2(i-1) | convert(i+1) | pass1(i)  so that
+// warp % 4, column quarter = (warp - 1) / 4) running a software pipeline  convert(i+1) | pass2(i-1) | pass1(i)  so that
 // every MMA has a full stage of other work to hide behind.
 // Reference semantics: agent/model.py:19-37 (actor), 55-83 (critic); workers/trainer.py:489-506.
 #include <cudaTypedefs.h>
@@ -91,8 +92,7 @@ __device__ __forceinline__ uint32_t pack2(bf16 a, bf16 b) {
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(NUM_THREADS, 1) fused3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmR,
-                                                                const __grid_constant__ CUtensorMap tmDZ, Args g) {
+__global__ void __launch_bounds__(NUM_THREADS, 1) fused3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmDZ, Args g) {
     constexpr bool CRITIC = MODE != MODE_ACTOR_OUT && MODE != MODE_ACTOR_BWD;
     constexpr bool BWD = MODE == MODE_CRITIC_BWD || MODE == MODE_ACTOR_BWD;      // full backward: masks, r1 / dz2 to HBM, U
     constexpr bool ACTION = MODE == MODE_CRITIC_ACTION;                          // backward to the action input only
@@ -132,8 +132,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused3_kernel(const __grid_con
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmW);
-        if (BWD) { tma_prefetch_desc(&tmR); tma_prefetch_desc(&tmDZ); }
-        for (int i = 0; i < MAX_KB; ++i) { mbar_init(&a_full[i], i < 4 ? 4 : 8); mbar_init(&a_empty[i], BWD ? 2 : 1); }
+        if (BWD) tma_prefetch_desc(&tmDZ);
+        for (int i = 0; i < MAX_KB; ++i) { mbar_init(&a_full[i], i < 4 ? 4 : 8); mbar_init(&a_empty[i], 1); }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], NCONS);
             mbar_init(&part_full[i], NCONS); mbar_init(&x_full[i], 4);
@@ -179,11 +179,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused3_kernel(const __grid_con
             wa_tab[c] = wa;
             ba_tab[c] = ba;
         }
-        if (BWD && !CRITIC && ct < TILE_M) {   // constant tile [1 0 0 ...] behind the 256 actor features (slot 4 is otherwise unused)
-            uint8_t* crow = smem + OFF_RING + 4 * SLOT_BYTES + ct * 128;
-            *reinterpret_cast<uint4*>(crow + ((0 ^ (ct & 7)) << 4)) = make_uint4(0x00003F80u, 0u, 0u, 0u);      // bf16 1.0 = 0x3F80
-            *reinterpret_cast<uint4*>(crow + ((1 ^ (ct & 7)) << 4)) = make_uint4(0u, 0u, 0u, 0u);
-        }
         fence_proxy_async();
     }
     tc_fence_before();
@@ -222,14 +217,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused3_kernel(const __grid_con
                              make_desc_noswz(b1_addr + h * (L2N * 16), L1N * 16, 128), idesc, 0);
                 mma_commit(z1_full);
             };
-            auto mma2 = [&](int t) {          // layer 2 of local tile t -> TMEM accumulator t & 1
+            auto mma2 = [&](int t) {          // layer 2 of local tile t -> TMEM accumulator t & 1 (+ r1 tile stores, backward modes)
                 mbar_wait(&acc_empty[t & 1], (((uint32_t)t >> 1) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t tacc = tmem_base + (uint32_t)((t & 1) * L2N);
                 for (int kb = 0; kb < NKB; ++kb) {
                     mbar_wait(&a_full[kb], (uint32_t)t & 1);
                     tc_fence_after();
-                    if (BWD) tma_store_3d(&tmR, smem + OFF_RING + kb * SLOT_BYTES, kb * KB, tile_of(t) * TILE_M, agent);
                     const uint32_t a_addr = smem_u32(smem + OFF_RING + kb * SLOT_BYTES);
                     const int nm = min(4, (F - kb * KB) / 16);
                     for (int j = 0; j < nm; ++j)
@@ -238,17 +232,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused3_kernel(const __grid_con
                     mma_commit(&a_empty[kb]);
                 }
                 mma_commit(&acc_full[t & 1]);
-                if (BWD && !CRITIC) tma_store_3d(&tmR, smem + OFF_RING + 4 * SLOT_BYTES, L1N, tile_of(t) * TILE_M, agent);   // the constant-one column
-                if (BWD) {                    // the r1 slots are also free only once the TMA stores have read them
-                    bulk_commit();
-                    bulk_wait_read0();
-                    for (int kb = 0; kb < NKB; ++kb) mbar_arrive(&a_empty[kb]);
-                }
             };
             auto dz_out = [&](int t) {        // dz2 tile of local tile t: to HBM (BWD) or through the action-column dgrad MMA (ACTION)
                 mbar_wait(dz_full, (uint32_t)t & 1);
                 tc_fence_after();
-                if (BWD) {
+                if (BWD) {                    // the tile is free again once the TMA stores have read it
                     tma_store_3d(&tmDZ, smem + OFF_DZ, 0, tile_of(t) * TILE_M, agent);
                     tma_store_3d(&tmDZ, smem + OFF_DZ + SLOT_BYTES, KB, tile_of(t) * TILE_M, agent);
                     bulk_commit();
@@ -267,19 +255,34 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused3_kernel(const __grid_con
             };
 
             mbar_wait(w_full, 0);
-            mma1(0);
-            mma2(0);
-            if (T > 1) mma1(1);
-            for (int i = 0; i < T; ++i) {
-                if (BWD && i >= 1) dz_out(i - 1);
-                if (i + 1 < T) mma2(i + 1);
-                if (ACTION && i >= 1) dz_out(i - 1);
-                if (i + 2 < T) {
-                    if (ACTION && i >= 1) mbar_wait(dra_empty, (uint32_t)(i - 1) & 1);
-                    mma1(i + 2);
+            if (ACTION) {
+                mma1(0);
+                mma2(0);
+                if (T > 1) mma1(1);
+                for (int i = 0; i < T; ++i) {
+                    if (i + 1 < T) mma2(i + 1);
+                    if (i >= 1) dz_out(i - 1);
+                    if (i + 2 < T) {
+                        if (i >= 1) mbar_wait(dra_empty, (uint32_t)(i - 1) & 1);
+                        mma1(i + 2);
+                    }
                 }
+                dz_out(T - 1);
+            } else {
+                // The tensor pipe executes in issue order: the (tiny) layer-1 MMA of the NEXT tile goes in front of the layer-2
+                // MMA, so that the converters of the next iteration never wait behind a whole layer-2 product.
+                mma1(0);
+                if (T > 1) mma1(1);
+                mma2(0);
+                for (int i = 0; i < T; ++i) {
+                    if (i + 1 < T) {
+                        if (i + 2 < T) mma1(i + 2);
+                        mma2(i + 1);
+                    }
+                    if (BWD && i >= 1) dz_out(i - 1);
+                }
+                if (BWD) dz_out(T - 1);
             }
-            if (HAS_DZ) dz_out(T - 1);
         }
     } else {
         // ================================================ consumers ================================================
@@ -293,6 +296,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused3_kernel(const __grid_con
 #pragma unroll
         for (int j = 0; j < 32; ++j) u[j] = 0.0f;
         float sdq_acc = 0.0f, loss_acc = 0.0f;
+        uint32_t rp[16];                     // backward modes: relu(z2 + b2') of this thread's 32 columns as bf16 pairs, pass 1 -> pass 2
+#pragma unroll
+        for (int j = 0; j < 16; ++j) rp[j] = 0u;
 
         auto rowinfo = [&](int tc, bool& valid) -> int64_t {
             const int64_t r_in = (int64_t)tile_of(tc) * TILE_M + row;
@@ -335,16 +341,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused3_kernel(const __grid_con
                 float z[32];
                 tmem_ld32(tmem_base + 256u + (uint32_t)(c4 * 64 + h * 32) + tlane, z);
                 uint32_t m = 0;
+                if (BWD) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    m = __funnelshift_l(__float_as_uint(z[j]), m, 1);
-                    z[j] = fmaxf(z[j], 0.0f);
+                    for (int j = 0; j < 32; ++j) m = __funnelshift_l(__float_as_uint(z[j]), m, 1);
                 }
                 neg[h] = m;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    const uint4 pk = make_uint4(pack_bf16x2(z[8 * k], z[8 * k + 1]), pack_bf16x2(z[8 * k + 2], z[8 * k + 3]),
-                                                pack_bf16x2(z[8 * k + 4], z[8 * k + 5]), pack_bf16x2(z[8 * k + 6], z[8 * k + 7]));
+                    const uint4 pk = make_uint4(pack_relu_bf16x2(z[8 * k], z[8 * k + 1]), pack_relu_bf16x2(z[8 * k + 2], z[8 * k + 3]),
+                                                pack_relu_bf16x2(z[8 * k + 4], z[8 * k + 5]), pack_relu_bf16x2(z[8 * k + 6], z[8 * k + 7]));
                     *reinterpret_cast<uint4*>(slot + (((h * 4 + k) ^ (row & 7)) << 4)) = pk;      // SWIZZLE_128B
                 }
             }
@@ -361,19 +366,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused3_kernel(const __grid_con
                 uint32_t m = 0;
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
-                    const float zz = fmaf(a_val, wa_tab[j0 + j], ba_tab[j0 + j]);
-                    m = __funnelshift_l(__float_as_uint(zz), m, 1);
-                    z[j] = fmaxf(zz, 0.0f);
+                    z[j] = fmaf(a_val, wa_tab[j0 + j], ba_tab[j0 + j]);
+                    if (BWD) m = __funnelshift_l(__float_as_uint(z[j]), m, 1);
                 }
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const int col = j0 + 8 * k;
                     if (col < la) {
-                        const uint4 pk = make_uint4(pack_bf16x2(z[8 * k], z[8 * k + 1]), pack_bf16x2(z[8 * k + 2], z[8 * k + 3]),
-                                                    pack_bf16x2(z[8 * k + 4], z[8 * k + 5]), pack_bf16x2(z[8 * k + 6], z[8 * k + 7]));
+                        const uint4 pk = make_uint4(pack_relu_bf16x2(z[8 * k], z[8 * k + 1]), pack_relu_bf16x2(z[8 * k + 2], z[8 * k + 3]),
+                                                    pack_relu_bf16x2(z[8 * k + 4], z[8 * k + 5]), pack_relu_bf16x2(z[8 * k + 6], z[8 * k + 7]));
                         *reinterpret_cast<uint4*>(aslot + (((col >> 3) ^ (row & 7)) << 4)) = pk;
-                    } else if (BWD && col < la + 16) {   // [1 0 0 ...]: the constant-one feature that makes the wgrad GEMM produce db2
-                        *reinterpret_cast<uint4*>(aslot + (((col >> 3) ^ (row & 7)) << 4)) = make_uint4(col == la ? 0x00003F80u : 0u, 0u, 0u, 0u);
                     }
                 }
                 fence_proxy_async();
@@ -396,16 +398,25 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused3_kernel(const __grid_con
             for (int j = 0; j < 32; j += 4) {
                 const float4 b4 = *reinterpret_cast<const float4*>(b2f_tab + c4 * 32 + j);
                 const float4 w4 = *reinterpret_cast<const float4*>(w3f_tab + c4 * 32 + j);
-                acc = fmaf(fmaxf(v[j] + b4.x, 0.0f), w4.x, acc);
-                acc = fmaf(fmaxf(v[j + 1] + b4.y, 0.0f), w4.y, acc);
-                acc = fmaf(fmaxf(v[j + 2] + b4.z, 0.0f), w4.z, acc);
-                acc = fmaf(fmaxf(v[j + 3] + b4.w, 0.0f), w4.w, acc);
+                const float r0 = fmaxf(v[j] + b4.x, 0.0f), r1 = fmaxf(v[j + 1] + b4.y, 0.0f);
+                const float r2 = fmaxf(v[j + 2] + b4.z, 0.0f), r3 = fmaxf(v[j + 3] + b4.w, 0.0f);
+                acc = fmaf(r0, w4.x, acc);
+                acc = fmaf(r1, w4.y, acc);
+                acc = fmaf(r2, w4.z, acc);
+                acc = fmaf(r3, w4.w, acc);
+                if (BWD) {
+                    rp[j >> 1] = pack_bf16x2(r0, r1);
+                    rp[(j >> 1) + 1] = pack_bf16x2(r2, r3);
+                }
             }
             part[(buf * 4 + c4) * TILE_M + row] = acc;
-            if (!HAS_DZ) tc_fence_before();
+            if (!ACTION) tc_fence_before();
             __syncwarp();
             if (lane == 0) {
-                if (!HAS_DZ) mbar_arrive(&acc_empty[buf]);       // forward modes are done with the accumulator
+                // Only the action mode reads the accumulator again in pass 2.  In the forward modes the quarter-0 warps release it
+                // in pass 2 instead: the layer-2 MMA of tile tc + 2 (and with it every pass1(tc + 2) that overwrites `part`)
+                // then cannot start before they have combined the partial sums of tile tc.
+                if (BWD || (!ACTION && c4 != 0)) mbar_arrive(&acc_empty[buf]);
                 mbar_arrive(&part_full[buf]);
             }
         };
@@ -429,6 +440,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused3_kernel(const __grid_con
                 else if (MODE == MODE_TARGET) o = yv + g.gamma * qv;                 // trainer.py:494 (no terminal mask)
                 else o = qv;
                 if (valid) g.out[nrow] = o;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[buf]);
                 return;
             }
             float dq;
@@ -448,19 +461,33 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused3_kernel(const __grid_con
             }
             if (c4 == 0) sdq_acc += dq;
             float v[32];
-            tmem_ld32(tmem_base + (uint32_t)(buf * L2N + c4 * 32) + tlane, v);
-            tc_fence_before();
+            if (ACTION) {
+                tmem_ld32(tmem_base + (uint32_t)(buf * L2N + c4 * 32) + tlane, v);
+                tc_fence_before();
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-                const float4 b4 = *reinterpret_cast<const float4*>(b2f_tab + c4 * 32 + j);
-                const float4 w4 = *reinterpret_cast<const float4*>(w3f_tab + c4 * 32 + j);
-                const float bb[4] = {b4.x, b4.y, b4.z, b4.w}, ww[4] = {w4.x, w4.y, w4.z, w4.w};
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 b4 = *reinterpret_cast<const float4*>(b2f_tab + c4 * 32 + j);
+                    const float4 w4 = *reinterpret_cast<const float4*>(w3f_tab + c4 * 32 + j);
+                    v[j] = (v[j] + b4.x > 0.0f ? dq : 0.0f) * w4.x;
+                    v[j + 1] = (v[j + 1] + b4.y > 0.0f ? dq : 0.0f) * w4.y;
+                    v[j + 2] = (v[j + 2] + b4.z > 0.0f ? dq : 0.0f) * w4.z;
+                    v[j + 3] = (v[j + 3] + b4.w > 0.0f ? dq : 0.0f) * w4.w;
+                }
+            } else {
+                // relu(z2 + b2') comes back from the bf16 stash of pass 1 (exact sign; U uses the bf16-rounded value, like every
+                // other tensor-core operand of this path), so the TMEM accumulator was released a whole stage earlier
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const float t = v[j + k] + bb[k];
-                    const float e = t > 0.0f ? dq : 0.0f;
-                    if (BWD) u[j + k] = fmaf(e, t, u[j + k]);
-                    v[j + k] = e * ww[k];
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 w4 = *reinterpret_cast<const float4*>(w3f_tab + c4 * 32 + j);
+                    const float ww[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t pr = rp[(j + k) >> 1];
+                        const float r = __uint_as_float((k & 1) ? (pr & 0xFFFF0000u) : (pr << 16));
+                        const float e = r > 0.0f ? dq : 0.0f;
+                        u[j + k] = fmaf(e, r, u[j + k]);
+                        v[j + k] = e * ww[k];
+                    }
                 }
             }
             mbar_wait(dz_empty, ((uint32_t)tc & 1) ^ 1);
@@ -473,7 +500,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused3_kernel(const __grid_con
             }
             fence_proxy_async();
             __syncwarp();
-            if (lane == 0) { mbar_arrive(&acc_empty[buf]); mbar_arrive(dz_full); }
+            if (lane == 0) {
+                if (ACTION) mbar_arrive(&acc_empty[buf]);
+                mbar_arrive(dz_full);
+            }
         };
 
         // ---- stage 4 (MODE_CRITIC_ACTION): d loss / d action = sum_f [za_f > 0] dRa_f wa_f      (trainer.py:503-506)
@@ -509,10 +539,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused3_kernel(const __grid_con
         else if (cw < 8 && T > 1) produce_x(1);
         convert(0);
         for (int i = 0; i < T; ++i) {
-            if (i >= 1) pass2(i - 1);
-            if (i + 1 < T) convert(i + 1);
-            pass1(i);
-            if (ACTION && i >= 1) action_grad(i - 1);
+            if (ACTION) {                    // the action-column dgrad borrows the z1 columns between convert(i+1) and the next layer-1 MMA
+                if (i >= 1) pass2(i - 1);
+                if (i + 1 < T) convert(i + 1);
+                pass1(i);
+                if (i >= 1) action_grad(i - 1);
+            } else {                         // every stage waits on work that is at least one stage old
+                if (i + 1 < T) convert(i + 1);
+                if (i >= 1) pass2(i - 1);
+                pass1(i);
+            }
         }
         pass2(T - 1);
         if (ACTION) action_grad(T - 1);
@@ -576,26 +612,26 @@ static int make_map(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t 
 }
 
 bool supported(const avd_net_dims& d) {
-    return d.l2 == L2N && d.ns >= 1 && d.ns <= 4 && d.l1 == L1N && d.la % 16 == 0 && d.la >= 16 && d.la <= 48;   // la = 64 leaves no pad column for the constant-one feature
+    return d.l2 == L2N && d.ns >= 1 && d.ns <= 4 && d.l1 == L1N && d.la % 16 == 0 && d.la >= 16 && d.la <= 64;
 }
 
 template <int MODE>
-static int launch(const CUtensorMap& tmW, const CUtensorMap& tmR, const CUtensorMap& tmDZ, const Args& g, dim3 grid, cudaStream_t st) {
+static int launch(const CUtensorMap& tmW, const CUtensorMap& tmDZ, const Args& g, dim3 grid, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
         AVD_CUDA_OK(cudaFuncSetAttribute(fused3_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         attr_set = true;
     }
-    fused3_kernel<MODE><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmW, tmR, tmDZ, g);
+    fused3_kernel<MODE><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmW, tmDZ, g);
     AVD_LAUNCH_OK();
     return AVD_OK;
 }
 
 // One pass.  W2T: bf16 [A][128][F] folded layer-2 kernel (K-major), b2f: [A][128]  (pack_fold_kernel).
-// R1_out: bf16 [A*R][r1_pitch] (backward modes; columns F..F+15 receive [1 0 ... 0]), DZ_out: bf16 [A*R][128] (backward modes).
+// Backward modes: mask_out [A*R][2*ceil(F/64)] sign masks of z1, DZ_out: bf16 [A*R][128], U [A][128] and sdq [A] accumulated into.
 int run(int mode, const avd_net_dims& d, int A, int64_t R, const float* params, int64_t pstride, const bf16* W2T, const float* b2f, const float* s,
         int64_t s_rs, int64_t s_cs, const float* act, const float* rew, float gamma, float high, const float* y, const float* dpi, float* out,
-        bf16* R1_out, int64_t r1_pitch, uint32_t* mask_out, bf16* DZ_out, float* U, float* sdq, float* loss, cudaStream_t st) {
+        uint32_t* mask_out, bf16* DZ_out, float* U, float* sdq, float* loss, cudaStream_t st) {
     if (!supported(d)) {
         set_error("fused pass kernel does not support these layer sizes");
         return AVD_ERR_UNSUPPORTED;
@@ -605,16 +641,13 @@ int run(int mode, const avd_net_dims& d, int A, int64_t R, const float* params, 
     const int F = critic ? d.l1 + d.la : d.l1;
     AVD_REQUIRE(params && W2T && b2f && s, "null buffer");
     AVD_REQUIRE(!critic || act, "critic passes need actions");
-    AVD_REQUIRE(!bwd || (R1_out && mask_out && DZ_out && U && sdq && r1_pitch >= F + 16 && r1_pitch % 8 == 0), "backward passes need r1 / mask / dz2 / U / sdq outputs");
+    AVD_REQUIRE(!bwd || (mask_out && DZ_out && U && sdq), "backward passes need mask / dz2 / U / sdq outputs");
     AVD_REQUIRE(bwd || out, "null output");
-    CUtensorMap tmW, tmR, tmDZ;
+    CUtensorMap tmW, tmDZ;
     if (int rc = make_map(&tmW, W2T, (uint64_t)F, L2N, (uint64_t)A, (uint64_t)F, (uint64_t)F * L2N)) return rc;
-    tmR = tmW;
     tmDZ = tmW;
-    if (bwd) {
-        if (int rc = make_map(&tmR, R1_out, (uint64_t)F + 16, (uint64_t)R, (uint64_t)A, (uint64_t)r1_pitch, (uint64_t)R * r1_pitch)) return rc;
+    if (bwd)
         if (int rc = make_map(&tmDZ, DZ_out, L2N, (uint64_t)R, (uint64_t)A, L2N, (uint64_t)R * L2N)) return rc;
-    }
     Args g;
     g.d = d; g.A = A; g.R = R; g.params = params; g.pstride = pstride; g.b2f = b2f; g.s = s; g.s_rs = s_rs; g.s_cs = s_cs; g.act = act;
     g.rew = rew; g.gamma = gamma; g.high = high; g.y = y; g.dpi = dpi; g.out = out; g.mask_out = mask_out; g.mask_words = 2 * ((F + KB - 1) / KB);
@@ -623,12 +656,12 @@ int run(int mode, const avd_net_dims& d, int A, int64_t R, const float* params, 
     g.ctas_per_agent = std::max(1, std::min(g.tiles_per_agent, sm_count() / std::max(1, A)));
     const dim3 grid((unsigned)(g.ctas_per_agent * A));
     switch (mode) {
-        case MODE_ACTOR_OUT: return launch<MODE_ACTOR_OUT>(tmW, tmR, tmDZ, g, grid, st);
-        case MODE_TARGET: return launch<MODE_TARGET>(tmW, tmR, tmDZ, g, grid, st);
-        case MODE_Q: return launch<MODE_Q>(tmW, tmR, tmDZ, g, grid, st);
-        case MODE_CRITIC_BWD: return launch<MODE_CRITIC_BWD>(tmW, tmR, tmDZ, g, grid, st);
-        case MODE_ACTOR_BWD: return launch<MODE_ACTOR_BWD>(tmW, tmR, tmDZ, g, grid, st);
-        case MODE_CRITIC_ACTION: return launch<MODE_CRITIC_ACTION>(tmW, tmR, tmDZ, g, grid, st);
+        case MODE_ACTOR_OUT: return launch<MODE_ACTOR_OUT>(tmW, tmDZ, g, grid, st);
+        case MODE_TARGET: return launch<MODE_TARGET>(tmW, tmDZ, g, grid, st);
+        case MODE_Q: return launch<MODE_Q>(tmW, tmDZ, g, grid, st);
+        case MODE_CRITIC_BWD: return launch<MODE_CRITIC_BWD>(tmW, tmDZ, g, grid, st);
+        case MODE_ACTOR_BWD: return launch<MODE_ACTOR_BWD>(tmW, tmDZ, g, grid, st);
+        case MODE_CRITIC_ACTION: return launch<MODE_CRITIC_ACTION>(tmW, tmDZ, g, grid, st);
     }
     set_error("unknown fused pass mode %d", mode);
     return AVD_ERR_INVALID_ARG;

@@ -133,6 +133,13 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// relu + round-to-nearest bf16 + pack in ONE instruction (F2FP.RELU): the max() never touches the half-rate ALU pipe
+__device__ __forceinline__ uint32_t pack_relu_bf16x2(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+
 // ---- coalesced store of a 32 x 32 fp32 block held one-row-per-lane -----------------------------------
 // After tcgen05.ld.32x32b every lane owns 32 consecutive columns of ITS row, so a direct store makes each
 // instruction touch 32 different 128-byte lines (32 L1 wavefronts).  Staging the block through a padded

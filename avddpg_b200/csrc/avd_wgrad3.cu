@@ -1,0 +1,335 @@
+// avd_wgrad3.cu -- layer-2 weight gradient of the DDPG learn step with the activations RECOMPUTED on chip (sm_100a):
+//
+//   G2[f][j] += sum_n r1[n][f] dz2[n][j],      r1 = relu(x W1 + b1)   (the BN-folded formulation of avd_fused3.cu)
+//
+// r1 is 608 B per row as bf16; the inputs it is made of are 16-20 B.  So instead of streaming r1 back from HBM, each CTA
+// owns one 128-feature slab of one agent and, per 128-row tile,
+//   x tile --tcgen05.mma (hi/lo split bf16, K = 16)--> z1 slab in TMEM --converter warps: relu, bf16--> r1 slab in shared
+//   memory, laid out as the MN-major A operand (M = features, K = rows) --tcgen05.mma against the dz2 tile (TMA, MN-major B)-->
+//   one 128 x 128 fp32 accumulator that stays in TMEM for the whole kernel and is added to global memory once per CTA.
+// HBM traffic per row: 256 B (dz2, re-read once per feature slab, mostly from L2) + 16-20 B inputs; nothing is written.
+// The action-branch slab of the critic (one input per feature, model.py:69-70) is converted on the CUDA cores.
+// Reference: workers/trainer.py:498, 506 (tape.gradient) through agent/model.py:19-33, 62-77.
+//
+// Warps: 0 MMA issuer, 1 TMA producer, 2..9 converters (TMEM lane quadrant = warp % 4, 64 columns each).
+// TMEM: z1 slab double buffered (2 x 128 columns) + accumulator (128 columns).
+#include <cudaTypedefs.h>
+
+#include <algorithm>
+
+#include "avd_common.cuh"
+#include "avd_ddpg_layout.cuh"
+#include "avd_umma.cuh"
+
+namespace avd {
+namespace wgrad3 {
+
+using namespace umma;
+typedef __nv_bfloat16 bf16;
+
+constexpr int TILE_M = 128, L2N = 128, KB = 64, SLAB = 128;
+constexpr int NUM_THREADS = 32 * 10;
+constexpr int HALF_BYTES = TILE_M * 128;                     // [128 rows][64 bf16]: 16 KB
+constexpr int OFF_DZ = 0;                                    // 2 x dz2 tile (2 halves of 64 columns)
+constexpr int OFF_R1 = OFF_DZ + 2 * 2 * HALF_BYTES;          // 2 x r1 slab (2 halves of 64 features)
+constexpr int OFF_B1 = OFF_R1 + 2 * 2 * HALF_BYTES;          // W1ext slab, no-swizzle K-major [2 chunks][128 rows][16 B]
+constexpr int OFF_X = OFF_B1 + 2 * SLAB * 16;                // 2 input tiles [2 chunks][128 rows][16 B]
+constexpr int X_BYTES = 2 * TILE_M * 16;
+constexpr int OFF_TAB = OFF_X + 2 * X_BYTES;                 // wa[64] ba[64]
+constexpr int OFF_BAR = OFF_TAB + 512;
+constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
+
+struct Args {
+    avd_net_dims d;
+    int critic, A, FT;          // FT feature slabs per agent (actor 2; critic 3, the last one = action branch)
+    int64_t R;
+    const float* params;        // [A][pstride]
+    int64_t pstride;
+    const float* s;             // [A*R][ns]
+    const float* act;           // [A*R] (critic)
+    float* grads;               // [A][gstride]; G2 is accumulated at grads + oW2 (row-major [F][128])
+    int64_t gstride, oW2;
+    int tiles_per_agent, ctas_per_slab;
+};
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ uint64_t make_desc_noswz(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void split_bf16(float v, bf16& hi, bf16& lo) {
+    hi = __float2bfloat16_rn(v);
+    lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+__device__ __forceinline__ uint32_t pack2(bf16 a, bf16 b) {
+    return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1) wgrad3_kernel(const __grid_constant__ CUtensorMap tmDZ, Args g) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    float* wa_tab = reinterpret_cast<float*>(smem + OFF_TAB);
+    float* ba_tab = wa_tab + 64;
+    uint64_t* dz_full = reinterpret_cast<uint64_t*>(smem + OFF_BAR);  // [2]
+    uint64_t* dz_empty = dz_full + 2;                                 // [2]
+    uint64_t* r_full = dz_empty + 2;                                  // [2]
+    uint64_t* r_empty = r_full + 2;                                   // [2]
+    uint64_t* x_full = r_empty + 2;                                   // [2]
+    uint64_t* z1_full = x_full + 2;                                   // [2]
+    uint64_t* z1_empty = z1_full + 2;                                 // [2]
+    uint64_t* acc_done = z1_empty + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_done + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const avd_net_dims d = g.d;
+    const int per_agent = g.FT * g.ctas_per_slab;
+    const int agent = (int)blockIdx.x / per_agent;
+    const int rem = (int)blockIdx.x - agent * per_agent;
+    const int ft = rem / g.ctas_per_slab, cta = rem - ft * g.ctas_per_slab;
+    const int T = (g.tiles_per_agent - cta + g.ctas_per_slab - 1) / g.ctas_per_slab;
+    const bool act_slab = g.critic && ft == g.FT - 1;        // features l1 .. l1+la-1: one input (the action) per feature
+    const int f0 = ft * SLAB;
+    const int nfeat = act_slab ? d.la : SLAB;                // valid features of this slab
+    const float* P = g.params + (int64_t)agent * g.pstride;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmDZ);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&dz_full[i], 1); mbar_init(&dz_empty[i], 1);
+            mbar_init(&r_full[i], 8); mbar_init(&r_empty[i], 1);
+            mbar_init(&x_full[i], 4); mbar_init(&z1_full[i], 1); mbar_init(&z1_empty[i], 8);
+        }
+        mbar_init(acc_done, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(tmem_slot, 512);
+    if (warp >= 2) {
+        const int ct = threadIdx.x - 64;     // 0..255
+        if (!act_slab && ct < SLAB) {        // W1ext row of layer-1 output column f0 + ct
+            const int64_t oW = g.critic ? critic_off(d).Ws : actor_off(d).W1, ob = g.critic ? critic_off(d).bs : actor_off(d).b1;
+            const int n = f0 + ct;
+            bf16 whi[4], wlo[4], bhi, blo;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) split_bf16(k < d.ns ? P[oW + (int64_t)k * d.l1 + n] : 0.0f, whi[k], wlo[k]);
+            split_bf16(P[ob + n], bhi, blo);
+            const bf16 zero = __float2bfloat16_rn(0.0f);
+            *reinterpret_cast<uint4*>(smem + OFF_B1 + ct * 16) = make_uint4(pack2(whi[0], whi[1]), pack2(whi[2], whi[3]), pack2(bhi, whi[0]), pack2(whi[1], whi[2]));
+            *reinterpret_cast<uint4*>(smem + OFF_B1 + SLAB * 16 + ct * 16) = make_uint4(pack2(whi[3], bhi), pack2(wlo[0], wlo[1]), pack2(wlo[2], wlo[3]), pack2(blo, zero));
+        }
+        if (act_slab && ct < 64) {
+            const CriticOff o = critic_off(d);
+            wa_tab[ct] = ct < d.la ? P[o.Wa + ct] : 0.0f;
+            ba_tab[ct] = ct < d.la ? P[o.ba + ct] : 0.0f;
+        }
+        if (act_slab) {                      // features 64..127 of the action slab do not exist: zero the second half of both r1 buffers once
+            for (int i = ct; i < 2 * HALF_BYTES / 16; i += 256) {
+                const int b = i / (HALF_BYTES / 16), o16 = i - b * (HALF_BYTES / 16);
+                *reinterpret_cast<uint4*>(smem + OFF_R1 + b * 2 * HALF_BYTES + HALF_BYTES + o16 * 16) = make_uint4(0u, 0u, 0u, 0u);
+            }
+        }
+        fence_proxy_async();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    auto tile_of = [&](int tc) { return cta + tc * g.ctas_per_slab; };
+
+    if (warp == 0) {
+        // ================================================ MMA issuer ================================================
+        if (lane == 0 && T > 0) {
+            constexpr uint32_t idesc1 = make_idesc_bf16(TILE_M, SLAB, false, false);   // x (K-major) x W1ext slab (K-major)
+            constexpr uint32_t idesc2 = make_idesc_bf16(SLAB, L2N, true, true);        // r1 slab (MN-major) x dz2 tile (MN-major)
+            const uint32_t b1_addr = smem_u32(smem + OFF_B1), x_addr = smem_u32(smem + OFF_X);
+            const uint32_t r_addr = smem_u32(smem + OFF_R1), dz_addr = smem_u32(smem + OFF_DZ);
+            auto mma1 = [&](int t) {          // z1 slab of local tile t -> TMEM columns 128 (t & 1)
+                mbar_wait(&x_full[t & 1], ((uint32_t)t >> 1) & 1);
+                mbar_wait(&z1_empty[t & 1], (((uint32_t)t >> 1) & 1) ^ 1);
+                tc_fence_after();
+                mma_bf16(tmem_base + (uint32_t)((t & 1) * SLAB), make_desc_noswz(x_addr + (t & 1) * X_BYTES, TILE_M * 16, 128),
+                         make_desc_noswz(b1_addr, SLAB * 16, 128), idesc1, 0);
+                mma_commit(&z1_full[t & 1]);
+            };
+            auto mma2 = [&](int t) {          // acc += r1 slab^T . dz2 tile   (K = the 128 rows of the tile)
+                mbar_wait(&r_full[t & 1], ((uint32_t)t >> 1) & 1);
+                mbar_wait(&dz_full[t & 1], ((uint32_t)t >> 1) & 1);
+                tc_fence_after();
+                const uint32_t ra = r_addr + (t & 1) * 2 * HALF_BYTES, da = dz_addr + (t & 1) * 2 * HALF_BYTES;
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks)
+                    mma_bf16(tmem_base + 256u, make_smem_desc(ra + ks * 2048, HALF_BYTES, 1024), make_smem_desc(da + ks * 2048, HALF_BYTES, 1024), idesc2,
+                             (t | ks) != 0);
+                mma_commit(&r_empty[t & 1]);
+                mma_commit(&dz_empty[t & 1]);
+            };
+            if (!act_slab) {
+                mma1(0);
+                if (T > 1) mma1(1);
+            }
+            for (int t = 0; t < T; ++t) {
+                mma2(t);
+                if (!act_slab && t + 2 < T) mma1(t + 2);
+            }
+            mma_commit(acc_done);
+        }
+    } else if (warp == 1) {
+        // ================================================ TMA producer ================================================
+        if (lane == 0) {
+            for (int t = 0; t < T; ++t) {
+                const int b = t & 1;
+                mbar_wait(&dz_empty[b], (((uint32_t)t >> 1) & 1) ^ 1);
+                uint8_t* dst = smem + OFF_DZ + b * 2 * HALF_BYTES;
+                mbar_expect_tx(&dz_full[b], 2 * HALF_BYTES);
+                tma_load_3d(dst, &tmDZ, &dz_full[b], 0, tile_of(t) * TILE_M, agent);
+                tma_load_3d(dst + HALF_BYTES, &tmDZ, &dz_full[b], KB, tile_of(t) * TILE_M, agent);
+            }
+        }
+    } else {
+        // ================================================ converters ================================================
+        const int cw = warp - 2;             // 0..7
+        const int q = warp & 3, half = cw >> 2;
+        const int row = q * 32 + lane;
+        const uint32_t tlane = (uint32_t)(q * 32) << 16;
+        auto rowidx = [&](int tc) -> int64_t {
+            const int64_t r_in = (int64_t)tile_of(tc) * TILE_M + row;
+            return (int64_t)agent * g.R + (r_in < g.R ? r_in : g.R - 1);
+        };
+        auto produce_x = [&](int t) {         // [v_hi(5) v_lo(5) v_hi(5) 0],  v = (s0..s3, 1)
+            const int64_t n = rowidx(t);
+            bf16 hi[5], lo[5];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) split_bf16(k < d.ns ? __ldg(g.s + n * d.ns + k) : 0.0f, hi[k], lo[k]);
+            hi[4] = __float2bfloat16_rn(1.0f);
+            lo[4] = __float2bfloat16_rn(0.0f);
+            uint8_t* xbase = smem + OFF_X + (t & 1) * X_BYTES;
+            *reinterpret_cast<uint4*>(xbase + row * 16) = make_uint4(pack2(hi[0], hi[1]), pack2(hi[2], hi[3]), pack2(hi[4], lo[0]), pack2(lo[1], lo[2]));
+            *reinterpret_cast<uint4*>(xbase + TILE_M * 16 + row * 16) =
+                make_uint4(pack2(lo[3], lo[4]), pack2(hi[0], hi[1]), pack2(hi[2], hi[3]), pack2(hi[4], lo[4]));
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&x_full[t & 1]);
+        };
+        if (!act_slab && half == 0) {
+            produce_x(0);
+            if (T > 1) produce_x(1);
+        }
+        for (int t = 0; t < T; ++t) {
+            const int b = t & 1;
+            // rows past the end of the agent's batch: dz2 is zero-filled by TMA there, so whatever r1 holds contributes nothing
+            uint8_t* rrow = smem + OFF_R1 + b * 2 * HALF_BYTES + half * HALF_BYTES + row * 128;
+            if (!act_slab) {
+                mbar_wait(&z1_full[b], ((uint32_t)t >> 1) & 1);
+                tc_fence_after();
+                mbar_wait(&r_empty[b], (((uint32_t)t >> 1) & 1) ^ 1);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    float z[32];
+                    tmem_ld32(tmem_base + (uint32_t)(b * SLAB + half * 64 + h * 32) + tlane, z);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint4 pk = make_uint4(pack_relu_bf16x2(z[8 * k], z[8 * k + 1]), pack_relu_bf16x2(z[8 * k + 2], z[8 * k + 3]),
+                                                    pack_relu_bf16x2(z[8 * k + 4], z[8 * k + 5]), pack_relu_bf16x2(z[8 * k + 6], z[8 * k + 7]));
+                        *reinterpret_cast<uint4*>(rrow + (((h * 4 + k) ^ (row & 7)) << 4)) = pk;
+                    }
+                }
+                tc_fence_before();
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) { mbar_arrive(&z1_empty[b]); mbar_arrive(&r_full[b]); }
+                if (half == 0 && t + 2 < T) produce_x(t + 2);     // X buffer b is free: z1_full(t) implies the layer-1 MMA has read it
+            } else {
+                const float a_val = __ldg(g.act + rowidx(t));
+                mbar_wait(&r_empty[b], (((uint32_t)t >> 1) & 1) ^ 1);      // every warp waits, so that no arrival can lap a phase of r_full
+                if (half == 0) {             // 64 action-branch columns (zero weights beyond la give relu(0) = 0)
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        float r[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) r[j] = fmaf(a_val, wa_tab[8 * k + j], ba_tab[8 * k + j]);
+                        *reinterpret_cast<uint4*>(rrow + ((k ^ (row & 7)) << 4)) =
+                            make_uint4(pack_relu_bf16x2(r[0], r[1]), pack_relu_bf16x2(r[2], r[3]), pack_relu_bf16x2(r[4], r[5]), pack_relu_bf16x2(r[6], r[7]));
+                    }
+                    fence_proxy_async();
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&r_full[b]);
+            }
+        }
+        // ---- accumulator of this CTA -> global: features f0 + row, all 128 columns (warps of column half `half`)
+        if (T > 0) {
+            mbar_wait(acc_done, 0);
+            tc_fence_after();
+            const int f = f0 + row;
+            float* dst = g.grads + (int64_t)agent * g.gstride + g.oW2 + (int64_t)f * L2N + half * 64;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                float v[32];
+                tmem_ld32(tmem_base + 256u + (uint32_t)(half * 64 + h * 32) + tlane, v);
+                if (row < nfeat) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) atomicAdd(dst + h * 32 + j, v[j]);
+                }
+            }
+            tc_fence_before();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+static PFN_cuTensorMapEncodeTiled encode_fn() {
+    static PFN_cuTensorMapEncodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(p);
+    }
+    return fn;
+}
+
+// grads + oW2: row-major [F][128] fp32 per agent, accumulated into (zero it first).  DZ: bf16 [A*R][128].
+int run(const avd_net_dims& d, bool critic, int A, int64_t R, const float* params, int64_t pstride, const float* s, const float* act, const bf16* DZ,
+        float* grads, int64_t gstride, int64_t oW2, cudaStream_t st) {
+    AVD_REQUIRE(d.l1 == 256 && d.l2 == L2N && d.ns >= 1 && d.ns <= 4 && (!critic || (d.la >= 8 && d.la <= 64)), "unsupported layer sizes for the fused wgrad kernel");
+    AVD_REQUIRE(params && s && DZ && grads && (!critic || act), "null buffer");
+    PFN_cuTensorMapEncodeTiled enc = encode_fn();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled is not available from the driver");
+        return AVD_ERR_CUDA;
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        AVD_CUDA_OK(cudaFuncSetAttribute(wgrad3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        attr_set = true;
+    }
+    CUtensorMap tm;
+    cuuint64_t dims[3] = {L2N, (cuuint64_t)R, (cuuint64_t)A};
+    cuuint64_t strides[2] = {L2N * 2, (cuuint64_t)R * L2N * 2};
+    cuuint32_t box[3] = {KB, TILE_M, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<bf16*>(DZ), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled(dz2) failed with %d", (int)r);
+        return AVD_ERR_CUDA;
+    }
+    Args g;
+    g.d = d; g.critic = critic ? 1 : 0; g.A = A; g.FT = critic ? 3 : 2; g.R = R; g.params = params; g.pstride = pstride; g.s = s; g.act = act;
+    g.grads = grads; g.gstride = gstride; g.oW2 = oW2;
+    g.tiles_per_agent = (int)((R + TILE_M - 1) / TILE_M);
+    g.ctas_per_slab = std::max(1, std::min(g.tiles_per_agent, sm_count() / std::max(1, A * g.FT)));
+    wgrad3_kernel<<<(unsigned)(A * g.FT * g.ctas_per_slab), NUM_THREADS, SMEM_BYTES, st>>>(tm, g);
+    AVD_LAUNCH_OK();
+    return AVD_OK;
+}
+
+}  // namespace wgrad3
+}  // namespace avd
