@@ -98,48 +98,52 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dgrad3_kernel(const __grid_con
 
     if (warp == 0) {
         // ================================================ MMA issuer ================================================
-        if (lane == 0 && T > 0) {
+        // warp-uniform control flow; the tcgen05 instructions are predicated on one elected lane (see avd_umma.cuh)
+        if (T > 0) {
+            const uint32_t leader = elect_one();
             constexpr uint32_t idesc_d = make_idesc_bf16(TILE_M, 64, false, false);    // dz2 (K-major) x W2' chunk (K-major)
-            constexpr uint32_t idesc_g = make_idesc_bf16(TILE_M, 16, true, false);     // dz1 (MN-major) x xext^T (K-major)
-            const uint32_t w_addr = smem_u32(smem + OFF_W), a_addr0 = smem_u32(smem + OFF_A), st_addr = smem_u32(smem + OFF_ST);
-            const uint32_t xt_addr0 = smem_u32(smem + OFF_XT);
+            constexpr uint32_t idesc_g = make_idesc_bf16(TILE_M, 16, true, false);     // dz1 / dz2 (MN-major) x xext^T (K-major)
+            const uint64_t dA = make_smem_desc(smem_u32(smem + OFF_A), 16, 1024);                 // dz2 tile as K-major A
+            const uint64_t dAt = make_smem_desc(smem_u32(smem + OFF_A), TILE_M * 128, 1024);      // dz2 tile as MN-major A (two 64-column halves)
+            const uint64_t dW = make_smem_desc(smem_u32(smem + OFF_W), 16, 1024);
+            const uint64_t dX = make_smem_desc(smem_u32(smem + OFF_XT), 16, 1024);
+            const uint64_t dS = make_smem_desc(smem_u32(smem + OFF_ST), TILE_M * 128, 1024);      // staged dz1 chunk pair as MN-major A
             // chunk c of local tile t: dR chunk = dz2 tile . W2'[64 c .. 64 c + 63]^T  -> ring slot (t NC + c) % 7
             auto mma_chunk = [&](int t, int c) {
-                const uint32_t a_addr = a_addr0 + (t & 1) * A_BYTES;
+                const uint32_t a_off = (uint32_t)(t & 1) * A_BYTES;
                 if (c == 0) {
                     mbar_wait(&a_full[t & 1], ((uint32_t)t >> 1) & 1);
                     mbar_wait(&xt_full[t % NXT], ((uint32_t)t / NXT) & 1);
                     tc_fence_after();
                     // db2[j] = sum_n dz2[n][j]: the dz2 tile read as an MN-major A operand against the constant-one column (5) of xext
-                    const uint32_t xt_addr = xt_addr0 + (t % NXT) * XT_BYTES;
+                    const uint32_t x_off = (uint32_t)(t % NXT) * XT_BYTES;
 #pragma unroll
                     for (int ks = 0; ks < 8; ++ks)
-                        mma_bf16(tmem_base + 496u, make_smem_desc(a_addr + ks * 2048, TILE_M * 128, 1024),
-                                 make_smem_desc(xt_addr + (ks >> 2) * (16 * 128) + (ks & 3) * 32, 16, 1024), idesc_g, (t | ks) != 0);
+                        mma_bf16_p(leader, tmem_base + 496u, desc_add(dAt, a_off + ks * 2048), desc_add(dX, x_off + (ks >> 2) * (16 * 128) + (ks & 3) * 32),
+                                   idesc_g, (t | ks) != 0);
                 }
                 const uint32_t k = (uint32_t)(t * NC + c), slot = k % NRING;
                 mbar_wait(&d_empty[slot], ((k / NRING) & 1) ^ 1);
                 tc_fence_after();
 #pragma unroll
                 for (int ks = 0; ks < 8; ++ks)
-                    mma_bf16(tmem_base + slot * 64, make_smem_desc(a_addr + (ks >> 2) * (TILE_M * 128) + (ks & 3) * 32, 16, 1024),
-                             make_smem_desc(w_addr + ((ks >> 2) * MAX_NC + c) * WCHUNK_BYTES + (ks & 3) * 32, 16, 1024), idesc_d, ks != 0);
-                mma_commit(&d_full[slot]);
-                if (c == NC - 1) mma_commit(&a_empty[t & 1]);       // the dz2 tile can be reloaded two tiles ahead
+                    mma_bf16_p(leader, tmem_base + slot * 64, desc_add(dA, a_off + (ks >> 2) * (TILE_M * 128) + (ks & 3) * 32),
+                               desc_add(dW, (uint32_t)((ks >> 2) * MAX_NC + c) * WCHUNK_BYTES + (ks & 3) * 32), idesc_d, ks != 0);
+                mma_commit_p(leader, &d_full[slot]);
+                if (c == NC - 1) mma_commit_p(leader, &a_empty[t & 1]);       // the dz2 tile can be reloaded two tiles ahead
             };
             // chunk pair p of local tile t: G1[128 p ..] += dz1 pair^T . xext tile
             auto g1_pair = [&](int t, int p) {
-                const uint32_t xt_addr = xt_addr0 + (t % NXT) * XT_BYTES;
+                const uint32_t x_off = (uint32_t)(t % NXT) * XT_BYTES;
                 const uint32_t pk = (uint32_t)(t * NP + p), sb = pk & 1;
-                if (p == 0) mbar_wait(&xt_full[t % NXT], ((uint32_t)t / NXT) & 1);
                 mbar_wait(&st_full[sb], (pk >> 1) & 1);
                 tc_fence_after();
 #pragma unroll
                 for (int ks = 0; ks < 8; ++ks)
-                    mma_bf16(tmem_base + 448u + (uint32_t)(p * 16), make_smem_desc(st_addr + sb * (2 * TILE_M * 128) + ks * 2048, TILE_M * 128, 1024),
-                             make_smem_desc(xt_addr + (ks >> 2) * (16 * 128) + (ks & 3) * 32, 16, 1024), idesc_g, (t | ks) != 0);
-                mma_commit(&st_empty[sb]);
-                if (p == NP - 1) mma_commit(&xt_empty[t % NXT]);
+                    mma_bf16_p(leader, tmem_base + 448u + (uint32_t)(p * 16), desc_add(dS, sb * (2 * TILE_M * 128) + ks * 2048),
+                               desc_add(dX, x_off + (ks >> 2) * (16 * 128) + (ks & 3) * 32), idesc_g, (t | ks) != 0);
+                mma_commit_p(leader, &st_empty[sb]);
+                if (p == NP - 1) mma_commit_p(leader, &xt_empty[t % NXT]);
             };
             mbar_wait(w_full, 0);
             for (int c = 0; c < NC; ++c) mma_chunk(0, c);
@@ -154,27 +158,28 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dgrad3_kernel(const __grid_con
                     g1_pair(t, p);
                 }
             }
-            mma_commit(g1_done);
+            mma_commit_p(leader, g1_done);
         }
     } else if (warp == 1) {
         // ================================================ TMA producer ================================================
-        if (lane == 0 && T > 0) {
-            mbar_expect_tx(w_full, (uint32_t)(2 * NC * WCHUNK_BYTES));
+        if (T > 0) {
+            const uint32_t leader = elect_one();
+            mbar_expect_tx_p(leader, w_full, (uint32_t)(2 * NC * WCHUNK_BYTES));
             for (int kb = 0; kb < 2; ++kb)
-                for (int c = 0; c < NC; ++c) tma_load_3d(smem + OFF_W + (kb * MAX_NC + c) * WCHUNK_BYTES, &tmW, w_full, kb * KB, c * 64, agent);
+                for (int c = 0; c < NC; ++c) tma_load_3d_p(leader, smem + OFF_W + (kb * MAX_NC + c) * WCHUNK_BYTES, &tmW, w_full, kb * KB, c * 64, agent);
             for (int t = 0; t < T; ++t) {
                 const int b = t & 1, xb = t % NXT;
                 const int r0 = tile_of(t) * TILE_M;
                 mbar_wait(&xt_empty[xb], (((uint32_t)t / NXT) & 1) ^ 1);
                 uint8_t* xdst = smem + OFF_XT + xb * XT_BYTES;
-                mbar_expect_tx(&xt_full[xb], XT_BYTES);
-                tma_load_3d(xdst, &tmXT, &xt_full[xb], r0, 0, agent);
-                tma_load_3d(xdst + 16 * 128, &tmXT, &xt_full[xb], r0 + KB, 0, agent);
+                mbar_expect_tx_p(leader, &xt_full[xb], XT_BYTES);
+                tma_load_3d_p(leader, xdst, &tmXT, &xt_full[xb], r0, 0, agent);
+                tma_load_3d_p(leader, xdst + 16 * 128, &tmXT, &xt_full[xb], r0 + KB, 0, agent);
                 mbar_wait(&a_empty[b], (((uint32_t)t >> 1) & 1) ^ 1);
                 uint8_t* dst = smem + OFF_A + b * A_BYTES;
-                mbar_expect_tx(&a_full[b], A_BYTES);
-                tma_load_3d(dst, &tmDZ, &a_full[b], 0, r0, agent);
-                tma_load_3d(dst + TILE_M * 128, &tmDZ, &a_full[b], KB, r0, agent);
+                mbar_expect_tx_p(leader, &a_full[b], A_BYTES);
+                tma_load_3d_p(leader, dst, &tmDZ, &a_full[b], 0, r0, agent);
+                tma_load_3d_p(leader, dst + TILE_M * 128, &tmDZ, &a_full[b], KB, r0, agent);
             }
         }
     } else {

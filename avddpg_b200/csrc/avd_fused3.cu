@@ -36,10 +36,11 @@ constexpr int TILE_M = 128, L2N = 128, KB = 64, MAX_KB = 5, L1N = 256;
 constexpr int NCONS = 16;
 constexpr int NUM_THREADS = 32 * (1 + NCONS);
 constexpr int SLOT_BYTES = TILE_M * KB * 2;                  // 16 KB
-constexpr int OFF_RING = 0;                                  // r1 k-blocks of the current tile (slot = k-block)
-constexpr int OFF_W = OFF_RING + MAX_KB * SLOT_BYTES;        // W2'^T k-blocks
-constexpr int OFF_DZ = OFF_W + MAX_KB * SLOT_BYTES;          // dz2 tile: 2 k-blocks
-constexpr int OFF_B1 = OFF_DZ + 2 * SLOT_BYTES;              // W1ext, no-swizzle K-major [2 chunks][256 rows][16 B]
+constexpr int MAX_SLOT = 7;
+constexpr int OFF_W = 0;                                     // W2'^T k-blocks
+constexpr int OFF_RING = OFF_W + MAX_KB * SLOT_BYTES;        // ring of r1 k-blocks: 7 slots in the forward modes, 5 when ...
+constexpr int OFF_DZ = OFF_RING + 5 * SLOT_BYTES;            // ... the last two hold the dz2 tile (2 k-blocks) of the backward modes
+constexpr int OFF_B1 = OFF_RING + MAX_SLOT * SLOT_BYTES;     // W1ext, no-swizzle K-major [2 chunks][256 rows][16 B]
 constexpr int B1_BYTES = 2 * L1N * 16;
 constexpr int OFF_X = OFF_B1 + B1_BYTES;                     // 2 input tiles [2 chunks][128 rows][16 B]
 constexpr int X_BYTES = 2 * TILE_M * 16;
@@ -98,6 +99,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused3_kernel(const __grid_con
     constexpr bool ACTION = MODE == MODE_CRITIC_ACTION;                          // backward to the action input only
     constexpr bool HAS_DZ = BWD || ACTION;
     constexpr int NKB = CRITIC ? 5 : 4;
+    // k-block kb of local tile t lives in ring slot (t NKB + kb) % NSLOT: with more slots than k-blocks the converters of the
+    // next tile start while the layer-2 MMA of this tile still reads its operands
+    constexpr int NSLOT = HAS_DZ ? 5 : MAX_SLOT;
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -107,9 +111,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused3_kernel(const __grid_con
     float* ba_tab = wa_tab + 64;
     float* scal = ba_tab + 64;                                   // [1..4] partial sums of sh2 . w3, [5] = b3
     float* part = reinterpret_cast<float*>(smem + OFF_PART);
-    uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + OFF_BAR);   // [5]
-    uint64_t* a_empty = a_full + MAX_KB;                              // [5]
-    uint64_t* acc_full = a_empty + MAX_KB;                            // [2]
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + OFF_BAR);   // [7]
+    uint64_t* a_empty = a_full + MAX_SLOT;                            // [7]
+    uint64_t* acc_full = a_empty + MAX_SLOT;                          // [2]
     uint64_t* acc_empty = acc_full + 2;                               // [2]
     uint64_t* part_full = acc_empty + 2;                              // [2]
     uint64_t* x_full = part_full + 2;                                 // [2]
@@ -133,7 +137,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused3_kernel(const __grid_con
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmW);
         if (BWD) tma_prefetch_desc(&tmDZ);
-        for (int i = 0; i < MAX_KB; ++i) { mbar_init(&a_full[i], i < 4 ? 4 : 8); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < MAX_SLOT; ++i) { mbar_init(&a_full[i], 8); mbar_init(&a_empty[i], 1); }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], NCONS);
             mbar_init(&part_full[i], NCONS); mbar_init(&x_full[i], 4);
@@ -196,16 +200,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused3_kernel(const __grid_con
 
     if (warp == 0) {
         // ============================================ TMA / MMA issuer ============================================
-        if (lane == 0) {
+        // warp-uniform control flow; the one-thread instructions are predicated on an elected lane (see avd_umma.cuh)
+        {
+            const uint32_t leader = elect_one();
             constexpr uint32_t idesc = make_idesc_bf16(TILE_M, L2N, false, false);
             constexpr uint32_t idesc_act = make_idesc_bf16(TILE_M, 64, false, true);      // dz2 (K-major) x W2'^T block (MN-major)
-            const uint32_t w_addr = smem_u32(smem + OFF_W);
-            const uint32_t b1_addr = smem_u32(smem + OFF_B1);
-            const uint32_t x_addr = smem_u32(smem + OFF_X);
-            const uint32_t dz_addr = smem_u32(smem + OFF_DZ);
             const int F = L1N + la;
-            mbar_expect_tx(w_full, (uint32_t)NKB * SLOT_BYTES);
-            for (int kb = 0; kb < NKB; ++kb) tma_load_3d(smem + OFF_W + kb * SLOT_BYTES, &tmW, w_full, kb * KB, 0, agent);
+            const uint64_t dW = make_smem_desc(smem_u32(smem + OFF_W), 16, 1024);
+            const uint64_t dR = make_smem_desc(smem_u32(smem + OFF_RING), 16, 1024);
+            const uint64_t dDZ = make_smem_desc(smem_u32(smem + OFF_DZ), 16, 1024);
+            const uint64_t dX = make_desc_noswz(smem_u32(smem + OFF_X), TILE_M * 16, 128);
+            const uint64_t dB1 = make_desc_noswz(smem_u32(smem + OFF_B1), L1N * 16, 128);
+            mbar_expect_tx_p(leader, w_full, (uint32_t)NKB * SLOT_BYTES);
+            for (int kb = 0; kb < NKB; ++kb) tma_load_3d_p(leader, smem + OFF_W + kb * SLOT_BYTES, &tmW, w_full, kb * KB, 0, agent);
 
             auto mma1 = [&](int t) {          // layer 1 of local tile t -> TMEM columns [256, 512)
                 mbar_wait(&x_full[t & 1], ((uint32_t)t >> 1) & 1);
@@ -213,44 +220,48 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused3_kernel(const __grid_con
                 tc_fence_after();
 #pragma unroll
                 for (int h = 0; h < 2; ++h)
-                    mma_bf16(tmem_base + 256u + (uint32_t)(h * L2N), make_desc_noswz(x_addr + (t & 1) * X_BYTES, TILE_M * 16, 128),
-                             make_desc_noswz(b1_addr + h * (L2N * 16), L1N * 16, 128), idesc, 0);
-                mma_commit(z1_full);
+                    mma_bf16_p(leader, tmem_base + 256u + (uint32_t)(h * L2N), desc_add(dX, (uint32_t)(t & 1) * X_BYTES), desc_add(dB1, h * (L2N * 16)), idesc, 0);
+                mma_commit_p(leader, z1_full);
             };
-            auto mma2 = [&](int t) {          // layer 2 of local tile t -> TMEM accumulator t & 1 (+ r1 tile stores, backward modes)
+            auto mma2 = [&](int t) {          // layer 2 of local tile t -> TMEM accumulator t & 1
                 mbar_wait(&acc_empty[t & 1], (((uint32_t)t >> 1) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t tacc = tmem_base + (uint32_t)((t & 1) * L2N);
+#pragma unroll
                 for (int kb = 0; kb < NKB; ++kb) {
-                    mbar_wait(&a_full[kb], (uint32_t)t & 1);
+                    const uint32_t kc = (uint32_t)(t * NKB + kb), sl = kc % NSLOT;
+                    mbar_wait(&a_full[sl], (kc / NSLOT) & 1);
                     tc_fence_after();
-                    const uint32_t a_addr = smem_u32(smem + OFF_RING + kb * SLOT_BYTES);
                     const int nm = min(4, (F - kb * KB) / 16);
-                    for (int j = 0; j < nm; ++j)
-                        mma_bf16(tacc, make_smem_desc(a_addr + j * 32, 16, 1024), make_smem_desc(w_addr + kb * SLOT_BYTES + j * 32, 16, 1024), idesc,
-                                 (kb | j) != 0);
-                    mma_commit(&a_empty[kb]);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (j < nm)
+                            mma_bf16_p(leader, tacc, desc_add(dR, sl * SLOT_BYTES + j * 32), desc_add(dW, kb * SLOT_BYTES + j * 32), idesc, (kb | j) != 0);
+                    mma_commit_p(leader, &a_empty[sl]);
                 }
-                mma_commit(&acc_full[t & 1]);
+                mma_commit_p(leader, &acc_full[t & 1]);
             };
             auto dz_out = [&](int t) {        // dz2 tile of local tile t: to HBM (BWD) or through the action-column dgrad MMA (ACTION)
                 mbar_wait(dz_full, (uint32_t)t & 1);
                 tc_fence_after();
                 if (BWD) {                    // the tile is free again once the TMA stores have read it
-                    tma_store_3d(&tmDZ, smem + OFF_DZ, 0, tile_of(t) * TILE_M, agent);
-                    tma_store_3d(&tmDZ, smem + OFF_DZ + SLOT_BYTES, KB, tile_of(t) * TILE_M, agent);
-                    bulk_commit();
-                    bulk_wait_read0();
-                    mbar_arrive(dz_empty);
+                    tma_store_3d_p(leader, &tmDZ, smem + OFF_DZ, 0, tile_of(t) * TILE_M, agent);
+                    tma_store_3d_p(leader, &tmDZ, smem + OFF_DZ + SLOT_BYTES, KB, tile_of(t) * TILE_M, agent);
+                    if (leader) {
+                        bulk_commit();
+                        bulk_wait_read0();
+                    }
+                    __syncwarp();
+                    mbar_arrive_p(leader, dz_empty);
                 } else {
                     if (t + 2 < T) mbar_wait(z1_empty, (uint32_t)(t + 2) & 1);     // convert(t + 2) has drained the z1 columns
                     tc_fence_after();
 #pragma unroll
                     for (int ks = 0; ks < 8; ++ks)
-                        mma_bf16(tmem_base + 256u, make_smem_desc(dz_addr + (ks >> 2) * SLOT_BYTES + (ks & 3) * 32, 16, 1024),
-                                 make_smem_desc(w_addr + 4 * SLOT_BYTES + ks * 2048, 16, 1024), idesc_act, ks != 0);
-                    mma_commit(dra_full);
-                    mma_commit(dz_empty);
+                        mma_bf16_p(leader, tmem_base + 256u, desc_add(dDZ, (ks >> 2) * SLOT_BYTES + (ks & 3) * 32), desc_add(dW, 4 * SLOT_BYTES + ks * 2048),
+                                   idesc_act, ks != 0);
+                    mma_commit_p(leader, dra_full);
+                    mma_commit_p(leader, dz_empty);
                 }
             };
 
@@ -333,8 +344,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused3_kernel(const __grid_con
             if (CRITIC && (c4 == ga0 || c4 == ga0 + 1)) a_val = __ldg(g.act + nrow);
             mbar_wait(z1_full, (uint32_t)tc & 1);
             tc_fence_after();
-            mbar_wait(&a_empty[c4], ((uint32_t)tc & 1) ^ 1);
-            uint8_t* slot = smem + OFF_RING + c4 * SLOT_BYTES + row * 128;
+            const uint32_t kc = (uint32_t)(tc * NKB + c4), sl = kc % NSLOT;
+            mbar_wait(&a_empty[sl], ((kc / NSLOT) & 1) ^ 1);
+            uint8_t* slot = smem + OFF_RING + sl * SLOT_BYTES + row * 128;
             uint32_t neg[2];
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
@@ -356,12 +368,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused3_kernel(const __grid_con
             tc_fence_before();
             fence_proxy_async();
             __syncwarp();
-            if (lane == 0) { mbar_arrive(z1_empty); mbar_arrive(&a_full[c4]); }
+            if (lane == 0) { mbar_arrive(z1_empty); mbar_arrive_cnt(&a_full[sl], 2); }   // every slot barrier counts 8: 4 warps x 2 here, 8 warps x 1 for the action block
             if (BWD && valid) *reinterpret_cast<uint2*>(g.mask_out + nrow * g.mask_words + 2 * c4) = make_uint2(neg[0], neg[1]);
             if (CRITIC && (c4 == ga0 || c4 == ga0 + 1)) {        // action branch: one input per column, CUDA cores
                 const int j0 = (c4 == ga0) ? 0 : 32;
-                mbar_wait(&a_empty[4], ((uint32_t)tc & 1) ^ 1);
-                uint8_t* aslot = smem + OFF_RING + 4 * SLOT_BYTES + row * 128;
+                const uint32_t kca = (uint32_t)(tc * NKB + 4), sla = kca % NSLOT;
+                mbar_wait(&a_empty[sla], ((kca / NSLOT) & 1) ^ 1);
+                uint8_t* aslot = smem + OFF_RING + sla * SLOT_BYTES + row * 128;
                 float z[32];
                 uint32_t m = 0;
 #pragma unroll
@@ -380,7 +393,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused3_kernel(const __grid_con
                 }
                 fence_proxy_async();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&a_full[4]);
+                if (lane == 0) mbar_arrive(&a_full[sla]);
                 if (BWD && valid) g.mask_out[nrow * g.mask_words + 8 + (j0 >> 5)] = m;
             }
             if (c4 == xg && tc + 2 < T) produce_x(tc + 2);       // X buffer tc & 1 is free: z1_full(tc) implies the layer-1 MMA has read it

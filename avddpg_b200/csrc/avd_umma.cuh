@@ -32,6 +32,9 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_cnt(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t done;
     asm volatile(
@@ -210,6 +213,86 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, bool a_mn, 
     return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) |
            ((uint32_t)(M >> 4) << 24);
 }
+
+// ---- single-issuer helpers -----------------------------------------------------------------------
+// The issuing warp keeps WARP-UNIFORM control flow (all 32 lanes run the loops and the barrier waits) and predicates the
+// one-thread instructions on an elected lane inside the asm block.  With divergent `if (lane == 0)` code the compiler has to
+// wrap every uniform-datapath instruction (UTCHMMA, UTCBAR, UTMALDG) in a waterfall loop (ELECT / R2UR / BRA.U.ANY, ~17 SASS
+// instructions per MMA), and the serial latency of that single thread becomes the critical path of the whole CTA.
+__device__ __forceinline__ uint32_t elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred;
+}
+__device__ __forceinline__ void mma_bf16_p(uint32_t leader, uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p, q;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "setp.ne.b32 q, %5, 0;\n"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(leader)
+        : "memory");
+}
+__device__ __forceinline__ void mma_commit_p(uint32_t leader, uint64_t* bar) {
+    asm volatile(
+        "{\n"
+        ".reg .pred q;\n"
+        "setp.ne.b32 q, %1, 0;\n"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(leader)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_p(uint32_t leader, uint64_t* bar) {
+    asm volatile(
+        "{\n"
+        ".reg .pred q;\n"
+        "setp.ne.b32 q, %1, 0;\n"
+        "@q mbarrier.arrive.shared::cta.b64 _, [%0];\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(leader)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_p(uint32_t leader, uint64_t* bar, uint32_t bytes) {
+    asm volatile(
+        "{\n"
+        ".reg .pred q;\n"
+        "setp.ne.b32 q, %2, 0;\n"
+        "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(bytes), "r"(leader)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_p(uint32_t leader, void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "{\n"
+        ".reg .pred q;\n"
+        "setp.ne.b32 q, %6, 0;\n"
+        "@q cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n"
+        "}\n" ::"r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(leader)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_3d_p(uint32_t leader, const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2) {
+    asm volatile(
+        "{\n"
+        ".reg .pred q;\n"
+        "setp.ne.b32 q, %5, 0;\n"
+        "@q cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];\n"
+        "}\n" ::"l"(reinterpret_cast<uint64_t>(map)),
+        "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(leader)
+        : "memory");
+}
+// SWIZZLE_128B descriptor with the 16-byte-unit address added to a precomputed base (address field: bits [0,14))
+__device__ __forceinline__ uint64_t desc_add(uint64_t base_desc, uint32_t byte_offset) { return base_desc + (uint64_t)(byte_offset >> 4); }
 
 }  // namespace umma
 }  // namespace avd

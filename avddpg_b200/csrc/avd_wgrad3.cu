@@ -140,30 +140,31 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad3_kernel(const __grid_con
 
     if (warp == 0) {
         // ================================================ MMA issuer ================================================
-        if (lane == 0 && T > 0) {
+        // warp-uniform control flow; the tcgen05 instructions are predicated on one elected lane (see avd_umma.cuh)
+        if (T > 0) {
+            const uint32_t leader = elect_one();
             constexpr uint32_t idesc1 = make_idesc_bf16(TILE_M, SLAB, false, false);   // x (K-major) x W1ext slab (K-major)
             constexpr uint32_t idesc2 = make_idesc_bf16(SLAB, L2N, true, true);        // r1 slab (MN-major) x dz2 tile (MN-major)
-            const uint32_t b1_addr = smem_u32(smem + OFF_B1), x_addr = smem_u32(smem + OFF_X);
-            const uint32_t r_addr = smem_u32(smem + OFF_R1), dz_addr = smem_u32(smem + OFF_DZ);
+            const uint64_t dX = make_desc_noswz(smem_u32(smem + OFF_X), TILE_M * 16, 128);
+            const uint64_t dB1 = make_desc_noswz(smem_u32(smem + OFF_B1), SLAB * 16, 128);
+            const uint64_t dR = make_smem_desc(smem_u32(smem + OFF_R1), HALF_BYTES, 1024);
+            const uint64_t dDZ = make_smem_desc(smem_u32(smem + OFF_DZ), HALF_BYTES, 1024);
             auto mma1 = [&](int t) {          // z1 slab of local tile t -> TMEM columns 128 (t & 1)
                 mbar_wait(&x_full[t & 1], ((uint32_t)t >> 1) & 1);
                 mbar_wait(&z1_empty[t & 1], (((uint32_t)t >> 1) & 1) ^ 1);
                 tc_fence_after();
-                mma_bf16(tmem_base + (uint32_t)((t & 1) * SLAB), make_desc_noswz(x_addr + (t & 1) * X_BYTES, TILE_M * 16, 128),
-                         make_desc_noswz(b1_addr, SLAB * 16, 128), idesc1, 0);
-                mma_commit(&z1_full[t & 1]);
+                mma_bf16_p(leader, tmem_base + (uint32_t)((t & 1) * SLAB), desc_add(dX, (uint32_t)(t & 1) * X_BYTES), dB1, idesc1, 0);
+                mma_commit_p(leader, &z1_full[t & 1]);
             };
             auto mma2 = [&](int t) {          // acc += r1 slab^T . dz2 tile   (K = the 128 rows of the tile)
                 mbar_wait(&r_full[t & 1], ((uint32_t)t >> 1) & 1);
                 mbar_wait(&dz_full[t & 1], ((uint32_t)t >> 1) & 1);
                 tc_fence_after();
-                const uint32_t ra = r_addr + (t & 1) * 2 * HALF_BYTES, da = dz_addr + (t & 1) * 2 * HALF_BYTES;
+                const uint32_t off = (uint32_t)(t & 1) * 2 * HALF_BYTES;
 #pragma unroll
-                for (int ks = 0; ks < 8; ++ks)
-                    mma_bf16(tmem_base + 256u, make_smem_desc(ra + ks * 2048, HALF_BYTES, 1024), make_smem_desc(da + ks * 2048, HALF_BYTES, 1024), idesc2,
-                             (t | ks) != 0);
-                mma_commit(&r_empty[t & 1]);
-                mma_commit(&dz_empty[t & 1]);
+                for (int ks = 0; ks < 8; ++ks) mma_bf16_p(leader, tmem_base + 256u, desc_add(dR, off + ks * 2048), desc_add(dDZ, off + ks * 2048), idesc2, (t | ks) != 0);
+                mma_commit_p(leader, &r_empty[t & 1]);
+                mma_commit_p(leader, &dz_empty[t & 1]);
             };
             if (!act_slab) {
                 mma1(0);
@@ -173,18 +174,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad3_kernel(const __grid_con
                 mma2(t);
                 if (!act_slab && t + 2 < T) mma1(t + 2);
             }
-            mma_commit(acc_done);
+            mma_commit_p(leader, acc_done);
         }
     } else if (warp == 1) {
         // ================================================ TMA producer ================================================
-        if (lane == 0) {
+        {
+            const uint32_t leader = elect_one();
             for (int t = 0; t < T; ++t) {
                 const int b = t & 1;
                 mbar_wait(&dz_empty[b], (((uint32_t)t >> 1) & 1) ^ 1);
                 uint8_t* dst = smem + OFF_DZ + b * 2 * HALF_BYTES;
-                mbar_expect_tx(&dz_full[b], 2 * HALF_BYTES);
-                tma_load_3d(dst, &tmDZ, &dz_full[b], 0, tile_of(t) * TILE_M, agent);
-                tma_load_3d(dst + HALF_BYTES, &tmDZ, &dz_full[b], KB, tile_of(t) * TILE_M, agent);
+                mbar_expect_tx_p(leader, &dz_full[b], 2 * HALF_BYTES);
+                tma_load_3d_p(leader, dst, &tmDZ, &dz_full[b], 0, tile_of(t) * TILE_M, agent);
+                tma_load_3d_p(leader, dst + HALF_BYTES, &tmDZ, &dz_full[b], KB, tile_of(t) * TILE_M, agent);
             }
         }
     } else {
