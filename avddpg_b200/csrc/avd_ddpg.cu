@@ -16,8 +16,6 @@
 //
 // BatchNormalization is always the inference affine (models are never called with training=True):
 //   y = g*(x-mu)/sqrt(var+1e-3)+be, with trainable g/be and frozen mu/var.
-#include <stdlib.h>
-
 #include <algorithm>
 
 #include <cuda_bf16.h>
@@ -29,13 +27,6 @@
 namespace avd {
 
 typedef __nv_bfloat16 bf16;
-
-namespace fused {  // avd_fused.cu
-bool supported(const avd_net_dims& d, bool critic);
-int forward(const avd_net_dims& d, bool critic, int A, int64_t R, const float* params, int64_t pstride, const bf16* W2T, const float* b2f,
-            const float* s, int64_t s_rs, int64_t s_cs, const float* act, bf16* H_out, uint32_t* mask_out, float* Z_out, int head,
-            const float* rew, float gamma, float high, float* out, cudaStream_t st, bf16* DZ_out = nullptr, float* loss = nullptr);
-}
 
 namespace fused3 {  // avd_fused3.cu
 enum Mode { MODE_ACTOR_OUT = 0, MODE_TARGET = 1, MODE_Q = 2, MODE_CRITIC_BWD = 3, MODE_ACTOR_BWD = 4, MODE_CRITIC_ACTION = 5 };
@@ -57,7 +48,7 @@ int run(int A, int64_t R, int F, const bf16* DZ, const bf16* W2b, const uint32_t
 
 namespace umma {   // avd_umma.cu
 int gemm_bf16(int layout, int batch, int M, int N, int K, const void* A, int64_t lda, int64_t a_batch, const void* B, int64_t ldb,
-              int64_t b_batch, float* C, int64_t ldc, int64_t c_batch, int splitk, cudaStream_t st, const ReluMaskEpilogue* rm = nullptr);
+              int64_t b_batch, float* C, int64_t ldc, int64_t c_batch, int splitk, cudaStream_t st);
 }
 
 __device__ __forceinline__ void store_out(float* p, float v) { *p = v; }
@@ -244,7 +235,7 @@ __global__ void __launch_bounds__(128) l1_backward_kernel(avd_net_dims d, const 
 // One thread per row; the la (<= 64) per-column parameters are staged in shared memory.
 __global__ void __launch_bounds__(256) action_grad_kernel(avd_net_dims d, const float* __restrict__ params, int64_t pstride,
                                                           const float* __restrict__ act, int64_t R, const float* __restrict__ dHa,
-                                                          float* __restrict__ dact, int folded) {
+                                                          float* __restrict__ dact) {
     const CriticOff o = critic_off(d);
     const int agent = blockIdx.y;
     const float* P = params + (int64_t)agent * pstride;
@@ -252,7 +243,7 @@ __global__ void __launch_bounds__(256) action_grad_kernel(avd_net_dims d, const 
     for (int f = threadIdx.x; f < d.la; f += blockDim.x) {
         wa[f] = P[o.Wa + f];
         ba[f] = P[o.ba + f];
-        gi[f] = folded ? 1.0f : P[o.ga + f] / sqrtf(P[o.vara + f] + kBnEps);   // folded: dHa already carries ga*inva (W2' = diag(sc1) W2)
+        gi[f] = P[o.ga + f] / sqrtf(P[o.vara + f] + kBnEps);
     }
     __syncthreads();
     for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < R; r += (int64_t)gridDim.x * blockDim.x) {
@@ -283,7 +274,6 @@ struct HeadArgs {
     const float* params;   // [A][pstride]
     int64_t pstride;
     int64_t o_b2, o_g2, o_be2, o_mu2, o_var2, o_W3, o_b3;
-    const float* b2f;      // nullable [A][L2]: folded layer-2 bias that replaces params[o_b2] (BN-folded tensor-core path)
     const float* Z;        // [A*R][L2] raw GEMM output (bias not yet added)
     int64_t R;
     float high, gamma;
@@ -312,7 +302,7 @@ __global__ void __launch_bounds__(256) head_kernel(HeadArgs h) {
 #pragma unroll
     for (int j = 0; j < CPL; ++j) {
         const int c = lane + 32 * j;
-        b2[j] = h.b2f ? h.b2f[(int64_t)agent * L2 + c] : P[h.o_b2 + c];
+        b2[j] = P[h.o_b2 + c];
         inv[j] = 1.0f / sqrtf(P[h.o_var2 + c] + kBnEps);
         mu[j] = P[h.o_mu2 + c];
         ginv[j] = P[h.o_g2 + c] * inv[j];
@@ -607,18 +597,14 @@ __global__ void __launch_bounds__(256) pack_fold_kernel(const float* __restrict_
     }
 }
 
-// xext[n] = [ s_hi(4) a_hi 1 0 0 | s_lo(4) a_lo 0 0 0 ] (bf16): B operand of the layer-1 weight-gradient GEMM
-//   G1[f][c] = sum_n dz1[n][f] xext[n][c]   =>  dW1[k][f] = G1[f][k] + G1[f][8+k],  dWa[f] = G1[l1+f][4] + G1[l1+f][12],  db[f] = G1[f][5]
-// Optionally also writes the constant-one column behind the r1 activations of the critic / actor ([N][pitch], column
-// `col`): the weight-gradient GEMM  [r1 | 1]^T dz2  then yields db2 as row F of its output, which is where b2 follows W2.
+// xextT[agent][c][r] (bf16, row pitch Rp): x_ext = [ s_hi(4) a_hi 1 0 0 | s_lo(4) a_lo 0 0 0 ] of row r, stored transposed so that a
+// [16][128-row] tile is the K-major B operand of the fused dgrad kernel (avd_dgrad3.cu):
+//   G1[f][c] = sum_n dz1[n][f] x_ext[n][c]  =>  dW1[k][f] = G1[f][k] + G1[f][8+k],  dWa[f] = G1[l1+f][4] + G1[l1+f][12],  db[f] = G1[f][5]
+// and column 5 (the constant one) also yields db2 = sum_n dz2[n][:].
 __global__ void __launch_bounds__(256) xext_kernel(const float* __restrict__ s, const float* __restrict__ a, int ns, int64_t N,
-                                                   bf16* __restrict__ xext, bf16* __restrict__ ones_c, int64_t pitch_c, int col_c,
-                                                   bf16* __restrict__ ones_a, int64_t pitch_a, int col_a, bf16* __restrict__ xextT, int64_t R,
-                                                   int64_t Rp) {
+                                                   bf16* __restrict__ xextT, int64_t R, int64_t Rp) {
     const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N) return;
-    if (ones_c) ones_c[n * pitch_c + col_c] = __float2bfloat16_rn(1.0f);
-    if (ones_a) ones_a[n * pitch_a + col_a] = __float2bfloat16_rn(1.0f);
     float v[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
     for (int k = 0; k < ns && k < 4; ++k) v[k] = s[n * ns + k];
     v[4] = a[n];
@@ -631,28 +617,12 @@ __global__ void __launch_bounds__(256) xext_kernel(const float* __restrict__ s, 
         lo[k] = __float2bfloat16_rn(v[k] - __bfloat162float(hi[k]));
     }
     hi[5] = __float2bfloat16_rn(1.0f);
-    uint4 h4, l4;
-    h4.x = (uint32_t)__bfloat16_as_ushort(hi[0]) | ((uint32_t)__bfloat16_as_ushort(hi[1]) << 16);
-    h4.y = (uint32_t)__bfloat16_as_ushort(hi[2]) | ((uint32_t)__bfloat16_as_ushort(hi[3]) << 16);
-    h4.z = (uint32_t)__bfloat16_as_ushort(hi[4]) | ((uint32_t)__bfloat16_as_ushort(hi[5]) << 16);
-    h4.w = 0;
-    l4.x = (uint32_t)__bfloat16_as_ushort(lo[0]) | ((uint32_t)__bfloat16_as_ushort(lo[1]) << 16);
-    l4.y = (uint32_t)__bfloat16_as_ushort(lo[2]) | ((uint32_t)__bfloat16_as_ushort(lo[3]) << 16);
-    l4.z = (uint32_t)__bfloat16_as_ushort(lo[4]);
-    l4.w = 0;
-    if (xext) {
-        uint4* dst = reinterpret_cast<uint4*>(xext + n * 16);
-        dst[0] = h4;
-        dst[1] = l4;
-    }
-    if (xextT) {   // transposed copy [A][16][Rp] for the fused dgrad kernel (K-major B operand of dz1^T xext)
-        const int64_t agent = n / R, r = n - agent * R;
-        bf16* col = xextT + agent * 16 * Rp + r;
+    const int64_t agent = n / R, r = n - agent * R;
+    bf16* col = xextT + agent * 16 * Rp + r;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            col[(int64_t)k * Rp] = hi[k];
-            col[(int64_t)(8 + k) * Rp] = lo[k];
-        }
+    for (int k = 0; k < 8; ++k) {
+        col[(int64_t)k * Rp] = hi[k];
+        col[(int64_t)(8 + k) * Rp] = lo[k];
     }
 }
 
@@ -733,7 +703,7 @@ struct Workspace {
     bf16 *cW2b, *cW2T, *tcW2T, *aW2b, *aW2T, *taW2T;   // packed weights (precision 1)
     // BN-folded tensor-core path: sign masks of z1, [x_hi | 1 | x_lo] operand, layer-1 weight-gradient accumulator, folded biases
     uint32_t* mask;
-    bf16 *xext, *xextT;
+    bf16* xextT;               // [A][16][Rp], Rp = R rounded up to 64
     float *G1, *c_b2f, *tc_b2f, *a_b2f, *ta_b2f;
     float *U, *sdq;            // [2][A][l2], [2][A]: head-gradient sums of the critic [0] and actor [1] backward passes
     static constexpr int kMaskWords = 10, kFp = 320;
@@ -742,7 +712,7 @@ struct Workspace {
         const int64_t acts = N * (2 * F + d.l1 + 3 * (int64_t)d.l2) * (int64_t)sizeof(float);
         const int64_t packed = A * (3 * F + 3 * (int64_t)d.l1) * d.l2 * (int64_t)sizeof(bf16);
         const int64_t vecs = 4 * ((N + 3) / 4 * 4) * (int64_t)sizeof(float);
-        const int64_t fold = N * (kMaskWords * 4 + 2 * 16 * 2) + A * (kFp * 16 + 6 * (int64_t)d.l2 + 8) * (int64_t)sizeof(float) + A * 16 * 64 * 2;
+        const int64_t fold = N * (kMaskWords * 4 + 16 * 2) + A * (kFp * 16 + 6 * (int64_t)d.l2 + 8) * (int64_t)sizeof(float) + A * 16 * 64 * 2;
         return acts + packed + vecs + fold + 1024;
     }
     void carve(void* base_, const avd_net_dims& d, int64_t A, int64_t N) {
@@ -775,8 +745,7 @@ struct Workspace {
         U = p; p += 2 * A * d.l2;
         sdq = p; p += (2 * A + 3) / 4 * 4;
         mask = reinterpret_cast<uint32_t*>(p); p += N * kMaskWords;
-        xext = reinterpret_cast<bf16*>(((uintptr_t)p + 15) & ~(uintptr_t)15);
-        xextT = xext + N * 16;       // [A][16][Rp], Rp = R rounded up to 64
+        xextT = reinterpret_cast<bf16*>(((uintptr_t)p + 15) & ~(uintptr_t)15);
     }
 };
 
@@ -892,21 +861,6 @@ struct Pass {
         return o;
     }
 
-    // dz1[a] (R x Fp, bf16, zero pad) = relu'(z1) . (DZ[a] (R x l2) . W2'[a]^T): dgrad GEMM with the sign-mask epilogue
-    int dgrad_masked(const void* DZ, const bf16* W2b, int F, const uint32_t* mask, int mask_words, bf16* dz1, int Fp) const {
-        umma::ReluMaskEpilogue rm{mask, mask_words, dz1, Fp};
-        return umma::gemm_bf16(0, A, (int)R, F, d.l2, DZ, d.l2, R * d.l2, W2b, d.l2, (int64_t)F * d.l2, nullptr, 0, 0, 1, st, &rm);
-    }
-
-    // G1[a] (Fp x 16) += dz1[a]^T (F x R) . xext[a] (R x 16); then unfold everything into the Keras gradient tensors
-    int l1_wgrad_unfold(bool critic, const float* params, const bf16* dz1, int F, int Fp, const bf16* xext, float* G1, float* grads) const {
-        AVD_CUDA_OK(cudaMemsetAsync(G1, 0, (size_t)A * Fp * 16 * sizeof(float), st));
-        const int tiles = ((F + 127) / 128) * A;
-        int split = (int)std::min<int64_t>((R + 63) / 64, std::max(1, 4 * sm_count() / std::max(1, tiles)));
-        if (int rc = umma::gemm_bf16(1, A, F, 16, (int)R, dz1, Fp, R * Fp, xext, 16, R * 16, G1, 16, (int64_t)Fp * 16, std::max(1, split), st)) return rc;
-        return unfold(critic, params, F, Fp, G1, grads);
-    }
-
     // fused dgrad + layer-1 weight gradient (avd_dgrad3.cu), then unfold
     int dgrad3_unfold(bool critic, const float* params, const bf16* DZ, const bf16* W2b, int F, int Fp, const uint32_t* mask, int mask_words,
                       const bf16* xextT, float* G1, float* grads) const {
@@ -1014,13 +968,10 @@ extern "C" int avd_actor_forward(const avd_net_dims* dims, int32_t A, int64_t R,
     float* H = reinterpret_cast<float*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
     float* Z = H + N * d.l1;
     bf16* W2T = reinterpret_cast<bf16*>(Z + N * d.l2);
-    if (precision && fused::supported(d, false)) {   // fused kernel: H / Z are never materialised, their space holds the folded bias
+    if (precision && fused3::supported(d)) {   // fused kernel: H / Z are never materialised, their space holds the folded bias
         AVD_TRY(p.pack_fold(false, actor_params, nullptr, W2T, H));
-        if (fused3::supported(d))
-            return fused3::run(fused3::MODE_ACTOR_OUT, d, A, R, actor_params, o.total, W2T, H, s, s_rs, s_cs, nullptr, nullptr, 0.f, action_high, nullptr,
+        return fused3::run(fused3::MODE_ACTOR_OUT, d, A, R, actor_params, o.total, W2T, H, s, s_rs, s_cs, nullptr, nullptr, 0.f, action_high, nullptr,
                                nullptr, out, nullptr, nullptr, nullptr, nullptr, nullptr, p.st);
-        return fused::forward(d, false, A, R, actor_params, o.total, W2T, H, s, s_rs, s_cs, nullptr, nullptr, nullptr, nullptr, 1, nullptr, 0.f,
-                              action_high, out, p.st);
     }
     if (precision) AVD_TRY(p.pack(actor_params, o.total, o.W2, d.l1, nullptr, W2T));
     AVD_TRY(p.layer1(false, actor_params, s, s_rs, s_cs, nullptr, H));
@@ -1047,12 +998,10 @@ extern "C" int avd_critic_forward(const avd_net_dims* dims, int32_t A, int64_t R
     float* H = reinterpret_cast<float*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
     float* Z = H + N * F;
     bf16* W2T = reinterpret_cast<bf16*>(Z + N * d.l2);
-    if (precision && fused::supported(d, true)) {
+    if (precision && fused3::supported(d)) {
         AVD_TRY(p.pack_fold(true, critic_params, nullptr, W2T, H));
-        if (fused3::supported(d))
-            return fused3::run(fused3::MODE_Q, d, A, R, critic_params, o.total, W2T, H, s, d.ns, 1, a, nullptr, 0.f, 0.f, nullptr, nullptr, q, nullptr,
+        return fused3::run(fused3::MODE_Q, d, A, R, critic_params, o.total, W2T, H, s, d.ns, 1, a, nullptr, 0.f, 0.f, nullptr, nullptr, q, nullptr,
                                nullptr, nullptr, nullptr, nullptr, p.st);
-        return fused::forward(d, true, A, R, critic_params, o.total, W2T, H, s, d.ns, 1, a, nullptr, nullptr, nullptr, 3, nullptr, 0.f, 0.f, q, p.st);
     }
     if (precision) AVD_TRY(p.pack(critic_params, o.total, o.W2, F, nullptr, W2T));
     AVD_TRY(p.layer1(true, critic_params, s, d.ns, 1, a, H));
@@ -1137,66 +1086,6 @@ static int apply_local_updates(const avd_learn_io* io, void* stream) {
     return AVD_OK;
 }
 
-// The learn step on the fused tensor-core kernels (precision 1, 256/48/128 layers).  BatchNorm of layer 1 is folded into
-// layer 2 (pack_fold_kernel), so the stored activation is r1 = relu(z1) and the layer-1 backward needs only its sign mask:
-//   forward (+mask, r1, z2) -> head-backward -> wgrad G2 = r1^T dz2 -> dgrad with ReLU-mask epilogue (dz1, bf16)
-//   -> G1 = dz1^T [x_hi | 1 | x_lo] -> unfold_kernel (dW2, dgamma1, dbeta1, dW1, db1)
-static int learn_fused(const avd_learn_io* io, const Pass& p, const Workspace& w, cudaStream_t st) {
-    const avd_net_dims d = io->dims;
-    const int A = io->A;
-    const int64_t R = io->rows_per_agent, N = (int64_t)A * R;
-    const ActorOff ao = actor_off(d);
-    const CriticOff co = critic_off(d);
-    const int F = d.l1 + d.la;
-    constexpr int Fp = Workspace::kFp, MW = Workspace::kMaskWords;
-    bf16* Hc = reinterpret_cast<bf16*>(w.H);        // r1 of the critic   [N][F]
-    bf16* Ha = reinterpret_cast<bf16*>(w.H1a);      // r1 of the actor    [N][l1]
-    bf16* dz1 = reinterpret_cast<bf16*>(w.DH);      // [N][Fp] (critic) / [N][l1] (actor); shares DH with the action-column dgrad
-    AVD_TRY(p.pack_fold(false, io->t_actor, nullptr, w.taW2T, w.ta_b2f));
-    AVD_TRY(p.pack_fold(true, io->t_critic, nullptr, w.tcW2T, w.tc_b2f));
-    AVD_TRY(p.pack_fold(true, io->critic, w.cW2b, w.cW2T, w.c_b2f));
-    AVD_TRY(p.pack_fold(false, io->actor, w.aW2b, w.aW2T, w.a_b2f));
-    xext_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(io->s, io->a, d.ns, N, w.xext, nullptr, 0, 0, nullptr, 0, 0, nullptr, R, 0);
-    AVD_LAUNCH_OK();
-    // ---- TD target: y = r + gamma * target_critic(s', target_actor(s'))            trainer.py:493-494
-    AVD_TRY(fused::forward(d, false, A, R, io->t_actor, ao.total, w.taW2T, w.ta_b2f, io->s2, d.ns, 1, nullptr, nullptr, nullptr, nullptr, 1, nullptr,
-                           0.f, io->action_high, w.a2, st));
-    AVD_TRY(fused::forward(d, true, A, R, io->t_critic, co.total, w.tcW2T, w.tc_b2f, io->s2, d.ns, 1, w.a2, nullptr, nullptr, nullptr, 2, io->r,
-                           io->gamma, 0.f, w.y, st));
-    // ---- critic loss gradient on (s, a)                                             trainer.py:495-498
-    AVD_TRY(fused::forward(d, true, A, R, io->critic, co.total, w.cW2T, w.c_b2f, io->s, d.ns, 1, io->a, Hc, w.mask, w.Z, 0, nullptr, 0.f, 0.f, nullptr,
-                           st));
-    {
-        HeadArgs h = critic_head(d, io->critic, w.Z, R);
-        h.b2f = w.c_b2f;
-        h.y = w.y; h.out = w.q; h.DZ = w.DZ; h.grads = io->critic_grad; h.gstride = co.n_train; h.loss = io->loss;
-        AVD_TRY(launch_head<HEAD_CRITIC_BWD>(h, d.l2, A, st, true));
-    }
-    AVD_TRY(p.wgrad(Hc, F, w.DZ, io->critic_grad, co.n_train, co.W2));
-    AVD_TRY(p.dgrad_masked(w.DZ, w.cW2b, F, w.mask, MW, dz1, Fp));
-    AVD_TRY(p.l1_wgrad_unfold(true, io->critic, dz1, F, Fp, w.xext, w.G1, io->critic_grad));
-    // ---- actor loss gradient: -mean(critic(s, actor(s)))                            trainer.py:501-506
-    AVD_TRY(fused::forward(d, false, A, R, io->actor, ao.total, w.aW2T, w.a_b2f, io->s, d.ns, 1, nullptr, Ha, w.mask, w.Za, 1, nullptr, 0.f,
-                           io->action_high, w.a2, st));   // pi
-    // critic(s, pi) with the action-only head-backward fused into the TMEM epilogue: emits dz2 (bf16) directly
-    AVD_TRY(fused::forward(d, true, A, R, io->critic, co.total, w.cW2T, w.c_b2f, io->s, d.ns, 1, w.a2, nullptr, nullptr, nullptr, 4, nullptr, 0.f, 0.f,
-                           nullptr, st, (bf16*)w.DZ, io->loss));
-    AVD_TRY(umma::gemm_bf16(0, A, (int)R, d.la, d.l2, w.DZ, d.l2, R * d.l2, w.cW2b + (int64_t)d.l1 * d.l2, d.l2, (int64_t)F * d.l2, w.DH, d.la,
-                            R * d.la, 1, st));   // action columns of dR only
-    action_grad_kernel<<<dim3((unsigned)std::min<int64_t>((R + 255) / 256, 2048), A), 256, 0, st>>>(d, io->critic, co.total, w.a2, R, w.DH, w.dpi, 1);
-    AVD_LAUNCH_OK();
-    {
-        HeadArgs h = actor_head(d, io->actor, w.Za, R, io->action_high);
-        h.b2f = w.a_b2f;
-        h.dpi = w.dpi; h.DZ = w.DZ; h.grads = io->actor_grad; h.gstride = ao.n_train;
-        AVD_TRY(launch_head<HEAD_ACTOR_BWD>(h, d.l2, A, st, true));
-    }
-    AVD_TRY(p.wgrad(Ha, d.l1, w.DZ, io->actor_grad, ao.n_train, ao.W2));
-    AVD_TRY(p.dgrad_masked(w.DZ, w.aW2b, d.l1, w.mask, 8, dz1, d.l1));
-    AVD_TRY(p.l1_wgrad_unfold(false, io->actor, dz1, d.l1, d.l1, w.xext, w.G1, io->actor_grad));
-    return apply_local_updates(io, (void*)st);
-}
-
 // The learn step on the third-generation kernels: six persistent pass launches (avd_fused3.cu) cover every forward pass,
 // both head backwards and the critic -> actor link; per differentiated net only dz2 (256 B per row) and the ReLU sign masks
 // (40 B) go to HBM, for the layer-2 weight gradient (avd_wgrad3.cu, recomputes r1 on chip) and the fused dgrad + layer-1
@@ -1217,7 +1106,7 @@ static int learn_fused3(const avd_learn_io* io, const Pass& p, const Workspace& 
     AVD_TRY(p.pack_fold(true, io->critic, w.cW2b, w.cW2T, w.c_b2f));
     AVD_TRY(p.pack_fold(false, io->actor, w.aW2b, w.aW2T, w.a_b2f));
     const int64_t Rp = (R + 63) / 64 * 64;
-    xext_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(io->s, io->a, d.ns, N, nullptr, nullptr, 0, 0, nullptr, 0, 0, w.xextT, R, Rp);
+    xext_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(io->s, io->a, d.ns, N, w.xextT, R, Rp);
     AVD_LAUNCH_OK();
     AVD_CUDA_OK(cudaMemsetAsync(w.U, 0, (size_t)(2 * A * d.l2 + 2 * A) * sizeof(float), st));   // U and sdq are adjacent
     auto head_unfold = [&](bool critic, const float* params, float* grads, const float* U, const float* sdq) {
@@ -1279,12 +1168,8 @@ extern "C" int avd_ddpg_learn(const avd_learn_io* io, void* stream) {
     AVD_CUDA_OK(cudaMemsetAsync(io->actor_grad, 0, (size_t)A * ao.n_train * sizeof(float), st));
     AVD_CUDA_OK(cudaMemsetAsync(io->critic_grad, 0, (size_t)A * co.n_train * sizeof(float), st));
     if (io->loss) AVD_CUDA_OK(cudaMemsetAsync(io->loss, 0, (size_t)A * 2 * sizeof(float), st));
-    const bool fz = tc && fused::supported(d, false) && fused::supported(d, true);   // fused layer1 -> tcgen05 -> head kernels
-    if (fz) {
-        static int gen = -1;
-        if (gen < 0) { const char* e = getenv("AVD_LEARN_GEN"); gen = (e && e[0] == '2') ? 2 : 3; }   // "2": previous generation (A/B comparisons)
-        return (gen == 3 && fused3::supported(d)) ? learn_fused3(io, p, w, st) : learn_fused(io, p, w, st);
-    }
+    const bool fz = tc && fused3::supported(d);   // persistent fused pass / dgrad / wgrad kernels
+    if (fz) return learn_fused3(io, p, w, st);
     if (tc) {   // bf16 copies of the four layer-2 kernels (K-major for forward, and for dgrad on the online nets)
         AVD_TRY(p.pack(io->t_actor, ao.total, ao.W2, d.l1, nullptr, w.taW2T));
         AVD_TRY(p.pack(io->t_critic, co.total, co.W2, F, nullptr, w.tcW2T));
@@ -1334,7 +1219,7 @@ extern "C" int avd_ddpg_learn(const avd_learn_io* io, void* stream) {
         AVD_TRY(launch_head<HEAD_CRITIC_BWD_ACTION>(h, d.l2, A, st, tc));
     }
     AVD_TRY(p.dgrad(w.DZ, io->critic, co.total, co.W2, w.cW2b, F, d.l1, d.la, w.DH));   // action columns only
-    action_grad_kernel<<<dim3((unsigned)std::min<int64_t>((R + 255) / 256, 2048), A), 256, 0, st>>>(d, io->critic, co.total, w.a2, R, w.DH, w.dpi, 0);
+    action_grad_kernel<<<dim3((unsigned)std::min<int64_t>((R + 255) / 256, 2048), A), 256, 0, st>>>(d, io->critic, co.total, w.a2, R, w.DH, w.dpi);
     AVD_LAUNCH_OK();
     {
         HeadArgs h = actor_head(d, io->actor, w.Za, R, io->action_high);

@@ -33,7 +33,6 @@ constexpr int STAGES_TN = 2, STAGES_NT = 4;
 constexpr int NUM_THREADS = 192;             // warp 0 TMA, warp 1 MMA (+TMEM alloc), warps 2..5 epilogue
 
 struct GemmParams {
-    ReluMaskEpilogue rm;
     int M, N;              // valid output rows / columns (per batch)
     int k_blocks;          // number of 64-deep K blocks per split
     int splitk;
@@ -138,19 +137,10 @@ __global__ void __launch_bounds__(NUM_THREADS, (STAGES <= 2) ? 3 : 1) gemm_bf16_
 #pragma unroll 1
         for (int c = 0; c < BN_ / 32; ++c) {
             const int col0 = n0 + c * 32;
-            if (g.rm.mask ? (col0 >= g.rm.ldo) : (col0 >= g.N)) break;
+            if (col0 >= g.N) break;
             float v[32];
             tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
-            if (g.rm.mask) {
-                if (rows_here > 0) {
-                    const int64_t grow = (int64_t)batch * g.M + min(row, g.M - 1);
-                    const uint32_t neg = g.rm.mask[grow * g.rm.words + (col0 >> 5)];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if ((neg & (0x80000000u >> j)) || col0 + j >= g.N) v[j] = 0.0f;
-                    store_block_32x32_bf16(scratch, v, g.rm.out + ((int64_t)batch * g.M + m0 + q * 32) * g.rm.ldo + col0, g.rm.ldo, rows_here, lane);
-                }
-            } else if (g.atomic) {
+            if (g.atomic) {
                 if (row < g.M) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
@@ -205,12 +195,10 @@ static int make_map(CUtensorMap* map, const void* base, uint64_t inner, uint64_t
 }
 
 int gemm_bf16(int layout, int batch, int M, int N, int K, const void* A, int64_t lda, int64_t a_batch, const void* B, int64_t ldb,
-              int64_t b_batch, float* C, int64_t ldc, int64_t c_batch, int splitk, cudaStream_t st, const ReluMaskEpilogue* rm) {
+              int64_t b_batch, float* C, int64_t ldc, int64_t c_batch, int splitk, cudaStream_t st) {
     AVD_REQUIRE(layout == 0 || layout == 1, "layout must be 0 (TN) or 1 (NT)");
     AVD_REQUIRE(batch >= 1 && M >= 1 && N >= 1 && K >= 1 && splitk >= 1, "bad GEMM sizes");
-    AVD_REQUIRE(A && B && (C || rm), "null operand");
-    AVD_REQUIRE(!rm || (layout == 0 && splitk == 1 && rm->mask && rm->out && rm->ldo % 32 == 0 && rm->ldo >= N),
-                "the ReLU-mask epilogue needs the TN layout without split-K and an output pitch that is a multiple of 32");
+    AVD_REQUIRE(A && B && C, "null operand");
     AVD_REQUIRE(lda % 8 == 0 && ldb % 8 == 0 && a_batch % 8 == 0 && b_batch % 8 == 0, "bf16 leading dimensions must be multiples of 8 elements (16 B)");
     AVD_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0, "operands must be 16-byte aligned");
     static bool attr_set = false;
@@ -224,14 +212,12 @@ int gemm_bf16(int layout, int batch, int M, int N, int K, const void* A, int64_t
     const int kblocks_total = (K + BK - 1) / BK;
     if (splitk > kblocks_total) splitk = kblocks_total;
     GemmParams g;
-    if (rm) g.rm = *rm; else g.rm = ReluMaskEpilogue{nullptr, 0, nullptr, 0};
     g.M = M; g.N = N; g.splitk = splitk;
     g.k_blocks = (kblocks_total + splitk - 1) / splitk;
     g.C = C; g.ldc = ldc; g.c_batch = c_batch; g.atomic = (splitk > 1 || layout == 1) ? 1 : 0;
-    const bool narrow = layout == 1 && N <= 64;     // e.g. the layer-1 weight gradient  dz1^T [x_hi | 1 | x_lo]  (N = 16)
+    const bool narrow = layout == 1 && N <= 64;     // narrow outputs: one 64-column MN chunk of B per stage
     const int bn = narrow ? 64 : BN;
-    const int ncols = rm ? (int)rm->ldo : N;        // the mask epilogue also writes the zero pad up to the output pitch
-    dim3 grid((M + BM - 1) / BM, (ncols + bn - 1) / bn, batch * splitk);
+    dim3 grid((M + BM - 1) / BM, (N + bn - 1) / bn, batch * splitk);
     g.n_fastest = (layout == 0 && grid.y > 1 && grid.x <= 65535) ? 1 : 0;
     if (g.n_fastest) std::swap(grid.x, grid.y);
     if (layout == 0) {
@@ -253,5 +239,5 @@ int gemm_bf16(int layout, int batch, int M, int N, int K, const void* A, int64_t
 
 extern "C" int avd_gemm_bf16(int layout, int batch, int M, int N, int K, const void* A, int64_t lda, int64_t a_batch, const void* B,
                              int64_t ldb, int64_t b_batch, float* C, int64_t ldc, int64_t c_batch, int splitk, void* stream) {
-    return avd::umma::gemm_bf16(layout, batch, M, N, K, A, lda, a_batch, B, ldb, b_batch, C, ldc, c_batch, splitk, (cudaStream_t)stream, nullptr);
+    return avd::umma::gemm_bf16(layout, batch, M, N, K, A, lda, a_batch, B, ldb, b_batch, C, ldc, c_batch, splitk, (cudaStream_t)stream);
 }

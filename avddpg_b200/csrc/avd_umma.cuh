@@ -9,17 +9,6 @@
 namespace avd {
 namespace umma {
 
-// Optional epilogue of the dgrad GEMM (TN layout): instead of storing dR = dZ W2'^T in fp32, zero the entries whose
-// layer-1 pre-activation was not positive (ReLU backward, agent/model.py:19,27,62,69 through trainer.py:498,506) and
-// store bf16.  The sign bits come from the forward kernel (avd_fused.cu): word w of a row covers columns 32w..32w+31,
-// column j of the word sits at bit 31-j, 1 = "z1 had its sign bit set".  Pad columns N..ldo-1 are written as zeros.
-struct ReluMaskEpilogue {
-    const uint32_t* mask;  // [batch*M][words]   (nullptr: epilogue disabled)
-    int words;
-    __nv_bfloat16* out;    // [batch*M][ldo]
-    int64_t ldo;
-};
-
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // ---- mbarrier ----------------------------------------------------------------------------------
@@ -170,27 +159,6 @@ __device__ __forceinline__ void store_block_32x32(float* scratch, const float* v
                 if (cq + 2 < ncols) dst[2] = c;
                 if (cq + 3 < ncols) dst[3] = d;
             }
-        }
-    }
-    __syncwarp();
-}
-
-// Same staging, bf16 output (e.g. dz2 tiles consumed by the dgrad / wgrad GEMMs): 8-byte stores, 4 rows x 64 B per instruction.
-__device__ __forceinline__ void store_block_32x32_bf16(float* scratch, const float* v, __nv_bfloat16* row_ptr0, int64_t ld, int nrows, int lane) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) scratch[lane * 33 + j] = v[j];
-    __syncwarp();
-    const int cq = (lane & 7) * 4, rsub = lane >> 3;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int r = i * 4 + rsub;
-        const __nv_bfloat162 lo = __floats2bfloat162_rn(scratch[r * 33 + cq], scratch[r * 33 + cq + 1]);
-        const __nv_bfloat162 hi = __floats2bfloat162_rn(scratch[r * 33 + cq + 2], scratch[r * 33 + cq + 3]);
-        if (r < nrows) {
-            uint2 pk;
-            pk.x = *reinterpret_cast<const uint32_t*>(&lo);
-            pk.y = *reinterpret_cast<const uint32_t*>(&hi);
-            *reinterpret_cast<uint2*>(row_ptr0 + (int64_t)r * ld + cq) = pk;
         }
     }
     __syncwarp();

@@ -1,0 +1,25 @@
+"""Per-tensor error of the bf16 tensor-core learn step (precision=1) against the fp32 oracle, for a few batch sizes.
+    python tools/accuracy_report.py > profiles/r01_tensor_core_accuracy.txt"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from oracle import ddpg_np as D
+import tests.test_gpu_ddpg as T
+from avddpg_b200 import _lib, trainer
+from avddpg_b200.config import Config
+
+mods = dict(lib=_lib, trainer=trainer, Config=Config)
+print("# rel-L2 error of every gradient tensor, precision=1 (bf16 tcgen05) vs oracle/ddpg_np.py (fp32 numpy)")
+for R in (64, 1024, 16384, 262144):
+    conf, pop, nets, batches, (s, a, r, s2) = T.build_population(mods, 1, R, [50])
+    pop.precision = 1
+    pop.learn(s, a, r, s2, apply_updates=False)
+    torch.cuda.synchronize()
+    ocg, oag, info = D.learn(nets[0][0], nets[0][1], nets[0][2], nets[0][3], batches[0], gamma=conf.gamma, high=conf.action_high)
+    row = []
+    for bank, ref in ((pop.critic, ocg), (pop.actor, oag)):
+        for name in bank.trainable_names:
+            got = bank.view(name, 0, bank.grad).cpu().numpy()
+            row.append(f"{bank.kind[0]}.{name}={T._l2(got, ref[name].reshape(got.shape)):.1e}")
+    loss = pop.loss[0].cpu().numpy()
+    print(f"R={R:7d}  loss_c {abs(loss[0]-info['critic_loss'])/abs(info['critic_loss']):.1e} loss_a {abs(loss[1]-info['actor_loss'])/abs(info['actor_loss']):.1e}  " + " ".join(row))
