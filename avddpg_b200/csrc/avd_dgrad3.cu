@@ -187,14 +187,23 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dgrad3_kernel(const __grid_con
         const int q = warp & 3, grp = (warp - 2) >> 2;
         const int row = q * 32 + lane;
         const uint32_t tlane = (uint32_t)(q * 32) << 16;
-        for (int t = 0; t < T; ++t) {
+        // The sign masks of a chunk are fetched while the PREVIOUS chunk of this group is processed (chunks k, k + 4, ...):
+        // a load issued right before its use would put a full global-memory latency on every chunk of the pipeline.
+        auto load_mask = [&](uint32_t k) -> uint2 {
+            const int t = (int)(k / (uint32_t)NC), c = (int)(k - (uint32_t)t * NC);
+            if (t >= T) return make_uint2(0u, 0u);
             const int64_t r_in = (int64_t)tile_of(t) * TILE_M + row;
             const int64_t nrow = (int64_t)agent * g.R + (r_in < g.R ? r_in : g.R - 1);
+            return __ldg(reinterpret_cast<const uint2*>(g.mask + nrow * g.mask_words + 2 * c));
+        };
+        uint2 neg_next = load_mask((uint32_t)grp);
+        for (int t = 0; t < T; ++t) {
             for (int c = 0; c < NC; ++c) {
                 const uint32_t k = (uint32_t)(t * NC + c);
                 if ((int)(k & 3) != grp) continue;
                 const uint32_t slot = k % NRING;
-                const uint2 neg = *reinterpret_cast<const uint2*>(g.mask + nrow * g.mask_words + 2 * c);
+                const uint2 neg = neg_next;
+                neg_next = load_mask(k + 4);
                 const uint32_t pk = (uint32_t)(t * NP + (c >> 1)), sb = pk & 1;
                 mbar_wait(&d_full[slot], (k / NRING) & 1);
                 tc_fence_after();

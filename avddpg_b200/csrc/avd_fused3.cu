@@ -316,13 +316,25 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused3_kernel(const __grid_con
             valid = r_in < g.R;
             return (int64_t)agent * g.R + (valid ? r_in : g.R - 1);
         };
-        // hi/lo-split input row of local tile t -> X buffer t & 1:  [v_hi(5) v_lo(5) v_hi(5) 0],  v = (s0..s3, 1)
-        auto produce_x = [&](int t) {
+        // Per-row global inputs are fetched one stage ahead of their use and carried in registers: a load issued right before
+        // its use would put a full global-memory latency on the critical path of every tile.
+        //   xs   : state row of the tile whose X buffer this thread's quarter writes at the end of its next convert()
+        //   a_pf : action of the next tile whose action-branch columns this quarter converts
+        //   y_pf : reward / TD target / d loss/d action of the tile whose pass 2 comes next;  a_ag: action for action_grad()
+        float xs[4] = {0.f, 0.f, 0.f, 0.f}, a_pf = 0.0f, y_pf = 0.0f, a_ag = 0.0f;
+        auto xg_of = [&](int tc) { return CRITIC ? 2 * (1 - (tc & 1)) : (tc & 3); };      // quarter that stages tile tc + 2 during convert(tc)
+        auto is_action_quarter = [&](int tc) { return CRITIC && (c4 >> 1) == (tc & 1); };   // quarters 2 (tc & 1), 2 (tc & 1) + 1
+        auto load_x = [&](int t) {
             bool valid;
             const int64_t n = rowinfo(t, valid);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) xs[k] = k < d.ns ? __ldg(g.s + n * g.s_rs + k * g.s_cs) : 0.0f;
+        };
+        // hi/lo-split input row of local tile t -> X buffer t & 1:  [v_hi(5) v_lo(5) v_hi(5) 0],  v = (s0..s3, 1)
+        auto write_x = [&](int t) {
             bf16 hi[5], lo[5];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) split_bf16(k < d.ns ? __ldg(g.s + n * g.s_rs + k * g.s_cs) : 0.0f, hi[k], lo[k]);
+            for (int k = 0; k < 4; ++k) split_bf16(xs[k], hi[k], lo[k]);
             hi[4] = __float2bfloat16_rn(1.0f);
             lo[4] = __float2bfloat16_rn(0.0f);
             uint8_t* xbase = smem + OFF_X + (t & 1) * X_BYTES;
@@ -339,9 +351,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused3_kernel(const __grid_con
             bool valid;
             const int64_t nrow = rowinfo(tc, valid);
             const int ga0 = CRITIC ? 2 * (tc & 1) : -1;          // quarter that converts action columns 0..31; ga0 + 1: columns 32..la-1
-            const int xg = CRITIC ? 2 * (1 - (tc & 1)) : (tc & 3);   // quarter that stages the input tile of local tile tc + 2
-            float a_val = 0.0f;
-            if (CRITIC && (c4 == ga0 || c4 == ga0 + 1)) a_val = __ldg(g.act + nrow);
+            const float a_val = a_pf;
             mbar_wait(z1_full, (uint32_t)tc & 1);
             tc_fence_after();
             const uint32_t kc = (uint32_t)(tc * NKB + c4), sl = kc % NSLOT;
@@ -396,12 +406,25 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused3_kernel(const __grid_con
                 if (lane == 0) mbar_arrive(&a_full[sla]);
                 if (BWD && valid) g.mask_out[nrow * g.mask_words + 8 + (j0 >> 5)] = m;
             }
-            if (c4 == xg && tc + 2 < T) produce_x(tc + 2);       // X buffer tc & 1 is free: z1_full(tc) implies the layer-1 MMA has read it
+            if (c4 == xg_of(tc) && tc + 2 < T) write_x(tc + 2);  // X buffer tc & 1 is free: z1_full(tc) implies the layer-1 MMA has read it
+            // prefetch for the next convert()
+            if (tc + 3 < T && c4 == xg_of(tc + 1)) load_x(tc + 3);
+            if (tc + 1 < T && is_action_quarter(tc + 1)) {
+                bool v1;
+                a_pf = __ldg(g.act + rowinfo(tc + 1, v1));
+            }
         };
 
         // ---- stage 2: partial row sums of the head over this warp's 32 z2 columns
         auto pass1 = [&](int tc) {
             const int buf = tc & 1;
+            if (MODE == MODE_TARGET || BWD) {                    // consumed by pass2(tc), one iteration later
+                bool v0;
+                const int64_t n0 = rowinfo(tc, v0);
+                if (MODE == MODE_TARGET) { if (c4 == 0) y_pf = __ldg(g.rew + n0); }
+                else if (MODE == MODE_CRITIC_BWD) y_pf = __ldg(g.y + n0);
+                else y_pf = __ldg(g.dpi + n0);
+            }
             mbar_wait(&acc_full[buf], ((uint32_t)tc >> 1) & 1);
             tc_fence_after();
             float v[32];
@@ -440,10 +463,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused3_kernel(const __grid_con
             if (!HAS_DZ && c4 != 0) return;
             bool valid;
             const int64_t nrow = rowinfo(tc, valid);
-            float yv = 0.0f;
-            if (MODE == MODE_TARGET) yv = __ldg(g.rew + nrow);
-            if (MODE == MODE_CRITIC_BWD) yv = __ldg(g.y + nrow);
-            if (MODE == MODE_ACTOR_BWD) yv = __ldg(g.dpi + nrow);
+            const float yv = y_pf;
+            if (ACTION && c4 == (tc & 3)) a_ag = __ldg(g.act + nrow);   // consumed by action_grad(tc), two stages later
             mbar_wait(&part_full[buf], ((uint32_t)tc >> 1) & 1);
             const float* pb = part + buf * 4 * TILE_M + row;
             const float qv = pb[0] + pb[TILE_M] + pb[2 * TILE_M] + pb[3 * TILE_M] + b3f;
@@ -524,7 +545,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused3_kernel(const __grid_con
             if (c4 != (tc & 3)) return;
             bool valid;
             const int64_t nrow = rowinfo(tc, valid);
-            const float a_val = __ldg(g.act + nrow);
+            const float a_val = a_ag;
             mbar_wait(dra_full, (uint32_t)tc & 1);
             tc_fence_after();
             float acc = 0.0f;
@@ -548,8 +569,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused3_kernel(const __grid_con
         };
 
         // ---- software pipeline
-        if (cw < 4) produce_x(0);
-        else if (cw < 8 && T > 1) produce_x(1);
+        if (cw < 4) { load_x(0); write_x(0); }
+        else if (cw < 8 && T > 1) { load_x(1); write_x(1); }
+        if (T > 2 && c4 == xg_of(0)) load_x(2);
+        if (is_action_quarter(0)) {
+            bool v0;
+            a_pf = __ldg(g.act + rowinfo(0, v0));
+        }
         convert(0);
         for (int i = 0; i < T; ++i) {
             if (ACTION) {                    // the action-column dgrad borrows the z1 columns between convert(i+1) and the next layer-1 MMA

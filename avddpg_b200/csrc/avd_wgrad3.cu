@@ -3,16 +3,17 @@
 //   G2[f][j] += sum_n r1[n][f] dz2[n][j],      r1 = relu(x W1 + b1)   (the BN-folded formulation of avd_fused3.cu)
 //
 // r1 is 608 B per row as bf16; the inputs it is made of are 16-20 B.  So instead of streaming r1 back from HBM, each CTA
-// owns one 128-feature slab of one agent and, per 128-row tile,
+// loads a 128-row dz2 tile ONCE (TMA) and walks the 128-feature slabs of the layer:
 //   x tile --tcgen05.mma (hi/lo split bf16, K = 16)--> z1 slab in TMEM --converter warps: relu, bf16--> r1 slab in shared
-//   memory, laid out as the MN-major A operand (M = features, K = rows) --tcgen05.mma against the dz2 tile (TMA, MN-major B)-->
-//   one 128 x 128 fp32 accumulator that stays in TMEM for the whole kernel and is added to global memory once per CTA.
-// HBM traffic per row: 256 B (dz2, re-read once per feature slab, mostly from L2) + 16-20 B inputs; nothing is written.
+//   memory, laid out as the MN-major A operand (M = features, K = rows) --tcgen05.mma against the dz2 tile (MN-major B)-->
+//   one 128 x 128 fp32 accumulator per slab; the 2-3 accumulators stay in TMEM for the whole kernel and are added to global
+//   memory once per CTA.
+// HBM traffic per row: 256 B (dz2) + 16-20 B inputs; nothing is written.
 // The action-branch slab of the critic (one input per feature, model.py:69-70) is converted on the CUDA cores.
 // Reference: workers/trainer.py:498, 506 (tape.gradient) through agent/model.py:19-33, 62-77.
 //
 // Warps: 0 MMA issuer, 1 TMA producer, 2..9 converters (TMEM lane quadrant = warp % 4, 64 columns each).
-// TMEM: z1 slab double buffered (2 x 128 columns) + accumulator (128 columns).
+// TMEM: three slab accumulators (3 x 128 columns) + the z1 slab (128 columns).
 #include <cudaTypedefs.h>
 
 #include <algorithm>
@@ -32,8 +33,9 @@ constexpr int NUM_THREADS = 32 * 10;
 constexpr int HALF_BYTES = TILE_M * 128;                     // [128 rows][64 bf16]: 16 KB
 constexpr int OFF_DZ = 0;                                    // 2 x dz2 tile (2 halves of 64 columns)
 constexpr int OFF_R1 = OFF_DZ + 2 * 2 * HALF_BYTES;          // 2 x r1 slab (2 halves of 64 features)
-constexpr int OFF_B1 = OFF_R1 + 2 * 2 * HALF_BYTES;          // W1ext slab, no-swizzle K-major [2 chunks][128 rows][16 B]
-constexpr int OFF_X = OFF_B1 + 2 * SLAB * 16;                // 2 input tiles [2 chunks][128 rows][16 B]
+constexpr int L1N = 256;
+constexpr int OFF_B1 = OFF_R1 + 2 * 2 * HALF_BYTES;          // W1ext, no-swizzle K-major [2 chunks][256 rows][16 B]
+constexpr int OFF_X = OFF_B1 + 2 * L1N * 16;                 // 2 input tiles [2 chunks][128 rows][16 B]
 constexpr int X_BYTES = 2 * TILE_M * 16;
 constexpr int OFF_TAB = OFF_X + 2 * X_BYTES;                 // wa[64] ba[64]
 constexpr int OFF_BAR = OFF_TAB + 512;
@@ -49,7 +51,7 @@ struct Args {
     const float* act;           // [A*R] (critic)
     float* grads;               // [A][gstride]; G2 is accumulated at grads + oW2 (row-major [F][128])
     int64_t gstride, oW2;
-    int tiles_per_agent, ctas_per_slab;
+    int tiles_per_agent, ctas_per_agent;
 };
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
@@ -78,21 +80,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad3_kernel(const __grid_con
     uint64_t* r_full = dz_empty + 2;                                  // [2]
     uint64_t* r_empty = r_full + 2;                                   // [2]
     uint64_t* x_full = r_empty + 2;                                   // [2]
-    uint64_t* z1_full = x_full + 2;                                   // [2]
-    uint64_t* z1_empty = z1_full + 2;                                 // [2]
-    uint64_t* acc_done = z1_empty + 2;
+    uint64_t* z1_full = x_full + 2;
+    uint64_t* acc_done = z1_full + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_done + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const avd_net_dims d = g.d;
-    const int per_agent = g.FT * g.ctas_per_slab;
-    const int agent = (int)blockIdx.x / per_agent;
-    const int rem = (int)blockIdx.x - agent * per_agent;
-    const int ft = rem / g.ctas_per_slab, cta = rem - ft * g.ctas_per_slab;
-    const int T = (g.tiles_per_agent - cta + g.ctas_per_slab - 1) / g.ctas_per_slab;
-    const bool act_slab = g.critic && ft == g.FT - 1;        // features l1 .. l1+la-1: one input (the action) per feature
-    const int f0 = ft * SLAB;
-    const int nfeat = act_slab ? d.la : SLAB;                // valid features of this slab
+    const int agent = (int)blockIdx.x / g.ctas_per_agent;
+    const int cta = (int)blockIdx.x - agent * g.ctas_per_agent;
+    const int T = (g.tiles_per_agent - cta + g.ctas_per_agent - 1) / g.ctas_per_agent;
+    const int FT = g.FT;                                     // feature slabs: 2 state slabs (+ the action-branch slab of the critic)
     const float* P = g.params + (int64_t)agent * g.pstride;
 
     if (threadIdx.x == 0) {
@@ -100,35 +97,27 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad3_kernel(const __grid_con
         for (int i = 0; i < 2; ++i) {
             mbar_init(&dz_full[i], 1); mbar_init(&dz_empty[i], 1);
             mbar_init(&r_full[i], 8); mbar_init(&r_empty[i], 1);
-            mbar_init(&x_full[i], 4); mbar_init(&z1_full[i], 1); mbar_init(&z1_empty[i], 8);
+            mbar_init(&x_full[i], 4);
         }
+        mbar_init(z1_full, 1);
         mbar_init(acc_done, 1);
         fence_barrier_init();
     }
     if (warp == 0) tmem_alloc(tmem_slot, 512);
     if (warp >= 2) {
-        const int ct = threadIdx.x - 64;     // 0..255
-        if (!act_slab && ct < SLAB) {        // W1ext row of layer-1 output column f0 + ct
-            const int64_t oW = g.critic ? critic_off(d).Ws : actor_off(d).W1, ob = g.critic ? critic_off(d).bs : actor_off(d).b1;
-            const int n = f0 + ct;
-            bf16 whi[4], wlo[4], bhi, blo;
+        const int ct = threadIdx.x - 64;     // 0..255: W1ext row of layer-1 output column ct
+        const int64_t oW = g.critic ? critic_off(d).Ws : actor_off(d).W1, ob = g.critic ? critic_off(d).bs : actor_off(d).b1;
+        bf16 whi[4], wlo[4], bhi, blo;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) split_bf16(k < d.ns ? P[oW + (int64_t)k * d.l1 + n] : 0.0f, whi[k], wlo[k]);
-            split_bf16(P[ob + n], bhi, blo);
-            const bf16 zero = __float2bfloat16_rn(0.0f);
-            *reinterpret_cast<uint4*>(smem + OFF_B1 + ct * 16) = make_uint4(pack2(whi[0], whi[1]), pack2(whi[2], whi[3]), pack2(bhi, whi[0]), pack2(whi[1], whi[2]));
-            *reinterpret_cast<uint4*>(smem + OFF_B1 + SLAB * 16 + ct * 16) = make_uint4(pack2(whi[3], bhi), pack2(wlo[0], wlo[1]), pack2(wlo[2], wlo[3]), pack2(blo, zero));
-        }
-        if (act_slab && ct < 64) {
+        for (int k = 0; k < 4; ++k) split_bf16(k < d.ns ? P[oW + (int64_t)k * d.l1 + ct] : 0.0f, whi[k], wlo[k]);
+        split_bf16(P[ob + ct], bhi, blo);
+        const bf16 zero = __float2bfloat16_rn(0.0f);
+        *reinterpret_cast<uint4*>(smem + OFF_B1 + ct * 16) = make_uint4(pack2(whi[0], whi[1]), pack2(whi[2], whi[3]), pack2(bhi, whi[0]), pack2(whi[1], whi[2]));
+        *reinterpret_cast<uint4*>(smem + OFF_B1 + L1N * 16 + ct * 16) = make_uint4(pack2(whi[3], bhi), pack2(wlo[0], wlo[1]), pack2(wlo[2], wlo[3]), pack2(blo, zero));
+        if (g.critic && ct < 64) {
             const CriticOff o = critic_off(d);
             wa_tab[ct] = ct < d.la ? P[o.Wa + ct] : 0.0f;
             ba_tab[ct] = ct < d.la ? P[o.ba + ct] : 0.0f;
-        }
-        if (act_slab) {                      // features 64..127 of the action slab do not exist: zero the second half of both r1 buffers once
-            for (int i = ct; i < 2 * HALF_BYTES / 16; i += 256) {
-                const int b = i / (HALF_BYTES / 16), o16 = i - b * (HALF_BYTES / 16);
-                *reinterpret_cast<uint4*>(smem + OFF_R1 + b * 2 * HALF_BYTES + HALF_BYTES + o16 * 16) = make_uint4(0u, 0u, 0u, 0u);
-            }
         }
         fence_proxy_async();
     }
@@ -136,7 +125,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad3_kernel(const __grid_con
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    auto tile_of = [&](int tc) { return cta + tc * g.ctas_per_slab; };
+    auto tile_of = [&](int tc) { return cta + tc * g.ctas_per_agent; };
+    // Work is a sequence of slab steps q = t FT + s (row tile t, feature slab s); r1 buffer q & 1.  State slabs (s < 2) go
+    // through the layer-1 MMA and the single z1 buffer; zi = 2 t + s counts them.
 
     if (warp == 0) {
         // ================================================ MMA issuer ================================================
@@ -146,33 +137,32 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad3_kernel(const __grid_con
             constexpr uint32_t idesc1 = make_idesc_bf16(TILE_M, SLAB, false, false);   // x (K-major) x W1ext slab (K-major)
             constexpr uint32_t idesc2 = make_idesc_bf16(SLAB, L2N, true, true);        // r1 slab (MN-major) x dz2 tile (MN-major)
             const uint64_t dX = make_desc_noswz(smem_u32(smem + OFF_X), TILE_M * 16, 128);
-            const uint64_t dB1 = make_desc_noswz(smem_u32(smem + OFF_B1), SLAB * 16, 128);
+            const uint64_t dB1 = make_desc_noswz(smem_u32(smem + OFF_B1), L1N * 16, 128);
             const uint64_t dR = make_smem_desc(smem_u32(smem + OFF_R1), HALF_BYTES, 1024);
             const uint64_t dDZ = make_smem_desc(smem_u32(smem + OFF_DZ), HALF_BYTES, 1024);
-            auto mma1 = [&](int t) {          // z1 slab of local tile t -> TMEM columns 128 (t & 1)
-                mbar_wait(&x_full[t & 1], ((uint32_t)t >> 1) & 1);
-                mbar_wait(&z1_empty[t & 1], (((uint32_t)t >> 1) & 1) ^ 1);
+            auto mma1 = [&](int t, int sl) {  // z1 of state slab sl of local tile t -> TMEM columns [384, 512); the caller knows they are drained
+                if (sl == 0) mbar_wait(&x_full[t & 1], ((uint32_t)t >> 1) & 1);
                 tc_fence_after();
-                mma_bf16_p(leader, tmem_base + (uint32_t)((t & 1) * SLAB), desc_add(dX, (uint32_t)(t & 1) * X_BYTES), dB1, idesc1, 0);
-                mma_commit_p(leader, &z1_full[t & 1]);
+                mma_bf16_p(leader, tmem_base + 384u, desc_add(dX, (uint32_t)(t & 1) * X_BYTES), desc_add(dB1, (uint32_t)sl * SLAB * 16), idesc1, 0);
+                mma_commit_p(leader, z1_full);
             };
-            auto mma2 = [&](int t) {          // acc += r1 slab^T . dz2 tile   (K = the 128 rows of the tile)
-                mbar_wait(&r_full[t & 1], ((uint32_t)t >> 1) & 1);
-                mbar_wait(&dz_full[t & 1], ((uint32_t)t >> 1) & 1);
-                tc_fence_after();
-                const uint32_t off = (uint32_t)(t & 1) * 2 * HALF_BYTES;
-#pragma unroll
-                for (int ks = 0; ks < 8; ++ks) mma_bf16_p(leader, tmem_base + 256u, desc_add(dR, off + ks * 2048), desc_add(dDZ, off + ks * 2048), idesc2, (t | ks) != 0);
-                mma_commit_p(leader, &r_empty[t & 1]);
-                mma_commit_p(leader, &dz_empty[t & 1]);
-            };
-            if (!act_slab) {
-                mma1(0);
-                if (T > 1) mma1(1);
-            }
+            mma1(0, 0);
             for (int t = 0; t < T; ++t) {
-                mma2(t);
-                if (!act_slab && t + 2 < T) mma1(t + 2);
+                for (int sl = 0; sl < FT; ++sl) {
+                    const uint32_t q = (uint32_t)(t * FT + sl);
+                    mbar_wait(&r_full[q & 1], (q >> 1) & 1);             // converters are done with this step (and with z1, if it used it)
+                    if (sl == 0) mbar_wait(&dz_full[t & 1], ((uint32_t)t >> 1) & 1);
+                    tc_fence_after();
+                    // the (tiny) layer-1 MMA of the next state slab goes first: its converters then overlap this step's product
+                    if (sl == 0) mma1(t, 1);
+                    else if (sl == 1 && t + 1 < T) mma1(t + 1, 0);
+                    const uint32_t off = (q & 1) * 2 * HALF_BYTES, doff = (uint32_t)(t & 1) * 2 * HALF_BYTES;
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks)
+                        mma_bf16_p(leader, tmem_base + (uint32_t)(sl * SLAB), desc_add(dR, off + ks * 2048), desc_add(dDZ, doff + ks * 2048), idesc2, (t | ks) != 0);
+                    mma_commit_p(leader, &r_empty[q & 1]);
+                    if (sl == FT - 1) mma_commit_p(leader, &dz_empty[t & 1]);
+                }
             }
             mma_commit_p(leader, acc_done);
         }
@@ -192,18 +182,25 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad3_kernel(const __grid_con
     } else {
         // ================================================ converters ================================================
         const int cw = warp - 2;             // 0..7
-        const int q = warp & 3, half = cw >> 2;
-        const int row = q * 32 + lane;
-        const uint32_t tlane = (uint32_t)(q * 32) << 16;
+        const int q4 = warp & 3, half = cw >> 2;
+        const int row = q4 * 32 + lane;
+        const uint32_t tlane = (uint32_t)(q4 * 32) << 16;
         auto rowidx = [&](int tc) -> int64_t {
             const int64_t r_in = (int64_t)tile_of(tc) * TILE_M + row;
             return (int64_t)agent * g.R + (r_in < g.R ? r_in : g.R - 1);
         };
-        auto produce_x = [&](int t) {         // [v_hi(5) v_lo(5) v_hi(5) 0],  v = (s0..s3, 1)
+        // Per-row inputs are fetched one tile ahead of their use (xs: state row of the tile whose X buffer is written next,
+        // a_nx: action of the next tile): a load issued right before its use would put a global-memory latency on every tile.
+        float xs[4] = {0.f, 0.f, 0.f, 0.f}, a_nx = 0.0f;
+        auto load_x = [&](int t) {
             const int64_t n = rowidx(t);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) xs[k] = k < d.ns ? __ldg(g.s + n * d.ns + k) : 0.0f;
+        };
+        auto write_x = [&](int t) {           // [v_hi(5) v_lo(5) v_hi(5) 0],  v = (s0..s3, 1)
             bf16 hi[5], lo[5];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) split_bf16(k < d.ns ? __ldg(g.s + n * d.ns + k) : 0.0f, hi[k], lo[k]);
+            for (int k = 0; k < 4; ++k) split_bf16(xs[k], hi[k], lo[k]);
             hi[4] = __float2bfloat16_rn(1.0f);
             lo[4] = __float2bfloat16_rn(0.0f);
             uint8_t* xbase = smem + OFF_X + (t & 1) * X_BYTES;
@@ -214,65 +211,77 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad3_kernel(const __grid_con
             __syncwarp();
             if (lane == 0) mbar_arrive(&x_full[t & 1]);
         };
-        if (!act_slab && half == 0) {
-            produce_x(0);
-            if (T > 1) produce_x(1);
+        if (half == 0 && T > 0) {
+            load_x(0);
+            write_x(0);
+            if (T > 1) { load_x(1); write_x(1); }
+            if (T > 2) load_x(2);
         }
+        if (FT > 2 && T > 0) a_nx = __ldg(g.act + rowidx(0));
         for (int t = 0; t < T; ++t) {
-            const int b = t & 1;
-            // rows past the end of the agent's batch: dz2 is zero-filled by TMA there, so whatever r1 holds contributes nothing
-            uint8_t* rrow = smem + OFF_R1 + b * 2 * HALF_BYTES + half * HALF_BYTES + row * 128;
-            if (!act_slab) {
-                mbar_wait(&z1_full[b], ((uint32_t)t >> 1) & 1);
-                tc_fence_after();
-                mbar_wait(&r_empty[b], (((uint32_t)t >> 1) & 1) ^ 1);
+            for (int sl = 0; sl < FT; ++sl) {
+                const uint32_t q = (uint32_t)(t * FT + sl), rb = q & 1;
+                // rows past the end of the agent's batch: dz2 is zero-filled by TMA there, so whatever r1 holds contributes nothing
+                uint8_t* rrow = smem + OFF_R1 + rb * 2 * HALF_BYTES + half * HALF_BYTES + row * 128;
+                if (sl < 2) {
+                    mbar_wait(z1_full, (uint32_t)(2 * t + sl) & 1);
+                    tc_fence_after();
+                    mbar_wait(&r_empty[rb], ((q >> 1) & 1) ^ 1);
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    float z[32];
-                    tmem_ld32(tmem_base + (uint32_t)(b * SLAB + half * 64 + h * 32) + tlane, z);
+                    for (int h = 0; h < 2; ++h) {
+                        float z[32];
+                        tmem_ld32(tmem_base + 384u + (uint32_t)(half * 64 + h * 32) + tlane, z);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const uint4 pk = make_uint4(pack_relu_bf16x2(z[8 * k], z[8 * k + 1]), pack_relu_bf16x2(z[8 * k + 2], z[8 * k + 3]),
-                                                    pack_relu_bf16x2(z[8 * k + 4], z[8 * k + 5]), pack_relu_bf16x2(z[8 * k + 6], z[8 * k + 7]));
-                        *reinterpret_cast<uint4*>(rrow + (((h * 4 + k) ^ (row & 7)) << 4)) = pk;
+                        for (int k = 0; k < 4; ++k) {
+                            const uint4 pk = make_uint4(pack_relu_bf16x2(z[8 * k], z[8 * k + 1]), pack_relu_bf16x2(z[8 * k + 2], z[8 * k + 3]),
+                                                        pack_relu_bf16x2(z[8 * k + 4], z[8 * k + 5]), pack_relu_bf16x2(z[8 * k + 6], z[8 * k + 7]));
+                            *reinterpret_cast<uint4*>(rrow + (((h * 4 + k) ^ (row & 7)) << 4)) = pk;
+                        }
                     }
-                }
-                tc_fence_before();
-                fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) { mbar_arrive(&z1_empty[b]); mbar_arrive(&r_full[b]); }
-                if (half == 0 && t + 2 < T) produce_x(t + 2);     // X buffer b is free: z1_full(t) implies the layer-1 MMA has read it
-            } else {
-                const float a_val = __ldg(g.act + rowidx(t));
-                mbar_wait(&r_empty[b], (((uint32_t)t >> 1) & 1) ^ 1);      // every warp waits, so that no arrival can lap a phase of r_full
-                if (half == 0) {             // 64 action-branch columns (zero weights beyond la give relu(0) = 0)
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        float r[8];
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) r[j] = fmaf(a_val, wa_tab[8 * k + j], ba_tab[8 * k + j]);
-                        *reinterpret_cast<uint4*>(rrow + ((k ^ (row & 7)) << 4)) =
-                            make_uint4(pack_relu_bf16x2(r[0], r[1]), pack_relu_bf16x2(r[2], r[3]), pack_relu_bf16x2(r[4], r[5]), pack_relu_bf16x2(r[6], r[7]));
-                    }
+                    tc_fence_before();
                     fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&r_full[rb]);
+                    // both layer-1 MMAs of tile t have read X buffer t & 1 once z1_full of its second slab has been seen
+                    if (sl == 1 && half == 0 && t + 2 < T) {
+                        write_x(t + 2);
+                        if (t + 3 < T) load_x(t + 3);
+                    }
+                } else {                     // action-branch slab of the critic: 64 columns on the CUDA cores (zero weights beyond la)
+                    const float a_val = a_nx;
+                    if (t + 1 < T) a_nx = __ldg(g.act + rowidx(t + 1));
+                    mbar_wait(&r_empty[rb], ((q >> 1) & 1) ^ 1);         // every warp waits, so that no arrival can lap a phase of r_full
+                    if (half == 0) {         // features 64..127 of this slab do not exist: that half keeps stale (finite) data, its rows are never flushed
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            float r[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) r[j] = fmaf(a_val, wa_tab[8 * k + j], ba_tab[8 * k + j]);
+                            *reinterpret_cast<uint4*>(rrow + ((k ^ (row & 7)) << 4)) =
+                                make_uint4(pack_relu_bf16x2(r[0], r[1]), pack_relu_bf16x2(r[2], r[3]), pack_relu_bf16x2(r[4], r[5]), pack_relu_bf16x2(r[6], r[7]));
+                        }
+                        fence_proxy_async();
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&r_full[rb]);
                 }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&r_full[b]);
             }
         }
-        // ---- accumulator of this CTA -> global: features f0 + row, all 128 columns (warps of column half `half`)
+        // ---- accumulators of this CTA -> global: slab sl, feature sl*128 + row, this warp's 64 columns
         if (T > 0) {
             mbar_wait(acc_done, 0);
             tc_fence_after();
-            const int f = f0 + row;
-            float* dst = g.grads + (int64_t)agent * g.gstride + g.oW2 + (int64_t)f * L2N + half * 64;
+            for (int sl = 0; sl < FT; ++sl) {
+                const int nfeat = sl < 2 ? SLAB : d.la;
+                float* dst = g.grads + (int64_t)agent * g.gstride + g.oW2 + (int64_t)(sl * SLAB + row) * L2N + half * 64;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                float v[32];
-                tmem_ld32(tmem_base + 256u + (uint32_t)(half * 64 + h * 32) + tlane, v);
-                if (row < nfeat) {
+                for (int h = 0; h < 2; ++h) {
+                    float v[32];
+                    tmem_ld32(tmem_base + (uint32_t)(sl * SLAB + half * 64 + h * 32) + tlane, v);
+                    if (row < nfeat) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) atomicAdd(dst + h * 32 + j, v[j]);
+                        for (int j = 0; j < 32; ++j) atomicAdd(dst + h * 32 + j, v[j]);
+                    }
                 }
             }
             tc_fence_before();
@@ -327,8 +336,8 @@ int run(const avd_net_dims& d, bool critic, int A, int64_t R, const float* param
     g.d = d; g.critic = critic ? 1 : 0; g.A = A; g.FT = critic ? 3 : 2; g.R = R; g.params = params; g.pstride = pstride; g.s = s; g.act = act;
     g.grads = grads; g.gstride = gstride; g.oW2 = oW2;
     g.tiles_per_agent = (int)((R + TILE_M - 1) / TILE_M);
-    g.ctas_per_slab = std::max(1, std::min(g.tiles_per_agent, sm_count() / std::max(1, A * g.FT)));
-    wgrad3_kernel<<<(unsigned)(A * g.FT * g.ctas_per_slab), NUM_THREADS, SMEM_BYTES, st>>>(tm, g);
+    g.ctas_per_agent = std::max(1, std::min(g.tiles_per_agent, sm_count() / std::max(1, A)));
+    wgrad3_kernel<<<(unsigned)(A * g.ctas_per_agent), NUM_THREADS, SMEM_BYTES, st>>>(tm, g);
     AVD_LAUNCH_OK();
     return AVD_OK;
 }

@@ -335,29 +335,30 @@ def test_batched_trainer_interfrl_keeps_replicas_identical(mods):
 # ------------------------------------------------------------------------------------------ bf16 tensor-core mode
 @pytest.mark.parametrize("A,R", [(1, 64), (3, 64), (2, 1000), (1, 4096), (1, 250_000), (3, 100_003)])
 def test_learn_gradients_tensor_core_mode(mods, A, R):
-    """precision=1: the 256x128 / 304x128 contractions run as bf16 tcgen05 GEMMs with fp32 TMEM accumulation.
-    Bar against the fp32 oracle, per gradient tensor: relative L2 error < 6e-2 (critic) / 1e-1 (actor).  bf16 has an
-    8-bit mantissa; the critic gradient is driven by the TD error q - y, a small difference of two quantities that each
-    carry ~0.3 % bf16 noise (measured 3-4 % on single 64-sample minibatches, <1 % at 1000+ rows), and the actor gradient
-    passes through five bf16-rounded operands (dz2', W2c, dz2, W2, h1).  Losses agree to 1e-2.  precision=0 is the
-    parity mode (2e-4).  The two large cases give every persistent CTA 6-14 row tiles (ragged last tile, several agents per
-    launch), so the mbarrier phase arithmetic of the software pipelines wraps many times."""
+    """precision=1: every contraction of the learn step runs on tcgen05 (bf16 operands, fp32 TMEM accumulation; layer 1 with
+    hi/lo-split operands), heads / losses / reductions in fp32.  Bar against the fp32 oracle, per gradient tensor: relative L2
+    error < 6e-2 (max error < 1.2e-1) on single 64-row minibatches, where the critic gradient is driven by the TD error q - y, a
+    small difference of two bf16-noisy values (measured 0.05 % - 4.5 %), and < 2e-2 (4e-2) from 1000 rows up (measured < 0.7 %,
+    profiles/r01_tensor_core_accuracy.txt).  Losses agree to 1e-3.  precision=0 is the parity mode (2e-4).
+    The two large cases give every persistent CTA 6-14 row tiles (ragged last tile, several agents per launch), so the mbarrier
+    phase arithmetic of the software pipelines wraps many times."""
     conf, pop, nets, batches, (s, a, r, s2) = build_population(mods, A, R, list(range(50, 50 + A)))
     pop.precision = 1
     pop.learn(s, a, r, s2, apply_updates=False)
     torch.cuda.synchronize()
     bad = []
+    l2_tol, mx_tol = (6e-2, 1.2e-1) if R < 1000 else (2e-2, 4e-2)
     for i in range(A):
         ocg, oag, info = D.learn(nets[i][0], nets[i][1], nets[i][2], nets[i][3], batches[i], gamma=conf.gamma, high=conf.action_high)
-        for bank, ref, l2_tol, mx_tol in ((pop.critic, ocg, 6e-2, 1.5e-1), (pop.actor, oag, 1e-1, 2e-1)):
+        for bank, ref in ((pop.critic, ocg), (pop.actor, oag)):
             for name in bank.trainable_names:
                 got = bank.view(name, i, bank.grad).cpu().numpy()
                 e2, em = _l2(got, ref[name].reshape(got.shape)), _nrm(got, ref[name].reshape(got.shape))
                 if not (e2 < l2_tol and em < mx_tol):
                     bad.append((i, bank.kind, name, round(e2, 4), round(em, 4)))
         loss = pop.loss[i].cpu().numpy()
-        assert abs(loss[0] - info["critic_loss"]) < 1e-2 * max(1, abs(info["critic_loss"]))
-        assert abs(loss[1] - info["actor_loss"]) < 1e-2 * max(1, abs(info["actor_loss"]))
+        assert abs(loss[0] - info["critic_loss"]) < 1e-3 * max(1, abs(info["critic_loss"]))
+        assert abs(loss[1] - info["actor_loss"]) < 1e-3 * max(1, abs(info["actor_loss"]))
     assert not bad, f"(agent, net, tensor, rel-L2, rel-max) out of tolerance: {bad}"
 
 

@@ -4,7 +4,8 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from oracle import ddpg_np as D
-import tests.test_gpu_ddpg as T
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+import test_gpu_ddpg as T
 from avddpg_b200 import _lib, trainer
 from avddpg_b200.config import Config
 
