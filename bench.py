@@ -34,6 +34,20 @@ WORKLOAD = "C2: 4096 platoons x 4 followers per GPU, decentralized Model B euler
 P_C2, M_C2, RING_CAP, BATCH = 4096, 4, 100_000, 64
 
 
+def _ncu_traffic():
+    """DRAM bytes per launch from the committed `ncu --set full` captures (profiles/r01_traffic.json, written by
+    tools/ncu_traffic.py): {"env": bytes per env_step_kernel launch at the roofline population,
+    "learn": bytes summed over the launches of one learn step at C2}.  None when the file is missing."""
+    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if not os.path.exists(path):
+        return {"env": None, "learn": None}
+    d = json.load(open(path))
+    env = d.get("r01_env_plain.ncu-rep") or []
+    learn = d.get("r01_learn_step.ncu-rep") or []
+    tot = lambda rows: float(sum(r["dram_read_bytes"] + r["dram_write_bytes"] for r in rows)) if rows else None
+    return {"env": tot(env[:1]), "learn": tot(learn)}
+
+
 def _peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -262,14 +276,20 @@ def run_native(args):
         learn_flops = 2.0 * LEARN_MACS_PER_SAMPLE * rows
         learn_tf = learn_flops / (ms_learn * 1e-3) / 1e12
         rl = time_env_roofline(args.roofline_platoons, M)
+        traffic = _ncu_traffic()
         achieved = rl["alg_bytes"] / (rl["avg_ms"] * 1e-3) / 1e9
         roofline_env = {"bound": "hbm", "kernel": "env_step_kernel<4>", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                        "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                        "frac": achieved / hbm_peak, "traffic": traffic["env"] if args.roofline_platoons == 4 * 1024 * 1024 else None,
+                        "traffic_unit": "DRAM bytes per launch (ncu, profiles/r01_env_step_plain_ncu.txt)", "alg_bytes_per_launch": rl["alg_bytes"],
+                        "peak_source": peak_src,
                         "population": f"{args.roofline_platoons} platoons x {M} (state working set {rl['working_set_mb']:.0f} MB > 126 MB L2)",
                         "alg_bytes_per_vehicle_step": ENV_BYTES_PER_VEHICLE_STEP, "avg_launch_ms": rl["avg_ms"],
                         "vehicle_steps_per_s": args.roofline_platoons * M / (rl["avg_ms"] * 1e-3)}
-        roofline_learn = {"bound": "tensor", "kernel": "learn step GEMMs (" + ("bf16 tcgen05" if args.precision else "fp32 SIMT parity mode") + ")",
-                          "achieved": learn_tf, "peak": tf_peak / 1e0, "unit": "TFLOP/s", "frac": learn_tf / tf_peak, "traffic": None,
+        roofline_learn = {"bound": "tensor", "kernel": ("learn step: 6 fused pass launches (fused3_kernel) + 2 wgrad3 + 2 dgrad3, bf16 tcgen05"
+                                                       if args.precision else "learn step, fp32 SIMT parity mode"),
+                          "achieved": learn_tf, "peak": tf_peak / 1e0, "unit": "TFLOP/s", "frac": learn_tf / tf_peak,
+                          "traffic": traffic["learn"] if args.precision else None,
+                          "traffic_unit": "DRAM bytes per learn step, summed over its launches (ncu, profiles/r01_learn_kernels_ncu.txt)",
                           "peak_source": peak_src + " bf16 sustained", "alg_flops_per_step": learn_flops,
                           "alg_macs_per_sample": LEARN_MACS_PER_SAMPLE, "rows_per_step": rows, "learn_ms": ms_learn}
         dominant = roofline_learn if ms_learn > ms_env else roofline_env
