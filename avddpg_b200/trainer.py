@@ -193,6 +193,38 @@ class BatchedTrainer:
                     self.fed.aggregate_weights()
         self.step_in_run += 1
 
+    def episodic_rewards(self):
+        """Cumulative reward of the current episode per agent, [G][M] nested lists of np.float32 (the reference's
+        all_episodic_reward_counters, trainer.py:249, 321); with E environments per group: the mean over the group's platoons."""
+        r = self.env.ep_reward.reshape(self.M, self.G, self.E).mean(dim=2).t().contiguous().cpu().numpy().astype(np.float32)
+        return [[r[g, m] for m in range(self.M)] for g in range(self.G)]
+
+    def run(self, episodes: int, reward_log=None, *, global_break: bool = True, learn: bool = True):
+        """The episode loop of Trainer.run (workers/trainer.py:232-273) for the whole population: every episode resets ALL
+        platoons (246-249), runs up to conf.steps_per_episode steps (251), ends early for everybody when ANY platoon reports a
+        terminal state (268-269; `global_break=False` lets the other platoons finish) and appends the episodic rewards to
+        `reward_log` (an avddpg_b200.results.RewardLog; trainer.py:273, 510-517).  In-kernel auto-reset is switched off for the
+        duration, so episodes line up across platoons exactly like the reference's; one D2H read of the done flags per step is
+        the price (the free-running `step()` loop used by the benchmark never synchronises).  Returns the number of env steps."""
+        env, conf = self.env, self.conf
+        saved = env.auto_reset
+        env.auto_reset = False
+        steps = 0
+        try:
+            for _ in range(int(episodes)):
+                env.reset()
+                for _ in range(int(conf.steps_per_episode)):
+                    self.step(learn=learn)
+                    steps += 1
+                    if global_break and bool((env.done & 1).any().item()):
+                        break
+                if reward_log is not None:
+                    reward_log.update_reward_list(self.episodic_rewards())
+                self.episode += 1
+        finally:
+            env.auto_reset = saved
+        return steps
+
     def capture(self, warmup: int = 3):
         """Capture one full step (learn included) into a CUDA graph; afterwards `replay()` costs one launch."""
         assert self.buffer_counter > self.conf.batch_size, "fill the buffers past batch_size before capturing"

@@ -413,3 +413,32 @@ def test_evaluator_rollout_vs_reference_golden(mods, golden):
     # device-drawn leader inputs: runs, finite, same initial state
     pl2 = evaluator.run(conf, pop, num_platoons=64, manual_timestep_override=20, precision=1)
     assert np.isfinite(pl2)
+
+
+def test_batched_trainer_reference_episode_loop_and_csvs(mods, tmp_path):
+    """Trainer.run-shaped episode loop (trainer.py:232-273) on the batched trainer + the reference's CSV / conf.json formats."""
+    from avddpg_b200 import results
+    conf = mods["Config"](pl_size=2, episode_sim_time=3, can_terminate=False, reward_averaging_window=2)
+    assert conf.steps_per_episode == 30
+    tr = mods["trainer"].BatchedTrainer(conf, num_groups=3, envs_per_group=2, ring_capacity=128, precision=0)
+    log = results.RewardLog(conf, num_platoons=3, num_models=2)
+    steps = tr.run(4, reward_log=log, learn=False)
+    assert steps == 4 * 30 and tr.env.auto_reset is True          # restored afterwards
+    ep = np.array(log.all_ep_reward_lists, dtype=np.float64)      # [3][2][4]
+    assert ep.shape == (3, 2, 4) and np.isfinite(ep).all() and (ep < 0).all()
+    # the logged value is the sum over the episode of the per-step rewards (trainer.py:321), averaged over the group's platoons
+    tr.env.auto_reset = False
+    tr.env.reset()
+    acc = torch.zeros(2, 6, device="cuda")
+    for _ in range(30):
+        tr.step(learn=False)
+        acc += tr.env._reward          # raw [M, P] layout
+    tr.env.auto_reset = True
+    want = acc.reshape(2, 3, 2).mean(dim=2).t().cpu().numpy()
+    got = np.array(tr.episodic_rewards(), dtype=np.float64)
+    np.testing.assert_allclose(got, want, rtol=1e-5)
+    paths = log.generate_csvs(str(tmp_path))
+    rows = open(paths[1]).read().strip().splitlines()
+    assert rows[0] == ",Vehicle 1,Vehicle 2,seed,platoon" and len(rows) == 1 + 3 * 4
+    results.config_writer(str(tmp_path / "conf.json"), conf)
+    assert results.config_loader(str(tmp_path / "conf.json")).pl_size == 2
