@@ -11,8 +11,8 @@
 // Math: dR = dz2 W2'^T with W2' = diag(sc1) W2 (BatchNorm folded, pack_fold_kernel), dz1 = dR [z1 > 0]
 // (workers/trainer.py:498, 506 through agent/model.py:19-33, 62-77).
 //
-// Warps: 0 MMA issuer, 1 TMA producer, 2..17 epilogue (TMEM lane quadrant = warp % 4; the four groups of four warps
-// take the 64-column chunks round-robin).  TMEM: 7-slot ring of 64-column dR chunks + 3 x 16 columns of G1 + 16 columns of
+// Warps: 0 MMA issuer, 1 TMA producer, 2..17 epilogue (TMEM lane quadrant = warp % 4; four quarters of four warps, two
+// quarters per chunk pair).  TMEM: 3-slot ring of 128-column dR chunk pairs + 3 x 16 columns of G1 + 16 columns of
 // dz2^T xext, whose column 5 (xext's constant one) is the layer-2 bias gradient db2.
 #include <cudaTypedefs.h>
 
@@ -27,7 +27,7 @@ namespace dgrad3 {
 using namespace umma;
 typedef __nv_bfloat16 bf16;
 
-constexpr int TILE_M = 128, L2N = 128, KB = 64, MAX_NC = 5, NRING = 7;
+constexpr int TILE_M = 128, L2N = 128, KB = 64, MAX_NC = 5, NRING = 3;
 constexpr int NUM_THREADS = 32 * 18;
 constexpr int WCHUNK_BYTES = 64 * 128;                       // one 64-feature x 64-k block of W2': 8 KB
 constexpr int OFF_W = 0;                                     // [2 k-blocks][5 chunks][64 rows][128 B] = 80 KB
@@ -62,8 +62,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dgrad3_kernel(const __grid_con
                                                                 const __grid_constant__ CUtensorMap tmXT, Args g) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint64_t* d_full = reinterpret_cast<uint64_t*>(smem + OFF_BAR);   // [7]
-    uint64_t* d_empty = d_full + NRING;                               // [7]
+    uint64_t* d_full = reinterpret_cast<uint64_t*>(smem + OFF_BAR);   // [3]
+    uint64_t* d_empty = d_full + NRING;                               // [3]
     uint64_t* st_full = d_empty + NRING;                              // [2]
     uint64_t* st_empty = st_full + 2;                                 // [2]
     uint64_t* a_full = st_empty + 2;                                  // [2]
@@ -78,13 +78,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dgrad3_kernel(const __grid_con
     const int agent = (int)blockIdx.x / g.ctas_per_agent;
     const int cta = (int)blockIdx.x - agent * g.ctas_per_agent;
     const int T = (g.tiles_per_agent - cta + g.ctas_per_agent - 1) / g.ctas_per_agent;
-    const int NC = g.NC, NP = (NC + 1) >> 1;
+    const int NC = g.NC, NP = (NC + 1) >> 1;           // 64-feature chunks, chunk pairs (the last pair of the critic has one chunk)
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmW); tma_prefetch_desc(&tmDZ); tma_prefetch_desc(&tmXT);
-        for (int i = 0; i < NRING; ++i) { mbar_init(&d_full[i], 1); mbar_init(&d_empty[i], 4); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&st_full[i], 8); mbar_init(&st_empty[i], 1); mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-        for (int i = 0; i < NXT; ++i) { mbar_init(&xt_full[i], 1); mbar_init(&xt_empty[i], 1); }
+        for (int i = 0; i < NRING; ++i) { mbar_init(&d_full[i], 1); mbar_init(&d_empty[i], 8); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&st_full[i], 8); mbar_init(&st_empty[i], 1); mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 8); }
+        for (int i = 0; i < NXT; ++i) { mbar_init(&xt_full[i], 1); mbar_init(&xt_empty[i], 8); }
         mbar_init(w_full, 1);
         mbar_init(g1_done, 1);
         fence_barrier_init();
@@ -95,23 +95,29 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dgrad3_kernel(const __grid_con
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     auto tile_of = [&](int tc) { return cta + tc * g.ctas_per_agent; };
+    // Chunk pair p of local tile t has the running index pk = t NP + p: TMEM ring slot pk % 3 (128 columns), staging buffer
+    // pk & 1, epilogue quarters 2 (pk & 1) and 2 (pk & 1) + 1 (one 64-column chunk each).
 
     if (warp == 0) {
         // ================================================ MMA issuer ================================================
-        // warp-uniform control flow; the tcgen05 instructions are predicated on one elected lane (see avd_umma.cuh)
+        // Warp-uniform control flow, tcgen05 instructions predicated on one elected lane (see avd_umma.cuh).  A tcgen05.mma
+        // issues at the pace of the tensor pipe and every tcgen05.commit costs this thread ~140 cycles, so the work is cut
+        // into few, wide MMAs (chunk pairs, N = 128) and the buffers that only the issuer's own program order protects
+        // (dz2 tile, x_ext tile) are handed back by the epilogue warps instead of through extra commits.
         if (T > 0) {
             const uint32_t leader = elect_one();
-            constexpr uint32_t idesc_d = make_idesc_bf16(TILE_M, 64, false, false);    // dz2 (K-major) x W2' chunk (K-major)
+            constexpr uint32_t idesc_2 = make_idesc_bf16(TILE_M, 128, false, false);   // dz2 (K-major) x W2' chunk pair (K-major)
+            constexpr uint32_t idesc_1 = make_idesc_bf16(TILE_M, 64, false, false);    // ... x single chunk
             constexpr uint32_t idesc_g = make_idesc_bf16(TILE_M, 16, true, false);     // dz1 / dz2 (MN-major) x xext^T (K-major)
             const uint64_t dA = make_smem_desc(smem_u32(smem + OFF_A), 16, 1024);                 // dz2 tile as K-major A
             const uint64_t dAt = make_smem_desc(smem_u32(smem + OFF_A), TILE_M * 128, 1024);      // dz2 tile as MN-major A (two 64-column halves)
             const uint64_t dW = make_smem_desc(smem_u32(smem + OFF_W), 16, 1024);
             const uint64_t dX = make_smem_desc(smem_u32(smem + OFF_XT), 16, 1024);
             const uint64_t dS = make_smem_desc(smem_u32(smem + OFF_ST), TILE_M * 128, 1024);      // staged dz1 chunk pair as MN-major A
-            // chunk c of local tile t: dR chunk = dz2 tile . W2'[64 c .. 64 c + 63]^T  -> ring slot (t NC + c) % 7
-            auto mma_chunk = [&](int t, int c) {
+            // dR of chunk pair p of local tile t = dz2 tile . W2'[128 p .. 128 p + 127]^T  -> ring slot pk % 3
+            auto mma_pair = [&](int t, int p) {
                 const uint32_t a_off = (uint32_t)(t & 1) * A_BYTES;
-                if (c == 0) {
+                if (p == 0) {
                     mbar_wait(&a_full[t & 1], ((uint32_t)t >> 1) & 1);
                     mbar_wait(&xt_full[t % NXT], ((uint32_t)t / NXT) & 1);
                     tc_fence_after();
@@ -119,20 +125,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dgrad3_kernel(const __grid_con
                     const uint32_t x_off = (uint32_t)(t % NXT) * XT_BYTES;
 #pragma unroll
                     for (int ks = 0; ks < 8; ++ks)
-                        mma_bf16_p(leader, tmem_base + 496u, desc_add(dAt, a_off + ks * 2048), desc_add(dX, x_off + (ks >> 2) * (16 * 128) + (ks & 3) * 32),
+                        mma_bf16_p(leader, tmem_base + 432u, desc_add(dAt, a_off + ks * 2048), desc_add(dX, x_off + (ks >> 2) * (16 * 128) + (ks & 3) * 32),
                                    idesc_g, (t | ks) != 0);
                 }
-                const uint32_t k = (uint32_t)(t * NC + c), slot = k % NRING;
-                mbar_wait(&d_empty[slot], ((k / NRING) & 1) ^ 1);
+                const uint32_t pk = (uint32_t)(t * NP + p), rs = pk % NRING;
+                const bool both = 2 * p + 1 < NC;
+                mbar_wait(&d_empty[rs], ((pk / NRING) & 1) ^ 1);
                 tc_fence_after();
 #pragma unroll
                 for (int ks = 0; ks < 8; ++ks)
-                    mma_bf16_p(leader, tmem_base + slot * 64, desc_add(dA, a_off + (ks >> 2) * (TILE_M * 128) + (ks & 3) * 32),
-                               desc_add(dW, (uint32_t)((ks >> 2) * MAX_NC + c) * WCHUNK_BYTES + (ks & 3) * 32), idesc_d, ks != 0);
-                mma_commit_p(leader, &d_full[slot]);
-                if (c == NC - 1) mma_commit_p(leader, &a_empty[t & 1]);       // the dz2 tile can be reloaded two tiles ahead
+                    mma_bf16_p(leader, tmem_base + rs * 128, desc_add(dA, a_off + (ks >> 2) * (TILE_M * 128) + (ks & 3) * 32),
+                               desc_add(dW, (uint32_t)((ks >> 2) * MAX_NC + 2 * p) * WCHUNK_BYTES + (ks & 3) * 32), both ? idesc_2 : idesc_1, ks != 0);
+                mma_commit_p(leader, &d_full[rs]);
             };
-            // chunk pair p of local tile t: G1[128 p ..] += dz1 pair^T . xext tile
+            // G1[128 p ..] += (staged dz1 chunk pair)^T . xext tile
             auto g1_pair = [&](int t, int p) {
                 const uint32_t x_off = (uint32_t)(t % NXT) * XT_BYTES;
                 const uint32_t pk = (uint32_t)(t * NP + p), sb = pk & 1;
@@ -140,21 +146,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dgrad3_kernel(const __grid_con
                 tc_fence_after();
 #pragma unroll
                 for (int ks = 0; ks < 8; ++ks)
-                    mma_bf16_p(leader, tmem_base + 448u + (uint32_t)(p * 16), desc_add(dS, sb * (2 * TILE_M * 128) + ks * 2048),
+                    mma_bf16_p(leader, tmem_base + 384u + (uint32_t)(p * 16), desc_add(dS, sb * (2 * TILE_M * 128) + ks * 2048),
                                desc_add(dX, x_off + (ks >> 2) * (16 * 128) + (ks & 3) * 32), idesc_g, (t | ks) != 0);
                 mma_commit_p(leader, &st_empty[sb]);
-                if (p == NP - 1) mma_commit_p(leader, &xt_empty[t % NXT]);
             };
             mbar_wait(w_full, 0);
-            for (int c = 0; c < NC; ++c) mma_chunk(0, c);
-            // steady state: the chunk MMAs of tile t + 1 are interleaved with the G1 MMAs of tile t, pair by pair, so that a
-            // staging buffer is handed back as early as possible (every wait only depends on work issued earlier)
+            for (int p = 0; p < NP; ++p) mma_pair(0, p);
+            // steady state: the pair MMAs of tile t + 1 are interleaved with the G1 MMAs of tile t, so that a staging buffer is
+            // handed back as early as possible (every wait only depends on work issued earlier)
             for (int t = 0; t < T; ++t) {
                 for (int p = 0; p < NP; ++p) {
-                    if (t + 1 < T) {
-                        mma_chunk(t + 1, 2 * p);
-                        if (2 * p + 1 < NC) mma_chunk(t + 1, 2 * p + 1);
-                    }
+                    if (t + 1 < T) mma_pair(t + 1, p);
                     g1_pair(t, p);
                 }
             }
@@ -185,54 +187,62 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dgrad3_kernel(const __grid_con
     } else {
         // ================================================== epilogue ==================================================
         const int q = warp & 3, grp = (warp - 2) >> 2;
+        const int h = grp & 1;               // which 64-column chunk of a pair this quarter takes
         const int row = q * 32 + lane;
         const uint32_t tlane = (uint32_t)(q * 32) << 16;
-        // The sign masks of a chunk are fetched while the PREVIOUS chunk of this group is processed (chunks k, k + 4, ...):
+        // The sign masks of a chunk are fetched while the PREVIOUS pair of this quarter is processed (pairs pk, pk + 2, ...):
         // a load issued right before its use would put a full global-memory latency on every chunk of the pipeline.
-        auto load_mask = [&](uint32_t k) -> uint2 {
-            const int t = (int)(k / (uint32_t)NC), c = (int)(k - (uint32_t)t * NC);
-            if (t >= T) return make_uint2(0u, 0u);
+        auto load_mask = [&](uint32_t pk) -> uint2 {
+            const int t = (int)(pk / (uint32_t)NP), c = 2 * (int)(pk - (uint32_t)t * NP) + h;
+            if (t >= T || c >= NC) return make_uint2(0u, 0u);
             const int64_t r_in = (int64_t)tile_of(t) * TILE_M + row;
             const int64_t nrow = (int64_t)agent * g.R + (r_in < g.R ? r_in : g.R - 1);
             return __ldg(reinterpret_cast<const uint2*>(g.mask + nrow * g.mask_words + 2 * c));
         };
-        uint2 neg_next = load_mask((uint32_t)grp);
+        uint2 neg_next = load_mask((uint32_t)(grp >> 1));
         for (int t = 0; t < T; ++t) {
-            for (int c = 0; c < NC; ++c) {
-                const uint32_t k = (uint32_t)(t * NC + c);
-                if ((int)(k & 3) != grp) continue;
-                const uint32_t slot = k % NRING;
+            for (int p = 0; p < NP; ++p) {
+                const uint32_t pk = (uint32_t)(t * NP + p);
+                if ((int)(pk & 1) != (grp >> 1)) continue;
+                const uint32_t rs = pk % NRING, sb = pk & 1;
+                const bool work = 2 * p + h < NC;        // the partner quarter of a lone last chunk only keeps the barrier counts
                 const uint2 neg = neg_next;
-                neg_next = load_mask(k + 4);
-                const uint32_t pk = (uint32_t)(t * NP + (c >> 1)), sb = pk & 1;
-                mbar_wait(&d_full[slot], (k / NRING) & 1);
+                neg_next = load_mask(pk + 2);
+                mbar_wait(&d_full[rs], (pk / NRING) & 1);
                 tc_fence_after();
+                if (p == NP - 1 && lane == 0) {
+                    // every MMA issued before this tile's last pair has completed: the dz2 tile of tile t (read by its pair and db2
+                    // MMAs) and the x_ext tile of tile t - 2 (read by G1 / db2 MMAs issued two iterations ago) are free again
+                    mbar_arrive(&a_empty[t & 1]);
+                    if (t >= 2) mbar_arrive(&xt_empty[(t - 2) % NXT]);
+                }
                 uint32_t pkd[32];            // the masked chunk as bf16 pairs: the TMEM slot is released before the staging buffer is needed
+                if (work) {
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    float v[32];
-                    tmem_ld32(tmem_base + slot * 64 + (uint32_t)(h * 32) + tlane, v);
-                    const uint32_t m = h ? neg.y : neg.x;
+                    for (int hh = 0; hh < 2; ++hh) {
+                        float v[32];
+                        tmem_ld32(tmem_base + rs * 128 + (uint32_t)(h * 64 + hh * 32) + tlane, v);
+                        const uint32_t m = hh ? neg.y : neg.x;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (m & (0x80000000u >> j)) v[j] = 0.0f;
+                        for (int j = 0; j < 32; ++j)
+                            if (m & (0x80000000u >> j)) v[j] = 0.0f;
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) pkd[h * 16 + j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+                        for (int j = 0; j < 16; ++j) pkd[hh * 16 + j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+                    }
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&d_empty[slot]);
+                if (lane == 0) mbar_arrive(&d_empty[rs]);
                 mbar_wait(&st_empty[sb], ((pk >> 1) & 1) ^ 1);
-                uint8_t* srow = smem + OFF_ST + sb * (2 * TILE_M * 128) + (c & 1) * (TILE_M * 128) + row * 128;
+                if (work) {
+                    uint8_t* srow = smem + OFF_ST + sb * (2 * TILE_M * 128) + h * (TILE_M * 128) + row * 128;
 #pragma unroll
-                for (int kk = 0; kk < 8; ++kk)
-                    *reinterpret_cast<uint4*>(srow + ((kk ^ (row & 7)) << 4)) = make_uint4(pkd[4 * kk], pkd[4 * kk + 1], pkd[4 * kk + 2], pkd[4 * kk + 3]);
-                fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) {
-                    mbar_arrive(&st_full[sb]);
-                    if ((NC & 1) && c == NC - 1) mbar_arrive(&st_full[sb]);     // a lone last chunk stands in for its missing partner
+                    for (int kk = 0; kk < 8; ++kk)
+                        *reinterpret_cast<uint4*>(srow + ((kk ^ (row & 7)) << 4)) = make_uint4(pkd[4 * kk], pkd[4 * kk + 1], pkd[4 * kk + 2], pkd[4 * kk + 3]);
+                    fence_proxy_async();
                 }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&st_full[sb]);
             }
         }
         // ---- G1 accumulators of this CTA -> global (features p*128 + row, 16 columns)
@@ -241,7 +251,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dgrad3_kernel(const __grid_con
             tc_fence_after();
             for (int p = 0; p < NP; ++p) {
                 float v[16];
-                tmem_ld16(tmem_base + 448u + (uint32_t)(p * 16) + tlane, v);
+                tmem_ld16(tmem_base + 384u + (uint32_t)(p * 16) + tlane, v);
                 const int f = p * 128 + row;
                 if (f < g.F) {
                     float* dst = g.G1 + ((int64_t)agent * g.Fp + f) * 16;
@@ -255,7 +265,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dgrad3_kernel(const __grid_con
             mbar_wait(g1_done, 0);
             tc_fence_after();
             float v[16];
-            tmem_ld16(tmem_base + 496u + tlane, v);
+            tmem_ld16(tmem_base + 432u + tlane, v);
             atomicAdd(g.db2 + (int64_t)agent * g.db2_stride + row, v[5]);
             tc_fence_before();
         }

@@ -24,16 +24,20 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_arrive_cnt(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
+// try_wait with a suspend-time hint: the hardware parks the thread until the phase completes (or the hint expires) instead
+// of returning after a short system-dependent interval.  A waiting warp then costs no issue slots -- without the hint the
+// consumer warps' polling loops (SYNCS / BRA / YIELD, ~30 % of all executed instructions) competed with the single MMA-issuing
+// warp for its scheduler, and that warp's serial instruction stream is the critical path of every persistent kernel here.
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t done;
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
         "selp.u32 %0, 1, 0, p;\n"
         "}\n"
         : "=r"(done)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
         : "memory");
     return done != 0;
 }
@@ -109,6 +113,27 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// 64 consecutive fp32 columns: both 32-column loads are in flight before the single wait
+__device__ __forceinline__ void tmem_ld64(uint32_t taddr, float* v) {
+    uint32_t r[64];
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(r[32 * h + 0]), "=r"(r[32 * h + 1]), "=r"(r[32 * h + 2]), "=r"(r[32 * h + 3]), "=r"(r[32 * h + 4]), "=r"(r[32 * h + 5]),
+              "=r"(r[32 * h + 6]), "=r"(r[32 * h + 7]), "=r"(r[32 * h + 8]), "=r"(r[32 * h + 9]), "=r"(r[32 * h + 10]), "=r"(r[32 * h + 11]),
+              "=r"(r[32 * h + 12]), "=r"(r[32 * h + 13]), "=r"(r[32 * h + 14]), "=r"(r[32 * h + 15]), "=r"(r[32 * h + 16]), "=r"(r[32 * h + 17]),
+              "=r"(r[32 * h + 18]), "=r"(r[32 * h + 19]), "=r"(r[32 * h + 20]), "=r"(r[32 * h + 21]), "=r"(r[32 * h + 22]), "=r"(r[32 * h + 23]),
+              "=r"(r[32 * h + 24]), "=r"(r[32 * h + 25]), "=r"(r[32 * h + 26]), "=r"(r[32 * h + 27]), "=r"(r[32 * h + 28]), "=r"(r[32 * h + 29]),
+              "=r"(r[32 * h + 30]), "=r"(r[32 * h + 31])
+            : "r"(taddr + 32u * h));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(r[i]);
 }
 
 // 16 consecutive fp32 columns of this thread's TMEM lane
@@ -257,6 +282,18 @@ __device__ __forceinline__ void tma_store_3d_p(uint32_t leader, const CUtensorMa
         "@q cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];\n"
         "}\n" ::"l"(reinterpret_cast<uint64_t>(map)),
         "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(leader)
+        : "memory");
+}
+// L2 prefetch of a tile (no shared-memory destination): issued a few tiles ahead, it turns the HBM latency of the later
+// cp.async.bulk.tensor load into an L2 hit when shared memory is too small for a deeper ring
+__device__ __forceinline__ void tma_prefetch_3d_p(uint32_t leader, const CUtensorMap* map, int c0, int c1, int c2) {
+    asm volatile(
+        "{\n"
+        ".reg .pred q;\n"
+        "setp.ne.b32 q, %4, 0;\n"
+        "@q cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];\n"
+        "}\n" ::"l"(reinterpret_cast<uint64_t>(map)),
+        "r"(c0), "r"(c1), "r"(c2), "r"(leader)
         : "memory");
 }
 // SWIZZLE_128B descriptor with the 16-byte-unit address added to a precomputed base (address field: bits [0,14))

@@ -170,8 +170,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad3_kernel(const __grid_con
         // ================================================ TMA producer ================================================
         {
             const uint32_t leader = elect_one();
+            constexpr int PF = 3;            // dz2 tiles are pulled into L2 this many tiles ahead of their shared-memory load
+            for (int t = 2; t < 2 + PF && t < T; ++t) {
+                tma_prefetch_3d_p(leader, &tmDZ, 0, tile_of(t) * TILE_M, agent);
+                tma_prefetch_3d_p(leader, &tmDZ, KB, tile_of(t) * TILE_M, agent);
+            }
             for (int t = 0; t < T; ++t) {
                 const int b = t & 1;
+                if (t >= 2 && t + PF < T) {
+                    tma_prefetch_3d_p(leader, &tmDZ, 0, tile_of(t + PF) * TILE_M, agent);
+                    tma_prefetch_3d_p(leader, &tmDZ, KB, tile_of(t + PF) * TILE_M, agent);
+                }
                 mbar_wait(&dz_empty[b], (((uint32_t)t >> 1) & 1) ^ 1);
                 uint8_t* dst = smem + OFF_DZ + b * 2 * HALF_BYTES;
                 mbar_expect_tx_p(leader, &dz_full[b], 2 * HALF_BYTES);
