@@ -12,7 +12,7 @@
 // The action-branch slab of the critic (one input per feature, model.py:69-70) is converted on the CUDA cores.
 // Reference: workers/trainer.py:498, 506 (tape.gradient) through agent/model.py:19-33, 62-77.
 //
-// Warps: 0 MMA issuer, 1 TMA producer, 2..9 converters (TMEM lane quadrant = warp % 4, 64 columns each).
+// Warps: 0 MMA issuer, 1 TMA producer, 2..17 converters (TMEM lane quadrant = warp % 4, 32 columns each).
 // TMEM: three slab accumulators (3 x 128 columns) + the z1 slab (128 columns).
 #include <cudaTypedefs.h>
 
@@ -29,7 +29,8 @@ using namespace umma;
 typedef __nv_bfloat16 bf16;
 
 constexpr int TILE_M = 128, L2N = 128, KB = 64, SLAB = 128;
-constexpr int NUM_THREADS = 32 * 10;
+constexpr int NCONV = 16;                                   // converter warps: 4 per TMEM lane quadrant, 32 columns each
+constexpr int NUM_THREADS = 32 * (2 + NCONV);
 constexpr int HALF_BYTES = TILE_M * 128;                     // [128 rows][64 bf16]: 16 KB
 constexpr int OFF_DZ = 0;                                    // 2 x dz2 tile (2 halves of 64 columns)
 constexpr int OFF_R1 = OFF_DZ + 2 * 2 * HALF_BYTES;          // 2 x r1 slab (2 halves of 64 features)
@@ -96,7 +97,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad3_kernel(const __grid_con
         tma_prefetch_desc(&tmDZ);
         for (int i = 0; i < 2; ++i) {
             mbar_init(&dz_full[i], 1); mbar_init(&dz_empty[i], 1);
-            mbar_init(&r_full[i], 8); mbar_init(&r_empty[i], 1);
+            mbar_init(&r_full[i], NCONV); mbar_init(&r_empty[i], 1);
             mbar_init(&x_full[i], 4);
         }
         mbar_init(z1_full, 1);
@@ -105,15 +106,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad3_kernel(const __grid_con
     }
     if (warp == 0) tmem_alloc(tmem_slot, 512);
     if (warp >= 2) {
-        const int ct = threadIdx.x - 64;     // 0..255: W1ext row of layer-1 output column ct
-        const int64_t oW = g.critic ? critic_off(d).Ws : actor_off(d).W1, ob = g.critic ? critic_off(d).bs : actor_off(d).b1;
-        bf16 whi[4], wlo[4], bhi, blo;
+        const int ct = threadIdx.x - 64;     // 0..511; the first 256 build the W1ext row of layer-1 output column ct
+        if (ct < L1N) {
+            const int64_t oW = g.critic ? critic_off(d).Ws : actor_off(d).W1, ob = g.critic ? critic_off(d).bs : actor_off(d).b1;
+            bf16 whi[4], wlo[4], bhi, blo;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) split_bf16(k < d.ns ? P[oW + (int64_t)k * d.l1 + ct] : 0.0f, whi[k], wlo[k]);
-        split_bf16(P[ob + ct], bhi, blo);
-        const bf16 zero = __float2bfloat16_rn(0.0f);
-        *reinterpret_cast<uint4*>(smem + OFF_B1 + ct * 16) = make_uint4(pack2(whi[0], whi[1]), pack2(whi[2], whi[3]), pack2(bhi, whi[0]), pack2(whi[1], whi[2]));
-        *reinterpret_cast<uint4*>(smem + OFF_B1 + L1N * 16 + ct * 16) = make_uint4(pack2(whi[3], bhi), pack2(wlo[0], wlo[1]), pack2(wlo[2], wlo[3]), pack2(blo, zero));
+            for (int k = 0; k < 4; ++k) split_bf16(k < d.ns ? P[oW + (int64_t)k * d.l1 + ct] : 0.0f, whi[k], wlo[k]);
+            split_bf16(P[ob + ct], bhi, blo);
+            const bf16 zero = __float2bfloat16_rn(0.0f);
+            *reinterpret_cast<uint4*>(smem + OFF_B1 + ct * 16) = make_uint4(pack2(whi[0], whi[1]), pack2(whi[2], whi[3]), pack2(bhi, whi[0]), pack2(whi[1], whi[2]));
+            *reinterpret_cast<uint4*>(smem + OFF_B1 + L1N * 16 + ct * 16) = make_uint4(pack2(whi[3], bhi), pack2(wlo[0], wlo[1]), pack2(wlo[2], wlo[3]), pack2(blo, zero));
+        }
         if (g.critic && ct < 64) {
             const CriticOff o = critic_off(d);
             wa_tab[ct] = ct < d.la ? P[o.Wa + ct] : 0.0f;
@@ -190,8 +193,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad3_kernel(const __grid_con
         }
     } else {
         // ================================================ converters ================================================
-        const int cw = warp - 2;             // 0..7
-        const int q4 = warp & 3, half = cw >> 2;
+        const int cw = warp - 2;             // 0..15
+        const int q4 = warp & 3, qtr = cw >> 2;      // TMEM lane quadrant; 32-column quarter of the 128-feature slab
+        const int half = qtr >> 1;                   // which 64-feature MN chunk of the r1 slab
         const int row = q4 * 32 + lane;
         const uint32_t tlane = (uint32_t)(q4 * 32) << 16;
         auto rowidx = [&](int tc) -> int64_t {
@@ -220,7 +224,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad3_kernel(const __grid_con
             __syncwarp();
             if (lane == 0) mbar_arrive(&x_full[t & 1]);
         };
-        if (half == 0 && T > 0) {
+        if (qtr == 0 && T > 0) {
             load_x(0);
             write_x(0);
             if (T > 1) { load_x(1); write_x(1); }
@@ -236,15 +240,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad3_kernel(const __grid_con
                     mbar_wait(z1_full, (uint32_t)(2 * t + sl) & 1);
                     tc_fence_after();
                     mbar_wait(&r_empty[rb], ((q >> 1) & 1) ^ 1);
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
+                    {
                         float z[32];
-                        tmem_ld32(tmem_base + 384u + (uint32_t)(half * 64 + h * 32) + tlane, z);
+                        tmem_ld32(tmem_base + 384u + (uint32_t)(qtr * 32) + tlane, z);
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
                             const uint4 pk = make_uint4(pack_relu_bf16x2(z[8 * k], z[8 * k + 1]), pack_relu_bf16x2(z[8 * k + 2], z[8 * k + 3]),
                                                         pack_relu_bf16x2(z[8 * k + 4], z[8 * k + 5]), pack_relu_bf16x2(z[8 * k + 6], z[8 * k + 7]));
-                            *reinterpret_cast<uint4*>(rrow + (((h * 4 + k) ^ (row & 7)) << 4)) = pk;
+                            *reinterpret_cast<uint4*>(rrow + ((((qtr & 1) * 4 + k) ^ (row & 7)) << 4)) = pk;
                         }
                     }
                     tc_fence_before();
@@ -252,7 +255,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad3_kernel(const __grid_con
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&r_full[rb]);
                     // both layer-1 MMAs of tile t have read X buffer t & 1 once z1_full of its second slab has been seen
-                    if (sl == 1 && half == 0 && t + 2 < T) {
+                    if (sl == 1 && qtr == 0 && t + 2 < T) {
                         write_x(t + 2);
                         if (t + 3 < T) load_x(t + 3);
                     }
@@ -262,11 +265,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad3_kernel(const __grid_con
                     mbar_wait(&r_empty[rb], ((q >> 1) & 1) ^ 1);         // every warp waits, so that no arrival can lap a phase of r_full
                     if (half == 0) {         // features 64..127 of this slab do not exist: that half keeps stale (finite) data, its rows are never flushed
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) {
+                        for (int k = 0; k < 4; ++k) {
                             float r[8];
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) r[j] = fmaf(a_val, wa_tab[8 * k + j], ba_tab[8 * k + j]);
-                            *reinterpret_cast<uint4*>(rrow + ((k ^ (row & 7)) << 4)) =
+                            for (int j = 0; j < 8; ++j) r[j] = fmaf(a_val, wa_tab[qtr * 32 + 8 * k + j], ba_tab[qtr * 32 + 8 * k + j]);
+                            *reinterpret_cast<uint4*>(rrow + (((qtr * 4 + k) ^ (row & 7)) << 4)) =
                                 make_uint4(pack_relu_bf16x2(r[0], r[1]), pack_relu_bf16x2(r[2], r[3]), pack_relu_bf16x2(r[4], r[5]), pack_relu_bf16x2(r[6], r[7]));
                         }
                         fence_proxy_async();
@@ -276,21 +279,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad3_kernel(const __grid_con
                 }
             }
         }
-        // ---- accumulators of this CTA -> global: slab sl, feature sl*128 + row, this warp's 64 columns
+        // ---- accumulators of this CTA -> global: slab sl, feature sl*128 + row, this warp's 32 columns
         if (T > 0) {
             mbar_wait(acc_done, 0);
             tc_fence_after();
             for (int sl = 0; sl < FT; ++sl) {
                 const int nfeat = sl < 2 ? SLAB : d.la;
-                float* dst = g.grads + (int64_t)agent * g.gstride + g.oW2 + (int64_t)(sl * SLAB + row) * L2N + half * 64;
+                float* dst = g.grads + (int64_t)agent * g.gstride + g.oW2 + (int64_t)(sl * SLAB + row) * L2N + qtr * 32;
+                float v[32];
+                tmem_ld32(tmem_base + (uint32_t)(sl * SLAB + qtr * 32) + tlane, v);
+                if (row < nfeat) {
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    float v[32];
-                    tmem_ld32(tmem_base + (uint32_t)(sl * SLAB + half * 64 + h * 32) + tlane, v);
-                    if (row < nfeat) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) atomicAdd(dst + h * 32 + j, v[j]);
-                    }
+                    for (int j = 0; j < 32; ++j) atomicAdd(dst + j, v[j]);
                 }
             }
             tc_fence_before();
