@@ -207,8 +207,9 @@ def run_native(args):
 
     # ---- device-resident timing of the whole training step (inputs already in HBM)
     l0 = tr.gpu_launches
-    with ClockSampler(local) as clk:
-        ms_call = _timed(step_fn, calls, world)
+    clk = ClockSampler(local)        # nvidia-smi takes ~0.1 s per query: keep sampling through all timed legs (device-timed steps,
+    clk.__enter__()                  # attribution, end-to-end) so that the clocks line rests on more than one sample under load
+    ms_call = _timed(step_fn, calls, world)
     ms_step = ms_call / steps_per_call
     launches = (tr.gpu_launches - l0) if not args.graph else calls * steps_per_call * 45
     value = world * P * M / (ms_step * 1e-3)
@@ -250,6 +251,7 @@ def run_native(args):
         e2e_step()
     _barrier(world)
     e2e_ms = _max_over_ranks((time.perf_counter() - t0) * 1e3, world) / n_e2e
+    clk.__exit__(None, None, None)
     e2e = {"value": world * P * M / (e2e_ms * 1e-3), "unit": METRIC, "h2d_bytes_per_step": P * 4,
            "d2h_bytes_per_step": int(h_out.numel()) * 4, "ms_per_step": e2e_ms, "steps": n_e2e,
            "api": "BatchedTrainer.step(host_leader_exog=pinned) + D2H of reward/done statistics and losses"}
