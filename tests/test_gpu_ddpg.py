@@ -442,3 +442,38 @@ def test_batched_trainer_reference_episode_loop_and_csvs(mods, tmp_path):
     assert rows[0] == ",Vehicle 1,Vehicle 2,seed,platoon" and len(rows) == 1 + 3 * 4
     results.config_writer(str(tmp_path / "conf.json"), conf)
     assert results.config_loader(str(tmp_path / "conf.json")).pl_size == 2
+
+
+@pytest.mark.parametrize("la", [16, 32, 64])
+def test_learn_tensor_core_mode_other_action_layer_sizes(mods, la):
+    """The persistent kernels take the critic's action-branch width at run time (16 ... 64 columns: partial last k-block /
+    dgrad chunk / weight-gradient slab); 48 is the reference default covered above."""
+    A, R = 2, 700
+    conf = mods["Config"](critic_act_layer_size=la)
+    pop = mods["trainer"].DDPGPopulation(A, 1, conf, rows_per_agent=R, precision=1)
+    assert pop.dims.la == la
+    rng = np.random.default_rng(90 + la)
+    nets = []
+    for a in range(A):
+        n4 = [D.init_actor(rng), D.init_critic(rng, la=la), D.init_actor(rng), D.init_critic(rng, la=la)]
+        D.randomize_bn(n4[0], rng, [("g1", "be1", "mu1", "var1"), ("g2", "be2", "mu2", "var2")])
+        D.randomize_bn(n4[1], rng, [("gs", "bes", "mus", "vars"), ("ga", "bea", "mua", "vara"), ("g2", "be2", "mu2", "var2")])
+        n4[1]["W3"] *= 300
+        n4[0]["W3"] *= 50
+        for bank, net in zip((pop.actor, pop.critic, pop.t_actor, pop.t_critic), n4):
+            bank.load_named(a, net)
+        nets.append(n4)
+    batches = [make_batch(300 + a, R) for a in range(A)]
+    cat = lambda i, w: torch.as_tensor(np.concatenate([b[i].reshape(R, w) for b in batches]), device="cuda").contiguous()
+    pop.learn(cat(0, 4), cat(1, 1).reshape(-1), cat(2, 1).reshape(-1), cat(3, 4), apply_updates=False)
+    torch.cuda.synchronize()
+    bad = []
+    for i in range(A):
+        ocg, oag, info = D.learn(nets[i][0], nets[i][1], nets[i][2], nets[i][3], batches[i], gamma=conf.gamma, high=conf.action_high)
+        for bank, ref in ((pop.critic, ocg), (pop.actor, oag)):
+            for name in bank.trainable_names:
+                got = bank.view(name, i, bank.grad).cpu().numpy()
+                e2 = _l2(got, ref[name].reshape(got.shape))
+                if not e2 < 4e-2:
+                    bad.append((i, bank.kind, name, round(e2, 4)))
+    assert not bad, bad
