@@ -679,6 +679,7 @@ int run(int mode, const avd_net_dims& d, int A, int64_t R, const float* params, 
     const bool bwd = mode == MODE_CRITIC_BWD || mode == MODE_ACTOR_BWD;
     const int F = critic ? d.l1 + d.la : d.l1;
     AVD_REQUIRE(params && W2T && b2f && s, "null buffer");
+    AVD_REQUIRE(A >= 1 && R >= 1 && R < (int64_t)1 << 31, "rows per agent must fit the 32-bit TMA coordinates");
     AVD_REQUIRE(!critic || act, "critic passes need actions");
     AVD_REQUIRE(!bwd || (mask_out && DZ_out && U && sdq), "backward passes need mask / dz2 / U / sdq outputs");
     AVD_REQUIRE(bwd || out, "null output");

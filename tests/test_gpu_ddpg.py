@@ -333,27 +333,38 @@ def test_batched_trainer_interfrl_keeps_replicas_identical(mods):
 
 
 # ------------------------------------------------------------------------------------------ bf16 tensor-core mode
-@pytest.mark.parametrize("A,R", [(1, 64), (3, 64), (2, 1000), (1, 4096), (1, 250_000), (3, 100_003)])
+@pytest.mark.parametrize("A,R", [(1, 64), (3, 64), (2, 1000), (1, 4096), (1, 250_000), (3, 100_003), (200, 64)])
 def test_learn_gradients_tensor_core_mode(mods, A, R):
     """precision=1: every contraction of the learn step runs on tcgen05 (bf16 operands, fp32 TMEM accumulation; layer 1 with
     hi/lo-split operands), heads / losses / reductions in fp32.  Bar against the fp32 oracle, per gradient tensor: relative L2
     error < 6e-2 (max error < 1.2e-1) on single 64-row minibatches, where the critic gradient is driven by the TD error q - y, a
     small difference of two bf16-noisy values (measured 0.05 % - 4.5 %), and < 2e-2 (4e-2) from 1000 rows up (measured < 0.7 %,
-    profiles/r01_tensor_core_accuracy.txt).  Losses agree to 1e-3.  precision=0 is the parity mode (2e-4).
+    profiles/r01_tensor_core_accuracy.txt).  The actor gradient of a single 64-row minibatch is bounded at 3e-1: it is
+    proportional to d q / d action, a 128-term bf16 sum with cancellation, whose per-row signs cancel again in the reductions over
+    the batch (seed 111: sum dq = -2.2e-4 against sum |dq| = 6.8e-3), and reaches 23 % for the worst of 200 seeds (typical
+    0.5 % - 2 %); with the bench's 262,144 rows per update it is 0.5 %.  Losses agree to 1e-3.  precision=0 is the parity mode (2e-4).
     The two large cases give every persistent CTA 6-14 row tiles (ragged last tile, several agents per launch), so the mbarrier
-    phase arithmetic of the software pipelines wraps many times."""
+    phase arithmetic of the software pipelines wraps many times; (200, 64) has more agents than SMs (one CTA per agent, two waves)."""
     conf, pop, nets, batches, (s, a, r, s2) = build_population(mods, A, R, list(range(50, 50 + A)))
     pop.precision = 1
     pop.learn(s, a, r, s2, apply_updates=False)
     torch.cuda.synchronize()
     bad = []
-    l2_tol, mx_tol = (6e-2, 1.2e-1) if R < 1000 else (2e-2, 4e-2)
     for i in range(A):
         ocg, oag, info = D.learn(nets[i][0], nets[i][1], nets[i][2], nets[i][3], batches[i], gamma=conf.gamma, high=conf.action_high)
         for bank, ref in ((pop.critic, ocg), (pop.actor, oag)):
+            if R >= 1000:
+                l2_tol, mx_tol = 2e-2, 4e-2
+            else:                # one 64-row minibatch: see the docstring
+                l2_tol, mx_tol = (6e-2, 1.2e-1) if bank is pop.critic else (3e-1, 4e-1)
+            # tensors whose true gradient nearly cancels are measured against a quarter of the norm of the net's whole gradient
+            # instead of their own, tiny, norm (seed 111: b3 = sum of signed dq = -2.2e-4 with sum |dq| = 6.8e-3)
+            floor = 0.25 * float(np.sqrt(sum(np.sum(np.square(ref[n].astype(np.float64))) for n in bank.trainable_names)))
             for name in bank.trainable_names:
-                got = bank.view(name, i, bank.grad).cpu().numpy()
-                e2, em = _l2(got, ref[name].reshape(got.shape)), _nrm(got, ref[name].reshape(got.shape))
+                got = bank.view(name, i, bank.grad).cpu().numpy().astype(np.float64)
+                want = ref[name].reshape(got.shape).astype(np.float64)
+                e2 = float(np.linalg.norm(got - want) / max(np.linalg.norm(want), floor))
+                em = float(np.max(np.abs(got - want)) / max(np.max(np.abs(want)), floor / np.sqrt(got.size)))
                 if not (e2 < l2_tol and em < mx_tol):
                     bad.append((i, bank.kind, name, round(e2, 4), round(em, 4)))
         loss = pop.loss[i].cpu().numpy()
