@@ -90,6 +90,7 @@ _lib = None
 SIGNATURES = {
     "avd_abi_version": (C.c_int, []),
     "avd_last_error": (C.c_char_p, []),
+    "avd_kernel_launches": (C.c_int64, []),
     "avd_sizeof": (C.c_int64, [C.c_int]),
     "avd_device_info": (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int64)]),
     "avd_clock_advance": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]),

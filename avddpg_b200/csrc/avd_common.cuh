@@ -9,6 +9,7 @@
 namespace avd {
 
 void set_error(const char* fmt, ...);           // defined in avd_lib.cu
+void count_launch(int n = 1);                    // kernels launched by this library so far (avd_kernel_launches)
 int sm_count();                                  // cached multiprocessor count of the current device
 
 #define AVD_REQUIRE(cond, ...)                    \
@@ -30,6 +31,7 @@ int sm_count();                                  // cached multiprocessor count 
 
 #define AVD_LAUNCH_OK()                                                                     \
     do {                                                                                    \
+        ::avd::count_launch();                                                              \
         cudaError_t _e = cudaGetLastError();                                                \
         if (_e != cudaSuccess) {                                                            \
             ::avd::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \

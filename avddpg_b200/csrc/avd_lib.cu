@@ -2,6 +2,8 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <atomic>
+
 #include "avd_common.cuh"
 
 namespace avd {
@@ -14,6 +16,10 @@ void set_error(const char* fmt, ...) {
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
 }
+
+static std::atomic<long long> g_launches{0};
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 int sm_count() {
     static int cached = 0;
@@ -33,6 +39,8 @@ int sm_count() {
 extern "C" int avd_abi_version(void) { return AVD_ABI_VERSION; }
 
 extern "C" const char* avd_last_error(void) { return avd::g_err; }
+
+extern "C" int64_t avd_kernel_launches(void) { return (int64_t)avd::g_launches.load(std::memory_order_relaxed); }
 
 extern "C" int64_t avd_sizeof(int which) {
     switch (which) {

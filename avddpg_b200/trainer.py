@@ -47,7 +47,6 @@ class DDPGPopulation:
         self._ws = None
         self._act_ws = None
         self.io = _lib.LearnIO()
-        self.launches = 0
 
     def sync_targets(self):
         """target.set_weights(online.get_weights())  (trainer.py:130-131)."""
@@ -75,7 +74,6 @@ class DDPGPopulation:
         _lib.check(self.lib.avd_actor_forward(C.byref(d), self.A, rows, _lib.ptr(self.actor.flat), _lib.ptr(native_state), 1,
                                               M * P, float(self.config.action_high), _lib.ptr(out), _lib.ptr(self._act_ws),
                                               self._act_ws.numel(), self.precision, _lib.current_stream()))
-        self.launches += 3
         return out
 
     # ------------------------------------------------------------------ learning
@@ -107,7 +105,6 @@ class DDPGPopulation:
         io.workspace, io.workspace_bytes = ws.data_ptr(), ws.numel()
         io.precision = self.precision
         _lib.check(self.lib.avd_ddpg_learn(C.byref(io), _lib.current_stream()))
-        self.launches += 27 + (8 if apply_updates else 0)
         return self.critic.grad, self.actor.grad
 
     def apply_gradients(self, apply_mask: Optional[torch.Tensor] = None):
@@ -117,14 +114,12 @@ class DDPGPopulation:
             _lib.check(self.lib.avd_adam_apply(_lib.ptr(bank.flat), bank.total, _lib.ptr(bank.grad), bank.n_train, _lib.ptr(bank.m),
                                                _lib.ptr(bank.v), _lib.ptr(bank.step), _lib.ptr(apply_mask), self.A, bank.n_train,
                                                float(lr), 0.9, 0.999, 1e-7, _lib.current_stream()))
-        self.launches += 4
 
     def soft_update(self, apply_mask: Optional[torch.Tensor] = None):
         """ddpgagent.update_target + set_weights for every agent (trainer.py:352-356)."""
         for tgt, onl in ((self.t_critic, self.critic), (self.t_actor, self.actor)):
             _lib.check(self.lib.avd_polyak_update(_lib.ptr(tgt.flat), _lib.ptr(onl.flat), _lib.ptr(apply_mask), self.A, onl.total,
                                                   float(self.config.tau), _lib.current_stream()))
-        self.launches += 2
 
 
 class BatchedTrainer:
@@ -167,7 +162,8 @@ class BatchedTrainer:
 
     @property
     def gpu_launches(self):
-        return self.env.gpu_launches + self.pop.launches
+        """Kernels launched by libavddpg_b200 in this process so far (counted at the launch sites inside the library)."""
+        return int(self.pop.lib.avd_kernel_launches())
 
     def step(self, learn: bool = True, host_leader_exog: Optional[torch.Tensor] = None):
         """One environment step for every platoon + one learn() for every agent (when the buffers hold more than
@@ -237,9 +233,11 @@ class BatchedTrainer:
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         cur, counters = self.env._cur, (self.buffer_counter, self.step_in_run)
+        n0 = self.pop.lib.avd_kernel_launches()
         with torch.cuda.graph(self.graph):
             self.step()
             self.step()      # two steps per graph so the ping-pong state buffers end where they started
+        self.kernels_per_step = (self.pop.lib.avd_kernel_launches() - n0) // 2
         assert self.env._cur == cur
         self.buffer_counter, self.step_in_run = counters     # capturing executes nothing on the device
         return self.graph

@@ -206,12 +206,15 @@ def run_native(args):
     calls = max(1, args.steps // steps_per_call)
 
     # ---- device-resident timing of the whole training step (inputs already in HBM)
-    l0 = tr.gpu_launches
+    from avddpg_b200 import _lib as _avd
+    l0 = _avd.load().avd_kernel_launches()      # counted inside the library, one per kernel launch site executed
     clk = ClockSampler(local)        # nvidia-smi takes ~0.1 s per query: keep sampling through all timed legs (device-timed steps,
     clk.__enter__()                  # attribution, end-to-end) so that the clocks line rests on more than one sample under load
     ms_call = _timed(step_fn, calls, world)
     ms_step = ms_call / steps_per_call
-    launches = (tr.gpu_launches - l0) if not args.graph else calls * steps_per_call * 45
+    launches = _avd.load().avd_kernel_launches() - l0
+    if args.graph:      # replays do not pass through the launch sites: kernels per captured step x replayed steps
+        launches = calls * steps_per_call * tr.kernels_per_step
     value = world * P * M / (ms_step * 1e-3)
 
     # ---- attribution: env part (act + env step + replay add) and learn part (sample + learn + Adam + Polyak) alone

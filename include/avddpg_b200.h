@@ -121,6 +121,9 @@ typedef struct avd_env_io {
 /* ---- library ------------------------------------------------------------------------------- */
 int avd_abi_version(void);
 const char* avd_last_error(void);
+/* number of CUDA kernels this library has launched in the calling process so far (every launch site counts itself);
+ * callers difference it around a region, e.g. bench.py's "gpu_launches" */
+int64_t avd_kernel_launches(void);
 /* sizeof of the ABI structs as compiled (0 avd_env_params, 1 avd_env_io, 2 avd_clock): bindings
  * assert their own layout against these at load time. */
 int64_t avd_sizeof(int which);
