@@ -488,3 +488,26 @@ def test_learn_tensor_core_mode_other_action_layer_sizes(mods, la):
                 if not e2 < 4e-2:
                     bad.append((i, bank.kind, name, round(e2, 4)))
     assert not bad, bad
+
+
+def test_learn_edge_cases_and_errors(mods):
+    """Empty population is a no-op; bad arguments come back as ValueError through the C ABI's error convention."""
+    lib, conf = mods["lib"], mods["Config"]()
+    pop = mods["trainer"].DDPGPopulation(1, 1, conf, rows_per_agent=64, precision=1)
+    s = torch.zeros(64, 4, device="cuda"); a = torch.zeros(64, device="cuda")
+    pop.learn(s, a, a, s, apply_updates=False)
+    io = pop.io
+    io.A = 0
+    assert lib.load().avd_ddpg_learn(io, lib.current_stream()) == 0               # no agents: nothing to do
+    io.A, io.precision = 1, 7
+    with pytest.raises(ValueError, match="precision"):
+        lib.check(lib.load().avd_ddpg_learn(io, lib.current_stream()))
+    io.precision, io.rows_per_agent = 1, 0
+    with pytest.raises(ValueError):
+        lib.check(lib.load().avd_ddpg_learn(io, lib.current_stream()))
+    io.rows_per_agent, io.workspace_bytes = 64, 16
+    with pytest.raises(ValueError, match="workspace"):
+        lib.check(lib.load().avd_ddpg_learn(io, lib.current_stream()))
+    with pytest.raises(ValueError):
+        pop.learn(s[:10], a, a, s)                                                # shape mismatch caught on the host side
+    torch.cuda.synchronize()
