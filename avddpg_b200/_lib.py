@@ -78,6 +78,14 @@ class LearnIO(C.Structure):
     ]
 
 
+AVD_MAX_PEERS = 16
+
+
+class PeerComm(C.Structure):
+    _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("epoch", C.c_uint32), ("reserved0", C.c_uint32),
+                ("peer_base", C.c_uint64 * AVD_MAX_PEERS), ("multicast_base", C.c_uint64)]
+
+
 class AvdError(RuntimeError):
     pass
 
@@ -120,7 +128,12 @@ SIGNATURES = {
     "avd_polyak_update": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_void_p]),
     "avd_fed_reduce": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int64, C.c_int64,
                                  C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "avd_fed_reduce2": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32,
+                                  C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
+    "avd_fed_broadcast2": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int32,
+                                     C.c_int32, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "avd_fed_finalize": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_void_p]),
+    "avd_fed_exchange_peer": (C.c_int, [C.POINTER(PeerComm), C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_void_p]),
     "avd_fed_broadcast": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int64, C.c_int64,
                                     C.c_void_p, C.c_int64, C.c_void_p]),
     "avd_gemm_bf16": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64,

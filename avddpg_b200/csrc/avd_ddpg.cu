@@ -522,6 +522,46 @@ __global__ void __launch_bounds__(256) fed_reduce_kernel(float* __restrict__ out
     }
 }
 
+// Both banks of a federated round in one launch: out[s][0..na) / out[s][na..na+nc) = sum_x w[s][x] * actor / critic vector of
+// member (s, x), and the divisor column out[s][na+nc] = sum_x w[s][x] (or the member count) that turns the exchanged sums into
+// the mean (federated.py:62) or the weighted mean (federated.py:110).
+__global__ void __launch_bounds__(256) fed_reduce2_kernel(float* __restrict__ out, int64_t out_pitch, const float* __restrict__ in_a,
+                                                          int64_t pitch_a, int64_t na, const float* __restrict__ in_c, int64_t pitch_c,
+                                                          int64_t nc, int n_members, int64_t stride_s, int64_t stride_x,
+                                                          const float* __restrict__ weights) {
+    const int s = blockIdx.y;
+    const int64_t n = na + nc;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += (int64_t)gridDim.x * blockDim.x) {
+        float acc = 0.0f;
+        if (i == n) {
+            for (int x = 0; x < n_members; ++x) acc += weights ? weights[(int64_t)s * n_members + x] : 1.0f;
+        } else {
+            const float* in = i < na ? in_a : in_c;
+            const int64_t pitch = i < na ? pitch_a : pitch_c, col = i < na ? i : i - na;
+            for (int x = 0; x < n_members; ++x) {
+                const float w = weights ? weights[(int64_t)s * n_members + x] : 1.0f;
+                acc = fmaf(w, in[((int64_t)s * stride_s + (int64_t)x * stride_x) * pitch + col], acc);
+            }
+        }
+        out[(int64_t)s * out_pitch + i] = acc;
+    }
+}
+
+// ... and the way back: member (s, x) of both banks receives columns [0, na) / [na, na+nc) of system s (set_weights, trainer.py:448-456)
+__global__ void __launch_bounds__(256) fed_broadcast2_kernel(float* __restrict__ out_a, int64_t pitch_a, int64_t na, float* __restrict__ out_c,
+                                                             int64_t pitch_c, int64_t nc, const float* __restrict__ in, int64_t in_pitch,
+                                                             int n_members, int64_t stride_s, int64_t stride_x, const uint8_t* __restrict__ mask) {
+    const int s = blockIdx.y, x = blockIdx.z;
+    const int64_t member = (int64_t)s * stride_s + (int64_t)x * stride_x;
+    if (mask && !mask[member]) return;
+    const int64_t n = na + nc;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float v = in[(int64_t)s * in_pitch + i];
+        if (i < na) out_a[member * pitch_a + i] = v;
+        else out_c[member * pitch_c + (i - na)] = v;
+    }
+}
+
 __global__ void __launch_bounds__(256) fed_finalize_kernel(float* __restrict__ buf, int64_t pitch, int64_t n) {
     float* row = buf + (int64_t)blockIdx.y * pitch;
     const float inv = 1.0f / row[n];
@@ -1046,6 +1086,32 @@ extern "C" int avd_fed_reduce(float* out, int64_t out_pitch, const float* in, in
     const int gx = (int)std::min<int64_t>((n + 255) / 256, 128);
     fed_reduce_kernel<<<dim3(gx, n_systems), 256, 0, (cudaStream_t)stream>>>(out, out_pitch, in, pitch, n_members, member_stride_s,
                                                                               member_stride_x, weights, scale, n);
+    AVD_LAUNCH_OK();
+    return AVD_OK;
+}
+
+extern "C" int avd_fed_reduce2(float* out, int64_t out_pitch, const float* in_a, int64_t pitch_a, int64_t na, const float* in_c, int64_t pitch_c,
+                               int64_t nc, int32_t n_systems, int32_t n_members, int64_t member_stride_s, int64_t member_stride_x,
+                               const float* weights, void* stream) {
+    AVD_REQUIRE(out && in_a && in_c, "null buffer");
+    AVD_REQUIRE(n_systems >= 0 && n_members >= 1 && na >= 0 && nc >= 0 && out_pitch > na + nc, "bad sizes");
+    if (n_systems == 0) return AVD_OK;
+    const int gx = (int)std::min<int64_t>((na + nc + 256) / 256, 128);
+    fed_reduce2_kernel<<<dim3(gx, n_systems), 256, 0, (cudaStream_t)stream>>>(out, out_pitch, in_a, pitch_a, na, in_c, pitch_c, nc, n_members,
+                                                                               member_stride_s, member_stride_x, weights);
+    AVD_LAUNCH_OK();
+    return AVD_OK;
+}
+
+extern "C" int avd_fed_broadcast2(float* out_a, int64_t pitch_a, int64_t na, float* out_c, int64_t pitch_c, int64_t nc, const float* in,
+                                  int64_t in_pitch, int32_t n_systems, int32_t n_members, int64_t member_stride_s, int64_t member_stride_x,
+                                  const uint8_t* apply_mask, void* stream) {
+    AVD_REQUIRE(out_a && out_c && in, "null buffer");
+    AVD_REQUIRE(n_systems >= 0 && n_members >= 1 && na >= 0 && nc >= 0, "bad sizes");
+    if (n_systems == 0 || na + nc == 0) return AVD_OK;
+    const int gx = (int)std::min<int64_t>((na + nc + 255) / 256, 64);
+    fed_broadcast2_kernel<<<dim3(gx, n_systems, n_members), 256, 0, (cudaStream_t)stream>>>(out_a, pitch_a, na, out_c, pitch_c, nc, in, in_pitch,
+                                                                                             n_members, member_stride_s, member_stride_x, apply_mask);
     AVD_LAUNCH_OK();
     return AVD_OK;
 }

@@ -67,18 +67,63 @@ class Server:
         return out
 
 
-def exchange_and_scale(buf: torch.Tensor, process_group=None) -> torch.Tensor:
+def exchange_and_scale(buf: torch.Tensor, process_group=None, n: Optional[int] = None) -> torch.Tensor:
     """buf[systems, n+1]: local (weighted) SUMS with the local member count / weight sum in the last column.
     One all_reduce(sum) over the group (NCCL on GPUs, gloo in the CPU tests), then the division that turns the
     sums into the mean (federated.py:62) or the weighted mean (federated.py:110).  In place."""
+    n = buf.shape[1] - 1 if n is None else int(n)      # divisor column (the row pitch may be padded beyond n + 1)
     if process_group is not None:
         import torch.distributed as dist
         dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=process_group)
     if buf.is_cuda:
-        _lib.check(_lib.load().avd_fed_finalize(_lib.ptr(buf), buf.shape[1], buf.shape[0], buf.shape[1] - 1, _lib.current_stream()))
+        _lib.check(_lib.load().avd_fed_finalize(_lib.ptr(buf), buf.shape[1], buf.shape[0], n, _lib.current_stream()))
     else:   # host tensors: only the gloo unit test of the exchange logic
-        buf[:, :-1] *= (1.0 / buf[:, -1]).unsqueeze(1)
+        buf[:, :n] *= (1.0 / buf[:, n]).unsqueeze(1)
     return buf
+
+
+class PeerExchange:
+    """NVLink-native transport of the interfrl exchange (csrc/avd_peer.cu): a symmetric, peer-mapped buffer per rank
+    (torch.distributed._symmetric_memory) holding two alternating halves of partial sums plus the epoch flags; ONE kernel per
+    round signals the peers, waits for them, reads the sum over ranks -- reduced inside the NVSwitch through the NVLS multicast
+    mapping when the fabric provides one, otherwise with peer loads -- and writes the means locally.  Collective: every rank of
+    the group must construct it (rendezvous) and call `exchange` the same number of times."""
+    FLAG_BYTES = 256
+
+    def __init__(self, process_group, n_systems: int, max_pitch: int, device, allow_multicast: bool = True):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        self.lib = _lib.load()
+        self.half_bytes = (n_systems * max_pitch * 4 + 255) // 256 * 256
+        nbytes = self.FLAG_BYTES + 2 * self.half_bytes
+        self.raw = symm.empty(nbytes, dtype=torch.uint8, device=device)
+        self.raw.zero_()
+        torch.cuda.synchronize(device)
+        self.hdl = symm.rendezvous(self.raw, process_group.group_name)
+        self.comm = _lib.PeerComm()
+        self.comm.rank, self.comm.world, self.comm.epoch = self.hdl.rank, self.hdl.world_size, 0
+        if self.hdl.world_size > _lib.AVD_MAX_PEERS:
+            raise ValueError(f"at most {_lib.AVD_MAX_PEERS} ranks")
+        for r, ptr in enumerate(self.hdl.buffer_ptrs):
+            self.comm.peer_base[r] = int(ptr)
+        self.comm.multicast_base = int(getattr(self.hdl, "multicast_ptr", 0) or 0) if allow_multicast else 0
+        self.nvls = self.comm.multicast_base != 0
+        dist.barrier(group=process_group)        # every rank has zeroed its flags before the first signal can arrive
+        self.round = 0
+
+    def half(self, n_systems: int, pitch: int) -> torch.Tensor:
+        """This round's [n_systems, pitch] float32 view of the local symmetric buffer (fill it, then call exchange)."""
+        off = self.FLAG_BYTES + (self.round & 1) * self.half_bytes
+        return self.raw[off:off + n_systems * pitch * 4].view(torch.float32).view(n_systems, pitch)
+
+    def exchange(self, out: torch.Tensor, n: int):
+        """out[s, :n] = sum over ranks of half[s, :n] / sum over ranks of half[s, n]."""
+        S, pitch = out.shape
+        self.comm.epoch = self.round + 1
+        off = self.FLAG_BYTES + (self.round & 1) * self.half_bytes
+        _lib.check(self.lib.avd_fed_exchange_peer(C.byref(self.comm), 0, off, _lib.ptr(out), pitch, S, n, _lib.current_stream()))
+        self.round += 1
+        return out
 
 
 def shard_platoons(num_platoons: int, rank: int, world: int):
@@ -90,10 +135,13 @@ def shard_platoons(num_platoons: int, rank: int, world: int):
 
 class FederatedAggregator:
     def __init__(self, population, conf, process_group=None, world_size: Optional[int] = None,
-                 reference_weights_quirk: bool = True):
+                 reference_weights_quirk: bool = True, transport: str = "auto"):
         """population: DDPGPopulation (A = G*M agents of THIS rank).  process_group: a torch.distributed group
         (NCCL on GPUs) or None for single-process.  reference_weights_quirk: weights mode applies system 0's
-        average to every agent, as workers/trainer.py:442-456 does (`[...][0]`)."""
+        average to every agent, as workers/trainer.py:442-456 does (`[...][0]`).  transport: "peer" = the NVLink-native
+        one-kernel exchange over symmetric memory (NVLS in-switch reduction when available; "p2p" forces plain peer loads),
+        "nccl" = all_reduce + finalize,
+        "auto" = peer when the group spans several CUDA ranks and symmetric memory can be set up, else nccl."""
         self.pop, self.conf, self.pg = population, conf, process_group
         self.lib = _lib.load()
         if conf.fed_method not in ("interfrl", "intrafrl"):
@@ -113,19 +161,31 @@ class FederatedAggregator:
         dev = population.device
         self._bufs = {}
         self.device = dev
-        self._ones = torch.ones(self.n_systems, dtype=torch.float32, device=dev)
-        self._count = torch.full((self.n_systems,), float(self.n_members), dtype=torch.float32, device=dev)
         self.apply_mask = None
         if (not self.inter) and getattr(conf, "intra_directional_averaging", False):
             mask = torch.ones(G * M, dtype=torch.uint8, device=dev)
             mask[:G] = 0            # follower m = 0 ("leader is king", trainer.py:417-418, 450-451)
             self.apply_mask = mask
         self.rounds = 0
+        self.peer = None
+        self.transport = "nccl"
+        if transport not in ("auto", "peer", "p2p", "nccl"):
+            raise ValueError("transport must be auto, peer, p2p or nccl")
+        if transport != "nccl" and self.inter and self.world > 1 and dev.type == "cuda":
+            max_pitch = (population.actor.total + population.critic.total + 1 + 3) // 4 * 4
+            try:
+                self.peer = PeerExchange(process_group, self.n_systems, max_pitch, dev, allow_multicast=transport != "p2p")
+                self.transport = "peer/nvls" if self.peer.nvls else "peer/p2p"
+            except Exception:
+                if transport in ("peer", "p2p"):
+                    raise
+                self.peer = None
 
     def _buffer(self, na, nc):
         key = (na, nc)
         if key not in self._bufs:
-            self._bufs[key] = torch.zeros(self.n_systems, na + nc + 1, dtype=torch.float32, device=self.device)
+            pitch = (na + nc + 1 + 3) // 4 * 4        # rows start 16-byte aligned (vector / multimem loads of the peer exchange)
+            self._bufs[key] = torch.zeros(self.n_systems, pitch, dtype=torch.float32, device=self.device)
         return self._bufs[key]
 
     def _reduce_exchange(self, a_src, na, c_src, nc, a_pitch, c_pitch, weights):
@@ -133,17 +193,19 @@ class FederatedAggregator:
         S, X = self.n_systems, self.n_members
         buf = self._buffer(na, nc)
         pitch = buf.shape[1]
+        use_peer = self.peer is not None and self.inter and self.world > 1
+        dst = self.peer.half(S, pitch) if use_peer else buf        # partial sums go straight into the symmetric buffer
         st = _lib.current_stream()
-        ones = self._ones
         w = None
         if weights is not None:
             w = torch.as_tensor(weights, dtype=torch.float32, device=self.device).reshape(S, X).contiguous()
-        for src, n, src_pitch, off in ((a_src, na, a_pitch, 0), (c_src, nc, c_pitch, na)):
-            out = buf[:, off:]
-            _lib.check(self.lib.avd_fed_reduce(_lib.ptr(out), pitch, _lib.ptr(src), src_pitch, S, X, self.stride_s, self.stride_x,
-                                               _lib.ptr(w), _lib.ptr(ones), n, st))
-        buf[:, na + nc].copy_(w.sum(dim=1) if w is not None else self._count)
-        exchange_and_scale(buf, self.pg if (self.inter and self.world > 1) else None)
+        # one launch: (weighted) sums of both banks + the divisor column
+        _lib.check(self.lib.avd_fed_reduce2(_lib.ptr(dst), pitch, _lib.ptr(a_src), a_pitch, na, _lib.ptr(c_src), c_pitch, nc, S, X,
+                                            self.stride_s, self.stride_x, _lib.ptr(w), st))
+        if use_peer:
+            self.peer.exchange(buf, na + nc)
+        else:
+            exchange_and_scale(buf, self.pg if (self.inter and self.world > 1) else None, n=na + nc)
         self.rounds += 1
         return buf
 
@@ -153,12 +215,9 @@ class FederatedAggregator:
         pop = self.pop
         na, nc = pop.actor.n_train, pop.critic.n_train
         buf = self._reduce_exchange(pop.actor.grad, na, pop.critic.grad, nc, na, nc, weights)
-        pitch = buf.shape[1]
-        st = _lib.current_stream()
-        for bank, n, off in ((pop.actor, na, 0), (pop.critic, nc, na)):
-            src = buf[:, off:]
-            _lib.check(self.lib.avd_fed_broadcast(_lib.ptr(bank.grad), n, _lib.ptr(src), pitch, self.n_systems, self.n_members,
-                                                  self.stride_s, self.stride_x, _lib.ptr(self.apply_mask), n, st))
+        _lib.check(self.lib.avd_fed_broadcast2(_lib.ptr(pop.actor.grad), na, na, _lib.ptr(pop.critic.grad), nc, nc, _lib.ptr(buf), buf.shape[1],
+                                               self.n_systems, self.n_members, self.stride_s, self.stride_x, _lib.ptr(self.apply_mask),
+                                               _lib.current_stream()))
         if apply:
             pop.apply_gradients(self.apply_mask)
             pop.soft_update(self.apply_mask)
@@ -170,16 +229,13 @@ class FederatedAggregator:
         pop = self.pop
         na, nc = pop.actor.total, pop.critic.total
         buf = self._reduce_exchange(pop.actor.flat, na, pop.critic.flat, nc, na, nc, weights)
-        pitch = buf.shape[1]
         st = _lib.current_stream()
-        for banks, n, off in (((pop.actor, pop.t_actor), na, 0), ((pop.critic, pop.t_critic), nc, na)):
-            src = buf[:, off:]
-            for bank in banks:
-                if self.quirk:   # every agent receives system 0's average
-                    _lib.check(self.lib.avd_fed_broadcast(_lib.ptr(bank.flat), n, _lib.ptr(src), pitch, 1, pop.A, 0, 1,
-                                                          _lib.ptr(self.apply_mask), n, st))
-                else:
-                    _lib.check(self.lib.avd_fed_broadcast(_lib.ptr(bank.flat), n, _lib.ptr(src), pitch, self.n_systems,
-                                                          self.n_members, self.stride_s, self.stride_x,
-                                                          _lib.ptr(self.apply_mask), n, st))
+        for a_bank, c_bank in ((pop.actor, pop.critic), (pop.t_actor, pop.t_critic)):      # online AND target nets (trainer.py:448-456)
+            if self.quirk:   # every agent receives system 0's average
+                _lib.check(self.lib.avd_fed_broadcast2(_lib.ptr(a_bank.flat), na, na, _lib.ptr(c_bank.flat), nc, nc, _lib.ptr(buf), buf.shape[1],
+                                                       1, pop.A, 0, 1, _lib.ptr(self.apply_mask), st))
+            else:
+                _lib.check(self.lib.avd_fed_broadcast2(_lib.ptr(a_bank.flat), na, na, _lib.ptr(c_bank.flat), nc, nc, _lib.ptr(buf), buf.shape[1],
+                                                       self.n_systems, self.n_members, self.stride_s, self.stride_x,
+                                                       _lib.ptr(self.apply_mask), st))
         return buf

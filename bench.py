@@ -272,8 +272,15 @@ def run_native(args):
     ms_frl = _timed(lambda: agg.aggregate_gradients(), 50, world)
     ms_frl_exchange = _timed(lambda: agg.aggregate_gradients(apply=False), 50, world)
     frl = {"mode": "interfrl / gradients / unweighted", "round_us": ms_frl * 1e3, "reduce_exchange_broadcast_us": ms_frl_exchange * 1e3,
-           "payload_bytes": int(M * (pop.actor.n_train + pop.critic.n_train + 1) * 4), "ranks": world,
-           "includes": "avd_fed_reduce + NCCL all_reduce(sum) [N>1] + scale + avd_fed_broadcast + Adam x2 + Polyak x2"}
+           "payload_bytes": int(M * (pop.actor.n_train + pop.critic.n_train + 1) * 4), "ranks": world, "transport": agg.transport,
+           "includes": "avd_fed_reduce + exchange [N>1: one NVLink kernel, in-switch NVLS reduction when available] + scale + "
+                       "avd_fed_broadcast + Adam x2 + Polyak x2"}
+    if world > 1:       # the NCCL transport (all_reduce + finalize kernel) for comparison
+        agg_nccl = FederatedAggregator(pop, _Config(pl_size=M, fed_method="interfrl", weighted_average_enabled=False), process_group=pg,
+                                       transport="nccl")
+        for _ in range(5):
+            agg_nccl.aggregate_gradients(apply=False)
+        frl["reduce_exchange_broadcast_us_nccl"] = _timed(lambda: agg_nccl.aggregate_gradients(apply=False), 50, world) * 1e3
 
     out = None
     if rank == 0:

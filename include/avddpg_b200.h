@@ -273,9 +273,38 @@ int avd_fed_reduce(float* out, int64_t out_pitch, const float* in, int64_t pitch
                    int64_t member_stride_s, int64_t member_stride_x, const float* weights, const float* scale, int64_t n,
                    void* stream);
 
+/* One-launch forms for a whole federated round (actor and critic vectors side by side in one [systems][pitch] buffer):
+ * avd_fed_reduce2: out[s][0..na) / out[s][na..na+nc) = sum_x w[s][x] * actor / critic vector of member (s, x) (weights NULL = 1)
+ * and out[s][na+nc] = sum_x w[s][x] -- the divisor that travels through the exchange; avd_fed_broadcast2: the way back.      */
+int avd_fed_reduce2(float* out, int64_t out_pitch, const float* in_a, int64_t pitch_a, int64_t na, const float* in_c, int64_t pitch_c,
+                    int64_t nc, int32_t n_systems, int32_t n_members, int64_t member_stride_s, int64_t member_stride_x,
+                    const float* weights, void* stream);
+int avd_fed_broadcast2(float* out_a, int64_t pitch_a, int64_t na, float* out_c, int64_t pitch_c, int64_t nc, const float* in,
+                       int64_t in_pitch, int32_t n_systems, int32_t n_members, int64_t member_stride_s, int64_t member_stride_x,
+                       const uint8_t* apply_mask, void* stream);
+
 /* buf[s][0..n) *= 1 / buf[s][n]: turns the exchanged (weighted) sums into means (federated.py:62 / :110); the
  * divisor (member count or sum of weights) travels in column n of the same buffer through the all_reduce.     */
 int avd_fed_finalize(float* buf, int64_t pitch, int32_t n_systems, int64_t n, void* stream);
+
+/* NVLink-native exchange step of an interfrl round (replaces ncclAllReduce + avd_fed_finalize; src/server/federated.py:56-62,
+ * 109-110 across GPUs).  Every rank owns one allocation of a SYMMETRIC buffer (peer-mapped into all ranks, e.g. from
+ * torch.distributed._symmetric_memory); peer_base[r] is rank r's allocation as seen from this process, multicast_base the NVLS
+ * multicast mapping of the same allocation (0 if the fabric has none).  Inside the allocation: `flag_offset` -> AVD_MAX_PEERS
+ * uint32 epoch flags (zero-initialised once), `data_offset` -> this round's partial sums [n_systems][pitch] fp32 with the local
+ * member count / weight sum in column n.  The kernel signals `epoch` to every peer, waits for all peers, reads the sums over
+ * ranks (multimem.ld_reduce in the NVSwitch, or peer loads) and writes out[s][j] = sum_r data_r[s][j] / sum_r data_r[s][n].
+ * `epoch` must increase by one per call on every rank and the caller alternates `data_offset` between two halves.          */
+#define AVD_MAX_PEERS 16
+typedef struct avd_peer_comm {
+    int32_t rank, world;
+    uint32_t epoch;
+    uint32_t reserved0;
+    uint64_t peer_base[AVD_MAX_PEERS];
+    uint64_t multicast_base;
+} avd_peer_comm;
+int avd_fed_exchange_peer(const avd_peer_comm* comm, int64_t flag_offset, int64_t data_offset, float* out, int64_t pitch,
+                          int32_t n_systems, int64_t n, void* stream);
 
 /* out[a][j] = in[src(a)][j]: broadcast system averages back onto members (set_weights, trainer.py:448-456). */
 int avd_fed_broadcast(float* out, int64_t out_pitch, const float* in, int64_t in_pitch, int32_t n_systems,

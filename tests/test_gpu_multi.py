@@ -1,5 +1,6 @@
-"""Multi-GPU tests (run with at least 2 visible GPUs; skipped otherwise): interfrl aggregation over NCCL equals the
-single-process aggregation over the union of the platoons, and sharded platoons reproduce the single-GPU streams."""
+"""Multi-GPU tests (run with at least 2 visible GPUs; skipped otherwise): interfrl aggregation -- over NCCL and over the
+NVLink-native peer exchange -- equals the single-process aggregation over the union of the platoons, and sharded platoons
+reproduce the single-GPU streams."""
 import os
 import socket
 
@@ -35,10 +36,26 @@ def _worker(rank, world, port, q):
     lo = rank * G
     pop.actor.grad.copy_(full_a[:, lo:lo + G].reshape(M * G, -1))
     pop.critic.grad.copy_(full_c[:, lo:lo + G].reshape(M * G, -1))
-    agg = FederatedAggregator(pop, conf, process_group=dist.group.WORLD)
-    agg.aggregate_gradients(apply=False)
-    ok_a = torch.allclose(pop.actor.grad.reshape(M, G, -1), full_a.mean(1, keepdim=True).expand(M, G, -1), rtol=1e-5, atol=1e-6)
-    ok_c = torch.allclose(pop.critic.grad.reshape(M, G, -1), full_c.mean(1, keepdim=True).expand(M, G, -1), rtol=1e-5, atol=1e-6)
+    ok_a = ok_c = True
+    transports = []
+    for transport in ("nccl", "p2p", "peer"):      # NCCL all_reduce + finalize vs. the one-kernel NVLink exchange (peer loads / NVLS)
+        agg = FederatedAggregator(pop, conf, process_group=dist.group.WORLD, transport=transport)
+        transports.append(agg.transport)
+        for rnd in range(5):                # several rounds: epochs advance and the symmetric buffer alternates halves
+            scale = 1.0 + rnd
+            pop.actor.grad.copy_(scale * full_a[:, lo:lo + G].reshape(M * G, -1))
+            pop.critic.grad.copy_(scale * full_c[:, lo:lo + G].reshape(M * G, -1))
+            w = None
+            want_a, want_c = full_a.mean(1, keepdim=True), full_c.mean(1, keepdim=True)
+            if rnd % 2 == 1:                # weighted round: members arrive pre-multiplied by w, result = sum / sum_w (federated.py:99-118)
+                wf = 0.5 + torch.arange(M * G_total, device="cuda", dtype=torch.float32).reshape(M, G_total) / 7.0
+                w = wf[:, lo:lo + G].contiguous()
+                want_a = (wf.unsqueeze(-1) * full_a).sum(1, keepdim=True) / wf.sum(1).reshape(M, 1, 1)
+                want_c = (wf.unsqueeze(-1) * full_c).sum(1, keepdim=True) / wf.sum(1).reshape(M, 1, 1)
+            agg.aggregate_gradients(weights=w, apply=False)
+            ok_a &= torch.allclose(pop.actor.grad.reshape(M, G, -1), (scale * want_a).expand(M, G, -1), rtol=2e-5, atol=1e-6)
+            ok_c &= torch.allclose(pop.critic.grad.reshape(M, G, -1), (scale * want_c).expand(M, G, -1), rtol=2e-5, atol=1e-6)
+    assert transports[0] == "nccl" and transports[1] == "peer/p2p" and transports[2].startswith("peer/"), transports
     # sharded env == slice of the global env (RNG streams keyed by global platoon id)
     P_total = 64
     Pl = P_total // world
@@ -47,7 +64,7 @@ def _worker(rank, world, port, q):
     for _ in range(5):
         env.action_mu.zero_()
         env.step_native(explore=True, gen_exog=True)
-    q.put((rank, bool(ok_a), bool(ok_c), env.state.cpu().numpy()))
+    q.put((rank, bool(ok_a), bool(ok_c), env.state.cpu().numpy(), transports[2]))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -65,7 +82,8 @@ def test_interfrl_nccl_and_sharded_env_world2():
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
-    assert all(r[1] and r[2] for r in res)
+    assert all(r[1] and r[2] for r in res), res
+    print("peer transport:", res[0][4])
     from avddpg_b200.config import Config
     from avddpg_b200.environment import BatchedPlatoons
     conf = Config(pl_size=2)
