@@ -491,6 +491,46 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ params, i
     }
 }
 
+// Adam on the trainable prefix and the Polyak update of the target vector in one pass over an agent's parameters
+// (trainer.py:348-349 then 352-356 / ddpgagent.py:44-55: the target sees the freshly updated online weights).
+__global__ void __launch_bounds__(256) adam_polyak_kernel(float* __restrict__ params, float* __restrict__ target, int64_t pstride,
+                                                          const float* __restrict__ grads, int64_t gstride, float* __restrict__ m,
+                                                          float* __restrict__ v, const int32_t* __restrict__ step,
+                                                          const uint8_t* __restrict__ mask, int64_t n_train, int64_t total, float lr, float b1,
+                                                          float b2, float eps, float tau) {
+    const int agent = blockIdx.y;
+    if (mask && !mask[agent]) return;
+    const float t = (float)(step[agent] + 1);
+    const float lr_t = lr * sqrtf(1.0f - powf(b2, t)) / (1.0f - powf(b1, t));
+    float* P = params + (int64_t)agent * pstride;
+    float* T = target + (int64_t)agent * pstride;
+    const float* G = grads + (int64_t)agent * gstride;
+    float* Mm = m + (int64_t)agent * n_train;
+    float* Vv = v + (int64_t)agent * n_train;
+    const float omt = 1.0f - tau;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        float p = P[i];
+        if (i < n_train) {
+            const float g = G[i];
+            const float mi = Mm[i] + (g - Mm[i]) * (1.0f - b1);
+            const float vi = Vv[i] + (g * g - Vv[i]) * (1.0f - b2);
+            Mm[i] = mi;
+            Vv[i] = vi;
+            p -= lr_t * mi / (sqrtf(vi) + eps);
+            P[i] = p;
+        }
+        T[i] = p * tau + T[i] * omt;
+    }
+}
+
+__global__ void step_increment2_kernel(int32_t* step_a, int32_t* step_b, const uint8_t* mask, int A) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a < A && (!mask || mask[a])) {
+        step_a[a] += 1;
+        step_b[a] += 1;
+    }
+}
+
 __global__ void step_increment_kernel(int32_t* step, const uint8_t* mask, int A) {
     const int a = blockIdx.x * blockDim.x + threadIdx.x;
     if (a < A && (!mask || mask[a])) step[a] += 1;
@@ -1066,6 +1106,30 @@ extern "C" int avd_adam_apply(float* params, int64_t param_stride, const float* 
     return AVD_OK;
 }
 
+extern "C" int avd_adam_polyak_apply2(float* actor, float* t_actor, int64_t actor_total, const float* actor_grad, int64_t actor_gstride,
+                                      float* actor_m, float* actor_v, int32_t* actor_step, int64_t actor_train, float actor_lr, float* critic,
+                                      float* t_critic, int64_t critic_total, const float* critic_grad, int64_t critic_gstride, float* critic_m,
+                                      float* critic_v, int32_t* critic_step, int64_t critic_train, float critic_lr, const uint8_t* apply_mask,
+                                      int32_t A, float beta1, float beta2, float eps, float tau, void* stream) {
+    AVD_REQUIRE(actor && t_actor && actor_grad && actor_m && actor_v && actor_step && critic && t_critic && critic_grad && critic_m && critic_v &&
+                    critic_step,
+                "null buffer");
+    AVD_REQUIRE(A >= 0 && actor_train >= 0 && actor_total >= actor_train && critic_train >= 0 && critic_total >= critic_train, "bad sizes");
+    if (A == 0) return AVD_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    adam_polyak_kernel<<<dim3((unsigned)std::min<int64_t>((critic_total + 255) / 256, 64), A), 256, 0, st>>>(
+        critic, t_critic, critic_total, critic_grad, critic_gstride, critic_m, critic_v, critic_step, apply_mask, critic_train, critic_total,
+        critic_lr, beta1, beta2, eps, tau);
+    AVD_LAUNCH_OK();
+    adam_polyak_kernel<<<dim3((unsigned)std::min<int64_t>((actor_total + 255) / 256, 64), A), 256, 0, st>>>(
+        actor, t_actor, actor_total, actor_grad, actor_gstride, actor_m, actor_v, actor_step, apply_mask, actor_train, actor_total, actor_lr,
+        beta1, beta2, eps, tau);
+    AVD_LAUNCH_OK();
+    step_increment2_kernel<<<(A + 127) / 128, 128, 0, st>>>(actor_step, critic_step, apply_mask, A);
+    AVD_LAUNCH_OK();
+    return AVD_OK;
+}
+
 extern "C" int avd_polyak_update(float* target, const float* online, const uint8_t* apply_mask, int32_t A, int64_t n, float tau,
                                  void* stream) {
     AVD_REQUIRE(target && online, "null buffer");
@@ -1143,12 +1207,10 @@ static int apply_local_updates(const avd_learn_io* io, void* stream) {
     const ActorOff ao = actor_off(io->dims);
     const CriticOff co = critic_off(io->dims);
     const int A = io->A;
-    AVD_TRY(avd_adam_apply(io->critic, co.total, io->critic_grad, co.n_train, io->critic_m, io->critic_v, io->critic_t, io->apply_mask,
-                           A, co.n_train, io->critic_lr, io->adam_beta1, io->adam_beta2, io->adam_eps, stream));
-    AVD_TRY(avd_adam_apply(io->actor, ao.total, io->actor_grad, ao.n_train, io->actor_m, io->actor_v, io->actor_t, io->apply_mask, A,
-                           ao.n_train, io->actor_lr, io->adam_beta1, io->adam_beta2, io->adam_eps, stream));
-    AVD_TRY(avd_polyak_update(io->t_critic, io->critic, io->apply_mask, A, co.total, io->tau, stream));
-    AVD_TRY(avd_polyak_update(io->t_actor, io->actor, io->apply_mask, A, ao.total, io->tau, stream));
+    AVD_TRY(avd_adam_polyak_apply2(io->actor, io->t_actor, ao.total, io->actor_grad, ao.n_train, io->actor_m, io->actor_v, io->actor_t, ao.n_train,
+                                   io->actor_lr, io->critic, io->t_critic, co.total, io->critic_grad, co.n_train, io->critic_m, io->critic_v,
+                                   io->critic_t, co.n_train, io->critic_lr, io->apply_mask, A, io->adam_beta1, io->adam_beta2, io->adam_eps,
+                                   io->tau, stream));
     return AVD_OK;
 }
 

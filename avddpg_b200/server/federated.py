@@ -219,8 +219,7 @@ class FederatedAggregator:
                                                self.n_systems, self.n_members, self.stride_s, self.stride_x, _lib.ptr(self.apply_mask),
                                                _lib.current_stream()))
         if apply:
-            pop.apply_gradients(self.apply_mask)
-            pop.soft_update(self.apply_mask)
+            pop.apply_gradients_and_soft_update(self.apply_mask)
         return buf
 
     def aggregate_weights(self, weights=None):

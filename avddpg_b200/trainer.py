@@ -115,6 +115,15 @@ class DDPGPopulation:
                                                _lib.ptr(bank.v), _lib.ptr(bank.step), _lib.ptr(apply_mask), self.A, bank.n_train,
                                                float(lr), 0.9, 0.999, 1e-7, _lib.current_stream()))
 
+    def apply_gradients_and_soft_update(self, apply_mask: Optional[torch.Tensor] = None):
+        """apply_gradients + soft_update in three launches (Adam and Polyak of a net share one pass over its weights)."""
+        conf, a, c = self.config, self.actor, self.critic
+        _lib.check(self.lib.avd_adam_polyak_apply2(
+            _lib.ptr(a.flat), _lib.ptr(self.t_actor.flat), a.total, _lib.ptr(a.grad), a.n_train, _lib.ptr(a.m), _lib.ptr(a.v), _lib.ptr(a.step),
+            a.n_train, float(conf.actor_lr), _lib.ptr(c.flat), _lib.ptr(self.t_critic.flat), c.total, _lib.ptr(c.grad), c.n_train, _lib.ptr(c.m),
+            _lib.ptr(c.v), _lib.ptr(c.step), c.n_train, float(conf.critic_lr), _lib.ptr(apply_mask), self.A, 0.9, 0.999, 1e-7, float(conf.tau),
+            _lib.current_stream()))
+
     def soft_update(self, apply_mask: Optional[torch.Tensor] = None):
         """ddpgagent.update_target + set_weights for every agent (trainer.py:352-356)."""
         for tgt, onl in ((self.t_critic, self.critic), (self.t_actor, self.actor)):

@@ -260,6 +260,15 @@ int avd_adam_apply(float* params, int64_t param_stride, const float* grads, int6
                    float* v, int32_t* step, const uint8_t* apply_mask, int32_t A, int64_t n, float lr, float beta1,
                    float beta2, float eps, void* stream);
 
+/* avd_adam_apply for both nets followed by avd_polyak_update of both targets (trainer.py:348-356), fused: one pass per net
+ * applies Adam to the trainable prefix and the Polyak update to ALL weights, then both step counters advance.  Per-agent
+ * gradient vectors have stride *_gstride (0 = one shared vector for every agent, as after FedAvg).                          */
+int avd_adam_polyak_apply2(float* actor, float* t_actor, int64_t actor_total, const float* actor_grad, int64_t actor_gstride,
+                           float* actor_m, float* actor_v, int32_t* actor_step, int64_t actor_train, float actor_lr, float* critic,
+                           float* t_critic, int64_t critic_total, const float* critic_grad, int64_t critic_gstride, float* critic_m,
+                           float* critic_v, int32_t* critic_step, int64_t critic_train, float critic_lr, const uint8_t* apply_mask,
+                           int32_t A, float beta1, float beta2, float eps, float tau, void* stream);
+
 /* ddpgagent.update_target (agent/ddpgagent.py:44-55): target = tau*online + (1-tau)*target over n floats
  * per agent (ALL weights incl. BN statistics).                                                          */
 int avd_polyak_update(float* target, const float* online, const uint8_t* apply_mask, int32_t A, int64_t n, float tau,
