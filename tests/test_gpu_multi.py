@@ -27,7 +27,7 @@ def _worker(rank, world, port, q):
     from avddpg_b200.server.federated import FederatedAggregator
     from avddpg_b200.trainer import DDPGPopulation
     conf = Config(pl_size=2, fed_method="interfrl", weighted_average_enabled=False)
-    G_total, M = 4, 2
+    G_total, M = 2 * world, 2
     G = G_total // world
     pop = DDPGPopulation(G, M, conf)
     gen = torch.Generator(device="cuda").manual_seed(123)
@@ -69,13 +69,19 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
+def _world_sizes():
+    n = torch.cuda.device_count() if torch.cuda.is_available() else 0
+    return [w for w in (2, 4, 8) if w <= n] or [2]
+
+
 @pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_interfrl_nccl_and_sharded_env_world2():
+@pytest.mark.parametrize("world", _world_sizes())
+def test_interfrl_transports_and_sharded_env(world):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
     res = sorted([q.get(timeout=300) for _ in procs], key=lambda t: t[0])
@@ -93,4 +99,4 @@ def test_interfrl_nccl_and_sharded_env_world2():
         env.action_mu.zero_()
         env.step_native(explore=True, gen_exog=True)
     full = env.state.cpu().numpy()
-    assert np.array_equal(np.concatenate([res[0][3], res[1][3]], axis=0), full)
+    assert np.array_equal(np.concatenate([r[3] for r in res], axis=0), full)
