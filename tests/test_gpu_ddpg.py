@@ -511,3 +511,32 @@ def test_learn_edge_cases_and_errors(mods):
     with pytest.raises(ValueError):
         pop.learn(s[:10], a, a, s)                                                # shape mismatch caught on the host side
     torch.cuda.synchronize()
+
+
+def test_learn_full_size_batch_additivity(mods):
+    """Size-independent property at the BASELINE C2 size (262,144 rows per agent-update): every loss is a MEAN over the rows, so
+    the gradient of the full batch equals the average of the gradients of its two halves, and the losses average the same way.
+    The three learn calls tile the rows differently across the persistent CTAs (55 vs. 28 tiles per CTA)."""
+    conf = mods["Config"]()
+    R = 262_144
+    pop = mods["trainer"].DDPGPopulation(1, 1, conf, rows_per_agent=R, precision=1)
+    pop.t_actor.flat.copy_(pop.actor.flat * 1.01)
+    pop.t_critic.flat.copy_(pop.critic.flat * 0.99)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    s = torch.randn(R, 4, device="cuda", generator=g) * 2
+    a = torch.rand(R, device="cuda", generator=g) * 5 - 2.5
+    r = -torch.rand(R, device="cuda", generator=g) * 0.5
+    s2 = s + 0.1 * torch.randn(R, 4, device="cuda", generator=g)
+
+    def run(lo, hi):
+        pop.learn(s[lo:hi].contiguous(), a[lo:hi].contiguous(), r[lo:hi].contiguous(), s2[lo:hi].contiguous(), apply_updates=False,
+                  rows_per_agent=hi - lo)
+        return pop.critic.grad.clone(), pop.actor.grad.clone(), pop.loss.clone()
+
+    cf, af, lf = run(0, R)
+    c1, a1, l1 = run(0, R // 2)
+    c2, a2, l2 = run(R // 2, R)
+    for full, h1, h2 in ((cf, c1, c2), (af, a1, a2), (lf, l1, l2)):
+        want = 0.5 * (h1 + h2)
+        err = float((full - want).norm() / want.norm())
+        assert err < 2e-3, err          # fp32 accumulation order only: both sides carry the same bf16 operand rounding
