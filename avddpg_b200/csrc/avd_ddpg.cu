@@ -37,8 +37,9 @@ int run(int mode, const avd_net_dims& d, int A, int64_t R, const float* params, 
 }
 
 namespace wgrad3 {  // avd_wgrad3.cu
+int ctas_per_agent(int A, int64_t R);
 int run(const avd_net_dims& d, bool critic, int A, int64_t R, const float* params, int64_t pstride, const float* s, const float* act, const bf16* DZ,
-        float* grads, int64_t gstride, int64_t oW2, cudaStream_t st);
+        float* out, int64_t out_agent_stride, int64_t out_cta_stride, cudaStream_t st);
 }
 
 namespace dgrad3 {  // avd_dgrad3.cu
@@ -707,8 +708,8 @@ __global__ void __launch_bounds__(256) xext_kernel(const float* __restrict__ s, 
 }
 
 // Unfold the gradients of the BN-folded formulation into the Keras trainable tensors (one warp per layer-1 feature f).
-// In:  G[oW2 + f*l2 + j] = G2[f][j] = sum_n r1[n][f] dz2[n][j]   (wgrad GEMM),  G[ob2 + j] = db2[j]  (head-backward kernel),
-//      G1[f][16] (layer-1 weight-gradient GEMM, see xext_kernel).
+// In:  G2[f][j] = sum_n r1[n][f] dz2[n][j] and G1[f][16] as `ncta` partial slices per agent (one per persistent CTA of the
+//      wgrad / dgrad kernels, summed here),  G[ob2 + j] = db2[j]  (dgrad kernel).
 // Out: dW2[f][j] = sc1[f] G2[f][j] + sh1[f] db2[j];   dsh1[f] = sum_j W2[f][j] db2[j];   dsc1[f] = sum_j W2[f][j] G2[f][j];
 //      dbeta1 = dsh1;   dgamma1 = inv1 (dsc1 - mu1 dsh1);   dW1 / db1 from G1.          (trainer.py:498, 506; model.py:19-33, 62-77)
 struct UnfoldOff {
@@ -717,11 +718,30 @@ struct UnfoldOff {
 };
 
 __global__ void __launch_bounds__(256) unfold_kernel(const float* __restrict__ params, int64_t pstride, float* __restrict__ grads, int64_t gstride,
-                                                     const float* __restrict__ G1, UnfoldOff o, int F, int Fp, int l2, int ns) {
+                                                     const float* __restrict__ G2, int64_t g2_agent_stride, int64_t g2_cta_stride,
+                                                     const float* __restrict__ G1, int ncta, UnfoldOff o, int F, int Fp, int l2, int ns) {
+    // one CTA per (feature f, agent); its 8 warps split the partial slices between them (slice w, w + 8, ...) so that every
+    // load is independent and 64 warps per SM hide the L2 / HBM latency, then combine through shared memory
     const int agent = blockIdx.y;
-    const int f = blockIdx.x * 8 + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (f >= F) return;
+    const int f = blockIdx.x;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    __shared__ float red[8][128 + 16];
+    const float* g2row = G2 + (int64_t)agent * g2_agent_stride + (int64_t)f * l2;
+    const float* g1row = G1 + ((int64_t)agent * ncta * Fp + f) * 16;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f}, acc1 = 0.0f;
+    for (int sl = wid; sl < ncta; sl += 8) {
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+            const int j = lane + 32 * jj;
+            if (j < l2) acc[jj] += __ldg(g2row + (int64_t)sl * g2_cta_stride + j);
+        }
+        if (lane < 16) acc1 += __ldg(g1row + (int64_t)sl * Fp * 16 + lane);
+    }
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) red[wid][lane + 32 * jj] = acc[jj];
+    if (lane < 16) red[wid][128 + lane] = acc1;
+    __syncthreads();
+    if (wid != 0) return;
     const float* P = params + (int64_t)agent * pstride;
     float* G = grads + (int64_t)agent * gstride;
     const bool st = f < o.f.l1;
@@ -732,19 +752,33 @@ __global__ void __launch_bounds__(256) unfold_kernel(const float* __restrict__ p
     const float mu = P[(st ? o.f.mu[0] : o.f.mu[1]) + c];
     const float sh = P[obe + c] - mu * sc;
     float dsc = 0.0f, dsh = 0.0f;
-    for (int j = lane; j < l2; j += 32) {
-        const int64_t i = o.f.W2 + (int64_t)f * l2 + j;
-        const float g2 = G[i], w = P[i], db2 = G[o.f.b2 + j];
-        dsc = fmaf(w, g2, dsc);
-        dsh = fmaf(w, db2, dsh);
-        G[i] = fmaf(sc, g2, sh * db2);
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+        const int j = lane + 32 * jj;
+        if (j < l2) {
+            float g2 = 0.0f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) g2 += red[w][j];
+            const int64_t i = o.f.W2 + (int64_t)f * l2 + j;
+            const float w2 = P[i], db2 = G[o.f.b2 + j];
+            dsc = fmaf(w2, g2, dsc);
+            dsh = fmaf(w2, db2, dsh);
+            G[i] = fmaf(sc, g2, sh * db2);
+        }
     }
     dsc = warp_sum(dsc);
     dsh = warp_sum(dsh);
+    float g1k = 0.0f;
+    if (lane < 16) {
+#pragma unroll
+        for (int w = 0; w < 8; ++w) g1k += red[w][128 + lane];
+    }
+    float g1[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) g1[k] = __shfl_sync(0xffffffffu, g1k, k);
     if (lane == 0) {
         G[obe + c] = dsh;
         G[og + c] = inv * (dsc - mu * dsh);
-        const float* g1 = G1 + ((int64_t)agent * Fp + f) * 16;
         G[ob1 + c] = g1[5];
         if (st) {
             for (int x = 0; x < ns && x < 4; ++x) G[o.W1[0] + (int64_t)x * o.f.l1 + c] = g1[x] + g1[8 + x];
@@ -784,15 +818,17 @@ struct Workspace {
     // BN-folded tensor-core path: sign masks of z1, [x_hi | 1 | x_lo] operand, layer-1 weight-gradient accumulator, folded biases
     uint32_t* mask;
     bf16* xextT;               // [A][16][Rp], Rp = R rounded up to 64
-    float *G1, *c_b2f, *tc_b2f, *a_b2f, *ta_b2f;
+    float *G1, *G2part, *c_b2f, *tc_b2f, *a_b2f, *ta_b2f;     // G1 / G2part: one partial slice per persistent CTA (<= max(A, #SMs) slices)
     float *U, *sdq;            // [2][A][l2], [2][A]: head-gradient sums of the critic [0] and actor [1] backward passes
-    static constexpr int kMaskWords = 10, kFp = 320;
+    static constexpr int kMaskWords = 10, kFp = 320, kG2Rows = 384;
     static int64_t bytes(const avd_net_dims& d, int64_t A, int64_t N) {
         const int64_t F = d.l1 + d.la;
         const int64_t acts = N * (2 * F + d.l1 + 3 * (int64_t)d.l2) * (int64_t)sizeof(float);
         const int64_t packed = A * (3 * F + 3 * (int64_t)d.l1) * d.l2 * (int64_t)sizeof(bf16);
         const int64_t vecs = 4 * ((N + 3) / 4 * 4) * (int64_t)sizeof(float);
-        const int64_t fold = N * (kMaskWords * 4 + 16 * 2) + A * (kFp * 16 + 6 * (int64_t)d.l2 + 8) * (int64_t)sizeof(float) + A * 16 * 64 * 2;
+        const int64_t slices = std::max<int64_t>(A, sm_count());
+        const int64_t fold = N * (kMaskWords * 4 + 16 * 2) + A * (6 * (int64_t)d.l2 + 8) * (int64_t)sizeof(float) + A * 16 * 64 * 2 +
+                             slices * (kFp * 16 + kG2Rows * (int64_t)d.l2) * (int64_t)sizeof(float);
         return acts + packed + vecs + fold + 1024;
     }
     void carve(void* base_, const avd_net_dims& d, int64_t A, int64_t N) {
@@ -817,7 +853,9 @@ struct Workspace {
         y = p; p += Np;
         q = p; p += Np;
         dpi = p; p += Np;
-        G1 = p; p += A * kFp * 16;
+        const int64_t slices = std::max<int64_t>(A, sm_count());
+        G1 = p; p += slices * kFp * 16;
+        G2part = p; p += slices * kG2Rows * d.l2;
         c_b2f = p; p += A * d.l2;
         tc_b2f = p; p += A * d.l2;
         a_b2f = p; p += A * d.l2;
@@ -941,27 +979,25 @@ struct Pass {
         return o;
     }
 
-    // fused dgrad + layer-1 weight gradient (avd_dgrad3.cu), then unfold
+    // fused dgrad + layer-1 weight gradient (avd_dgrad3.cu), then unfold.  G2part holds the partial G2 slices the wgrad kernel
+    // (avd_wgrad3.cu) stored before: [A][ncta][384][l2].
     int dgrad3_unfold(bool critic, const float* params, const bf16* DZ, const bf16* W2b, int F, int Fp, const uint32_t* mask, int mask_words,
-                      const bf16* xextT, float* G1, float* grads) const {
-        AVD_CUDA_OK(cudaMemsetAsync(G1, 0, (size_t)A * Fp * 16 * sizeof(float), st));
+                      const bf16* xextT, float* G1, const float* G2part, float* grads) const {
         const int64_t ob2 = critic ? critic_off(d).b2 : actor_off(d).b2, gs = critic ? critic_off(d).n_train : actor_off(d).n_train;
         if (int rc = dgrad3::run(A, R, F, DZ, W2b, mask, mask_words, xextT, (R + 63) / 64 * 64, G1, Fp, grads + ob2, gs, st)) return rc;
-        return unfold(critic, params, F, Fp, G1, grads);
-    }
-
-    int unfold(bool critic, const float* params, int F, int Fp, const float* G1, float* grads) const {
+        const int ncta = wgrad3::ctas_per_agent(A, R);
         UnfoldOff u;
         u.f = fold_off(critic);
-        int64_t ps, gs;
+        int64_t ps;
         if (critic) {
             const CriticOff c = critic_off(d);
-            u.W1[0] = c.Ws; u.b1[0] = c.bs; u.W1[1] = c.Wa; u.b1[1] = c.ba; ps = c.total; gs = c.n_train;
+            u.W1[0] = c.Ws; u.b1[0] = c.bs; u.W1[1] = c.Wa; u.b1[1] = c.ba; ps = c.total;
         } else {
             const ActorOff a = actor_off(d);
-            u.W1[0] = u.W1[1] = a.W1; u.b1[0] = u.b1[1] = a.b1; ps = a.total; gs = a.n_train;
+            u.W1[0] = u.W1[1] = a.W1; u.b1[0] = u.b1[1] = a.b1; ps = a.total;
         }
-        unfold_kernel<<<dim3((unsigned)((F + 7) / 8), A), 256, 0, st>>>(params, ps, grads, gs, G1, u, F, Fp, d.l2, d.ns);
+        unfold_kernel<<<dim3((unsigned)F, A), 256, 0, st>>>(params, ps, grads, gs, G2part, (int64_t)ncta * Workspace::kG2Rows * d.l2,
+                                                                        (int64_t)Workspace::kG2Rows * d.l2, G1, ncta, u, F, Fp, d.l2, d.ns);
         AVD_LAUNCH_OK();
         return AVD_OK;
     }
@@ -1252,10 +1288,12 @@ static int learn_fused3(const avd_learn_io* io, const Pass& p, const Workspace& 
     // ---- critic loss gradient on (s, a)                                             trainer.py:495-498
     AVD_TRY(fused3::run(fused3::MODE_CRITIC_BWD, d, A, R, io->critic, co.total, w.cW2T, w.c_b2f, io->s, d.ns, 1, io->a, nullptr, 0.f, 0.f, w.y,
                         nullptr, w.q, w.mask, DZ, Uc, w.sdq, io->loss, st));
-    AVD_TRY(wgrad3::run(d, true, A, R, io->critic, co.total, io->s, io->a, DZ, io->critic_grad, co.n_train, co.W2, st));
+    const int ncta = wgrad3::ctas_per_agent(A, R);
+    const int64_t g2_cta = (int64_t)Workspace::kG2Rows * d.l2, g2_agent = (int64_t)ncta * g2_cta;
+    AVD_TRY(wgrad3::run(d, true, A, R, io->critic, co.total, io->s, io->a, DZ, w.G2part, g2_agent, g2_cta, st));
     head_unfold(true, io->critic, io->critic_grad, Uc, w.sdq);
     AVD_LAUNCH_OK();
-    AVD_TRY(p.dgrad3_unfold(true, io->critic, DZ, w.cW2b, F, Fp, w.mask, MW, w.xextT, w.G1, io->critic_grad));
+    AVD_TRY(p.dgrad3_unfold(true, io->critic, DZ, w.cW2b, F, Fp, w.mask, MW, w.xextT, w.G1, w.G2part, io->critic_grad));
     // ---- actor loss gradient: -mean(critic(s, actor(s)))                            trainer.py:501-506
     AVD_TRY(fused3::run(fused3::MODE_ACTOR_OUT, d, A, R, io->actor, ao.total, w.aW2T, w.a_b2f, io->s, d.ns, 1, nullptr, nullptr, 0.f, io->action_high,
                         nullptr, nullptr, w.a2, nullptr, nullptr, nullptr, nullptr, nullptr, st));   // pi
@@ -1263,10 +1301,10 @@ static int learn_fused3(const avd_learn_io* io, const Pass& p, const Workspace& 
                         nullptr, w.dpi, nullptr, nullptr, nullptr, nullptr, io->loss, st));          // d(-mean q)/d pi
     AVD_TRY(fused3::run(fused3::MODE_ACTOR_BWD, d, A, R, io->actor, ao.total, w.aW2T, w.a_b2f, io->s, d.ns, 1, nullptr, nullptr, 0.f, io->action_high,
                         nullptr, w.dpi, nullptr, w.mask, DZ, Ua, w.sdq + A, nullptr, st));
-    AVD_TRY(wgrad3::run(d, false, A, R, io->actor, ao.total, io->s, nullptr, DZ, io->actor_grad, ao.n_train, ao.W2, st));
+    AVD_TRY(wgrad3::run(d, false, A, R, io->actor, ao.total, io->s, nullptr, DZ, w.G2part, g2_agent, g2_cta, st));
     head_unfold(false, io->actor, io->actor_grad, Ua, w.sdq + A);
     AVD_LAUNCH_OK();
-    AVD_TRY(p.dgrad3_unfold(false, io->actor, DZ, w.aW2b, d.l1, Fp, w.mask, 8, w.xextT, w.G1, io->actor_grad));
+    AVD_TRY(p.dgrad3_unfold(false, io->actor, DZ, w.aW2b, d.l1, Fp, w.mask, 8, w.xextT, w.G1, w.G2part, io->actor_grad));
     return apply_local_updates(io, (void*)st);
 }
 

@@ -46,7 +46,7 @@ struct Args {
     int64_t R;
     const uint32_t* mask;       // [A*R][mask_words]
     int mask_words;
-    float* G1;                  // [A][Fp][16] +=
+    float* G1;                  // partial slice of CTA (agent, cta): G1 + (agent*ctas_per_agent + cta)*Fp*16, [Fp][16]
     int Fp;
     float* db2;                 // [A][db2_stride] += sum_n dz2[n][j]   (layer-2 bias gradient)
     int64_t db2_stride;
@@ -253,10 +253,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dgrad3_kernel(const __grid_con
                 float v[16];
                 tmem_ld16(tmem_base + 384u + (uint32_t)(p * 16) + tlane, v);
                 const int f = p * 128 + row;
-                if (f < g.F) {
-                    float* dst = g.G1 + ((int64_t)agent * g.Fp + f) * 16;
+                if (f < g.F) {           // plain stores into this CTA's slice (summed by the unfold kernel)
+                    float* dst = g.G1 + (((int64_t)agent * g.ctas_per_agent + cta) * g.Fp + f) * 16;
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) atomicAdd(dst + j, v[j]);
+                    for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                 }
             }
             tc_fence_before();
@@ -311,8 +311,8 @@ static int make_map(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t 
 }
 
 // DZ: bf16 [A*R][128];  W2b: bf16 [A][F][128] folded layer-2 kernel;  mask: [A*R][mask_words];  xextT: bf16 [A][16][Rp]
-// (Rp = rows per agent rounded up to a multiple of 64);  G1: fp32 [A][Fp][16] and db2: fp32 [A][db2_stride] (first 128 entries),
-// both accumulated into (zero them first).
+// (Rp = rows per agent rounded up to a multiple of 64);  G1: fp32 [A][ctas_per_agent][Fp][16] partial slices, one per CTA, plain
+// stores (rows < F; the caller sums them);  db2: fp32 [A][db2_stride] (first 128 entries), accumulated into (zero it first).
 int run(int A, int64_t R, int F, const bf16* DZ, const bf16* W2b, const uint32_t* mask, int mask_words, const bf16* xextT, int64_t Rp, float* G1,
         int Fp, float* db2, int64_t db2_stride, cudaStream_t st) {
     AVD_REQUIRE(A >= 1 && R >= 1 && F >= 64 && F % 16 == 0 && F <= MAX_NC * 64 && Fp >= F, "bad sizes for the fused dgrad kernel");
@@ -329,7 +329,7 @@ int run(int A, int64_t R, int F, const bf16* DZ, const bf16* W2b, const uint32_t
     Args g;
     g.A = A; g.F = F; g.NC = (F + 63) / 64; g.R = R; g.mask = mask; g.mask_words = mask_words; g.G1 = G1; g.Fp = Fp; g.db2 = db2; g.db2_stride = db2_stride;
     g.tiles_per_agent = (int)((R + TILE_M - 1) / TILE_M);
-    g.ctas_per_agent = std::max(1, std::min(g.tiles_per_agent, sm_count() / std::max(1, A)));
+    g.ctas_per_agent = std::max(1, std::min(g.tiles_per_agent, sm_count() / std::max(1, A)));      // == wgrad3::ctas_per_agent(A, R)
     dgrad3_kernel<<<(unsigned)(g.ctas_per_agent * A), NUM_THREADS, SMEM_BYTES, st>>>(tmW, tmDZ, tmXT, g);
     AVD_LAUNCH_OK();
     return AVD_OK;

@@ -6,8 +6,8 @@
 // loads a 128-row dz2 tile ONCE (TMA) and walks the 128-feature slabs of the layer:
 //   x tile --tcgen05.mma (hi/lo split bf16, K = 16)--> z1 slab in TMEM --converter warps: relu, bf16--> r1 slab in shared
 //   memory, laid out as the MN-major A operand (M = features, K = rows) --tcgen05.mma against the dz2 tile (MN-major B)-->
-//   one 128 x 128 fp32 accumulator per slab; the 2-3 accumulators stay in TMEM for the whole kernel and are added to global
-//   memory once per CTA.
+//   one 128 x 128 fp32 accumulator per slab; the 2-3 accumulators stay in TMEM for the whole kernel and are stored to the
+//   CTA's own partial slice once at the end (the unfold kernel adds the slices up).
 // HBM traffic per row: 256 B (dz2) + 16-20 B inputs; nothing is written.
 // The action-branch slab of the critic (one input per feature, model.py:69-70) is converted on the CUDA cores.
 // Reference: workers/trainer.py:498, 506 (tape.gradient) through agent/model.py:19-33, 62-77.
@@ -50,8 +50,8 @@ struct Args {
     int64_t pstride;
     const float* s;             // [A*R][ns]
     const float* act;           // [A*R] (critic)
-    float* grads;               // [A][gstride]; G2 is accumulated at grads + oW2 (row-major [F][128])
-    int64_t gstride, oW2;
+    float* out;                 // G2 slice of CTA (agent, cta): out + agent*out_agent_stride + cta*out_cta_stride, row-major [F][128]
+    int64_t out_agent_stride, out_cta_stride;
     int tiles_per_agent, ctas_per_agent;
 };
 
@@ -285,12 +285,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad3_kernel(const __grid_con
             tc_fence_after();
             for (int sl = 0; sl < FT; ++sl) {
                 const int nfeat = sl < 2 ? SLAB : d.la;
-                float* dst = g.grads + (int64_t)agent * g.gstride + g.oW2 + (int64_t)(sl * SLAB + row) * L2N + qtr * 32;
+                float* dst = g.out + (int64_t)agent * g.out_agent_stride + (int64_t)cta * g.out_cta_stride + (int64_t)(sl * SLAB + row) * L2N + qtr * 32;
                 float v[32];
                 tmem_ld32(tmem_base + (uint32_t)(sl * SLAB + qtr * 32) + tlane, v);
-                if (row < nfeat) {
+                if (row < nfeat) {       // plain 16-byte stores: every CTA owns its slice, the unfold kernel adds the slices up
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) atomicAdd(dst + j, v[j]);
+                    for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                 }
             }
             tc_fence_before();
@@ -315,11 +315,20 @@ static PFN_cuTensorMapEncodeTiled encode_fn() {
     return fn;
 }
 
-// grads + oW2: row-major [F][128] fp32 per agent, accumulated into (zero it first).  DZ: bf16 [A*R][128].
+// Persistent CTAs per agent for R rows (shared with the dgrad kernel so that both produce the same number of partial slices)
+int ctas_per_agent(int A, int64_t R) {
+    const int tiles = (int)((R + TILE_M - 1) / TILE_M);
+    return std::max(1, std::min(tiles, sm_count() / std::max(1, A)));
+}
+
+// out: every CTA (agent, cta) stores its partial G2 (row-major [F][128] fp32, rows < F) at out + agent*out_agent_stride +
+// cta*out_cta_stride -- no atomics: the 37 x 4 CTAs of the C2 case would otherwise serialise 7 M atomic adds on 160 k
+// addresses (a quarter of the kernel time).  The caller sums the ctas_per_agent(A, R) slices.  DZ: bf16 [A*R][128].
 int run(const avd_net_dims& d, bool critic, int A, int64_t R, const float* params, int64_t pstride, const float* s, const float* act, const bf16* DZ,
-        float* grads, int64_t gstride, int64_t oW2, cudaStream_t st) {
+        float* out, int64_t out_agent_stride, int64_t out_cta_stride, cudaStream_t st) {
     AVD_REQUIRE(d.l1 == 256 && d.l2 == L2N && d.ns >= 1 && d.ns <= 4 && (!critic || (d.la >= 8 && d.la <= 64)), "unsupported layer sizes for the fused wgrad kernel");
-    AVD_REQUIRE(params && s && DZ && grads && (!critic || act), "null buffer");
+    AVD_REQUIRE(params && s && DZ && out && (!critic || act), "null buffer");
+    AVD_REQUIRE(out_agent_stride % 4 == 0 && out_cta_stride % 4 == 0 && ((uintptr_t)out & 15) == 0, "partial G2 slices must be 16-byte aligned");
     PFN_cuTensorMapEncodeTiled enc = encode_fn();
     if (!enc) {
         set_error("cuTensorMapEncodeTiled is not available from the driver");
@@ -343,9 +352,9 @@ int run(const avd_net_dims& d, bool critic, int A, int64_t R, const float* param
     }
     Args g;
     g.d = d; g.critic = critic ? 1 : 0; g.A = A; g.FT = critic ? 3 : 2; g.R = R; g.params = params; g.pstride = pstride; g.s = s; g.act = act;
-    g.grads = grads; g.gstride = gstride; g.oW2 = oW2;
+    g.out = out; g.out_agent_stride = out_agent_stride; g.out_cta_stride = out_cta_stride;
     g.tiles_per_agent = (int)((R + TILE_M - 1) / TILE_M);
-    g.ctas_per_agent = std::max(1, std::min(g.tiles_per_agent, sm_count() / std::max(1, A)));
+    g.ctas_per_agent = ctas_per_agent(A, R);
     wgrad3_kernel<<<(unsigned)(A * g.ctas_per_agent), NUM_THREADS, SMEM_BYTES, st>>>(tm, g);
     AVD_LAUNCH_OK();
     return AVD_OK;
