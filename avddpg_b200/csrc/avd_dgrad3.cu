@@ -11,8 +11,7 @@
 // Math: dR = dz2 W2'^T with W2' = diag(sc1) W2 (BatchNorm folded, pack_fold_kernel), dz1 = dR [z1 > 0]
 // (workers/trainer.py:498, 506 through agent/model.py:19-33, 62-77).
 //
-// Warps: 0 MMA issuer, 1 TMA producer, 2..17 epilogue (TMEM lane quadrant = warp % 4; four quarters of four warps, two
-// quarters per chunk pair).  TMEM: 3-slot ring of 128-column dR chunk pairs + 3 x 16 columns of G1 + 16 columns of
+// Warps: 0 MMA issuer, 1 TMA producer, 2..17 epilogue (TMEM lane quadrant = warp % 4, 32 of a chunk pair's 128 columns each).  TMEM: 3-slot ring of 128-column dR chunk pairs + 3 x 16 columns of G1 + 16 columns of
 // dz2^T xext, whose column 5 (xext's constant one) is the layer-2 bias gradient db2.
 #include <cudaTypedefs.h>
 
@@ -58,6 +57,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&v);
 }
 
+template <int NC>      // 64-feature chunks of layer 1: 4 (actor, 256 features) or 5 (critic, 256 + action features)
 __global__ void __launch_bounds__(NUM_THREADS, 1) dgrad3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmDZ,
                                                                 const __grid_constant__ CUtensorMap tmXT, Args g) {
     extern __shared__ uint8_t smem_raw[];
@@ -78,13 +78,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dgrad3_kernel(const __grid_con
     const int agent = (int)blockIdx.x / g.ctas_per_agent;
     const int cta = (int)blockIdx.x - agent * g.ctas_per_agent;
     const int T = (g.tiles_per_agent - cta + g.ctas_per_agent - 1) / g.ctas_per_agent;
-    const int NC = g.NC, NP = (NC + 1) >> 1;           // 64-feature chunks, chunk pairs (the last pair of the critic has one chunk)
+    constexpr int NP = (NC + 1) >> 1;                  // chunk pairs (the last pair of the critic has one chunk)
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmW); tma_prefetch_desc(&tmDZ); tma_prefetch_desc(&tmXT);
-        for (int i = 0; i < NRING; ++i) { mbar_init(&d_full[i], 1); mbar_init(&d_empty[i], 8); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&st_full[i], 8); mbar_init(&st_empty[i], 1); mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 8); }
-        for (int i = 0; i < NXT; ++i) { mbar_init(&xt_full[i], 1); mbar_init(&xt_empty[i], 8); }
+        for (int i = 0; i < NRING; ++i) { mbar_init(&d_full[i], 1); mbar_init(&d_empty[i], 16); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&st_full[i], 16); mbar_init(&st_empty[i], 1); mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 16); }
+        for (int i = 0; i < NXT; ++i) { mbar_init(&xt_full[i], 1); mbar_init(&xt_empty[i], 16); }
         mbar_init(w_full, 1);
         mbar_init(g1_done, 1);
         fence_barrier_init();
@@ -95,8 +95,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dgrad3_kernel(const __grid_con
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     auto tile_of = [&](int tc) { return cta + tc * g.ctas_per_agent; };
-    // Chunk pair p of local tile t has the running index pk = t NP + p: TMEM ring slot pk % 3 (128 columns), staging buffer
-    // pk & 1, epilogue quarters 2 (pk & 1) and 2 (pk & 1) + 1 (one 64-column chunk each).
+    // Chunk pair p of local tile t has the running index pk = t NP + p: TMEM ring slot pk % 3 (128 columns), staging buffer pk & 1.
 
     if (warp == 0) {
         // ================================================ MMA issuer ================================================
@@ -151,10 +150,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dgrad3_kernel(const __grid_con
                 mma_commit_p(leader, &st_empty[sb]);
             };
             mbar_wait(w_full, 0);
+#pragma unroll
             for (int p = 0; p < NP; ++p) mma_pair(0, p);
             // steady state: the pair MMAs of tile t + 1 are interleaved with the G1 MMAs of tile t, so that a staging buffer is
             // handed back as early as possible (every wait only depends on work issued earlier)
             for (int t = 0; t < T; ++t) {
+#pragma unroll
                 for (int p = 0; p < NP; ++p) {
                     if (t + 1 < T) mma_pair(t + 1, p);
                     g1_pair(t, p);
@@ -186,29 +187,33 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dgrad3_kernel(const __grid_con
         }
     } else {
         // ================================================== epilogue ==================================================
-        const int q = warp & 3, grp = (warp - 2) >> 2;
-        const int h = grp & 1;               // which 64-column chunk of a pair this quarter takes
+        // All 16 warps work on the SAME chunk pair: TMEM lane quadrant q, 32-column quarter c4 of the pair's 128 columns.  One
+        // warp alone issues a dependent instruction only every few cycles, so short per-thread streams (32 columns) and many
+        // warps per pair matter more than keeping several pairs in flight.
+        const int q = warp & 3, c4 = (warp - 2) >> 2;
         const int row = q * 32 + lane;
         const uint32_t tlane = (uint32_t)(q * 32) << 16;
-        // The sign masks of a chunk are fetched while the PREVIOUS pair of this quarter is processed (pairs pk, pk + 2, ...):
-        // a load issued right before its use would put a full global-memory latency on every chunk of the pipeline.
-        auto load_mask = [&](uint32_t pk) -> uint2 {
-            const int t = (int)(pk / (uint32_t)NP), c = 2 * (int)(pk - (uint32_t)t * NP) + h;
-            if (t >= T || c >= NC) return make_uint2(0u, 0u);
+        // The sign mask word of the next pair is fetched while the current pair is processed (a load issued right before its use
+        // would put a full global-memory latency on every pair), from a per-tile row pointer: the epilogue warps are bound by
+        // instruction issue, so the per-pair bookkeeping is kept to a handful of instructions.
+        auto mask_row = [&](int t) -> const uint32_t* {
             const int64_t r_in = (int64_t)tile_of(t) * TILE_M + row;
             const int64_t nrow = (int64_t)agent * g.R + (r_in < g.R ? r_in : g.R - 1);
-            return __ldg(reinterpret_cast<const uint2*>(g.mask + nrow * g.mask_words + 2 * c));
+            return g.mask + nrow * g.mask_words + c4;           // word 4 p + c4 of the row = columns 128 p + 32 c4 ..
         };
-        uint2 neg_next = load_mask((uint32_t)(grp >> 1));
+        const uint32_t* mrow = T > 0 ? mask_row(0) : g.mask;
+        uint32_t neg_next = T > 0 ? __ldg(mrow) : 0u;
+        uint32_t rs = 0, rph = 0, pk = 0;                        // TMEM ring slot and its phase, running pair index
         for (int t = 0; t < T; ++t) {
+            const uint32_t* mrow_next = t + 1 < T ? mask_row(t + 1) : mrow;
+#pragma unroll
             for (int p = 0; p < NP; ++p) {
-                const uint32_t pk = (uint32_t)(t * NP + p);
-                if ((int)(pk & 1) != (grp >> 1)) continue;
-                const uint32_t rs = pk % NRING, sb = pk & 1;
-                const bool work = 2 * p + h < NC;        // the partner quarter of a lone last chunk only keeps the barrier counts
-                const uint2 neg = neg_next;
-                neg_next = load_mask(pk + 2);
-                mbar_wait(&d_full[rs], (pk / NRING) & 1);
+                const uint32_t sb = pk & 1;
+                const bool work = 2 * p + (c4 >> 1) < NC;        // the second chunk of a lone last pair does not exist
+                const uint32_t neg = neg_next;
+                if (p + 1 < NP) neg_next = (2 * (p + 1) + (c4 >> 1) < NC) ? __ldg(mrow + 4 * (p + 1)) : 0u;
+                else neg_next = __ldg(mrow_next);
+                mbar_wait(&d_full[rs], rph);
                 tc_fence_after();
                 if (p == NP - 1 && lane == 0) {
                     // every MMA issued before this tile's last pair has completed: the dz2 tile of tile t (read by its pair and db2
@@ -216,39 +221,41 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dgrad3_kernel(const __grid_con
                     mbar_arrive(&a_empty[t & 1]);
                     if (t >= 2) mbar_arrive(&xt_empty[(t - 2) % NXT]);
                 }
-                uint32_t pkd[32];            // the masked chunk as bf16 pairs: the TMEM slot is released before the staging buffer is needed
+                uint32_t pkd[16];            // the masked quarter as bf16 pairs: the TMEM slot is released before the staging buffer is needed
                 if (work) {
+                    float v[32];
+                    tmem_ld32(tmem_base + rs * 128 + (uint32_t)(c4 * 32) + tlane, v);
 #pragma unroll
-                    for (int hh = 0; hh < 2; ++hh) {
-                        float v[32];
-                        tmem_ld32(tmem_base + rs * 128 + (uint32_t)(h * 64 + hh * 32) + tlane, v);
-                        const uint32_t m = hh ? neg.y : neg.x;
+                    for (int j = 0; j < 32; ++j)
+                        if (neg & (0x80000000u >> j)) v[j] = 0.0f;
 #pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (m & (0x80000000u >> j)) v[j] = 0.0f;
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) pkd[hh * 16 + j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
-                    }
+                    for (int j = 0; j < 16; ++j) pkd[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&d_empty[rs]);
                 mbar_wait(&st_empty[sb], ((pk >> 1) & 1) ^ 1);
                 if (work) {
-                    uint8_t* srow = smem + OFF_ST + sb * (2 * TILE_M * 128) + h * (TILE_M * 128) + row * 128;
+                    uint8_t* srow = smem + OFF_ST + sb * (2 * TILE_M * 128) + (c4 >> 1) * (TILE_M * 128) + row * 128;
 #pragma unroll
-                    for (int kk = 0; kk < 8; ++kk)
-                        *reinterpret_cast<uint4*>(srow + ((kk ^ (row & 7)) << 4)) = make_uint4(pkd[4 * kk], pkd[4 * kk + 1], pkd[4 * kk + 2], pkd[4 * kk + 3]);
+                    for (int kk = 0; kk < 4; ++kk)
+                        *reinterpret_cast<uint4*>(srow + ((((c4 & 1) * 4 + kk) ^ (row & 7)) << 4)) =
+                            make_uint4(pkd[4 * kk], pkd[4 * kk + 1], pkd[4 * kk + 2], pkd[4 * kk + 3]);
                     fence_proxy_async();
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&st_full[sb]);
+                ++pk;
+                if (++rs == NRING) { rs = 0; rph ^= 1; }
             }
+            mrow = mrow_next;
         }
+        const int grp = c4;
         // ---- G1 accumulators of this CTA -> global (features p*128 + row, 16 columns)
         if (grp == 0 && T > 0) {
             mbar_wait(g1_done, 0);
             tc_fence_after();
+#pragma unroll
             for (int p = 0; p < NP; ++p) {
                 float v[16];
                 tmem_ld16(tmem_base + 384u + (uint32_t)(p * 16) + tlane, v);
@@ -315,11 +322,12 @@ static int make_map(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t 
 // stores (rows < F; the caller sums them);  db2: fp32 [A][db2_stride] (first 128 entries), accumulated into (zero it first).
 int run(int A, int64_t R, int F, const bf16* DZ, const bf16* W2b, const uint32_t* mask, int mask_words, const bf16* xextT, int64_t Rp, float* G1,
         int Fp, float* db2, int64_t db2_stride, cudaStream_t st) {
-    AVD_REQUIRE(A >= 1 && R >= 1 && F >= 64 && F % 16 == 0 && F <= MAX_NC * 64 && Fp >= F, "bad sizes for the fused dgrad kernel");
+    AVD_REQUIRE(A >= 1 && R >= 1 && F > 192 && F % 16 == 0 && F <= MAX_NC * 64 && Fp >= F, "bad sizes for the fused dgrad kernel");
     AVD_REQUIRE(DZ && W2b && mask && xextT && G1 && db2 && Rp % 64 == 0 && Rp >= R, "null buffer / bad pitch");
     static bool attr_set = false;
     if (!attr_set) {
-        AVD_CUDA_OK(cudaFuncSetAttribute(dgrad3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        AVD_CUDA_OK(cudaFuncSetAttribute(dgrad3_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        AVD_CUDA_OK(cudaFuncSetAttribute(dgrad3_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         attr_set = true;
     }
     CUtensorMap tmW, tmDZ, tmXT;
@@ -330,7 +338,9 @@ int run(int A, int64_t R, int F, const bf16* DZ, const bf16* W2b, const uint32_t
     g.A = A; g.F = F; g.NC = (F + 63) / 64; g.R = R; g.mask = mask; g.mask_words = mask_words; g.G1 = G1; g.Fp = Fp; g.db2 = db2; g.db2_stride = db2_stride;
     g.tiles_per_agent = (int)((R + TILE_M - 1) / TILE_M);
     g.ctas_per_agent = std::max(1, std::min(g.tiles_per_agent, sm_count() / std::max(1, A)));      // == wgrad3::ctas_per_agent(A, R)
-    dgrad3_kernel<<<(unsigned)(g.ctas_per_agent * A), NUM_THREADS, SMEM_BYTES, st>>>(tmW, tmDZ, tmXT, g);
+    const unsigned grid = (unsigned)(g.ctas_per_agent * A);
+    if (g.NC == 4) dgrad3_kernel<4><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmW, tmDZ, tmXT, g);
+    else dgrad3_kernel<5><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmW, tmDZ, tmXT, g);
     AVD_LAUNCH_OK();
     return AVD_OK;
 }
