@@ -17,6 +17,8 @@
 // BatchNormalization is always the inference affine (models are never called with training=True):
 //   y = g*(x-mu)/sqrt(var+1e-3)+be, with trainable g/be and frozen mu/var.
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 
 #include <cuda_bf16.h>
 
@@ -1254,7 +1256,45 @@ static int apply_local_updates(const avd_learn_io* io, void* stream) {
 // both head backwards and the critic -> actor link; per differentiated net only dz2 (256 B per row) and the ReLU sign masks
 // (40 B) go to HBM, for the layer-2 weight gradient (avd_wgrad3.cu, recomputes r1 on chip) and the fused dgrad + layer-1
 // weight gradient + layer-2 bias gradient (avd_dgrad3.cu).
+// Diagnostic: AVD_STAGE_TIMES=1 brackets every stage of the tensor-core learn step with CUDA events and prints the durations
+// at real clocks (ncu's per-launch times are taken with idle clocks and cold caches).  Synchronises: never set it in a bench.
+struct StageTimer {
+    bool on;
+    cudaStream_t st;
+    int n = 0;
+    const char* names[32];
+    cudaEvent_t ev[32];
+    explicit StageTimer(cudaStream_t s) : st(s) {
+        static const bool enabled = getenv("AVD_STAGE_TIMES") != nullptr;
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing(s, &cs);
+        on = enabled && cs == cudaStreamCaptureStatusNone;
+        mark("start");
+    }
+    void mark(const char* name) {
+        if (!on || n >= 32) return;
+        cudaEventCreate(&ev[n]);
+        cudaEventRecord(ev[n], st);
+        names[n++] = name;
+    }
+    ~StageTimer() {
+        if (!on || n == 0) return;
+        cudaEventSynchronize(ev[n - 1]);
+        float total = 0.f;
+        cudaEventElapsedTime(&total, ev[0], ev[n - 1]);
+        fprintf(stderr, "[avd stage times] total %.1f us:", total * 1e3f);
+        for (int i = 1; i < n; ++i) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
+            fprintf(stderr, " %s=%.1f", names[i], ms * 1e3f);
+        }
+        fprintf(stderr, "\n");
+        for (int i = 0; i < n; ++i) cudaEventDestroy(ev[i]);
+    }
+};
+
 static int learn_fused3(const avd_learn_io* io, const Pass& p, const Workspace& w, cudaStream_t st) {
+    StageTimer tm(st);
     const avd_net_dims d = io->dims;
     const int A = io->A;
     const int64_t R = io->rows_per_agent, N = (int64_t)A * R;
@@ -1273,6 +1313,7 @@ static int learn_fused3(const avd_learn_io* io, const Pass& p, const Workspace& 
     xext_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(io->s, io->a, d.ns, N, w.xextT, R, Rp);
     AVD_LAUNCH_OK();
     AVD_CUDA_OK(cudaMemsetAsync(w.U, 0, (size_t)(2 * A * d.l2 + 2 * A) * sizeof(float), st));   // U and sdq are adjacent
+    tm.mark("fold+xext");
     auto head_unfold = [&](bool critic, const float* params, float* grads, const float* U, const float* sdq) {
         HeadOff o;
         int64_t ps, gs;
@@ -1283,29 +1324,41 @@ static int learn_fused3(const avd_learn_io* io, const Pass& p, const Workspace& 
     // ---- TD target: y = r + gamma * target_critic(s', target_actor(s'))            trainer.py:493-494
     AVD_TRY(fused3::run(fused3::MODE_ACTOR_OUT, d, A, R, io->t_actor, ao.total, w.taW2T, w.ta_b2f, io->s2, d.ns, 1, nullptr, nullptr, 0.f,
                         io->action_high, nullptr, nullptr, w.a2, nullptr, nullptr, nullptr, nullptr, nullptr, st));
+    tm.mark("t_actor");
     AVD_TRY(fused3::run(fused3::MODE_TARGET, d, A, R, io->t_critic, co.total, w.tcW2T, w.tc_b2f, io->s2, d.ns, 1, w.a2, io->r, io->gamma, 0.f,
                         nullptr, nullptr, w.y, nullptr, nullptr, nullptr, nullptr, nullptr, st));
+    tm.mark("t_critic");
     // ---- critic loss gradient on (s, a)                                             trainer.py:495-498
     AVD_TRY(fused3::run(fused3::MODE_CRITIC_BWD, d, A, R, io->critic, co.total, w.cW2T, w.c_b2f, io->s, d.ns, 1, io->a, nullptr, 0.f, 0.f, w.y,
                         nullptr, w.q, w.mask, DZ, Uc, w.sdq, io->loss, st));
+    tm.mark("critic_bwd");
     const int ncta = wgrad3::ctas_per_agent(A, R);
     const int64_t g2_cta = (int64_t)Workspace::kG2Rows * d.l2, g2_agent = (int64_t)ncta * g2_cta;
     AVD_TRY(wgrad3::run(d, true, A, R, io->critic, co.total, io->s, io->a, DZ, w.G2part, g2_agent, g2_cta, st));
+    tm.mark("critic_wgrad");
     head_unfold(true, io->critic, io->critic_grad, Uc, w.sdq);
     AVD_LAUNCH_OK();
     AVD_TRY(p.dgrad3_unfold(true, io->critic, DZ, w.cW2b, F, Fp, w.mask, MW, w.xextT, w.G1, w.G2part, io->critic_grad));
+    tm.mark("critic_dgrad+unfold");
     // ---- actor loss gradient: -mean(critic(s, actor(s)))                            trainer.py:501-506
     AVD_TRY(fused3::run(fused3::MODE_ACTOR_OUT, d, A, R, io->actor, ao.total, w.aW2T, w.a_b2f, io->s, d.ns, 1, nullptr, nullptr, 0.f, io->action_high,
                         nullptr, nullptr, w.a2, nullptr, nullptr, nullptr, nullptr, nullptr, st));   // pi
+    tm.mark("actor_fwd");
     AVD_TRY(fused3::run(fused3::MODE_CRITIC_ACTION, d, A, R, io->critic, co.total, w.cW2T, w.c_b2f, io->s, d.ns, 1, w.a2, nullptr, 0.f, 0.f, nullptr,
                         nullptr, w.dpi, nullptr, nullptr, nullptr, nullptr, io->loss, st));          // d(-mean q)/d pi
+    tm.mark("critic_action");
     AVD_TRY(fused3::run(fused3::MODE_ACTOR_BWD, d, A, R, io->actor, ao.total, w.aW2T, w.a_b2f, io->s, d.ns, 1, nullptr, nullptr, 0.f, io->action_high,
                         nullptr, w.dpi, nullptr, w.mask, DZ, Ua, w.sdq + A, nullptr, st));
+    tm.mark("actor_bwd");
     AVD_TRY(wgrad3::run(d, false, A, R, io->actor, ao.total, io->s, nullptr, DZ, w.G2part, g2_agent, g2_cta, st));
+    tm.mark("actor_wgrad");
     head_unfold(false, io->actor, io->actor_grad, Ua, w.sdq + A);
     AVD_LAUNCH_OK();
     AVD_TRY(p.dgrad3_unfold(false, io->actor, DZ, w.aW2b, d.l1, Fp, w.mask, 8, w.xextT, w.G1, w.G2part, io->actor_grad));
-    return apply_local_updates(io, (void*)st);
+    tm.mark("actor_dgrad+unfold");
+    const int rc = apply_local_updates(io, (void*)st);
+    tm.mark("adam+polyak");
+    return rc;
 }
 
 extern "C" int avd_ddpg_learn(const avd_learn_io* io, void* stream) {

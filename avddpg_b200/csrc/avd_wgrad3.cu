@@ -12,8 +12,12 @@
 // The action-branch slab of the critic (one input per feature, model.py:69-70) is converted on the CUDA cores.
 // Reference: workers/trainer.py:498, 506 (tape.gradient) through agent/model.py:19-33, 62-77.
 //
-// Warps: 0 MMA issuer, 1 TMA producer, 2..17 converters (TMEM lane quadrant = warp % 4, 32 columns each).
-// TMEM: three slab accumulators (3 x 128 columns) + the z1 slab (128 columns).
+// Warps: 0 issuer of the G2 products, 1 TMA producer, 2..17 converters (TMEM lane quadrant = warp % 4; two independent
+// groups of eight warps, one per 64-feature half of a slab, 32 columns per warp), 18 issuer of the layer-1 MMAs.
+// TMEM: 2-3 slab accumulators (128 columns each) + a ring of z1 HALF slabs (64 columns each) in the remaining columns: four
+// for the actor, two for the critic.  The layer-1 MMA of a half slab is issued as soon as the converters have drained the ring
+// entry it reuses, and r1 slabs go through a ring of four shared-memory buffers, so the MMA -> commit -> tcgen05.ld -> convert
+// -> MMA round trips of one half slab hide behind the work on the others.
 #include <cudaTypedefs.h>
 
 #include <algorithm>
@@ -30,12 +34,15 @@ typedef __nv_bfloat16 bf16;
 
 constexpr int TILE_M = 128, L2N = 128, KB = 64, SLAB = 128;
 constexpr int NCONV = 16;                                   // converter warps: 4 per TMEM lane quadrant, 32 columns each
-constexpr int NUM_THREADS = 32 * (2 + NCONV);
+constexpr int NUM_THREADS = 32 * (3 + NCONV);
+constexpr int WARP_L1 = 2 + NCONV;                           // issuer of the layer-1 MMAs
 constexpr int HALF_BYTES = TILE_M * 128;                     // [128 rows][64 bf16]: 16 KB
 constexpr int OFF_DZ = 0;                                    // 2 x dz2 tile (2 halves of 64 columns)
 constexpr int OFF_R1 = OFF_DZ + 2 * 2 * HALF_BYTES;          // 2 x r1 slab (2 halves of 64 features)
 constexpr int L1N = 256;
-constexpr int OFF_B1 = OFF_R1 + 2 * 2 * HALF_BYTES;          // W1ext, no-swizzle K-major [2 chunks][256 rows][16 B]
+constexpr int NRB = 4;                                       // ring of r1 slabs: deep enough that the barrier round trips converter -> issuer ->
+                                                             // tensor pipe -> converter of one slab hide behind the products of the others
+constexpr int OFF_B1 = OFF_R1 + NRB * 2 * HALF_BYTES;          // W1ext, no-swizzle K-major [2 chunks][256 rows][16 B]
 constexpr int OFF_X = OFF_B1 + 2 * L1N * 16;                 // 2 input tiles [2 chunks][128 rows][16 B]
 constexpr int X_BYTES = 2 * TILE_M * 16;
 constexpr int OFF_TAB = OFF_X + 2 * X_BYTES;                 // wa[64] ba[64]
@@ -78,11 +85,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad3_kernel(const __grid_con
     float* ba_tab = wa_tab + 64;
     uint64_t* dz_full = reinterpret_cast<uint64_t*>(smem + OFF_BAR);  // [2]
     uint64_t* dz_empty = dz_full + 2;                                 // [2]
-    uint64_t* r_full = dz_empty + 2;                                  // [2]
-    uint64_t* r_empty = r_full + 2;                                   // [2]
-    uint64_t* x_full = r_empty + 2;                                   // [2]
-    uint64_t* z1_full = x_full + 2;
-    uint64_t* acc_done = z1_full + 1;
+    uint64_t* r_full = dz_empty + 2;                                  // [NRB]
+    uint64_t* r_empty = r_full + NRB;                                 // [NRB]
+    uint64_t* x_full = r_empty + NRB;                                   // [2]
+    uint64_t* z1_full = x_full + 2;                                   // [4]
+    uint64_t* z1_empty = z1_full + 4;                                 // [4]
+    uint64_t* acc_done = z1_empty + 4;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_done + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -97,15 +105,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad3_kernel(const __grid_con
         tma_prefetch_desc(&tmDZ);
         for (int i = 0; i < 2; ++i) {
             mbar_init(&dz_full[i], 1); mbar_init(&dz_empty[i], 1);
-            mbar_init(&r_full[i], NCONV); mbar_init(&r_empty[i], 1);
             mbar_init(&x_full[i], 4);
         }
-        mbar_init(z1_full, 1);
+        for (int i = 0; i < 4; ++i) { mbar_init(&z1_full[i], 1); mbar_init(&z1_empty[i], NCONV / 2); }
+        for (int i = 0; i < NRB; ++i) { mbar_init(&r_full[i], NCONV); mbar_init(&r_empty[i], 1); }
         mbar_init(acc_done, 1);
         fence_barrier_init();
     }
     if (warp == 0) tmem_alloc(tmem_slot, 512);
-    if (warp >= 2) {
+    if (warp >= 2 && warp < WARP_L1) {
         const int ct = threadIdx.x - 64;     // 0..511; the first 256 build the W1ext row of layer-1 output column ct
         if (ct < L1N) {
             const int64_t oW = g.critic ? critic_off(d).Ws : actor_off(d).W1, ob = g.critic ? critic_off(d).bs : actor_off(d).b1;
@@ -116,6 +124,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad3_kernel(const __grid_con
             const bf16 zero = __float2bfloat16_rn(0.0f);
             *reinterpret_cast<uint4*>(smem + OFF_B1 + ct * 16) = make_uint4(pack2(whi[0], whi[1]), pack2(whi[2], whi[3]), pack2(bhi, whi[0]), pack2(whi[1], whi[2]));
             *reinterpret_cast<uint4*>(smem + OFF_B1 + L1N * 16 + ct * 16) = make_uint4(pack2(whi[3], bhi), pack2(wlo[0], wlo[1]), pack2(wlo[2], wlo[3]), pack2(blo, zero));
+        }
+        if (g.critic) {                  // the action slab leaves features 64..127 of its r1 buffers unwritten: start from finite values
+            for (int i = ct; i < NRB * 2 * HALF_BYTES / 16; i += 32 * NCONV) reinterpret_cast<uint4*>(smem + OFF_R1)[i] = make_uint4(0u, 0u, 0u, 0u);
         }
         if (g.critic && ct < 64) {
             const CriticOff o = critic_off(d);
@@ -129,45 +140,53 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad3_kernel(const __grid_con
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     auto tile_of = [&](int tc) { return cta + tc * g.ctas_per_agent; };
-    // Work is a sequence of slab steps q = t FT + s (row tile t, feature slab s); r1 buffer q & 1.  State slabs (s < 2) go
-    // through the layer-1 MMA and the single z1 buffer; zi = 2 t + s counts them.
+    // Work is a sequence of slab steps q = t FT + s (row tile t, feature slab s); r1 buffer q % NRB.  State slabs (s < 2) go
+    // through the layer-1 MMA in half-slab units u = 4 t + 2 s + h (64 features), z1 ring entry u % NZ.
+    const int nzs = FT > 2 ? 1 : 2, NZ = 1 << nzs;          // log2 / number of ring entries
+    const uint32_t zbase = tmem_base + (uint32_t)(FT * SLAB);
+    const int U = 4 * T;
 
     if (warp == 0) {
         // ================================================ MMA issuer ================================================
         // warp-uniform control flow; the tcgen05 instructions are predicated on one elected lane (see avd_umma.cuh)
         if (T > 0) {
             const uint32_t leader = elect_one();
-            constexpr uint32_t idesc1 = make_idesc_bf16(TILE_M, SLAB, false, false);   // x (K-major) x W1ext slab (K-major)
             constexpr uint32_t idesc2 = make_idesc_bf16(SLAB, L2N, true, true);        // r1 slab (MN-major) x dz2 tile (MN-major)
-            const uint64_t dX = make_desc_noswz(smem_u32(smem + OFF_X), TILE_M * 16, 128);
-            const uint64_t dB1 = make_desc_noswz(smem_u32(smem + OFF_B1), L1N * 16, 128);
             const uint64_t dR = make_smem_desc(smem_u32(smem + OFF_R1), HALF_BYTES, 1024);
             const uint64_t dDZ = make_smem_desc(smem_u32(smem + OFF_DZ), HALF_BYTES, 1024);
-            auto mma1 = [&](int t, int sl) {  // z1 of state slab sl of local tile t -> TMEM columns [384, 512); the caller knows they are drained
-                if (sl == 0) mbar_wait(&x_full[t & 1], ((uint32_t)t >> 1) & 1);
-                tc_fence_after();
-                mma_bf16_p(leader, tmem_base + 384u, desc_add(dX, (uint32_t)(t & 1) * X_BYTES), desc_add(dB1, (uint32_t)sl * SLAB * 16), idesc1, 0);
-                mma_commit_p(leader, z1_full);
-            };
-            mma1(0, 0);
             for (int t = 0; t < T; ++t) {
                 for (int sl = 0; sl < FT; ++sl) {
                     const uint32_t q = (uint32_t)(t * FT + sl);
-                    mbar_wait(&r_full[q & 1], (q >> 1) & 1);             // converters are done with this step (and with z1, if it used it)
+                    mbar_wait(&r_full[q % NRB], (q / NRB) & 1);             // converters are done with this step
                     if (sl == 0) mbar_wait(&dz_full[t & 1], ((uint32_t)t >> 1) & 1);
                     tc_fence_after();
-                    // the (tiny) layer-1 MMA of the next state slab goes first: its converters then overlap this step's product
-                    if (sl == 0) mma1(t, 1);
-                    else if (sl == 1 && t + 1 < T) mma1(t + 1, 0);
-                    const uint32_t off = (q & 1) * 2 * HALF_BYTES, doff = (uint32_t)(t & 1) * 2 * HALF_BYTES;
+                    const uint32_t off = (q % NRB) * 2 * HALF_BYTES, doff = (uint32_t)(t & 1) * 2 * HALF_BYTES;
 #pragma unroll
                     for (int ks = 0; ks < 8; ++ks)
                         mma_bf16_p(leader, tmem_base + (uint32_t)(sl * SLAB), desc_add(dR, off + ks * 2048), desc_add(dDZ, doff + ks * 2048), idesc2, (t | ks) != 0);
-                    mma_commit_p(leader, &r_empty[q & 1]);
+                    mma_commit_p(leader, &r_empty[q % NRB]);
                     if (sl == FT - 1) mma_commit_p(leader, &dz_empty[t & 1]);
                 }
             }
             mma_commit_p(leader, acc_done);
+        }
+    } else if (warp == WARP_L1) {
+        // ============================================ layer-1 MMA issuer ============================================
+        // A warp of its own: every tcgen05.commit costs the issuing thread ~140 cycles and an MMA issue blocks while the tensor
+        // pipe's queue is full, so one thread issuing both products was the bottleneck of the whole kernel.
+        if (T > 0) {
+            const uint32_t leader = elect_one();
+            const uint64_t dX = make_desc_noswz(smem_u32(smem + OFF_X), TILE_M * 16, 128);
+            const uint64_t dB1 = make_desc_noswz(smem_u32(smem + OFF_B1), L1N * 16, 128);
+            constexpr uint32_t idesc1h = make_idesc_bf16(TILE_M, 64, false, false);    // x (K-major) x W1ext half slab (K-major)
+            for (int u = 0; u < U; ++u) {     // z1 of half-slab unit u -> ring entry u % NZ, once the converters have drained its previous use
+                const int t = u >> 2, b = u & (NZ - 1);
+                if ((u & 3) == 0) mbar_wait(&x_full[t & 1], ((uint32_t)t >> 1) & 1);
+                if (u >= NZ) mbar_wait(&z1_empty[b], (((uint32_t)u >> nzs) - 1) & 1);
+                tc_fence_after();
+                mma_bf16_p(leader, zbase + (uint32_t)(b * 64), desc_add(dX, (uint32_t)(t & 1) * X_BYTES), desc_add(dB1, (uint32_t)(u & 3) * 64 * 16), idesc1h, 0);
+                mma_commit_p(leader, &z1_full[b]);
+            }
         }
     } else if (warp == 1) {
         // ================================================ TMA producer ================================================
@@ -194,8 +213,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad3_kernel(const __grid_con
     } else {
         // ================================================ converters ================================================
         const int cw = warp - 2;             // 0..15
-        const int q4 = warp & 3, qtr = cw >> 2;      // TMEM lane quadrant; 32-column quarter of the 128-feature slab
-        const int half = qtr >> 1;                   // which 64-feature MN chunk of the r1 slab
+        const int q4 = warp & 3, qtr = cw >> 2;      // TMEM lane quadrant; 16-column quarter of a half slab / 32-column quarter of an accumulator
+        const int half = qtr >> 1;                   // action slab: which 64-feature MN chunk of the r1 slab
         const int row = q4 * 32 + lane;
         const uint32_t tlane = (uint32_t)(q4 * 32) << 16;
         auto rowidx = [&](int tc) -> int64_t {
@@ -224,7 +243,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad3_kernel(const __grid_con
             __syncwarp();
             if (lane == 0) mbar_arrive(&x_full[t & 1]);
         };
-        if (qtr == 0 && T > 0) {
+        if (qtr == 2 && T > 0) {          // the half-1 group: its z1_full of a tile's last unit means all four layer-1 MMAs have read the X buffer
             load_x(0);
             write_x(0);
             if (T > 1) { load_x(1); write_x(1); }
@@ -233,16 +252,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad3_kernel(const __grid_con
         if (FT > 2 && T > 0) a_nx = __ldg(g.act + rowidx(0));
         for (int t = 0; t < T; ++t) {
             for (int sl = 0; sl < FT; ++sl) {
-                const uint32_t q = (uint32_t)(t * FT + sl), rb = q & 1;
+                const uint32_t q = (uint32_t)(t * FT + sl), rb = q % NRB;
                 // rows past the end of the agent's batch: dz2 is zero-filled by TMA there, so whatever r1 holds contributes nothing
                 uint8_t* rrow = smem + OFF_R1 + rb * 2 * HALF_BYTES + half * HALF_BYTES + row * 128;
                 if (sl < 2) {
-                    mbar_wait(z1_full, (uint32_t)(2 * t + sl) & 1);
-                    tc_fence_after();
-                    mbar_wait(&r_empty[rb], ((q >> 1) & 1) ^ 1);
+                    // Two independent groups of eight warps, one per 64-feature half of the slab: the round trip z1_full -> tcgen05.ld
+                    // -> z1_empty of one half overlaps the conversion of the other.
                     {
+                        const int h = half, u = 4 * t + 2 * sl + h, b = u & (NZ - 1);
+                        mbar_wait(&z1_full[b], ((uint32_t)u >> nzs) & 1);
+                        tc_fence_after();
                         float z[32];
-                        tmem_ld32(tmem_base + 384u + (uint32_t)(qtr * 32) + tlane, z);
+                        tmem_ld32(zbase + (uint32_t)(b * 64 + (qtr & 1) * 32) + tlane, z);
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&z1_empty[b]);        // the values are in registers: the ring entry can be refilled
+                        mbar_wait(&r_empty[rb], ((q / NRB) & 1) ^ 1);
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
                             const uint4 pk = make_uint4(pack_relu_bf16x2(z[8 * k], z[8 * k + 1]), pack_relu_bf16x2(z[8 * k + 2], z[8 * k + 3]),
@@ -250,19 +275,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad3_kernel(const __grid_con
                             *reinterpret_cast<uint4*>(rrow + ((((qtr & 1) * 4 + k) ^ (row & 7)) << 4)) = pk;
                         }
                     }
-                    tc_fence_before();
                     fence_proxy_async();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&r_full[rb]);
-                    // both layer-1 MMAs of tile t have read X buffer t & 1 once z1_full of its second slab has been seen
-                    if (sl == 1 && qtr == 0 && t + 2 < T) {
+                    // all four layer-1 MMAs of tile t have read X buffer t & 1 once z1_full of its last half has been seen
+                    if (sl == 1 && qtr == 2 && t + 2 < T) {
                         write_x(t + 2);
                         if (t + 3 < T) load_x(t + 3);
                     }
                 } else {                     // action-branch slab of the critic: 64 columns on the CUDA cores (zero weights beyond la)
                     const float a_val = a_nx;
                     if (t + 1 < T) a_nx = __ldg(g.act + rowidx(t + 1));
-                    mbar_wait(&r_empty[rb], ((q >> 1) & 1) ^ 1);         // every warp waits, so that no arrival can lap a phase of r_full
+                    mbar_wait(&r_empty[rb], ((q / NRB) & 1) ^ 1);         // every warp waits, so that no arrival can lap a phase of r_full
                     if (half == 0) {         // features 64..127 of this slab do not exist: that half keeps stale (finite) data, its rows are never flushed
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
