@@ -11,7 +11,7 @@
 // Math: dR = dz2 W2'^T with W2' = diag(sc1) W2 (BatchNorm folded, pack_fold_kernel), dz1 = dR [z1 > 0]
 // (workers/trainer.py:498, 506 through agent/model.py:19-33, 62-77).
 //
-// Warps: 0 MMA issuer, 1 TMA producer, 2..17 epilogue (TMEM lane quadrant = warp % 4, 32 of a chunk pair's 128 columns each).  TMEM: 3-slot ring of 128-column dR chunk pairs + 3 x 16 columns of G1 + 16 columns of
+// Warps: 0 issuer of the dR chunk MMAs, 18 issuer of the G1 / db2 MMAs, 1 TMA producer, 2..17 epilogue (TMEM lane quadrant = warp % 4, 32 of a chunk pair's 128 columns each).  TMEM: 3-slot ring of 128-column dR chunk pairs + 3 x 16 columns of G1 + 16 columns of
 // dz2^T xext, whose column 5 (xext's constant one) is the layer-2 bias gradient db2.
 #include <cudaTypedefs.h>
 
@@ -27,7 +27,8 @@ using namespace umma;
 typedef __nv_bfloat16 bf16;
 
 constexpr int TILE_M = 128, L2N = 128, KB = 64, MAX_NC = 5, NRING = 3;
-constexpr int NUM_THREADS = 32 * 18;
+constexpr int NUM_THREADS = 32 * 19;
+constexpr int WARP_G1 = 18;                                  // issuer of the G1 / db2 MMAs
 constexpr int WCHUNK_BYTES = 64 * 128;                       // one 64-feature x 64-k block of W2': 8 KB
 constexpr int OFF_W = 0;                                     // [2 k-blocks][5 chunks][64 rows][128 B] = 80 KB
 constexpr int OFF_A = OFF_W + 2 * MAX_NC * WCHUNK_BYTES;     // 2 dz2 tiles of 32 KB (released as soon as the chunk MMAs have read them)
@@ -83,8 +84,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dgrad3_kernel(const __grid_con
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmW); tma_prefetch_desc(&tmDZ); tma_prefetch_desc(&tmXT);
         for (int i = 0; i < NRING; ++i) { mbar_init(&d_full[i], 1); mbar_init(&d_empty[i], 16); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&st_full[i], 16); mbar_init(&st_empty[i], 1); mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 16); }
-        for (int i = 0; i < NXT; ++i) { mbar_init(&xt_full[i], 1); mbar_init(&xt_empty[i], 16); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&st_full[i], 16); mbar_init(&st_empty[i], 1); mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 2); }
+        for (int i = 0; i < NXT; ++i) { mbar_init(&xt_full[i], 1); mbar_init(&xt_empty[i], 1); }
         mbar_init(w_full, 1);
         mbar_init(g1_done, 1);
         fence_barrier_init();
@@ -97,12 +98,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dgrad3_kernel(const __grid_con
     auto tile_of = [&](int tc) { return cta + tc * g.ctas_per_agent; };
     // Chunk pair p of local tile t has the running index pk = t NP + p: TMEM ring slot pk % 3 (128 columns), staging buffer pk & 1.
 
-    if (warp == 0) {
-        // ================================================ MMA issuer ================================================
+    if (warp == 0 || warp == WARP_G1) {
+        // ================================================ MMA issuers ================================================
         // Warp-uniform control flow, tcgen05 instructions predicated on one elected lane (see avd_umma.cuh).  A tcgen05.mma
-        // issues at the pace of the tensor pipe and every tcgen05.commit costs this thread ~140 cycles, so the work is cut
-        // into few, wide MMAs (chunk pairs, N = 128) and the buffers that only the issuer's own program order protects
-        // (dz2 tile, x_ext tile) are handed back by the epilogue warps instead of through extra commits.
+        // issues at the pace of the tensor pipe and every tcgen05.commit costs its thread ~140 cycles; one thread issuing all
+        // 56 MMAs and 6 commits of a tile was busy ~80 % of the kernel, so the two products have an issuer warp each:
+        //   warp 0:  dR chunk pairs (N = 128)             warp 18:  db2 and G1 (N = 16), which read what the epilogue staged.
+        // A tcgen05.commit only tracks the MMAs of its own thread, so the dz2 tile is handed back by both (a_empty counts 2).
         if (T > 0) {
             const uint32_t leader = elect_one();
             constexpr uint32_t idesc_2 = make_idesc_bf16(TILE_M, 128, false, false);   // dz2 (K-major) x W2' chunk pair (K-major)
@@ -113,55 +115,57 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dgrad3_kernel(const __grid_con
             const uint64_t dW = make_smem_desc(smem_u32(smem + OFF_W), 16, 1024);
             const uint64_t dX = make_smem_desc(smem_u32(smem + OFF_XT), 16, 1024);
             const uint64_t dS = make_smem_desc(smem_u32(smem + OFF_ST), TILE_M * 128, 1024);      // staged dz1 chunk pair as MN-major A
-            // dR of chunk pair p of local tile t = dz2 tile . W2'[128 p .. 128 p + 127]^T  -> ring slot pk % 3
-            auto mma_pair = [&](int t, int p) {
-                const uint32_t a_off = (uint32_t)(t & 1) * A_BYTES;
-                if (p == 0) {
+            if (warp == 0) {
+                // dR of chunk pair p of local tile t = dz2 tile . W2'[128 p .. 128 p + 127]^T  -> ring slot pk % 3
+                mbar_wait(w_full, 0);
+                uint32_t rs = 0, rph = 0;
+                for (int t = 0; t < T; ++t) {
+                    const uint32_t a_off = (uint32_t)(t & 1) * A_BYTES;
+                    mbar_wait(&a_full[t & 1], ((uint32_t)t >> 1) & 1);
+#pragma unroll
+                    for (int p = 0; p < NP; ++p) {
+                        const bool both = 2 * p + 1 < NC;
+                        mbar_wait(&d_empty[rs], rph ^ 1);
+                        tc_fence_after();
+#pragma unroll
+                        for (int ks = 0; ks < 8; ++ks)
+                            mma_bf16_p(leader, tmem_base + rs * 128, desc_add(dA, a_off + (ks >> 2) * (TILE_M * 128) + (ks & 3) * 32),
+                                       desc_add(dW, (uint32_t)((ks >> 2) * MAX_NC + 2 * p) * WCHUNK_BYTES + (ks & 3) * 32), both ? idesc_2 : idesc_1, ks != 0);
+                        mma_commit_p(leader, &d_full[rs]);
+                        if (++rs == NRING) { rs = 0; rph ^= 1; }
+                    }
+                    mma_commit_p(leader, &a_empty[t & 1]);      // all chunk MMAs of this tile have read the dz2 tile
+                }
+            } else {
+                uint32_t pk = 0;
+                for (int t = 0; t < T; ++t) {
+                    const uint32_t a_off = (uint32_t)(t & 1) * A_BYTES, x_off = (uint32_t)(t % NXT) * XT_BYTES;
                     mbar_wait(&a_full[t & 1], ((uint32_t)t >> 1) & 1);
                     mbar_wait(&xt_full[t % NXT], ((uint32_t)t / NXT) & 1);
                     tc_fence_after();
                     // db2[j] = sum_n dz2[n][j]: the dz2 tile read as an MN-major A operand against the constant-one column (5) of xext
-                    const uint32_t x_off = (uint32_t)(t % NXT) * XT_BYTES;
 #pragma unroll
                     for (int ks = 0; ks < 8; ++ks)
                         mma_bf16_p(leader, tmem_base + 432u, desc_add(dAt, a_off + ks * 2048), desc_add(dX, x_off + (ks >> 2) * (16 * 128) + (ks & 3) * 32),
                                    idesc_g, (t | ks) != 0);
+                    mma_commit_p(leader, &a_empty[t & 1]);
+                    // G1[128 p ..] += (staged dz1 chunk pair)^T . xext tile
+#pragma unroll
+                    for (int p = 0; p < NP; ++p) {
+                        const uint32_t sb = pk & 1;
+                        mbar_wait(&st_full[sb], (pk >> 1) & 1);
+                        tc_fence_after();
+#pragma unroll
+                        for (int ks = 0; ks < 8; ++ks)
+                            mma_bf16_p(leader, tmem_base + 384u + (uint32_t)(p * 16), desc_add(dS, sb * (2 * TILE_M * 128) + ks * 2048),
+                                       desc_add(dX, x_off + (ks >> 2) * (16 * 128) + (ks & 3) * 32), idesc_g, (t | ks) != 0);
+                        mma_commit_p(leader, &st_empty[sb]);
+                        ++pk;
+                    }
+                    mma_commit_p(leader, &xt_empty[t % NXT]);   // db2 and G1 of this tile have read the x_ext tile
                 }
-                const uint32_t pk = (uint32_t)(t * NP + p), rs = pk % NRING;
-                const bool both = 2 * p + 1 < NC;
-                mbar_wait(&d_empty[rs], ((pk / NRING) & 1) ^ 1);
-                tc_fence_after();
-#pragma unroll
-                for (int ks = 0; ks < 8; ++ks)
-                    mma_bf16_p(leader, tmem_base + rs * 128, desc_add(dA, a_off + (ks >> 2) * (TILE_M * 128) + (ks & 3) * 32),
-                               desc_add(dW, (uint32_t)((ks >> 2) * MAX_NC + 2 * p) * WCHUNK_BYTES + (ks & 3) * 32), both ? idesc_2 : idesc_1, ks != 0);
-                mma_commit_p(leader, &d_full[rs]);
-            };
-            // G1[128 p ..] += (staged dz1 chunk pair)^T . xext tile
-            auto g1_pair = [&](int t, int p) {
-                const uint32_t x_off = (uint32_t)(t % NXT) * XT_BYTES;
-                const uint32_t pk = (uint32_t)(t * NP + p), sb = pk & 1;
-                mbar_wait(&st_full[sb], (pk >> 1) & 1);
-                tc_fence_after();
-#pragma unroll
-                for (int ks = 0; ks < 8; ++ks)
-                    mma_bf16_p(leader, tmem_base + 384u + (uint32_t)(p * 16), desc_add(dS, sb * (2 * TILE_M * 128) + ks * 2048),
-                               desc_add(dX, x_off + (ks >> 2) * (16 * 128) + (ks & 3) * 32), idesc_g, (t | ks) != 0);
-                mma_commit_p(leader, &st_empty[sb]);
-            };
-            mbar_wait(w_full, 0);
-#pragma unroll
-            for (int p = 0; p < NP; ++p) mma_pair(0, p);
-            // steady state: the pair MMAs of tile t + 1 are interleaved with the G1 MMAs of tile t, so that a staging buffer is
-            // handed back as early as possible (every wait only depends on work issued earlier)
-            for (int t = 0; t < T; ++t) {
-#pragma unroll
-                for (int p = 0; p < NP; ++p) {
-                    if (t + 1 < T) mma_pair(t + 1, p);
-                    g1_pair(t, p);
-                }
+                mma_commit_p(leader, g1_done);
             }
-            mma_commit_p(leader, g1_done);
         }
     } else if (warp == 1) {
         // ================================================ TMA producer ================================================
@@ -215,12 +219,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dgrad3_kernel(const __grid_con
                 else neg_next = __ldg(mrow_next);
                 mbar_wait(&d_full[rs], rph);
                 tc_fence_after();
-                if (p == NP - 1 && lane == 0) {
-                    // every MMA issued before this tile's last pair has completed: the dz2 tile of tile t (read by its pair and db2
-                    // MMAs) and the x_ext tile of tile t - 2 (read by G1 / db2 MMAs issued two iterations ago) are free again
-                    mbar_arrive(&a_empty[t & 1]);
-                    if (t >= 2) mbar_arrive(&xt_empty[(t - 2) % NXT]);
-                }
                 uint32_t pkd[16];            // the masked quarter as bf16 pairs: the TMEM slot is released before the staging buffer is needed
                 if (work) {
                     float v[32];
