@@ -526,6 +526,44 @@ __global__ void __launch_bounds__(256) adam_polyak_kernel(float* __restrict__ pa
     }
 }
 
+// Actor and critic in one launch (blockIdx.z): the two updates are independent and each is only a few microseconds long.
+struct AdamNet {
+    float *params, *target;
+    const float* grads;
+    float *m, *v;
+    const int32_t* step;
+    int64_t pstride, gstride, n_train, total;
+    float lr;
+};
+struct AdamNets { AdamNet n[2]; };
+
+__global__ void __launch_bounds__(256) adam_polyak2_kernel(AdamNets nets, const uint8_t* __restrict__ mask, float b1, float b2, float eps, float tau) {
+    const AdamNet& nt = nets.n[blockIdx.z];
+    const int agent = blockIdx.y;
+    if (mask && !mask[agent]) return;
+    const float t = (float)(nt.step[agent] + 1);
+    const float lr_t = nt.lr * sqrtf(1.0f - powf(b2, t)) / (1.0f - powf(b1, t));
+    float* P = nt.params + (int64_t)agent * nt.pstride;
+    float* T = nt.target + (int64_t)agent * nt.pstride;
+    const float* G = nt.grads + (int64_t)agent * nt.gstride;
+    float* Mm = nt.m + (int64_t)agent * nt.n_train;
+    float* Vv = nt.v + (int64_t)agent * nt.n_train;
+    const float omt = 1.0f - tau;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nt.total; i += (int64_t)gridDim.x * blockDim.x) {
+        float p = P[i];
+        if (i < nt.n_train) {
+            const float g = G[i];
+            const float mi = Mm[i] + (g - Mm[i]) * (1.0f - b1);
+            const float vi = Vv[i] + (g * g - Vv[i]) * (1.0f - b2);
+            Mm[i] = mi;
+            Vv[i] = vi;
+            p -= lr_t * mi / (sqrtf(vi) + eps);
+            P[i] = p;
+        }
+        T[i] = p * tau + T[i] * omt;
+    }
+}
+
 __global__ void step_increment2_kernel(int32_t* step_a, int32_t* step_b, const uint8_t* mask, int A) {
     const int a = blockIdx.x * blockDim.x + threadIdx.x;
     if (a < A && (!mask || mask[a])) {
@@ -680,6 +718,50 @@ __global__ void __launch_bounds__(256) pack_fold_kernel(const float* __restrict_
     }
 }
 
+// The four networks of a learn step (target actor, target critic, critic, actor) in ONE launch: blockIdx.z = job * A + agent.
+struct FoldJob {
+    const float* params;
+    int64_t pstride;
+    FoldOff o;
+    int F;
+    bf16 *W2b, *W2T;
+    float* b2f;
+};
+struct FoldJobs { FoldJob j[4]; };
+
+__global__ void __launch_bounds__(256) pack_fold4_kernel(FoldJobs jobs, int A, int l2) {
+    const int job = blockIdx.z / A, agent = blockIdx.z - job * A;
+    const FoldJob& jb = jobs.j[job];
+    if ((int)blockIdx.y * 8 >= jb.F) return;
+    const FoldOff& o = jb.o;
+    const float* P = jb.params + (int64_t)agent * jb.pstride;
+    const int F = jb.F;
+    const int j = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int fy = threadIdx.x >> 5;
+    const int f = blockIdx.y * 8 + fy;
+    __shared__ float red[8][32];
+    float acc = 0.0f;
+    if (j < l2 && f < F) {
+        const bool st = f < o.l1;
+        const int c = st ? f : f - o.l1;
+        const float sc = P[(st ? o.g[0] : o.g[1]) + c] / sqrtf(P[(st ? o.var[0] : o.var[1]) + c] + kBnEps);
+        const float sh = P[(st ? o.be[0] : o.be[1]) + c] - P[(st ? o.mu[0] : o.mu[1]) + c] * sc;
+        const float w = P[o.W2 + (int64_t)f * l2 + j];
+        const bf16 v = __float2bfloat16_rn(sc * w);
+        if (jb.W2b) jb.W2b[((int64_t)agent * F + f) * l2 + j] = v;
+        jb.W2T[((int64_t)agent * l2 + j) * F + f] = v;
+        acc = sh * w;
+    }
+    red[fy][threadIdx.x & 31] = acc;
+    __syncthreads();
+    if (fy == 0 && j < l2) {
+        float t = blockIdx.y == 0 ? P[o.b2 + j] : 0.0f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x];
+        atomicAdd(jb.b2f + (int64_t)agent * l2 + j, t);
+    }
+}
+
 // xextT[agent][c][r] (bf16, row pitch Rp): x_ext = [ s_hi(4) a_hi 1 0 0 | s_lo(4) a_lo 0 0 0 ] of row r, stored transposed so that a
 // [16][128-row] tile is the K-major B operand of the fused dgrad kernel (avd_dgrad3.cu):
 //   G1[f][c] = sum_n dz1[n][f] x_ext[n][c]  =>  dW1[k][f] = G1[f][k] + G1[f][8+k],  dWa[f] = G1[l1+f][4] + G1[l1+f][12],  db[f] = G1[f][5]
@@ -731,6 +813,7 @@ __global__ void __launch_bounds__(256) unfold_kernel(const float* __restrict__ p
     const float* g2row = G2 + (int64_t)agent * g2_agent_stride + (int64_t)f * l2;
     const float* g1row = G1 + ((int64_t)agent * ncta * Fp + f) * 16;
     float acc[4] = {0.f, 0.f, 0.f, 0.f}, acc1 = 0.0f;
+#pragma unroll 5
     for (int sl = wid; sl < ncta; sl += 8) {
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
@@ -966,6 +1049,24 @@ struct Pass {
         return AVD_OK;
     }
 
+    // all four networks of a learn step in one launch; the b2f buffers must have been zeroed
+    int pack_fold4(const float* const params[4], const bool critic[4], bf16* const W2b[4], bf16* const W2T[4], float* const b2f[4]) const {
+        FoldJobs jobs;
+        int Fmax = 0;
+        for (int i = 0; i < 4; ++i) {
+            FoldJob& jb = jobs.j[i];
+            jb.params = params[i];
+            jb.pstride = critic[i] ? critic_off(d).total : actor_off(d).total;
+            jb.o = fold_off(critic[i]);
+            jb.F = critic[i] ? d.l1 + d.la : d.l1;
+            jb.W2b = W2b[i]; jb.W2T = W2T[i]; jb.b2f = b2f[i];
+            Fmax = std::max(Fmax, jb.F);
+        }
+        pack_fold4_kernel<<<dim3((unsigned)((d.l2 + 31) / 32), (unsigned)((Fmax + 7) / 8), (unsigned)(4 * A)), 256, 0, st>>>(jobs, A, d.l2);
+        AVD_LAUNCH_OK();
+        return AVD_OK;
+    }
+
     FoldOff fold_off(bool critic) const {
         FoldOff o;
         if (critic) {
@@ -1155,13 +1256,11 @@ extern "C" int avd_adam_polyak_apply2(float* actor, float* t_actor, int64_t acto
     AVD_REQUIRE(A >= 0 && actor_train >= 0 && actor_total >= actor_train && critic_train >= 0 && critic_total >= critic_train, "bad sizes");
     if (A == 0) return AVD_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    adam_polyak_kernel<<<dim3((unsigned)std::min<int64_t>((critic_total + 255) / 256, 64), A), 256, 0, st>>>(
-        critic, t_critic, critic_total, critic_grad, critic_gstride, critic_m, critic_v, critic_step, apply_mask, critic_train, critic_total,
-        critic_lr, beta1, beta2, eps, tau);
-    AVD_LAUNCH_OK();
-    adam_polyak_kernel<<<dim3((unsigned)std::min<int64_t>((actor_total + 255) / 256, 64), A), 256, 0, st>>>(
-        actor, t_actor, actor_total, actor_grad, actor_gstride, actor_m, actor_v, actor_step, apply_mask, actor_train, actor_total, actor_lr,
-        beta1, beta2, eps, tau);
+    AdamNets nets;
+    nets.n[0] = AdamNet{critic, t_critic, critic_grad, critic_m, critic_v, critic_step, critic_total, critic_gstride, critic_train, critic_total, critic_lr};
+    nets.n[1] = AdamNet{actor, t_actor, actor_grad, actor_m, actor_v, actor_step, actor_total, actor_gstride, actor_train, actor_total, actor_lr};
+    const int64_t blocks = std::min<int64_t>((std::max(critic_total, actor_total) + 255) / 256, 1024);
+    adam_polyak2_kernel<<<dim3((unsigned)blocks, (unsigned)A, 2), 256, 0, st>>>(nets, apply_mask, beta1, beta2, eps, tau);
     AVD_LAUNCH_OK();
     step_increment2_kernel<<<(A + 127) / 128, 128, 0, st>>>(actor_step, critic_step, apply_mask, A);
     AVD_LAUNCH_OK();
@@ -1305,14 +1404,19 @@ static int learn_fused3(const avd_learn_io* io, const Pass& p, const Workspace& 
     bf16* DZ = reinterpret_cast<bf16*>(w.DZ);
     float* Uc = w.U;
     float* Ua = w.U + (int64_t)A * d.l2;
-    AVD_TRY(p.pack_fold(false, io->t_actor, nullptr, w.taW2T, w.ta_b2f));
-    AVD_TRY(p.pack_fold(true, io->t_critic, nullptr, w.tcW2T, w.tc_b2f));
-    AVD_TRY(p.pack_fold(true, io->critic, w.cW2b, w.cW2T, w.c_b2f));
-    AVD_TRY(p.pack_fold(false, io->actor, w.aW2b, w.aW2T, w.a_b2f));
+    // c_b2f .. ta_b2f, U and sdq are adjacent in the workspace: one memset zeroes every accumulator of the step
+    AVD_CUDA_OK(cudaMemsetAsync(w.c_b2f, 0, (size_t)((char*)(w.sdq + 2 * A) - (char*)w.c_b2f), st));
+    {
+        const float* const prm[4] = {io->t_actor, io->t_critic, io->critic, io->actor};
+        const bool crit[4] = {false, true, true, false};
+        bf16* const W2b[4] = {nullptr, nullptr, w.cW2b, w.aW2b};
+        bf16* const W2T[4] = {w.taW2T, w.tcW2T, w.cW2T, w.aW2T};
+        float* const b2f[4] = {w.ta_b2f, w.tc_b2f, w.c_b2f, w.a_b2f};
+        AVD_TRY(p.pack_fold4(prm, crit, W2b, W2T, b2f));
+    }
     const int64_t Rp = (R + 63) / 64 * 64;
     xext_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(io->s, io->a, d.ns, N, w.xextT, R, Rp);
     AVD_LAUNCH_OK();
-    AVD_CUDA_OK(cudaMemsetAsync(w.U, 0, (size_t)(2 * A * d.l2 + 2 * A) * sizeof(float), st));   // U and sdq are adjacent
     tm.mark("fold+xext");
     auto head_unfold = [&](bool critic, const float* params, float* grads, const float* U, const float* sdq) {
         HeadOff o;
