@@ -257,6 +257,67 @@ class BatchedTrainer:
         self.step_in_run += 2
 
 
+class HostStepPipeline:
+    """Drives `BatchedTrainer.step()` from HOST buffers without ever draining the GPU.
+
+    The reference's loop is host-driven: the leaders' exogenous inputs are drawn on the host every step
+    (workers/trainer.py:292-295) and the rewards / losses are read there (trainer.py:321, 496-504).  A synchronous version of
+    that hand-off costs one GPU idle period per step (result read -> next input -> first launch).  Here both directions are
+    double-buffered in pinned memory: step k copies its inputs from buffer k & 1 and its results (reward / done statistics of
+    `env.stats`, critic and actor losses) into result buffer k & 1, and `submit()` returns the results of step k - 1 while step
+    k runs.  Every step's inputs go host -> device and every step's results come back; the host merely reads them one step late.
+
+        pipe = HostStepPipeline(trainer)
+        for k in range(n):
+            pipe.input_buffer().normal_(0, 0.1)      # leaders' exogenous inputs of step k, [P] pinned
+            prev = pipe.submit()                     # None for k = 0, else pinned [M + 1 + 2 A] of step k - 1
+        last = pipe.drain()
+    """
+
+    def __init__(self, trainer: "BatchedTrainer"):
+        self.tr = trainer
+        env, pop = trainer.env, trainer.pop
+        assert env.stats is not None, "construct the environment with collect_stats=True"
+        self.n_stats = int(env.stats.numel())
+        self.h_in = [torch.zeros(env.P, dtype=torch.float32).pin_memory() for _ in range(2)]
+        self.h_out = [torch.zeros(self.n_stats + int(pop.loss.numel()), dtype=torch.float32).pin_memory() for _ in range(2)]
+        self.done = [torch.cuda.Event(), torch.cuda.Event()]
+        self.k = 0
+
+    @property
+    def h2d_bytes_per_step(self) -> int:
+        return int(self.h_in[0].numel()) * 4
+
+    @property
+    def d2h_bytes_per_step(self) -> int:
+        return int(self.h_out[0].numel()) * 4
+
+    def input_buffer(self) -> torch.Tensor:
+        """Pinned [P] buffer to fill with the next step's leader inputs; its previous use (two steps ago) has completed."""
+        return self.h_in[self.k & 1]
+
+    def submit(self, learn: bool = True) -> Optional[torch.Tensor]:
+        tr, b = self.tr, self.k & 1
+        tr.env.stats.zero_()
+        tr.step(learn=learn, host_leader_exog=self.h_in[b])
+        self.h_out[b][: self.n_stats].copy_(tr.env.stats, non_blocking=True)
+        self.h_out[b][self.n_stats:].copy_(tr.pop.loss.reshape(-1), non_blocking=True)
+        self.done[b].record()
+        self.k += 1
+        if self.k < 2:
+            return None
+        self.done[b ^ 1].synchronize()               # step k - 1: finished while step k was being enqueued
+        return self.h_out[b ^ 1]
+
+    def drain(self) -> Optional[torch.Tensor]:
+        """Results of the last submitted step."""
+        if self.k == 0:
+            return None
+        b = (self.k - 1) & 1
+        self.done[b].synchronize()
+        return self.h_out[b]
+
+
 class Trainer:
     """Reference-shaped wrapper: ``learn`` on single-agent model objects (trainer.py:472-508)."""
 

@@ -402,6 +402,41 @@ def test_batched_trainer_tensor_core_mode(mods):
     assert torch.isfinite(tr.pop.actor.flat).all()
 
 
+def test_host_step_pipeline_matches_synchronous_stepping(mods):
+    """HostStepPipeline (double-buffered pinned inputs / results, results read one step late) returns for every step exactly
+    what a synchronous host loop reads (same seeds, same host inputs): pipelining the hand-off changes no arithmetic."""
+    conf = mods["Config"](pl_size=2, batch_size=8, buffer_size=64)
+    mk = lambda: mods["trainer"].BatchedTrainer(conf, num_groups=2, envs_per_group=3, ring_capacity=64)
+    n = 14
+    inputs = 0.1 * torch.randn(n, 6, generator=torch.Generator().manual_seed(5))
+    # synchronous loop
+    tr = mk()
+    h_in = torch.zeros(6).pin_memory()
+    want = []
+    for k in range(n):
+        h_in.copy_(inputs[k])
+        tr.env.stats.zero_()
+        tr.step(host_leader_exog=h_in)
+        want.append(torch.cat([tr.env.stats.cpu(), tr.pop.loss.reshape(-1).cpu()]))
+    w_sync = tr.pop.actor.flat.clone()
+    # pipelined loop
+    tr2 = mk()
+    pipe = mods["trainer"].HostStepPipeline(tr2)
+    assert pipe.h2d_bytes_per_step == 6 * 4 and pipe.d2h_bytes_per_step == want[0].numel() * 4
+    got = []
+    for k in range(n):
+        pipe.input_buffer().copy_(inputs[k])
+        prev = pipe.submit()
+        assert (prev is None) == (k == 0)
+        if prev is not None:
+            got.append(prev.clone())
+    got.append(pipe.drain().clone())
+    assert len(got) == n
+    for k in range(n):
+        assert torch.equal(got[k], want[k]), k
+    assert torch.equal(w_sync, tr2.pop.actor.flat)
+
+
 def test_evaluator_rollout_vs_reference_golden(mods, golden):
     """N2: noise-free evaluation rollout (workers/evaluator.py:40-96,145) on the reference's own seed-6 leader inputs
     and fixed evaluator initial state; actors injected.  precision=0 so the 100-step closed loop stays on the
