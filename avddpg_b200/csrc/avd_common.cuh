@@ -39,6 +39,31 @@ int sm_count();                                  // cached multiprocessor count 
         }                                                                                   \
     } while (0)
 
+// Programmatic dependent launch (PDL).  A kernel launched through launch_pdl() may become resident while the previous
+// kernel of the stream is still running -- SM by SM, as that kernel's CTAs exit -- and run its prologue (barrier init, TMEM
+// allocation, weight tables) there; it must execute pdl_wait() before it touches anything an earlier kernel wrote, and calls
+// pdl_launch_dependents() to allow the same for its successor.  AVD_PDL=0 in the environment restores plain launches.
+bool pdl_enabled();                              // defined in avd_lib.cu
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#endif
+
 // Persistent-style grid: enough 256-thread CTAs to fill every SM to 2048 threads, never more than
 // the work needs (B200: 148 SMs x 8 CTAs).
 inline int grid_for(int64_t work_items, int threads = 256, int ctas_per_sm = 8) {

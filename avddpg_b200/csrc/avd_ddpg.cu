@@ -538,6 +538,8 @@ struct AdamNet {
 struct AdamNets { AdamNet n[2]; };
 
 __global__ void __launch_bounds__(256) adam_polyak2_kernel(AdamNets nets, const uint8_t* __restrict__ mask, float b1, float b2, float eps, float tau) {
+    pdl_wait();                  // launched with programmatic dependent launch (avd_common.cuh): every CTA waits before it reads or exits
+    pdl_launch_dependents();
     const AdamNet& nt = nets.n[blockIdx.z];
     const int agent = blockIdx.y;
     if (mask && !mask[agent]) return;
@@ -565,6 +567,8 @@ __global__ void __launch_bounds__(256) adam_polyak2_kernel(AdamNets nets, const 
 }
 
 __global__ void step_increment2_kernel(int32_t* step_a, int32_t* step_b, const uint8_t* mask, int A) {
+    pdl_wait();
+    pdl_launch_dependents();
     const int a = blockIdx.x * blockDim.x + threadIdx.x;
     if (a < A && (!mask || mask[a])) {
         step_a[a] += 1;
@@ -804,6 +808,8 @@ struct UnfoldOff {
 __global__ void __launch_bounds__(256) unfold_kernel(const float* __restrict__ params, int64_t pstride, float* __restrict__ grads, int64_t gstride,
                                                      const float* __restrict__ G2, int64_t g2_agent_stride, int64_t g2_cta_stride,
                                                      const float* __restrict__ G1, int ncta, UnfoldOff o, int F, int Fp, int l2, int ns) {
+    pdl_wait();                  // partial slices of the wgrad / dgrad launches
+    pdl_launch_dependents();
     // one CTA per (feature f, agent); its 8 warps split the partial slices between them (slice w, w + 8, ...) so that every
     // load is independent and 64 warps per SM hide the L2 / HBM latency, then combine through shared memory
     const int agent = blockIdx.y;
@@ -880,6 +886,8 @@ struct HeadOff { int64_t g2, be2, mu2, var2, W3, b3; };
 
 __global__ void __launch_bounds__(128) head_unfold_kernel(const float* __restrict__ params, int64_t pstride, float* __restrict__ grads, int64_t gstride,
                                                           const float* __restrict__ U, const float* __restrict__ sdq, HeadOff o, int l2) {
+    pdl_wait();
+    pdl_launch_dependents();
     const int agent = blockIdx.x, j = threadIdx.x;
     if (j >= l2) return;
     const float* P = params + (int64_t)agent * pstride;
@@ -1099,8 +1107,8 @@ struct Pass {
             const ActorOff a = actor_off(d);
             u.W1[0] = u.W1[1] = a.W1; u.b1[0] = u.b1[1] = a.b1; ps = a.total;
         }
-        unfold_kernel<<<dim3((unsigned)F, A), 256, 0, st>>>(params, ps, grads, gs, G2part, (int64_t)ncta * Workspace::kG2Rows * d.l2,
-                                                                        (int64_t)Workspace::kG2Rows * d.l2, G1, ncta, u, F, Fp, d.l2, d.ns);
+        AVD_CUDA_OK(launch_pdl(unfold_kernel, dim3((unsigned)F, (unsigned)A), dim3(256), 0, st, params, ps, grads, gs, G2part,
+                               (int64_t)ncta * Workspace::kG2Rows * d.l2, (int64_t)Workspace::kG2Rows * d.l2, G1, ncta, u, F, Fp, d.l2, d.ns));
         AVD_LAUNCH_OK();
         return AVD_OK;
     }
@@ -1260,9 +1268,9 @@ extern "C" int avd_adam_polyak_apply2(float* actor, float* t_actor, int64_t acto
     nets.n[0] = AdamNet{critic, t_critic, critic_grad, critic_m, critic_v, critic_step, critic_total, critic_gstride, critic_train, critic_total, critic_lr};
     nets.n[1] = AdamNet{actor, t_actor, actor_grad, actor_m, actor_v, actor_step, actor_total, actor_gstride, actor_train, actor_total, actor_lr};
     const int64_t blocks = std::min<int64_t>((std::max(critic_total, actor_total) + 255) / 256, 1024);
-    adam_polyak2_kernel<<<dim3((unsigned)blocks, (unsigned)A, 2), 256, 0, st>>>(nets, apply_mask, beta1, beta2, eps, tau);
+    AVD_CUDA_OK(launch_pdl(adam_polyak2_kernel, dim3((unsigned)blocks, (unsigned)A, 2), dim3(256), 0, st, nets, apply_mask, beta1, beta2, eps, tau));
     AVD_LAUNCH_OK();
-    step_increment2_kernel<<<(A + 127) / 128, 128, 0, st>>>(actor_step, critic_step, apply_mask, A);
+    AVD_CUDA_OK(launch_pdl(step_increment2_kernel, dim3((unsigned)((A + 127) / 128)), dim3(128), 0, st, actor_step, critic_step, apply_mask, (int)A));
     AVD_LAUNCH_OK();
     return AVD_OK;
 }
@@ -1423,7 +1431,7 @@ static int learn_fused3(const avd_learn_io* io, const Pass& p, const Workspace& 
         int64_t ps, gs;
         if (critic) { o = HeadOff{co.g2, co.be2, co.mu2, co.var2, co.W3, co.b3}; ps = co.total; gs = co.n_train; }
         else { o = HeadOff{ao.g2, ao.be2, ao.mu2, ao.var2, ao.W3, ao.b3}; ps = ao.total; gs = ao.n_train; }
-        head_unfold_kernel<<<A, 128, 0, st>>>(params, ps, grads, gs, U, sdq, o, d.l2);
+        launch_pdl(head_unfold_kernel, dim3((unsigned)A), dim3(128), 0, st, params, ps, grads, gs, U, sdq, o, d.l2);
     };
     // ---- TD target: y = r + gamma * target_critic(s', target_actor(s'))            trainer.py:493-494
     AVD_TRY(fused3::run(fused3::MODE_ACTOR_OUT, d, A, R, io->t_actor, ao.total, w.taW2T, w.ta_b2f, io->s2, d.ns, 1, nullptr, nullptr, 0.f,

@@ -95,6 +95,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dgrad3_kernel(const __grid_con
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();                      // dz2, the sign masks and the partial-slice buffers belong to earlier launches until here
+    pdl_launch_dependents();
     auto tile_of = [&](int tc) { return cta + tc * g.ctas_per_agent; };
     // Chunk pair p of local tile t has the running index pk = t NP + p: TMEM ring slot pk % 3 (128 columns), staging buffer pk & 1.
 
@@ -337,8 +339,8 @@ int run(int A, int64_t R, int F, const bf16* DZ, const bf16* W2b, const uint32_t
     g.tiles_per_agent = (int)((R + TILE_M - 1) / TILE_M);
     g.ctas_per_agent = std::max(1, std::min(g.tiles_per_agent, sm_count() / std::max(1, A)));      // == wgrad3::ctas_per_agent(A, R)
     const unsigned grid = (unsigned)(g.ctas_per_agent * A);
-    if (g.NC == 4) dgrad3_kernel<4><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmW, tmDZ, tmXT, g);
-    else dgrad3_kernel<5><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmW, tmDZ, tmXT, g);
+    if (g.NC == 4) AVD_CUDA_OK(launch_pdl(dgrad3_kernel<4>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, st, tmW, tmDZ, tmXT, g));
+    else AVD_CUDA_OK(launch_pdl(dgrad3_kernel<5>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, st, tmW, tmDZ, tmXT, g));
     AVD_LAUNCH_OK();
     return AVD_OK;
 }

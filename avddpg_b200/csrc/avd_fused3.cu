@@ -171,7 +171,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused3_kernel(const __grid_con
             const float sc2 = P[og2 + c] / sqrtf(P[ovar2 + c] + kBnEps);
             const float sh2 = P[obe2 + c] - P[omu2 + c] * sc2;
             const float w3 = P[oW3 + c];
-            b2f_tab[c] = g.b2f[(int64_t)agent * L2N + c];
             w3f_tab[c] = w3 * sc2;
             const float t = warp_sum(sh2 * w3);                  // four full warps hold the 128 columns
             if (lane == 0) scal[1 + (c >> 5)] = t;
@@ -189,6 +188,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused3_kernel(const __grid_con
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // Everything above only read the parameters (last written by the previous step's Adam / Polyak launch).  From here on the
+    // kernel consumes what earlier launches of this step produced (folded weights and bias, actions, TD targets, dz2 ...).
+    pdl_wait();
+    pdl_launch_dependents();
+    if (threadIdx.x >= 32 && threadIdx.x < 32 + L2N) b2f_tab[threadIdx.x - 32] = g.b2f[(int64_t)agent * L2N + threadIdx.x - 32];   // written by the pack kernel, possibly the previous launch
+    __syncthreads();
     const float b3f = scal[5] + scal[1] + scal[2] + scal[3] + scal[4];       // b3' = b3 + sh2 . w3
     if (T <= 0) {   // never happens with the host-side grid; keep the TMEM bookkeeping correct anyway
         __syncthreads();
@@ -661,7 +666,7 @@ static int launch(const CUtensorMap& tmW, const CUtensorMap& tmDZ, const Args& g
         AVD_CUDA_OK(cudaFuncSetAttribute(fused3_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         attr_set = true;
     }
-    fused3_kernel<MODE><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmW, tmDZ, g);
+    AVD_CUDA_OK(launch_pdl(fused3_kernel<MODE>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, st, tmW, tmDZ, g));
     AVD_LAUNCH_OK();
     return AVD_OK;
 }

@@ -1,4 +1,5 @@
 // avd_lib.cu -- library-level entry points: ABI version, last-error text, device probe.
+#include <cstdlib>
 #include <stdarg.h>
 #include <string.h>
 
@@ -20,6 +21,14 @@ void set_error(const char* fmt, ...) {
 static std::atomic<long long> g_launches{0};
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+bool pdl_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("AVD_PDL");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
 
 int sm_count() {
     static int cached = 0;

@@ -139,6 +139,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad3_kernel(const __grid_con
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();                      // the prologue only read the parameters; dz2 comes from the previous launch
+    pdl_launch_dependents();
     auto tile_of = [&](int tc) { return cta + tc * g.ctas_per_agent; };
     // Work is a sequence of slab steps q = t FT + s (row tile t, feature slab s); r1 buffer q % NRB.  State slabs (s < 2) go
     // through the layer-1 MMA in half-slab units u = 4 t + 2 s + h (64 features), z1 ring entry u % NZ.
@@ -379,7 +381,7 @@ int run(const avd_net_dims& d, bool critic, int A, int64_t R, const float* param
     g.out = out; g.out_agent_stride = out_agent_stride; g.out_cta_stride = out_cta_stride;
     g.tiles_per_agent = (int)((R + TILE_M - 1) / TILE_M);
     g.ctas_per_agent = ctas_per_agent(A, R);
-    wgrad3_kernel<<<(unsigned)(A * g.ctas_per_agent), NUM_THREADS, SMEM_BYTES, st>>>(tm, g);
+    AVD_CUDA_OK(launch_pdl(wgrad3_kernel, dim3((unsigned)(A * g.ctas_per_agent)), dim3(NUM_THREADS), SMEM_BYTES, st, tm, g));
     AVD_LAUNCH_OK();
     return AVD_OK;
 }
