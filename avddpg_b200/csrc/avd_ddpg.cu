@@ -727,8 +727,9 @@ struct FoldJob {
     const float* params;
     int64_t pstride;
     FoldOff o;
+    int64_t g2, var2, W3;       // head: BatchNorm 2 scale / variance and the output weights (for w3' = sc2 w3)
     int F;
-    bf16 *W2b, *W2T;
+    bf16 *W2b, *W2T;            // W2b (dgrad operand, nullable): [F][l2] = W2' diag(w3');  W2T (forward operand): [l2][F] = W2'^T
     float* b2f;
 };
 struct FoldJobs { FoldJob j[4]; };
@@ -751,9 +752,11 @@ __global__ void __launch_bounds__(256) pack_fold4_kernel(FoldJobs jobs, int A, i
         const float sc = P[(st ? o.g[0] : o.g[1]) + c] / sqrtf(P[(st ? o.var[0] : o.var[1]) + c] + kBnEps);
         const float sh = P[(st ? o.be[0] : o.be[1]) + c] - P[(st ? o.mu[0] : o.mu[1]) + c] * sc;
         const float w = P[o.W2 + (int64_t)f * l2 + j];
-        const bf16 v = __float2bfloat16_rn(sc * w);
-        if (jb.W2b) jb.W2b[((int64_t)agent * F + f) * l2 + j] = v;
-        jb.W2T[((int64_t)agent * l2 + j) * F + f] = v;
+        if (jb.W2b) {       // the backward tile carries dq [z2 > 0] without the head weight (avd_fused3.cu): dR = dm (W2' diag(w3'))^T
+            const float w3p = P[jb.W3 + j] * P[jb.g2 + j] / sqrtf(P[jb.var2 + j] + kBnEps);
+            jb.W2b[((int64_t)agent * F + f) * l2 + j] = __float2bfloat16_rn(sc * w * w3p);
+        }
+        jb.W2T[((int64_t)agent * l2 + j) * F + f] = __float2bfloat16_rn(sc * w);
         acc = sh * w;
     }
     red[fy][threadIdx.x & 31] = acc;
@@ -805,9 +808,12 @@ struct UnfoldOff {
     int64_t W1[2], b1[2];     // layer-1 kernel / bias of the state columns [0] ([ns][l1]) and of the action columns [1] ([la])
 };
 
+struct HeadOff { int64_t g2, be2, mu2, var2, W3, b3; };
+
 __global__ void __launch_bounds__(256) unfold_kernel(const float* __restrict__ params, int64_t pstride, float* __restrict__ grads, int64_t gstride,
                                                      const float* __restrict__ G2, int64_t g2_agent_stride, int64_t g2_cta_stride,
-                                                     const float* __restrict__ G1, int ncta, UnfoldOff o, int F, int Fp, int l2, int ns) {
+                                                     const float* __restrict__ G1, int ncta, UnfoldOff o, int F, int Fp, int l2, int ns,
+                                                     const float* __restrict__ dbm, const float* __restrict__ b2f, float* __restrict__ U, HeadOff ho) {
     pdl_wait();                  // partial slices of the wgrad / dgrad launches
     pdl_launch_dependents();
     // one CTA per (feature f, agent); its 8 warps split the partial slices between them (slice w, w + 8, ...) so that every
@@ -842,19 +848,32 @@ __global__ void __launch_bounds__(256) unfold_kernel(const float* __restrict__ p
     const float sc = P[og + c] * inv;
     const float mu = P[(st ? o.f.mu[0] : o.f.mu[1]) + c];
     const float sh = P[obe + c] - mu * sc;
+    // The backward tile is dm = dq [z2 + b2' > 0] (avd_fused3.cu), so the sums arrive without the head weight:
+    //   G2m = r1^T dm,  dbm = sum_n dm   =>   G2 = G2m diag(w3'),  db2 = w3' dbm,   w3' = sc2 w3
+    // and the head-weight sum  U[j] = sum_n dq_n relu(z2 + b2')[n][j] = sum_f W2'[f][j] G2m[f][j] + b2'[j] dbm[j]  falls out of the
+    // same data (z2 = r1 W2'^T with the bf16-rounded W2' of the forward pass): every CTA adds its feature's term.
     float dsc = 0.0f, dsh = 0.0f;
 #pragma unroll
     for (int jj = 0; jj < 4; ++jj) {
         const int j = lane + 32 * jj;
         if (j < l2) {
-            float g2 = 0.0f;
+            float g2m = 0.0f;
 #pragma unroll
-            for (int w = 0; w < 8; ++w) g2 += red[w][j];
+            for (int w = 0; w < 8; ++w) g2m += red[w][j];
+            const float w3p = P[ho.W3 + j] * P[ho.g2 + j] / sqrtf(P[ho.var2 + j] + kBnEps);
+            const float dbmj = dbm[(int64_t)agent * l2 + j];
+            const float g2 = w3p * g2m, db2 = w3p * dbmj;
             const int64_t i = o.f.W2 + (int64_t)f * l2 + j;
-            const float w2 = P[i], db2 = G[o.f.b2 + j];
+            const float w2 = P[i];
             dsc = fmaf(w2, g2, dsc);
             dsh = fmaf(w2, db2, dsh);
             G[i] = fmaf(sc, g2, sh * db2);
+            float uj = __bfloat162float(__float2bfloat16_rn(sc * w2)) * g2m;
+            if (f == 0) {
+                uj = fmaf(b2f[(int64_t)agent * l2 + j], dbmj, uj);
+                G[o.f.b2 + j] = db2;
+            }
+            atomicAdd(U + (int64_t)agent * l2 + j, uj);
         }
     }
     dsc = warp_sum(dsc);
@@ -882,8 +901,6 @@ __global__ void __launch_bounds__(256) unfold_kernel(const float* __restrict__ p
 // Head / BN2 gradients from the sums the fused backward pass accumulates (avd_fused3.cu):
 //   U[j] = sum_n dq_n relu(z2)[n][j],  sd = sum_n dq_n,   h2 = relu(z2) sc2 + sh2,   q = h2 . w3 + b3
 //   dW3 = sc2 U + sh2 sd;   dgamma2 = w3 inv2 (U - mu2 sd);   dbeta2 = w3 sd;   db3 = sd     (db2 comes out of the wgrad GEMM)
-struct HeadOff { int64_t g2, be2, mu2, var2, W3, b3; };
-
 __global__ void __launch_bounds__(128) head_unfold_kernel(const float* __restrict__ params, int64_t pstride, float* __restrict__ grads, int64_t gstride,
                                                           const float* __restrict__ U, const float* __restrict__ sdq, HeadOff o, int l2) {
     pdl_wait();
@@ -913,6 +930,7 @@ struct Workspace {
     bf16* xextT;               // [A][16][Rp], Rp = R rounded up to 64
     float *G1, *G2part, *c_b2f, *tc_b2f, *a_b2f, *ta_b2f;     // G1 / G2part: one partial slice per persistent CTA (<= max(A, #SMs) slices)
     float *U, *sdq;            // [2][A][l2], [2][A]: head-gradient sums of the critic [0] and actor [1] backward passes
+    float* dbm;                // [2][A][l2]: sum_n dm[n][j] of the two backward passes (db2 = w3' dbm)
     static constexpr int kMaskWords = 10, kFp = 320, kG2Rows = 384;
     static int64_t bytes(const avd_net_dims& d, int64_t A, int64_t N) {
         const int64_t F = d.l1 + d.la;
@@ -920,7 +938,7 @@ struct Workspace {
         const int64_t packed = A * (3 * F + 3 * (int64_t)d.l1) * d.l2 * (int64_t)sizeof(bf16);
         const int64_t vecs = 4 * ((N + 3) / 4 * 4) * (int64_t)sizeof(float);
         const int64_t slices = std::max<int64_t>(A, sm_count());
-        const int64_t fold = N * (kMaskWords * 4 + 16 * 2) + A * (6 * (int64_t)d.l2 + 8) * (int64_t)sizeof(float) + A * 16 * 64 * 2 +
+        const int64_t fold = N * (kMaskWords * 4 + 16 * 2) + A * (8 * (int64_t)d.l2 + 8) * (int64_t)sizeof(float) + A * 16 * 64 * 2 +
                              slices * (kFp * 16 + kG2Rows * (int64_t)d.l2) * (int64_t)sizeof(float);
         return acts + packed + vecs + fold + 1024;
     }
@@ -953,6 +971,7 @@ struct Workspace {
         tc_b2f = p; p += A * d.l2;
         a_b2f = p; p += A * d.l2;
         ta_b2f = p; p += A * d.l2;
+        dbm = p; p += 2 * A * d.l2;
         U = p; p += 2 * A * d.l2;
         sdq = p; p += (2 * A + 3) / 4 * 4;
         mask = reinterpret_cast<uint32_t*>(p); p += N * kMaskWords;
@@ -1066,6 +1085,8 @@ struct Pass {
             jb.params = params[i];
             jb.pstride = critic[i] ? critic_off(d).total : actor_off(d).total;
             jb.o = fold_off(critic[i]);
+            if (critic[i]) { const CriticOff c = critic_off(d); jb.g2 = c.g2; jb.var2 = c.var2; jb.W3 = c.W3; }
+            else { const ActorOff a = actor_off(d); jb.g2 = a.g2; jb.var2 = a.var2; jb.W3 = a.W3; }
             jb.F = critic[i] ? d.l1 + d.la : d.l1;
             jb.W2b = W2b[i]; jb.W2T = W2T[i]; jb.b2f = b2f[i];
             Fmax = std::max(Fmax, jb.F);
@@ -1093,22 +1114,25 @@ struct Pass {
     // fused dgrad + layer-1 weight gradient (avd_dgrad3.cu), then unfold.  G2part holds the partial G2 slices the wgrad kernel
     // (avd_wgrad3.cu) stored before: [A][ncta][384][l2].
     int dgrad3_unfold(bool critic, const float* params, const bf16* DZ, const bf16* W2b, int F, int Fp, const uint32_t* mask, int mask_words,
-                      const bf16* xextT, float* G1, const float* G2part, float* grads) const {
-        const int64_t ob2 = critic ? critic_off(d).b2 : actor_off(d).b2, gs = critic ? critic_off(d).n_train : actor_off(d).n_train;
-        if (int rc = dgrad3::run(A, R, F, DZ, W2b, mask, mask_words, xextT, (R + 63) / 64 * 64, G1, Fp, grads + ob2, gs, st)) return rc;
+                      const bf16* xextT, float* G1, const float* G2part, float* grads, float* dbm, const float* b2f, float* U) const {
+        const int64_t gs = critic ? critic_off(d).n_train : actor_off(d).n_train;
+        if (int rc = dgrad3::run(A, R, F, DZ, W2b, mask, mask_words, xextT, (R + 63) / 64 * 64, G1, Fp, dbm, d.l2, st)) return rc;
         const int ncta = wgrad3::ctas_per_agent(A, R);
         UnfoldOff u;
         u.f = fold_off(critic);
         int64_t ps;
+        HeadOff ho;
         if (critic) {
             const CriticOff c = critic_off(d);
             u.W1[0] = c.Ws; u.b1[0] = c.bs; u.W1[1] = c.Wa; u.b1[1] = c.ba; ps = c.total;
+            ho = HeadOff{c.g2, c.be2, c.mu2, c.var2, c.W3, c.b3};
         } else {
             const ActorOff a = actor_off(d);
             u.W1[0] = u.W1[1] = a.W1; u.b1[0] = u.b1[1] = a.b1; ps = a.total;
+            ho = HeadOff{a.g2, a.be2, a.mu2, a.var2, a.W3, a.b3};
         }
         AVD_CUDA_OK(launch_pdl(unfold_kernel, dim3((unsigned)F, (unsigned)A), dim3(256), 0, st, params, ps, grads, gs, G2part,
-                               (int64_t)ncta * Workspace::kG2Rows * d.l2, (int64_t)Workspace::kG2Rows * d.l2, G1, ncta, u, F, Fp, d.l2, d.ns));
+                               (int64_t)ncta * Workspace::kG2Rows * d.l2, (int64_t)Workspace::kG2Rows * d.l2, G1, ncta, u, F, Fp, d.l2, d.ns, (const float*)dbm, b2f, U, ho));
         AVD_LAUNCH_OK();
         return AVD_OK;
     }
@@ -1448,9 +1472,9 @@ static int learn_fused3(const avd_learn_io* io, const Pass& p, const Workspace& 
     const int64_t g2_cta = (int64_t)Workspace::kG2Rows * d.l2, g2_agent = (int64_t)ncta * g2_cta;
     AVD_TRY(wgrad3::run(d, true, A, R, io->critic, co.total, io->s, io->a, DZ, w.G2part, g2_agent, g2_cta, st));
     tm.mark("critic_wgrad");
-    head_unfold(true, io->critic, io->critic_grad, Uc, w.sdq);
+    AVD_TRY(p.dgrad3_unfold(true, io->critic, DZ, w.cW2b, F, Fp, w.mask, MW, w.xextT, w.G1, w.G2part, io->critic_grad, w.dbm, w.c_b2f, Uc));
+    head_unfold(true, io->critic, io->critic_grad, Uc, w.sdq);            // after the unfold: it produces U
     AVD_LAUNCH_OK();
-    AVD_TRY(p.dgrad3_unfold(true, io->critic, DZ, w.cW2b, F, Fp, w.mask, MW, w.xextT, w.G1, w.G2part, io->critic_grad));
     tm.mark("critic_dgrad+unfold");
     // ---- actor loss gradient: -mean(critic(s, actor(s)))                            trainer.py:501-506
     AVD_TRY(fused3::run(fused3::MODE_ACTOR_OUT, d, A, R, io->actor, ao.total, w.aW2T, w.a_b2f, io->s, d.ns, 1, nullptr, nullptr, 0.f, io->action_high,
@@ -1464,9 +1488,10 @@ static int learn_fused3(const avd_learn_io* io, const Pass& p, const Workspace& 
     tm.mark("actor_bwd");
     AVD_TRY(wgrad3::run(d, false, A, R, io->actor, ao.total, io->s, nullptr, DZ, w.G2part, g2_agent, g2_cta, st));
     tm.mark("actor_wgrad");
+    AVD_TRY(p.dgrad3_unfold(false, io->actor, DZ, w.aW2b, d.l1, Fp, w.mask, 8, w.xextT, w.G1, w.G2part, io->actor_grad, w.dbm + (int64_t)A * d.l2,
+                            w.a_b2f, Ua));
     head_unfold(false, io->actor, io->actor_grad, Ua, w.sdq + A);
     AVD_LAUNCH_OK();
-    AVD_TRY(p.dgrad3_unfold(false, io->actor, DZ, w.aW2b, d.l1, Fp, w.mask, 8, w.xextT, w.G1, w.G2part, io->actor_grad));
     tm.mark("actor_dgrad+unfold");
     const int rc = apply_local_updates(io, (void*)st);
     tm.mark("adam+polyak");

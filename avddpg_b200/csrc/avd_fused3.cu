@@ -5,9 +5,10 @@
 //   --consumer warps-->  r1 = relu(z1) as bf16 into the 128B-swizzled K-major A tile (+ sign bits for the ReLU backward)
 //   --tcgen05.mma against the BN-folded W2'^T (resident in shared memory)-->  z2 (TMEM, double buffered)
 //   --pass 1-->  q = relu(z2 + b2') . w3' + b3'       (row sum split over four warps, combined through shared memory)
-//   --pass 2 (backward modes)-->  dq from the loss, dz2 = dq w3' [z2 + b2' > 0] as bf16 into a shared-memory tile,
-//        per-thread partial sums of  U[j] = sum_n dq_n relu(z2)[n][j]  (head / BN2 weight gradients),  sum dq,  loss
-//   --TMA store-->  the dz2 tile to HBM for the weight-gradient kernel (avd_wgrad3.cu, which recomputes r1 from the inputs)
+//   --pass 2 (backward modes)-->  dq from the loss, dm = dq [z2 + b2' > 0] as bf16 into a shared-memory tile (dz2 = dm diag(w3'):
+//        the head weight is folded into the dgrad operand and into the unfold of the weight gradient, which also yields
+//        U[j] = sum_n dq_n relu(z2)[n][j] for the head / BN2 weight gradients),  per-thread partial sums of  sum dq  and the loss
+//   --TMA store-->  the dm tile to HBM for the weight-gradient kernel (avd_wgrad3.cu, which recomputes r1 from the inputs)
 //        and the dgrad kernel (avd_dgrad3.cu)
 //   MODE_CRITIC_ACTION additionally runs the action columns of the dgrad as a third MMA (dz2 . W2'[action rows]^T) and
 //   reduces it to d(-mean q)/d(action) per row -- the critic -> actor link (trainer.py:503-506) never leaves the SM.
@@ -70,7 +71,7 @@ struct Args {
     float* out;                 // forward modes: [A*R]; MODE_CRITIC_ACTION: d loss / d action; MODE_CRITIC_BWD: q (nullable)
     uint32_t* mask_out;         // backward modes: [A*R][mask_words] sign bits of z1 (column j of word w at bit 31-j)
     int mask_words;
-    float* U;                   // backward modes: [A][128]  += sum_n dq_n relu(z2 + b2')[n][j]
+    float* U;                   // unused (the head-weight gradient sum now comes out of the unfold kernel)
     float* sdq;                 // backward modes: [A]       += sum_n dq_n
     float* loss;                // nullable; element 2*agent (+1 for the actor loss)
     int tiles_per_agent, ctas_per_agent;
@@ -308,13 +309,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused3_kernel(const __grid_con
         const int row = q * 32 + lane;
         const uint32_t tlane = (uint32_t)(q * 32) << 16;
         const float invR = 1.0f / (float)g.R;
-        float u[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) u[j] = 0.0f;
         float sdq_acc = 0.0f, loss_acc = 0.0f;
-        uint32_t rp[16];                     // backward modes: relu(z2 + b2') of this thread's 32 columns as bf16 pairs, pass 1 -> pass 2
-#pragma unroll
-        for (int j = 0; j < 16; ++j) rp[j] = 0u;
+        uint32_t zneg = 0u;                  // backward modes: sign bits of z2 + b2' of this thread's 32 columns (column j at bit 31 - j), pass 1 -> pass 2
 
         auto rowinfo = [&](int tc, bool& valid) -> int64_t {
             const int64_t r_in = (int64_t)tile_of(tc) * TILE_M + row;
@@ -435,21 +431,24 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused3_kernel(const __grid_con
             float v[32];
             tmem_ld32(tmem_base + (uint32_t)(buf * L2N + c4 * 32) + tlane, v);
             float acc = 0.0f;
+            uint32_t m = 0u;
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
                 const float4 b4 = *reinterpret_cast<const float4*>(b2f_tab + c4 * 32 + j);
                 const float4 w4 = *reinterpret_cast<const float4*>(w3f_tab + c4 * 32 + j);
-                const float r0 = fmaxf(v[j] + b4.x, 0.0f), r1 = fmaxf(v[j + 1] + b4.y, 0.0f);
-                const float r2 = fmaxf(v[j + 2] + b4.z, 0.0f), r3 = fmaxf(v[j + 3] + b4.w, 0.0f);
-                acc = fmaf(r0, w4.x, acc);
-                acc = fmaf(r1, w4.y, acc);
-                acc = fmaf(r2, w4.z, acc);
-                acc = fmaf(r3, w4.w, acc);
+                const float t0 = v[j] + b4.x, t1 = v[j + 1] + b4.y, t2 = v[j + 2] + b4.z, t3 = v[j + 3] + b4.w;
+                acc = fmaf(fmaxf(t0, 0.0f), w4.x, acc);
+                acc = fmaf(fmaxf(t1, 0.0f), w4.y, acc);
+                acc = fmaf(fmaxf(t2, 0.0f), w4.z, acc);
+                acc = fmaf(fmaxf(t3, 0.0f), w4.w, acc);
                 if (BWD) {
-                    rp[j >> 1] = pack_bf16x2(r0, r1);
-                    rp[(j >> 1) + 1] = pack_bf16x2(r2, r3);
+                    m = __funnelshift_l(__float_as_uint(t0), m, 1);
+                    m = __funnelshift_l(__float_as_uint(t1), m, 1);
+                    m = __funnelshift_l(__float_as_uint(t2), m, 1);
+                    m = __funnelshift_l(__float_as_uint(t3), m, 1);
                 }
             }
+            if (BWD) zneg = m;
             part[(buf * 4 + c4) * TILE_M + row] = acc;
             if (!ACTION) tc_fence_before();
             __syncwarp();
@@ -513,21 +512,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused3_kernel(const __grid_con
                     v[j + 3] = (v[j + 3] + b4.w > 0.0f ? dq : 0.0f) * w4.w;
                 }
             } else {
-                // relu(z2 + b2') comes back from the bf16 stash of pass 1 (exact sign; U uses the bf16-rounded value, like every
-                // other tensor-core operand of this path), so the TMEM accumulator was released a whole stage earlier
+                // The tile holds dq [z2 + b2' > 0] WITHOUT the head weight w3': it is folded into the dgrad operand (W2'' = W2' diag(w3'),
+                // pack_fold4_kernel) and into the unfold of the weight gradient, where U = sum_n dq_n relu(z2 + b2') also comes out
+                // of G2 (sum_f W2'[f][j] G2[f][j] + b2'[j] db2[j]) instead of 32 accumulator registers per thread here.  The sign
+                // bits come from pass 1, so the TMEM accumulator was released a whole stage earlier.
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const float4 w4 = *reinterpret_cast<const float4*>(w3f_tab + c4 * 32 + j);
-                    const float ww[4] = {w4.x, w4.y, w4.z, w4.w};
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const uint32_t pr = rp[(j + k) >> 1];
-                        const float r = __uint_as_float((k & 1) ? (pr & 0xFFFF0000u) : (pr << 16));
-                        const float e = r > 0.0f ? dq : 0.0f;
-                        u[j + k] = fmaf(e, r, u[j + k]);
-                        v[j + k] = e * ww[k];
-                    }
-                }
+                for (int j = 0; j < 32; ++j) v[j] = (zneg & (0x80000000u >> j)) ? 0.0f : dq;
             }
             mbar_wait(dz_empty, ((uint32_t)tc & 1) ^ 1);
             uint8_t* dzrow = smem + OFF_DZ + (c4 >> 1) * SLOT_BYTES + row * 128;
@@ -598,15 +588,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused3_kernel(const __grid_con
         if (ACTION) action_grad(T - 1);
 
         // ---- flush the per-thread partial sums of this CTA
-        if (BWD) {
-            float keep = 0.0f;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const float sj = warp_sum(u[j]);
-                if (lane == j) keep = sj;
-            }
-            atomicAdd(g.U + (int64_t)agent * L2N + c4 * 32 + lane, keep);
-        }
         if (HAS_DZ && c4 == 0) {
             const float sl = warp_sum(loss_acc), sd = warp_sum(sdq_acc);
             if (lane == 0) {
