@@ -441,22 +441,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused3_kernel(const __grid_con
                 acc = fmaf(fmaxf(t1, 0.0f), w4.y, acc);
                 acc = fmaf(fmaxf(t2, 0.0f), w4.z, acc);
                 acc = fmaf(fmaxf(t3, 0.0f), w4.w, acc);
-                if (BWD) {
+                if (HAS_DZ) {
                     m = __funnelshift_l(__float_as_uint(t0), m, 1);
                     m = __funnelshift_l(__float_as_uint(t1), m, 1);
                     m = __funnelshift_l(__float_as_uint(t2), m, 1);
                     m = __funnelshift_l(__float_as_uint(t3), m, 1);
                 }
             }
-            if (BWD) zneg = m;
+            if (HAS_DZ) zneg = m;
             part[(buf * 4 + c4) * TILE_M + row] = acc;
-            if (!ACTION) tc_fence_before();
+            tc_fence_before();
             __syncwarp();
             if (lane == 0) {
-                // Only the action mode reads the accumulator again in pass 2.  In the forward modes the quarter-0 warps release it
-                // in pass 2 instead: the layer-2 MMA of tile tc + 2 (and with it every pass1(tc + 2) that overwrites `part`)
-                // then cannot start before they have combined the partial sums of tile tc.
-                if (BWD || (!ACTION && c4 != 0)) mbar_arrive(&acc_empty[buf]);
+                // Pass 2 of the backward modes works from the sign bits kept above, so the accumulator is free again.  In the forward
+                // modes the quarter-0 warps release it in pass 2 instead: the layer-2 MMA of tile tc + 2 (and with it every
+                // pass1(tc + 2) that overwrites `part`) then cannot start before they have combined the partial sums of tile tc.
+                if (HAS_DZ || c4 != 0) mbar_arrive(&acc_empty[buf]);
                 mbar_arrive(&part_full[buf]);
             }
         };
@@ -499,17 +499,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused3_kernel(const __grid_con
             }
             if (c4 == 0) sdq_acc += dq;
             float v[32];
-            if (ACTION) {
-                tmem_ld32(tmem_base + (uint32_t)(buf * L2N + c4 * 32) + tlane, v);
-                tc_fence_before();
+            if (ACTION) {        // dz2 = dq w3' [z2 + b2' > 0]: this tile is multiplied with the resident W2'^T block, which carries no w3'
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
-                    const float4 b4 = *reinterpret_cast<const float4*>(b2f_tab + c4 * 32 + j);
                     const float4 w4 = *reinterpret_cast<const float4*>(w3f_tab + c4 * 32 + j);
-                    v[j] = (v[j] + b4.x > 0.0f ? dq : 0.0f) * w4.x;
-                    v[j + 1] = (v[j + 1] + b4.y > 0.0f ? dq : 0.0f) * w4.y;
-                    v[j + 2] = (v[j + 2] + b4.z > 0.0f ? dq : 0.0f) * w4.z;
-                    v[j + 3] = (v[j + 3] + b4.w > 0.0f ? dq : 0.0f) * w4.w;
+                    v[j] = (zneg & (0x80000000u >> j)) ? 0.0f : dq * w4.x;
+                    v[j + 1] = (zneg & (0x40000000u >> j)) ? 0.0f : dq * w4.y;
+                    v[j + 2] = (zneg & (0x20000000u >> j)) ? 0.0f : dq * w4.z;
+                    v[j + 3] = (zneg & (0x10000000u >> j)) ? 0.0f : dq * w4.w;
                 }
             } else {
                 // The tile holds dq [z2 + b2' > 0] WITHOUT the head weight w3': it is folded into the dgrad operand (W2'' = W2' diag(w3'),
@@ -529,10 +526,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused3_kernel(const __grid_con
             }
             fence_proxy_async();
             __syncwarp();
-            if (lane == 0) {
-                if (ACTION) mbar_arrive(&acc_empty[buf]);
-                mbar_arrive(dz_full);
-            }
+            if (lane == 0) mbar_arrive(dz_full);
         };
 
         // ---- stage 4 (MODE_CRITIC_ACTION): d loss / d action = sum_f [za_f > 0] dRa_f wa_f      (trainer.py:503-506)
