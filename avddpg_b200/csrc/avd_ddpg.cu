@@ -810,23 +810,25 @@ struct UnfoldOff {
 
 struct HeadOff { int64_t g2, be2, mu2, var2, W3, b3; };
 
-__global__ void __launch_bounds__(256) unfold_kernel(const float* __restrict__ params, int64_t pstride, float* __restrict__ grads, int64_t gstride,
+constexpr int kUnfoldWarps = 4;      // 128-thread CTAs: 16 per SM, so that the F x A <= 320 x 4 CTAs of the C2 case are a single wave
+
+__global__ void __launch_bounds__(32 * kUnfoldWarps) unfold_kernel(const float* __restrict__ params, int64_t pstride, float* __restrict__ grads, int64_t gstride,
                                                      const float* __restrict__ G2, int64_t g2_agent_stride, int64_t g2_cta_stride,
                                                      const float* __restrict__ G1, int ncta, UnfoldOff o, int F, int Fp, int l2, int ns,
                                                      const float* __restrict__ dbm, const float* __restrict__ b2f, float* __restrict__ U, HeadOff ho) {
     pdl_wait();                  // partial slices of the wgrad / dgrad launches
     pdl_launch_dependents();
-    // one CTA per (feature f, agent); its 8 warps split the partial slices between them (slice w, w + 8, ...) so that every
-    // load is independent and 64 warps per SM hide the L2 / HBM latency, then combine through shared memory
+    // one CTA per (feature f, agent); its warps split the partial slices between them (slice w, w + kUnfoldWarps, ...) so that
+    // every load is independent and 64 warps per SM hide the L2 / HBM latency, then combine through shared memory
     const int agent = blockIdx.y;
     const int f = blockIdx.x;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    __shared__ float red[8][128 + 16];
+    __shared__ float red[kUnfoldWarps][128 + 16];
     const float* g2row = G2 + (int64_t)agent * g2_agent_stride + (int64_t)f * l2;
     const float* g1row = G1 + ((int64_t)agent * ncta * Fp + f) * 16;
     float acc[4] = {0.f, 0.f, 0.f, 0.f}, acc1 = 0.0f;
 #pragma unroll 5
-    for (int sl = wid; sl < ncta; sl += 8) {
+    for (int sl = wid; sl < ncta; sl += kUnfoldWarps) {
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
             const int j = lane + 32 * jj;
@@ -859,7 +861,7 @@ __global__ void __launch_bounds__(256) unfold_kernel(const float* __restrict__ p
         if (j < l2) {
             float g2m = 0.0f;
 #pragma unroll
-            for (int w = 0; w < 8; ++w) g2m += red[w][j];
+            for (int w = 0; w < kUnfoldWarps; ++w) g2m += red[w][j];
             const float w3p = P[ho.W3 + j] * P[ho.g2 + j] / sqrtf(P[ho.var2 + j] + kBnEps);
             const float dbmj = dbm[(int64_t)agent * l2 + j];
             const float g2 = w3p * g2m, db2 = w3p * dbmj;
@@ -881,7 +883,7 @@ __global__ void __launch_bounds__(256) unfold_kernel(const float* __restrict__ p
     float g1k = 0.0f;
     if (lane < 16) {
 #pragma unroll
-        for (int w = 0; w < 8; ++w) g1k += red[w][128 + lane];
+        for (int w = 0; w < kUnfoldWarps; ++w) g1k += red[w][128 + lane];
     }
     float g1[16];
 #pragma unroll
@@ -1131,7 +1133,7 @@ struct Pass {
             u.W1[0] = u.W1[1] = a.W1; u.b1[0] = u.b1[1] = a.b1; ps = a.total;
             ho = HeadOff{a.g2, a.be2, a.mu2, a.var2, a.W3, a.b3};
         }
-        AVD_CUDA_OK(launch_pdl(unfold_kernel, dim3((unsigned)F, (unsigned)A), dim3(256), 0, st, params, ps, grads, gs, G2part,
+        AVD_CUDA_OK(launch_pdl(unfold_kernel, dim3((unsigned)F, (unsigned)A), dim3(32 * kUnfoldWarps), 0, st, params, ps, grads, gs, G2part,
                                (int64_t)ncta * Workspace::kG2Rows * d.l2, (int64_t)Workspace::kG2Rows * d.l2, G1, ncta, u, F, Fp, d.l2, d.ns, (const float*)dbm, b2f, U, ho));
         AVD_LAUNCH_OK();
         return AVD_OK;
