@@ -815,7 +815,8 @@ constexpr int kUnfoldWarps = 4;      // 128-thread CTAs: 16 per SM, so that the 
 __global__ void __launch_bounds__(32 * kUnfoldWarps) unfold_kernel(const float* __restrict__ params, int64_t pstride, float* __restrict__ grads, int64_t gstride,
                                                      const float* __restrict__ G2, int64_t g2_agent_stride, int64_t g2_cta_stride,
                                                      const float* __restrict__ G1, int ncta, UnfoldOff o, int F, int Fp, int l2, int ns,
-                                                     const float* __restrict__ dbm, const float* __restrict__ b2f, float* __restrict__ U, HeadOff ho) {
+                                                     const float* __restrict__ dbm, const float* __restrict__ b2f, float* __restrict__ U, HeadOff ho,
+                                                     const float* __restrict__ sdq, int* __restrict__ ticket) {
     pdl_wait();                  // partial slices of the wgrad / dgrad launches
     pdl_launch_dependents();
     // one CTA per (feature f, agent); its warps split the partial slices between them (slice w, w + kUnfoldWarps, ...) so that
@@ -898,28 +899,30 @@ __global__ void __launch_bounds__(32 * kUnfoldWarps) unfold_kernel(const float* 
             G[o.W1[1] + c] = g1[4] + g1[12];
         }
     }
+    // ---- head / BatchNorm-2 gradients: they need the COMPLETE U of the agent, so the CTA that takes the last of the agent's F
+    // tickets does them (every CTA's atomics on U precede its ticket; the counters are zeroed with the other accumulators)
+    __threadfence();
+    int last = 0;
+    if (lane == 0) last = atomicAdd(ticket + agent, 1) == F - 1;
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (!last) return;
+    __threadfence();
+    const float sd = __ldcg(sdq + agent);
+    for (int j = lane; j < l2; j += 32) {
+        const float inv2 = 1.0f / sqrtf(P[ho.var2 + j] + kBnEps);
+        const float sc2 = P[ho.g2 + j] * inv2, mu2 = P[ho.mu2 + j];
+        const float sh2 = P[ho.be2 + j] - mu2 * sc2;
+        const float w3 = P[ho.W3 + j], u = __ldcg(U + (int64_t)agent * l2 + j);
+        G[ho.W3 + j] = fmaf(sc2, u, sh2 * sd);           // dW3 = sc2 U + sh2 sum dq
+        G[ho.g2 + j] = w3 * inv2 * (u - mu2 * sd);
+        G[ho.be2 + j] = w3 * sd;
+    }
+    if (lane == 0) G[ho.b3] = sd;
 }
 
 // Head / BN2 gradients from the sums the fused backward pass accumulates (avd_fused3.cu):
 //   U[j] = sum_n dq_n relu(z2)[n][j],  sd = sum_n dq_n,   h2 = relu(z2) sc2 + sh2,   q = h2 . w3 + b3
 //   dW3 = sc2 U + sh2 sd;   dgamma2 = w3 inv2 (U - mu2 sd);   dbeta2 = w3 sd;   db3 = sd     (db2 comes out of the wgrad GEMM)
-__global__ void __launch_bounds__(128) head_unfold_kernel(const float* __restrict__ params, int64_t pstride, float* __restrict__ grads, int64_t gstride,
-                                                          const float* __restrict__ U, const float* __restrict__ sdq, HeadOff o, int l2) {
-    pdl_wait();
-    pdl_launch_dependents();
-    const int agent = blockIdx.x, j = threadIdx.x;
-    if (j >= l2) return;
-    const float* P = params + (int64_t)agent * pstride;
-    float* G = grads + (int64_t)agent * gstride;
-    const float inv = 1.0f / sqrtf(P[o.var2 + j] + kBnEps);
-    const float sc = P[o.g2 + j] * inv, mu = P[o.mu2 + j];
-    const float sh = P[o.be2 + j] - mu * sc;
-    const float w3 = P[o.W3 + j], u = U[(int64_t)agent * l2 + j], sd = sdq[agent];
-    G[o.W3 + j] = fmaf(sc, u, sh * sd);
-    G[o.g2 + j] = w3 * inv * (u - mu * sd);
-    G[o.be2 + j] = w3 * sd;
-    if (j == 0) G[o.b3] = sd;
-}
 
 // ------------------------------------------------------------------------------------------------
 // host orchestration
@@ -933,6 +936,7 @@ struct Workspace {
     float *G1, *G2part, *c_b2f, *tc_b2f, *a_b2f, *ta_b2f;     // G1 / G2part: one partial slice per persistent CTA (<= max(A, #SMs) slices)
     float *U, *sdq;            // [2][A][l2], [2][A]: head-gradient sums of the critic [0] and actor [1] backward passes
     float* dbm;                // [2][A][l2]: sum_n dm[n][j] of the two backward passes (db2 = w3' dbm)
+    int* ticket;               // [2][A]: CTAs of the unfold kernel that have finished (the last one unfolds the head)
     static constexpr int kMaskWords = 10, kFp = 320, kG2Rows = 384;
     static int64_t bytes(const avd_net_dims& d, int64_t A, int64_t N) {
         const int64_t F = d.l1 + d.la;
@@ -940,7 +944,7 @@ struct Workspace {
         const int64_t packed = A * (3 * F + 3 * (int64_t)d.l1) * d.l2 * (int64_t)sizeof(bf16);
         const int64_t vecs = 4 * ((N + 3) / 4 * 4) * (int64_t)sizeof(float);
         const int64_t slices = std::max<int64_t>(A, sm_count());
-        const int64_t fold = N * (kMaskWords * 4 + 16 * 2) + A * (8 * (int64_t)d.l2 + 8) * (int64_t)sizeof(float) + A * 16 * 64 * 2 +
+        const int64_t fold = N * (kMaskWords * 4 + 16 * 2) + A * (8 * (int64_t)d.l2 + 16) * (int64_t)sizeof(float) + A * 16 * 64 * 2 +
                              slices * (kFp * 16 + kG2Rows * (int64_t)d.l2) * (int64_t)sizeof(float);
         return acts + packed + vecs + fold + 1024;
     }
@@ -974,6 +978,7 @@ struct Workspace {
         a_b2f = p; p += A * d.l2;
         ta_b2f = p; p += A * d.l2;
         dbm = p; p += 2 * A * d.l2;
+        ticket = reinterpret_cast<int*>(p); p += (2 * A + 3) / 4 * 4;
         U = p; p += 2 * A * d.l2;
         sdq = p; p += (2 * A + 3) / 4 * 4;
         mask = reinterpret_cast<uint32_t*>(p); p += N * kMaskWords;
@@ -1116,7 +1121,8 @@ struct Pass {
     // fused dgrad + layer-1 weight gradient (avd_dgrad3.cu), then unfold.  G2part holds the partial G2 slices the wgrad kernel
     // (avd_wgrad3.cu) stored before: [A][ncta][384][l2].
     int dgrad3_unfold(bool critic, const float* params, const bf16* DZ, const bf16* W2b, int F, int Fp, const uint32_t* mask, int mask_words,
-                      const bf16* xextT, float* G1, const float* G2part, float* grads, float* dbm, const float* b2f, float* U) const {
+                      const bf16* xextT, float* G1, const float* G2part, float* grads, float* dbm, const float* b2f, float* U,
+                      const float* sdq, int* ticket) const {
         const int64_t gs = critic ? critic_off(d).n_train : actor_off(d).n_train;
         if (int rc = dgrad3::run(A, R, F, DZ, W2b, mask, mask_words, xextT, (R + 63) / 64 * 64, G1, Fp, dbm, d.l2, st)) return rc;
         const int ncta = wgrad3::ctas_per_agent(A, R);
@@ -1134,7 +1140,7 @@ struct Pass {
             ho = HeadOff{a.g2, a.be2, a.mu2, a.var2, a.W3, a.b3};
         }
         AVD_CUDA_OK(launch_pdl(unfold_kernel, dim3((unsigned)F, (unsigned)A), dim3(32 * kUnfoldWarps), 0, st, params, ps, grads, gs, G2part,
-                               (int64_t)ncta * Workspace::kG2Rows * d.l2, (int64_t)Workspace::kG2Rows * d.l2, G1, ncta, u, F, Fp, d.l2, d.ns, (const float*)dbm, b2f, U, ho));
+                               (int64_t)ncta * Workspace::kG2Rows * d.l2, (int64_t)Workspace::kG2Rows * d.l2, G1, ncta, u, F, Fp, d.l2, d.ns, (const float*)dbm, b2f, U, ho, sdq, ticket));
         AVD_LAUNCH_OK();
         return AVD_OK;
     }
@@ -1452,13 +1458,6 @@ static int learn_fused3(const avd_learn_io* io, const Pass& p, const Workspace& 
     xext_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(io->s, io->a, d.ns, N, w.xextT, R, Rp);
     AVD_LAUNCH_OK();
     tm.mark("fold+xext");
-    auto head_unfold = [&](bool critic, const float* params, float* grads, const float* U, const float* sdq) {
-        HeadOff o;
-        int64_t ps, gs;
-        if (critic) { o = HeadOff{co.g2, co.be2, co.mu2, co.var2, co.W3, co.b3}; ps = co.total; gs = co.n_train; }
-        else { o = HeadOff{ao.g2, ao.be2, ao.mu2, ao.var2, ao.W3, ao.b3}; ps = ao.total; gs = ao.n_train; }
-        launch_pdl(head_unfold_kernel, dim3((unsigned)A), dim3(128), 0, st, params, ps, grads, gs, U, sdq, o, d.l2);
-    };
     // ---- TD target: y = r + gamma * target_critic(s', target_actor(s'))            trainer.py:493-494
     AVD_TRY(fused3::run(fused3::MODE_ACTOR_OUT, d, A, R, io->t_actor, ao.total, w.taW2T, w.ta_b2f, io->s2, d.ns, 1, nullptr, nullptr, 0.f,
                         io->action_high, nullptr, nullptr, w.a2, nullptr, nullptr, nullptr, nullptr, nullptr, st));
@@ -1474,9 +1473,8 @@ static int learn_fused3(const avd_learn_io* io, const Pass& p, const Workspace& 
     const int64_t g2_cta = (int64_t)Workspace::kG2Rows * d.l2, g2_agent = (int64_t)ncta * g2_cta;
     AVD_TRY(wgrad3::run(d, true, A, R, io->critic, co.total, io->s, io->a, DZ, w.G2part, g2_agent, g2_cta, st));
     tm.mark("critic_wgrad");
-    AVD_TRY(p.dgrad3_unfold(true, io->critic, DZ, w.cW2b, F, Fp, w.mask, MW, w.xextT, w.G1, w.G2part, io->critic_grad, w.dbm, w.c_b2f, Uc));
-    head_unfold(true, io->critic, io->critic_grad, Uc, w.sdq);            // after the unfold: it produces U
-    AVD_LAUNCH_OK();
+    AVD_TRY(p.dgrad3_unfold(true, io->critic, DZ, w.cW2b, F, Fp, w.mask, MW, w.xextT, w.G1, w.G2part, io->critic_grad, w.dbm, w.c_b2f, Uc,
+                            w.sdq, w.ticket));
     tm.mark("critic_dgrad+unfold");
     // ---- actor loss gradient: -mean(critic(s, actor(s)))                            trainer.py:501-506
     AVD_TRY(fused3::run(fused3::MODE_ACTOR_OUT, d, A, R, io->actor, ao.total, w.aW2T, w.a_b2f, io->s, d.ns, 1, nullptr, nullptr, 0.f, io->action_high,
@@ -1491,9 +1489,7 @@ static int learn_fused3(const avd_learn_io* io, const Pass& p, const Workspace& 
     AVD_TRY(wgrad3::run(d, false, A, R, io->actor, ao.total, io->s, nullptr, DZ, w.G2part, g2_agent, g2_cta, st));
     tm.mark("actor_wgrad");
     AVD_TRY(p.dgrad3_unfold(false, io->actor, DZ, w.aW2b, d.l1, Fp, w.mask, 8, w.xextT, w.G1, w.G2part, io->actor_grad, w.dbm + (int64_t)A * d.l2,
-                            w.a_b2f, Ua));
-    head_unfold(false, io->actor, io->actor_grad, Ua, w.sdq + A);
-    AVD_LAUNCH_OK();
+                            w.a_b2f, Ua, w.sdq + A, w.ticket + A));
     tm.mark("actor_dgrad+unfold");
     const int rc = apply_local_updates(io, (void*)st);
     tm.mark("adam+polyak");
