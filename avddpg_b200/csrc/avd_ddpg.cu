@@ -10,7 +10,8 @@
 //   Adam x2 (TF-Keras form), Polyak x2
 // The three big contractions (forward, wgrad, dgrad on the l1 x l2 and (l1+la) x l2 layers, 97% of the FLOPs)
 // go through `gemm_batched`, which dispatches on io->precision: 0 = fp32 SIMT tiles (parity mode, this
-// file), 1 = bf16 tcgen05/TMEM tensor-core kernels (avd_umma.cu).  Everything else (K=ns and K=1 layers,
+// file), 1 = bf16 tcgen05/TMEM tensor-core kernels, 2 = the same kernels with fp16 layer-2 operands (11-bit significand;
+// the backward tile stays bf16) and the T formulation of the critic-action pass (avd_fused3.cu).  Everything else (K=ns and K=1 layers,
 // heads with N=1, BatchNorm affine, reductions for bias/BN gradients, TD target, losses) is fused into the
 // layer1 / head kernels below.
 //
@@ -21,6 +22,7 @@
 #include <cstdlib>
 
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "avd_common.cuh"
 #include "avd_ddpg_layout.cuh"
@@ -33,20 +35,20 @@ typedef __nv_bfloat16 bf16;
 namespace fused3 {  // avd_fused3.cu
 enum Mode { MODE_ACTOR_OUT = 0, MODE_TARGET = 1, MODE_Q = 2, MODE_CRITIC_BWD = 3, MODE_ACTOR_BWD = 4, MODE_CRITIC_ACTION = 5 };
 bool supported(const avd_net_dims& d);
-int run(int mode, const avd_net_dims& d, int A, int64_t R, const float* params, int64_t pstride, const bf16* W2T, const float* b2f, const float* s,
-        int64_t s_rs, int64_t s_cs, const float* act, const float* rew, float gamma, float high, const float* y, const float* dpi, float* out,
-        uint32_t* mask_out, bf16* DZ_out, float* U, float* sdq, float* loss, cudaStream_t st);
+int run(int mode, bool f16, const avd_net_dims& d, int A, int64_t R, const float* params, int64_t pstride, const bf16* W2T, const float* b2f,
+        const float* wscale, const float* s, int64_t s_rs, int64_t s_cs, const float* act, const float* rew, float gamma, float high, const float* y,
+        const float* dpi, float* out, uint32_t* mask_out, bf16* DZ_out, float dm_scale, float* sdq, float* loss, cudaStream_t st);
 }
 
 namespace wgrad3 {  // avd_wgrad3.cu
 int ctas_per_agent(int A, int64_t R);
-int run(const avd_net_dims& d, bool critic, int A, int64_t R, const float* params, int64_t pstride, const float* s, const float* act, const bf16* DZ,
-        float* out, int64_t out_agent_stride, int64_t out_cta_stride, cudaStream_t st);
+int run(bool f16, const avd_net_dims& d, bool critic, int A, int64_t R, const float* params, int64_t pstride, const float* s, const float* act,
+        const bf16* DZ, float* out, int64_t out_agent_stride, int64_t out_cta_stride, cudaStream_t st);
 }
 
 namespace dgrad3 {  // avd_dgrad3.cu
-int run(int A, int64_t R, int F, const bf16* DZ, const bf16* W2b, const uint32_t* mask, int mask_words, const bf16* xextT, int64_t Rp, float* G1,
-        int Fp, float* db2, int64_t db2_stride, cudaStream_t st);
+int run(bool f16, int A, int64_t R, int F, const bf16* DZ, const bf16* W2b, const uint32_t* mask, int mask_words, const bf16* xextT, int64_t Rp,
+        float* G1, int Fp, float* db2, int64_t db2_stride, cudaStream_t st);
 }
 
 namespace umma {   // avd_umma.cu
@@ -680,6 +682,16 @@ __global__ void __launch_bounds__(256) pack_w2_kernel(const float* __restrict__ 
     }
 }
 
+// 16-bit operand element: bf16 (precision 1) or fp16 (precision 2); both travel as bf16-typed pointers (TMA moves raw 16-bit words)
+__device__ __forceinline__ bf16 to_op16(float v, int f16) {
+    if (f16) {
+        const __half h = __float2half_rn(v);
+        return *reinterpret_cast<const bf16*>(&h);
+    }
+    return __float2bfloat16_rn(v);
+}
+__device__ __forceinline__ float round_op16(float v, int f16) { return f16 ? __half2float(__float2half_rn(v)) : __bfloat162float(__float2bfloat16_rn(v)); }
+
 // BN-folded packing for the fused tensor-core path.  With h1 = r1*sc1 + sh1 (r1 = relu(z1), inference BatchNorm):
 //   z2 = h1 W2 + b2 = r1 W2' + b2',   W2'[f][j] = sc1[f] W2[f][j],   b2'[j] = b2[j] + sum_f sh1[f] W2[f][j]
 // W2T [l2][F] is the forward B operand (K-major), W2b [F][l2] the dgrad B operand (nullable), b2f [l2] fp32.
@@ -691,7 +703,7 @@ struct FoldOff {
 };
 
 __global__ void __launch_bounds__(256) pack_fold_kernel(const float* __restrict__ params, int64_t pstride, FoldOff o, int F, int l2,
-                                                        bf16* __restrict__ W2b, bf16* __restrict__ W2T, float* __restrict__ b2f) {
+                                                        bf16* __restrict__ W2b, bf16* __restrict__ W2T, float* __restrict__ b2f, int f16) {
     // grid: (l2/32 column slabs, feature slabs of 8, agents); thread (fy, j) owns feature blockIdx.y*8 + fy, column j.
     // b2f must be zero on entry: every CTA adds its partial sum, the first feature slab also adds b2.
     const int agent = blockIdx.z;
@@ -707,7 +719,7 @@ __global__ void __launch_bounds__(256) pack_fold_kernel(const float* __restrict_
         const float sc = P[(st ? o.g[0] : o.g[1]) + c] / sqrtf(P[(st ? o.var[0] : o.var[1]) + c] + kBnEps);
         const float sh = P[(st ? o.be[0] : o.be[1]) + c] - P[(st ? o.mu[0] : o.mu[1]) + c] * sc;
         const float w = P[o.W2 + (int64_t)f * l2 + j];
-        const bf16 v = __float2bfloat16_rn(sc * w);
+        const bf16 v = to_op16(sc * w, f16);
         if (W2b) W2b[((int64_t)agent * F + f) * l2 + j] = v;
         W2T[((int64_t)agent * l2 + j) * F + f] = v;
         acc = sh * w;
@@ -730,14 +742,40 @@ struct FoldJob {
     int64_t g2, var2, W3;       // head: BatchNorm 2 scale / variance and the output weights (for w3' = sc2 w3)
     int F;
     bf16 *W2b, *W2T;            // W2b (dgrad operand, nullable): [F][l2] = W2' diag(w3');  W2T (forward operand): [l2][F] = W2'^T
-    float* b2f;
+    float* b2f;                 // nullable (the T pack shares the folded bias of the plain pack)
+    int tpack;                  // 1: W2T holds T^T = (W2' diag(w3') s)^T, the operand of the fp16 critic-action pass (avd_fused3.cu)
+    float* wscale;              // fp16 only, nullable: [A] 1 / s.  W2b and the T pack are scaled by s = 2^-e, max_j |w3'_j| 2^-e in [0.5, 1):
+                                // the products W2' w3' (~1e-5 at initialisation) would otherwise sit in the subnormal range of fp16
 };
-struct FoldJobs { FoldJob j[4]; };
+constexpr int kFoldJobs = 5;
+struct FoldJobs { FoldJob j[kFoldJobs]; };
 
-__global__ void __launch_bounds__(256) pack_fold4_kernel(FoldJobs jobs, int A, int l2) {
+__global__ void __launch_bounds__(256) pack_fold4_kernel(FoldJobs jobs, int A, int l2, int f16) {
     const int job = blockIdx.z / A, agent = blockIdx.z - job * A;
     const FoldJob& jb = jobs.j[job];
     if ((int)blockIdx.y * 8 >= jb.F) return;
+    float s_w3 = 1.0f;          // the power-of-two scale s of this (net, agent): every CTA derives it from the same 128 head weights
+    if (f16 && (jb.W2b || jb.tpack)) {
+        __shared__ float mx[8];
+        const float* Pq = jb.params + (int64_t)agent * jb.pstride;
+        float m = 0.0f;
+        for (int jj = threadIdx.x; jj < l2; jj += blockDim.x) m = fmaxf(m, fabsf(Pq[jb.W3 + jj] * Pq[jb.g2 + jj] / sqrtf(Pq[jb.var2 + jj] + kBnEps)));
+#pragma unroll
+        for (int o2 = 16; o2 > 0; o2 >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o2));
+        if ((threadIdx.x & 31) == 0) mx[threadIdx.x >> 5] = m;
+        __syncthreads();
+        m = mx[0];
+#pragma unroll
+        for (int k = 1; k < 8; ++k) m = fmaxf(m, mx[k]);
+        if (m > 0.0f && m < 3.0e38f) {
+            int e;
+            frexpf(m, &e);
+            e = max(-100, min(100, e));
+            s_w3 = ldexpf(1.0f, -e);
+        }
+        if (jb.wscale && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) jb.wscale[agent] = 1.0f / s_w3;
+        __syncthreads();
+    }
     const FoldOff& o = jb.o;
     const float* P = jb.params + (int64_t)agent * jb.pstride;
     const int F = jb.F;
@@ -752,16 +790,15 @@ __global__ void __launch_bounds__(256) pack_fold4_kernel(FoldJobs jobs, int A, i
         const float sc = P[(st ? o.g[0] : o.g[1]) + c] / sqrtf(P[(st ? o.var[0] : o.var[1]) + c] + kBnEps);
         const float sh = P[(st ? o.be[0] : o.be[1]) + c] - P[(st ? o.mu[0] : o.mu[1]) + c] * sc;
         const float w = P[o.W2 + (int64_t)f * l2 + j];
-        if (jb.W2b) {       // the backward tile carries dq [z2 > 0] without the head weight (avd_fused3.cu): dR = dm (W2' diag(w3'))^T
-            const float w3p = P[jb.W3 + j] * P[jb.g2 + j] / sqrtf(P[jb.var2 + j] + kBnEps);
-            jb.W2b[((int64_t)agent * F + f) * l2 + j] = __float2bfloat16_rn(sc * w * w3p);
-        }
-        jb.W2T[((int64_t)agent * l2 + j) * F + f] = __float2bfloat16_rn(sc * w);
+        const float w3p = (jb.W2b || jb.tpack) ? P[jb.W3 + j] * P[jb.g2 + j] / sqrtf(P[jb.var2 + j] + kBnEps) * s_w3 : 1.0f;
+        // the backward tile carries dq [z2 > 0] without the head weight (avd_fused3.cu): dR = dm (W2' diag(w3'))^T
+        if (jb.W2b) jb.W2b[((int64_t)agent * F + f) * l2 + j] = to_op16(sc * w * w3p, f16);
+        jb.W2T[((int64_t)agent * l2 + j) * F + f] = to_op16(jb.tpack ? sc * w * w3p : sc * w, f16);
         acc = sh * w;
     }
     red[fy][threadIdx.x & 31] = acc;
     __syncthreads();
-    if (fy == 0 && j < l2) {
+    if (fy == 0 && j < l2 && jb.b2f) {
         float t = blockIdx.y == 0 ? P[o.b2 + j] : 0.0f;
 #pragma unroll
         for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x];
@@ -774,7 +811,7 @@ __global__ void __launch_bounds__(256) pack_fold4_kernel(FoldJobs jobs, int A, i
 //   G1[f][c] = sum_n dz1[n][f] x_ext[n][c]  =>  dW1[k][f] = G1[f][k] + G1[f][8+k],  dWa[f] = G1[l1+f][4] + G1[l1+f][12],  db[f] = G1[f][5]
 // and column 5 (the constant one) also yields db2 = sum_n dz2[n][:].
 __global__ void __launch_bounds__(256) xext_kernel(const float* __restrict__ s, const float* __restrict__ a, int ns, int64_t N,
-                                                   bf16* __restrict__ xextT, int64_t R, int64_t Rp) {
+                                                   bf16* __restrict__ xextT, int64_t R, int64_t Rp, int f16) {
     const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N) return;
     float v[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
@@ -782,13 +819,13 @@ __global__ void __launch_bounds__(256) xext_kernel(const float* __restrict__ s, 
     v[4] = a[n];
     bf16 hi[8], lo[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { hi[k] = __float2bfloat16_rn(0.0f); lo[k] = hi[k]; }
+    for (int k = 0; k < 8; ++k) { hi[k] = to_op16(0.0f, f16); lo[k] = hi[k]; }
 #pragma unroll
-    for (int k = 0; k < 5; ++k) {
-        hi[k] = __float2bfloat16_rn(v[k]);
-        lo[k] = __float2bfloat16_rn(v[k] - __bfloat162float(hi[k]));
+    for (int k = 0; k < 5; ++k) {       // hi/lo split in the operand format of the dgrad kernel (bf16: 16 bits of v, fp16: 22)
+        hi[k] = to_op16(v[k], f16);
+        lo[k] = to_op16(v[k] - round_op16(v[k], f16), f16);
     }
-    hi[5] = __float2bfloat16_rn(1.0f);
+    hi[5] = to_op16(1.0f, f16);
     const int64_t agent = n / R, r = n - agent * R;
     bf16* col = xextT + agent * 16 * Rp + r;
 #pragma unroll
@@ -816,7 +853,8 @@ __global__ void __launch_bounds__(32 * kUnfoldWarps) unfold_kernel(const float* 
                                                      const float* __restrict__ G2, int64_t g2_agent_stride, int64_t g2_cta_stride,
                                                      const float* __restrict__ G1, int ncta, UnfoldOff o, int F, int Fp, int l2, int ns,
                                                      const float* __restrict__ dbm, const float* __restrict__ b2f, float* __restrict__ U, HeadOff ho,
-                                                     const float* __restrict__ sdq, int* __restrict__ ticket) {
+                                                     const float* __restrict__ sdq, int* __restrict__ ticket, const float* __restrict__ wscale, int f16,
+                                                     float inv_dm) {
     pdl_wait();                  // partial slices of the wgrad / dgrad launches
     pdl_launch_dependents();
     // one CTA per (feature f, agent); its warps split the partial slices between them (slice w, w + kUnfoldWarps, ...) so that
@@ -863,15 +901,16 @@ __global__ void __launch_bounds__(32 * kUnfoldWarps) unfold_kernel(const float* 
             float g2m = 0.0f;
 #pragma unroll
             for (int w = 0; w < kUnfoldWarps; ++w) g2m += red[w][j];
+            g2m *= inv_dm;           // the fp16 backward tile carried the power-of-two factor dm_scale (avd_fused3.cu); 1 for bf16
             const float w3p = P[ho.W3 + j] * P[ho.g2 + j] / sqrtf(P[ho.var2 + j] + kBnEps);
-            const float dbmj = dbm[(int64_t)agent * l2 + j];
+            const float dbmj = dbm[(int64_t)agent * l2 + j] * inv_dm;
             const float g2 = w3p * g2m, db2 = w3p * dbmj;
             const int64_t i = o.f.W2 + (int64_t)f * l2 + j;
             const float w2 = P[i];
             dsc = fmaf(w2, g2, dsc);
             dsh = fmaf(w2, db2, dsh);
             G[i] = fmaf(sc, g2, sh * db2);
-            float uj = __bfloat162float(__float2bfloat16_rn(sc * w2)) * g2m;
+            float uj = round_op16(sc * w2, f16) * g2m;
             if (f == 0) {
                 uj = fmaf(b2f[(int64_t)agent * l2 + j], dbmj, uj);
                 G[o.f.b2 + j] = db2;
@@ -885,6 +924,7 @@ __global__ void __launch_bounds__(32 * kUnfoldWarps) unfold_kernel(const float* 
     if (lane < 16) {
 #pragma unroll
         for (int w = 0; w < kUnfoldWarps; ++w) g1k += red[w][128 + lane];
+        g1k *= wscale ? wscale[agent] * inv_dm : inv_dm;       // the fp16 dgrad operands carried the power-of-two scales s (W2'') and dm_scale
     }
     float g1[16];
 #pragma unroll
@@ -929,7 +969,9 @@ __global__ void __launch_bounds__(32 * kUnfoldWarps) unfold_kernel(const float* 
 // ------------------------------------------------------------------------------------------------
 struct Workspace {
     float *H, *H1a, *Z, *Za, *DZ, *DH, *a2, *y, *q, *dpi;
-    bf16 *cW2b, *cW2T, *tcW2T, *aW2b, *aW2T, *taW2T;   // packed weights (precision 1)
+    bf16 *cW2b, *cW2T, *tcW2T, *aW2b, *aW2T, *taW2T;   // packed weights (precision 1: bf16; precision 2: fp16)
+    bf16* cTW2T;               // precision 2: T pack of the critic for the critic-action pass
+    float* wscale;             // precision 2: [2][A] 1 / s of the critic [0] and actor [1] W2'' / T packs
     // BN-folded tensor-core path: sign masks of z1, [x_hi | 1 | x_lo] operand, layer-1 weight-gradient accumulator, folded biases
     uint32_t* mask;
     bf16* xextT;               // [A][16][Rp], Rp = R rounded up to 64
@@ -941,7 +983,7 @@ struct Workspace {
     static int64_t bytes(const avd_net_dims& d, int64_t A, int64_t N) {
         const int64_t F = d.l1 + d.la;
         const int64_t acts = N * (2 * F + d.l1 + 3 * (int64_t)d.l2) * (int64_t)sizeof(float);
-        const int64_t packed = A * (3 * F + 3 * (int64_t)d.l1) * d.l2 * (int64_t)sizeof(bf16);
+        const int64_t packed = A * (4 * F + 3 * (int64_t)d.l1) * d.l2 * (int64_t)sizeof(bf16) + (2 * A + 4) * (int64_t)sizeof(float);
         const int64_t vecs = 4 * ((N + 3) / 4 * 4) * (int64_t)sizeof(float);
         const int64_t slices = std::max<int64_t>(A, sm_count());
         const int64_t fold = N * (kMaskWords * 4 + 16 * 2) + A * (8 * (int64_t)d.l2 + 16) * (int64_t)sizeof(float) + A * 16 * 64 * 2 +
@@ -964,7 +1006,9 @@ struct Workspace {
         aW2b = b; b += A * (int64_t)d.l1 * d.l2;
         aW2T = b; b += A * (int64_t)d.l1 * d.l2;
         taW2T = b; b += A * (int64_t)d.l1 * d.l2;
+        cTW2T = b; b += A * F * d.l2;
         p = reinterpret_cast<float*>(((uintptr_t)b + 15) & ~(uintptr_t)15);
+        wscale = p; p += (2 * A + 3) / 4 * 4;
         const int64_t Np = (N + 3) / 4 * 4;
         a2 = p; p += Np;
         y = p; p += Np;
@@ -991,13 +1035,13 @@ static int check_dims(const avd_net_dims* d, int precision = 0) {
     AVD_REQUIRE(d->ns >= 1 && d->ns <= 8, "ns=%d outside 1..8", d->ns);
     AVD_REQUIRE(d->l1 >= 4 && d->la >= 4 && d->l1 % 4 == 0 && d->la % 4 == 0 && d->la <= 64,
                 "layer sizes must be multiples of 4 and la <= 64 (l1=%d, la=%d)", d->l1, d->la);
-    AVD_REQUIRE(precision == 0 || precision == 1, "precision must be 0 (fp32 SIMT) or 1 (bf16 tcgen05)");
+    AVD_REQUIRE(precision >= 0 && precision <= 2, "precision must be 0 (fp32 SIMT), 1 (bf16 tcgen05) or 2 (fp16 tcgen05)");
     if (d->l2 != 32 && d->l2 != 64 && d->l2 != 96 && d->l2 != 128) {
         set_error("layer2 size %d not supported (32, 64, 96 or 128)", d->l2);
         return AVD_ERR_UNSUPPORTED;
     }
-    if (precision == 1 && (d->l1 % 8 || d->la % 8 || d->l2 % 8)) {
-        set_error("precision 1 needs layer sizes that are multiples of 8 (TMA 16-byte pitch)");
+    if (precision >= 1 && (d->l1 % 8 || d->la % 8 || d->l2 % 8)) {
+        set_error("precision 1 / 2 need layer sizes that are multiples of 8 (TMA 16-byte pitch)");
         return AVD_ERR_UNSUPPORTED;
     }
     return AVD_OK;
@@ -1050,6 +1094,8 @@ struct Pass {
     int64_t R;
     cudaStream_t st;
 
+    bool f16() const { return prec == 2; }     // fp16 layer-2 operands in the fused tensor-core kernels
+
     dim3 l1_grid() const { return dim3((unsigned)((R + kL1Rows - 1) / kL1Rows), A); }
 
     // layer 1 (+BN) of the actor (critic=false) or critic (true) into H ([N][F] fp32 or bf16)
@@ -1078,16 +1124,18 @@ struct Pass {
         const int F = critic ? d.l1 + d.la : d.l1;
         const int64_t ps = critic ? critic_off(d).total : actor_off(d).total;
         AVD_CUDA_OK(cudaMemsetAsync(b2f, 0, (size_t)A * d.l2 * sizeof(float), st));
-        pack_fold_kernel<<<dim3((unsigned)((d.l2 + 31) / 32), (unsigned)((F + 7) / 8), A), 256, 0, st>>>(params, ps, o, F, d.l2, W2b, W2T, b2f);
+        pack_fold_kernel<<<dim3((unsigned)((d.l2 + 31) / 32), (unsigned)((F + 7) / 8), A), 256, 0, st>>>(params, ps, o, F, d.l2, W2b, W2T, b2f, f16() ? 1 : 0);
         AVD_LAUNCH_OK();
         return AVD_OK;
     }
 
-    // all four networks of a learn step in one launch; the b2f buffers must have been zeroed
-    int pack_fold4(const float* const params[4], const bool critic[4], bf16* const W2b[4], bf16* const W2T[4], float* const b2f[4]) const {
-        FoldJobs jobs;
+    // all four networks of a learn step (+ the T pack of the critic with fp16 operands) in one launch; the b2f buffers must have
+    // been zeroed.  wscale[i] (fp16 only, nullable): [A] 1 / s of job i's W2b / T pack.
+    int pack_fold4(int njobs, const float* const params[], const bool critic[], bf16* const W2b[], bf16* const W2T[], float* const b2f[],
+                   const bool tpack[], float* const wscale[]) const {
+        FoldJobs jobs = {};
         int Fmax = 0;
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < njobs; ++i) {
             FoldJob& jb = jobs.j[i];
             jb.params = params[i];
             jb.pstride = critic[i] ? critic_off(d).total : actor_off(d).total;
@@ -1095,10 +1143,10 @@ struct Pass {
             if (critic[i]) { const CriticOff c = critic_off(d); jb.g2 = c.g2; jb.var2 = c.var2; jb.W3 = c.W3; }
             else { const ActorOff a = actor_off(d); jb.g2 = a.g2; jb.var2 = a.var2; jb.W3 = a.W3; }
             jb.F = critic[i] ? d.l1 + d.la : d.l1;
-            jb.W2b = W2b[i]; jb.W2T = W2T[i]; jb.b2f = b2f[i];
+            jb.W2b = W2b[i]; jb.W2T = W2T[i]; jb.b2f = b2f[i]; jb.tpack = tpack[i] ? 1 : 0; jb.wscale = wscale[i];
             Fmax = std::max(Fmax, jb.F);
         }
-        pack_fold4_kernel<<<dim3((unsigned)((d.l2 + 31) / 32), (unsigned)((Fmax + 7) / 8), (unsigned)(4 * A)), 256, 0, st>>>(jobs, A, d.l2);
+        pack_fold4_kernel<<<dim3((unsigned)((d.l2 + 31) / 32), (unsigned)((Fmax + 7) / 8), (unsigned)(njobs * A)), 256, 0, st>>>(jobs, A, d.l2, f16() ? 1 : 0);
         AVD_LAUNCH_OK();
         return AVD_OK;
     }
@@ -1122,9 +1170,9 @@ struct Pass {
     // (avd_wgrad3.cu) stored before: [A][ncta][384][l2].
     int dgrad3_unfold(bool critic, const float* params, const bf16* DZ, const bf16* W2b, int F, int Fp, const uint32_t* mask, int mask_words,
                       const bf16* xextT, float* G1, const float* G2part, float* grads, float* dbm, const float* b2f, float* U,
-                      const float* sdq, int* ticket) const {
+                      const float* sdq, int* ticket, const float* wscale, float dm_scale) const {
         const int64_t gs = critic ? critic_off(d).n_train : actor_off(d).n_train;
-        if (int rc = dgrad3::run(A, R, F, DZ, W2b, mask, mask_words, xextT, (R + 63) / 64 * 64, G1, Fp, dbm, d.l2, st)) return rc;
+        if (int rc = dgrad3::run(f16(), A, R, F, DZ, W2b, mask, mask_words, xextT, (R + 63) / 64 * 64, G1, Fp, dbm, d.l2, st)) return rc;
         const int ncta = wgrad3::ctas_per_agent(A, R);
         UnfoldOff u;
         u.f = fold_off(critic);
@@ -1140,7 +1188,8 @@ struct Pass {
             ho = HeadOff{a.g2, a.be2, a.mu2, a.var2, a.W3, a.b3};
         }
         AVD_CUDA_OK(launch_pdl(unfold_kernel, dim3((unsigned)F, (unsigned)A), dim3(32 * kUnfoldWarps), 0, st, params, ps, grads, gs, G2part,
-                               (int64_t)ncta * Workspace::kG2Rows * d.l2, (int64_t)Workspace::kG2Rows * d.l2, G1, ncta, u, F, Fp, d.l2, d.ns, (const float*)dbm, b2f, U, ho, sdq, ticket));
+                               (int64_t)ncta * Workspace::kG2Rows * d.l2, (int64_t)Workspace::kG2Rows * d.l2, G1, ncta, u, F, Fp, d.l2, d.ns, (const float*)dbm, b2f, U, ho, sdq, ticket,
+                               f16() ? wscale : (const float*)nullptr, f16() ? 1 : 0, 1.0f / dm_scale));
         AVD_LAUNCH_OK();
         return AVD_OK;
     }
@@ -1229,8 +1278,8 @@ extern "C" int avd_actor_forward(const avd_net_dims* dims, int32_t A, int64_t R,
     bf16* W2T = reinterpret_cast<bf16*>(Z + N * d.l2);
     if (precision && fused3::supported(d)) {   // fused kernel: H / Z are never materialised, their space holds the folded bias
         AVD_TRY(p.pack_fold(false, actor_params, nullptr, W2T, H));
-        return fused3::run(fused3::MODE_ACTOR_OUT, d, A, R, actor_params, o.total, W2T, H, s, s_rs, s_cs, nullptr, nullptr, 0.f, action_high, nullptr,
-                               nullptr, out, nullptr, nullptr, nullptr, nullptr, nullptr, p.st);
+        return fused3::run(fused3::MODE_ACTOR_OUT, p.f16(), d, A, R, actor_params, o.total, W2T, H, nullptr, s, s_rs, s_cs, nullptr, nullptr, 0.f,
+                           action_high, nullptr, nullptr, out, nullptr, nullptr, 1.0f, nullptr, nullptr, p.st);
     }
     if (precision) AVD_TRY(p.pack(actor_params, o.total, o.W2, d.l1, nullptr, W2T));
     AVD_TRY(p.layer1(false, actor_params, s, s_rs, s_cs, nullptr, H));
@@ -1259,8 +1308,8 @@ extern "C" int avd_critic_forward(const avd_net_dims* dims, int32_t A, int64_t R
     bf16* W2T = reinterpret_cast<bf16*>(Z + N * d.l2);
     if (precision && fused3::supported(d)) {
         AVD_TRY(p.pack_fold(true, critic_params, nullptr, W2T, H));
-        return fused3::run(fused3::MODE_Q, d, A, R, critic_params, o.total, W2T, H, s, d.ns, 1, a, nullptr, 0.f, 0.f, nullptr, nullptr, q, nullptr,
-                               nullptr, nullptr, nullptr, nullptr, p.st);
+        return fused3::run(fused3::MODE_Q, p.f16(), d, A, R, critic_params, o.total, W2T, H, nullptr, s, d.ns, 1, a, nullptr, 0.f, 0.f, nullptr,
+                           nullptr, q, nullptr, nullptr, 1.0f, nullptr, nullptr, p.st);
     }
     if (precision) AVD_TRY(p.pack(critic_params, o.total, o.W2, F, nullptr, W2T));
     AVD_TRY(p.layer1(true, critic_params, s, d.ns, 1, a, H));
@@ -1446,50 +1495,58 @@ static int learn_fused3(const avd_learn_io* io, const Pass& p, const Workspace& 
     float* Ua = w.U + (int64_t)A * d.l2;
     // c_b2f .. ta_b2f, U and sdq are adjacent in the workspace: one memset zeroes every accumulator of the step
     AVD_CUDA_OK(cudaMemsetAsync(w.c_b2f, 0, (size_t)((char*)(w.sdq + 2 * A) - (char*)w.c_b2f), st));
+    const bool f16 = p.f16();
+    float* const ws_c = w.wscale;
+    float* const ws_a = w.wscale + A;
     {
-        const float* const prm[4] = {io->t_actor, io->t_critic, io->critic, io->actor};
-        const bool crit[4] = {false, true, true, false};
-        bf16* const W2b[4] = {nullptr, nullptr, w.cW2b, w.aW2b};
-        bf16* const W2T[4] = {w.taW2T, w.tcW2T, w.cW2T, w.aW2T};
-        float* const b2f[4] = {w.ta_b2f, w.tc_b2f, w.c_b2f, w.a_b2f};
-        AVD_TRY(p.pack_fold4(prm, crit, W2b, W2T, b2f));
+        const float* const prm[5] = {io->t_actor, io->t_critic, io->critic, io->actor, io->critic};
+        const bool crit[5] = {false, true, true, false, true};
+        bf16* const W2b[5] = {nullptr, nullptr, w.cW2b, w.aW2b, nullptr};
+        bf16* const W2T[5] = {w.taW2T, w.tcW2T, w.cW2T, w.aW2T, w.cTW2T};
+        float* const b2f[5] = {w.ta_b2f, w.tc_b2f, w.c_b2f, w.a_b2f, nullptr};
+        const bool tpack[5] = {false, false, false, false, true};
+        float* const wsc[5] = {nullptr, nullptr, ws_c, ws_a, nullptr};
+        AVD_TRY(p.pack_fold4(f16 ? 5 : 4, prm, crit, W2b, W2T, b2f, tpack, wsc));
     }
     const int64_t Rp = (R + 63) / 64 * 64;
-    xext_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(io->s, io->a, d.ns, N, w.xextT, R, Rp);
+    xext_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(io->s, io->a, d.ns, N, w.xextT, R, Rp, f16 ? 1 : 0);
+    // fp16 backward tiles: dq ~ (q - y) / R (critic) and ~ dq/da / R (actor) are lifted by powers of two into the normal range of
+    // fp16 (they saturate at +-65504 * 2^-k instead of overflowing); the unfold kernel divides the factors out again
+    const float dm_c = f16 ? exp2f(ceilf(log2f((float)R))) : 1.0f, dm_a = f16 ? 256.0f * dm_c : 1.0f;
     AVD_LAUNCH_OK();
     tm.mark("fold+xext");
     // ---- TD target: y = r + gamma * target_critic(s', target_actor(s'))            trainer.py:493-494
-    AVD_TRY(fused3::run(fused3::MODE_ACTOR_OUT, d, A, R, io->t_actor, ao.total, w.taW2T, w.ta_b2f, io->s2, d.ns, 1, nullptr, nullptr, 0.f,
-                        io->action_high, nullptr, nullptr, w.a2, nullptr, nullptr, nullptr, nullptr, nullptr, st));
+    AVD_TRY(fused3::run(fused3::MODE_ACTOR_OUT, f16, d, A, R, io->t_actor, ao.total, w.taW2T, w.ta_b2f, nullptr, io->s2, d.ns, 1, nullptr, nullptr, 0.f,
+                        io->action_high, nullptr, nullptr, w.a2, nullptr, nullptr, 1.0f, nullptr, nullptr, st));
     tm.mark("t_actor");
-    AVD_TRY(fused3::run(fused3::MODE_TARGET, d, A, R, io->t_critic, co.total, w.tcW2T, w.tc_b2f, io->s2, d.ns, 1, w.a2, io->r, io->gamma, 0.f,
-                        nullptr, nullptr, w.y, nullptr, nullptr, nullptr, nullptr, nullptr, st));
+    AVD_TRY(fused3::run(fused3::MODE_TARGET, f16, d, A, R, io->t_critic, co.total, w.tcW2T, w.tc_b2f, nullptr, io->s2, d.ns, 1, w.a2, io->r, io->gamma, 0.f,
+                        nullptr, nullptr, w.y, nullptr, nullptr, 1.0f, nullptr, nullptr, st));
     tm.mark("t_critic");
     // ---- critic loss gradient on (s, a)                                             trainer.py:495-498
-    AVD_TRY(fused3::run(fused3::MODE_CRITIC_BWD, d, A, R, io->critic, co.total, w.cW2T, w.c_b2f, io->s, d.ns, 1, io->a, nullptr, 0.f, 0.f, w.y,
-                        nullptr, w.q, w.mask, DZ, Uc, w.sdq, io->loss, st));
+    AVD_TRY(fused3::run(fused3::MODE_CRITIC_BWD, f16, d, A, R, io->critic, co.total, w.cW2T, w.c_b2f, nullptr, io->s, d.ns, 1, io->a, nullptr, 0.f, 0.f,
+                        w.y, nullptr, w.q, w.mask, DZ, dm_c, w.sdq, io->loss, st));
     tm.mark("critic_bwd");
     const int ncta = wgrad3::ctas_per_agent(A, R);
     const int64_t g2_cta = (int64_t)Workspace::kG2Rows * d.l2, g2_agent = (int64_t)ncta * g2_cta;
-    AVD_TRY(wgrad3::run(d, true, A, R, io->critic, co.total, io->s, io->a, DZ, w.G2part, g2_agent, g2_cta, st));
+    AVD_TRY(wgrad3::run(f16, d, true, A, R, io->critic, co.total, io->s, io->a, DZ, w.G2part, g2_agent, g2_cta, st));
     tm.mark("critic_wgrad");
     AVD_TRY(p.dgrad3_unfold(true, io->critic, DZ, w.cW2b, F, Fp, w.mask, MW, w.xextT, w.G1, w.G2part, io->critic_grad, w.dbm, w.c_b2f, Uc,
-                            w.sdq, w.ticket));
+                            w.sdq, w.ticket, ws_c, dm_c));
     tm.mark("critic_dgrad+unfold");
     // ---- actor loss gradient: -mean(critic(s, actor(s)))                            trainer.py:501-506
-    AVD_TRY(fused3::run(fused3::MODE_ACTOR_OUT, d, A, R, io->actor, ao.total, w.aW2T, w.a_b2f, io->s, d.ns, 1, nullptr, nullptr, 0.f, io->action_high,
-                        nullptr, nullptr, w.a2, nullptr, nullptr, nullptr, nullptr, nullptr, st));   // pi
+    AVD_TRY(fused3::run(fused3::MODE_ACTOR_OUT, f16, d, A, R, io->actor, ao.total, w.aW2T, w.a_b2f, nullptr, io->s, d.ns, 1, nullptr, nullptr, 0.f,
+                        io->action_high, nullptr, nullptr, w.a2, nullptr, nullptr, 1.0f, nullptr, nullptr, st));   // pi
     tm.mark("actor_fwd");
-    AVD_TRY(fused3::run(fused3::MODE_CRITIC_ACTION, d, A, R, io->critic, co.total, w.cW2T, w.c_b2f, io->s, d.ns, 1, w.a2, nullptr, 0.f, 0.f, nullptr,
-                        nullptr, w.dpi, nullptr, nullptr, nullptr, nullptr, io->loss, st));          // d(-mean q)/d pi
+    AVD_TRY(fused3::run(fused3::MODE_CRITIC_ACTION, f16, d, A, R, io->critic, co.total, f16 ? w.cTW2T : w.cW2T, w.c_b2f, ws_c, io->s, d.ns, 1, w.a2,
+                        nullptr, 0.f, 0.f, nullptr, nullptr, w.dpi, nullptr, nullptr, 1.0f, nullptr, io->loss, st));          // d(-mean q)/d pi
     tm.mark("critic_action");
-    AVD_TRY(fused3::run(fused3::MODE_ACTOR_BWD, d, A, R, io->actor, ao.total, w.aW2T, w.a_b2f, io->s, d.ns, 1, nullptr, nullptr, 0.f, io->action_high,
-                        nullptr, w.dpi, nullptr, w.mask, DZ, Ua, w.sdq + A, nullptr, st));
+    AVD_TRY(fused3::run(fused3::MODE_ACTOR_BWD, f16, d, A, R, io->actor, ao.total, w.aW2T, w.a_b2f, nullptr, io->s, d.ns, 1, nullptr, nullptr, 0.f,
+                        io->action_high, nullptr, w.dpi, nullptr, w.mask, DZ, dm_a, w.sdq + A, nullptr, st));
     tm.mark("actor_bwd");
-    AVD_TRY(wgrad3::run(d, false, A, R, io->actor, ao.total, io->s, nullptr, DZ, w.G2part, g2_agent, g2_cta, st));
+    AVD_TRY(wgrad3::run(f16, d, false, A, R, io->actor, ao.total, io->s, nullptr, DZ, w.G2part, g2_agent, g2_cta, st));
     tm.mark("actor_wgrad");
     AVD_TRY(p.dgrad3_unfold(false, io->actor, DZ, w.aW2b, d.l1, Fp, w.mask, 8, w.xextT, w.G1, w.G2part, io->actor_grad, w.dbm + (int64_t)A * d.l2,
-                            w.a_b2f, Ua, w.sdq + A, w.ticket + A));
+                            w.a_b2f, Ua, w.sdq + A, w.ticket + A, ws_a, dm_a));
     tm.mark("actor_dgrad+unfold");
     const int rc = apply_local_updates(io, (void*)st);
     tm.mark("adam+polyak");

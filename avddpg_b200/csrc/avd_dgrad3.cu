@@ -58,7 +58,9 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&v);
 }
 
-template <int NC>      // 64-feature chunks of layer 1: 4 (actor, 256 features) or 5 (critic, 256 + action features)
+// NC: 64-feature chunks of layer 1: 4 (actor, 256 features) or 5 (critic, 256 + action features).  F16 (precision = 2): every
+// operand -- dz2 tile, W2'', the staged dz1 chunks and the hi/lo-split x_ext -- is fp16 instead of bf16 (no mixed-format MMA on B200).
+template <int NC, bool F16>
 __global__ void __launch_bounds__(NUM_THREADS, 1) dgrad3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmDZ,
                                                                 const __grid_constant__ CUtensorMap tmXT, Args g) {
     extern __shared__ uint8_t smem_raw[];
@@ -109,9 +111,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dgrad3_kernel(const __grid_con
         // A tcgen05.commit only tracks the MMAs of its own thread, so the dz2 tile is handed back by both (a_empty counts 2).
         if (T > 0) {
             const uint32_t leader = elect_one();
-            constexpr uint32_t idesc_2 = make_idesc_bf16(TILE_M, 128, false, false);   // dz2 (K-major) x W2' chunk pair (K-major)
-            constexpr uint32_t idesc_1 = make_idesc_bf16(TILE_M, 64, false, false);    // ... x single chunk
-            constexpr uint32_t idesc_g = make_idesc_bf16(TILE_M, 16, true, false);     // dz1 / dz2 (MN-major) x xext^T (K-major)
+            constexpr uint32_t FOP = F16 ? FMT_F16 : FMT_BF16;
+            constexpr uint32_t idesc_2 = make_idesc_f16kind(TILE_M, 128, false, false, FOP, FOP);   // dz2 (K-major) x W2'' chunk pair (K-major)
+            constexpr uint32_t idesc_1 = make_idesc_f16kind(TILE_M, 64, false, false, FOP, FOP);    // ... x single chunk
+            constexpr uint32_t idesc_g = make_idesc_f16kind(TILE_M, 16, true, false, FOP, FOP);     // dz1 / dz2 (MN-major) x xext^T (K-major)
             const uint64_t dA = make_smem_desc(smem_u32(smem + OFF_A), 16, 1024);                 // dz2 tile as K-major A
             const uint64_t dAt = make_smem_desc(smem_u32(smem + OFF_A), TILE_M * 128, 1024);      // dz2 tile as MN-major A (two 64-column halves)
             const uint64_t dW = make_smem_desc(smem_u32(smem + OFF_W), 16, 1024);
@@ -229,7 +232,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dgrad3_kernel(const __grid_con
                     for (int j = 0; j < 32; ++j)
                         if (neg & (0x80000000u >> j)) v[j] = 0.0f;
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) pkd[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+                    for (int j = 0; j < 16; ++j) pkd[j] = pack_x2<F16>(v[2 * j], v[2 * j + 1]);
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -317,17 +320,20 @@ static int make_map(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t 
     return AVD_OK;
 }
 
-// DZ: bf16 [A*R][128];  W2b: bf16 [A][F][128] folded layer-2 kernel;  mask: [A*R][mask_words];  xextT: bf16 [A][16][Rp]
+// DZ: 16-bit [A*R][128];  W2b: [A][F][128] folded layer-2 kernel W2'' = W2' diag(w3') (bf16, or with f16 = true everything fp16, W2b
+// scaled by a power of two s per agent and DZ by dm_scale: G1 / db2 then carry those factors, which the unfold kernel divides out);  mask: [A*R][mask_words];  xextT: bf16 [A][16][Rp]
 // (Rp = rows per agent rounded up to a multiple of 64);  G1: fp32 [A][ctas_per_agent][Fp][16] partial slices, one per CTA, plain
 // stores (rows < F; the caller sums them);  db2: fp32 [A][db2_stride] (first 128 entries), accumulated into (zero it first).
-int run(int A, int64_t R, int F, const bf16* DZ, const bf16* W2b, const uint32_t* mask, int mask_words, const bf16* xextT, int64_t Rp, float* G1,
+int run(bool f16, int A, int64_t R, int F, const bf16* DZ, const bf16* W2b, const uint32_t* mask, int mask_words, const bf16* xextT, int64_t Rp, float* G1,
         int Fp, float* db2, int64_t db2_stride, cudaStream_t st) {
     AVD_REQUIRE(A >= 1 && R >= 1 && F > 192 && F % 16 == 0 && F <= MAX_NC * 64 && Fp >= F, "bad sizes for the fused dgrad kernel");
     AVD_REQUIRE(DZ && W2b && mask && xextT && G1 && db2 && Rp % 64 == 0 && Rp >= R, "null buffer / bad pitch");
     static bool attr_set = false;
     if (!attr_set) {
-        AVD_CUDA_OK(cudaFuncSetAttribute(dgrad3_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        AVD_CUDA_OK(cudaFuncSetAttribute(dgrad3_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        AVD_CUDA_OK(cudaFuncSetAttribute(dgrad3_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        AVD_CUDA_OK(cudaFuncSetAttribute(dgrad3_kernel<5, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        AVD_CUDA_OK(cudaFuncSetAttribute(dgrad3_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        AVD_CUDA_OK(cudaFuncSetAttribute(dgrad3_kernel<5, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         attr_set = true;
     }
     CUtensorMap tmW, tmDZ, tmXT;
@@ -339,8 +345,10 @@ int run(int A, int64_t R, int F, const bf16* DZ, const bf16* W2b, const uint32_t
     g.tiles_per_agent = (int)((R + TILE_M - 1) / TILE_M);
     g.ctas_per_agent = std::max(1, std::min(g.tiles_per_agent, sm_count() / std::max(1, A)));      // == wgrad3::ctas_per_agent(A, R)
     const unsigned grid = (unsigned)(g.ctas_per_agent * A);
-    if (g.NC == 4) AVD_CUDA_OK(launch_pdl(dgrad3_kernel<4>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, st, tmW, tmDZ, tmXT, g));
-    else AVD_CUDA_OK(launch_pdl(dgrad3_kernel<5>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, st, tmW, tmDZ, tmXT, g));
+    if (g.NC == 4 && !f16) AVD_CUDA_OK(launch_pdl(dgrad3_kernel<4, false>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, st, tmW, tmDZ, tmXT, g));
+    else if (!f16) AVD_CUDA_OK(launch_pdl(dgrad3_kernel<5, false>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, st, tmW, tmDZ, tmXT, g));
+    else if (g.NC == 4) AVD_CUDA_OK(launch_pdl(dgrad3_kernel<4, true>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, st, tmW, tmDZ, tmXT, g));
+    else AVD_CUDA_OK(launch_pdl(dgrad3_kernel<5, true>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, st, tmW, tmDZ, tmXT, g));
     AVD_LAUNCH_OK();
     return AVD_OK;
 }

@@ -71,7 +71,8 @@ struct Args {
     float* out;                 // forward modes: [A*R]; MODE_CRITIC_ACTION: d loss / d action; MODE_CRITIC_BWD: q (nullable)
     uint32_t* mask_out;         // backward modes: [A*R][mask_words] sign bits of z1 (column j of word w at bit 31-j)
     int mask_words;
-    float* U;                   // unused (the head-weight gradient sum now comes out of the unfold kernel)
+    const float* wscale;        // MODE_CRITIC_ACTION with fp16 operands: [A] 1 / s of the T = W2' diag(w3') s pack (pack_fold4_kernel)
+    float dm_scale;             // backward modes: power-of-two factor on the dm tile (1 for bf16; fp16 needs dq ~ 1 / R lifted into its range)
     float* sdq;                 // backward modes: [A]       += sum_n dq_n
     float* loss;                // nullable; element 2*agent (+1 for the actor loss)
     int tiles_per_agent, ctas_per_agent;
@@ -79,6 +80,10 @@ struct Args {
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
     __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {
+    __half2 v = __floats2half2_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&v);
 }
 __device__ __forceinline__ uint64_t make_desc_noswz(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -93,7 +98,16 @@ __device__ __forceinline__ uint32_t pack2(bf16 a, bf16 b) {
     return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
 }
 
-template <int MODE>
+// F16 (precision = 2): the layer-2 operands r1 and W2'^T and the backward tile dm are fp16 instead of bf16 (same tensor-pipe
+// rate, 11-bit significand; B200 has no mixed fp16 x bf16 MMA).  dm = dq [z2 > 0] is written as dm_scale * dq with a power-of-two
+// dm_scale ~ R (dq ~ 1 / R would sit in the subnormal range of fp16), saturating; the unfold kernel divides it out.
+// MODE_CRITIC_ACTION then runs on
+// T = W2' diag(w3') s  (s = power of two, pack_fold4_kernel) in place of W2':  the accumulator holds s w3'_j z2_j, so
+//   u_j = sg_j (acc_j + s w3'_j b2'_j) = s |w3'_j| (z2_j + b2'_j)     has the sign of z2_j + b2'_j,      sg_j = sign(w3'_j)
+//   q   = sum_j max(u_j, 0) sg_j / s + b3'
+// and the action-column dgrad multiplies the EXACT 0/1 tile [z2 + b2' > 0] with the resident T block (one fp16 rounding per
+// weight, instead of bf16(dq w3') x bf16(W2')):   d(-mean q)/d a = -(1 / (R s)) sum_f [za_f > 0] wa_f sum_j [z2_j + b2'_j > 0] T[f][j].
+template <int MODE, bool F16>
 __global__ void __launch_bounds__(NUM_THREADS, 1) fused3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmDZ, Args g) {
     constexpr bool CRITIC = MODE != MODE_ACTOR_OUT && MODE != MODE_ACTOR_BWD;
     constexpr bool BWD = MODE == MODE_CRITIC_BWD || MODE == MODE_ACTOR_BWD;      // full backward: masks, r1 / dz2 to HBM, U
@@ -103,6 +117,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused3_kernel(const __grid_con
     // k-block kb of local tile t lives in ring slot (t NKB + kb) % NSLOT: with more slots than k-blocks the converters of the
     // next tile start while the layer-2 MMA of this tile still reads its operands
     constexpr int NSLOT = HAS_DZ ? 5 : MAX_SLOT;
+    constexpr bool TFORM = ACTION && F16;                                        // T formulation of the critic-action pass
+    constexpr uint32_t FOP = F16 ? FMT_F16 : FMT_BF16;                           // format of the layer-2 operands
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -193,7 +209,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused3_kernel(const __grid_con
     // kernel consumes what earlier launches of this step produced (folded weights and bias, actions, TD targets, dz2 ...).
     pdl_wait();
     pdl_launch_dependents();
-    if (threadIdx.x >= 32 && threadIdx.x < 32 + L2N) b2f_tab[threadIdx.x - 32] = g.b2f[(int64_t)agent * L2N + threadIdx.x - 32];   // written by the pack kernel, possibly the previous launch
+    const float inv_s = TFORM ? g.wscale[agent] : 1.0f;      // power of two
+    if (threadIdx.x >= 32 && threadIdx.x < 32 + L2N) {       // written by the pack kernel, possibly the previous launch
+        const int j = threadIdx.x - 32;
+        const float b2 = g.b2f[(int64_t)agent * L2N + j];
+        if (TFORM) {
+            const float w3p = w3f_tab[j];
+            b2f_tab[j] = fabsf(w3p) * (1.0f / inv_s) * b2;                      // sg_j s w3'_j b2'_j
+            w3f_tab[j] = w3p > 0.0f ? 1.0f : (w3p < 0.0f ? -1.0f : 0.0f);       // sg_j
+        } else {
+            b2f_tab[j] = b2;
+        }
+    }
     __syncthreads();
     const float b3f = scal[5] + scal[1] + scal[2] + scal[3] + scal[4];       // b3' = b3 + sh2 . w3
     if (T <= 0) {   // never happens with the host-side grid; keep the TMEM bookkeeping correct anyway
@@ -209,8 +236,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused3_kernel(const __grid_con
         // warp-uniform control flow; the one-thread instructions are predicated on an elected lane (see avd_umma.cuh)
         {
             const uint32_t leader = elect_one();
-            constexpr uint32_t idesc = make_idesc_bf16(TILE_M, L2N, false, false);
-            constexpr uint32_t idesc_act = make_idesc_bf16(TILE_M, 64, false, true);      // dz2 (K-major) x W2'^T block (MN-major)
+            constexpr uint32_t idesc1 = make_idesc_bf16(TILE_M, L2N, false, false);      // layer 1: hi/lo-split bf16
+            constexpr uint32_t idesc = make_idesc_f16kind(TILE_M, L2N, false, false, FOP, FOP);
+            constexpr uint32_t idesc_act = make_idesc_f16kind(TILE_M, 64, false, true, FOP, FOP);      // dz2 (K-major) x W2'^T block (MN-major)
             const int F = L1N + la;
             const uint64_t dW = make_smem_desc(smem_u32(smem + OFF_W), 16, 1024);
             const uint64_t dR = make_smem_desc(smem_u32(smem + OFF_RING), 16, 1024);
@@ -226,7 +254,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused3_kernel(const __grid_con
                 tc_fence_after();
 #pragma unroll
                 for (int h = 0; h < 2; ++h)
-                    mma_bf16_p(leader, tmem_base + 256u + (uint32_t)(h * L2N), desc_add(dX, (uint32_t)(t & 1) * X_BYTES), desc_add(dB1, h * (L2N * 16)), idesc, 0);
+                    mma_bf16_p(leader, tmem_base + 256u + (uint32_t)(h * L2N), desc_add(dX, (uint32_t)(t & 1) * X_BYTES), desc_add(dB1, h * (L2N * 16)), idesc1, 0);
                 mma_commit_p(leader, z1_full);
             };
             auto mma2 = [&](int t) {          // layer 2 of local tile t -> TMEM accumulator t & 1
@@ -371,8 +399,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused3_kernel(const __grid_con
                 neg[h] = m;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    const uint4 pk = make_uint4(pack_relu_bf16x2(z[8 * k], z[8 * k + 1]), pack_relu_bf16x2(z[8 * k + 2], z[8 * k + 3]),
-                                                pack_relu_bf16x2(z[8 * k + 4], z[8 * k + 5]), pack_relu_bf16x2(z[8 * k + 6], z[8 * k + 7]));
+                    const uint4 pk = make_uint4(pack_relu_x2<F16>(z[8 * k], z[8 * k + 1]), pack_relu_x2<F16>(z[8 * k + 2], z[8 * k + 3]),
+                                                pack_relu_x2<F16>(z[8 * k + 4], z[8 * k + 5]), pack_relu_x2<F16>(z[8 * k + 6], z[8 * k + 7]));
                     *reinterpret_cast<uint4*>(slot + (((h * 4 + k) ^ (row & 7)) << 4)) = pk;      // SWIZZLE_128B
                 }
             }
@@ -397,8 +425,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused3_kernel(const __grid_con
                 for (int k = 0; k < 4; ++k) {
                     const int col = j0 + 8 * k;
                     if (col < la) {
-                        const uint4 pk = make_uint4(pack_relu_bf16x2(z[8 * k], z[8 * k + 1]), pack_relu_bf16x2(z[8 * k + 2], z[8 * k + 3]),
-                                                    pack_relu_bf16x2(z[8 * k + 4], z[8 * k + 5]), pack_relu_bf16x2(z[8 * k + 6], z[8 * k + 7]));
+                        const uint4 pk = make_uint4(pack_relu_x2<F16>(z[8 * k], z[8 * k + 1]), pack_relu_x2<F16>(z[8 * k + 2], z[8 * k + 3]),
+                                                    pack_relu_x2<F16>(z[8 * k + 4], z[8 * k + 5]), pack_relu_x2<F16>(z[8 * k + 6], z[8 * k + 7]));
                         *reinterpret_cast<uint4*>(aslot + (((col >> 3) ^ (row & 7)) << 4)) = pk;
                     }
                 }
@@ -436,7 +464,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused3_kernel(const __grid_con
             for (int j = 0; j < 32; j += 4) {
                 const float4 b4 = *reinterpret_cast<const float4*>(b2f_tab + c4 * 32 + j);
                 const float4 w4 = *reinterpret_cast<const float4*>(w3f_tab + c4 * 32 + j);
-                const float t0 = v[j] + b4.x, t1 = v[j + 1] + b4.y, t2 = v[j + 2] + b4.z, t3 = v[j + 3] + b4.w;
+                // T formulation: w4 = sg, b4 = sg s w3' b2'  =>  t = s |w3'| (z2 + b2'), and max(t, 0) sg sums to s (q - b3')
+                const float t0 = TFORM ? fmaf(v[j], w4.x, b4.x) : v[j] + b4.x, t1 = TFORM ? fmaf(v[j + 1], w4.y, b4.y) : v[j + 1] + b4.y;
+                const float t2 = TFORM ? fmaf(v[j + 2], w4.z, b4.z) : v[j + 2] + b4.z, t3 = TFORM ? fmaf(v[j + 3], w4.w, b4.w) : v[j + 3] + b4.w;
                 acc = fmaf(fmaxf(t0, 0.0f), w4.x, acc);
                 acc = fmaf(fmaxf(t1, 0.0f), w4.y, acc);
                 acc = fmaf(fmaxf(t2, 0.0f), w4.z, acc);
@@ -471,7 +501,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused3_kernel(const __grid_con
             if (ACTION && c4 == (tc & 3)) a_ag = __ldg(g.act + nrow);   // consumed by action_grad(tc), two stages later
             mbar_wait(&part_full[buf], ((uint32_t)tc >> 1) & 1);
             const float* pb = part + buf * 4 * TILE_M + row;
-            const float qv = pb[0] + pb[TILE_M] + pb[2 * TILE_M] + pb[3 * TILE_M] + b3f;
+            const float qv = TFORM ? fmaf(pb[0] + pb[TILE_M] + pb[2 * TILE_M] + pb[3 * TILE_M], inv_s, b3f)
+                                   : pb[0] + pb[TILE_M] + pb[2 * TILE_M] + pb[3 * TILE_M] + b3f;
             if (!HAS_DZ) {
                 float o;
                 if (MODE == MODE_ACTOR_OUT) o = g.high * tanhf(qv);
@@ -499,7 +530,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused3_kernel(const __grid_con
             }
             if (c4 == 0) sdq_acc += dq;
             float v[32];
-            if (ACTION) {        // dz2 = dq w3' [z2 + b2' > 0]: this tile is multiplied with the resident W2'^T block, which carries no w3'
+            if (TFORM) {         // the exact 0/1 tile [z2 + b2' > 0]; dq = -1/R and 1/s are applied to the row sum in action_grad()
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = (zneg & (0x80000000u >> j)) ? 0.0f : 1.0f;
+            } else if (ACTION) { // dz2 = dq w3' [z2 + b2' > 0]: this tile is multiplied with the resident W2'^T block, which carries no w3'
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
                     const float4 w4 = *reinterpret_cast<const float4*>(w3f_tab + c4 * 32 + j);
@@ -513,15 +547,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused3_kernel(const __grid_con
                 // pack_fold4_kernel) and into the unfold of the weight gradient, where U = sum_n dq_n relu(z2 + b2') also comes out
                 // of G2 (sum_f W2'[f][j] G2[f][j] + b2'[j] db2[j]) instead of 32 accumulator registers per thread here.  The sign
                 // bits come from pass 1, so the TMEM accumulator was released a whole stage earlier.
+                const float dqs = dq * g.dm_scale;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = (zneg & (0x80000000u >> j)) ? 0.0f : dq;
+                for (int j = 0; j < 32; ++j) v[j] = (zneg & (0x80000000u >> j)) ? 0.0f : dqs;
             }
             mbar_wait(dz_empty, ((uint32_t)tc & 1) ^ 1);
             uint8_t* dzrow = smem + OFF_DZ + (c4 >> 1) * SLOT_BYTES + row * 128;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const uint4 pk = make_uint4(pack_bf16x2(v[8 * k], v[8 * k + 1]), pack_bf16x2(v[8 * k + 2], v[8 * k + 3]),
-                                            pack_bf16x2(v[8 * k + 4], v[8 * k + 5]), pack_bf16x2(v[8 * k + 6], v[8 * k + 7]));
+                const uint4 pk = TFORM ? make_uint4(pack_f16x2(v[8 * k], v[8 * k + 1]), pack_f16x2(v[8 * k + 2], v[8 * k + 3]),
+                                                    pack_f16x2(v[8 * k + 4], v[8 * k + 5]), pack_f16x2(v[8 * k + 6], v[8 * k + 7]))
+                                       : make_uint4(pack_x2<F16>(v[8 * k], v[8 * k + 1]), pack_x2<F16>(v[8 * k + 2], v[8 * k + 3]),
+                                                    pack_x2<F16>(v[8 * k + 4], v[8 * k + 5]), pack_x2<F16>(v[8 * k + 6], v[8 * k + 7]));
                 *reinterpret_cast<uint4*>(dzrow + ((((c4 & 1) * 4 + k) ^ (row & 7)) << 4)) = pk;
             }
             fence_proxy_async();
@@ -554,7 +591,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused3_kernel(const __grid_con
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(dra_empty);
-            if (valid) g.out[nrow] = acc;
+            if (valid) g.out[nrow] = TFORM ? acc * (-invR * inv_s) : acc;
         };
 
         // ---- software pipeline
@@ -634,23 +671,28 @@ bool supported(const avd_net_dims& d) {
     return d.l2 == L2N && d.ns >= 1 && d.ns <= 4 && d.l1 == L1N && d.la % 16 == 0 && d.la >= 16 && d.la <= 64;
 }
 
-template <int MODE>
-static int launch(const CUtensorMap& tmW, const CUtensorMap& tmDZ, const Args& g, dim3 grid, cudaStream_t st) {
+template <int MODE, bool F16>
+static int launch2(const CUtensorMap& tmW, const CUtensorMap& tmDZ, const Args& g, dim3 grid, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        AVD_CUDA_OK(cudaFuncSetAttribute(fused3_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        AVD_CUDA_OK(cudaFuncSetAttribute(fused3_kernel<MODE, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         attr_set = true;
     }
-    AVD_CUDA_OK(launch_pdl(fused3_kernel<MODE>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, st, tmW, tmDZ, g));
+    AVD_CUDA_OK(launch_pdl(fused3_kernel<MODE, F16>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, st, tmW, tmDZ, g));
     AVD_LAUNCH_OK();
     return AVD_OK;
 }
+template <int MODE>
+static int launch(bool f16, const CUtensorMap& tmW, const CUtensorMap& tmDZ, const Args& g, dim3 grid, cudaStream_t st) {
+    return f16 ? launch2<MODE, true>(tmW, tmDZ, g, grid, st) : launch2<MODE, false>(tmW, tmDZ, g, grid, st);
+}
 
-// One pass.  W2T: bf16 [A][128][F] folded layer-2 kernel (K-major), b2f: [A][128]  (pack_fold_kernel).
-// Backward modes: mask_out [A*R][2*ceil(F/64)] sign masks of z1, DZ_out: bf16 [A*R][128], U [A][128] and sdq [A] accumulated into.
-int run(int mode, const avd_net_dims& d, int A, int64_t R, const float* params, int64_t pstride, const bf16* W2T, const float* b2f, const float* s,
-        int64_t s_rs, int64_t s_cs, const float* act, const float* rew, float gamma, float high, const float* y, const float* dpi, float* out,
-        uint32_t* mask_out, bf16* DZ_out, float* U, float* sdq, float* loss, cudaStream_t st) {
+// One pass.  W2T: 16-bit [A][128][F] folded layer-2 kernel (K-major; bf16, or fp16 with f16 = true -- for MODE_CRITIC_ACTION
+// with f16 the T pack W2' diag(w3') s and wscale [A] = 1 / s), b2f: [A][128]  (pack_fold_kernel / pack_fold4_kernel).
+// Backward modes: mask_out [A*R][2*ceil(F/64)] sign masks of z1, DZ_out: 16-bit [A*R][128] = dm_scale * dq [z2 + b2' > 0], sdq [A] accumulated into.
+int run(int mode, bool f16, const avd_net_dims& d, int A, int64_t R, const float* params, int64_t pstride, const bf16* W2T, const float* b2f,
+        const float* wscale, const float* s, int64_t s_rs, int64_t s_cs, const float* act, const float* rew, float gamma, float high, const float* y,
+        const float* dpi, float* out, uint32_t* mask_out, bf16* DZ_out, float dm_scale, float* sdq, float* loss, cudaStream_t st) {
     if (!supported(d)) {
         set_error("fused pass kernel does not support these layer sizes");
         return AVD_ERR_UNSUPPORTED;
@@ -661,7 +703,8 @@ int run(int mode, const avd_net_dims& d, int A, int64_t R, const float* params, 
     AVD_REQUIRE(params && W2T && b2f && s, "null buffer");
     AVD_REQUIRE(A >= 1 && R >= 1 && R < (int64_t)1 << 31, "rows per agent must fit the 32-bit TMA coordinates");
     AVD_REQUIRE(!critic || act, "critic passes need actions");
-    AVD_REQUIRE(!bwd || (mask_out && DZ_out && U && sdq), "backward passes need mask / dz2 / U / sdq outputs");
+    AVD_REQUIRE(!bwd || (mask_out && DZ_out && sdq), "backward passes need mask / dz2 / sdq outputs");
+    AVD_REQUIRE(!(f16 && mode == MODE_CRITIC_ACTION) || wscale, "the fp16 critic-action pass needs the scale of its T pack");
     AVD_REQUIRE(bwd || out, "null output");
     CUtensorMap tmW, tmDZ;
     if (int rc = make_map(&tmW, W2T, (uint64_t)F, L2N, (uint64_t)A, (uint64_t)F, (uint64_t)F * L2N)) return rc;
@@ -671,17 +714,17 @@ int run(int mode, const avd_net_dims& d, int A, int64_t R, const float* params, 
     Args g;
     g.d = d; g.A = A; g.R = R; g.params = params; g.pstride = pstride; g.b2f = b2f; g.s = s; g.s_rs = s_rs; g.s_cs = s_cs; g.act = act;
     g.rew = rew; g.gamma = gamma; g.high = high; g.y = y; g.dpi = dpi; g.out = out; g.mask_out = mask_out; g.mask_words = 2 * ((F + KB - 1) / KB);
-    g.U = U; g.sdq = sdq; g.loss = loss;
+    g.wscale = wscale; g.dm_scale = dm_scale; g.sdq = sdq; g.loss = loss;
     g.tiles_per_agent = (int)((R + TILE_M - 1) / TILE_M);
     g.ctas_per_agent = std::max(1, std::min(g.tiles_per_agent, sm_count() / std::max(1, A)));
     const dim3 grid((unsigned)(g.ctas_per_agent * A));
     switch (mode) {
-        case MODE_ACTOR_OUT: return launch<MODE_ACTOR_OUT>(tmW, tmDZ, g, grid, st);
-        case MODE_TARGET: return launch<MODE_TARGET>(tmW, tmDZ, g, grid, st);
-        case MODE_Q: return launch<MODE_Q>(tmW, tmDZ, g, grid, st);
-        case MODE_CRITIC_BWD: return launch<MODE_CRITIC_BWD>(tmW, tmDZ, g, grid, st);
-        case MODE_ACTOR_BWD: return launch<MODE_ACTOR_BWD>(tmW, tmDZ, g, grid, st);
-        case MODE_CRITIC_ACTION: return launch<MODE_CRITIC_ACTION>(tmW, tmDZ, g, grid, st);
+        case MODE_ACTOR_OUT: return launch<MODE_ACTOR_OUT>(f16, tmW, tmDZ, g, grid, st);
+        case MODE_TARGET: return launch<MODE_TARGET>(f16, tmW, tmDZ, g, grid, st);
+        case MODE_Q: return launch<MODE_Q>(f16, tmW, tmDZ, g, grid, st);
+        case MODE_CRITIC_BWD: return launch<MODE_CRITIC_BWD>(f16, tmW, tmDZ, g, grid, st);
+        case MODE_ACTOR_BWD: return launch<MODE_ACTOR_BWD>(f16, tmW, tmDZ, g, grid, st);
+        case MODE_CRITIC_ACTION: return launch<MODE_CRITIC_ACTION>(f16, tmW, tmDZ, g, grid, st);
     }
     set_error("unknown fused pass mode %d", mode);
     return AVD_ERR_INVALID_ARG;

@@ -40,6 +40,7 @@ struct GemmParams {
     int64_t ldc, c_batch;
     int atomic;            // 1: atomicAdd into C (split-K)
     int n_fastest;         // 1: blockIdx.x walks the N tiles, so the CTAs that share an A tile run together and re-read it from L2
+    uint32_t a_fmt, b_fmt; // operand formats of the kind::f16 MMA: FMT_F16 / FMT_BF16, chosen independently
 };
 
 template <bool MN_MAJOR, int STAGES, int BN_>
@@ -101,7 +102,7 @@ __global__ void __launch_bounds__(NUM_THREADS, (STAGES <= 2) ? 3 : 1) gemm_bf16_
         }
     } else if (warp == 1) {
         if (lane == 0) {  // ===== MMA issuer =====
-            constexpr uint32_t idesc = make_idesc_bf16(BM, BN_, MN_MAJOR, MN_MAJOR);
+            const uint32_t idesc = make_idesc_f16kind(BM, BN_, MN_MAJOR, MN_MAJOR, g.a_fmt, g.b_fmt);
             for (int kb = 0; kb < g.k_blocks; ++kb) {
                 const int s = kb % STAGES;
                 const uint32_t ph = (kb / STAGES) & 1;
@@ -194,9 +195,14 @@ static int make_map(CUtensorMap* map, const void* base, uint64_t inner, uint64_t
     return AVD_OK;
 }
 
-int gemm_bf16(int layout, int batch, int M, int N, int K, const void* A, int64_t lda, int64_t a_batch, const void* B, int64_t ldb,
-              int64_t b_batch, float* C, int64_t ldc, int64_t c_batch, int splitk, cudaStream_t st) {
+int gemm_f16kind(int layout, int batch, int M, int N, int K, const void* A, int64_t lda, int64_t a_batch, const void* B, int64_t ldb,
+                 int64_t b_batch, float* C, int64_t ldc, int64_t c_batch, int splitk, int a_fmt, int b_fmt, cudaStream_t st) {
     AVD_REQUIRE(layout == 0 || layout == 1, "layout must be 0 (TN) or 1 (NT)");
+    AVD_REQUIRE((a_fmt == 0 || a_fmt == 1) && (b_fmt == 0 || b_fmt == 1), "operand formats: 0 = fp16, 1 = bf16");
+    if (a_fmt != b_fmt) {       // the instruction descriptor can express it, the B200 tensor pipe traps on it (illegal instruction)
+        set_error("kind::f16 MMAs need both operands in the same 16-bit format (got A %s, B %s)", a_fmt ? "bf16" : "fp16", b_fmt ? "bf16" : "fp16");
+        return AVD_ERR_UNSUPPORTED;
+    }
     AVD_REQUIRE(batch >= 1 && M >= 1 && N >= 1 && K >= 1 && splitk >= 1, "bad GEMM sizes");
     AVD_REQUIRE(A && B && C, "null operand");
     AVD_REQUIRE(lda % 8 == 0 && ldb % 8 == 0 && a_batch % 8 == 0 && b_batch % 8 == 0, "bf16 leading dimensions must be multiples of 8 elements (16 B)");
@@ -215,6 +221,7 @@ int gemm_bf16(int layout, int batch, int M, int N, int K, const void* A, int64_t
     g.M = M; g.N = N; g.splitk = splitk;
     g.k_blocks = (kblocks_total + splitk - 1) / splitk;
     g.C = C; g.ldc = ldc; g.c_batch = c_batch; g.atomic = (splitk > 1 || layout == 1) ? 1 : 0;
+    g.a_fmt = (uint32_t)a_fmt; g.b_fmt = (uint32_t)b_fmt;
     const bool narrow = layout == 1 && N <= 64;     // narrow outputs: one 64-column MN chunk of B per stage
     const int bn = narrow ? 64 : BN;
     dim3 grid((M + BM - 1) / BM, (N + bn - 1) / bn, batch * splitk);
@@ -234,8 +241,20 @@ int gemm_bf16(int layout, int batch, int M, int N, int K, const void* A, int64_t
     return AVD_OK;
 }
 
+int gemm_bf16(int layout, int batch, int M, int N, int K, const void* A, int64_t lda, int64_t a_batch, const void* B, int64_t ldb,
+              int64_t b_batch, float* C, int64_t ldc, int64_t c_batch, int splitk, cudaStream_t st) {
+    return gemm_f16kind(layout, batch, M, N, K, A, lda, a_batch, B, ldb, b_batch, C, ldc, c_batch, splitk, (int)FMT_BF16, (int)FMT_BF16, st);
+}
+
 }  // namespace umma
 }  // namespace avd
+
+extern "C" int avd_gemm_f16kind(int layout, int batch, int M, int N, int K, const void* A, int64_t lda, int64_t a_batch, const void* B,
+                                int64_t ldb, int64_t b_batch, float* C, int64_t ldc, int64_t c_batch, int splitk, int a_fmt, int b_fmt,
+                                void* stream) {
+    return avd::umma::gemm_f16kind(layout, batch, M, N, K, A, lda, a_batch, B, ldb, b_batch, C, ldc, c_batch, splitk, a_fmt, b_fmt,
+                                   (cudaStream_t)stream);
+}
 
 extern "C" int avd_gemm_bf16(int layout, int batch, int M, int N, int K, const void* A, int64_t lda, int64_t a_batch, const void* B,
                              int64_t ldb, int64_t b_batch, float* C, int64_t ldc, int64_t c_batch, int splitk, void* stream) {

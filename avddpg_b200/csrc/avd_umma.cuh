@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 namespace avd {
@@ -157,6 +158,26 @@ __device__ __forceinline__ uint32_t pack_relu_bf16x2(float lo, float hi) {
     return d;
 }
 
+// fp16 variant for precision = 2 (11-bit significand instead of 8): relu + round + SATURATE to the largest finite half
+// (F2FP.SATFINITE.RELU.F16), so an activation beyond 65504 clamps instead of turning the whole row into inf / NaN
+__device__ __forceinline__ uint32_t pack_relu_f16x2(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.satfinite.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+template <bool F16>
+__device__ __forceinline__ uint32_t pack_relu_x2(float lo, float hi) {
+    return F16 ? pack_relu_f16x2(lo, hi) : pack_relu_bf16x2(lo, hi);
+}
+// round + pack without the relu: bf16, or fp16 saturating to the largest finite half
+template <bool F16>
+__device__ __forceinline__ uint32_t pack_x2(float lo, float hi) {
+    uint32_t d;
+    if (F16) asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+
 // ---- coalesced store of a 32 x 32 fp32 block held one-row-per-lane -----------------------------------
 // After tcgen05.ld.32x32b every lane owns 32 consecutive columns of ITS row, so a direct store makes each
 // instruction touch 32 different 128-byte lines (32 L1 wavefronts).  Staging the block through a padded
@@ -204,6 +225,15 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
 //   [4,6) D fmt = 1 (f32) | [7,10) A fmt = 1 (bf16) | [10,13) B fmt = 1 | [15] A MN-major | [16] B MN-major | [17,23) N>>3 | [24,29) M>>4
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, bool a_mn, bool b_mn) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) |
+           ((uint32_t)(M >> 4) << 24);
+}
+
+// kind::f16 operand formats (0 = fp16, 1 = bf16).  The descriptor has one field per operand, but B200 executes only EQUAL
+// formats: fp16 x bf16 traps with "illegal instruction" (tests/test_gpu_umma.py::test_mixed_operand_formats pins this), so
+// precision = 2 switches whole products to fp16 (11-bit significand) and scales the operands whose range needs it.
+constexpr uint32_t FMT_F16 = 0u, FMT_BF16 = 1u;
+__host__ __device__ constexpr uint32_t make_idesc_f16kind(int M, int N, bool a_mn, bool b_mn, uint32_t a_fmt, uint32_t b_fmt) {
+    return (1u << 4) | (a_fmt << 7) | (b_fmt << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) |
            ((uint32_t)(M >> 4) << 24);
 }
 

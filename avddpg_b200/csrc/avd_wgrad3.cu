@@ -78,6 +78,9 @@ __device__ __forceinline__ uint32_t pack2(bf16 a, bf16 b) {
     return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
 }
 
+// F16 (precision = 2): the recomputed r1 slab is fp16, exactly the values the forward pass multiplied (the unfold kernel derives
+// the head-weight sum U from G2, which only holds if both see the same r1), and so is the dz2 tile the backward pass wrote.
+template <bool F16>
 __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad3_kernel(const __grid_constant__ CUtensorMap tmDZ, Args g) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -153,7 +156,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad3_kernel(const __grid_con
         // warp-uniform control flow; the tcgen05 instructions are predicated on one elected lane (see avd_umma.cuh)
         if (T > 0) {
             const uint32_t leader = elect_one();
-            constexpr uint32_t idesc2 = make_idesc_bf16(SLAB, L2N, true, true);        // r1 slab (MN-major) x dz2 tile (MN-major)
+            constexpr uint32_t idesc2 = make_idesc_f16kind(SLAB, L2N, true, true, F16 ? FMT_F16 : FMT_BF16, F16 ? FMT_F16 : FMT_BF16);   // r1 slab (MN-major) x dz2 tile (MN-major)
             const uint64_t dR = make_smem_desc(smem_u32(smem + OFF_R1), HALF_BYTES, 1024);
             const uint64_t dDZ = make_smem_desc(smem_u32(smem + OFF_DZ), HALF_BYTES, 1024);
             for (int t = 0; t < T; ++t) {
@@ -272,8 +275,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad3_kernel(const __grid_con
                         mbar_wait(&r_empty[rb], ((q / NRB) & 1) ^ 1);
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
-                            const uint4 pk = make_uint4(pack_relu_bf16x2(z[8 * k], z[8 * k + 1]), pack_relu_bf16x2(z[8 * k + 2], z[8 * k + 3]),
-                                                        pack_relu_bf16x2(z[8 * k + 4], z[8 * k + 5]), pack_relu_bf16x2(z[8 * k + 6], z[8 * k + 7]));
+                            const uint4 pk = make_uint4(pack_relu_x2<F16>(z[8 * k], z[8 * k + 1]), pack_relu_x2<F16>(z[8 * k + 2], z[8 * k + 3]),
+                                                        pack_relu_x2<F16>(z[8 * k + 4], z[8 * k + 5]), pack_relu_x2<F16>(z[8 * k + 6], z[8 * k + 7]));
                             *reinterpret_cast<uint4*>(rrow + ((((qtr & 1) * 4 + k) ^ (row & 7)) << 4)) = pk;
                         }
                     }
@@ -296,7 +299,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad3_kernel(const __grid_con
 #pragma unroll
                             for (int j = 0; j < 8; ++j) r[j] = fmaf(a_val, wa_tab[qtr * 32 + 8 * k + j], ba_tab[qtr * 32 + 8 * k + j]);
                             *reinterpret_cast<uint4*>(rrow + (((qtr * 4 + k) ^ (row & 7)) << 4)) =
-                                make_uint4(pack_relu_bf16x2(r[0], r[1]), pack_relu_bf16x2(r[2], r[3]), pack_relu_bf16x2(r[4], r[5]), pack_relu_bf16x2(r[6], r[7]));
+                                make_uint4(pack_relu_x2<F16>(r[0], r[1]), pack_relu_x2<F16>(r[2], r[3]), pack_relu_x2<F16>(r[4], r[5]), pack_relu_x2<F16>(r[6], r[7]));
                         }
                         fence_proxy_async();
                     }
@@ -350,7 +353,7 @@ int ctas_per_agent(int A, int64_t R) {
 // out: every CTA (agent, cta) stores its partial G2 (row-major [F][128] fp32, rows < F) at out + agent*out_agent_stride +
 // cta*out_cta_stride -- no atomics: the 37 x 4 CTAs of the C2 case would otherwise serialise 7 M atomic adds on 160 k
 // addresses (a quarter of the kernel time).  The caller sums the ctas_per_agent(A, R) slices.  DZ: bf16 [A*R][128].
-int run(const avd_net_dims& d, bool critic, int A, int64_t R, const float* params, int64_t pstride, const float* s, const float* act, const bf16* DZ,
+int run(bool f16, const avd_net_dims& d, bool critic, int A, int64_t R, const float* params, int64_t pstride, const float* s, const float* act, const bf16* DZ,
         float* out, int64_t out_agent_stride, int64_t out_cta_stride, cudaStream_t st) {
     AVD_REQUIRE(d.l1 == 256 && d.l2 == L2N && d.ns >= 1 && d.ns <= 4 && (!critic || (d.la >= 8 && d.la <= 64)), "unsupported layer sizes for the fused wgrad kernel");
     AVD_REQUIRE(params && s && DZ && out && (!critic || act), "null buffer");
@@ -362,7 +365,8 @@ int run(const avd_net_dims& d, bool critic, int A, int64_t R, const float* param
     }
     static bool attr_set = false;
     if (!attr_set) {
-        AVD_CUDA_OK(cudaFuncSetAttribute(wgrad3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        AVD_CUDA_OK(cudaFuncSetAttribute(wgrad3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        AVD_CUDA_OK(cudaFuncSetAttribute(wgrad3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         attr_set = true;
     }
     CUtensorMap tm;
@@ -381,7 +385,8 @@ int run(const avd_net_dims& d, bool critic, int A, int64_t R, const float* param
     g.out = out; g.out_agent_stride = out_agent_stride; g.out_cta_stride = out_cta_stride;
     g.tiles_per_agent = (int)((R + TILE_M - 1) / TILE_M);
     g.ctas_per_agent = ctas_per_agent(A, R);
-    AVD_CUDA_OK(launch_pdl(wgrad3_kernel, dim3((unsigned)(A * g.ctas_per_agent)), dim3(NUM_THREADS), SMEM_BYTES, st, tm, g));
+    if (f16) AVD_CUDA_OK(launch_pdl(wgrad3_kernel<true>, dim3((unsigned)(A * g.ctas_per_agent)), dim3(NUM_THREADS), SMEM_BYTES, st, tm, g));
+    else AVD_CUDA_OK(launch_pdl(wgrad3_kernel<false>, dim3((unsigned)(A * g.ctas_per_agent)), dim3(NUM_THREADS), SMEM_BYTES, st, tm, g));
     AVD_LAUNCH_OK();
     return AVD_OK;
 }

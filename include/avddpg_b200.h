@@ -332,6 +332,11 @@ int avd_fed_broadcast(float* out, int64_t out_pitch, const float* in, int64_t in
 int avd_gemm_bf16(int layout, int batch, int M, int N, int K, const void* A, int64_t lda, int64_t a_batch, const void* B,
                   int64_t ldb, int64_t b_batch, float* C, int64_t ldc, int64_t c_batch, int splitk, void* stream);
 
+/* Same GEMM with fp16 (a_fmt = b_fmt = 0) or bf16 (1) operands.  Mixed formats return AVD_ERR_UNSUPPORTED: the tcgen05 instruction
+ * descriptor has a format field per operand, but B200 traps on fp16 x bf16.                                                         */
+int avd_gemm_f16kind(int layout, int batch, int M, int N, int K, const void* A, int64_t lda, int64_t a_batch, const void* B,
+                     int64_t ldb, int64_t b_batch, float* C, int64_t ldc, int64_t c_batch, int splitk, int a_fmt, int b_fmt, void* stream);
+
 /* ---- raw RNG access (parity tests: bit-exact against oracle/philox_np.py) ------------------- */
 int avd_rng_words(uint32_t* out4 /*[n][4]*/, int64_t n, uint64_t id_base, uint32_t tick, uint32_t purpose,
                   uint64_t seed, void* stream);

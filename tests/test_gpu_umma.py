@@ -52,3 +52,38 @@ def test_nt_wgrad_shapes(lib, batch, M, N, K, splitk):
 
 def test_tn_splitk_accumulates(lib):
     assert _run(lib, 0, 1, 128, 128, 1024, splitk=4) < 1e-3
+
+
+@pytest.mark.parametrize("layout", [0, 1])
+@pytest.mark.parametrize("fmt", [0, 1])
+def test_fp16_and_bf16_operands(lib, layout, fmt):
+    """kind::f16 with fp16 (0) or bf16 (1) operands: the product of the rounded operands.  precision = 2 of the learn step uses fp16."""
+    batch, M, N, K = 2, 256, 128, 320
+    g = torch.Generator(device="cuda").manual_seed(17 + fmt + 4 * layout)
+    dt = {0: torch.float16, 1: torch.bfloat16}[fmt]
+    if layout == 0:
+        A = torch.randn(batch, M, K, device="cuda", generator=g).to(dt)
+        B = torch.randn(batch, N, K, device="cuda", generator=g).to(dt)
+        ref = torch.einsum("bmk,bnk->bmn", A.float(), B.float())
+        lda, ldb, a_batch, b_batch = K, K, M * K, N * K
+    else:
+        A = torch.randn(batch, K, M, device="cuda", generator=g).to(dt)
+        B = torch.randn(batch, K, N, device="cuda", generator=g).to(dt)
+        ref = torch.einsum("bkm,bkn->bmn", A.float(), B.float())
+        lda, ldb, a_batch, b_batch = M, N, K * M, K * N
+    C = torch.zeros(batch, M, N, device="cuda")
+    lib.check(lib.load().avd_gemm_f16kind(layout, batch, M, N, K, lib.ptr(A), lda, a_batch, lib.ptr(B), ldb, b_batch, lib.ptr(C), N, M * N, 1,
+                                          fmt, fmt, lib.current_stream()))
+    torch.cuda.synchronize()
+    assert (C - ref).abs().max().item() / ref.abs().max().item() < 1e-3
+
+
+def test_mixed_operand_formats_are_refused(lib):
+    """fp16 x bf16 is expressible in the instruction descriptor but traps on B200 (measured: cudaErrorIllegalInstruction), so the
+    entry point refuses it instead of poisoning the context."""
+    A = torch.zeros(128, 64, device="cuda", dtype=torch.float16)
+    B = torch.zeros(128, 64, device="cuda", dtype=torch.bfloat16)
+    C = torch.zeros(128, 128, device="cuda")
+    with pytest.raises(NotImplementedError):
+        lib.check(lib.load().avd_gemm_f16kind(0, 1, 128, 128, 64, lib.ptr(A), 64, 128 * 64, lib.ptr(B), 64, 128 * 64, lib.ptr(C), 128, 128 * 128, 1,
+                                              0, 1, lib.current_stream()))
