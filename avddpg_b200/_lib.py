@@ -11,7 +11,7 @@ import os
 
 AVD_MAX_FOLLOWERS = 16
 RING_RECORD_FLOATS = 10
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 RNG_RESET_VEHICLE, RNG_RESET_PLATOON, RNG_OU, RNG_LEADER_EXOG, RNG_REPLAY, RNG_INIT = range(6)
 
@@ -54,7 +54,8 @@ class EnvIO(C.Structure):
         ("ring", C.c_void_p), ("ring_capacity", C.c_int64),
         ("episode", C.c_void_p), ("step_in_episode", C.c_void_p), ("ep_reward", C.c_void_p),
         ("stats", C.c_void_p), ("clock", C.c_void_p),
-        ("gen_exog", C.c_int32), ("auto_reset", C.c_int32), ("clip_actions", C.c_int32), ("reserved0", C.c_int32),
+        ("gen_exog", C.c_int32), ("auto_reset", C.c_int32), ("clip_actions", C.c_int32), ("ep_hist_window", C.c_int32),
+        ("last_ep_reward", C.c_void_p), ("ep_hist", C.c_void_p),
     ]
 
 
@@ -82,8 +83,22 @@ AVD_MAX_PEERS = 16
 
 
 class PeerComm(C.Structure):
-    _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("epoch", C.c_uint32), ("reserved0", C.c_uint32),
+    _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("reserved0", C.c_uint32), ("reserved1", C.c_uint32),
                 ("peer_base", C.c_uint64 * AVD_MAX_PEERS), ("multicast_base", C.c_uint64)]
+
+
+class FedApplyIO(C.Structure):
+    _fields_ = [
+        ("comm", PeerComm), ("flag_offset", C.c_int64), ("data_offset", C.c_int64), ("local_sums", C.c_void_p), ("ctrl", C.c_void_p),
+        ("pitch", C.c_int64), ("n_systems", C.c_int32), ("n_members", C.c_int32), ("member_stride_s", C.c_int64), ("member_stride_x", C.c_int64),
+        ("A", C.c_int32), ("reserved0", C.c_int32),
+        ("actor", C.c_void_p), ("t_actor", C.c_void_p), ("actor_m", C.c_void_p), ("actor_v", C.c_void_p), ("actor_step", C.c_void_p),
+        ("actor_grad_out", C.c_void_p), ("actor_total", C.c_int64), ("actor_train", C.c_int64),
+        ("critic", C.c_void_p), ("t_critic", C.c_void_p), ("critic_m", C.c_void_p), ("critic_v", C.c_void_p), ("critic_step", C.c_void_p),
+        ("critic_grad_out", C.c_void_p), ("critic_total", C.c_int64), ("critic_train", C.c_int64),
+        ("apply_mask", C.c_void_p), ("wsum_out", C.c_void_p),
+        ("actor_lr", C.c_float), ("critic_lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("tau", C.c_float),
+    ]
 
 
 class AvdError(RuntimeError):
@@ -135,8 +150,11 @@ SIGNATURES = {
                                   C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "avd_fed_broadcast2": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int32,
                                      C.c_int32, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
+    "avd_fed_weights_from_history": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p]),
     "avd_fed_finalize": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_void_p]),
-    "avd_fed_exchange_peer": (C.c_int, [C.POINTER(PeerComm), C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_void_p]),
+    "avd_fed_exchange_peer": (C.c_int, [C.POINTER(PeerComm), C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int64,
+                                        C.c_void_p]),
+    "avd_fed_apply_gradients": (C.c_int, [C.POINTER(FedApplyIO), C.c_void_p]),
     "avd_fed_broadcast": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int64, C.c_int64,
                                     C.c_void_p, C.c_int64, C.c_void_p]),
     "avd_gemm_bf16": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64,
@@ -166,7 +184,7 @@ def load():
         fn.restype, fn.argtypes = res, args
     if lib.avd_abi_version() != ABI_VERSION:
         raise AvdError(f"ABI mismatch: library {lib.avd_abi_version()} vs binding {ABI_VERSION}")
-    for which, st in enumerate((EnvParams, EnvIO, Clock, NetDims, LearnIO)):
+    for which, st in enumerate((EnvParams, EnvIO, Clock, NetDims, LearnIO, PeerComm, FedApplyIO)):
         if lib.avd_sizeof(which) != C.sizeof(st):
             raise AvdError(f"struct layout mismatch for {st.__name__}: C {lib.avd_sizeof(which)} vs ctypes {C.sizeof(st)}")
     _lib = lib

@@ -649,6 +649,30 @@ __global__ void __launch_bounds__(256) fed_broadcast2_kernel(float* __restrict__
     }
 }
 
+// Trainer.get_weight (workers/trainer.py:385-398) for every agent at once: |1 / mean(last `window` episodic rewards)|, the episodic
+// reward of agent (g, m) being the mean over its group's E platoons.  One CTA per agent; ep_hist is the ring the env kernel keeps.
+__global__ void __launch_bounds__(256) fed_weights_kernel(const float* __restrict__ ep_hist, int window, int M, int64_t G, int64_t E,
+                                                          float* __restrict__ out, int transpose) {
+    const int m = blockIdx.x / (int)G;
+    const int64_t g = blockIdx.x - (int64_t)m * G;
+    const int64_t P = G * E;
+    float acc = 0.0f;
+    for (int64_t i = threadIdx.x; i < (int64_t)window * E; i += blockDim.x) {
+        const int64_t k = i / E, e = i - k * E;
+        acc += ep_hist[(k * M + m) * P + g * E + e];
+    }
+    __shared__ float red[8];
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.0f;
+        for (int k = 0; k < (int)(blockDim.x >> 5); ++k) t += red[k];
+        const float mean = t / (float)((int64_t)window * E);
+        out[transpose ? g * M + m : (int64_t)m * G + g] = fabsf(1.0f / mean);
+    }
+}
+
 __global__ void __launch_bounds__(256) fed_finalize_kernel(float* __restrict__ buf, int64_t pitch, int64_t n) {
     float* row = buf + (int64_t)blockIdx.y * pitch;
     const float inv = 1.0f / row[n];
@@ -684,13 +708,15 @@ __global__ void __launch_bounds__(256) pack_w2_kernel(const float* __restrict__ 
 
 // 16-bit operand element: bf16 (precision 1) or fp16 (precision 2); both travel as bf16-typed pointers (TMA moves raw 16-bit words)
 __device__ __forceinline__ bf16 to_op16(float v, int f16) {
-    if (f16) {
-        const __half h = __float2half_rn(v);
+    if (f16) {       // saturating, like the F2FP.SATFINITE conversions of the kernels: never inf from a finite value
+        const __half h = __float2half_rn(fminf(fmaxf(v, -65504.0f), 65504.0f));
         return *reinterpret_cast<const bf16*>(&h);
     }
     return __float2bfloat16_rn(v);
 }
-__device__ __forceinline__ float round_op16(float v, int f16) { return f16 ? __half2float(__float2half_rn(v)) : __bfloat162float(__float2bfloat16_rn(v)); }
+__device__ __forceinline__ float round_op16(float v, int f16) {
+    return f16 ? __half2float(__float2half_rn(fminf(fmaxf(v, -65504.0f), 65504.0f))) : __bfloat162float(__float2bfloat16_rn(v));
+}
 
 // BN-folded packing for the fused tensor-core path.  With h1 = r1*sc1 + sh1 (r1 = relu(z1), inference BatchNorm):
 //   z2 = h1 W2 + b2 = r1 W2' + b2',   W2'[f][j] = sc1[f] W2[f][j],   b2'[j] = b2[j] + sum_f sh1[f] W2[f][j]
@@ -1402,6 +1428,15 @@ extern "C" int avd_fed_broadcast2(float* out_a, int64_t pitch_a, int64_t na, flo
     const int gx = (int)std::min<int64_t>((na + nc + 255) / 256, 64);
     fed_broadcast2_kernel<<<dim3(gx, n_systems, n_members), 256, 0, (cudaStream_t)stream>>>(out_a, pitch_a, na, out_c, pitch_c, nc, in, in_pitch,
                                                                                              n_members, member_stride_s, member_stride_x, apply_mask);
+    AVD_LAUNCH_OK();
+    return AVD_OK;
+}
+
+extern "C" int avd_fed_weights_from_history(const float* ep_hist, int32_t window, int32_t M, int64_t G, int64_t E, float* out_w,
+                                            int32_t transpose, void* stream) {
+    AVD_REQUIRE(ep_hist && out_w, "null buffer");
+    AVD_REQUIRE(window >= 1 && M >= 1 && G >= 1 && E >= 1 && (int64_t)M * G < (1 << 30), "bad sizes");
+    fed_weights_kernel<<<(unsigned)(M * G), 256, 0, (cudaStream_t)stream>>>(ep_hist, window, M, G, E, out_w, transpose);
     AVD_LAUNCH_OK();
     return AVD_OK;
 }

@@ -13,10 +13,31 @@
 // 292-295), ReplayBuffer.add for every agent (src/replaybuffer.py:37-47), episodic reward accumulation
 // (workers/trainer.py:321), per-step reward/done statistics (block reduction + one atomic per CTA) and
 // per-platoon auto-reset (src/environment.py:284-301, 520-559).
+#include <cstdlib>
+
 #include "avd_common.cuh"
 #include "avd_rng.cuh"
 
 namespace avd {
+
+// ------------------------------------------------------------------------------------------------
+// end of an episode for one platoon: publish the episodic reward counters (trainer.py:510-517: all_ep_reward_lists.append) and
+// zero them (trainer.py:249).  `ep` = value of episode[p] before this reset = resets so far, so the finished episode is ep - 1.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void finish_episode(const avd_env_io& io, float* ep_reward, int M, int64_t p, uint32_t ep, bool stepped) {
+    if (!ep_reward) return;
+    const int64_t P = io.P;
+    const int64_t hslot = (io.ep_hist && io.ep_hist_window > 0) ? (int64_t)((ep ? ep - 1u : 0u) % (uint32_t)io.ep_hist_window) : 0;
+    for (int m = 0; m < M; ++m) {
+        const int64_t v = (int64_t)m * P + p;
+        if (stepped) {
+            const float r = ep_reward[v];
+            if (io.last_ep_reward) io.last_ep_reward[v] = r;
+            if (io.ep_hist && io.ep_hist_window > 0) io.ep_hist[(hslot * M + m) * P + p] = r;
+        }
+        ep_reward[v] = 0.0f;
+    }
+}
 
 // ------------------------------------------------------------------------------------------------
 // reset of one platoon (thread-local): Platoon.reset + Vehicle.reset
@@ -80,10 +101,9 @@ __global__ void __launch_bounds__(256) env_reset_kernel(const __grid_constant__ 
     for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < io.P; p += (int64_t)gridDim.x * blockDim.x) {
         if (mask && !mask[p]) continue;
         const uint32_t ep = io.episode ? (uint32_t)io.episode[p] : 0u;
+        finish_episode(io, io.ep_reward, prm.M, p, ep, io.step_in_episode ? io.step_in_episode[p] > 0 : false);
         reset_one_platoon(prm, io, p, ep, io.x_out);
         if (io.episode) io.episode[p] = (int32_t)(ep + 1u);
-        if (io.ep_reward)
-            for (int m = 0; m < prm.M; ++m) io.ep_reward[(int64_t)m * io.P + p] = 0.0f;
     }
 }
 
@@ -175,7 +195,9 @@ __device__ __forceinline__ float step_follower(const avd_env_params& prm, const 
     c.prev_a[v] = f.x2;
     if (!prm.centralized) c.reward[v] = r;
     if (c.ep_reward) c.ep_reward[v] += r;
-    if (c.ring) {  // ReplayBuffer.add: (s, a, r, s') -- one 40 B record, five 8-byte stores
+    if (c.ring) {  // ReplayBuffer.add: (s, a, r, s') -- one 40 B record, five 8-byte stores.  (A warp's 32 records are contiguous, 1280 B;
+                   // staging them through shared memory and writing 16-byte lines was measured in round 2 and dropped: +3..6 % launch
+                   // time -- the launch is bound by the 30 / 70 read / write mix at the DRAM, not by the store instructions.)
         float2* rec = reinterpret_cast<float2*>(c.ring + ((c.slot * M + m) * c.P + p) * AVD_RING_RECORD_FLOATS);
         rec[0] = make_float2(f.x0, f.x1);
         rec[1] = make_float2(f.x2, f.x3);
@@ -187,9 +209,11 @@ __device__ __forceinline__ float step_follower(const avd_env_params& prm, const 
     return r;
 }
 
-// Registers: the preloaded inputs cost 8 x M; 1..4 followers fit 80 registers (3 CTAs/SM), 5..8 need 128 (2 CTAs/SM).
+// Registers: the preloaded inputs cost 8 per follower.  Platoons of up to 4 followers are preloaded whole; longer ones in chunks of 4
+// (the exogenous input `w` carries the chain from chunk to chunk), so every instantiation fits 80 registers = 3 CTAs per SM --
+// preloading all 8 followers needed 128 registers (2 CTAs per SM) and left the M = 8 launches 15 % behind the M = 4 ones.
 template <int MT>
-__global__ void __launch_bounds__(256, (MT >= 1 && MT <= 4) ? 3 : 2) env_step_kernel(const __grid_constant__ avd_env_params prm,
+__global__ void __launch_bounds__(256, MT >= 1 ? 3 : 2) env_step_kernel(const __grid_constant__ avd_env_params prm,
                                                                                       const __grid_constant__ avd_env_io io) {
     const int M = MT ? MT : prm.M;
     StepCtx c;
@@ -216,10 +240,11 @@ __global__ void __launch_bounds__(256, (MT >= 1 && MT <= 4) ? 3 : 2) env_step_ke
 
     for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (int64_t)gridDim.x * blockDim.x) {
         const uint64_t gp = (uint64_t)(io.platoon_id_base + p);
-        FollowerIn fin[MT ? MT : 1];
+        constexpr int CH = MT > 4 ? 4 : (MT ? MT : 1);       // followers preloaded at a time
+        FollowerIn fin[CH];
         if (MT) {
 #pragma unroll
-            for (int m = 0; m < MT; ++m) fin[m] = load_follower(c, (int64_t)m * P + p);
+            for (int m = 0; m < CH; ++m) fin[m] = load_follower(c, (int64_t)m * P + p);
         }
         // exogenous input of follower 0 (environment.py:258-259 / 264-265, trainer.py:292-295)
         float w;
@@ -235,12 +260,22 @@ __global__ void __launch_bounds__(256, (MT >= 1 && MT <= 4) ? 3 : 2) env_step_ke
         float rew_sum = 0.0f;
         if (MT) {
 #pragma unroll
-            for (int m = 0; m < MT; ++m) {
-                bool term;
-                const float r = step_follower(prm, io, c, fin[m], m, MT, p, gp, w, term);
-                any_term |= term;
-                rew_sum += r;
-                stat_r[m] += r;
+            for (int m0 = 0; m0 < MT; m0 += CH) {
+                if (m0 > 0) {
+#pragma unroll
+                    for (int j = 0; j < CH; ++j)
+                        if (m0 + j < MT) fin[j] = load_follower(c, (int64_t)(m0 + j) * P + p);
+                }
+#pragma unroll
+                for (int j = 0; j < CH; ++j) {
+                    if (m0 + j < MT) {
+                        bool term;
+                        const float r = step_follower(prm, io, c, fin[j], m0 + j, MT, p, gp, w, term);
+                        any_term |= term;
+                        rew_sum += r;
+                        stat_r[m0 + j] += r;
+                    }
+                }
             }
         } else {
             for (int m = 0; m < M; ++m) {
@@ -263,6 +298,7 @@ __global__ void __launch_bounds__(256, (MT >= 1 && MT <= 4) ? 3 : 2) env_step_ke
         stat_done += any_term ? 1.0f : 0.0f;
         if (io.auto_reset && (any_term || timeout)) {
             const uint32_t ep = io.episode ? (uint32_t)io.episode[p] : 0u;
+            finish_episode(io, c.ep_reward, M, p, ep, true);
             reset_one_platoon(prm, io, p, ep, io.x_out);
             if (io.episode) io.episode[p] = (int32_t)(ep + 1u);
         }
@@ -355,6 +391,7 @@ extern "C" int avd_env_step(const avd_env_params* prm, const avd_env_io* io, voi
     AVD_REQUIRE(io->x_in != io->x_out, "x_in and x_out must not alias (ping-pong state buffers)");
     AVD_REQUIRE(!io->ring || io->ring_capacity > 0, "ring given with capacity %lld", (long long)io->ring_capacity);
     AVD_REQUIRE(!io->auto_reset || (io->episode && io->step_in_episode), "auto_reset needs episode and step_in_episode");
+    AVD_REQUIRE(!io->ep_hist || (io->ep_hist_window > 0 && io->ep_reward && io->episode), "ep_hist needs a window, ep_reward and episode counters");
     AVD_REQUIRE(io->leader_exog || io->gen_exog || (prm->model_a ? io->front_accel != nullptr : io->front_u != nullptr),
                 "no source for the leader's exogenous input");
     if (io->P == 0) return AVD_OK;

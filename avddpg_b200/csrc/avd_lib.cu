@@ -58,6 +58,8 @@ extern "C" int64_t avd_sizeof(int which) {
         case 2: return (int64_t)sizeof(avd_clock);
         case 3: return (int64_t)sizeof(avd_net_dims);
         case 4: return (int64_t)sizeof(avd_learn_io);
+        case 5: return (int64_t)sizeof(avd_peer_comm);
+        case 6: return (int64_t)sizeof(avd_fed_apply_io);
         default: return -1;
     }
 }

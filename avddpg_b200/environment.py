@@ -60,7 +60,7 @@ class BatchedPlatoons:
                  seed: Optional[int] = None, rand_states: bool = True, evaluator_states_enabled: bool = False,
                  track_kinematics: bool = True, ring=None, clock: Optional[DeviceClock] = None,
                  steps_per_episode: Optional[int] = None, auto_reset: bool = False, collect_stats: bool = False,
-                 track_episodes: bool = True, store_actions: bool = True):
+                 track_episodes: bool = True, store_actions: bool = True, reward_history: int = 0):
         self.lib = _lib.load()
         _lib.require_device()
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
@@ -93,6 +93,10 @@ class BatchedPlatoons:
         self.episode = torch.zeros(P, dtype=torch.int32, device=dev) if track_episodes else None
         self.step_in_episode = torch.zeros(P, dtype=torch.int32, device=dev) if track_episodes else None
         self.ep_reward = torch.zeros(M, P, **f32) if track_episodes else None
+        # finished-episode rewards: the last one, and a ring of the last `reward_history` (config.weighted_window) per agent --
+        # the device-resident all_ep_reward_lists[p][m][-weighted_window:] of workers/trainer.py:385-398
+        self.last_ep_reward = torch.zeros(M, P, **f32) if track_episodes else None
+        self.ep_hist = torch.zeros(int(reward_history), M, P, **f32) if (track_episodes and reward_history > 0) else None
         self.stats = torch.zeros(M + 1, **f32) if collect_stats else None
         self.clock = clock if clock is not None else DeviceClock(dev)
         self.ring = ring
@@ -100,8 +104,9 @@ class BatchedPlatoons:
         self.io = _lib.EnvIO()
         io = self.io
         io.P, io.platoon_id_base, io.seed = P, int(platoon_id_base), self.seed
+        io.ep_hist_window = 0 if self.ep_hist is None else int(reward_history)
         for name in ("prev_a", "cum_accel", "front_u", "front_accel", "jerk", "velocity", "headway", "episode",
-                     "step_in_episode", "ep_reward", "stats"):
+                     "step_in_episode", "ep_reward", "stats", "last_ep_reward", "ep_hist"):
             t = getattr(self, name)
             setattr(io, name, None if t is None else t.data_ptr())
         io.reward, io.done = self._reward.data_ptr(), self._done.data_ptr()

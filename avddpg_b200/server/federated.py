@@ -86,8 +86,10 @@ class PeerExchange:
     """NVLink-native transport of the interfrl exchange (csrc/avd_peer.cu): a symmetric, peer-mapped buffer per rank
     (torch.distributed._symmetric_memory) holding two alternating halves of partial sums plus the epoch flags; ONE kernel per
     round signals the peers, waits for them, reads the sum over ranks -- reduced inside the NVSwitch through the NVLS multicast
-    mapping when the fabric provides one, otherwise with peer loads -- and writes the means locally.  Collective: every rank of
-    the group must construct it (rendezvous) and call `exchange` the same number of times."""
+    mapping when the fabric provides one, otherwise with peer loads -- and either writes the means locally (`exchange`) or
+    consumes them on the spot (Adam + Polyak of every local member, `FederatedAggregator.aggregate_gradients`).  The epoch of the
+    barrier is a counter in device memory (`ctrl`), so rounds captured into a CUDA graph replay correctly.  Collective: every rank
+    of the group must construct it (rendezvous) and issue the same sequence of rounds."""
     FLAG_BYTES = 256
 
     def __init__(self, process_group, n_systems: int, max_pitch: int, device, allow_multicast: bool = True):
@@ -101,27 +103,30 @@ class PeerExchange:
         torch.cuda.synchronize(device)
         self.hdl = symm.rendezvous(self.raw, process_group.group_name)
         self.comm = _lib.PeerComm()
-        self.comm.rank, self.comm.world, self.comm.epoch = self.hdl.rank, self.hdl.world_size, 0
+        self.comm.rank, self.comm.world = self.hdl.rank, self.hdl.world_size
         if self.hdl.world_size > _lib.AVD_MAX_PEERS:
             raise ValueError(f"at most {_lib.AVD_MAX_PEERS} ranks")
         for r, ptr in enumerate(self.hdl.buffer_ptrs):
             self.comm.peer_base[r] = int(ptr)
         self.comm.multicast_base = int(getattr(self.hdl, "multicast_ptr", 0) or 0) if allow_multicast else 0
         self.nvls = self.comm.multicast_base != 0
+        self.ctrl = torch.zeros(2, dtype=torch.int32, device=device)      # [0] completed rounds (device-resident epoch), [1] CTA ticket
         dist.barrier(group=process_group)        # every rank has zeroed its flags before the first signal can arrive
-        self.round = 0
+        self.round = 0                           # host count: only its PARITY (which half) goes into launch arguments
+
+    def data_offset(self) -> int:
+        return self.FLAG_BYTES + (self.round & 1) * self.half_bytes
 
     def half(self, n_systems: int, pitch: int) -> torch.Tensor:
-        """This round's [n_systems, pitch] float32 view of the local symmetric buffer (fill it, then call exchange)."""
-        off = self.FLAG_BYTES + (self.round & 1) * self.half_bytes
+        """This round's [n_systems, pitch] float32 view of the local symmetric buffer (fill it, then exchange)."""
+        off = self.data_offset()
         return self.raw[off:off + n_systems * pitch * 4].view(torch.float32).view(n_systems, pitch)
 
     def exchange(self, out: torch.Tensor, n: int):
-        """out[s, :n] = sum over ranks of half[s, :n] / sum over ranks of half[s, n]."""
+        """out[s, :n] = sum over ranks of half[s, :n] / sum over ranks of half[s, n];  out[s, n] = that divisor."""
         S, pitch = out.shape
-        self.comm.epoch = self.round + 1
-        off = self.FLAG_BYTES + (self.round & 1) * self.half_bytes
-        _lib.check(self.lib.avd_fed_exchange_peer(C.byref(self.comm), 0, off, _lib.ptr(out), pitch, S, n, _lib.current_stream()))
+        _lib.check(self.lib.avd_fed_exchange_peer(C.byref(self.comm), 0, self.data_offset(), _lib.ptr(self.ctrl), _lib.ptr(out), pitch, S, n,
+                                                  _lib.current_stream()))
         self.round += 1
         return out
 
@@ -141,7 +146,7 @@ class FederatedAggregator:
         average to every agent, as workers/trainer.py:442-456 does (`[...][0]`).  transport: "peer" = the NVLink-native
         one-kernel exchange over symmetric memory (NVLS in-switch reduction when available; "p2p" forces plain peer loads),
         "nccl" = all_reduce + finalize,
-        "auto" = peer when the group spans several CUDA ranks and symmetric memory can be set up, else nccl."""
+        "auto" = peer when the group spans several CUDA ranks and symmetric memory can be set up ON EVERY RANK, else nccl."""
         self.pop, self.conf, self.pg = population, conf, process_group
         self.lib = _lib.load()
         if conf.fed_method not in ("interfrl", "intrafrl"):
@@ -168,18 +173,45 @@ class FederatedAggregator:
             self.apply_mask = mask
         self.rounds = 0
         self.peer = None
-        self.transport = "nccl"
+        self.transport = "nccl" if (self.inter and self.world > 1) else "local"
+        self.fallback_reason = None
         if transport not in ("auto", "peer", "p2p", "nccl"):
             raise ValueError("transport must be auto, peer, p2p or nccl")
         if transport != "nccl" and self.inter and self.world > 1 and dev.type == "cuda":
-            max_pitch = (population.actor.total + population.critic.total + 1 + 3) // 4 * 4
-            try:
-                self.peer = PeerExchange(process_group, self.n_systems, max_pitch, dev, allow_multicast=transport != "p2p")
-                self.transport = "peer/nvls" if self.peer.nvls else "peer/p2p"
-            except Exception:
-                if transport in ("peer", "p2p"):
-                    raise
-                self.peer = None
+            self._setup_peer(process_group, transport, dev)
+        self.ctrl = torch.zeros(2, dtype=torch.int32, device=dev) if dev.type == "cuda" else None     # single-rank rounds of the fused consumer
+        self.wsum = torch.zeros(self.n_systems, dtype=torch.float32, device=dev)
+        self.last_weight_sums = None         # [systems] divisors of the last round (sum of the FedAvg weights over ALL members), or None
+        self._apply_io = None
+
+    def _setup_peer(self, process_group, transport, dev):
+        """Symmetric-memory set-up, agreed COLLECTIVELY: a rank that failed locally must not call all_reduce while the others spin
+        in the peer kernel, so every rank contributes a success flag and all take the peer transport only if all succeeded."""
+        import torch.distributed as dist
+        pop = self.pop
+        max_pitch = (pop.actor.total + pop.critic.total + 1 + 3) // 4 * 4
+        peer, err = None, None
+        try:
+            peer = PeerExchange(process_group, self.n_systems, max_pitch, dev, allow_multicast=transport != "p2p")
+        except (RuntimeError, ValueError, ImportError, AttributeError, NotImplementedError) as e:      # what symm.empty / rendezvous raise
+            err = e
+        ok = torch.tensor([1 if peer is not None else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=process_group)
+        if int(ok.item()) == 1:
+            self.peer = peer
+            self.transport = "peer/nvls" if peer.nvls else "peer/p2p"
+            return
+        self.fallback_reason = repr(err) if err is not None else "symmetric memory unavailable on another rank"
+        if transport in ("peer", "p2p"):
+            raise RuntimeError(f"peer transport requested but not available on every rank: {self.fallback_reason}")
+        import warnings
+        warnings.warn(f"FederatedAggregator: falling back to the NCCL transport ({self.fallback_reason})")
+
+    @property
+    def graph_safe(self) -> bool:
+        """Rounds may be captured into a CUDA graph: the peer kernels keep their epoch on the device; single-rank rounds have no
+        exchange at all.  (The NCCL transport goes through torch.distributed, which this package does not capture.)"""
+        return self.world == 1 or self.peer is not None or not self.inter
 
     def _buffer(self, na, nc):
         key = (na, nc)
@@ -188,32 +220,53 @@ class FederatedAggregator:
             self._bufs[key] = torch.zeros(self.n_systems, pitch, dtype=torch.float32, device=self.device)
         return self._bufs[key]
 
-    def _reduce_exchange(self, a_src, na, c_src, nc, a_pitch, c_pitch, weights):
-        """-> buffer [systems, na+nc+1] holding the (weighted) means of actor / critic vectors."""
+    def _weights(self, weights):
+        if weights is None:
+            return None
+        return torch.as_tensor(weights, dtype=torch.float32, device=self.device).reshape(self.n_systems, self.n_members).contiguous()
+
+    def _use_peer(self):
+        return self.peer is not None and self.inter and self.world > 1
+
+    def _reduce(self, a_src, na, c_src, nc, a_pitch, c_pitch, weights):
+        """Local (weighted) sums of both banks + the divisor column, one launch; with the peer transport they go straight into this
+        round's half of the symmetric buffer.  -> (tensor [systems, pitch] holding the partial sums, pitch)"""
         S, X = self.n_systems, self.n_members
         buf = self._buffer(na, nc)
         pitch = buf.shape[1]
-        use_peer = self.peer is not None and self.inter and self.world > 1
-        dst = self.peer.half(S, pitch) if use_peer else buf        # partial sums go straight into the symmetric buffer
-        st = _lib.current_stream()
-        w = None
-        if weights is not None:
-            w = torch.as_tensor(weights, dtype=torch.float32, device=self.device).reshape(S, X).contiguous()
-        # one launch: (weighted) sums of both banks + the divisor column
+        dst = self.peer.half(S, pitch) if self._use_peer() else buf
+        w = self._weights(weights)
         _lib.check(self.lib.avd_fed_reduce2(_lib.ptr(dst), pitch, _lib.ptr(a_src), a_pitch, na, _lib.ptr(c_src), c_pitch, nc, S, X,
-                                            self.stride_s, self.stride_x, _lib.ptr(w), st))
-        if use_peer:
+                                            self.stride_s, self.stride_x, _lib.ptr(w), _lib.current_stream()))
+        return dst, pitch
+
+    def _reduce_exchange(self, a_src, na, c_src, nc, a_pitch, c_pitch, weights):
+        """-> buffer [systems, pitch]: columns [0, na+nc) the (weighted) means of actor / critic vectors, column na+nc the divisor."""
+        buf = self._buffer(na, nc)
+        self._reduce(a_src, na, c_src, nc, a_pitch, c_pitch, weights)
+        if self._use_peer():
             self.peer.exchange(buf, na + nc)
         else:
             exchange_and_scale(buf, self.pg if (self.inter and self.world > 1) else None, n=na + nc)
+        self.last_weight_sums = buf[:, na + nc]
         self.rounds += 1
         return buf
 
-    def aggregate_gradients(self, weights=None, apply: bool = True):
-        """train_all_models_federated_gradients (trainer.py:400-431): average actor/critic gradients per system,
-        then every member applies them with its own Adam and soft-updates its targets."""
+    def aggregate_gradients(self, weights=None, apply: bool = True, write_back: bool = True):
+        """train_all_models_federated_gradients (trainer.py:400-431): average actor/critic gradients per system, then every member
+        applies them with its own Adam and soft-updates its targets.  On CUDA with `apply` this is TWO launches: avd_fed_reduce2 and
+        the fused consumer avd_fed_apply_gradients (barrier -> in-switch reduction -> division -> Adam -> Polyak -> step counters);
+        `write_back` also stores the averaged gradients into every member's .grad row (what the unfused path leaves there).
+        The NCCL transport, `apply=False` and host tensors take reduce -> all_reduce -> finalize -> broadcast (-> Adam / Polyak)."""
         pop = self.pop
         na, nc = pop.actor.n_train, pop.critic.n_train
+        fused = apply and self.device.type == "cuda" and (self._use_peer() or not (self.inter and self.world > 1))
+        if fused:
+            part, pitch = self._reduce(pop.actor.grad, na, pop.critic.grad, nc, na, nc, weights)
+            self._apply_fused(part, pitch, write_back)
+            self.last_weight_sums = self.wsum
+            self.rounds += 1
+            return None
         buf = self._reduce_exchange(pop.actor.grad, na, pop.critic.grad, nc, na, nc, weights)
         _lib.check(self.lib.avd_fed_broadcast2(_lib.ptr(pop.actor.grad), na, na, _lib.ptr(pop.critic.grad), nc, nc, _lib.ptr(buf), buf.shape[1],
                                                self.n_systems, self.n_members, self.stride_s, self.stride_x, _lib.ptr(self.apply_mask),
@@ -221,6 +274,33 @@ class FederatedAggregator:
         if apply:
             pop.apply_gradients_and_soft_update(self.apply_mask)
         return buf
+
+    def _apply_fused(self, part, pitch, write_back):
+        pop, conf = self.pop, self.conf
+        if self._apply_io is None:
+            io = _lib.FedApplyIO()
+            a, c = pop.actor, pop.critic
+            io.n_systems, io.n_members, io.member_stride_s, io.member_stride_x, io.A = self.n_systems, self.n_members, self.stride_s, self.stride_x, pop.A
+            io.actor, io.t_actor, io.actor_m, io.actor_v, io.actor_step = a.flat.data_ptr(), pop.t_actor.flat.data_ptr(), a.m.data_ptr(), a.v.data_ptr(), a.step.data_ptr()
+            io.critic, io.t_critic, io.critic_m, io.critic_v, io.critic_step = c.flat.data_ptr(), pop.t_critic.flat.data_ptr(), c.m.data_ptr(), c.v.data_ptr(), c.step.data_ptr()
+            io.actor_total, io.actor_train, io.critic_total, io.critic_train = a.total, a.n_train, c.total, c.n_train
+            io.apply_mask = None if self.apply_mask is None else self.apply_mask.data_ptr()
+            io.wsum_out = self.wsum.data_ptr()
+            io.actor_lr, io.critic_lr, io.beta1, io.beta2, io.eps, io.tau = float(conf.actor_lr), float(conf.critic_lr), 0.9, 0.999, 1e-7, float(conf.tau)
+            self._apply_io = io
+        io = self._apply_io
+        io.pitch = pitch
+        io.actor_grad_out = pop.actor.grad.data_ptr() if write_back else None
+        io.critic_grad_out = pop.critic.grad.data_ptr() if write_back else None
+        if self._use_peer():
+            io.comm, io.flag_offset, io.data_offset = self.peer.comm, 0, self.peer.data_offset()
+            io.local_sums, io.ctrl = None, self.peer.ctrl.data_ptr()
+        else:
+            io.comm.rank, io.comm.world = 0, 1
+            io.flag_offset, io.data_offset, io.local_sums, io.ctrl = 0, 0, part.data_ptr(), self.ctrl.data_ptr()
+        _lib.check(self.lib.avd_fed_apply_gradients(C.byref(io), _lib.current_stream()))
+        if self._use_peer():
+            self.peer.round += 1
 
     def aggregate_weights(self, weights=None):
         """train_all_models_federated_weights (trainer.py:433-456): average `.weights` (incl. BN statistics) and

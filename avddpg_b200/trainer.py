@@ -146,7 +146,7 @@ class BatchedTrainer:
     """
 
     def __init__(self, conf, num_groups: int, envs_per_group: int = 1, *, ring_capacity=None, rank: int = 0, world: int = 1,
-                 process_group=None, precision: int = 0, seed=None, track_kinematics: bool = False):
+                 process_group=None, precision: int = 0, seed=None, track_kinematics: bool = False, fed_transport: str = "auto"):
         from .environment import BatchedPlatoons
         from .replaybuffer import ReplayRings
         self.conf, self.G, self.E, self.M = conf, int(num_groups), int(envs_per_group), int(conf.pl_size)
@@ -156,16 +156,24 @@ class BatchedTrainer:
         cap = int(conf.buffer_size if ring_capacity is None else ring_capacity)
         self.rings = ReplayRings(cap, self.M, self.P, int(conf.batch_size), seed=seed, ring_id_base=rank * self.M * self.P)
         self.env = BatchedPlatoons(self.P, self.M, conf, platoon_id_base=rank * self.P, seed=seed, ring=self.rings,
-                                   clock=self.rings.clock, auto_reset=True, collect_stats=True, track_kinematics=track_kinematics)
+                                   clock=self.rings.clock, auto_reset=True, collect_stats=True, track_kinematics=track_kinematics,
+                                   reward_history=int(conf.weighted_window) if is_fed_enabled(conf) and conf.weighted_average_enabled else 0)
         self.pop = DDPGPopulation(self.G, self.M, conf, num_states=self.env.num_states, rows_per_agent=self.E * int(conf.batch_size),
                                   seed=seed, precision=precision)
         self.fed = None
         if is_fed_enabled(conf):
             from .server.federated import FederatedAggregator
-            self.fed = FederatedAggregator(self.pop, conf, process_group=process_group)
+            self.fed = FederatedAggregator(self.pop, conf, process_group=process_group, transport=fed_transport)
         self.buffer_counter = 0          # == ReplayBuffer.buffer_counter of every ring
-        self.step_in_run = 0
-        self.episode = 0                 # used only by the FRL scheduling predicates
+        self.step_in_run = 0             # bookkeeping only
+        # What the FRL scheduling predicates see (workers/trainer.py:232, 251: `ep`, `i`).  run() counts real episodes and zeroes
+        # the step index at every env.reset(); the free-running step() loop (per-platoon auto-reset, no global episode) uses the
+        # nominal episode clock: a new episode every conf.steps_per_episode steps.
+        self.episode = 0
+        self.step_in_episode = 0
+        self._in_run = False
+        self.fed_weights = None          # [systems][members] device tensor of the current episode's FedAvg weights, or None
+        self._fed_w = None
         self.graph = None
         self.env.reset()
 
@@ -189,14 +197,49 @@ class BatchedTrainer:
         self.buffer_counter += 1
         if learn and self.buffer_counter > conf.batch_size:
             s, a, r, s2 = rings.sample(advance_clock=True)
-            fed_step = self.fed is not None and is_valid_update_step(conf, self.step_in_run)
+            ep, i = self.episode, self.step_in_episode
+            fed_step = self.fed is not None and is_valid_update_step(conf, i)
             pop.learn(s, a, r, s2, apply_updates=not fed_step)          # trainer.py:345: local update unless FRL step
             if self.fed is not None:
-                if is_valid_step_for_federated_training_with_gradients(conf, self.episode, self.step_in_run):
-                    self.fed.aggregate_gradients()
-                if is_valid_step_for_federated_training_with_weights(conf, self.episode, self.step_in_run):
-                    self.fed.aggregate_weights()
+                grads = is_valid_step_for_federated_training_with_gradients(conf, ep, i)
+                weights = is_valid_step_for_federated_training_with_weights(conf, ep, i)
+                if grads or weights:
+                    w = self._frl_weights(ep)                           # trainer.py:331-333: None before the weighting window
+                    if grads:
+                        self.fed.aggregate_gradients(w, write_back=False)
+                    if weights:
+                        self.fed.aggregate_weights(w)
         self.step_in_run += 1
+        self.step_in_episode += 1
+        if not self._in_run and self.step_in_episode >= int(conf.steps_per_episode):
+            self.step_in_episode, self.episode = 0, self.episode + 1
+
+    def _frl_weights(self, episode: int):
+        """FedAvg weights of this round, [systems][members] on the device: |1 / mean(last weighted_window episodic rewards)| per
+        agent (Trainer.get_weight, trainer.py:385-398), from the ring of finished-episode rewards the env kernel keeps.  None while
+        is_weighted_fed_enabled is false (plain mean)."""
+        conf = self.conf
+        self.fed_weights = None
+        if not is_weighted_fed_enabled(conf, episode):
+            return None
+        if self._fed_w is None:
+            self._fed_w = torch.zeros(self.fed.n_systems, self.fed.n_members, dtype=torch.float32, device=self.pop.device)
+        _lib.check(self.pop.lib.avd_fed_weights_from_history(_lib.ptr(self.env.ep_hist), int(conf.weighted_window), self.M, self.G, self.E,
+                                                             _lib.ptr(self._fed_w), 0 if self.fed.inter else 1, _lib.current_stream()))
+        self.fed_weights = self._fed_w
+        return self._fed_w
+
+    def frl_weight_lists(self):
+        """(fed_weights[g][m], fed_weight_sums[g][m]) of the last federated round as nested lists of np.float32, the layout
+        update_reward_list records (trainer.py:521-528), or (None, None) when the round was unweighted.  fed_weight_sums is the sum
+        over ALL members of the system -- over every rank's platoons for interfrl (it travels through the exchange)."""
+        if self.fed is None or self.fed_weights is None or self.fed.last_weight_sums is None:
+            return None, None
+        w = self.fed_weights.cpu().numpy().astype(np.float32)            # [S][X]
+        sums = self.fed.last_weight_sums.cpu().numpy().astype(np.float32)  # [S]
+        if self.fed.inter:      # systems = followers m, members = groups g
+            return ([[w[m, g] for m in range(self.M)] for g in range(self.G)], [[sums[m] for m in range(self.M)] for g in range(self.G)])
+        return ([[w[g, m] for m in range(self.M)] for g in range(self.G)], [[sums[g] for m in range(self.M)] for g in range(self.G)])
 
     def episodic_rewards(self):
         """Cumulative reward of the current episode per agent, [G][M] nested lists of np.float32 (the reference's
@@ -204,35 +247,59 @@ class BatchedTrainer:
         r = self.env.ep_reward.reshape(self.M, self.G, self.E).mean(dim=2).t().contiguous().cpu().numpy().astype(np.float32)
         return [[r[g, m] for m in range(self.M)] for g in range(self.G)]
 
-    def run(self, episodes: int, reward_log=None, *, global_break: bool = True, learn: bool = True):
+    def run(self, episodes: int, reward_log=None, *, global_break: bool = True, learn: bool = True, any_terminal_group=None):
         """The episode loop of Trainer.run (workers/trainer.py:232-273) for the whole population: every episode resets ALL
         platoons (246-249), runs up to conf.steps_per_episode steps (251), ends early for everybody when ANY platoon reports a
         terminal state (268-269; `global_break=False` lets the other platoons finish) and appends the episodic rewards to
         `reward_log` (an avddpg_b200.results.RewardLog; trainer.py:273, 510-517).  In-kernel auto-reset is switched off for the
         duration, so episodes line up across platoons exactly like the reference's; one D2H read of the done flags per step is
-        the price (the free-running `step()` loop used by the benchmark never synchronises).  Returns the number of env steps."""
+        the price (the free-running `step()` loop used by the benchmark never synchronises).  `any_terminal_group`: a
+        torch.distributed group over which "any platoon terminal" is agreed (one 1-word all_reduce(MAX) per step) so that platoons
+        sharded over several GPUs still end their episodes together (opt-in).  Returns the number of env steps."""
         env, conf = self.env, self.conf
         saved = env.auto_reset
         env.auto_reset = False
+        self._in_run = True
         steps = 0
         try:
             for _ in range(int(episodes)):
                 env.reset()
+                self.step_in_episode = 0                       # trainer.py:251: `i` restarts with every episode
                 for _ in range(int(conf.steps_per_episode)):
                     self.step(learn=learn)
                     steps += 1
-                    if global_break and bool((env.done & 1).any().item()):
-                        break
+                    if global_break:
+                        term = (env.done & 1).any()
+                        if any_terminal_group is not None:
+                            import torch.distributed as dist
+                            term = term.to(torch.int32)
+                            dist.all_reduce(term, op=dist.ReduceOp.MAX, group=any_terminal_group)
+                        if bool(term.item()):
+                            break
                 if reward_log is not None:
-                    reward_log.update_reward_list(self.episodic_rewards())
+                    fw, fws = self.frl_weight_lists() if is_weighted_fed_enabled(conf, self.episode) else (None, None)
+                    reward_log.update_reward_list(self.episodic_rewards(), fw, fws)
                 self.episode += 1
         finally:
             env.auto_reset = saved
+            self._in_run = False
         return steps
 
     def capture(self, warmup: int = 3):
-        """Capture one full step (learn included) into a CUDA graph; afterwards `replay()` costs one launch."""
+        """Capture one full step (learn included) into a CUDA graph; afterwards `replay()` costs one launch.  The host-side FRL
+        schedule is frozen into the graph, so capture is refused unless every step takes the same branch (fed_update_delay_steps == 1
+        and every episode a federated one); the cross-GPU exchange keeps its epoch / buffer half in device memory
+        (FederatedAggregator), so replays synchronise exactly like eager rounds."""
         assert self.buffer_counter > self.conf.batch_size, "fill the buffers past batch_size before capturing"
+        if self.fed is not None:
+            conf = self.conf
+            uniform = (int(conf.fed_update_delay_steps) == 1 and int(conf.fed_update_count) == 1 and float(conf.fed_cutoff_ratio) >= 1.0
+                       and not (conf.weighted_average_enabled and self.episode < int(conf.weighted_window)))
+            if not uniform:
+                raise RuntimeError("capture() needs a step-invariant FRL schedule: fed_update_delay_steps == 1, fed_update_count == 1, "
+                                   "fed_cutoff_ratio >= 1 and, with weighted averaging, an episode past the weighting window")
+            if not self.fed.graph_safe:
+                raise RuntimeError(f"the {self.fed.transport} FRL transport cannot be captured into a CUDA graph")
         stream = torch.cuda.Stream()
         stream.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(stream):
@@ -241,20 +308,24 @@ class BatchedTrainer:
         torch.cuda.current_stream().wait_stream(stream)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
-        cur, counters = self.env._cur, (self.buffer_counter, self.step_in_run)
+        cur, counters = self.env._cur, (self.buffer_counter, self.step_in_run, self.step_in_episode, self.episode)
         n0 = self.pop.lib.avd_kernel_launches()
         with torch.cuda.graph(self.graph):
             self.step()
             self.step()      # two steps per graph so the ping-pong state buffers end where they started
         self.kernels_per_step = (self.pop.lib.avd_kernel_launches() - n0) // 2
         assert self.env._cur == cur
-        self.buffer_counter, self.step_in_run = counters     # capturing executes nothing on the device
+        self.buffer_counter, self.step_in_run, self.step_in_episode, self.episode = counters     # capturing executes nothing on the device
         return self.graph
 
     def replay(self):
         self.graph.replay()
         self.buffer_counter += 2
         self.step_in_run += 2
+        self.step_in_episode += 2
+        spe = int(self.conf.steps_per_episode)
+        if not self._in_run and self.step_in_episode >= spe:
+            self.step_in_episode, self.episode = self.step_in_episode - spe, self.episode + 1
 
 
 class HostStepPipeline:

@@ -31,7 +31,7 @@ extern "C" {
 
 #define AVD_MAX_FOLLOWERS 16
 #define AVD_RING_RECORD_FLOATS 10
-#define AVD_ABI_VERSION 1
+#define AVD_ABI_VERSION 2
 
 typedef enum avd_status {
     AVD_OK = 0,
@@ -115,7 +115,12 @@ typedef struct avd_env_io {
     int32_t auto_reset;        /* 1: platoons that are done / timed out are reset inside the kernel  */
     int32_t clip_actions;      /* 1: clip the (noisy) action to [action_low, action_high] (ddpgagent.py:27);
                                   0: apply action_mu as given, like Platoon.step does                 */
-    int32_t reserved0;
+    int32_t ep_hist_window;    /* entries of ep_hist per agent (config.weighted_window); 0 with ep_hist == NULL */
+    /* End of an episode (avd_env_reset of a platoon that has stepped, or the in-kernel auto-reset): ep_reward is published to
+     * last_ep_reward and to slot (finished episode index % ep_hist_window) of ep_hist, then zeroed -- the reference's
+     * all_ep_reward_lists[p][m][-weighted_window:] (trainer.py:385-398, 510-517) without leaving the device.              */
+    float* last_ep_reward;     /* [M][P] nullable: cumulative reward of the last FINISHED episode              */
+    float* ep_hist;            /* [ep_hist_window][M][P] nullable: ring of the last finished episodes' rewards */
 } avd_env_io;
 
 /* ---- library ------------------------------------------------------------------------------- */
@@ -124,8 +129,8 @@ const char* avd_last_error(void);
 /* number of CUDA kernels this library has launched in the calling process so far (every launch site counts itself);
  * callers difference it around a region, e.g. bench.py's "gpu_launches" */
 int64_t avd_kernel_launches(void);
-/* sizeof of the ABI structs as compiled (0 avd_env_params, 1 avd_env_io, 2 avd_clock): bindings
- * assert their own layout against these at load time. */
+/* sizeof of the ABI structs as compiled (0 avd_env_params, 1 avd_env_io, 2 avd_clock, 3 avd_net_dims, 4 avd_learn_io,
+ * 5 avd_peer_comm, 6 avd_fed_apply_io): bindings assert their own layout against these at load time. */
 int64_t avd_sizeof(int which);
 /* SM count, compute capability major*10+minor of the current device; AVD_ERR_NO_DEVICE if none */
 int avd_device_info(int* sm_count, int* cc, int64_t* total_mem);
@@ -292,6 +297,12 @@ int avd_fed_broadcast2(float* out_a, int64_t pitch_a, int64_t na, float* out_c, 
                        int64_t in_pitch, int32_t n_systems, int32_t n_members, int64_t member_stride_s, int64_t member_stride_x,
                        const uint8_t* apply_mask, void* stream);
 
+/* Trainer.get_weight (workers/trainer.py:385-398) for all agents: w = |1 / mean(last `window` episodic rewards)| from the ring of
+ * finished-episode rewards the env kernel keeps (avd_env_io.ep_hist, [window][M][P], P = G*E; an agent's episodic reward is the mean
+ * over its group's E platoons).  out_w[m*G + g] (interfrl: systems = followers) or, with transpose, out_w[g*M + m] (intrafrl).       */
+int avd_fed_weights_from_history(const float* ep_hist, int32_t window, int32_t M, int64_t G, int64_t E, float* out_w,
+                                 int32_t transpose, void* stream);
+
 /* buf[s][0..n) *= 1 / buf[s][n]: turns the exchanged (weighted) sums into means (federated.py:62 / :110); the
  * divisor (member count or sum of weights) travels in column n of the same buffer through the all_reduce.     */
 int avd_fed_finalize(float* buf, int64_t pitch, int32_t n_systems, int64_t n, void* stream);
@@ -301,19 +312,49 @@ int avd_fed_finalize(float* buf, int64_t pitch, int32_t n_systems, int64_t n, vo
  * torch.distributed._symmetric_memory); peer_base[r] is rank r's allocation as seen from this process, multicast_base the NVLS
  * multicast mapping of the same allocation (0 if the fabric has none).  Inside the allocation: `flag_offset` -> AVD_MAX_PEERS
  * uint32 epoch flags (zero-initialised once), `data_offset` -> this round's partial sums [n_systems][pitch] fp32 with the local
- * member count / weight sum in column n.  The kernel signals `epoch` to every peer, waits for all peers, reads the sums over
- * ranks (multimem.ld_reduce in the NVSwitch, or peer loads) and writes out[s][j] = sum_r data_r[s][j] / sum_r data_r[s][n].
- * `epoch` must increase by one per call on every rank and the caller alternates `data_offset` between two halves.          */
+ * member count / weight sum in column n.  The kernel signals the round's epoch to every peer, waits for all peers, reads the sums
+ * over ranks (multimem.ld_reduce in the NVSwitch, or peer loads) and writes out[s][j] = sum_r data_r[s][j] / sum_r data_r[s][n]
+ * for j < n and the reduced divisor itself to out[s][n] (fed_weight_sums, trainer.py:358-359).
+ * `ctrl`: two zero-initialised uint32 words in LOCAL device memory, owned by the exchange kernels: [0] counts the completed rounds
+ * (the epoch: it is read at kernel start and advanced by the round's last CTA, so nothing about the barrier is baked into launch
+ * arguments and a captured CUDA graph replays correctly), [1] is a CTA ticket.  Every rank must issue the same sequence of
+ * exchange calls (this entry and avd_fed_apply_gradients share the epoch); the caller alternates `data_offset` between two halves. */
 #define AVD_MAX_PEERS 16
 typedef struct avd_peer_comm {
     int32_t rank, world;
-    uint32_t epoch;
-    uint32_t reserved0;
+    uint32_t reserved0, reserved1;
     uint64_t peer_base[AVD_MAX_PEERS];
     uint64_t multicast_base;
 } avd_peer_comm;
-int avd_fed_exchange_peer(const avd_peer_comm* comm, int64_t flag_offset, int64_t data_offset, float* out, int64_t pitch,
-                          int32_t n_systems, int64_t n, void* stream);
+int avd_fed_exchange_peer(const avd_peer_comm* comm, int64_t flag_offset, int64_t data_offset, uint32_t* ctrl, float* out,
+                          int64_t pitch, int32_t n_systems, int64_t n, void* stream);
+
+/* One federated GRADIENTS round after avd_fed_reduce2 (train_all_models_federated_gradients, workers/trainer.py:400-431), fused:
+ * cross-rank barrier -> sums over ranks (NVLS multimem.ld_reduce / peer loads; world == 1: `local_sums`) -> division by the reduced
+ * member count / weight sum (federated.py:62, :110) -> for every local member (s, x) = agent s*member_stride_s + x*member_stride_x
+ * with apply_mask != 0: tf.keras Adam on the trainable prefix with the averaged gradient, Polyak update of ALL target weights
+ * (ddpgagent.py:44-55), Adam step counters += 1.  The partial sums are rows [n_systems][pitch] with the actor gradient in columns
+ * [0, actor_train), the critic gradient in [actor_train, actor_train + critic_train) and the divisor in the next column.
+ * *_grad_out (nullable): the averaged gradient is also stored into every member's gradient row.  wsum_out (nullable): [n_systems]
+ * reduced divisors.  `ctrl`: see avd_fed_exchange_peer.                                                                          */
+typedef struct avd_fed_apply_io {
+    avd_peer_comm comm;
+    int64_t flag_offset, data_offset;
+    const float* local_sums;      /* world == 1 only: [n_systems][pitch]                               */
+    uint32_t* ctrl;
+    int64_t pitch;
+    int32_t n_systems, n_members;
+    int64_t member_stride_s, member_stride_x;
+    int32_t A, reserved0;
+    float *actor, *t_actor, *actor_m, *actor_v; int32_t* actor_step; float* actor_grad_out;
+    int64_t actor_total, actor_train;
+    float *critic, *t_critic, *critic_m, *critic_v; int32_t* critic_step; float* critic_grad_out;
+    int64_t critic_total, critic_train;
+    const uint8_t* apply_mask;    /* [A] nullable                                                      */
+    float* wsum_out;
+    float actor_lr, critic_lr, beta1, beta2, eps, tau;
+} avd_fed_apply_io;
+int avd_fed_apply_gradients(const avd_fed_apply_io* io, void* stream);
 
 /* out[a][j] = in[src(a)][j]: broadcast system averages back onto members (set_weights, trainer.py:448-456). */
 int avd_fed_broadcast(float* out, int64_t out_pitch, const float* in, int64_t in_pitch, int32_t n_systems,

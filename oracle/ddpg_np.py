@@ -108,19 +108,26 @@ def actor_forward(p, s, high=2.5):
     return out, dict(s=s, z1=z1, xh1=xh1, inv1=inv1, h1=h1, z2=z2, xh2=xh2, inv2=inv2, h2=h2, t=t, high=F32(high))
 
 
-def actor_backward(p, c, dout):
-    """dout[B,1] = dL/d(actor output).  Returns grads in ACTOR_TRAINABLE order (dict)."""
+def _ident(x):
+    return x
+
+
+def actor_backward(p, c, dout, absolute=False):
+    """dout[B,1] = dL/d(actor output).  Returns grads in ACTOR_TRAINABLE order (dict).
+    absolute=True: the same sums over the batch with every row's contribution replaced by its magnitude, sum_n |g_n| -- the
+    scale against which a rounding error of a gradient tensor is judged when the signed sum nearly cancels (tests only)."""
+    A = np.abs if absolute else _ident
     g = {}
     dpre3 = dout * c["high"] * (F32(1) - c["t"] ** 2)
-    g["W3"] = c["h2"].T @ dpre3; g["b3"] = dpre3.sum(0)
+    g["W3"] = A(c["h2"]).T @ A(dpre3); g["b3"] = A(dpre3).sum(0)
     dh2 = dpre3 @ p["W3"].T
-    g["g2"] = (dh2 * c["xh2"]).sum(0); g["be2"] = dh2.sum(0)
+    g["g2"] = A(dh2 * c["xh2"]).sum(0); g["be2"] = A(dh2).sum(0)
     dz2 = dh2 * p["g2"] * c["inv2"] * (c["z2"] > 0)
-    g["W2"] = c["h1"].T @ dz2; g["b2"] = dz2.sum(0)
+    g["W2"] = A(c["h1"]).T @ A(dz2); g["b2"] = A(dz2).sum(0)
     dh1 = dz2 @ p["W2"].T
-    g["g1"] = (dh1 * c["xh1"]).sum(0); g["be1"] = dh1.sum(0)
+    g["g1"] = A(dh1 * c["xh1"]).sum(0); g["be1"] = A(dh1).sum(0)
     dz1 = dh1 * p["g1"] * c["inv1"] * (c["z1"] > 0)
-    g["W1"] = c["s"].T @ dz1; g["b1"] = dz1.sum(0)
+    g["W1"] = A(c["s"]).T @ A(dz1); g["b1"] = A(dz1).sum(0)
     return {k: v.astype(F32) for k, v in g.items()}
 
 
@@ -137,8 +144,9 @@ def critic_forward(p, s, a):
     return q, dict(s=s, a=a, zs=zs, xhs=xhs, invs=invs, za=za, xha=xha, inva=inva, cat=cat, z2=z2, xh2=xh2, inv2=inv2, h2=h2)
 
 
-def critic_backward(p, c, dq, want_params=True):
-    """dq[B,1] = dL/dq.  Returns (param grads dict or None, dL/da[B,1])."""
+def critic_backward(p, c, dq, want_params=True, absolute=False):
+    """dq[B,1] = dL/dq.  Returns (param grads dict or None, dL/da[B,1]).  absolute: see actor_backward."""
+    A = np.abs if absolute else _ident
     g = {}
     dh2 = dq @ p["W3"].T
     dz2 = dh2 * p["g2"] * c["inv2"] * (c["z2"] > 0)
@@ -149,18 +157,18 @@ def critic_backward(p, c, dq, want_params=True):
     dza = dha * p["ga"] * c["inva"] * (c["za"] > 0)
     da = dza @ p["Wa"].T
     if want_params:
-        g["W3"] = c["h2"].T @ dq; g["b3"] = dq.sum(0)
-        g["g2"] = (dh2 * c["xh2"]).sum(0); g["be2"] = dh2.sum(0)
-        g["W2"] = c["cat"].T @ dz2; g["b2"] = dz2.sum(0)
-        g["gs"] = (dhs * c["xhs"]).sum(0); g["bes"] = dhs.sum(0)
-        g["ga"] = (dha * c["xha"]).sum(0); g["bea"] = dha.sum(0)
-        g["Ws"] = c["s"].T @ dzs; g["bs"] = dzs.sum(0)
-        g["Wa"] = c["a"].T @ dza; g["ba"] = dza.sum(0)
+        g["W3"] = A(c["h2"]).T @ A(dq); g["b3"] = A(dq).sum(0)
+        g["g2"] = A(dh2 * c["xh2"]).sum(0); g["be2"] = A(dh2).sum(0)
+        g["W2"] = A(c["cat"]).T @ A(dz2); g["b2"] = A(dz2).sum(0)
+        g["gs"] = A(dhs * c["xhs"]).sum(0); g["bes"] = A(dhs).sum(0)
+        g["ga"] = A(dha * c["xha"]).sum(0); g["bea"] = A(dha).sum(0)
+        g["Ws"] = A(c["s"]).T @ A(dzs); g["bs"] = A(dzs).sum(0)
+        g["Wa"] = A(c["a"]).T @ A(dza); g["ba"] = A(dza).sum(0)
         g = {k: v.astype(F32) for k, v in g.items()}
     return (g if want_params else None), da.astype(F32)
 
 
-def learn(actor, critic, t_actor, t_critic, batch, gamma=0.99, high=2.5):
+def learn(actor, critic, t_actor, t_critic, batch, gamma=0.99, high=2.5, with_abs=False):
     """Trainer.learn (trainer.py:489-506).  batch = (s[B,ns], a[B,1], r[B,1], s2[B,ns]).
     Returns (critic_grads, actor_grads, info) with grads as dicts keyed like *_TRAINABLE."""
     s, a, r, s2 = (np.asarray(x, F32) for x in batch)
@@ -177,7 +185,11 @@ def learn(actor, critic, t_actor, t_critic, batch, gamma=0.99, high=2.5):
     actor_loss = -np.mean(qpi)                                              # trainer.py:504
     _, dpi = critic_backward(critic, cc2, np.full_like(qpi, -1.0 / B), want_params=False)
     ag = actor_backward(actor, ca, dpi)                                     # trainer.py:506
-    return cg, ag, dict(critic_loss=float(critic_loss), actor_loss=float(actor_loss), y=y, q=q, pi=pi)
+    info = dict(critic_loss=float(critic_loss), actor_loss=float(actor_loss), y=y, q=q, pi=pi)
+    if with_abs:      # sum over the batch of the magnitudes of the per-row contributions, per tensor
+        info["critic_abs"], _ = critic_backward(critic, cc, dq, absolute=True)
+        info["actor_abs"] = actor_backward(actor, ca, dpi, absolute=True)
+    return cg, ag, info
 
 
 # ----------------------------------------------------------------------------------- optimiser / targets

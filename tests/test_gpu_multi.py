@@ -56,6 +56,30 @@ def _worker(rank, world, port, q):
             ok_a &= torch.allclose(pop.actor.grad.reshape(M, G, -1), (scale * want_a).expand(M, G, -1), rtol=2e-5, atol=1e-6)
             ok_c &= torch.allclose(pop.critic.grad.reshape(M, G, -1), (scale * want_c).expand(M, G, -1), rtol=2e-5, atol=1e-6)
     assert transports[0] == "nccl" and transports[1] == "peer/p2p" and transports[2].startswith("peer/"), transports
+    # full rounds with the update applied: the fused consumer of the peer transports (barrier -> in-switch reduction -> Adam ->
+    # Polyak in one kernel) ends where all_reduce + finalize + broadcast + Adam/Polyak ends; three rounds, weighted and not
+    snap = {k: getattr(pop, k).flat.clone() for k in ("actor", "critic", "t_actor", "t_critic")}
+    finals = []
+    for transport in ("nccl", "p2p", "peer"):
+        for k, v in snap.items():
+            getattr(pop, k).flat.copy_(v)
+        for bank in (pop.actor, pop.critic):
+            bank.m.zero_(); bank.v.zero_(); bank.step.zero_()
+        agg = FederatedAggregator(pop, conf, process_group=dist.group.WORLD, transport=transport)
+        for rnd in range(3):
+            pop.actor.grad.copy_((1.0 + rnd) * full_a[:, lo:lo + G].reshape(M * G, -1))
+            pop.critic.grad.copy_((1.0 + rnd) * full_c[:, lo:lo + G].reshape(M * G, -1))
+            wf = 0.5 + torch.arange(M * G_total, device="cuda", dtype=torch.float32).reshape(M, G_total) / 7.0
+            w = wf[:, lo:lo + G].contiguous() if rnd == 1 else None
+            out = agg.aggregate_gradients(weights=w, apply=True, write_back=False)
+            assert (out is None) == (transport != "nccl")          # peer transports: fused, nothing materialised
+            if w is not None:
+                ok_a &= torch.allclose(agg.last_weight_sums, wf.sum(1), rtol=1e-6)
+        ok_a &= pop.actor.step.tolist() == [3] * (M * G)
+        finals.append({k: getattr(pop, k).flat.clone() for k in snap})
+    for other in finals[1:]:
+        for k in snap:
+            ok_c &= torch.allclose(other[k], finals[0][k], rtol=2e-5, atol=1e-7)
     # sharded env == slice of the global env (RNG streams keyed by global platoon id)
     P_total = 64
     Pl = P_total // world

@@ -21,8 +21,8 @@ def timed(fn, n):
 
 
 for name, kw, G in (("C1 1 platoon x 2 followers", dict(pl_size=2), 1),
-                    ("C3 8 platoons x 4 followers, interfrl gradients", dict(pl_size=4, fed_method="interfrl"), 8)):
-    for prec in (0, 1):
+                    ("C3 8 platoons x 4 followers, interfrl gradients", dict(pl_size=4, fed_method="interfrl", weighted_average_enabled=False), 8)):
+    for prec in (0, 2):
         conf = Config(**kw)
         tr = BatchedTrainer(conf, num_groups=G, envs_per_group=1, ring_capacity=4096, precision=prec)
         for _ in range(conf.batch_size + 8):
