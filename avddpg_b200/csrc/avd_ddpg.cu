@@ -33,11 +33,12 @@ namespace avd {
 typedef __nv_bfloat16 bf16;
 
 namespace fused3 {  // avd_fused3.cu
-enum Mode { MODE_ACTOR_OUT = 0, MODE_TARGET = 1, MODE_Q = 2, MODE_CRITIC_BWD = 3, MODE_ACTOR_BWD = 4, MODE_CRITIC_ACTION = 5 };
+enum Mode { MODE_ACTOR_OUT = 0, MODE_TARGET = 1, MODE_Q = 2, MODE_CRITIC_BWD = 3, MODE_ACTOR_BWD = 4, MODE_CRITIC_ACTION = 5, MODE_ACTOR_SAVE = 6 };
 bool supported(const avd_net_dims& d);
 int run(int mode, bool f16, const avd_net_dims& d, int A, int64_t R, const float* params, int64_t pstride, const bf16* W2T, const float* b2f,
         const float* wscale, const float* s, int64_t s_rs, int64_t s_cs, const float* act, const float* rew, float gamma, float high, const float* y,
-        const float* dpi, float* out, uint32_t* mask_out, bf16* DZ_out, float dm_scale, float* sdq, float* loss, cudaStream_t st);
+        const float* dpi, float* out, uint32_t* mask_out, bf16* DZ_out, float dm_scale, float* sdq, float* loss, cudaStream_t st,
+        uint32_t* mask2_out = nullptr, float* dact_out = nullptr);
 }
 
 namespace wgrad3 {  // avd_wgrad3.cu
@@ -861,6 +862,43 @@ __global__ void __launch_bounds__(256) xext_kernel(const float* __restrict__ s, 
     }
 }
 
+// Actor backward tile of the learn step without a second forward pass: MODE_ACTOR_SAVE kept the sign bits of z2 + b2' and
+// d(action)/d(pre-activation), the critic-action pass delivered d(-mean q)/d(action) per row, so
+//   dq_n = dpi_n * dact_n,     dm[n][j] = dm_scale * dq_n [z2 + b2' > 0][n][j]      (trainer.py:503-506 through model.py:30-37)
+// is elementwise: 24 B read and 256 B written per row (HBM-bound) instead of the 118 us tensor-core pass it replaces.
+// 16 threads per row (8 columns = one 16-byte store each); grid (row blocks, agents); sum_n dq_n accumulated per agent.
+template <bool F16>
+__global__ void __launch_bounds__(256) actor_dm_kernel(const float* __restrict__ dpi, const float* __restrict__ dact, const uint32_t* __restrict__ mask2,
+                                                       bf16* __restrict__ DZ, float* __restrict__ sdq, int64_t R, float dm_scale) {
+    pdl_wait();
+    pdl_launch_dependents();
+    const int agent = blockIdx.y;
+    const int seg = threadIdx.x & 15;
+    float acc = 0.0f;
+    for (int64_t r = (int64_t)blockIdx.x * 16 + (threadIdx.x >> 4); r < R; r += (int64_t)gridDim.x * 16) {
+        const int64_t n = (int64_t)agent * R + r;
+        const float dq = __ldg(dpi + n) * __ldg(dact + n);
+        if (seg == 0) acc += dq;
+        const uint32_t bits = __ldg(mask2 + n * 4 + (seg >> 2)) << ((seg & 3) * 8);      // column 8 seg + k at bit 31 - k
+        const float dqs = dq * dm_scale;
+        uint32_t pk[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            pk[k] = umma::pack_x2<F16>((bits & (0x80000000u >> (2 * k))) ? 0.0f : dqs, (bits & (0x80000000u >> (2 * k + 1))) ? 0.0f : dqs);
+        *reinterpret_cast<uint4*>(DZ + n * 128 + seg * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+    __shared__ float red[8];
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += red[k];
+        atomicAdd(sdq + agent, t);
+    }
+}
+
 // Unfold the gradients of the BN-folded formulation into the Keras trainable tensors (one warp per layer-1 feature f).
 // In:  G2[f][j] = sum_n r1[n][f] dz2[n][j] and G1[f][16] as `ncta` partial slices per agent (one per persistent CTA of the
 //      wgrad / dgrad kernels, summed here),  G[ob2 + j] = db2[j]  (dgrad kernel).
@@ -998,6 +1036,8 @@ struct Workspace {
     bf16 *cW2b, *cW2T, *tcW2T, *aW2b, *aW2T, *taW2T;   // packed weights (precision 1: bf16; precision 2: fp16)
     bf16* cTW2T;               // precision 2: T pack of the critic for the critic-action pass
     float* wscale;             // precision 2: [2][A] 1 / s of the critic [0] and actor [1] W2'' / T packs
+    uint32_t* mask2;           // [N][4] sign bits of the actor's z2 + b2' (MODE_ACTOR_SAVE -> actor_dm_kernel)
+    float* dact;               // [N] d(action)/d(pre-activation) of the actor
     // BN-folded tensor-core path: sign masks of z1, [x_hi | 1 | x_lo] operand, layer-1 weight-gradient accumulator, folded biases
     uint32_t* mask;
     bf16* xextT;               // [A][16][Rp], Rp = R rounded up to 64
@@ -1010,7 +1050,7 @@ struct Workspace {
         const int64_t F = d.l1 + d.la;
         const int64_t acts = N * (2 * F + d.l1 + 3 * (int64_t)d.l2) * (int64_t)sizeof(float);
         const int64_t packed = A * (4 * F + 3 * (int64_t)d.l1) * d.l2 * (int64_t)sizeof(bf16) + (2 * A + 4) * (int64_t)sizeof(float);
-        const int64_t vecs = 4 * ((N + 3) / 4 * 4) * (int64_t)sizeof(float);
+        const int64_t vecs = (5 + 4) * ((N + 3) / 4 * 4) * (int64_t)sizeof(float);
         const int64_t slices = std::max<int64_t>(A, sm_count());
         const int64_t fold = N * (kMaskWords * 4 + 16 * 2) + A * (8 * (int64_t)d.l2 + 16) * (int64_t)sizeof(float) + A * 16 * 64 * 2 +
                              slices * (kFp * 16 + kG2Rows * (int64_t)d.l2) * (int64_t)sizeof(float);
@@ -1040,6 +1080,8 @@ struct Workspace {
         y = p; p += Np;
         q = p; p += Np;
         dpi = p; p += Np;
+        dact = p; p += Np;
+        mask2 = reinterpret_cast<uint32_t*>(p); p += 4 * Np;
         const int64_t slices = std::max<int64_t>(A, sm_count());
         G1 = p; p += slices * kFp * 16;
         G2part = p; p += slices * kG2Rows * d.l2;
@@ -1569,14 +1611,23 @@ static int learn_fused3(const avd_learn_io* io, const Pass& p, const Workspace& 
                             w.sdq, w.ticket, ws_c, dm_c));
     tm.mark("critic_dgrad+unfold");
     // ---- actor loss gradient: -mean(critic(s, actor(s)))                            trainer.py:501-506
-    AVD_TRY(fused3::run(fused3::MODE_ACTOR_OUT, f16, d, A, R, io->actor, ao.total, w.aW2T, w.a_b2f, nullptr, io->s, d.ns, 1, nullptr, nullptr, 0.f,
-                        io->action_high, nullptr, nullptr, w.a2, nullptr, nullptr, 1.0f, nullptr, nullptr, st));   // pi
+    static const bool legacy_actor_bwd = getenv("AVD_ACTOR_BWD_PASS") != nullptr;     // diagnostic: the round-1 second forward pass
+    AVD_TRY(fused3::run(legacy_actor_bwd ? fused3::MODE_ACTOR_OUT : fused3::MODE_ACTOR_SAVE, f16, d, A, R, io->actor, ao.total, w.aW2T, w.a_b2f, nullptr,
+                        io->s, d.ns, 1, nullptr, nullptr, 0.f, io->action_high, nullptr, nullptr, w.a2, legacy_actor_bwd ? nullptr : w.mask, nullptr, 1.0f,
+                        nullptr, nullptr, st, w.mask2, w.dact));   // pi (+ the sign masks and d(action)/d(pre-activation) for the backward)
     tm.mark("actor_fwd");
     AVD_TRY(fused3::run(fused3::MODE_CRITIC_ACTION, f16, d, A, R, io->critic, co.total, f16 ? w.cTW2T : w.cW2T, w.c_b2f, ws_c, io->s, d.ns, 1, w.a2,
                         nullptr, 0.f, 0.f, nullptr, nullptr, w.dpi, nullptr, nullptr, 1.0f, nullptr, io->loss, st));          // d(-mean q)/d pi
     tm.mark("critic_action");
-    AVD_TRY(fused3::run(fused3::MODE_ACTOR_BWD, f16, d, A, R, io->actor, ao.total, w.aW2T, w.a_b2f, nullptr, io->s, d.ns, 1, nullptr, nullptr, 0.f,
-                        io->action_high, nullptr, w.dpi, nullptr, w.mask, DZ, dm_a, w.sdq + A, nullptr, st));
+    if (legacy_actor_bwd) {
+        AVD_TRY(fused3::run(fused3::MODE_ACTOR_BWD, f16, d, A, R, io->actor, ao.total, w.aW2T, w.a_b2f, nullptr, io->s, d.ns, 1, nullptr, nullptr, 0.f,
+                            io->action_high, nullptr, w.dpi, nullptr, w.mask, DZ, dm_a, w.sdq + A, nullptr, st));
+    } else {
+        const dim3 grid((unsigned)std::min<int64_t>((R + 15) / 16, std::max(1, 8 * sm_count() / A)), (unsigned)A);
+        if (f16) AVD_CUDA_OK(launch_pdl(actor_dm_kernel<true>, grid, dim3(256), 0, st, (const float*)w.dpi, (const float*)w.dact, (const uint32_t*)w.mask2, DZ, w.sdq + A, R, dm_a));
+        else AVD_CUDA_OK(launch_pdl(actor_dm_kernel<false>, grid, dim3(256), 0, st, (const float*)w.dpi, (const float*)w.dact, (const uint32_t*)w.mask2, DZ, w.sdq + A, R, dm_a));
+        AVD_LAUNCH_OK();
+    }
     tm.mark("actor_bwd");
     AVD_TRY(wgrad3::run(f16, d, false, A, R, io->actor, ao.total, io->s, nullptr, DZ, w.G2part, g2_agent, g2_cta, st));
     tm.mark("actor_wgrad");

@@ -52,7 +52,10 @@ constexpr int OFF_BAR = OFF_PART + 2 * 4 * TILE_M * 4;
 constexpr int SMEM_BYTES = OFF_BAR + 512 + 1024;
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB shared memory of an sm_100 CTA");
 
-enum Mode { MODE_ACTOR_OUT = 0, MODE_TARGET = 1, MODE_Q = 2, MODE_CRITIC_BWD = 3, MODE_ACTOR_BWD = 4, MODE_CRITIC_ACTION = 5 };
+// MODE_ACTOR_SAVE: the actor forward pass that ALSO keeps what its backward needs -- sign bits of z1 (40 B per row) and of
+// z2 + b2' (16 B), and d(action)/d(pre-activation) = high (1 - tanh^2) (4 B) -- so that the actor backward of the learn step is an
+// elementwise kernel (actor_dm_kernel, avd_ddpg.cu) instead of a second full forward pass (MODE_ACTOR_BWD, kept for reference).
+enum Mode { MODE_ACTOR_OUT = 0, MODE_TARGET = 1, MODE_Q = 2, MODE_CRITIC_BWD = 3, MODE_ACTOR_BWD = 4, MODE_CRITIC_ACTION = 5, MODE_ACTOR_SAVE = 6 };
 
 struct Args {
     avd_net_dims d;
@@ -69,8 +72,10 @@ struct Args {
     const float* y;             // MODE_CRITIC_BWD: TD targets
     const float* dpi;           // MODE_ACTOR_BWD: d loss / d action
     float* out;                 // forward modes: [A*R]; MODE_CRITIC_ACTION: d loss / d action; MODE_CRITIC_BWD: q (nullable)
-    uint32_t* mask_out;         // backward modes: [A*R][mask_words] sign bits of z1 (column j of word w at bit 31-j)
+    uint32_t* mask_out;         // backward modes / MODE_ACTOR_SAVE: [A*R][mask_words] sign bits of z1 (column j of word w at bit 31-j)
     int mask_words;
+    uint32_t* mask2_out;        // MODE_ACTOR_SAVE: [A*R][4] sign bits of z2 + b2'
+    float* dact_out;            // MODE_ACTOR_SAVE: [A*R] high (1 - tanh^2(pre-activation))
     const float* wscale;        // MODE_CRITIC_ACTION with fp16 operands: [A] 1 / s of the T = W2' diag(w3') s pack (pack_fold4_kernel)
     float dm_scale;             // backward modes: power-of-two factor on the dm tile (1 for bf16; fp16 needs dq ~ 1 / R lifted into its range)
     float* sdq;                 // backward modes: [A]       += sum_n dq_n
@@ -109,7 +114,8 @@ __device__ __forceinline__ uint32_t pack2(bf16 a, bf16 b) {
 // weight, instead of bf16(dq w3') x bf16(W2')):   d(-mean q)/d a = -(1 / (R s)) sum_f [za_f > 0] wa_f sum_j [z2_j + b2'_j > 0] T[f][j].
 template <int MODE, bool F16>
 __global__ void __launch_bounds__(NUM_THREADS, 1) fused3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmDZ, Args g) {
-    constexpr bool CRITIC = MODE != MODE_ACTOR_OUT && MODE != MODE_ACTOR_BWD;
+    constexpr bool CRITIC = MODE != MODE_ACTOR_OUT && MODE != MODE_ACTOR_BWD && MODE != MODE_ACTOR_SAVE;
+    constexpr bool SAVE = MODE == MODE_ACTOR_SAVE;                               // forward pass that keeps its sign masks
     constexpr bool BWD = MODE == MODE_CRITIC_BWD || MODE == MODE_ACTOR_BWD;      // full backward: masks, r1 / dz2 to HBM, U
     constexpr bool ACTION = MODE == MODE_CRITIC_ACTION;                          // backward to the action input only
     constexpr bool HAS_DZ = BWD || ACTION;
@@ -392,7 +398,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused3_kernel(const __grid_con
                 float z[32];
                 tmem_ld32(tmem_base + 256u + (uint32_t)(c4 * 64 + h * 32) + tlane, z);
                 uint32_t m = 0;
-                if (BWD) {
+                if (BWD || SAVE) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) m = __funnelshift_l(__float_as_uint(z[j]), m, 1);
                 }
@@ -408,7 +414,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused3_kernel(const __grid_con
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) { mbar_arrive(z1_empty); mbar_arrive_cnt(&a_full[sl], 2); }   // every slot barrier counts 8: 4 warps x 2 here, 8 warps x 1 for the action block
-            if (BWD && valid) *reinterpret_cast<uint2*>(g.mask_out + nrow * g.mask_words + 2 * c4) = make_uint2(neg[0], neg[1]);
+            if ((BWD || SAVE) && valid) *reinterpret_cast<uint2*>(g.mask_out + nrow * g.mask_words + 2 * c4) = make_uint2(neg[0], neg[1]);
             if (CRITIC && (c4 == ga0 || c4 == ga0 + 1)) {        // action branch: one input per column, CUDA cores
                 const int j0 = (c4 == ga0) ? 0 : 32;
                 const uint32_t kca = (uint32_t)(tc * NKB + 4), sla = kca % NSLOT;
@@ -471,7 +477,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused3_kernel(const __grid_con
                 acc = fmaf(fmaxf(t1, 0.0f), w4.y, acc);
                 acc = fmaf(fmaxf(t2, 0.0f), w4.z, acc);
                 acc = fmaf(fmaxf(t3, 0.0f), w4.w, acc);
-                if (HAS_DZ) {
+                if (HAS_DZ || SAVE) {
                     m = __funnelshift_l(__float_as_uint(t0), m, 1);
                     m = __funnelshift_l(__float_as_uint(t1), m, 1);
                     m = __funnelshift_l(__float_as_uint(t2), m, 1);
@@ -479,6 +485,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused3_kernel(const __grid_con
                 }
             }
             if (HAS_DZ) zneg = m;
+            if (SAVE) {
+                bool v1;
+                const int64_t n1 = rowinfo(tc, v1);
+                if (v1) g.mask2_out[n1 * 4 + c4] = m;
+            }
             part[(buf * 4 + c4) * TILE_M + row] = acc;
             tc_fence_before();
             __syncwarp();
@@ -505,7 +516,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused3_kernel(const __grid_con
                                    : pb[0] + pb[TILE_M] + pb[2 * TILE_M] + pb[3 * TILE_M] + b3f;
             if (!HAS_DZ) {
                 float o;
-                if (MODE == MODE_ACTOR_OUT) o = g.high * tanhf(qv);
+                if (MODE == MODE_ACTOR_OUT || SAVE) {
+                    const float t = tanhf(qv);
+                    o = g.high * t;
+                    if (SAVE && valid) g.dact_out[nrow] = g.high * (1.0f - t * t);       // through high * tanh(.)    model.py:36-37
+                }
                 else if (MODE == MODE_TARGET) o = yv + g.gamma * qv;                 // trainer.py:494 (no terminal mask)
                 else o = qv;
                 if (valid) g.out[nrow] = o;
@@ -692,12 +707,13 @@ static int launch(bool f16, const CUtensorMap& tmW, const CUtensorMap& tmDZ, con
 // Backward modes: mask_out [A*R][2*ceil(F/64)] sign masks of z1, DZ_out: 16-bit [A*R][128] = dm_scale * dq [z2 + b2' > 0], sdq [A] accumulated into.
 int run(int mode, bool f16, const avd_net_dims& d, int A, int64_t R, const float* params, int64_t pstride, const bf16* W2T, const float* b2f,
         const float* wscale, const float* s, int64_t s_rs, int64_t s_cs, const float* act, const float* rew, float gamma, float high, const float* y,
-        const float* dpi, float* out, uint32_t* mask_out, bf16* DZ_out, float dm_scale, float* sdq, float* loss, cudaStream_t st) {
+        const float* dpi, float* out, uint32_t* mask_out, bf16* DZ_out, float dm_scale, float* sdq, float* loss, cudaStream_t st,
+        uint32_t* mask2_out, float* dact_out) {
     if (!supported(d)) {
         set_error("fused pass kernel does not support these layer sizes");
         return AVD_ERR_UNSUPPORTED;
     }
-    const bool critic = mode != MODE_ACTOR_OUT && mode != MODE_ACTOR_BWD;
+    const bool critic = mode != MODE_ACTOR_OUT && mode != MODE_ACTOR_BWD && mode != MODE_ACTOR_SAVE;
     const bool bwd = mode == MODE_CRITIC_BWD || mode == MODE_ACTOR_BWD;
     const int F = critic ? d.l1 + d.la : d.l1;
     AVD_REQUIRE(params && W2T && b2f && s, "null buffer");
@@ -706,6 +722,7 @@ int run(int mode, bool f16, const avd_net_dims& d, int A, int64_t R, const float
     AVD_REQUIRE(!bwd || (mask_out && DZ_out && sdq), "backward passes need mask / dz2 / sdq outputs");
     AVD_REQUIRE(!(f16 && mode == MODE_CRITIC_ACTION) || wscale, "the fp16 critic-action pass needs the scale of its T pack");
     AVD_REQUIRE(bwd || out, "null output");
+    AVD_REQUIRE(mode != MODE_ACTOR_SAVE || (mask_out && mask2_out && dact_out), "MODE_ACTOR_SAVE needs the mask / d(action) outputs");
     CUtensorMap tmW, tmDZ;
     if (int rc = make_map(&tmW, W2T, (uint64_t)F, L2N, (uint64_t)A, (uint64_t)F, (uint64_t)F * L2N)) return rc;
     tmDZ = tmW;
@@ -714,7 +731,7 @@ int run(int mode, bool f16, const avd_net_dims& d, int A, int64_t R, const float
     Args g;
     g.d = d; g.A = A; g.R = R; g.params = params; g.pstride = pstride; g.b2f = b2f; g.s = s; g.s_rs = s_rs; g.s_cs = s_cs; g.act = act;
     g.rew = rew; g.gamma = gamma; g.high = high; g.y = y; g.dpi = dpi; g.out = out; g.mask_out = mask_out; g.mask_words = 2 * ((F + KB - 1) / KB);
-    g.wscale = wscale; g.dm_scale = dm_scale; g.sdq = sdq; g.loss = loss;
+    g.wscale = wscale; g.dm_scale = dm_scale; g.sdq = sdq; g.loss = loss; g.mask2_out = mask2_out; g.dact_out = dact_out;
     g.tiles_per_agent = (int)((R + TILE_M - 1) / TILE_M);
     g.ctas_per_agent = std::max(1, std::min(g.tiles_per_agent, sm_count() / std::max(1, A)));
     const dim3 grid((unsigned)(g.ctas_per_agent * A));
@@ -725,6 +742,7 @@ int run(int mode, bool f16, const avd_net_dims& d, int A, int64_t R, const float
         case MODE_CRITIC_BWD: return launch<MODE_CRITIC_BWD>(f16, tmW, tmDZ, g, grid, st);
         case MODE_ACTOR_BWD: return launch<MODE_ACTOR_BWD>(f16, tmW, tmDZ, g, grid, st);
         case MODE_CRITIC_ACTION: return launch<MODE_CRITIC_ACTION>(f16, tmW, tmDZ, g, grid, st);
+        case MODE_ACTOR_SAVE: return launch<MODE_ACTOR_SAVE>(f16, tmW, tmDZ, g, grid, st);
     }
     set_error("unknown fused pass mode %d", mode);
     return AVD_ERR_INVALID_ARG;
