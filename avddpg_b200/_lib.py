@@ -75,7 +75,7 @@ class LearnIO(C.Structure):
         ("actor_t", C.c_void_p), ("critic_t", C.c_void_p),
         ("apply_mask", C.c_void_p), ("loss", C.c_void_p),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
-        ("precision", C.c_int32), ("reserved0", C.c_int32),
+        ("precision", C.c_int32), ("s_stride", C.c_int32),
     ]
 
 

@@ -35,16 +35,19 @@ typedef __nv_bfloat16 bf16;
 namespace fused3 {  // avd_fused3.cu
 enum Mode { MODE_ACTOR_OUT = 0, MODE_TARGET = 1, MODE_Q = 2, MODE_CRITIC_BWD = 3, MODE_ACTOR_BWD = 4, MODE_CRITIC_ACTION = 5, MODE_ACTOR_SAVE = 6 };
 bool supported(const avd_net_dims& d);
+int vtab_rows();
+int vtab_stride();
+int vtab_floats();
 int run(int mode, bool f16, const avd_net_dims& d, int A, int64_t R, const float* params, int64_t pstride, const bf16* W2T, const float* b2f,
-        const float* wscale, const float* s, int64_t s_rs, int64_t s_cs, const float* act, const float* rew, float gamma, float high, const float* y,
+        const float* vtab, const float* s, int64_t s_rs, int64_t s_cs, const float* act, const float* rew, float gamma, float high, const float* y,
         const float* dpi, float* out, uint32_t* mask_out, bf16* DZ_out, float dm_scale, float* sdq, float* loss, cudaStream_t st,
         uint32_t* mask2_out = nullptr, float* dact_out = nullptr);
 }
 
 namespace wgrad3 {  // avd_wgrad3.cu
 int ctas_per_agent(int A, int64_t R);
-int run(bool f16, const avd_net_dims& d, bool critic, int A, int64_t R, const float* params, int64_t pstride, const float* s, const float* act,
-        const bf16* DZ, float* out, int64_t out_agent_stride, int64_t out_cta_stride, cudaStream_t st);
+int run(bool f16, const avd_net_dims& d, bool critic, int A, int64_t R, const float* params, int64_t pstride, const float* s, int64_t s_rs,
+        const float* act, const bf16* DZ, float* out, int64_t out_agent_stride, int64_t out_cta_stride, cudaStream_t st);
 }
 
 namespace dgrad3 {  // avd_dgrad3.cu
@@ -135,7 +138,7 @@ __global__ void __launch_bounds__(128) l1_forward_kernel(avd_net_dims d, const f
 // state / action columns run in separately specialised loops.
 template <bool CRITIC>
 __global__ void __launch_bounds__(128) l1_backward_kernel(avd_net_dims d, const float* __restrict__ params, int64_t pstride,
-                                                          const float* __restrict__ s, const float* __restrict__ act, int64_t R,
+                                                          const float* __restrict__ s, int64_t s_rs, const float* __restrict__ act, int64_t R,
                                                           const float* __restrict__ dH, float* __restrict__ grads, int64_t gstride) {
     constexpr int ROWS = kL1BwdRows;
     const int agent = blockIdx.y;
@@ -151,7 +154,7 @@ __global__ void __launch_bounds__(128) l1_backward_kernel(avd_net_dims d, const 
     for (int r = threadIdx.x; r < ROWS; r += blockDim.x) {
         float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         if (r < nrows)
-            for (int k = 0; k < d.ns; ++k) v[k] = s[(base + r) * d.ns + k];
+            for (int k = 0; k < d.ns; ++k) v[k] = s[(base + r) * s_rs + k];
         xs4[r] = make_float4(v[0], v[1], v[2], v[3]);
         xs_hi[r] = make_float4(v[4], v[5], v[6], v[7]);
         xa[r] = (CRITIC && r < nrows) ? act[base + r] : 0.0f;
@@ -769,12 +772,11 @@ struct FoldJob {
     int64_t g2, var2, W3;       // head: BatchNorm 2 scale / variance and the output weights (for w3' = sc2 w3)
     int F;
     bf16 *W2b, *W2T;            // W2b (dgrad operand, nullable): [F][l2] = W2' diag(w3');  W2T (forward operand): [l2][F] = W2'^T
-    float* b2f;                 // nullable (the T pack shares the folded bias of the plain pack)
-    int tpack;                  // 1: W2T holds T^T = (W2' diag(w3') s)^T, the operand of the fp16 critic-action pass (avd_fused3.cu)
-    float* wscale;              // fp16 only, nullable: [A] 1 / s.  W2b and the T pack are scaled by s = 2^-e, max_j |w3'_j| 2^-e in [0.5, 1):
+    float* b2f;
+    float* wscale;              // fp16 only, nullable: [A] 1 / s.  W2b is scaled by s = 2^-e, max_j |w3'_j| 2^-e in [0.5, 1):
                                 // the products W2' w3' (~1e-5 at initialisation) would otherwise sit in the subnormal range of fp16
 };
-constexpr int kFoldJobs = 5;
+constexpr int kFoldJobs = 4;
 struct FoldJobs { FoldJob j[kFoldJobs]; };
 
 __global__ void __launch_bounds__(256) pack_fold4_kernel(FoldJobs jobs, int A, int l2, int f16) {
@@ -782,7 +784,7 @@ __global__ void __launch_bounds__(256) pack_fold4_kernel(FoldJobs jobs, int A, i
     const FoldJob& jb = jobs.j[job];
     if ((int)blockIdx.y * 8 >= jb.F) return;
     float s_w3 = 1.0f;          // the power-of-two scale s of this (net, agent): every CTA derives it from the same 128 head weights
-    if (f16 && (jb.W2b || jb.tpack)) {
+    if (f16 && jb.W2b) {
         __shared__ float mx[8];
         const float* Pq = jb.params + (int64_t)agent * jb.pstride;
         float m = 0.0f;
@@ -817,15 +819,17 @@ __global__ void __launch_bounds__(256) pack_fold4_kernel(FoldJobs jobs, int A, i
         const float sc = P[(st ? o.g[0] : o.g[1]) + c] / sqrtf(P[(st ? o.var[0] : o.var[1]) + c] + kBnEps);
         const float sh = P[(st ? o.be[0] : o.be[1]) + c] - P[(st ? o.mu[0] : o.mu[1]) + c] * sc;
         const float w = P[o.W2 + (int64_t)f * l2 + j];
-        const float w3p = (jb.W2b || jb.tpack) ? P[jb.W3 + j] * P[jb.g2 + j] / sqrtf(P[jb.var2 + j] + kBnEps) * s_w3 : 1.0f;
         // the backward tile carries dq [z2 > 0] without the head weight (avd_fused3.cu): dR = dm (W2' diag(w3'))^T
-        if (jb.W2b) jb.W2b[((int64_t)agent * F + f) * l2 + j] = to_op16(sc * w * w3p, f16);
-        jb.W2T[((int64_t)agent * l2 + j) * F + f] = to_op16(jb.tpack ? sc * w * w3p : sc * w, f16);
+        if (jb.W2b) {
+            const float w3p = P[jb.W3 + j] * P[jb.g2 + j] / sqrtf(P[jb.var2 + j] + kBnEps) * s_w3;
+            jb.W2b[((int64_t)agent * F + f) * l2 + j] = to_op16(sc * w * w3p, f16);
+        }
+        jb.W2T[((int64_t)agent * l2 + j) * F + f] = to_op16(sc * w, f16);
         acc = sh * w;
     }
     red[fy][threadIdx.x & 31] = acc;
     __syncthreads();
-    if (fy == 0 && j < l2 && jb.b2f) {
+    if (fy == 0 && j < l2) {
         float t = blockIdx.y == 0 ? P[o.b2 + j] : 0.0f;
 #pragma unroll
         for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x];
@@ -837,12 +841,12 @@ __global__ void __launch_bounds__(256) pack_fold4_kernel(FoldJobs jobs, int A, i
 // [16][128-row] tile is the K-major B operand of the fused dgrad kernel (avd_dgrad3.cu):
 //   G1[f][c] = sum_n dz1[n][f] x_ext[n][c]  =>  dW1[k][f] = G1[f][k] + G1[f][8+k],  dWa[f] = G1[l1+f][4] + G1[l1+f][12],  db[f] = G1[f][5]
 // and column 5 (the constant one) also yields db2 = sum_n dz2[n][:].
-__global__ void __launch_bounds__(256) xext_kernel(const float* __restrict__ s, const float* __restrict__ a, int ns, int64_t N,
+__global__ void __launch_bounds__(256) xext_kernel(const float* __restrict__ s, int64_t s_rs, const float* __restrict__ a, int ns, int64_t N,
                                                    bf16* __restrict__ xextT, int64_t R, int64_t Rp, int f16) {
     const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N) return;
     float v[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-    for (int k = 0; k < ns && k < 4; ++k) v[k] = s[n * ns + k];
+    for (int k = 0; k < ns && k < 4; ++k) v[k] = s[n * s_rs + k];
     v[4] = a[n];
     bf16 hi[8], lo[8];
 #pragma unroll
@@ -859,6 +863,70 @@ __global__ void __launch_bounds__(256) xext_kernel(const float* __restrict__ s, 
     for (int k = 0; k < 8; ++k) {
         col[(int64_t)k * Rp] = hi[k];
         col[(int64_t)(8 + k) * Rp] = lo[k];
+    }
+}
+
+// V table of the critic-action pass (avd_fused3.cu, MODE_CRITIC_ACTION): the action reaches the critic through one scalar, so
+// d q / d a = sum_j [z2_j + b2'_j > 0] V[k(a)][j] with V[k][j] = sum_{f active in interval k} wa_f W2'[l1 + f][j] w3'_j, k(a) = number of
+// breakpoints -ba_f / wa_f below a.  Grid (agents, 4 column slabs of 32); 256 threads = 32 columns x 8 row groups.  Every CTA sorts
+// the breakpoints (rank sort, la <= 64), stages its [la][32] slab of wa_f W2' w3' in shared memory with coalesced loads, and fills
+// its rows -- the active set of interval k is evaluated with the forward pass's own test fma(a, wa_f, ba_f) > 0 at a point inside
+// the interval.  Output per agent: [rows][stride] fp32 (pad columns zero) followed by 64 sorted breakpoints (+inf padded).
+__global__ void __launch_bounds__(256) critic_vtab_kernel(const float* __restrict__ params, int64_t pstride, CriticOff o, avd_net_dims d,
+                                                          float* __restrict__ vtab, int rows, int stride, int total) {
+    pdl_wait();
+    pdl_launch_dependents();
+    const int agent = blockIdx.x, slab = blockIdx.y, tid = threadIdx.x;
+    const float* P = params + (int64_t)agent * pstride;
+    float* out = vtab + (int64_t)agent * total;
+    __shared__ float wa[64], ba[64], brk[64], sorted[64], col[64][33];
+    const int la = d.la;
+    const float inf = __int_as_float(0x7f800000);
+    if (tid < 64) {
+        const float w = tid < la ? P[o.Wa + tid] : 0.0f, b = tid < la ? P[o.ba + tid] : 0.0f;
+        wa[tid] = w;
+        ba[tid] = b;
+        brk[tid] = (tid < la && w != 0.0f) ? -b / w : inf;
+        sorted[tid] = inf;
+    }
+    for (int i = tid; i < 64 * 32; i += blockDim.x) {        // col[f][c] = wa_f sc_a,f W2[l1 + f][j] w3'_j,  j = 32 slab + c
+        const int f = i >> 5, c = i & 31, jj = slab * 32 + c;
+        float v = 0.0f;
+        if (f < la && jj < d.l2) {
+            const float sca = P[o.ga + f] / sqrtf(P[o.vara + f] + kBnEps);
+            const float w3p = P[o.W3 + jj] * P[o.g2 + jj] / sqrtf(P[o.var2 + jj] + kBnEps);
+            v = P[o.Wa + f] * sca * P[o.W2 + (int64_t)(d.l1 + f) * d.l2 + jj] * w3p;
+        }
+        col[f][c] = v;
+    }
+    __syncthreads();
+    if (tid < la) {       // rank sort (ties broken by index)
+        const float t = brk[tid];
+        int rank = 0;
+        for (int g2 = 0; g2 < la; ++g2) rank += (brk[g2] < t || (brk[g2] == t && g2 < tid)) ? 1 : 0;
+        sorted[rank] = t;
+    }
+    __syncthreads();
+    int m = 0;          // finite breakpoints
+    for (int i = 0; i < la; ++i) m += sorted[i] < inf ? 1 : 0;
+    if (slab == 0) {
+        if (tid < 64) out[rows * stride + tid] = sorted[tid];
+        for (int i = rows * stride + 64 + tid; i < total; i += blockDim.x) out[i] = 0.0f;
+        for (int i = tid; i < rows * (stride - d.l2); i += blockDim.x) out[(i / (stride - d.l2)) * stride + d.l2 + i % (stride - d.l2)] = 0.0f;
+    }
+    const int c = tid & 31, jj = slab * 32 + c;
+    if (jj >= d.l2) return;
+    for (int k = tid >> 5; k < rows; k += 8) {
+        const int kk = min(k, m);                                   // intervals beyond the last finite breakpoint repeat it (never selected)
+        float a;
+        if (m == 0) a = 0.0f;
+        else if (kk == 0) a = sorted[0] - fmaxf(1.0f, fabsf(sorted[0]));
+        else if (kk == m) a = sorted[m - 1] + fmaxf(1.0f, fabsf(sorted[m - 1]));
+        else a = 0.5f * (sorted[kk - 1] + sorted[kk]);
+        float acc = 0.0f;
+        for (int f = 0; f < la; ++f)
+            if (fmaf(a, wa[f], ba[f]) > 0.0f) acc += col[f][c];
+        out[k * stride + jj] = acc;
     }
 }
 
@@ -1034,7 +1102,7 @@ __global__ void __launch_bounds__(32 * kUnfoldWarps) unfold_kernel(const float* 
 struct Workspace {
     float *H, *H1a, *Z, *Za, *DZ, *DH, *a2, *y, *q, *dpi;
     bf16 *cW2b, *cW2T, *tcW2T, *aW2b, *aW2T, *taW2T;   // packed weights (precision 1: bf16; precision 2: fp16)
-    bf16* cTW2T;               // precision 2: T pack of the critic for the critic-action pass
+    float* vtab;               // [A][fused3::vtab_floats()] V table + breakpoints of the critic-action pass
     float* wscale;             // precision 2: [2][A] 1 / s of the critic [0] and actor [1] W2'' / T packs
     uint32_t* mask2;           // [N][4] sign bits of the actor's z2 + b2' (MODE_ACTOR_SAVE -> actor_dm_kernel)
     float* dact;               // [N] d(action)/d(pre-activation) of the actor
@@ -1049,7 +1117,7 @@ struct Workspace {
     static int64_t bytes(const avd_net_dims& d, int64_t A, int64_t N) {
         const int64_t F = d.l1 + d.la;
         const int64_t acts = N * (2 * F + d.l1 + 3 * (int64_t)d.l2) * (int64_t)sizeof(float);
-        const int64_t packed = A * (4 * F + 3 * (int64_t)d.l1) * d.l2 * (int64_t)sizeof(bf16) + (2 * A + 4) * (int64_t)sizeof(float);
+        const int64_t packed = A * (3 * F + 3 * (int64_t)d.l1) * d.l2 * (int64_t)sizeof(bf16) + (2 * A + 4 + A * (int64_t)fused3::vtab_floats()) * (int64_t)sizeof(float);
         const int64_t vecs = (5 + 4) * ((N + 3) / 4 * 4) * (int64_t)sizeof(float);
         const int64_t slices = std::max<int64_t>(A, sm_count());
         const int64_t fold = N * (kMaskWords * 4 + 16 * 2) + A * (8 * (int64_t)d.l2 + 16) * (int64_t)sizeof(float) + A * 16 * 64 * 2 +
@@ -1072,9 +1140,9 @@ struct Workspace {
         aW2b = b; b += A * (int64_t)d.l1 * d.l2;
         aW2T = b; b += A * (int64_t)d.l1 * d.l2;
         taW2T = b; b += A * (int64_t)d.l1 * d.l2;
-        cTW2T = b; b += A * F * d.l2;
         p = reinterpret_cast<float*>(((uintptr_t)b + 15) & ~(uintptr_t)15);
         wscale = p; p += (2 * A + 3) / 4 * 4;
+        vtab = p; p += A * (int64_t)fused3::vtab_floats();
         const int64_t Np = (N + 3) / 4 * 4;
         a2 = p; p += Np;
         y = p; p += Np;
@@ -1197,10 +1265,10 @@ struct Pass {
         return AVD_OK;
     }
 
-    // all four networks of a learn step (+ the T pack of the critic with fp16 operands) in one launch; the b2f buffers must have
-    // been zeroed.  wscale[i] (fp16 only, nullable): [A] 1 / s of job i's W2b / T pack.
+    // all four networks of a learn step in one launch; the b2f buffers must have been zeroed.
+    // wscale[i] (fp16 only, nullable): [A] 1 / s of job i's W2b pack.
     int pack_fold4(int njobs, const float* const params[], const bool critic[], bf16* const W2b[], bf16* const W2T[], float* const b2f[],
-                   const bool tpack[], float* const wscale[]) const {
+                   float* const wscale[]) const {
         FoldJobs jobs = {};
         int Fmax = 0;
         for (int i = 0; i < njobs; ++i) {
@@ -1211,7 +1279,7 @@ struct Pass {
             if (critic[i]) { const CriticOff c = critic_off(d); jb.g2 = c.g2; jb.var2 = c.var2; jb.W3 = c.W3; }
             else { const ActorOff a = actor_off(d); jb.g2 = a.g2; jb.var2 = a.var2; jb.W3 = a.W3; }
             jb.F = critic[i] ? d.l1 + d.la : d.l1;
-            jb.W2b = W2b[i]; jb.W2T = W2T[i]; jb.b2f = b2f[i]; jb.tpack = tpack[i] ? 1 : 0; jb.wscale = wscale[i];
+            jb.W2b = W2b[i]; jb.W2T = W2T[i]; jb.b2f = b2f[i]; jb.wscale = wscale[i];
             Fmax = std::max(Fmax, jb.F);
         }
         pack_fold4_kernel<<<dim3((unsigned)((d.l2 + 31) / 32), (unsigned)((Fmax + 7) / 8), (unsigned)(njobs * A)), 256, 0, st>>>(jobs, A, d.l2, f16() ? 1 : 0);
@@ -1573,39 +1641,42 @@ static int learn_fused3(const avd_learn_io* io, const Pass& p, const Workspace& 
     // c_b2f .. ta_b2f, U and sdq are adjacent in the workspace: one memset zeroes every accumulator of the step
     AVD_CUDA_OK(cudaMemsetAsync(w.c_b2f, 0, (size_t)((char*)(w.sdq + 2 * A) - (char*)w.c_b2f), st));
     const bool f16 = p.f16();
+    const int64_t srs = io->s_stride ? io->s_stride : d.ns;      // row pitch of the state batches
     float* const ws_c = w.wscale;
     float* const ws_a = w.wscale + A;
     {
-        const float* const prm[5] = {io->t_actor, io->t_critic, io->critic, io->actor, io->critic};
-        const bool crit[5] = {false, true, true, false, true};
-        bf16* const W2b[5] = {nullptr, nullptr, w.cW2b, w.aW2b, nullptr};
-        bf16* const W2T[5] = {w.taW2T, w.tcW2T, w.cW2T, w.aW2T, w.cTW2T};
-        float* const b2f[5] = {w.ta_b2f, w.tc_b2f, w.c_b2f, w.a_b2f, nullptr};
-        const bool tpack[5] = {false, false, false, false, true};
-        float* const wsc[5] = {nullptr, nullptr, ws_c, ws_a, nullptr};
-        AVD_TRY(p.pack_fold4(f16 ? 5 : 4, prm, crit, W2b, W2T, b2f, tpack, wsc));
+        const float* const prm[4] = {io->t_actor, io->t_critic, io->critic, io->actor};
+        const bool crit[4] = {false, true, true, false};
+        bf16* const W2b[4] = {nullptr, nullptr, w.cW2b, w.aW2b};
+        bf16* const W2T[4] = {w.taW2T, w.tcW2T, w.cW2T, w.aW2T};
+        float* const b2f[4] = {w.ta_b2f, w.tc_b2f, w.c_b2f, w.a_b2f};
+        float* const wsc[4] = {nullptr, nullptr, ws_c, ws_a};
+        AVD_TRY(p.pack_fold4(4, prm, crit, W2b, W2T, b2f, wsc));
+        AVD_CUDA_OK(launch_pdl(critic_vtab_kernel, dim3((unsigned)A, (unsigned)((d.l2 + 31) / 32)), dim3(256), 0, st, (const float*)io->critic, co.total, co, d, w.vtab,
+                               fused3::vtab_rows(), fused3::vtab_stride(), fused3::vtab_floats()));
+        AVD_LAUNCH_OK();
     }
     const int64_t Rp = (R + 63) / 64 * 64;
-    xext_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(io->s, io->a, d.ns, N, w.xextT, R, Rp, f16 ? 1 : 0);
+    xext_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(io->s, srs, io->a, d.ns, N, w.xextT, R, Rp, f16 ? 1 : 0);
     // fp16 backward tiles: dq ~ (q - y) / R (critic) and ~ dq/da / R (actor) are lifted by powers of two into the normal range of
     // fp16 (they saturate at +-65504 * 2^-k instead of overflowing); the unfold kernel divides the factors out again
     const float dm_c = f16 ? exp2f(ceilf(log2f((float)R))) : 1.0f, dm_a = f16 ? 256.0f * dm_c : 1.0f;
     AVD_LAUNCH_OK();
     tm.mark("fold+xext");
     // ---- TD target: y = r + gamma * target_critic(s', target_actor(s'))            trainer.py:493-494
-    AVD_TRY(fused3::run(fused3::MODE_ACTOR_OUT, f16, d, A, R, io->t_actor, ao.total, w.taW2T, w.ta_b2f, nullptr, io->s2, d.ns, 1, nullptr, nullptr, 0.f,
+    AVD_TRY(fused3::run(fused3::MODE_ACTOR_OUT, f16, d, A, R, io->t_actor, ao.total, w.taW2T, w.ta_b2f, nullptr, io->s2, srs, 1, nullptr, nullptr, 0.f,
                         io->action_high, nullptr, nullptr, w.a2, nullptr, nullptr, 1.0f, nullptr, nullptr, st));
     tm.mark("t_actor");
-    AVD_TRY(fused3::run(fused3::MODE_TARGET, f16, d, A, R, io->t_critic, co.total, w.tcW2T, w.tc_b2f, nullptr, io->s2, d.ns, 1, w.a2, io->r, io->gamma, 0.f,
+    AVD_TRY(fused3::run(fused3::MODE_TARGET, f16, d, A, R, io->t_critic, co.total, w.tcW2T, w.tc_b2f, nullptr, io->s2, srs, 1, w.a2, io->r, io->gamma, 0.f,
                         nullptr, nullptr, w.y, nullptr, nullptr, 1.0f, nullptr, nullptr, st));
     tm.mark("t_critic");
     // ---- critic loss gradient on (s, a)                                             trainer.py:495-498
-    AVD_TRY(fused3::run(fused3::MODE_CRITIC_BWD, f16, d, A, R, io->critic, co.total, w.cW2T, w.c_b2f, nullptr, io->s, d.ns, 1, io->a, nullptr, 0.f, 0.f,
+    AVD_TRY(fused3::run(fused3::MODE_CRITIC_BWD, f16, d, A, R, io->critic, co.total, w.cW2T, w.c_b2f, nullptr, io->s, srs, 1, io->a, nullptr, 0.f, 0.f,
                         w.y, nullptr, w.q, w.mask, DZ, dm_c, w.sdq, io->loss, st));
     tm.mark("critic_bwd");
     const int ncta = wgrad3::ctas_per_agent(A, R);
     const int64_t g2_cta = (int64_t)Workspace::kG2Rows * d.l2, g2_agent = (int64_t)ncta * g2_cta;
-    AVD_TRY(wgrad3::run(f16, d, true, A, R, io->critic, co.total, io->s, io->a, DZ, w.G2part, g2_agent, g2_cta, st));
+    AVD_TRY(wgrad3::run(f16, d, true, A, R, io->critic, co.total, io->s, srs, io->a, DZ, w.G2part, g2_agent, g2_cta, st));
     tm.mark("critic_wgrad");
     AVD_TRY(p.dgrad3_unfold(true, io->critic, DZ, w.cW2b, F, Fp, w.mask, MW, w.xextT, w.G1, w.G2part, io->critic_grad, w.dbm, w.c_b2f, Uc,
                             w.sdq, w.ticket, ws_c, dm_c));
@@ -1613,14 +1684,14 @@ static int learn_fused3(const avd_learn_io* io, const Pass& p, const Workspace& 
     // ---- actor loss gradient: -mean(critic(s, actor(s)))                            trainer.py:501-506
     static const bool legacy_actor_bwd = getenv("AVD_ACTOR_BWD_PASS") != nullptr;     // diagnostic: the round-1 second forward pass
     AVD_TRY(fused3::run(legacy_actor_bwd ? fused3::MODE_ACTOR_OUT : fused3::MODE_ACTOR_SAVE, f16, d, A, R, io->actor, ao.total, w.aW2T, w.a_b2f, nullptr,
-                        io->s, d.ns, 1, nullptr, nullptr, 0.f, io->action_high, nullptr, nullptr, w.a2, legacy_actor_bwd ? nullptr : w.mask, nullptr, 1.0f,
+                        io->s, srs, 1, nullptr, nullptr, 0.f, io->action_high, nullptr, nullptr, w.a2, legacy_actor_bwd ? nullptr : w.mask, nullptr, 1.0f,
                         nullptr, nullptr, st, w.mask2, w.dact));   // pi (+ the sign masks and d(action)/d(pre-activation) for the backward)
     tm.mark("actor_fwd");
-    AVD_TRY(fused3::run(fused3::MODE_CRITIC_ACTION, f16, d, A, R, io->critic, co.total, f16 ? w.cTW2T : w.cW2T, w.c_b2f, ws_c, io->s, d.ns, 1, w.a2,
+    AVD_TRY(fused3::run(fused3::MODE_CRITIC_ACTION, f16, d, A, R, io->critic, co.total, w.cW2T, w.c_b2f, w.vtab, io->s, srs, 1, w.a2,
                         nullptr, 0.f, 0.f, nullptr, nullptr, w.dpi, nullptr, nullptr, 1.0f, nullptr, io->loss, st));          // d(-mean q)/d pi
     tm.mark("critic_action");
     if (legacy_actor_bwd) {
-        AVD_TRY(fused3::run(fused3::MODE_ACTOR_BWD, f16, d, A, R, io->actor, ao.total, w.aW2T, w.a_b2f, nullptr, io->s, d.ns, 1, nullptr, nullptr, 0.f,
+        AVD_TRY(fused3::run(fused3::MODE_ACTOR_BWD, f16, d, A, R, io->actor, ao.total, w.aW2T, w.a_b2f, nullptr, io->s, srs, 1, nullptr, nullptr, 0.f,
                             io->action_high, nullptr, w.dpi, nullptr, w.mask, DZ, dm_a, w.sdq + A, nullptr, st));
     } else {
         const dim3 grid((unsigned)std::min<int64_t>((R + 15) / 16, std::max(1, 8 * sm_count() / A)), (unsigned)A);
@@ -1629,7 +1700,7 @@ static int learn_fused3(const avd_learn_io* io, const Pass& p, const Workspace& 
         AVD_LAUNCH_OK();
     }
     tm.mark("actor_bwd");
-    AVD_TRY(wgrad3::run(f16, d, false, A, R, io->actor, ao.total, io->s, nullptr, DZ, w.G2part, g2_agent, g2_cta, st));
+    AVD_TRY(wgrad3::run(f16, d, false, A, R, io->actor, ao.total, io->s, srs, nullptr, DZ, w.G2part, g2_agent, g2_cta, st));
     tm.mark("actor_wgrad");
     AVD_TRY(p.dgrad3_unfold(false, io->actor, DZ, w.aW2b, d.l1, Fp, w.mask, 8, w.xextT, w.G1, w.G2part, io->actor_grad, w.dbm + (int64_t)A * d.l2,
                             w.a_b2f, Ua, w.sdq + A, w.ticket + A, ws_a, dm_a));
@@ -1661,6 +1732,8 @@ extern "C" int avd_ddpg_learn(const avd_learn_io* io, void* stream) {
     Workspace w;
     w.carve(io->workspace, d, A, N);
     const dim3 gl1b((unsigned)((R + kL1BwdRows - 1) / kL1BwdRows), A);
+    const int64_t srs = io->s_stride ? io->s_stride : d.ns;      // row pitch of the state batches
+    AVD_REQUIRE(srs >= d.ns, "s_stride %d is smaller than the state width %d", (int)io->s_stride, d.ns);
 
     AVD_CUDA_OK(cudaMemsetAsync(io->actor_grad, 0, (size_t)A * ao.n_train * sizeof(float), st));
     AVD_CUDA_OK(cudaMemsetAsync(io->critic_grad, 0, (size_t)A * co.n_train * sizeof(float), st));
@@ -1674,14 +1747,14 @@ extern "C" int avd_ddpg_learn(const avd_learn_io* io, void* stream) {
         AVD_TRY(p.pack(io->actor, ao.total, ao.W2, d.l1, w.aW2b, w.aW2T));
     }
     // ---- TD target: y = r + gamma * target_critic(s', target_actor(s'))            trainer.py:493-494
-    AVD_TRY(p.layer1(false, io->t_actor, io->s2, d.ns, 1, nullptr, w.H1a));
+    AVD_TRY(p.layer1(false, io->t_actor, io->s2, srs, 1, nullptr, w.H1a));
     AVD_TRY(p.forward(w.H1a, d.l1, io->t_actor, ao.total, ao.W2, w.taW2T, w.Z));
     {
         HeadArgs h = actor_head(d, io->t_actor, w.Z, R, io->action_high);
         h.out = w.a2;
         AVD_TRY(launch_head<HEAD_ACTOR_FWD>(h, d.l2, A, st));
     }
-    AVD_TRY(p.layer1(true, io->t_critic, io->s2, d.ns, 1, w.a2, w.H));
+    AVD_TRY(p.layer1(true, io->t_critic, io->s2, srs, 1, w.a2, w.H));
     AVD_TRY(p.forward(w.H, F, io->t_critic, co.total, co.W2, w.tcW2T, w.Z));
     {
         HeadArgs h = critic_head(d, io->t_critic, w.Z, R);
@@ -1689,7 +1762,7 @@ extern "C" int avd_ddpg_learn(const avd_learn_io* io, void* stream) {
         AVD_TRY(launch_head<HEAD_CRITIC_TARGET>(h, d.l2, A, st));
     }
     // ---- critic loss gradient on (s, a)                                             trainer.py:495-498
-    AVD_TRY(p.layer1(true, io->critic, io->s, d.ns, 1, io->a, w.H));
+    AVD_TRY(p.layer1(true, io->critic, io->s, srs, 1, io->a, w.H));
     AVD_TRY(p.forward(w.H, F, io->critic, co.total, co.W2, w.cW2T, w.Z));
     {
         HeadArgs h = critic_head(d, io->critic, w.Z, R);
@@ -1698,17 +1771,17 @@ extern "C" int avd_ddpg_learn(const avd_learn_io* io, void* stream) {
     }
     AVD_TRY(p.wgrad(w.H, F, w.DZ, io->critic_grad, co.n_train, co.W2));
     AVD_TRY(p.dgrad(w.DZ, io->critic, co.total, co.W2, w.cW2b, F, 0, F, w.DH));
-    l1_backward_kernel<true><<<gl1b, 128, 0, st>>>(d, io->critic, co.total, io->s, io->a, R, w.DH, io->critic_grad, co.n_train);
+    l1_backward_kernel<true><<<gl1b, 128, 0, st>>>(d, io->critic, co.total, io->s, srs, io->a, R, w.DH, io->critic_grad, co.n_train);
     AVD_LAUNCH_OK();
     // ---- actor loss gradient: -mean(critic(s, actor(s)))                            trainer.py:501-506
-    AVD_TRY(p.layer1(false, io->actor, io->s, d.ns, 1, nullptr, w.H1a));
+    AVD_TRY(p.layer1(false, io->actor, io->s, srs, 1, nullptr, w.H1a));
     AVD_TRY(p.forward(w.H1a, d.l1, io->actor, ao.total, ao.W2, w.aW2T, w.Za));
     {
         HeadArgs h = actor_head(d, io->actor, w.Za, R, io->action_high);
         h.out = w.a2;   // pi
         AVD_TRY(launch_head<HEAD_ACTOR_FWD>(h, d.l2, A, st));
     }
-    AVD_TRY(p.layer1(true, io->critic, io->s, d.ns, 1, w.a2, w.H));
+    AVD_TRY(p.layer1(true, io->critic, io->s, srs, 1, w.a2, w.H));
     AVD_TRY(p.forward(w.H, F, io->critic, co.total, co.W2, w.cW2T, w.Z));
     {
         HeadArgs h = critic_head(d, io->critic, w.Z, R);
@@ -1725,7 +1798,7 @@ extern "C" int avd_ddpg_learn(const avd_learn_io* io, void* stream) {
     }
     AVD_TRY(p.wgrad(w.H1a, d.l1, w.DZ, io->actor_grad, ao.n_train, ao.W2));
     AVD_TRY(p.dgrad(w.DZ, io->actor, ao.total, ao.W2, w.aW2b, d.l1, 0, d.l1, w.DH));
-    l1_backward_kernel<false><<<gl1b, 128, 0, st>>>(d, io->actor, ao.total, io->s, nullptr, R, w.DH, io->actor_grad, ao.n_train);
+    l1_backward_kernel<false><<<gl1b, 128, 0, st>>>(d, io->actor, ao.total, io->s, srs, nullptr, R, w.DH, io->actor_grad, ao.n_train);
     AVD_LAUNCH_OK();
     return apply_local_updates(io, stream);
 }

@@ -10,8 +10,8 @@
 //        U[j] = sum_n dq_n relu(z2)[n][j] for the head / BN2 weight gradients),  per-thread partial sums of  sum dq  and the loss
 //   --TMA store-->  the dm tile to HBM for the weight-gradient kernel (avd_wgrad3.cu, which recomputes r1 from the inputs)
 //        and the dgrad kernel (avd_dgrad3.cu)
-//   MODE_CRITIC_ACTION additionally runs the action columns of the dgrad as a third MMA (dz2 . W2'[action rows]^T) and
-//   reduces it to d(-mean q)/d(action) per row -- the critic -> actor link (trainer.py:503-506) never leaves the SM.
+//   MODE_CRITIC_ACTION reduces d(-mean q)/d(action) per row in the head pass itself -- the critic -> actor link
+//   (trainer.py:503-506) never leaves the SM and needs no backward product at all (the V table below).
 //
 // BatchNorm folding (inference affine):  W2' = diag(sc1) W2,  b2' = b2 + sh1 W2  (pack_fold_kernel);
 // w3' = sc2 * w3,  b3' = b3 + sh2 . w3  (table set-up below).  One CTA works on ONE agent: weights and
@@ -50,6 +50,10 @@ constexpr int TAB_BYTES = 2048;
 constexpr int OFF_PART = OFF_TAB + TAB_BYTES;                // [2 buffers][4 quarters][128 rows] partial row sums
 constexpr int OFF_BAR = OFF_PART + 2 * 4 * TILE_M * 4;
 constexpr int SMEM_BYTES = OFF_BAR + 512 + 1024;
+// V table of MODE_CRITIC_ACTION (in the dz2-tile slots): (la + 1) rows of 128 fp32, row pitch 132 floats so that the rows the 8 lanes
+// of a quarter warp gather (one row per lane: its own action interval) spread over all bank groups; sorted breakpoints behind it
+constexpr int kVRows = 49, kVStride = 132, kVBrk = 64;
+static_assert((kVRows * kVStride + kVBrk) * 4 + 2 * 4 * TILE_M * 4 <= 2 * SLOT_BYTES, "V table + partial sums exceed the dz2-tile slots");
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB shared memory of an sm_100 CTA");
 
 // MODE_ACTOR_SAVE: the actor forward pass that ALSO keeps what its backward needs -- sign bits of z1 (40 B per row) and of
@@ -76,7 +80,7 @@ struct Args {
     int mask_words;
     uint32_t* mask2_out;        // MODE_ACTOR_SAVE: [A*R][4] sign bits of z2 + b2'
     float* dact_out;            // MODE_ACTOR_SAVE: [A*R] high (1 - tanh^2(pre-activation))
-    const float* wscale;        // MODE_CRITIC_ACTION with fp16 operands: [A] 1 / s of the T = W2' diag(w3') s pack (pack_fold4_kernel)
+    const float* vtab;          // MODE_CRITIC_ACTION: [A][kVRows][128] V table, [A][kVBrk] sorted breakpoints behind it (critic_vtab_kernel)
     float dm_scale;             // backward modes: power-of-two factor on the dm tile (1 for bf16; fp16 needs dq ~ 1 / R lifted into its range)
     float* sdq;                 // backward modes: [A]       += sum_n dq_n
     float* loss;                // nullable; element 2*agent (+1 for the actor loss)
@@ -106,24 +110,27 @@ __device__ __forceinline__ uint32_t pack2(bf16 a, bf16 b) {
 // F16 (precision = 2): the layer-2 operands r1 and W2'^T and the backward tile dm are fp16 instead of bf16 (same tensor-pipe
 // rate, 11-bit significand; B200 has no mixed fp16 x bf16 MMA).  dm = dq [z2 > 0] is written as dm_scale * dq with a power-of-two
 // dm_scale ~ R (dq ~ 1 / R would sit in the subnormal range of fp16), saturating; the unfold kernel divides it out.
-// MODE_CRITIC_ACTION then runs on
-// T = W2' diag(w3') s  (s = power of two, pack_fold4_kernel) in place of W2':  the accumulator holds s w3'_j z2_j, so
-//   u_j = sg_j (acc_j + s w3'_j b2'_j) = s |w3'_j| (z2_j + b2'_j)     has the sign of z2_j + b2'_j,      sg_j = sign(w3'_j)
-//   q   = sum_j max(u_j, 0) sg_j / s + b3'
-// and the action-column dgrad multiplies the EXACT 0/1 tile [z2 + b2' > 0] with the resident T block (one fp16 rounding per
-// weight, instead of bf16(dq w3') x bf16(W2')):   d(-mean q)/d a = -(1 / (R s)) sum_f [za_f > 0] wa_f sum_j [z2_j + b2'_j > 0] T[f][j].
+//
+// MODE_CRITIC_ACTION -- d q / d action without a backward product.  The action enters the critic through ONE scalar:
+//   za_f = wa_f a + ba_f,   d q / d a = sum_f [za_f > 0] wa_f sum_j [z2_j + b2'_j > 0] W2'[l1 + f][j] w3'_j          (model.py:69-83)
+// As a function of a the sign pattern [za_f > 0] is piecewise constant with at most la breakpoints -ba_f / wa_f, so
+//   d q / d a = sum_j [z2_j + b2'_j > 0] V[k(a)][j],     V[k][j] = sum_{f active in interval k} wa_f W2'[l1 + f][j] w3'_j,
+// with k(a) = number of breakpoints below a.  critic_vtab_kernel (avd_ddpg.cu) builds the (la + 1) x 128 fp32 table and the sorted
+// breakpoints per agent; the table sits in the shared memory the other backward modes use for the dz2 tile, and the head pass adds
+// V[k][j] over its columns with z2_j + b2'_j > 0.  Round 1 ran the action columns of the dgrad as a third MMA on a bf16 tile
+// dq w3' [z2 > 0] (a 32 KB tile written by all consumer warps per row tile, 8 MMAs, a TMEM read-back and a fourth pipeline stage:
+// 160 us, and a 0.5 % bias on every actor gradient from the two bf16 roundings); this is exact in fp32.
 template <int MODE, bool F16>
 __global__ void __launch_bounds__(NUM_THREADS, 1) fused3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmDZ, Args g) {
     constexpr bool CRITIC = MODE != MODE_ACTOR_OUT && MODE != MODE_ACTOR_BWD && MODE != MODE_ACTOR_SAVE;
     constexpr bool SAVE = MODE == MODE_ACTOR_SAVE;                               // forward pass that keeps its sign masks
     constexpr bool BWD = MODE == MODE_CRITIC_BWD || MODE == MODE_ACTOR_BWD;      // full backward: masks, r1 / dz2 to HBM, U
-    constexpr bool ACTION = MODE == MODE_CRITIC_ACTION;                          // backward to the action input only
-    constexpr bool HAS_DZ = BWD || ACTION;
+    constexpr bool ACTION = MODE == MODE_CRITIC_ACTION;                          // forward + d q / d action (V table)
+    constexpr bool HAS_DZ = BWD;
     constexpr int NKB = CRITIC ? 5 : 4;
     // k-block kb of local tile t lives in ring slot (t NKB + kb) % NSLOT: with more slots than k-blocks the converters of the
     // next tile start while the layer-2 MMA of this tile still reads its operands
-    constexpr int NSLOT = HAS_DZ ? 5 : MAX_SLOT;
-    constexpr bool TFORM = ACTION && F16;                                        // T formulation of the critic-action pass
+    constexpr int NSLOT = (HAS_DZ || ACTION) ? 5 : MAX_SLOT;                     // the last two slots: dz2 tile (BWD) / V table (ACTION)
     constexpr uint32_t FOP = F16 ? FMT_F16 : FMT_BF16;                           // format of the layer-2 operands
 
     extern __shared__ uint8_t smem_raw[];
@@ -215,17 +222,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused3_kernel(const __grid_con
     // kernel consumes what earlier launches of this step produced (folded weights and bias, actions, TD targets, dz2 ...).
     pdl_wait();
     pdl_launch_dependents();
-    const float inv_s = TFORM ? g.wscale[agent] : 1.0f;      // power of two
-    if (threadIdx.x >= 32 && threadIdx.x < 32 + L2N) {       // written by the pack kernel, possibly the previous launch
-        const int j = threadIdx.x - 32;
-        const float b2 = g.b2f[(int64_t)agent * L2N + j];
-        if (TFORM) {
-            const float w3p = w3f_tab[j];
-            b2f_tab[j] = fabsf(w3p) * (1.0f / inv_s) * b2;                      // sg_j s w3'_j b2'_j
-            w3f_tab[j] = w3p > 0.0f ? 1.0f : (w3p < 0.0f ? -1.0f : 0.0f);       // sg_j
-        } else {
-            b2f_tab[j] = b2;
-        }
+    if (threadIdx.x >= 32 && threadIdx.x < 32 + L2N) b2f_tab[threadIdx.x - 32] = g.b2f[(int64_t)agent * L2N + threadIdx.x - 32];   // written by the pack kernel, possibly the previous launch
+    float* vtab_s = reinterpret_cast<float*>(smem + OFF_DZ);                 // ACTION: [kVRows][kVStride] V table
+    float* vbrk_s = vtab_s + kVRows * kVStride;                              //         [kVBrk] sorted breakpoints (+inf padded)
+    float* part2 = vbrk_s + kVBrk;                                           //         [2 buffers][4 quarters][128 rows] partial d q / d a
+    if (ACTION) {
+        const float4* src = reinterpret_cast<const float4*>(g.vtab + (int64_t)agent * (kVRows * kVStride + kVBrk));
+        for (int i = threadIdx.x; i < (kVRows * kVStride + kVBrk) / 4; i += NUM_THREADS) reinterpret_cast<float4*>(vtab_s)[i] = src[i];
     }
     __syncthreads();
     const float b3f = scal[5] + scal[1] + scal[2] + scal[3] + scal[4];       // b3' = b3 + sh2 . w3
@@ -244,11 +247,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused3_kernel(const __grid_con
             const uint32_t leader = elect_one();
             constexpr uint32_t idesc1 = make_idesc_bf16(TILE_M, L2N, false, false);      // layer 1: hi/lo-split bf16
             constexpr uint32_t idesc = make_idesc_f16kind(TILE_M, L2N, false, false, FOP, FOP);
-            constexpr uint32_t idesc_act = make_idesc_f16kind(TILE_M, 64, false, true, FOP, FOP);      // dz2 (K-major) x W2'^T block (MN-major)
             const int F = L1N + la;
             const uint64_t dW = make_smem_desc(smem_u32(smem + OFF_W), 16, 1024);
             const uint64_t dR = make_smem_desc(smem_u32(smem + OFF_RING), 16, 1024);
-            const uint64_t dDZ = make_smem_desc(smem_u32(smem + OFF_DZ), 16, 1024);
             const uint64_t dX = make_desc_noswz(smem_u32(smem + OFF_X), TILE_M * 16, 128);
             const uint64_t dB1 = make_desc_noswz(smem_u32(smem + OFF_B1), L1N * 16, 128);
             mbar_expect_tx_p(leader, w_full, (uint32_t)NKB * SLOT_BYTES);
@@ -281,45 +282,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused3_kernel(const __grid_con
                 }
                 mma_commit_p(leader, &acc_full[t & 1]);
             };
-            auto dz_out = [&](int t) {        // dz2 tile of local tile t: to HBM (BWD) or through the action-column dgrad MMA (ACTION)
+            auto dz_out = [&](int t) {        // dz2 tile of local tile t to HBM; the tile is free again once the TMA stores have read it
                 mbar_wait(dz_full, (uint32_t)t & 1);
                 tc_fence_after();
-                if (BWD) {                    // the tile is free again once the TMA stores have read it
-                    tma_store_3d_p(leader, &tmDZ, smem + OFF_DZ, 0, tile_of(t) * TILE_M, agent);
-                    tma_store_3d_p(leader, &tmDZ, smem + OFF_DZ + SLOT_BYTES, KB, tile_of(t) * TILE_M, agent);
-                    if (leader) {
-                        bulk_commit();
-                        bulk_wait_read0();
-                    }
-                    __syncwarp();
-                    mbar_arrive_p(leader, dz_empty);
-                } else {
-                    if (t + 2 < T) mbar_wait(z1_empty, (uint32_t)(t + 2) & 1);     // convert(t + 2) has drained the z1 columns
-                    tc_fence_after();
-#pragma unroll
-                    for (int ks = 0; ks < 8; ++ks)
-                        mma_bf16_p(leader, tmem_base + 256u, desc_add(dDZ, (ks >> 2) * SLOT_BYTES + (ks & 3) * 32), desc_add(dW, 4 * SLOT_BYTES + ks * 2048),
-                                   idesc_act, ks != 0);
-                    mma_commit_p(leader, dra_full);
-                    mma_commit_p(leader, dz_empty);
+                tma_store_3d_p(leader, &tmDZ, smem + OFF_DZ, 0, tile_of(t) * TILE_M, agent);
+                tma_store_3d_p(leader, &tmDZ, smem + OFF_DZ + SLOT_BYTES, KB, tile_of(t) * TILE_M, agent);
+                if (leader) {
+                    bulk_commit();
+                    bulk_wait_read0();
                 }
+                __syncwarp();
+                mbar_arrive_p(leader, dz_empty);
             };
 
             mbar_wait(w_full, 0);
-            if (ACTION) {
-                mma1(0);
-                mma2(0);
-                if (T > 1) mma1(1);
-                for (int i = 0; i < T; ++i) {
-                    if (i + 1 < T) mma2(i + 1);
-                    if (i >= 1) dz_out(i - 1);
-                    if (i + 2 < T) {
-                        if (i >= 1) mbar_wait(dra_empty, (uint32_t)(i - 1) & 1);
-                        mma1(i + 2);
-                    }
-                }
-                dz_out(T - 1);
-            } else {
+            {
                 // The tensor pipe executes in issue order: the (tiny) layer-1 MMA of the NEXT tile goes in front of the layer-2
                 // MMA, so that the converters of the next iteration never wait behind a whole layer-2 product.
                 mma1(0);
@@ -355,7 +332,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused3_kernel(const __grid_con
         // its use would put a full global-memory latency on the critical path of every tile.
         //   xs   : state row of the tile whose X buffer this thread's quarter writes at the end of its next convert()
         //   a_pf : action of the next tile whose action-branch columns this quarter converts
-        //   y_pf : reward / TD target / d loss/d action of the tile whose pass 2 comes next;  a_ag: action for action_grad()
+        //   y_pf : reward / TD target / d loss/d action of the tile whose pass 2 comes next;  a_ag: action of the next pass1() (ACTION)
         float xs[4] = {0.f, 0.f, 0.f, 0.f}, a_pf = 0.0f, y_pf = 0.0f, a_ag = 0.0f;
         auto xg_of = [&](int tc) { return CRITIC ? 2 * (1 - (tc & 1)) : (tc & 3); };      // quarter that stages tile tc + 2 during convert(tc)
         auto is_action_quarter = [&](int tc) { return CRITIC && (c4 >> 1) == (tc & 1); };   // quarters 2 (tc & 1), 2 (tc & 1) + 1
@@ -460,19 +437,37 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused3_kernel(const __grid_con
                 else if (MODE == MODE_CRITIC_BWD) y_pf = __ldg(g.y + n0);
                 else y_pf = __ldg(g.dpi + n0);
             }
+            const float* vrow = vtab_s;          // ACTION: this row's V[k(a)] (its 32 columns), k(a) = breakpoints below the action
+            if (ACTION) {
+                const float a_cur = a_ag;
+                if (tc + 1 < T) {
+                    bool v1;
+                    a_ag = __ldg(g.act + rowinfo(tc + 1, v1));
+                }
+                int k = 0;
+#pragma unroll
+                for (int st = 32; st >= 1; st >>= 1)
+                    if (vbrk_s[k + st - 1] < a_cur) k += st;
+                vrow = vtab_s + k * kVStride + c4 * 32;
+            }
             mbar_wait(&acc_full[buf], ((uint32_t)tc >> 1) & 1);
             tc_fence_after();
             float v[32];
             tmem_ld32(tmem_base + (uint32_t)(buf * L2N + c4 * 32) + tlane, v);
-            float acc = 0.0f;
+            float acc = 0.0f, gacc = 0.0f;
             uint32_t m = 0u;
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
                 const float4 b4 = *reinterpret_cast<const float4*>(b2f_tab + c4 * 32 + j);
                 const float4 w4 = *reinterpret_cast<const float4*>(w3f_tab + c4 * 32 + j);
-                // T formulation: w4 = sg, b4 = sg s w3' b2'  =>  t = s |w3'| (z2 + b2'), and max(t, 0) sg sums to s (q - b3')
-                const float t0 = TFORM ? fmaf(v[j], w4.x, b4.x) : v[j] + b4.x, t1 = TFORM ? fmaf(v[j + 1], w4.y, b4.y) : v[j + 1] + b4.y;
-                const float t2 = TFORM ? fmaf(v[j + 2], w4.z, b4.z) : v[j + 2] + b4.z, t3 = TFORM ? fmaf(v[j + 3], w4.w, b4.w) : v[j + 3] + b4.w;
+                const float t0 = v[j] + b4.x, t1 = v[j + 1] + b4.y, t2 = v[j + 2] + b4.z, t3 = v[j + 3] + b4.w;
+                if (ACTION) {        // + V[k][j] where z2_j + b2'_j > 0 (sign bit clear): AND with the inverted sign mask, no branch
+                    const float4 V4 = *reinterpret_cast<const float4*>(vrow + j);
+                    gacc += __uint_as_float(__float_as_uint(V4.x) & ~(uint32_t)((int32_t)__float_as_uint(t0) >> 31));
+                    gacc += __uint_as_float(__float_as_uint(V4.y) & ~(uint32_t)((int32_t)__float_as_uint(t1) >> 31));
+                    gacc += __uint_as_float(__float_as_uint(V4.z) & ~(uint32_t)((int32_t)__float_as_uint(t2) >> 31));
+                    gacc += __uint_as_float(__float_as_uint(V4.w) & ~(uint32_t)((int32_t)__float_as_uint(t3) >> 31));
+                }
                 acc = fmaf(fmaxf(t0, 0.0f), w4.x, acc);
                 acc = fmaf(fmaxf(t1, 0.0f), w4.y, acc);
                 acc = fmaf(fmaxf(t2, 0.0f), w4.z, acc);
@@ -491,6 +486,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused3_kernel(const __grid_con
                 if (v1) g.mask2_out[n1 * 4 + c4] = m;
             }
             part[(buf * 4 + c4) * TILE_M + row] = acc;
+            if (ACTION) part2[(buf * 4 + c4) * TILE_M + row] = gacc;
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
@@ -509,11 +505,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused3_kernel(const __grid_con
             bool valid;
             const int64_t nrow = rowinfo(tc, valid);
             const float yv = y_pf;
-            if (ACTION && c4 == (tc & 3)) a_ag = __ldg(g.act + nrow);   // consumed by action_grad(tc), two stages later
             mbar_wait(&part_full[buf], ((uint32_t)tc >> 1) & 1);
             const float* pb = part + buf * 4 * TILE_M + row;
-            const float qv = TFORM ? fmaf(pb[0] + pb[TILE_M] + pb[2 * TILE_M] + pb[3 * TILE_M], inv_s, b3f)
-                                   : pb[0] + pb[TILE_M] + pb[2 * TILE_M] + pb[3 * TILE_M] + b3f;
+            const float qv = pb[0] + pb[TILE_M] + pb[2 * TILE_M] + pb[3 * TILE_M] + b3f;
             if (!HAS_DZ) {
                 float o;
                 if (MODE == MODE_ACTOR_OUT || SAVE) {
@@ -522,13 +516,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused3_kernel(const __grid_con
                     if (SAVE && valid) g.dact_out[nrow] = g.high * (1.0f - t * t);       // through high * tanh(.)    model.py:36-37
                 }
                 else if (MODE == MODE_TARGET) o = yv + g.gamma * qv;                 // trainer.py:494 (no terminal mask)
+                else if (ACTION) {                                                   // d(-mean q)/d a   trainer.py:503-506
+                    const float* pg = part2 + buf * 4 * TILE_M + row;
+                    o = -invR * (pg[0] + pg[TILE_M] + pg[2 * TILE_M] + pg[3 * TILE_M]);
+                    if (valid) loss_acc -= qv * invR;                                // -mean q          trainer.py:504
+                }
                 else o = qv;
                 if (valid) g.out[nrow] = o;
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&acc_empty[buf]);
                 return;
             }
-            float dq;
+            float dq = 0.0f;
             if (MODE == MODE_CRITIC_BWD) {
                 const float diff = qv - yv;
                 dq = valid ? 2.0f * diff * invR : 0.0f;                              // d mean((y-q)^2) / dq      trainer.py:496
@@ -539,25 +538,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused3_kernel(const __grid_con
             } else if (MODE == MODE_ACTOR_BWD) {
                 const float t = tanhf(qv);
                 dq = valid ? yv * g.high * (1.0f - t * t) : 0.0f;                    // through high * tanh(.)    model.py:36-37
-            } else {
-                dq = valid ? -invR : 0.0f;                                           // d(-mean q) / dq          trainer.py:504
-                if (c4 == 0 && valid) loss_acc -= qv * invR;
             }
             if (c4 == 0) sdq_acc += dq;
             float v[32];
-            if (TFORM) {         // the exact 0/1 tile [z2 + b2' > 0]; dq = -1/R and 1/s are applied to the row sum in action_grad()
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = (zneg & (0x80000000u >> j)) ? 0.0f : 1.0f;
-            } else if (ACTION) { // dz2 = dq w3' [z2 + b2' > 0]: this tile is multiplied with the resident W2'^T block, which carries no w3'
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const float4 w4 = *reinterpret_cast<const float4*>(w3f_tab + c4 * 32 + j);
-                    v[j] = (zneg & (0x80000000u >> j)) ? 0.0f : dq * w4.x;
-                    v[j + 1] = (zneg & (0x40000000u >> j)) ? 0.0f : dq * w4.y;
-                    v[j + 2] = (zneg & (0x20000000u >> j)) ? 0.0f : dq * w4.z;
-                    v[j + 3] = (zneg & (0x10000000u >> j)) ? 0.0f : dq * w4.w;
-                }
-            } else {
+            {
                 // The tile holds dq [z2 + b2' > 0] WITHOUT the head weight w3': it is folded into the dgrad operand (W2'' = W2' diag(w3'),
                 // pack_fold4_kernel) and into the unfold of the weight gradient, where U = sum_n dq_n relu(z2 + b2') also comes out
                 // of G2 (sum_f W2'[f][j] G2[f][j] + b2'[j] db2[j]) instead of 32 accumulator registers per thread here.  The sign
@@ -570,43 +554,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused3_kernel(const __grid_con
             uint8_t* dzrow = smem + OFF_DZ + (c4 >> 1) * SLOT_BYTES + row * 128;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const uint4 pk = TFORM ? make_uint4(pack_f16x2(v[8 * k], v[8 * k + 1]), pack_f16x2(v[8 * k + 2], v[8 * k + 3]),
-                                                    pack_f16x2(v[8 * k + 4], v[8 * k + 5]), pack_f16x2(v[8 * k + 6], v[8 * k + 7]))
-                                       : make_uint4(pack_x2<F16>(v[8 * k], v[8 * k + 1]), pack_x2<F16>(v[8 * k + 2], v[8 * k + 3]),
-                                                    pack_x2<F16>(v[8 * k + 4], v[8 * k + 5]), pack_x2<F16>(v[8 * k + 6], v[8 * k + 7]));
+                const uint4 pk = make_uint4(pack_x2<F16>(v[8 * k], v[8 * k + 1]), pack_x2<F16>(v[8 * k + 2], v[8 * k + 3]),
+                                            pack_x2<F16>(v[8 * k + 4], v[8 * k + 5]), pack_x2<F16>(v[8 * k + 6], v[8 * k + 7]));
                 *reinterpret_cast<uint4*>(dzrow + ((((c4 & 1) * 4 + k) ^ (row & 7)) << 4)) = pk;
             }
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(dz_full);
-        };
-
-        // ---- stage 4 (MODE_CRITIC_ACTION): d loss / d action = sum_f [za_f > 0] dRa_f wa_f      (trainer.py:503-506)
-        auto action_grad = [&](int tc) {
-            if (c4 != (tc & 3)) return;
-            bool valid;
-            const int64_t nrow = rowinfo(tc, valid);
-            const float a_val = a_ag;
-            mbar_wait(dra_full, (uint32_t)tc & 1);
-            tc_fence_after();
-            float acc = 0.0f;
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                if (h * 32 < la) {
-                    float v[32];
-                    tmem_ld32(tmem_base + 256u + (uint32_t)(h * 32) + tlane, v);
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float w = wa_tab[h * 32 + j];                          // zero beyond la
-                        const float zz = fmaf(a_val, w, ba_tab[h * 32 + j]);
-                        acc = fmaf(zz > 0.0f ? v[j] : 0.0f, w, acc);
-                    }
-                }
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(dra_empty);
-            if (valid) g.out[nrow] = TFORM ? acc * (-invR * inv_s) : acc;
         };
 
         // ---- software pipeline
@@ -617,24 +571,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused3_kernel(const __grid_con
             bool v0;
             a_pf = __ldg(g.act + rowinfo(0, v0));
         }
+        if (ACTION) {
+            bool v0;
+            a_ag = __ldg(g.act + rowinfo(0, v0));
+        }
         convert(0);
         for (int i = 0; i < T; ++i) {
-            if (ACTION) {                    // the action-column dgrad borrows the z1 columns between convert(i+1) and the next layer-1 MMA
-                if (i >= 1) pass2(i - 1);
-                if (i + 1 < T) convert(i + 1);
-                pass1(i);
-                if (i >= 1) action_grad(i - 1);
-            } else {                         // every stage waits on work that is at least one stage old
+            {                                // every stage waits on work that is at least one stage old
                 if (i + 1 < T) convert(i + 1);
                 if (i >= 1) pass2(i - 1);
                 pass1(i);
             }
         }
         pass2(T - 1);
-        if (ACTION) action_grad(T - 1);
 
         // ---- flush the per-thread partial sums of this CTA
-        if (HAS_DZ && c4 == 0) {
+        if ((HAS_DZ || ACTION) && c4 == 0) {
             const float sl = warp_sum(loss_acc), sd = warp_sum(sdq_acc);
             if (lane == 0) {
                 if (g.loss && MODE != MODE_ACTOR_BWD) atomicAdd(g.loss + 2 * agent + (MODE == MODE_CRITIC_BWD ? 0 : 1), sl);
@@ -682,9 +634,12 @@ static int make_map(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t 
     return AVD_OK;
 }
 
-bool supported(const avd_net_dims& d) {
-    return d.l2 == L2N && d.ns >= 1 && d.ns <= 4 && d.l1 == L1N && d.la % 16 == 0 && d.la >= 16 && d.la <= 64;
+bool supported(const avd_net_dims& d) {       // la <= 48: the V table of the critic-action pass has la + 1 <= kVRows rows
+    return d.l2 == L2N && d.ns >= 1 && d.ns <= 4 && d.l1 == L1N && d.la % 16 == 0 && d.la >= 16 && d.la < kVRows;
 }
+int vtab_rows() { return kVRows; }
+int vtab_stride() { return kVStride; }
+int vtab_floats() { return kVRows * kVStride + kVBrk; }
 
 template <int MODE, bool F16>
 static int launch2(const CUtensorMap& tmW, const CUtensorMap& tmDZ, const Args& g, dim3 grid, cudaStream_t st) {
@@ -702,11 +657,11 @@ static int launch(bool f16, const CUtensorMap& tmW, const CUtensorMap& tmDZ, con
     return f16 ? launch2<MODE, true>(tmW, tmDZ, g, grid, st) : launch2<MODE, false>(tmW, tmDZ, g, grid, st);
 }
 
-// One pass.  W2T: 16-bit [A][128][F] folded layer-2 kernel (K-major; bf16, or fp16 with f16 = true -- for MODE_CRITIC_ACTION
-// with f16 the T pack W2' diag(w3') s and wscale [A] = 1 / s), b2f: [A][128]  (pack_fold_kernel / pack_fold4_kernel).
+// One pass.  W2T: 16-bit [A][128][F] folded layer-2 kernel (K-major; bf16, or fp16 with f16 = true), b2f: [A][128]
+// (pack_fold_kernel / pack_fold4_kernel).  MODE_CRITIC_ACTION: vtab [A][vtab_floats()] from critic_vtab_kernel.
 // Backward modes: mask_out [A*R][2*ceil(F/64)] sign masks of z1, DZ_out: 16-bit [A*R][128] = dm_scale * dq [z2 + b2' > 0], sdq [A] accumulated into.
 int run(int mode, bool f16, const avd_net_dims& d, int A, int64_t R, const float* params, int64_t pstride, const bf16* W2T, const float* b2f,
-        const float* wscale, const float* s, int64_t s_rs, int64_t s_cs, const float* act, const float* rew, float gamma, float high, const float* y,
+        const float* vtab, const float* s, int64_t s_rs, int64_t s_cs, const float* act, const float* rew, float gamma, float high, const float* y,
         const float* dpi, float* out, uint32_t* mask_out, bf16* DZ_out, float dm_scale, float* sdq, float* loss, cudaStream_t st,
         uint32_t* mask2_out, float* dact_out) {
     if (!supported(d)) {
@@ -720,7 +675,7 @@ int run(int mode, bool f16, const avd_net_dims& d, int A, int64_t R, const float
     AVD_REQUIRE(A >= 1 && R >= 1 && R < (int64_t)1 << 31, "rows per agent must fit the 32-bit TMA coordinates");
     AVD_REQUIRE(!critic || act, "critic passes need actions");
     AVD_REQUIRE(!bwd || (mask_out && DZ_out && sdq), "backward passes need mask / dz2 / sdq outputs");
-    AVD_REQUIRE(!(f16 && mode == MODE_CRITIC_ACTION) || wscale, "the fp16 critic-action pass needs the scale of its T pack");
+    AVD_REQUIRE(mode != MODE_CRITIC_ACTION || (vtab && d.la < kVRows), "the critic-action pass needs its V table (la <= %d)", kVRows - 1);
     AVD_REQUIRE(bwd || out, "null output");
     AVD_REQUIRE(mode != MODE_ACTOR_SAVE || (mask_out && mask2_out && dact_out), "MODE_ACTOR_SAVE needs the mask / d(action) outputs");
     CUtensorMap tmW, tmDZ;
@@ -731,7 +686,7 @@ int run(int mode, bool f16, const avd_net_dims& d, int A, int64_t R, const float
     Args g;
     g.d = d; g.A = A; g.R = R; g.params = params; g.pstride = pstride; g.b2f = b2f; g.s = s; g.s_rs = s_rs; g.s_cs = s_cs; g.act = act;
     g.rew = rew; g.gamma = gamma; g.high = high; g.y = y; g.dpi = dpi; g.out = out; g.mask_out = mask_out; g.mask_words = 2 * ((F + KB - 1) / KB);
-    g.wscale = wscale; g.dm_scale = dm_scale; g.sdq = sdq; g.loss = loss; g.mask2_out = mask2_out; g.dact_out = dact_out;
+    g.vtab = vtab; g.dm_scale = dm_scale; g.sdq = sdq; g.loss = loss; g.mask2_out = mask2_out; g.dact_out = dact_out;
     g.tiles_per_agent = (int)((R + TILE_M - 1) / TILE_M);
     g.ctas_per_agent = std::max(1, std::min(g.tiles_per_agent, sm_count() / std::max(1, A)));
     const dim3 grid((unsigned)(g.ctas_per_agent * A));

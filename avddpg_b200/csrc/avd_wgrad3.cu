@@ -55,7 +55,8 @@ struct Args {
     int64_t R;
     const float* params;        // [A][pstride]
     int64_t pstride;
-    const float* s;             // [A*R][ns]
+    const float* s;             // [A*R][s_rs]: the first ns words of a row
+    int64_t s_rs;
     const float* act;           // [A*R] (critic)
     float* out;                 // G2 slice of CTA (agent, cta): out + agent*out_agent_stride + cta*out_cta_stride, row-major [F][128]
     int64_t out_agent_stride, out_cta_stride;
@@ -232,7 +233,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad3_kernel(const __grid_con
         auto load_x = [&](int t) {
             const int64_t n = rowidx(t);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) xs[k] = k < d.ns ? __ldg(g.s + n * d.ns + k) : 0.0f;
+            for (int k = 0; k < 4; ++k) xs[k] = k < d.ns ? __ldg(g.s + n * g.s_rs + k) : 0.0f;
         };
         auto write_x = [&](int t) {           // [v_hi(5) v_lo(5) v_hi(5) 0],  v = (s0..s3, 1)
             bf16 hi[5], lo[5];
@@ -353,7 +354,7 @@ int ctas_per_agent(int A, int64_t R) {
 // out: every CTA (agent, cta) stores its partial G2 (row-major [F][128] fp32, rows < F) at out + agent*out_agent_stride +
 // cta*out_cta_stride -- no atomics: the 37 x 4 CTAs of the C2 case would otherwise serialise 7 M atomic adds on 160 k
 // addresses (a quarter of the kernel time).  The caller sums the ctas_per_agent(A, R) slices.  DZ: bf16 [A*R][128].
-int run(bool f16, const avd_net_dims& d, bool critic, int A, int64_t R, const float* params, int64_t pstride, const float* s, const float* act, const bf16* DZ,
+int run(bool f16, const avd_net_dims& d, bool critic, int A, int64_t R, const float* params, int64_t pstride, const float* s, int64_t s_rs, const float* act, const bf16* DZ,
         float* out, int64_t out_agent_stride, int64_t out_cta_stride, cudaStream_t st) {
     AVD_REQUIRE(d.l1 == 256 && d.l2 == L2N && d.ns >= 1 && d.ns <= 4 && (!critic || (d.la >= 8 && d.la <= 64)), "unsupported layer sizes for the fused wgrad kernel");
     AVD_REQUIRE(params && s && DZ && out && (!critic || act), "null buffer");
@@ -381,7 +382,7 @@ int run(bool f16, const avd_net_dims& d, bool critic, int A, int64_t R, const fl
         return AVD_ERR_CUDA;
     }
     Args g;
-    g.d = d; g.critic = critic ? 1 : 0; g.A = A; g.FT = critic ? 3 : 2; g.R = R; g.params = params; g.pstride = pstride; g.s = s; g.act = act;
+    g.d = d; g.critic = critic ? 1 : 0; g.A = A; g.FT = critic ? 3 : 2; g.R = R; g.params = params; g.pstride = pstride; g.s = s; g.s_rs = s_rs; g.act = act;
     g.out = out; g.out_agent_stride = out_agent_stride; g.out_cta_stride = out_cta_stride;
     g.tiles_per_agent = (int)((R + TILE_M - 1) / TILE_M);
     g.ctas_per_agent = ctas_per_agent(A, R);

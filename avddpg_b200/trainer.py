@@ -103,7 +103,7 @@ class DDPGPopulation:
         io.apply_mask = None if apply_mask is None else apply_mask.data_ptr()
         io.loss = self.loss.data_ptr()
         io.workspace, io.workspace_bytes = ws.data_ptr(), ws.numel()
-        io.precision = self.precision
+        io.precision, io.s_stride = self.precision, 4         # the replay gather writes 4 state words per row; dims.ns of them are read
         _lib.check(self.lib.avd_ddpg_learn(C.byref(io), _lib.current_stream()))
         return self.critic.grad, self.actor.grad
 
@@ -411,9 +411,7 @@ class Trainer:
             out[:, : x.shape[1]] = x
             return out
 
-        if d.ns != 4:
-            raise NotImplementedError("per-object learn supports the 4-state Model B layout")
-        s, s2 = pad4(s), pad4(s2)
+        s, s2 = pad4(s), pad4(s2)                   # 3-state Model A batches travel in 4-word rows (s_stride = 4, dims.ns = 3)
         a, r = a.reshape(-1).contiguous(), r.reshape(-1).contiguous()
         dev = s.device
         ag = torch.zeros(1, actor_model.bank.n_train, dtype=torch.float32, device=dev)
@@ -429,6 +427,7 @@ class Trainer:
         io.t_actor, io.t_critic = target_actor.bank.flat.data_ptr(), target_critic.bank.flat.data_ptr()
         io.actor_grad, io.critic_grad = ag.data_ptr(), cg.data_ptr()
         io.workspace, io.workspace_bytes = self._ws.data_ptr(), self._ws.numel()
+        io.s_stride = 4
         _lib.check(lib.avd_ddpg_learn(C.byref(io), _lib.current_stream()))
         critic_grad = [critic_model.bank.view(nm, 0, cg) for nm in critic_model.bank.trainable_names]
         actor_grad = [actor_model.bank.view(nm, 0, ag) for nm in actor_model.bank.trainable_names]

@@ -216,10 +216,10 @@ typedef struct avd_learn_io {
     int64_t rows_per_agent;     /* transitions per agent and update (reference: batch_size = 64)       */
     float gamma, action_high, tau, actor_lr, critic_lr;
     float adam_beta1, adam_beta2, adam_eps;
-    const float* s;             /* [A*rows][4]  sampled states   (replay gather output)                */
+    const float* s;             /* [A*rows][s_stride]  sampled states: the first dims.ns words of every row are read     */
     const float* a;             /* [A*rows]                                                            */
     const float* r;             /* [A*rows]                                                            */
-    const float* s2;            /* [A*rows][4]                                                         */
+    const float* s2;            /* [A*rows][s_stride]                                                  */
     float* actor;               /* [A][actor_total]                                                    */
     float* critic;              /* [A][critic_total]                                                   */
     float* t_actor;
@@ -232,8 +232,8 @@ typedef struct avd_learn_io {
     float* loss;                /* [A][2] nullable: critic_loss, actor_loss                            */
     void* workspace;            /* avd_ddpg_workspace_bytes() bytes                                    */
     int64_t workspace_bytes;
-    int32_t precision;          /* 0: fp32 SIMT kernels (parity mode); 1: bf16 tcgen05 tensor-core GEMMs */
-    int32_t reserved0;
+    int32_t precision;          /* 0: fp32 SIMT kernels (parity mode); 1: bf16 tcgen05 tensor-core GEMMs; 2: fp16 tcgen05 */
+    int32_t s_stride;           /* row pitch of s / s2 in floats: 4 for the replay gather output (avd_replay_gather), 0 = dims.ns */
 } avd_learn_io;
 
 /* sizes of the flat parameter vectors: out4 = {actor_trainable, actor_total, critic_trainable, critic_total} */

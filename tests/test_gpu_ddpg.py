@@ -105,6 +105,33 @@ def test_learn_gradients_vs_oracle(mods, A, R):
         assert abs(loss[1] - info["actor_loss"]) < 1e-4 * max(1, abs(info["actor_loss"]))
 
 
+@pytest.mark.parametrize("precision", [0, 2])
+def test_learn_three_state_model_a(mods, precision):
+    """Model A agents see 3 state words (environment.py:47-49); their batches still travel in the replay gather's 4-word rows
+    (avd_learn_io.s_stride = 4, dims.ns = 3) and the 4th word -- a_lead, whatever it holds -- must not leak into the networks."""
+    conf = mods["Config"](model="ModelA")
+    R = 1000
+    pop = mods["trainer"].DDPGPopulation(1, 1, conf, num_states=3, rows_per_agent=R, precision=precision)
+    rng = np.random.default_rng(3)
+    nets = [D.init_actor(rng, ns=3), D.init_critic(rng, ns=3), D.init_actor(rng, ns=3), D.init_critic(rng, ns=3)]
+    nets[0]["W3"] *= 50; nets[1]["W3"] *= 300; nets[2]["W3"] *= 50; nets[3]["W3"] *= 300
+    for bank, net in zip((pop.actor, pop.critic, pop.t_actor, pop.t_critic), nets):
+        bank.load_named(0, net)
+    s, a, r, s2 = make_batch(5, R)
+    s3, s23 = s[:, :3].copy(), s2[:, :3].copy()
+    s[:, 3], s2[:, 3] = 1e3, -1e3                      # garbage in the unused word
+    dev = lambda x: torch.as_tensor(np.ascontiguousarray(x), device="cuda")
+    pop.learn(dev(s), dev(a.reshape(-1)), dev(r.reshape(-1)), dev(s2), apply_updates=False)
+    torch.cuda.synchronize()
+    ocg, oag, info = D.learn(nets[0], nets[1], nets[2], nets[3], (s3, a, r, s23), gamma=conf.gamma, high=conf.action_high, with_abs=True)
+    for bank, ref, ab in ((pop.critic, ocg, info["critic_abs"]), (pop.actor, oag, info["actor_abs"])):
+        for name in bank.trainable_names:
+            got = bank.view(name, 0, bank.grad).cpu().numpy().astype(np.float64)
+            want = ref[name].reshape(got.shape).astype(np.float64)
+            err = np.linalg.norm(got - want) / max(np.linalg.norm(ab[name].astype(np.float64)), 1e-300)
+            assert err < (2e-4 if precision == 0 else 8e-3), (bank.kind, name, err)
+
+
 def test_learn_apply_updates_sequence(mods):
     """3 consecutive local updates (Adam x2 + Polyak) stay on the oracle's trajectory."""
     A, R = 2, 64

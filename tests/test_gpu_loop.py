@@ -8,7 +8,7 @@ row order of the gather, which weights a pass reads, Adam step counters, FRL mem
 Tolerances:
   precision 0 (fp32 SIMT)    states 2e-5 normwise, losses 1e-4, weight UPDATES (theta_K - theta_0) 5e-3 rel-L2 per tensor
                              (measured 3.7e-6 / 2.8e-5 / 2.8e-3)
-  precision 2 (fp16 tcgen05) states 5e-4, losses 5e-3, weight updates 5e-2 (64 x E = 256 rows per update: the small-batch regime;
+  precision 2 (fp16 tcgen05) states 5e-4, losses 1e-2, weight updates 5e-2 (64 x E = 256 rows per update: the small-batch regime;
                              measured 1.4e-4 / 1.5e-3 / 1.9e-2)
 """
 import numpy as np
@@ -49,7 +49,7 @@ def test_closed_loop_parity(precision, fed):
         for bank, net in zip((tr.pop.actor, tr.pop.critic, tr.pop.t_actor, tr.pop.t_critic), four):
             bank.load_named(a, net)
     ora = TrainLoopOracle(conf, G, E, M, nets, seed=tr.env.seed, ring_capacity=64, fed=fed)
-    st_tol, loss_tol, upd_tol = (2e-5, 1e-4, 5e-3) if precision == 0 else (5e-4, 5e-3, 5e-2)
+    st_tol, loss_tol, upd_tol = (2e-5, 1e-4, 5e-3) if precision == 0 else (5e-4, 1e-2, 5e-2)
     worst_state = worst_loss = 0.0
     n_learn = 0
     for k in range(K_STEPS):
