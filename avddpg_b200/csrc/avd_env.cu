@@ -150,13 +150,15 @@ __device__ __forceinline__ FollowerIn load_follower(const StepCtx& c, int64_t v)
 
 // One Vehicle.step (environment.py:460-518) + fused OU/clip/replay write.  `w` is this follower's exogenous
 // input on entry and the next follower's on exit.  Returns the (negated) reward; sets `term`.
+// (Sharing one Philox block + Box-Muller transform between two followers -- z0 / z1 -- was measured in round 2: 5 % slower at M = 4,
+// 3 % faster at M = 8, 10 % slower plain M = 8 launches from the changed register allocation; every follower keeps its own block.)
 __device__ __forceinline__ float step_follower(const avd_env_params& prm, const avd_env_io& io, const StepCtx& c,
                                                const FollowerIn& f, int m, int M, int64_t p, uint64_t gp, float& w, bool& term) {
     const int64_t v = (int64_t)m * c.P + p;
     float u = f.mu;
     if (c.ou_state) {  // noise.py:14-23 with explicit single roundings (bit-exact vs the host restatement)
-        const uint4 wo = rng_words(io.seed, gp * (uint64_t)M + (uint64_t)m, c.tick, AVD_RNG_OU);
         float z0, z1;
+        const uint4 wo = rng_words(io.seed, gp * (uint64_t)M + (uint64_t)m, c.tick, AVD_RNG_OU);
         normal_pair(wo.x, wo.y, z0, z1);
         const float drift = __fmul_rn(__fmul_rn(prm.ou_theta, __fadd_rn(prm.ou_mean, -f.ou)), prm.ou_dt);
         const float n1 = __fadd_rn(__fadd_rn(f.ou, drift), __fmul_rn(c.ou_c, z0));
@@ -212,9 +214,13 @@ __device__ __forceinline__ float step_follower(const avd_env_params& prm, const 
 // Registers: the preloaded inputs cost 8 per follower.  Platoons of up to 4 followers are preloaded whole; longer ones in chunks of 4
 // (the exogenous input `w` carries the chain from chunk to chunk), so every instantiation fits 80 registers = 3 CTAs per SM --
 // preloading all 8 followers needed 128 registers (2 CTAs per SM) and left the M = 8 launches 15 % behind the M = 4 ones.
-template <int MT>
-__global__ void __launch_bounds__(256, MT >= 1 ? 3 : 2) env_step_kernel(const __grid_constant__ avd_env_params prm,
-                                                                                      const __grid_constant__ avd_env_io io) {
+// TRAIN (OU noise / replay ring fused: the launch of the training loop) is compute-heavier per vehicle (Philox + Box-Muller per
+// follower) than the plain step, so it trades loads in flight per thread for more resident warps: 4 CTAs per SM (64 registers), and
+// for platoons longer than 4 chunks of 2 followers, which fit 64 registers without spilling.  Measured on 4 Mi platoons (launch
+// time, us; `chunk / CTAs per SM`):      M = 4:  4/3 428   4/4 370   2/4 388   2/5 388        M = 8:  4/3 881   4/4 1002   2/4 829   2/5 959
+template <int MT, bool TRAIN>
+__global__ void __launch_bounds__(256, MT >= 1 ? (TRAIN ? 4 : 3) : 2)
+    env_step_kernel(const __grid_constant__ avd_env_params prm, const __grid_constant__ avd_env_io io) {
     const int M = MT ? MT : prm.M;
     StepCtx c;
     c.x_in = io.x_in; c.x_out = io.x_out; c.prev_a = io.prev_a; c.action_mu = io.action_mu; c.ou_state = io.ou_state;
@@ -240,7 +246,7 @@ __global__ void __launch_bounds__(256, MT >= 1 ? 3 : 2) env_step_kernel(const __
 
     for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (int64_t)gridDim.x * blockDim.x) {
         const uint64_t gp = (uint64_t)(io.platoon_id_base + p);
-        constexpr int CH = MT > 4 ? 4 : (MT ? MT : 1);       // followers preloaded at a time
+        constexpr int CH = MT > 4 ? (TRAIN ? 2 : 4) : (MT ? MT : 1);       // followers preloaded at a time
         FollowerIn fin[CH];
         if (MT) {
 #pragma unroll
@@ -396,7 +402,12 @@ extern "C" int avd_env_step(const avd_env_params* prm, const avd_env_io* io, voi
                 "no source for the leader's exogenous input");
     if (io->P == 0) return AVD_OK;
     cudaStream_t st = (cudaStream_t)stream;
-#define AVD_LAUNCH_STEP(MT) env_step_kernel<MT><<<resident_grid(env_step_kernel<MT>, io->P), 256, 0, st>>>(*prm, *io)
+    const bool train = io->ring != nullptr || io->ou_state != nullptr;
+#define AVD_LAUNCH_STEP(MT)                                                                                            \
+    do {                                                                                                               \
+        if (train) env_step_kernel<MT, true><<<resident_grid(env_step_kernel<MT, true>, io->P), 256, 0, st>>>(*prm, *io); \
+        else env_step_kernel<MT, false><<<resident_grid(env_step_kernel<MT, false>, io->P), 256, 0, st>>>(*prm, *io);   \
+    } while (0)
     switch (prm->M) {
         case 1: AVD_LAUNCH_STEP(1); break;
         case 2: AVD_LAUNCH_STEP(2); break;

@@ -144,37 +144,14 @@ __global__ void __launch_bounds__(256) fed_apply_kernel(ApplyArgs a) {
         const float t = (float)(nt.step[i % a.A] + 1);
         lr_tab[i] = nt.lr * sqrtf(1.0f - powf(a.b2, t)) / (1.0f - powf(a.b1, t));
     }
+    peer_barrier(g);                       // ends with __syncthreads(): the table is complete
     const int64_t na = a.net[0].n_train;
     const float omt = 1.0f - a.tau;
     const int64_t row_f4 = g.pitch / 4;
     const int64_t total = (int64_t)g.n_systems * row_f4;
-    // The round is latency-bound (1.2 - 2.5 MB): the optimiser state of this thread's FIRST item (member 0) does not depend on the
-    // peers, so its loads are issued BEFORE the barrier and complete while the thread waits for the slowest rank.
-    const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    float pm[4], pv[4], pp[4], pt[4];
-    bool pre = false;
-    if (i0 < total) {
-        const int s = (int)(i0 / row_f4);
-        const int64_t c4 = (i0 - (int64_t)s * row_f4) * 4;
-        const int64_t ag = (int64_t)s * a.stride_s;
-        pre = !(a.mask && !a.mask[ag]);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int64_t col = c4 + j;
-            if (pre && col < g.n) {
-                const ApplyNet& nt = a.net[col < na ? 0 : 1];
-                const int64_t idx = col < na ? col : col - na;
-                pm[j] = nt.m[ag * nt.n_train + idx];
-                pv[j] = nt.v[ag * nt.n_train + idx];
-                pp[j] = nt.params[ag * nt.total + idx];
-                pt[j] = nt.target[ag * nt.total + idx];
-            }
-        }
-    }
-    peer_barrier(g);                       // ends with __syncthreads(): the table is complete
     int cur_s = -1;
     float inv = 0.0f, divisor = 0.0f;
-    for (int64_t i = i0; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int s = (int)(i / row_f4);
         const int64_t c4 = (i - (int64_t)s * row_f4) * 4;
         const float4 v4 = peer_sum4(g, ((int64_t)s * g.pitch + c4) * 4);      // issued before the divisor is needed: both loads in flight
@@ -201,15 +178,13 @@ __global__ void __launch_bounds__(256) fed_apply_kernel(ApplyArgs a) {
                 float* Vv = nt.v + ag * nt.n_train + idx;
                 float* Pp = nt.params + ag * nt.total + idx;
                 float* Tt = nt.target + ag * nt.total + idx;
-                const bool have = pre && i == i0 && x == 0;        // prefetched before the barrier
-                const float m0 = have ? pm[j] : *Mm, v0 = have ? pv[j] : *Vv, p0 = have ? pp[j] : *Pp, t0 = have ? pt[j] : *Tt;
-                const float mi = m0 + (gavg - m0) * (1.0f - a.b1);
-                const float vi = v0 + (gavg * gavg - v0) * (1.0f - a.b2);
+                const float mi = *Mm + (gavg - *Mm) * (1.0f - a.b1);
+                const float vi = *Vv + (gavg * gavg - *Vv) * (1.0f - a.b2);
                 *Mm = mi;
                 *Vv = vi;
-                const float p = p0 - lr_tab[k * a.A + (int)ag] * mi / (sqrtf(vi) + a.eps);
+                const float p = *Pp - lr_tab[k * a.A + (int)ag] * mi / (sqrtf(vi) + a.eps);
                 *Pp = p;
-                *Tt = p * a.tau + t0 * omt;
+                *Tt = p * a.tau + *Tt * omt;
             }
         }
     }

@@ -12,7 +12,7 @@ def t(P, M, train, iters=40):
     conf = Config(pl_size=M, can_terminate=train)
     if train:
         rings = ReplayRings(4, M, P, 64)
-        env = BatchedPlatoons(P, M, conf, ring=rings, clock=rings.clock, auto_reset=True, track_kinematics=False)
+        env = BatchedPlatoons(P, M, conf, ring=rings, clock=rings.clock, auto_reset=True, track_kinematics=False, store_actions=train != 2)
         step = lambda: env.step_native(explore=True, gen_exog=True, advance_clock=False)
     else:
         env = BatchedPlatoons(P, M, conf, track_kinematics=False, track_episodes=False, store_actions=False)
@@ -28,4 +28,4 @@ def t(P, M, train, iters=40):
 
 
 tag = sys.argv[1] if len(sys.argv) > 1 else ""
-print(tag, " ".join(f"P=4Mi M={M} {'train' if tr else 'plain'} {t(1 << 22, M, tr):.1f}us" for M in (4, 8) for tr in (False, True)), flush=True)
+print(tag, " ".join(f"P=4Mi M={M} {('plain', 'train', 'train-noact')[tr]} {t(1 << 22, M, tr):.1f}us" for M in (4, 8) for tr in (0, 1, 2)), flush=True)
