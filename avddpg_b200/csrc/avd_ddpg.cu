@@ -779,10 +779,10 @@ struct FoldJob {
 constexpr int kFoldJobs = 4;
 struct FoldJobs { FoldJob j[kFoldJobs]; };
 
-__global__ void __launch_bounds__(256) pack_fold4_kernel(FoldJobs jobs, int A, int l2, int f16) {
-    const int job = blockIdx.z / A, agent = blockIdx.z - job * A;
+__device__ __forceinline__ void pack_fold4_body(const FoldJobs& jobs, int A, int l2, int f16, int bx, int by, int bz) {
+    const int job = bz / A, agent = bz - job * A;
     const FoldJob& jb = jobs.j[job];
-    if ((int)blockIdx.y * 8 >= jb.F) return;
+    if (by * 8 >= jb.F) return;
     float s_w3 = 1.0f;          // the power-of-two scale s of this (net, agent): every CTA derives it from the same 128 head weights
     if (f16 && jb.W2b) {
         __shared__ float mx[8];
@@ -802,15 +802,15 @@ __global__ void __launch_bounds__(256) pack_fold4_kernel(FoldJobs jobs, int A, i
             e = max(-100, min(100, e));
             s_w3 = ldexpf(1.0f, -e);
         }
-        if (jb.wscale && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) jb.wscale[agent] = 1.0f / s_w3;
+        if (jb.wscale && bx == 0 && by == 0 && threadIdx.x == 0) jb.wscale[agent] = 1.0f / s_w3;
         __syncthreads();
     }
     const FoldOff& o = jb.o;
     const float* P = jb.params + (int64_t)agent * jb.pstride;
     const int F = jb.F;
-    const int j = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int j = bx * 32 + (threadIdx.x & 31);
     const int fy = threadIdx.x >> 5;
-    const int f = blockIdx.y * 8 + fy;
+    const int f = by * 8 + fy;
     __shared__ float red[8][32];
     float acc = 0.0f;
     if (j < l2 && f < F) {
@@ -830,7 +830,7 @@ __global__ void __launch_bounds__(256) pack_fold4_kernel(FoldJobs jobs, int A, i
     red[fy][threadIdx.x & 31] = acc;
     __syncthreads();
     if (fy == 0 && j < l2) {
-        float t = blockIdx.y == 0 ? P[o.b2 + j] : 0.0f;
+        float t = by == 0 ? P[o.b2 + j] : 0.0f;
 #pragma unroll
         for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x];
         atomicAdd(jb.b2f + (int64_t)agent * l2 + j, t);
@@ -841,9 +841,9 @@ __global__ void __launch_bounds__(256) pack_fold4_kernel(FoldJobs jobs, int A, i
 // [16][128-row] tile is the K-major B operand of the fused dgrad kernel (avd_dgrad3.cu):
 //   G1[f][c] = sum_n dz1[n][f] x_ext[n][c]  =>  dW1[k][f] = G1[f][k] + G1[f][8+k],  dWa[f] = G1[l1+f][4] + G1[l1+f][12],  db[f] = G1[f][5]
 // and column 5 (the constant one) also yields db2 = sum_n dz2[n][:].
-__global__ void __launch_bounds__(256) xext_kernel(const float* __restrict__ s, int64_t s_rs, const float* __restrict__ a, int ns, int64_t N,
-                                                   bf16* __restrict__ xextT, int64_t R, int64_t Rp, int f16) {
-    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void xext_body(const float* __restrict__ s, int64_t s_rs, const float* __restrict__ a, int ns, int64_t N,
+                                          bf16* __restrict__ xextT, int64_t R, int64_t Rp, int f16, int64_t block) {
+    const int64_t n = block * blockDim.x + threadIdx.x;
     if (n >= N) return;
     float v[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
     for (int k = 0; k < ns && k < 4; ++k) v[k] = s[n * s_rs + k];
@@ -872,11 +872,9 @@ __global__ void __launch_bounds__(256) xext_kernel(const float* __restrict__ s, 
 // the breakpoints (rank sort, la <= 64), stages its [la][32] slab of wa_f W2' w3' in shared memory with coalesced loads, and fills
 // its rows -- the active set of interval k is evaluated with the forward pass's own test fma(a, wa_f, ba_f) > 0 at a point inside
 // the interval.  Output per agent: [rows][stride] fp32 (pad columns zero) followed by 64 sorted breakpoints (+inf padded).
-__global__ void __launch_bounds__(256) critic_vtab_kernel(const float* __restrict__ params, int64_t pstride, CriticOff o, avd_net_dims d,
-                                                          float* __restrict__ vtab, int rows, int stride, int total) {
-    pdl_wait();
-    pdl_launch_dependents();
-    const int agent = blockIdx.x, slab = blockIdx.y, tid = threadIdx.x;
+__device__ __forceinline__ void critic_vtab_body(const float* __restrict__ params, int64_t pstride, const CriticOff& o, const avd_net_dims& d,
+                                                 float* __restrict__ vtab, int rows, int stride, int total, int agent, int slab) {
+    const int tid = threadIdx.x;
     const float* P = params + (int64_t)agent * pstride;
     float* out = vtab + (int64_t)agent * total;
     __shared__ float wa[64], ba[64], brk[64], sorted[64], col[64][33];
@@ -927,6 +925,29 @@ __global__ void __launch_bounds__(256) critic_vtab_kernel(const float* __restric
         for (int f = 0; f < la; ++f)
             if (fmaf(a, wa[f], ba[f]) > 0.0f) acc += col[f][c];
         out[k * stride + jj] = acc;
+    }
+}
+
+// Everything a learn step prepares before its first network pass, in ONE launch (three dependent small launches cost ~40 us of
+// launch gaps at C2): the V table of the critic-action pass (first blocks: the longest dependent chain), the BN-folded 16-bit
+// weight packs of the four networks, and the hi/lo-split x_ext operand of the dgrad kernels.
+struct PrepArgs {
+    FoldJobs jobs;
+    int A, l2, f16;
+    unsigned fold_gx, fold_gy, n_fold, n_vtab, vtab_gy;
+    const float* critic; int64_t cstride; CriticOff co; avd_net_dims d; float* vtab; int v_rows, v_stride, v_total;
+    const float* s; int64_t s_rs; const float* a; int64_t N; bf16* xextT; int64_t R, Rp;
+};
+
+__global__ void __launch_bounds__(256) learn_prep_kernel(const __grid_constant__ PrepArgs p) {
+    const unsigned b = blockIdx.x;
+    if (b < p.n_vtab) {
+        critic_vtab_body(p.critic, p.cstride, p.co, p.d, p.vtab, p.v_rows, p.v_stride, p.v_total, (int)(b / p.vtab_gy), (int)(b % p.vtab_gy));
+    } else if (b < p.n_vtab + p.n_fold) {
+        const unsigned f = b - p.n_vtab;
+        pack_fold4_body(p.jobs, p.A, p.l2, p.f16, (int)(f % p.fold_gx), (int)((f / p.fold_gx) % p.fold_gy), (int)(f / (p.fold_gx * p.fold_gy)));
+    } else {
+        xext_body(p.s, p.s_rs, p.a, p.d.ns, p.N, p.xextT, p.R, p.Rp, p.f16, (int64_t)(b - p.n_vtab - p.n_fold));
     }
 }
 
@@ -1114,9 +1135,11 @@ struct Workspace {
     float* dbm;                // [2][A][l2]: sum_n dm[n][j] of the two backward passes (db2 = w3' dbm)
     int* ticket;               // [2][A]: CTAs of the unfold kernel that have finished (the last one unfolds the head)
     static constexpr int kMaskWords = 10, kFp = 320, kG2Rows = 384;
-    static int64_t bytes(const avd_net_dims& d, int64_t A, int64_t N) {
+    // fused: the persistent tensor-core kernels keep every activation on chip -- only the dz2 tile (DZ) of the fp32 activation
+    // buffers exists then (C2: 0.9 GB instead of 5.4 GB of workspace, C4: 3.5 GB instead of 21 GB)
+    static int64_t bytes(const avd_net_dims& d, int64_t A, int64_t N, bool fused) {
         const int64_t F = d.l1 + d.la;
-        const int64_t acts = N * (2 * F + d.l1 + 3 * (int64_t)d.l2) * (int64_t)sizeof(float);
+        const int64_t acts = N * (fused ? (int64_t)d.l2 : 2 * F + d.l1 + 3 * (int64_t)d.l2) * (int64_t)sizeof(float);
         const int64_t packed = A * (3 * F + 3 * (int64_t)d.l1) * d.l2 * (int64_t)sizeof(bf16) + (2 * A + 4 + A * (int64_t)fused3::vtab_floats()) * (int64_t)sizeof(float);
         const int64_t vecs = (5 + 4) * ((N + 3) / 4 * 4) * (int64_t)sizeof(float);
         const int64_t slices = std::max<int64_t>(A, sm_count());
@@ -1124,14 +1147,17 @@ struct Workspace {
                              slices * (kFp * 16 + kG2Rows * (int64_t)d.l2) * (int64_t)sizeof(float);
         return acts + packed + vecs + fold + 1024;
     }
-    void carve(void* base_, const avd_net_dims& d, int64_t A, int64_t N) {
+    void carve(void* base_, const avd_net_dims& d, int64_t A, int64_t N, bool fused) {
         const int64_t F = d.l1 + d.la;
         float* p = reinterpret_cast<float*>(((uintptr_t)base_ + 255) & ~(uintptr_t)255);
-        H = p; p += N * F;
-        DH = p; p += N * F;
-        H1a = p; p += N * d.l1;
-        Z = p; p += N * d.l2;
-        Za = p; p += N * d.l2;
+        H = DH = H1a = Z = Za = nullptr;
+        if (!fused) {
+            H = p; p += N * F;
+            DH = p; p += N * F;
+            H1a = p; p += N * d.l1;
+            Z = p; p += N * d.l2;
+            Za = p; p += N * d.l2;
+        }
         DZ = p; p += N * d.l2;
         bf16* b = reinterpret_cast<bf16*>(p);
         cW2b = b; b += A * F * d.l2;
@@ -1267,10 +1293,10 @@ struct Pass {
 
     // all four networks of a learn step in one launch; the b2f buffers must have been zeroed.
     // wscale[i] (fp16 only, nullable): [A] 1 / s of job i's W2b pack.
-    int pack_fold4(int njobs, const float* const params[], const bool critic[], bf16* const W2b[], bf16* const W2T[], float* const b2f[],
-                   float* const wscale[]) const {
-        FoldJobs jobs = {};
-        int Fmax = 0;
+    int pack_fold4(FoldJobs& jobs, int& Fmax, int njobs, const float* const params[], const bool critic[], bf16* const W2b[], bf16* const W2T[],
+                   float* const b2f[], float* const wscale[]) const {
+        jobs = FoldJobs{};
+        Fmax = 0;
         for (int i = 0; i < njobs; ++i) {
             FoldJob& jb = jobs.j[i];
             jb.params = params[i];
@@ -1282,8 +1308,6 @@ struct Pass {
             jb.W2b = W2b[i]; jb.W2T = W2T[i]; jb.b2f = b2f[i]; jb.wscale = wscale[i];
             Fmax = std::max(Fmax, jb.F);
         }
-        pack_fold4_kernel<<<dim3((unsigned)((d.l2 + 31) / 32), (unsigned)((Fmax + 7) / 8), (unsigned)(njobs * A)), 256, 0, st>>>(jobs, A, d.l2, f16() ? 1 : 0);
-        AVD_LAUNCH_OK();
         return AVD_OK;
     }
 
@@ -1385,9 +1409,9 @@ extern "C" int avd_ddpg_param_counts(const avd_net_dims* dims, int64_t* out4) {
     return AVD_OK;
 }
 
-extern "C" int64_t avd_ddpg_workspace_bytes(const avd_net_dims* dims, int32_t A, int64_t rows_per_agent) {
+extern "C" int64_t avd_ddpg_workspace_bytes(const avd_net_dims* dims, int32_t A, int64_t rows_per_agent, int32_t precision) {
     if (!dims || A < 0 || rows_per_agent < 0) return -1;
-    return Workspace::bytes(*dims, A, (int64_t)A * rows_per_agent);
+    return Workspace::bytes(*dims, A, (int64_t)A * rows_per_agent, precision != 0 && fused3::supported(*dims));
 }
 
 #define AVD_TRY(expr)             \
@@ -1651,13 +1675,18 @@ static int learn_fused3(const avd_learn_io* io, const Pass& p, const Workspace& 
         bf16* const W2T[4] = {w.taW2T, w.tcW2T, w.cW2T, w.aW2T};
         float* const b2f[4] = {w.ta_b2f, w.tc_b2f, w.c_b2f, w.a_b2f};
         float* const wsc[4] = {nullptr, nullptr, ws_c, ws_a};
-        AVD_TRY(p.pack_fold4(4, prm, crit, W2b, W2T, b2f, wsc));
-        AVD_CUDA_OK(launch_pdl(critic_vtab_kernel, dim3((unsigned)A, (unsigned)((d.l2 + 31) / 32)), dim3(256), 0, st, (const float*)io->critic, co.total, co, d, w.vtab,
-                               fused3::vtab_rows(), fused3::vtab_stride(), fused3::vtab_floats()));
-        AVD_LAUNCH_OK();
+        PrepArgs pa = {};
+        int Fmax = 0;
+        AVD_TRY(p.pack_fold4(pa.jobs, Fmax, 4, prm, crit, W2b, W2T, b2f, wsc));
+        pa.A = A; pa.l2 = d.l2; pa.f16 = f16 ? 1 : 0;
+        pa.fold_gx = (unsigned)((d.l2 + 31) / 32); pa.fold_gy = (unsigned)((Fmax + 7) / 8); pa.n_fold = pa.fold_gx * pa.fold_gy * (unsigned)(4 * A);
+        pa.vtab_gy = (unsigned)((d.l2 + 31) / 32); pa.n_vtab = (unsigned)A * pa.vtab_gy;
+        pa.critic = io->critic; pa.cstride = co.total; pa.co = co; pa.d = d; pa.vtab = w.vtab;
+        pa.v_rows = fused3::vtab_rows(); pa.v_stride = fused3::vtab_stride(); pa.v_total = fused3::vtab_floats();
+        pa.s = io->s; pa.s_rs = srs; pa.a = io->a; pa.N = N; pa.xextT = w.xextT; pa.R = R; pa.Rp = (R + 63) / 64 * 64;
+        const unsigned n_xext = (unsigned)((N + 255) / 256);
+        learn_prep_kernel<<<pa.n_vtab + pa.n_fold + n_xext, 256, 0, st>>>(pa);
     }
-    const int64_t Rp = (R + 63) / 64 * 64;
-    xext_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(io->s, srs, io->a, d.ns, N, w.xextT, R, Rp, f16 ? 1 : 0);
     // fp16 backward tiles: dq ~ (q - y) / R (critic) and ~ dq/da / R (actor) are lifted by powers of two into the normal range of
     // fp16 (they saturate at +-65504 * 2^-k instead of overflowing); the unfold kernel divides the factors out again
     const float dm_c = f16 ? exp2f(ceilf(log2f((float)R))) : 1.0f, dm_a = f16 ? 256.0f * dm_c : 1.0f;
@@ -1721,7 +1750,7 @@ extern "C" int avd_ddpg_learn(const avd_learn_io* io, void* stream) {
     const avd_net_dims d = io->dims;
     const int A = io->A;
     const int64_t R = io->rows_per_agent, N = (int64_t)A * R;
-    AVD_REQUIRE(io->workspace && io->workspace_bytes >= avd_ddpg_workspace_bytes(&d, A, R), "workspace too small");
+    AVD_REQUIRE(io->workspace && io->workspace_bytes >= avd_ddpg_workspace_bytes(&d, A, R, io->precision), "workspace too small");
     if (A == 0) return AVD_OK;
     cudaStream_t st = (cudaStream_t)stream;
     const bool tc = io->precision != 0;
@@ -1730,7 +1759,8 @@ extern "C" int avd_ddpg_learn(const avd_learn_io* io, void* stream) {
     const CriticOff co = critic_off(d);
     const int F = d.l1 + d.la;
     Workspace w;
-    w.carve(io->workspace, d, A, N);
+    const bool fz = tc && fused3::supported(d);   // persistent fused pass / dgrad / wgrad kernels
+    w.carve(io->workspace, d, A, N, fz);
     const dim3 gl1b((unsigned)((R + kL1BwdRows - 1) / kL1BwdRows), A);
     const int64_t srs = io->s_stride ? io->s_stride : d.ns;      // row pitch of the state batches
     AVD_REQUIRE(srs >= d.ns, "s_stride %d is smaller than the state width %d", (int)io->s_stride, d.ns);
@@ -1738,7 +1768,6 @@ extern "C" int avd_ddpg_learn(const avd_learn_io* io, void* stream) {
     AVD_CUDA_OK(cudaMemsetAsync(io->actor_grad, 0, (size_t)A * ao.n_train * sizeof(float), st));
     AVD_CUDA_OK(cudaMemsetAsync(io->critic_grad, 0, (size_t)A * co.n_train * sizeof(float), st));
     if (io->loss) AVD_CUDA_OK(cudaMemsetAsync(io->loss, 0, (size_t)A * 2 * sizeof(float), st));
-    const bool fz = tc && fused3::supported(d);   // persistent fused pass / dgrad / wgrad kernels
     if (fz) return learn_fused3(io, p, w, st);
     if (tc) {   // bf16 copies of the four layer-2 kernels (K-major for forward, and for dgrad on the online nets)
         AVD_TRY(p.pack(io->t_actor, ao.total, ao.W2, d.l1, nullptr, w.taW2T));

@@ -54,7 +54,7 @@ class DDPGPopulation:
         self.t_critic.flat.copy_(self.critic.flat)
 
     def _workspace(self, rows):
-        need = self.lib.avd_ddpg_workspace_bytes(C.byref(self.dims), self.A, rows)
+        need = self.lib.avd_ddpg_workspace_bytes(C.byref(self.dims), self.A, rows, self.precision)
         if self._ws is None or self._ws.numel() < need:
             self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
         return self._ws
@@ -416,7 +416,7 @@ class Trainer:
         dev = s.device
         ag = torch.zeros(1, actor_model.bank.n_train, dtype=torch.float32, device=dev)
         cg = torch.zeros(1, critic_model.bank.n_train, dtype=torch.float32, device=dev)
-        need = lib.avd_ddpg_workspace_bytes(C.byref(d), 1, n)
+        need = lib.avd_ddpg_workspace_bytes(C.byref(d), 1, n, 0)
         if self._ws is None or self._ws.numel() < need:
             self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
         io = _lib.LearnIO()

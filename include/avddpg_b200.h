@@ -230,7 +230,7 @@ typedef struct avd_learn_io {
     int32_t* actor_t; int32_t* critic_t;                                  /* [A] Adam step counters       */
     const uint8_t* apply_mask;  /* [A] nullable: agents with 0 keep their weights (intrafrl "leader is king") */
     float* loss;                /* [A][2] nullable: critic_loss, actor_loss                            */
-    void* workspace;            /* avd_ddpg_workspace_bytes() bytes                                    */
+    void* workspace;            /* avd_ddpg_workspace_bytes(dims, A, rows_per_agent, precision) bytes  */
     int64_t workspace_bytes;
     int32_t precision;          /* 0: fp32 SIMT kernels (parity mode); 1: bf16 tcgen05 tensor-core GEMMs; 2: fp16 tcgen05 */
     int32_t s_stride;           /* row pitch of s / s2 in floats: 4 for the replay gather output (avd_replay_gather), 0 = dims.ns */
@@ -238,7 +238,7 @@ typedef struct avd_learn_io {
 
 /* sizes of the flat parameter vectors: out4 = {actor_trainable, actor_total, critic_trainable, critic_total} */
 int avd_ddpg_param_counts(const avd_net_dims* dims, int64_t* out4);
-int64_t avd_ddpg_workspace_bytes(const avd_net_dims* dims, int32_t A, int64_t rows_per_agent);
+int64_t avd_ddpg_workspace_bytes(const avd_net_dims* dims, int32_t A, int64_t rows_per_agent, int32_t precision);
 
 /* Trainer.learn (workers/trainer.py:472-508) for all agents at once: TD target from the target nets,
  * critic MSE gradient, actor -mean(Q) gradient (both on the pre-update weights); then, if apply_updates,
