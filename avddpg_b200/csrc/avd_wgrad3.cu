@@ -12,12 +12,15 @@
 // The action-branch slab of the critic (one input per feature, model.py:69-70) is converted on the CUDA cores.
 // Reference: workers/trainer.py:498, 506 (tape.gradient) through agent/model.py:19-33, 62-77.
 //
-// Warps: 0 issuer of the G2 products, 1 TMA producer, 2..17 converters (TMEM lane quadrant = warp % 4; two independent
-// groups of eight warps, one per 64-feature half of a slab, 32 columns per warp), 18 issuer of the layer-1 MMAs.
-// TMEM: 2-3 slab accumulators (128 columns each) + a ring of z1 HALF slabs (64 columns each) in the remaining columns: four
-// for the actor, two for the critic.  The layer-1 MMA of a half slab is issued as soon as the converters have drained the ring
-// entry it reuses, and r1 slabs go through a ring of four shared-memory buffers, so the MMA -> commit -> tcgen05.ld -> convert
-// -> MMA round trips of one half slab hide behind the work on the others.
+// Warps: 0 issuer of the G2 products, 1 TMA producer, 2..17 converters in four TEAMS of four warps (one warp per TMEM lane
+// quadrant), 18 issuer of the layer-1 MMAs.  Team k owns the 64-feature unit k of every row tile (features [64 k, 64 k + 64)):
+// per tile a warp waits for ONE layer-1 product, pulls its 64 values into registers (two tcgen05.ld in flight), hands the ring
+// entry back at once and converts from registers -- four independent unit pipelines per CTA instead of two groups that walked the
+// units of a tile one after the other (round 2, first version: 1560 cycles per unit chain against 512 cycles of tensor-pipe
+// work per slab).  The action-branch features of the critic are spread over two teams, alternating with the tile parity.
+// TMEM: the accumulator is G2^T -- lane = layer-2 unit j, column = feature f (the dz2 tile is the MN-major A operand, the r1 slab
+// the MN-major B operand) -- 256 columns for the state features + 64 for the action branch (N = 64 products instead of a third
+// 128-wide slab), which leaves a ring of four (actor) / three (critic) 64-column z1 entries.
 #include <cudaTypedefs.h>
 
 #include <algorithm>
@@ -33,7 +36,7 @@ using namespace umma;
 typedef __nv_bfloat16 bf16;
 
 constexpr int TILE_M = 128, L2N = 128, KB = 64, SLAB = 128;
-constexpr int NCONV = 16;                                   // converter warps: 4 per TMEM lane quadrant, 32 columns each
+constexpr int NCONV = 16;                                   // converter warps: four teams of four (one per TMEM lane quadrant), 64 columns each
 constexpr int NUM_THREADS = 32 * (3 + NCONV);
 constexpr int WARP_L1 = 2 + NCONV;                           // issuer of the layer-1 MMAs
 constexpr int HALF_BYTES = TILE_M * 128;                     // [128 rows][64 bf16]: 16 KB
@@ -51,7 +54,7 @@ constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
 
 struct Args {
     avd_net_dims d;
-    int critic, A, FT;          // FT feature slabs per agent (actor 2; critic 3, the last one = action branch)
+    int critic, A, FT;          // FT slab steps per row tile (actor 2; critic 3, the last one = action branch)
     int64_t R;
     const float* params;        // [A][pstride]
     int64_t pstride;
@@ -102,7 +105,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad3_kernel(const __grid_con
     const int agent = (int)blockIdx.x / g.ctas_per_agent;
     const int cta = (int)blockIdx.x - agent * g.ctas_per_agent;
     const int T = (g.tiles_per_agent - cta + g.ctas_per_agent - 1) / g.ctas_per_agent;
-    const int FT = g.FT;                                     // feature slabs: 2 state slabs (+ the action-branch slab of the critic)
+    const int FT = g.FT;                                     // slab steps per row tile: 2 state slabs (+ the action-branch step of the critic)
     const float* P = g.params + (int64_t)agent * g.pstride;
 
     if (threadIdx.x == 0) {
@@ -111,8 +114,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad3_kernel(const __grid_con
             mbar_init(&dz_full[i], 1); mbar_init(&dz_empty[i], 1);
             mbar_init(&x_full[i], 4);
         }
-        for (int i = 0; i < 4; ++i) { mbar_init(&z1_full[i], 1); mbar_init(&z1_empty[i], NCONV / 2); }
-        for (int i = 0; i < NRB; ++i) { mbar_init(&r_full[i], NCONV); mbar_init(&r_empty[i], 1); }
+        for (int i = 0; i < 4; ++i) { mbar_init(&z1_full[i], 1); mbar_init(&z1_empty[i], 4); }
+        for (int i = 0; i < NRB; ++i) { mbar_init(&r_full[i], NCONV / 2); mbar_init(&r_empty[i], 1); }    // every step is filled by two teams
         mbar_init(acc_done, 1);
         fence_barrier_init();
     }
@@ -129,10 +132,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad3_kernel(const __grid_con
             *reinterpret_cast<uint4*>(smem + OFF_B1 + ct * 16) = make_uint4(pack2(whi[0], whi[1]), pack2(whi[2], whi[3]), pack2(bhi, whi[0]), pack2(whi[1], whi[2]));
             *reinterpret_cast<uint4*>(smem + OFF_B1 + L1N * 16 + ct * 16) = make_uint4(pack2(whi[3], bhi), pack2(wlo[0], wlo[1]), pack2(wlo[2], wlo[3]), pack2(blo, zero));
         }
-        if (g.critic) {                  // the action slab leaves features 64..127 of its r1 buffers unwritten: start from finite values
-            for (int i = ct; i < NRB * 2 * HALF_BYTES / 16; i += 32 * NCONV) reinterpret_cast<uint4*>(smem + OFF_R1)[i] = make_uint4(0u, 0u, 0u, 0u);
-        }
-        if (g.critic && ct < 64) {
+        if (g.critic && ct < 64) {           // zero weights beyond la: those features convert to relu(0) = 0
             const CriticOff o = critic_off(d);
             wa_tab[ct] = ct < d.la ? P[o.Wa + ct] : 0.0f;
             ba_tab[ct] = ct < d.la ? P[o.ba + ct] : 0.0f;
@@ -146,10 +146,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad3_kernel(const __grid_con
     pdl_wait();                      // the prologue only read the parameters; dz2 comes from the previous launch
     pdl_launch_dependents();
     auto tile_of = [&](int tc) { return cta + tc * g.ctas_per_agent; };
-    // Work is a sequence of slab steps q = t FT + s (row tile t, feature slab s); r1 buffer q % NRB.  State slabs (s < 2) go
-    // through the layer-1 MMA in half-slab units u = 4 t + 2 s + h (64 features), z1 ring entry u % NZ.
-    const int nzs = FT > 2 ? 1 : 2, NZ = 1 << nzs;          // log2 / number of ring entries
-    const uint32_t zbase = tmem_base + (uint32_t)(FT * SLAB);
+    // Row tile t: units u = 4 t + k (64 state features each, z1 ring entry u % NZ), slab steps q = t FT + sl (r1 buffer q % NRB):
+    // sl < 2 the 128-feature state slabs (units 2 sl, 2 sl + 1), sl = 2 the action branch (64 feature columns, la of them non-zero).
+    const int NZ = FT > 2 ? 3 : 4;
+    const uint32_t kActCol = 2 * SLAB;                               // accumulator columns of the action-branch features
+    const uint32_t zbase = tmem_base + (FT > 2 ? kActCol + 64u : kActCol);
     const int U = 4 * T;
 
     if (warp == 0) {
@@ -157,7 +158,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad3_kernel(const __grid_con
         // warp-uniform control flow; the tcgen05 instructions are predicated on one elected lane (see avd_umma.cuh)
         if (T > 0) {
             const uint32_t leader = elect_one();
-            constexpr uint32_t idesc2 = make_idesc_f16kind(SLAB, L2N, true, true, F16 ? FMT_F16 : FMT_BF16, F16 ? FMT_F16 : FMT_BF16);   // r1 slab (MN-major) x dz2 tile (MN-major)
+            constexpr uint32_t FOP = F16 ? FMT_F16 : FMT_BF16;
+            constexpr uint32_t idesc2 = make_idesc_f16kind(L2N, SLAB, true, true, FOP, FOP);    // dz2 tile^T (MN-major A) x r1 slab (MN-major B)
+            constexpr uint32_t idesc2a = make_idesc_f16kind(L2N, 64, true, true, FOP, FOP);     // ... x the 64 action-branch columns
             const uint64_t dR = make_smem_desc(smem_u32(smem + OFF_R1), HALF_BYTES, 1024);
             const uint64_t dDZ = make_smem_desc(smem_u32(smem + OFF_DZ), HALF_BYTES, 1024);
             for (int t = 0; t < T; ++t) {
@@ -169,7 +172,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad3_kernel(const __grid_con
                     const uint32_t off = (q % NRB) * 2 * HALF_BYTES, doff = (uint32_t)(t & 1) * 2 * HALF_BYTES;
 #pragma unroll
                     for (int ks = 0; ks < 8; ++ks)
-                        mma_bf16_p(leader, tmem_base + (uint32_t)(sl * SLAB), desc_add(dR, off + ks * 2048), desc_add(dDZ, doff + ks * 2048), idesc2, (t | ks) != 0);
+                        mma_bf16_p(leader, tmem_base + (uint32_t)(sl * SLAB), desc_add(dDZ, doff + ks * 2048), desc_add(dR, off + ks * 2048), sl < 2 ? idesc2 : idesc2a,
+                                   (t | ks) != 0);
                     mma_commit_p(leader, &r_empty[q % NRB]);
                     if (sl == FT - 1) mma_commit_p(leader, &dz_empty[t & 1]);
                 }
@@ -184,14 +188,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad3_kernel(const __grid_con
             const uint32_t leader = elect_one();
             const uint64_t dX = make_desc_noswz(smem_u32(smem + OFF_X), TILE_M * 16, 128);
             const uint64_t dB1 = make_desc_noswz(smem_u32(smem + OFF_B1), L1N * 16, 128);
-            constexpr uint32_t idesc1h = make_idesc_bf16(TILE_M, 64, false, false);    // x (K-major) x W1ext half slab (K-major)
-            for (int u = 0; u < U; ++u) {     // z1 of half-slab unit u -> ring entry u % NZ, once the converters have drained its previous use
-                const int t = u >> 2, b = u & (NZ - 1);
+            constexpr uint32_t idesc1h = make_idesc_bf16(TILE_M, 64, false, false);    // x (K-major) x W1ext unit (K-major)
+            // The ring barriers are per TEAM (z1_full[k] / z1_empty[k]: unit k of every tile), not per ring entry: with three entries an
+            // entry changes hands between teams, and a team waiting for the entry's NEXT phase while another team's phase is still
+            // open would see the parity of an already completed phase.  Unit u goes into entry u % NZ, once the team of the entry's
+            // previous unit u - NZ has pulled that one into registers.
+            int e = 0;
+            for (int u = 0; u < U; ++u) {
+                const int t = u >> 2;
                 if ((u & 3) == 0) mbar_wait(&x_full[t & 1], ((uint32_t)t >> 1) & 1);
-                if (u >= NZ) mbar_wait(&z1_empty[b], (((uint32_t)u >> nzs) - 1) & 1);
+                if (u >= NZ) mbar_wait(&z1_empty[(u - NZ) & 3], ((uint32_t)(u - NZ) >> 2) & 1);
                 tc_fence_after();
-                mma_bf16_p(leader, zbase + (uint32_t)(b * 64), desc_add(dX, (uint32_t)(t & 1) * X_BYTES), desc_add(dB1, (uint32_t)(u & 3) * 64 * 16), idesc1h, 0);
-                mma_commit_p(leader, &z1_full[b]);
+                mma_bf16_p(leader, zbase + (uint32_t)(e * 64), desc_add(dX, (uint32_t)(t & 1) * X_BYTES), desc_add(dB1, (uint32_t)(u & 3) * 64 * 16), idesc1h, 0);
+                mma_commit_p(leader, &z1_full[u & 3]);
+                if (++e == NZ) e = 0;
             }
         }
     } else if (warp == 1) {
@@ -219,8 +229,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad3_kernel(const __grid_con
     } else {
         // ================================================ converters ================================================
         const int cw = warp - 2;             // 0..15
-        const int q4 = warp & 3, qtr = cw >> 2;      // TMEM lane quadrant; 16-column quarter of a half slab / 32-column quarter of an accumulator
-        const int half = qtr >> 1;                   // action slab: which 64-feature MN chunk of the r1 slab
+        const int q4 = warp & 3, team = cw >> 2;     // TMEM lane quadrant; team = 64-feature unit of every tile
+        const int sl_own = team >> 1, half = team & 1;
         const int row = q4 * 32 + lane;
         const uint32_t tlane = (uint32_t)(q4 * 32) << 16;
         auto rowidx = [&](int tc) -> int64_t {
@@ -228,7 +238,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad3_kernel(const __grid_con
             return (int64_t)agent * g.R + (r_in < g.R ? r_in : g.R - 1);
         };
         // Per-row inputs are fetched one tile ahead of their use (xs: state row of the tile whose X buffer is written next,
-        // a_nx: action of the next tile): a load issued right before its use would put a global-memory latency on every tile.
+        // a_nx: action of the next tile this team converts): a load issued right before its use would put a global-memory latency on every tile.
         float xs[4] = {0.f, 0.f, 0.f, 0.f}, a_nx = 0.0f;
         auto load_x = [&](int t) {
             const int64_t n = rowidx(t);
@@ -249,79 +259,79 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad3_kernel(const __grid_con
             __syncwarp();
             if (lane == 0) mbar_arrive(&x_full[t & 1]);
         };
-        if (qtr == 2 && T > 0) {          // the half-1 group: its z1_full of a tile's last unit means all four layer-1 MMAs have read the X buffer
+        // the action-branch step of tile t belongs to the two teams of slab t & 1 (32 feature columns per warp)
+        auto has_action = [&](int t) { return FT > 2 && sl_own == (t & 1); };
+        if (team == 3 && T > 0) {         // team 3 owns the LAST unit of a tile: its z1_full means all four layer-1 MMAs have read the X buffer
             load_x(0);
             write_x(0);
             if (T > 1) { load_x(1); write_x(1); }
             if (T > 2) load_x(2);
         }
-        if (FT > 2 && T > 0) a_nx = __ldg(g.act + rowidx(0));
+        if (T > 0 && has_action(0)) a_nx = __ldg(g.act + rowidx(0));
+        int e = team % NZ;                    // ring entry (4 t + team) % NZ
         for (int t = 0; t < T; ++t) {
-            for (int sl = 0; sl < FT; ++sl) {
-                const uint32_t q = (uint32_t)(t * FT + sl), rb = q % NRB;
-                // rows past the end of the agent's batch: dz2 is zero-filled by TMA there, so whatever r1 holds contributes nothing
+            float z[64];
+            mbar_wait(&z1_full[team], (uint32_t)t & 1);
+            tc_fence_after();
+            tmem_ld64(zbase + (uint32_t)(e * 64) + tlane, z);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&z1_empty[team]);         // the values are in registers: the ring entry can be refilled
+            e += 4 - NZ;
+            if (e >= NZ) e -= NZ;
+            const float a_val = a_nx;
+            if (t + 1 < T && has_action(t + 1)) a_nx = __ldg(g.act + rowidx(t + 1));
+            if (team == 3 && t + 2 < T) {                         // X buffer t & 1 is free (see above)
+                write_x(t + 2);
+                if (t + 3 < T) load_x(t + 3);
+            }
+            // rows past the end of the agent's batch: dz2 is zero-filled by TMA there, so whatever r1 holds contributes nothing
+            {
+                const uint32_t q = (uint32_t)(t * FT + sl_own), rb = q % NRB;
                 uint8_t* rrow = smem + OFF_R1 + rb * 2 * HALF_BYTES + half * HALF_BYTES + row * 128;
-                if (sl < 2) {
-                    // Two independent groups of eight warps, one per 64-feature half of the slab: the round trip z1_full -> tcgen05.ld
-                    // -> z1_empty of one half overlaps the conversion of the other.
-                    {
-                        const int h = half, u = 4 * t + 2 * sl + h, b = u & (NZ - 1);
-                        mbar_wait(&z1_full[b], ((uint32_t)u >> nzs) & 1);
-                        tc_fence_after();
-                        float z[32];
-                        tmem_ld32(zbase + (uint32_t)(b * 64 + (qtr & 1) * 32) + tlane, z);
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&z1_empty[b]);        // the values are in registers: the ring entry can be refilled
-                        mbar_wait(&r_empty[rb], ((q / NRB) & 1) ^ 1);
+                mbar_wait(&r_empty[rb], ((q / NRB) & 1) ^ 1);
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const uint4 pk = make_uint4(pack_relu_x2<F16>(z[8 * k], z[8 * k + 1]), pack_relu_x2<F16>(z[8 * k + 2], z[8 * k + 3]),
-                                                        pack_relu_x2<F16>(z[8 * k + 4], z[8 * k + 5]), pack_relu_x2<F16>(z[8 * k + 6], z[8 * k + 7]));
-                            *reinterpret_cast<uint4*>(rrow + ((((qtr & 1) * 4 + k) ^ (row & 7)) << 4)) = pk;
-                        }
-                    }
-                    fence_proxy_async();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&r_full[rb]);
-                    // all four layer-1 MMAs of tile t have read X buffer t & 1 once z1_full of its last half has been seen
-                    if (sl == 1 && qtr == 2 && t + 2 < T) {
-                        write_x(t + 2);
-                        if (t + 3 < T) load_x(t + 3);
-                    }
-                } else {                     // action-branch slab of the critic: 64 columns on the CUDA cores (zero weights beyond la)
-                    const float a_val = a_nx;
-                    if (t + 1 < T) a_nx = __ldg(g.act + rowidx(t + 1));
-                    mbar_wait(&r_empty[rb], ((q / NRB) & 1) ^ 1);         // every warp waits, so that no arrival can lap a phase of r_full
-                    if (half == 0) {         // features 64..127 of this slab do not exist: that half keeps stale (finite) data, its rows are never flushed
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            float r[8];
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) r[j] = fmaf(a_val, wa_tab[qtr * 32 + 8 * k + j], ba_tab[qtr * 32 + 8 * k + j]);
-                            *reinterpret_cast<uint4*>(rrow + (((qtr * 4 + k) ^ (row & 7)) << 4)) =
-                                make_uint4(pack_relu_x2<F16>(r[0], r[1]), pack_relu_x2<F16>(r[2], r[3]), pack_relu_x2<F16>(r[4], r[5]), pack_relu_x2<F16>(r[6], r[7]));
-                        }
-                        fence_proxy_async();
-                    }
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&r_full[rb]);
+                for (int k = 0; k < 8; ++k) {
+                    const uint4 pk = make_uint4(pack_relu_x2<F16>(z[8 * k], z[8 * k + 1]), pack_relu_x2<F16>(z[8 * k + 2], z[8 * k + 3]),
+                                                pack_relu_x2<F16>(z[8 * k + 4], z[8 * k + 5]), pack_relu_x2<F16>(z[8 * k + 6], z[8 * k + 7]));
+                    *reinterpret_cast<uint4*>(rrow + ((k ^ (row & 7)) << 4)) = pk;
                 }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&r_full[rb]);
+            }
+            if (has_action(t)) {             // action-branch columns [32 half, +32) of the critic: one input per feature, CUDA cores
+                const uint32_t q = (uint32_t)(t * FT + 2), rb = q % NRB;
+                uint8_t* rrow = smem + OFF_R1 + rb * 2 * HALF_BYTES + row * 128;
+                mbar_wait(&r_empty[rb], ((q / NRB) & 1) ^ 1);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    float r[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) r[j] = fmaf(a_val, wa_tab[half * 32 + 8 * k + j], ba_tab[half * 32 + 8 * k + j]);
+                    *reinterpret_cast<uint4*>(rrow + (((half * 4 + k) ^ (row & 7)) << 4)) =
+                        make_uint4(pack_relu_x2<F16>(r[0], r[1]), pack_relu_x2<F16>(r[2], r[3]), pack_relu_x2<F16>(r[4], r[5]), pack_relu_x2<F16>(r[6], r[7]));
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&r_full[rb]);
             }
         }
-        // ---- accumulators of this CTA -> global: slab sl, feature sl*128 + row, this warp's 32 columns
+        // ---- accumulator G2^T of this CTA -> global: lane = layer-2 unit j, this team's feature columns; 32 lanes write 128 contiguous bytes
         if (T > 0) {
             mbar_wait(acc_done, 0);
             tc_fence_after();
-            for (int sl = 0; sl < FT; ++sl) {
-                const int nfeat = sl < 2 ? SLAB : d.la;
-                float* dst = g.out + (int64_t)agent * g.out_agent_stride + (int64_t)cta * g.out_cta_stride + (int64_t)(sl * SLAB + row) * L2N + qtr * 32;
-                float v[32];
-                tmem_ld32(tmem_base + (uint32_t)(sl * SLAB + qtr * 32) + tlane, v);
-                if (row < nfeat) {       // plain 16-byte stores: every CTA owns its slice, the unfold kernel adds the slices up
+            float* dst = g.out + (int64_t)agent * g.out_agent_stride + (int64_t)cta * g.out_cta_stride + row;
+            float v[64];
+            tmem_ld64(tmem_base + (uint32_t)(team * 64) + tlane, v);
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                }
+            for (int i = 0; i < 64; ++i) dst[(int64_t)(team * 64 + i) * L2N] = v[i];
+            if (FT > 2) {
+                float w[16];
+                tmem_ld16(tmem_base + kActCol + (uint32_t)(team * 16) + tlane, w);
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                    if (team * 16 + i < d.la) dst[(int64_t)(2 * SLAB + team * 16 + i) * L2N] = w[i];
             }
             tc_fence_before();
         }
