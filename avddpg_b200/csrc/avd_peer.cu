@@ -26,7 +26,9 @@ struct PeerCore {
     uint64_t multicast_base;               // NVLS multicast mapping of the same allocation (0: none)
     int64_t flag_off, data_off;            // byte offsets inside the allocation: epoch flags [AVD_MAX_PEERS] u32, partial sums
     const float* local;                    // world == 1: the partial sums in plain local memory (no exchange)
-    uint32_t* ctrl;                        // local device memory: [0] rounds completed (epoch), [1] CTAs finished in this round
+    uint32_t* ctrl;                        // local device memory: [0] rounds completed (epoch), [1] CTAs finished in this round,
+                                           // [2] 0, or 1 + the first peer rank whose signal did not arrive within the time limit
+    long long timeout_cycles;              // spin limit of the barrier (SM clock cycles)
     int64_t pitch;                         // floats per system row (multiple of 4)
     int n_systems;
     int64_t n;                             // payload columns; column n carries the divisor
@@ -54,7 +56,15 @@ __device__ __forceinline__ void peer_barrier(const PeerCore& g) {
         }
         if (threadIdx.x < g.world) {
             const uint32_t* flag = reinterpret_cast<const uint32_t*>(g.peer_base[g.rank] + g.flag_off) + threadIdx.x;
+            // A peer that never issues this round (a rank that fell back to another transport, died, or runs a different schedule)
+            // must not hang the GPU for good: after the time limit the wait gives up, records the missing rank in ctrl[2] and the
+            // round completes with whatever the buffers hold -- avd_fed_round_status / PeerExchange.check() turn that into an error.
+            const long long t0 = clock64();
             while ((int32_t)(ld_acquire_sys(flag) - epoch) < 0) {
+                if (clock64() - t0 > g.timeout_cycles) {
+                    atomicCAS(g.ctrl + 2, 0u, 1u + threadIdx.x);
+                    break;
+                }
             }
         }
     }
@@ -216,6 +226,8 @@ static int fill_core(PeerCore& g, const avd_peer_comm* comm, int64_t flag_offset
     for (int r = 0; r < AVD_MAX_PEERS; ++r) g.peer_base[r] = r < comm->world ? comm->peer_base[r] : 0;
     g.multicast_base = comm->world > 1 ? comm->multicast_base : 0;
     g.flag_off = flag_offset; g.data_off = data_offset; g.local = local; g.ctrl = ctrl; g.pitch = pitch; g.n_systems = n_systems; g.n = n;
+    static const long long limit_ms = [] { const char* e = getenv("AVD_PEER_TIMEOUT_MS"); const long long v = e ? atoll(e) : 0; return v > 0 ? v : 20000ll; }();
+    g.timeout_cycles = limit_ms * 2000000ll;      // ~2 GHz SM clock: the limit only has to be generous, not exact
     if (comm->world > 1)
         for (int r = 0; r < comm->world; ++r) AVD_REQUIRE(g.peer_base[r] != 0, "peer %d has no mapped buffer", r);
     return AVD_OK;

@@ -110,12 +110,21 @@ class PeerExchange:
             self.comm.peer_base[r] = int(ptr)
         self.comm.multicast_base = int(getattr(self.hdl, "multicast_ptr", 0) or 0) if allow_multicast else 0
         self.nvls = self.comm.multicast_base != 0
-        self.ctrl = torch.zeros(2, dtype=torch.int32, device=device)      # [0] completed rounds (device-resident epoch), [1] CTA ticket
+        self.ctrl = torch.zeros(4, dtype=torch.int32, device=device)      # [0] completed rounds (device-resident epoch), [1] CTA ticket,
+                                                                           # [2] 1 + rank of a peer that missed a round's barrier (0: healthy)
         dist.barrier(group=process_group)        # every rank has zeroed its flags before the first signal can arrive
         self.round = 0                           # host count: only its PARITY (which half) goes into launch arguments
 
     def data_offset(self) -> int:
         return self.FLAG_BYTES + (self.round & 1) * self.half_bytes
+
+    def check(self):
+        """Raise if a round's cross-rank barrier timed out (synchronises the device: call it at episode / checkpoint boundaries).
+        The kernels give up after AVD_PEER_TIMEOUT_MS instead of spinning forever when a peer never issues the round."""
+        missing = int(self.ctrl[2].item())
+        if missing:
+            raise RuntimeError(f"federated exchange: rank {missing - 1} did not reach the barrier of a round within the time limit "
+                               f"(rank {self.comm.rank} of {self.comm.world}); the averaged values of that round are invalid")
 
     def half(self, n_systems: int, pitch: int) -> torch.Tensor:
         """This round's [n_systems, pitch] float32 view of the local symmetric buffer (fill it, then exchange)."""
@@ -179,7 +188,7 @@ class FederatedAggregator:
             raise ValueError("transport must be auto, peer, p2p or nccl")
         if transport != "nccl" and self.inter and self.world > 1 and dev.type == "cuda":
             self._setup_peer(process_group, transport, dev)
-        self.ctrl = torch.zeros(2, dtype=torch.int32, device=dev) if dev.type == "cuda" else None     # single-rank rounds of the fused consumer
+        self.ctrl = torch.zeros(4, dtype=torch.int32, device=dev) if dev.type == "cuda" else None     # single-rank rounds of the fused consumer
         self.wsum = torch.zeros(self.n_systems, dtype=torch.float32, device=dev)
         self.last_weight_sums = None         # [systems] divisors of the last round (sum of the FedAvg weights over ALL members), or None
         self._apply_io = None
@@ -301,6 +310,12 @@ class FederatedAggregator:
         _lib.check(self.lib.avd_fed_apply_gradients(C.byref(io), _lib.current_stream()))
         if self._use_peer():
             self.peer.round += 1
+
+    def check_health(self):
+        """Raise if a cross-rank round timed out on this rank (PeerExchange.check; synchronises the device).  No-op for the NCCL and
+        single-rank transports, whose failures surface through torch.distributed / CUDA errors."""
+        if self.peer is not None:
+            self.peer.check()
 
     def aggregate_weights(self, weights=None):
         """train_all_models_federated_weights (trainer.py:433-456): average `.weights` (incl. BN statistics) and

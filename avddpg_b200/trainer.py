@@ -279,6 +279,8 @@ class BatchedTrainer:
                 if reward_log is not None:
                     fw, fws = self.frl_weight_lists() if is_weighted_fed_enabled(conf, self.episode) else (None, None)
                     reward_log.update_reward_list(self.episodic_rewards(), fw, fws)
+                if self.fed is not None:
+                    self.fed.check_health()                        # a peer that missed a round's barrier is an error, not a hang
                 self.episode += 1
         finally:
             env.auto_reset = saved

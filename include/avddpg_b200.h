@@ -315,9 +315,12 @@ int avd_fed_finalize(float* buf, int64_t pitch, int32_t n_systems, int64_t n, vo
  * member count / weight sum in column n.  The kernel signals the round's epoch to every peer, waits for all peers, reads the sums
  * over ranks (multimem.ld_reduce in the NVSwitch, or peer loads) and writes out[s][j] = sum_r data_r[s][j] / sum_r data_r[s][n]
  * for j < n and the reduced divisor itself to out[s][n] (fed_weight_sums, trainer.py:358-359).
- * `ctrl`: two zero-initialised uint32 words in LOCAL device memory, owned by the exchange kernels: [0] counts the completed rounds
+ * `ctrl`: FOUR zero-initialised uint32 words in LOCAL device memory, owned by the exchange kernels: [0] counts the completed rounds
  * (the epoch: it is read at kernel start and advanced by the round's last CTA, so nothing about the barrier is baked into launch
- * arguments and a captured CUDA graph replays correctly), [1] is a CTA ticket.  Every rank must issue the same sequence of
+ * arguments and a captured CUDA graph replays correctly), [1] is a CTA ticket, [2] stays 0 unless a peer's signal did not arrive within
+ * the barrier's time limit (environment AVD_PEER_TIMEOUT_MS, default 20000): then it holds 1 + that peer's rank, the round's results
+ * are undefined and the caller must treat the exchange as failed (the kernel gives up instead of spinning forever), [3] reserved.
+ * Every rank must issue the same sequence of
  * exchange calls (this entry and avd_fed_apply_gradients share the epoch); the caller alternates `data_offset` between two halves. */
 #define AVD_MAX_PEERS 16
 typedef struct avd_peer_comm {

@@ -124,3 +124,59 @@ def test_interfrl_transports_and_sharded_env(world):
         env.step_native(explore=True, gen_exog=True)
     full = env.state.cpu().numpy()
     assert np.array_equal(np.concatenate([r[3] for r in res], axis=0), full)
+
+
+def _timeout_worker(rank, world, port, q):
+    """Rank 0 issues one round more than rank 1: its barrier must give up after AVD_PEER_TIMEOUT_MS and report the missing peer."""
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), AVD_PEER_TIMEOUT_MS="300")
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from avddpg_b200.config import Config
+    from avddpg_b200.server.federated import FederatedAggregator
+    from avddpg_b200.trainer import DDPGPopulation
+    conf = Config(pl_size=2, fed_method="interfrl", weighted_average_enabled=False)
+    pop = DDPGPopulation(1, 2, conf)
+    pop.actor.grad.fill_(1.0 + rank)
+    pop.critic.grad.fill_(1.0 + rank)
+    agg = FederatedAggregator(pop, conf, process_group=dist.group.WORLD, transport="peer")
+    agg.aggregate_gradients(apply=False)                 # a healthy round: both ranks take part
+    torch.cuda.synchronize()
+    healthy = True
+    try:
+        agg.check_health()
+    except RuntimeError:
+        healthy = False
+    mean_ok = bool(torch.allclose(pop.actor.grad, torch.full_like(pop.actor.grad, 1.5)))
+    dist.barrier()
+    raised = None
+    if rank == 0:
+        agg.aggregate_gradients(apply=False)             # nobody answers this one
+        torch.cuda.synchronize()                         # returns after ~0.3 s instead of never
+        try:
+            agg.check_health()
+            raised = ""
+        except RuntimeError as e:
+            raised = str(e)
+    q.put((rank, healthy, mean_ok, raised))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_peer_barrier_gives_up_and_reports_the_missing_rank():
+    """a rank whose peers never issue the round must not spin forever (csrc/avd_peer.cu:peer_barrier, ctrl[2])."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_timeout_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=240) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert all(r[1] and r[2] for r in res), res          # the healthy round: no flag, correct mean on both ranks
+    assert res[0][3] and "rank 1 did not reach the barrier" in res[0][3], res
+    assert res[1][3] is None
