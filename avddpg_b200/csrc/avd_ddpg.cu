@@ -1331,8 +1331,15 @@ struct Pass {
     int dgrad3_unfold(bool critic, const float* params, const bf16* DZ, const bf16* W2b, int F, int Fp, const uint32_t* mask, int mask_words,
                       const bf16* xextT, float* G1, const float* G2part, float* grads, float* dbm, const float* b2f, float* U,
                       const float* sdq, int* ticket, const float* wscale, float dm_scale) const {
-        const int64_t gs = critic ? critic_off(d).n_train : actor_off(d).n_train;
         if (int rc = dgrad3::run(f16(), A, R, F, DZ, W2b, mask, mask_words, xextT, (R + 63) / 64 * 64, G1, Fp, dbm, d.l2, st)) return rc;
+        return unfold(critic, params, F, Fp, G1, G2part, grads, dbm, b2f, U, sdq, ticket, wscale, dm_scale);
+    }
+    int dgrad3_only(const bf16* DZ, const bf16* W2b, int F, int Fp, const uint32_t* mask, int mask_words, const bf16* xextT, float* G1, float* dbm) const {
+        return dgrad3::run(f16(), A, R, F, DZ, W2b, mask, mask_words, xextT, (R + 63) / 64 * 64, G1, Fp, dbm, d.l2, st);
+    }
+    int unfold(bool critic, const float* params, int F, int Fp, float* G1, const float* G2part, float* grads, float* dbm, const float* b2f, float* U,
+               const float* sdq, int* ticket, const float* wscale, float dm_scale) const {
+        const int64_t gs = critic ? critic_off(d).n_train : actor_off(d).n_train;
         const int ncta = wgrad3::ctas_per_agent(A, R);
         UnfoldOff u;
         u.f = fold_off(critic);
@@ -1705,11 +1712,14 @@ static int learn_fused3(const avd_learn_io* io, const Pass& p, const Workspace& 
     tm.mark("critic_bwd");
     const int ncta = wgrad3::ctas_per_agent(A, R);
     const int64_t g2_cta = (int64_t)Workspace::kG2Rows * d.l2, g2_agent = (int64_t)ncta * g2_cta;
+    // dgrad first, wgrad second: the unfold kernel then finds the 23 MB of partial G2 slices the weight-gradient CTAs have just written
+    // still in L2 (after a dgrad pass, which streams 340 MB, it read them back from HBM)
+    AVD_TRY(p.dgrad3_only(DZ, w.cW2b, F, Fp, w.mask, MW, w.xextT, w.G1, w.dbm));
+    tm.mark("critic_dgrad");
     AVD_TRY(wgrad3::run(f16, d, true, A, R, io->critic, co.total, io->s, srs, io->a, DZ, w.G2part, g2_agent, g2_cta, st));
     tm.mark("critic_wgrad");
-    AVD_TRY(p.dgrad3_unfold(true, io->critic, DZ, w.cW2b, F, Fp, w.mask, MW, w.xextT, w.G1, w.G2part, io->critic_grad, w.dbm, w.c_b2f, Uc,
-                            w.sdq, w.ticket, ws_c, dm_c));
-    tm.mark("critic_dgrad+unfold");
+    AVD_TRY(p.unfold(true, io->critic, F, Fp, w.G1, w.G2part, io->critic_grad, w.dbm, w.c_b2f, Uc, w.sdq, w.ticket, ws_c, dm_c));
+    tm.mark("critic_unfold");
     // ---- actor loss gradient: -mean(critic(s, actor(s)))                            trainer.py:501-506
     static const bool legacy_actor_bwd = getenv("AVD_ACTOR_BWD_PASS") != nullptr;     // diagnostic: the round-1 second forward pass
     AVD_TRY(fused3::run(legacy_actor_bwd ? fused3::MODE_ACTOR_OUT : fused3::MODE_ACTOR_SAVE, f16, d, A, R, io->actor, ao.total, w.aW2T, w.a_b2f, nullptr,
@@ -1729,11 +1739,12 @@ static int learn_fused3(const avd_learn_io* io, const Pass& p, const Workspace& 
         AVD_LAUNCH_OK();
     }
     tm.mark("actor_bwd");
+    AVD_TRY(p.dgrad3_only(DZ, w.aW2b, d.l1, Fp, w.mask, 8, w.xextT, w.G1, w.dbm + (int64_t)A * d.l2));
+    tm.mark("actor_dgrad");
     AVD_TRY(wgrad3::run(f16, d, false, A, R, io->actor, ao.total, io->s, srs, nullptr, DZ, w.G2part, g2_agent, g2_cta, st));
     tm.mark("actor_wgrad");
-    AVD_TRY(p.dgrad3_unfold(false, io->actor, DZ, w.aW2b, d.l1, Fp, w.mask, 8, w.xextT, w.G1, w.G2part, io->actor_grad, w.dbm + (int64_t)A * d.l2,
-                            w.a_b2f, Ua, w.sdq + A, w.ticket + A, ws_a, dm_a));
-    tm.mark("actor_dgrad+unfold");
+    AVD_TRY(p.unfold(false, io->actor, d.l1, Fp, w.G1, w.G2part, io->actor_grad, w.dbm + (int64_t)A * d.l2, w.a_b2f, Ua, w.sdq + A, w.ticket + A, ws_a, dm_a));
+    tm.mark("actor_unfold");
     const int rc = apply_local_updates(io, (void*)st);
     tm.mark("adam+polyak");
     return rc;
