@@ -10,14 +10,16 @@ act (actor forward) -> OU noise + clip -> Platoon.step -> ReplayBuffer.add for e
 DDPG learn -> federated round (interfrl, gradients, every step: local reduce -> ONE NVLink kernel that reduces in the switch and
 applies Adam + Polyak) -- the exchange is INSIDE the timed step on every GPU count.
 
-  c1  BASELINE configs[0]: 1 platoon x 2 followers, no FRL (the reference's default `python run.py tr`), CUDA-graph replay
+  c1  BASELINE configs[0]: 1 platoon x 2 followers, no FRL (the reference's default `python run.py tr`)
   c2  BASELINE configs[1]: 4096 platoons x 4 followers per GPU (the N=1 headline; default)
-  c3  BASELINE configs[2]: 8 platoons x 4 followers, FedAvg of actor/critic gradients every step, CUDA-graph replay
+  c3  BASELINE configs[2]: 8 platoons x 4 followers, FedAvg of actor/critic gradients every step
   c4  BASELINE configs[3]: 65,536 platoons x 8 followers over 8 GPUs = 8192 x 8 per GPU, NVLS allreduce aggregation every step
   sweep  BASELINE configs[4]: env-step kernel, 2^10 .. 2^24 platoons, M in {4, 8}, plain and training launch, vs the HBM roofline
 
 Weak scaling: every rank owns its own platoons (global platoon ids are offset by rank, so RNG streams do not depend on the GPU
-count); the only data-path collective is the FRL exchange.
+count); the only data-path collective is the FRL exchange.  Every config replays the training step as a captured CUDA graph
+(`BatchedTrainer.capture / replay`; the FRL epoch and buffer half live in device memory, so the NVLink exchange replays too);
+`--eager` launches it kernel by kernel (C2: 1.094 vs 1.072 ms per step).
 
 The JSON line also carries
   roofline     : the dominant kernel group (learn step: tensor pipe) + roofline_env / roofline_env_train (HBM), CUDA-event timed
@@ -45,11 +47,11 @@ CONFIGS = {
     # G platoon-groups per GPU (agents of a group share nothing; groups of one follower index are the FRL system), E envs per group
     "c1": dict(G=1, E=1, M=2, fed=False, graph=True,
                workload="C1: 1 platoon x 2 followers (reference default run), decentralized Model B euler, OU noise, replay cap 100000, batch 64"),
-    "c2": dict(G=1, E=4096, M=4, fed=True, graph=False,
+    "c2": dict(G=1, E=4096, M=4, fed=True, graph=True,
                workload="C2: 4096 platoons x 4 followers per GPU, decentralized Model B euler, OU noise, replay cap 100000, batch 64"),
     "c3": dict(G=8, E=1, M=4, fed=True, graph=True,
                workload="C3: 8 platoons x 4 followers, interfrl FedAvg of actor/critic gradients every step, replay cap 100000, batch 64"),
-    "c4": dict(G=1, E=8192, M=8, fed=True, graph=False,
+    "c4": dict(G=1, E=8192, M=8, fed=True, graph=True,
                workload="C4: 8192 platoons x 8 followers per GPU (65,536 x 8 on 8 GPUs), interfrl allreduce aggregation every step, batch 64"),
 }
 
@@ -287,23 +289,32 @@ def run_native(args):
     warm = max(3, args.warmup)
     for _ in range(warm):
         tr.step()
-    graph = cfg["graph"] or args.graph
+    # The training step is replayed as a captured CUDA graph (BatchedTrainer.capture / replay: two steps per replay, ping-pong state)
+    # whenever the FRL transport can be captured (device-resident epoch: local and NVLink peer transports; not NCCL); --eager opts out.
+    graph = (cfg["graph"] or args.graph) and not args.eager and (tr.fed is None or tr.fed.graph_safe)
     if graph:
         tr.capture(warmup=1)
-    step_fn = (lambda: tr.replay()) if graph else (lambda: tr.step())
-    steps_per_call = 2 if graph else 1
-    calls = max(1, args.steps // steps_per_call)
+    K = max(1, args.steps)
+
+    def run_steps():                 # EXACTLY K steps: K // 2 replays (+ one eager step when K is odd)
+        if graph:
+            for _ in range(K // 2):
+                tr.replay()
+            if K & 1:
+                tr.step()
+        else:
+            for _ in range(K):
+                tr.step()
 
     # ---- device-resident timing of the whole training step (inputs already in HBM; the FRL exchange is part of the step)
     lib = _lib.load()
     l0 = lib.avd_kernel_launches()      # counted inside the library, one per kernel launch site executed
     clk = ClockSampler(local)           # nvidia-smi takes ~0.1 s per query: keep sampling through all timed legs
     clk.__enter__()
-    ms_call = _timed(step_fn, calls, world)
-    ms_step = ms_call / steps_per_call
+    ms_step = _timed(run_steps, 1, world) / K
     launches = lib.avd_kernel_launches() - l0
-    if graph:      # replays do not pass through the launch sites: kernels per captured step x replayed steps
-        launches = calls * steps_per_call * tr.kernels_per_step
+    if graph:      # replays do not pass through the launch sites: kernels per captured step x replayed steps (+ the eager one)
+        launches += (K // 2) * 2 * tr.kernels_per_step
     value = world * P * M / (ms_step * 1e-3)
 
     # ---- attribution: env part (act + env step + replay add), learn part (sample + learn), FRL round (reduce + fused consumer)
@@ -424,7 +435,7 @@ def run_native(args):
             cpu_env = cpu_baseline.time_env_steps(M=M, target_seconds=max(2.0, args.cpu_seconds / 3), with_learn=False)
             cpu["env_only_loop"] = {"value": cpu_env["value"], "sample": cpu_env["sample"]}
         agent_updates = world * pop.A / (ms_step * 1e-3)
-        out = {"metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": calls * steps_per_call, "warmup": warm,
+        out = {"metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": K, "warmup": warm,
                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                "dtype": {0: "f32", 1: "bf16", 2: "fp16"}[args.precision], "data": "synthetic", "impl": "native",
                "config": {"workload": cfg["workload"]},
@@ -536,7 +547,8 @@ def main():
     ap.add_argument("--quick", action="store_true", help="main timing, attribution and e2e only (no rooflines, precision-0 or CPU legs)")
     ap.add_argument("--precision", type=int, default=2,
                     help="learn kernels: 0 fp32 SIMT (parity mode), 1 bf16 tcgen05, 2 fp16 tcgen05 (default; DESIGN.md section 4)")
-    ap.add_argument("--graph", action="store_true", help="replay a captured CUDA graph of the training step (c1 / c3 always do)")
+    ap.add_argument("--graph", action="store_true", help="replay a captured CUDA graph of the training step (the default of every config)")
+    ap.add_argument("--eager", action="store_true", help="launch the training step kernel by kernel instead of replaying its CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
