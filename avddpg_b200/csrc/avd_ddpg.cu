@@ -1657,8 +1657,65 @@ struct StageTimer {
     }
 };
 
+// The preparation launch of the tensor-core learn step: weight half (V table, BN-folded 16-bit packs + folded biases of the four
+// networks; needs the b2f accumulators zeroed) and / or batch half (hi/lo-split [x_hi | 1 | x_lo] operand of the dgrad kernels).
+static int learn_prep(const avd_learn_io* io, const Pass& p, const Workspace& w, bool weights, bool batch, cudaStream_t st) {
+    const avd_net_dims d = io->dims;
+    const int A = io->A;
+    const int64_t R = io->rows_per_agent, N = (int64_t)A * R;
+    const CriticOff co = critic_off(d);
+    const int64_t srs = io->s_stride ? io->s_stride : d.ns;
+    const float* const prm[4] = {io->t_actor, io->t_critic, io->critic, io->actor};
+    const bool crit[4] = {false, true, true, false};
+    bf16* const W2b[4] = {nullptr, nullptr, w.cW2b, w.aW2b};
+    bf16* const W2T[4] = {w.taW2T, w.tcW2T, w.cW2T, w.aW2T};
+    float* const b2f[4] = {w.ta_b2f, w.tc_b2f, w.c_b2f, w.a_b2f};
+    float* const wsc[4] = {nullptr, nullptr, w.wscale, w.wscale + A};
+    PrepArgs pa = {};
+    int Fmax = 0;
+    AVD_TRY(p.pack_fold4(pa.jobs, Fmax, 4, prm, crit, W2b, W2T, b2f, wsc));
+    pa.A = A; pa.l2 = d.l2; pa.f16 = p.f16() ? 1 : 0;
+    pa.fold_gx = (unsigned)((d.l2 + 31) / 32); pa.fold_gy = (unsigned)((Fmax + 7) / 8); pa.n_fold = weights ? pa.fold_gx * pa.fold_gy * (unsigned)(4 * A) : 0u;
+    pa.vtab_gy = (unsigned)((d.l2 + 31) / 32); pa.n_vtab = weights ? (unsigned)A * pa.vtab_gy : 0u;
+    pa.critic = io->critic; pa.cstride = co.total; pa.co = co; pa.d = d; pa.vtab = w.vtab;
+    pa.v_rows = fused3::vtab_rows(); pa.v_stride = fused3::vtab_stride(); pa.v_total = fused3::vtab_floats();
+    pa.s = io->s; pa.s_rs = srs; pa.a = io->a; pa.N = N; pa.xextT = w.xextT; pa.R = R; pa.Rp = (R + 63) / 64 * 64;
+    const unsigned n_xext = batch ? (unsigned)((N + 255) / 256) : 0u;
+    if (pa.n_vtab + pa.n_fold + n_xext == 0) return AVD_OK;
+    learn_prep_kernel<<<pa.n_vtab + pa.n_fold + n_xext, 256, 0, st>>>(pa);
+    AVD_LAUNCH_OK();
+    return AVD_OK;
+}
+
+// Side stream of the learn step (one per device, created on first use): the critic's unfold kernel -- 1216 small CTAs that need the
+// gradients of BOTH critic products but feed nothing before the optimiser -- runs there while the actor's forward pass occupies the
+// tensor pipe on the caller's stream (a 128-thread unfold CTA fits beside a persistent 220 KB CTA on the same SM).  Fork / join by
+// events, so a CUDA-graph capture of the caller's stream records the branch.
+struct SideStream {
+    cudaStream_t s = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+};
+static SideStream* side_stream() {
+    static SideStream tab[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    SideStream& x = tab[dev];
+    if (!x.s) {
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        (void)cs;
+        if (cudaStreamCreateWithFlags(&x.s, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&x.fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&x.join, cudaEventDisableTiming) != cudaSuccess) {
+            x.s = nullptr;
+            return nullptr;
+        }
+    }
+    return &x;
+}
+
 static int learn_fused3(const avd_learn_io* io, const Pass& p, const Workspace& w, cudaStream_t st) {
     StageTimer tm(st);
+    static const bool no_side = getenv("AVD_NO_SIDE_STREAM") != nullptr || getenv("AVD_STAGE_TIMES") != nullptr;
+    SideStream* side = no_side ? nullptr : side_stream();
     const avd_net_dims d = io->dims;
     const int A = io->A;
     const int64_t R = io->rows_per_agent, N = (int64_t)A * R;
@@ -1669,31 +1726,15 @@ static int learn_fused3(const avd_learn_io* io, const Pass& p, const Workspace& 
     bf16* DZ = reinterpret_cast<bf16*>(w.DZ);
     float* Uc = w.U;
     float* Ua = w.U + (int64_t)A * d.l2;
-    // c_b2f .. ta_b2f, U and sdq are adjacent in the workspace: one memset zeroes every accumulator of the step
-    AVD_CUDA_OK(cudaMemsetAsync(w.c_b2f, 0, (size_t)((char*)(w.sdq + 2 * A) - (char*)w.c_b2f), st));
     const bool f16 = p.f16();
     const int64_t srs = io->s_stride ? io->s_stride : d.ns;      // row pitch of the state batches
     float* const ws_c = w.wscale;
     float* const ws_a = w.wscale + A;
-    {
-        const float* const prm[4] = {io->t_actor, io->t_critic, io->critic, io->actor};
-        const bool crit[4] = {false, true, true, false};
-        bf16* const W2b[4] = {nullptr, nullptr, w.cW2b, w.aW2b};
-        bf16* const W2T[4] = {w.taW2T, w.tcW2T, w.cW2T, w.aW2T};
-        float* const b2f[4] = {w.ta_b2f, w.tc_b2f, w.c_b2f, w.a_b2f};
-        float* const wsc[4] = {nullptr, nullptr, ws_c, ws_a};
-        PrepArgs pa = {};
-        int Fmax = 0;
-        AVD_TRY(p.pack_fold4(pa.jobs, Fmax, 4, prm, crit, W2b, W2T, b2f, wsc));
-        pa.A = A; pa.l2 = d.l2; pa.f16 = f16 ? 1 : 0;
-        pa.fold_gx = (unsigned)((d.l2 + 31) / 32); pa.fold_gy = (unsigned)((Fmax + 7) / 8); pa.n_fold = pa.fold_gx * pa.fold_gy * (unsigned)(4 * A);
-        pa.vtab_gy = (unsigned)((d.l2 + 31) / 32); pa.n_vtab = (unsigned)A * pa.vtab_gy;
-        pa.critic = io->critic; pa.cstride = co.total; pa.co = co; pa.d = d; pa.vtab = w.vtab;
-        pa.v_rows = fused3::vtab_rows(); pa.v_stride = fused3::vtab_stride(); pa.v_total = fused3::vtab_floats();
-        pa.s = io->s; pa.s_rs = srs; pa.a = io->a; pa.N = N; pa.xextT = w.xextT; pa.R = R; pa.Rp = (R + 63) / 64 * 64;
-        const unsigned n_xext = (unsigned)((N + 255) / 256);
-        learn_prep_kernel<<<pa.n_vtab + pa.n_fold + n_xext, 256, 0, st>>>(pa);
-    }
+    // c_b2f .. ta_b2f (folded biases, accumulated by the fold job), then dbm, ticket, U and sdq are adjacent in the workspace: one
+    // memset zeroes every accumulator of the step.  (Running the weight half of the preparation on a side stream beside the
+    // environment step and the replay gather was measured: -15 us per step with eager launches, nothing under CUDA-graph replay.)
+    AVD_CUDA_OK(cudaMemsetAsync(w.c_b2f, 0, (size_t)((char*)(w.sdq + 2 * A) - (char*)w.c_b2f), st));
+    AVD_TRY(learn_prep(io, p, w, true, true, st));
     // fp16 backward tiles: dq ~ (q - y) / R (critic) and ~ dq/da / R (actor) are lifted by powers of two into the normal range of
     // fp16 (they saturate at +-65504 * 2^-k instead of overflowing); the unfold kernel divides the factors out again
     const float dm_c = f16 ? exp2f(ceilf(log2f((float)R))) : 1.0f, dm_a = f16 ? 256.0f * dm_c : 1.0f;
@@ -1718,7 +1759,16 @@ static int learn_fused3(const avd_learn_io* io, const Pass& p, const Workspace& 
     tm.mark("critic_dgrad");
     AVD_TRY(wgrad3::run(f16, d, true, A, R, io->critic, co.total, io->s, srs, io->a, DZ, w.G2part, g2_agent, g2_cta, st));
     tm.mark("critic_wgrad");
-    AVD_TRY(p.unfold(true, io->critic, F, Fp, w.G1, w.G2part, io->critic_grad, w.dbm, w.c_b2f, Uc, w.sdq, w.ticket, ws_c, dm_c));
+    if (side) {        // branch: the critic's unfold beside the actor's forward pass (joined before the actor's products reuse G1 / G2part)
+        AVD_CUDA_OK(cudaEventRecord(side->fork, st));
+        AVD_CUDA_OK(cudaStreamWaitEvent(side->s, side->fork, 0));
+        Pass ps = p;
+        ps.st = side->s;
+        AVD_TRY(ps.unfold(true, io->critic, F, Fp, w.G1, w.G2part, io->critic_grad, w.dbm, w.c_b2f, Uc, w.sdq, w.ticket, ws_c, dm_c));
+        AVD_CUDA_OK(cudaEventRecord(side->join, side->s));
+    } else {
+        AVD_TRY(p.unfold(true, io->critic, F, Fp, w.G1, w.G2part, io->critic_grad, w.dbm, w.c_b2f, Uc, w.sdq, w.ticket, ws_c, dm_c));
+    }
     tm.mark("critic_unfold");
     // ---- actor loss gradient: -mean(critic(s, actor(s)))                            trainer.py:501-506
     static const bool legacy_actor_bwd = getenv("AVD_ACTOR_BWD_PASS") != nullptr;     // diagnostic: the round-1 second forward pass
@@ -1739,6 +1789,7 @@ static int learn_fused3(const avd_learn_io* io, const Pass& p, const Workspace& 
         AVD_LAUNCH_OK();
     }
     tm.mark("actor_bwd");
+    if (side) AVD_CUDA_OK(cudaStreamWaitEvent(st, side->join, 0));      // the critic's unfold has read G1 / G2part
     AVD_TRY(p.dgrad3_only(DZ, w.aW2b, d.l1, Fp, w.mask, 8, w.xextT, w.G1, w.dbm + (int64_t)A * d.l2));
     tm.mark("actor_dgrad");
     AVD_TRY(wgrad3::run(f16, d, false, A, R, io->actor, ao.total, io->s, srs, nullptr, DZ, w.G2part, g2_agent, g2_cta, st));
