@@ -1129,6 +1129,11 @@ struct Workspace {
     float* dact;               // [N] d(action)/d(pre-activation) of the actor
     // BN-folded tensor-core path: sign masks of z1, [x_hi | 1 | x_lo] operand, layer-1 weight-gradient accumulator, folded biases
     uint32_t* mask;
+    // The actor's backward chain (tile, layer-1 sign masks, partial slices) has buffers of its own, so that it can overlap the critic's
+    // chain on the side stream: DZa is the second half of the DZ region (sized for fp32 tiles, the fused path writes 16-bit ones).
+    bf16* DZa;
+    uint32_t* mask_a;          // [N][8]
+    float *G1a, *G2part_a;
     bf16* xextT;               // [A][16][Rp], Rp = R rounded up to 64
     float *G1, *G2part, *c_b2f, *tc_b2f, *a_b2f, *ta_b2f;     // G1 / G2part: one partial slice per persistent CTA (<= max(A, #SMs) slices)
     float *U, *sdq;            // [2][A][l2], [2][A]: head-gradient sums of the critic [0] and actor [1] backward passes
@@ -1143,8 +1148,8 @@ struct Workspace {
         const int64_t packed = A * (3 * F + 3 * (int64_t)d.l1) * d.l2 * (int64_t)sizeof(bf16) + (2 * A + 4 + A * (int64_t)fused3::vtab_floats()) * (int64_t)sizeof(float);
         const int64_t vecs = (5 + 4) * ((N + 3) / 4 * 4) * (int64_t)sizeof(float);
         const int64_t slices = std::max<int64_t>(A, sm_count());
-        const int64_t fold = N * (kMaskWords * 4 + 16 * 2) + A * (8 * (int64_t)d.l2 + 16) * (int64_t)sizeof(float) + A * 16 * 64 * 2 +
-                             slices * (kFp * 16 + kG2Rows * (int64_t)d.l2) * (int64_t)sizeof(float);
+        const int64_t fold = N * ((kMaskWords + 8) * 4 + 16 * 2) + A * (8 * (int64_t)d.l2 + 16) * (int64_t)sizeof(float) + A * 16 * 64 * 2 +
+                             2 * slices * (kFp * 16 + kG2Rows * (int64_t)d.l2) * (int64_t)sizeof(float);
         return acts + packed + vecs + fold + 1024;
     }
     void carve(void* base_, const avd_net_dims& d, int64_t A, int64_t N, bool fused) {
@@ -1159,6 +1164,7 @@ struct Workspace {
             Za = p; p += N * d.l2;
         }
         DZ = p; p += N * d.l2;
+        DZa = reinterpret_cast<bf16*>(DZ) + N * d.l2;
         bf16* b = reinterpret_cast<bf16*>(p);
         cW2b = b; b += A * F * d.l2;
         cW2T = b; b += A * F * d.l2;
@@ -1179,6 +1185,8 @@ struct Workspace {
         const int64_t slices = std::max<int64_t>(A, sm_count());
         G1 = p; p += slices * kFp * 16;
         G2part = p; p += slices * kG2Rows * d.l2;
+        G1a = p; p += slices * kFp * 16;
+        G2part_a = p; p += slices * kG2Rows * d.l2;
         c_b2f = p; p += A * d.l2;
         tc_b2f = p; p += A * d.l2;
         a_b2f = p; p += A * d.l2;
@@ -1188,6 +1196,7 @@ struct Workspace {
         U = p; p += 2 * A * d.l2;
         sdq = p; p += (2 * A + 3) / 4 * 4;
         mask = reinterpret_cast<uint32_t*>(p); p += N * kMaskWords;
+        mask_a = reinterpret_cast<uint32_t*>(p); p += N * 8;
         xextT = reinterpret_cast<bf16*>(((uintptr_t)p + 15) & ~(uintptr_t)15);
     }
 };
@@ -1693,7 +1702,7 @@ static int learn_prep(const avd_learn_io* io, const Pass& p, const Workspace& w,
 // events, so a CUDA-graph capture of the caller's stream records the branch.
 struct SideStream {
     cudaStream_t s = nullptr;
-    cudaEvent_t fork = nullptr, join = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr, fork2 = nullptr, join2 = nullptr;
 };
 static SideStream* side_stream() {
     static SideStream tab[64];
@@ -1704,7 +1713,8 @@ static SideStream* side_stream() {
         cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
         (void)cs;
         if (cudaStreamCreateWithFlags(&x.s, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&x.fork, cudaEventDisableTiming) != cudaSuccess ||
-            cudaEventCreateWithFlags(&x.join, cudaEventDisableTiming) != cudaSuccess) {
+            cudaEventCreateWithFlags(&x.join, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&x.fork2, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&x.join2, cudaEventDisableTiming) != cudaSuccess) {
             x.s = nullptr;
             return nullptr;
         }
@@ -1747,33 +1757,16 @@ static int learn_fused3(const avd_learn_io* io, const Pass& p, const Workspace& 
     AVD_TRY(fused3::run(fused3::MODE_TARGET, f16, d, A, R, io->t_critic, co.total, w.tcW2T, w.tc_b2f, nullptr, io->s2, srs, 1, w.a2, io->r, io->gamma, 0.f,
                         nullptr, nullptr, w.y, nullptr, nullptr, 1.0f, nullptr, nullptr, st));
     tm.mark("t_critic");
-    // ---- critic loss gradient on (s, a)                                             trainer.py:495-498
-    AVD_TRY(fused3::run(fused3::MODE_CRITIC_BWD, f16, d, A, R, io->critic, co.total, w.cW2T, w.c_b2f, nullptr, io->s, srs, 1, io->a, nullptr, 0.f, 0.f,
-                        w.y, nullptr, w.q, w.mask, DZ, dm_c, w.sdq, io->loss, st));
-    tm.mark("critic_bwd");
     const int ncta = wgrad3::ctas_per_agent(A, R);
     const int64_t g2_cta = (int64_t)Workspace::kG2Rows * d.l2, g2_agent = (int64_t)ncta * g2_cta;
-    // dgrad first, wgrad second: the unfold kernel then finds the 23 MB of partial G2 slices the weight-gradient CTAs have just written
-    // still in L2 (after a dgrad pass, which streams 340 MB, it read them back from HBM)
-    AVD_TRY(p.dgrad3_only(DZ, w.cW2b, F, Fp, w.mask, MW, w.xextT, w.G1, w.dbm));
-    tm.mark("critic_dgrad");
-    AVD_TRY(wgrad3::run(f16, d, true, A, R, io->critic, co.total, io->s, srs, io->a, DZ, w.G2part, g2_agent, g2_cta, st));
-    tm.mark("critic_wgrad");
-    if (side) {        // branch: the critic's unfold beside the actor's forward pass (joined before the actor's products reuse G1 / G2part)
-        AVD_CUDA_OK(cudaEventRecord(side->fork, st));
-        AVD_CUDA_OK(cudaStreamWaitEvent(side->s, side->fork, 0));
-        Pass ps = p;
-        ps.st = side->s;
-        AVD_TRY(ps.unfold(true, io->critic, F, Fp, w.G1, w.G2part, io->critic_grad, w.dbm, w.c_b2f, Uc, w.sdq, w.ticket, ws_c, dm_c));
-        AVD_CUDA_OK(cudaEventRecord(side->join, side->s));
-    } else {
-        AVD_TRY(p.unfold(true, io->critic, F, Fp, w.G1, w.G2part, io->critic_grad, w.dbm, w.c_b2f, Uc, w.sdq, w.ticket, ws_c, dm_c));
-    }
-    tm.mark("critic_unfold");
-    // ---- actor loss gradient: -mean(critic(s, actor(s)))                            trainer.py:501-506
+    float* const dbm_a = w.dbm + (int64_t)A * d.l2;
+    // The actor's chain needs the critic's WEIGHTS, not its gradients, so its first half goes in front of the critic's backward pass: the
+    // elementwise kernel that forms the actor's backward tile (HBM-bound, 55 us) then runs on the side stream beside the critic's
+    // backward pass (tensor-bound), and the critic's unfold beside the actor's dgrad.  Both chains have their own tile / mask / slice buffers.
+    // ---- actor loss gradient, first half: pi(s), d(-mean q)/d pi                    trainer.py:501-506
     static const bool legacy_actor_bwd = getenv("AVD_ACTOR_BWD_PASS") != nullptr;     // diagnostic: the round-1 second forward pass
     AVD_TRY(fused3::run(legacy_actor_bwd ? fused3::MODE_ACTOR_OUT : fused3::MODE_ACTOR_SAVE, f16, d, A, R, io->actor, ao.total, w.aW2T, w.a_b2f, nullptr,
-                        io->s, srs, 1, nullptr, nullptr, 0.f, io->action_high, nullptr, nullptr, w.a2, legacy_actor_bwd ? nullptr : w.mask, nullptr, 1.0f,
+                        io->s, srs, 1, nullptr, nullptr, 0.f, io->action_high, nullptr, nullptr, w.a2, legacy_actor_bwd ? nullptr : w.mask_a, nullptr, 1.0f,
                         nullptr, nullptr, st, w.mask2, w.dact));   // pi (+ the sign masks and d(action)/d(pre-activation) for the backward)
     tm.mark("actor_fwd");
     AVD_TRY(fused3::run(fused3::MODE_CRITIC_ACTION, f16, d, A, R, io->critic, co.total, w.cW2T, w.c_b2f, w.vtab, io->s, srs, 1, w.a2,
@@ -1781,21 +1774,51 @@ static int learn_fused3(const avd_learn_io* io, const Pass& p, const Workspace& 
     tm.mark("critic_action");
     if (legacy_actor_bwd) {
         AVD_TRY(fused3::run(fused3::MODE_ACTOR_BWD, f16, d, A, R, io->actor, ao.total, w.aW2T, w.a_b2f, nullptr, io->s, srs, 1, nullptr, nullptr, 0.f,
-                            io->action_high, nullptr, w.dpi, nullptr, w.mask, DZ, dm_a, w.sdq + A, nullptr, st));
+                            io->action_high, nullptr, w.dpi, nullptr, w.mask_a, w.DZa, dm_a, w.sdq + A, nullptr, st));
     } else {
+        cudaStream_t sd = st;
+        if (side) {    // branch A: the actor's backward tile beside the critic's backward pass
+            AVD_CUDA_OK(cudaEventRecord(side->fork, st));
+            AVD_CUDA_OK(cudaStreamWaitEvent(side->s, side->fork, 0));
+            sd = side->s;
+        }
         const dim3 grid((unsigned)std::min<int64_t>((R + 15) / 16, std::max(1, 8 * sm_count() / A)), (unsigned)A);
-        if (f16) AVD_CUDA_OK(launch_pdl(actor_dm_kernel<true>, grid, dim3(256), 0, st, (const float*)w.dpi, (const float*)w.dact, (const uint32_t*)w.mask2, DZ, w.sdq + A, R, dm_a));
-        else AVD_CUDA_OK(launch_pdl(actor_dm_kernel<false>, grid, dim3(256), 0, st, (const float*)w.dpi, (const float*)w.dact, (const uint32_t*)w.mask2, DZ, w.sdq + A, R, dm_a));
+        if (f16) AVD_CUDA_OK(launch_pdl(actor_dm_kernel<true>, grid, dim3(256), 0, sd, (const float*)w.dpi, (const float*)w.dact, (const uint32_t*)w.mask2, w.DZa, w.sdq + A, R, dm_a));
+        else AVD_CUDA_OK(launch_pdl(actor_dm_kernel<false>, grid, dim3(256), 0, sd, (const float*)w.dpi, (const float*)w.dact, (const uint32_t*)w.mask2, w.DZa, w.sdq + A, R, dm_a));
         AVD_LAUNCH_OK();
+        if (side) AVD_CUDA_OK(cudaEventRecord(side->join, side->s));
     }
     tm.mark("actor_bwd");
-    if (side) AVD_CUDA_OK(cudaStreamWaitEvent(st, side->join, 0));      // the critic's unfold has read G1 / G2part
-    AVD_TRY(p.dgrad3_only(DZ, w.aW2b, d.l1, Fp, w.mask, 8, w.xextT, w.G1, w.dbm + (int64_t)A * d.l2));
+    // ---- critic loss gradient on (s, a)                                             trainer.py:495-498
+    AVD_TRY(fused3::run(fused3::MODE_CRITIC_BWD, f16, d, A, R, io->critic, co.total, w.cW2T, w.c_b2f, nullptr, io->s, srs, 1, io->a, nullptr, 0.f, 0.f,
+                        w.y, nullptr, w.q, w.mask, DZ, dm_c, w.sdq, io->loss, st));
+    tm.mark("critic_bwd");
+    // dgrad first, wgrad second: the unfold kernel then finds the 23 MB of partial G2 slices the weight-gradient CTAs have just written
+    // still in L2 (after a dgrad pass, which streams 340 MB, it read them back from HBM)
+    AVD_TRY(p.dgrad3_only(DZ, w.cW2b, F, Fp, w.mask, MW, w.xextT, w.G1, w.dbm));
+    tm.mark("critic_dgrad");
+    AVD_TRY(wgrad3::run(f16, d, true, A, R, io->critic, co.total, io->s, srs, io->a, DZ, w.G2part, g2_agent, g2_cta, st));
+    tm.mark("critic_wgrad");
+    if (side) {        // branch B: the critic's unfold beside the actor's dgrad
+        AVD_CUDA_OK(cudaEventRecord(side->fork2, st));
+        AVD_CUDA_OK(cudaStreamWaitEvent(side->s, side->fork2, 0));
+        Pass ps = p;
+        ps.st = side->s;
+        AVD_TRY(ps.unfold(true, io->critic, F, Fp, w.G1, w.G2part, io->critic_grad, w.dbm, w.c_b2f, Uc, w.sdq, w.ticket, ws_c, dm_c));
+        AVD_CUDA_OK(cudaEventRecord(side->join2, side->s));
+    } else {
+        AVD_TRY(p.unfold(true, io->critic, F, Fp, w.G1, w.G2part, io->critic_grad, w.dbm, w.c_b2f, Uc, w.sdq, w.ticket, ws_c, dm_c));
+    }
+    tm.mark("critic_unfold");
+    // ---- actor loss gradient, second half
+    if (side && !legacy_actor_bwd) AVD_CUDA_OK(cudaStreamWaitEvent(st, side->join, 0));      // join A: the actor's backward tile is complete
+    AVD_TRY(p.dgrad3_only(w.DZa, w.aW2b, d.l1, Fp, w.mask_a, 8, w.xextT, w.G1a, dbm_a));
     tm.mark("actor_dgrad");
-    AVD_TRY(wgrad3::run(f16, d, false, A, R, io->actor, ao.total, io->s, srs, nullptr, DZ, w.G2part, g2_agent, g2_cta, st));
+    AVD_TRY(wgrad3::run(f16, d, false, A, R, io->actor, ao.total, io->s, srs, nullptr, w.DZa, w.G2part_a, g2_agent, g2_cta, st));
     tm.mark("actor_wgrad");
-    AVD_TRY(p.unfold(false, io->actor, d.l1, Fp, w.G1, w.G2part, io->actor_grad, w.dbm + (int64_t)A * d.l2, w.a_b2f, Ua, w.sdq + A, w.ticket + A, ws_a, dm_a));
+    AVD_TRY(p.unfold(false, io->actor, d.l1, Fp, w.G1a, w.G2part_a, io->actor_grad, dbm_a, w.a_b2f, Ua, w.sdq + A, w.ticket + A, ws_a, dm_a));
     tm.mark("actor_unfold");
+    if (side) AVD_CUDA_OK(cudaStreamWaitEvent(st, side->join2, 0));      // join B: the critic's gradients are complete
     const int rc = apply_local_updates(io, (void*)st);
     tm.mark("adam+polyak");
     return rc;
