@@ -934,7 +934,7 @@ __device__ __forceinline__ void critic_vtab_body(const float* __restrict__ param
 struct PrepArgs {
     FoldJobs jobs;
     int A, l2, f16;
-    unsigned fold_gx, fold_gy, n_fold, n_vtab, vtab_gy;
+    unsigned fold_gx, fold_gy, n_fold, n_vtab, vtab_gy, fold_z0;
     const float* critic; int64_t cstride; CriticOff co; avd_net_dims d; float* vtab; int v_rows, v_stride, v_total;
     const float* s; int64_t s_rs; const float* a; int64_t N; bf16* xextT; int64_t R, Rp;
 };
@@ -945,7 +945,7 @@ __global__ void __launch_bounds__(256) learn_prep_kernel(const __grid_constant__
         critic_vtab_body(p.critic, p.cstride, p.co, p.d, p.vtab, p.v_rows, p.v_stride, p.v_total, (int)(b / p.vtab_gy), (int)(b % p.vtab_gy));
     } else if (b < p.n_vtab + p.n_fold) {
         const unsigned f = b - p.n_vtab;
-        pack_fold4_body(p.jobs, p.A, p.l2, p.f16, (int)(f % p.fold_gx), (int)((f / p.fold_gx) % p.fold_gy), (int)(f / (p.fold_gx * p.fold_gy)));
+        pack_fold4_body(p.jobs, p.A, p.l2, p.f16, (int)(f % p.fold_gx), (int)((f / p.fold_gx) % p.fold_gy), (int)(f / (p.fold_gx * p.fold_gy) + p.fold_z0));
     } else {
         xext_body(p.s, p.s_rs, p.a, p.d.ns, p.N, p.xextT, p.R, p.Rp, p.f16, (int64_t)(b - p.n_vtab - p.n_fold));
     }
@@ -964,17 +964,34 @@ __global__ void __launch_bounds__(256) actor_dm_kernel(const float* __restrict__
     const int agent = blockIdx.y;
     const int seg = threadIdx.x & 15;
     float acc = 0.0f;
-    for (int64_t r = (int64_t)blockIdx.x * 16 + (threadIdx.x >> 4); r < R; r += (int64_t)gridDim.x * 16) {
-        const int64_t n = (int64_t)agent * R + r;
-        const float dq = __ldg(dpi + n) * __ldg(dact + n);
-        if (seg == 0) acc += dq;
-        const uint32_t bits = __ldg(mask2 + n * 4 + (seg >> 2)) << ((seg & 3) * 8);      // column 8 seg + k at bit 31 - k
-        const float dqs = dq * dm_scale;
-        uint32_t pk[4];
+    // Four rows per thread and iteration, all twelve loads issued before the first store.  Stand-alone (8 CTAs per SM) this is slower than
+    // one row per iteration; beside a persistent tensor-core CTA, where only one or two of these CTAs fit on an SM, the loads in
+    // flight per thread are what keeps the HBM write stream going.
+    constexpr int UNR = 4;
+    const int64_t stride = (int64_t)gridDim.x * 16;
+    for (int64_t r0 = (int64_t)blockIdx.x * 16 + (threadIdx.x >> 4); r0 < R; r0 += stride * UNR) {
+        float dq[UNR];
+        uint32_t bits[UNR];
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-            pk[k] = umma::pack_x2<F16>((bits & (0x80000000u >> (2 * k))) ? 0.0f : dqs, (bits & (0x80000000u >> (2 * k + 1))) ? 0.0f : dqs);
-        *reinterpret_cast<uint4*>(DZ + n * 128 + seg * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        for (int u = 0; u < UNR; ++u) {
+            const int64_t r = r0 + u * stride;
+            const int64_t n = (int64_t)agent * R + (r < R ? r : R - 1);
+            dq[u] = __ldg(dpi + n) * __ldg(dact + n);
+            bits[u] = __ldg(mask2 + n * 4 + (seg >> 2)) << ((seg & 3) * 8);      // column 8 seg + k at bit 31 - k
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const int64_t r = r0 + u * stride;
+            if (r < R) {
+                if (seg == 0) acc += dq[u];
+                const float dqs = dq[u] * dm_scale;
+                uint32_t pk[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    pk[k] = umma::pack_x2<F16>((bits[u] & (0x80000000u >> (2 * k))) ? 0.0f : dqs, (bits[u] & (0x80000000u >> (2 * k + 1))) ? 0.0f : dqs);
+                *reinterpret_cast<uint4*>(DZ + ((int64_t)agent * R + r) * 128 + seg * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+        }
     }
     __shared__ float red[8];
     acc = warp_sum(acc);
@@ -1668,7 +1685,7 @@ struct StageTimer {
 
 // The preparation launch of the tensor-core learn step: weight half (V table, BN-folded 16-bit packs + folded biases of the four
 // networks; needs the b2f accumulators zeroed) and / or batch half (hi/lo-split [x_hi | 1 | x_lo] operand of the dgrad kernels).
-static int learn_prep(const avd_learn_io* io, const Pass& p, const Workspace& w, bool weights, bool batch, cudaStream_t st) {
+static int learn_prep(const avd_learn_io* io, const Pass& p, const Workspace& w, int job_lo, int job_hi, bool vtab, bool batch, cudaStream_t st) {
     const avd_net_dims d = io->dims;
     const int A = io->A;
     const int64_t R = io->rows_per_agent, N = (int64_t)A * R;
@@ -1684,8 +1701,10 @@ static int learn_prep(const avd_learn_io* io, const Pass& p, const Workspace& w,
     int Fmax = 0;
     AVD_TRY(p.pack_fold4(pa.jobs, Fmax, 4, prm, crit, W2b, W2T, b2f, wsc));
     pa.A = A; pa.l2 = d.l2; pa.f16 = p.f16() ? 1 : 0;
-    pa.fold_gx = (unsigned)((d.l2 + 31) / 32); pa.fold_gy = (unsigned)((Fmax + 7) / 8); pa.n_fold = weights ? pa.fold_gx * pa.fold_gy * (unsigned)(4 * A) : 0u;
-    pa.vtab_gy = (unsigned)((d.l2 + 31) / 32); pa.n_vtab = weights ? (unsigned)A * pa.vtab_gy : 0u;
+    // fold jobs [job_lo, job_hi) of {target actor, target critic, critic, actor}: z index of the fold grid = job * A + agent
+    pa.fold_gx = (unsigned)((d.l2 + 31) / 32); pa.fold_gy = (unsigned)((Fmax + 7) / 8); pa.n_fold = pa.fold_gx * pa.fold_gy * (unsigned)((job_hi - job_lo) * A);
+    pa.fold_z0 = (unsigned)(job_lo * A);
+    pa.vtab_gy = (unsigned)((d.l2 + 31) / 32); pa.n_vtab = vtab ? (unsigned)A * pa.vtab_gy : 0u;
     pa.critic = io->critic; pa.cstride = co.total; pa.co = co; pa.d = d; pa.vtab = w.vtab;
     pa.v_rows = fused3::vtab_rows(); pa.v_stride = fused3::vtab_stride(); pa.v_total = fused3::vtab_floats();
     pa.s = io->s; pa.s_rs = srs; pa.a = io->a; pa.N = N; pa.xextT = w.xextT; pa.R = R; pa.Rp = (R + 63) / 64 * 64;
@@ -1702,7 +1721,7 @@ static int learn_prep(const avd_learn_io* io, const Pass& p, const Workspace& w,
 // events, so a CUDA-graph capture of the caller's stream records the branch.
 struct SideStream {
     cudaStream_t s = nullptr;
-    cudaEvent_t fork = nullptr, join = nullptr, fork2 = nullptr, join2 = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr, fork2 = nullptr, join2 = nullptr, fork0 = nullptr, join0 = nullptr;
 };
 static SideStream* side_stream() {
     static SideStream tab[64];
@@ -1714,7 +1733,8 @@ static SideStream* side_stream() {
         (void)cs;
         if (cudaStreamCreateWithFlags(&x.s, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&x.fork, cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&x.join, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&x.fork2, cudaEventDisableTiming) != cudaSuccess ||
-            cudaEventCreateWithFlags(&x.join2, cudaEventDisableTiming) != cudaSuccess) {
+            cudaEventCreateWithFlags(&x.join2, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&x.fork0, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&x.join0, cudaEventDisableTiming) != cudaSuccess) {
             x.s = nullptr;
             return nullptr;
         }
@@ -1744,7 +1764,9 @@ static int learn_fused3(const avd_learn_io* io, const Pass& p, const Workspace& 
     // memset zeroes every accumulator of the step.  (Running the weight half of the preparation on a side stream beside the
     // environment step and the replay gather was measured: -15 us per step with eager launches, nothing under CUDA-graph replay.)
     AVD_CUDA_OK(cudaMemsetAsync(w.c_b2f, 0, (size_t)((char*)(w.sdq + 2 * A) - (char*)w.c_b2f), st));
-    AVD_TRY(learn_prep(io, p, w, true, true, st));
+    // (only the target actor's pack is needed at once; running the rest of the preparation on the side stream beside the first pass was
+    // measured: +9 us -- the 2400 small CTAs of the fold job get in the way of the persistent pass instead of hiding behind it)
+    AVD_TRY(learn_prep(io, p, w, 0, 4, true, true, st));
     // fp16 backward tiles: dq ~ (q - y) / R (critic) and ~ dq/da / R (actor) are lifted by powers of two into the normal range of
     // fp16 (they saturate at +-65504 * 2^-k instead of overflowing); the unfold kernel divides the factors out again
     const float dm_c = f16 ? exp2f(ceilf(log2f((float)R))) : 1.0f, dm_a = f16 ? 256.0f * dm_c : 1.0f;
