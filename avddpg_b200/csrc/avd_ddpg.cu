@@ -1354,12 +1354,6 @@ struct Pass {
 
     // fused dgrad + layer-1 weight gradient (avd_dgrad3.cu), then unfold.  G2part holds the partial G2 slices the wgrad kernel
     // (avd_wgrad3.cu) stored before: [A][ncta][384][l2].
-    int dgrad3_unfold(bool critic, const float* params, const bf16* DZ, const bf16* W2b, int F, int Fp, const uint32_t* mask, int mask_words,
-                      const bf16* xextT, float* G1, const float* G2part, float* grads, float* dbm, const float* b2f, float* U,
-                      const float* sdq, int* ticket, const float* wscale, float dm_scale) const {
-        if (int rc = dgrad3::run(f16(), A, R, F, DZ, W2b, mask, mask_words, xextT, (R + 63) / 64 * 64, G1, Fp, dbm, d.l2, st)) return rc;
-        return unfold(critic, params, F, Fp, G1, G2part, grads, dbm, b2f, U, sdq, ticket, wscale, dm_scale);
-    }
     int dgrad3_only(const bf16* DZ, const bf16* W2b, int F, int Fp, const uint32_t* mask, int mask_words, const bf16* xextT, float* G1, float* dbm) const {
         return dgrad3::run(f16(), A, R, F, DZ, W2b, mask, mask_words, xextT, (R + 63) / 64 * 64, G1, Fp, dbm, d.l2, st);
     }

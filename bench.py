@@ -98,7 +98,7 @@ class ClockSampler:
                     self.rows.append([c.strip() for c in out.split(",")])
             except Exception:
                 pass
-            self._stop.wait(0.05)
+            self._stop.wait(float(os.environ.get("AVD_CLOCK_PERIOD", "0.05")))
 
     def __enter__(self):
         self._t = threading.Thread(target=self._run, daemon=True)
