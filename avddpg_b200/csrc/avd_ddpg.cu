@@ -1717,14 +1717,15 @@ struct SideStream {
     cudaStream_t s = nullptr;
     cudaEvent_t fork = nullptr, join = nullptr, fork2 = nullptr, join2 = nullptr, fork0 = nullptr, join0 = nullptr;
 };
-static SideStream* side_stream() {
+static SideStream* side_stream(cudaStream_t caller) {
     static SideStream tab[64];
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
     SideStream& x = tab[dev];
     if (!x.s) {
+        // never create the stream / events while the caller's stream is being captured (a first call inside a capture runs unbranched)
         cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-        (void)cs;
+        if (cudaStreamIsCapturing(caller, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return nullptr;
         if (cudaStreamCreateWithFlags(&x.s, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&x.fork, cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&x.join, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&x.fork2, cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&x.join2, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&x.fork0, cudaEventDisableTiming) != cudaSuccess ||
@@ -1739,7 +1740,7 @@ static SideStream* side_stream() {
 static int learn_fused3(const avd_learn_io* io, const Pass& p, const Workspace& w, cudaStream_t st) {
     StageTimer tm(st);
     static const bool no_side = getenv("AVD_NO_SIDE_STREAM") != nullptr || getenv("AVD_STAGE_TIMES") != nullptr;
-    SideStream* side = no_side ? nullptr : side_stream();
+    SideStream* side = no_side ? nullptr : side_stream(st);
     const avd_net_dims d = io->dims;
     const int A = io->A;
     const int64_t R = io->rows_per_agent, N = (int64_t)A * R;
