@@ -60,6 +60,41 @@ __global__ void __launch_bounds__(256) replay_gather_kernel(const float* __restr
     }
 }
 
+// index draw + gather fused: thread t owns Philox block jb of ring `ring` (four samples).  All four records (20 x 8 bytes) are requested
+// before the first use, so a thread overlaps four TLB / DRAM latencies instead of one; outputs are 16-byte stores.
+__global__ void __launch_bounds__(256) replay_sample_kernel(const float* __restrict__ ring, int64_t n_rings, int64_t ring_id_base, int32_t batch,
+                                                            int64_t capacity, uint64_t seed, const avd_clock* __restrict__ clock,
+                                                            int64_t* __restrict__ idx_out, float* __restrict__ s, float* __restrict__ a,
+                                                            float* __restrict__ r, float* __restrict__ s2) {
+    const uint64_t count = clock->ring_count;
+    const uint64_t range = count < (uint64_t)capacity ? count : (uint64_t)capacity;   // replaybuffer.py:52
+    const uint32_t tick = (uint32_t)clock->update_tick;
+    const int64_t blocks_per_ring = batch / 4;
+    const int64_t total = n_rings * blocks_per_ring;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t rg = t / blocks_per_ring, jb = t - rg * blocks_per_ring;
+        const uint64_t id = (uint64_t)(ring_id_base + rg) * (uint64_t)blocks_per_ring + (uint64_t)jb;
+        const uint4 w = rng_words(seed, id, tick, AVD_RNG_REPLAY);
+        const int64_t ix[4] = {index_from_word(w.x, range), index_from_word(w.y, range), index_from_word(w.z, range), index_from_word(w.w, range)};
+        const int64_t n0 = rg * batch + jb * 4;
+        if (idx_out) *reinterpret_cast<longlong4*>(idx_out + n0) = make_longlong4(ix[0], ix[1], ix[2], ix[3]);
+        float2 q[4][5];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float2* rec = reinterpret_cast<const float2*>(ring + (ix[u] * n_rings + rg) * AVD_RING_RECORD_FLOATS);
+#pragma unroll
+            for (int k = 0; k < 5; ++k) q[u][k] = __ldg(rec + k);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            reinterpret_cast<float4*>(s)[n0 + u] = make_float4(q[u][0].x, q[u][0].y, q[u][1].x, q[u][1].y);
+            reinterpret_cast<float4*>(s2)[n0 + u] = make_float4(q[u][3].x, q[u][3].y, q[u][4].x, q[u][4].y);
+        }
+        *reinterpret_cast<float4*>(a + n0) = make_float4(q[0][2].x, q[1][2].x, q[2][2].x, q[3][2].x);
+        *reinterpret_cast<float4*>(r + n0) = make_float4(q[0][2].y, q[1][2].y, q[2][2].y, q[3][2].y);
+    }
+}
+
 __global__ void __launch_bounds__(256) replay_fill_kernel(float* __restrict__ ring, int64_t n_records, uint64_t seed) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_records; i += (int64_t)gridDim.x * blockDim.x) {
         const uint4 w0 = rng_words(seed, (uint64_t)i, 0u, 0x7F);
@@ -124,6 +159,20 @@ extern "C" int avd_replay_gather(const float* ring, int64_t capacity, int64_t M,
     AVD_REQUIRE(capacity > 0 && M > 0 && P >= 0 && batch > 0, "bad sizes");
     if (P == 0) return AVD_OK;
     replay_gather_kernel<<<grid_for(M * P * batch), 256, 0, (cudaStream_t)stream>>>(ring, M * P, idx, batch, s, a, r, s2);
+    AVD_LAUNCH_OK();
+    return AVD_OK;
+}
+
+extern "C" int avd_replay_sample(const float* ring, int64_t capacity, int64_t M, int64_t P, int64_t ring_id_base, int32_t batch, uint64_t seed,
+                                 const avd_clock* clock, int64_t* idx_out, float* s, float* a, float* r, float* s2, void* stream) {
+    AVD_REQUIRE(ring && clock && s && a && r && s2, "null buffer");
+    AVD_REQUIRE(batch > 0 && batch % 4 == 0, "batch must be a positive multiple of 4 (got %d)", batch);
+    AVD_REQUIRE(capacity > 0 && M > 0 && P >= 0, "bad sizes");
+    AVD_REQUIRE(((uintptr_t)a & 15) == 0 && ((uintptr_t)r & 15) == 0 && ((uintptr_t)s & 15) == 0 && ((uintptr_t)s2 & 15) == 0 &&
+                (!idx_out || ((uintptr_t)idx_out & 31) == 0), "sample outputs must be 16-byte (indices: 32-byte) aligned");
+    if (P == 0) return AVD_OK;
+    replay_sample_kernel<<<grid_for(M * P * (batch / 4)), 256, 0, (cudaStream_t)stream>>>(ring, M * P, ring_id_base, batch, capacity, seed, clock, idx_out, s, a,
+                                                                                        r, s2);
     AVD_LAUNCH_OK();
     return AVD_OK;
 }

@@ -69,12 +69,16 @@ class ReplayRings:
                                               _lib.ptr(self.s2), _lib.current_stream()))
         return self.s, self.a, self.r, self.s2
 
-    def sample(self, advance_clock=True):
-        self.sample_indices()
-        out = self.gather()
+    def sample(self, advance_clock=True, keep_indices=False):
+        """ReplayBuffer.sample for every ring in one launch (avd_replay_sample: index draw + gathers fused, identical to
+        sample_indices() + gather()); keep_indices also writes the draws to self.idx."""
+        self._alloc_sample_buffers()
+        _lib.check(self.lib.avd_replay_sample(_lib.ptr(self.data), self.capacity, self.M, self.P, self.ring_id_base, self.batch_size, self.seed,
+                                              self.clock.ptr, _lib.ptr(self.idx) if keep_indices else None, _lib.ptr(self.s), _lib.ptr(self.a),
+                                              _lib.ptr(self.r), _lib.ptr(self.s2), _lib.current_stream()))
         if advance_clock:
             self.clock.advance(update=1)
-        return out
+        return self.s, self.a, self.r, self.s2
 
 
 class ReplayBuffer:

@@ -189,6 +189,14 @@ int avd_replay_sample_indices(int64_t* idx_out, int64_t n_rings, int64_t ring_id
 int avd_replay_gather(const float* ring, int64_t capacity, int64_t M, int64_t P, const int64_t* idx,
                       int32_t batch, float* s, float* a, float* r, float* s2, void* stream);
 
+/* ReplayBuffer.sample in ONE launch (replaybuffer.py:52-61): the index draw of avd_replay_sample_indices and the gathers of
+ * avd_replay_gather, identical results.  A thread owns one Philox block = four samples of a ring and has their twenty 8-byte loads in
+ * flight at once (random 40-byte records out of a ring that can span tens of GB: the gather is latency / TLB bound), and the indices
+ * need not travel through HBM.  idx_out: nullable int64 [n_rings][batch] (written when the caller wants the draws).                  */
+int avd_replay_sample(const float* ring, int64_t capacity, int64_t M, int64_t P, int64_t ring_id_base, int32_t batch, uint64_t seed,
+                      const avd_clock* clock, int64_t* idx_out, float* s, float* a, float* r, float* s2, void* stream);
+
+
 /* Fill the whole ring with synthetic transitions (benchmark warm start: steady-state sampling
  * range without running `capacity` env steps).                                                    */
 int avd_replay_fill_synthetic(float* ring, int64_t capacity, int64_t M, int64_t P, uint64_t seed, void* stream);

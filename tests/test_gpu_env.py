@@ -276,6 +276,14 @@ def test_fused_replay_write_sample_gather(mods):
         pick = flat[idx, np.arange(M * P)[:, None]]   # [rings, batch, 10]
         assert np.array_equal(s, pick[..., 0:4].reshape(-1, 4)) and np.array_equal(a, pick[..., 4].reshape(-1))
         assert np.array_equal(r, pick[..., 5].reshape(-1)) and np.array_equal(s2, pick[..., 6:10].reshape(-1, 4))
+        # the one-launch form (avd_replay_sample: draw + gathers fused) returns the same draws and the same rows
+        rings.idx.zero_()
+        fs, fa, fr, fs2 = (t.cpu().numpy().copy() for t in rings.sample(advance_clock=False, keep_indices=True))
+        assert np.array_equal(rings.idx.cpu().numpy(), ref)
+        assert np.array_equal(fs, s) and np.array_equal(fa, a) and np.array_equal(fr, r) and np.array_equal(fs2, s2)
+        rings.idx.fill_(-1)
+        gs = rings.sample(advance_clock=False)[0].cpu().numpy()
+        assert np.array_equal(gs, s) and (rings.idx == -1).all()        # without keep_indices the draws stay on chip
         rings.clock.advance(update=1)
 
 
