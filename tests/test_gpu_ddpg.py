@@ -519,7 +519,7 @@ def _fp16_errors(mods, A, R, seeds):
     return np.array(rel), np.array(cond), names
 
 
-@pytest.mark.parametrize("A,R", [(1, 64), (3, 64), (200, 64), (2, 1000), (1, 4096), (1, 16384), (1, 250_000), (3, 100_003)])
+@pytest.mark.parametrize("A,R", [(1, 64), (3, 64), (200, 64), (2, 1000), (8, 1000), (1, 4096), (1, 16384), (1, 250_000), (3, 100_003)])
 def test_learn_gradients_fp16_mode(mods, A, R):
     """precision = 2, the bench default: the layer-2 products, the backward tile and the dgrad run on tcgen05 with fp16 operands
     (11-bit significand, power-of-two operand scales), layer 1 with hi/lo-split bf16, fp32 accumulation in TMEM, heads / losses /
